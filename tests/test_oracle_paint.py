@@ -1,0 +1,241 @@
+"""Oracle (CPU restatement of libmypaint + envs/mnist.py) against the known answers that are
+derivable from the reference source alone.  PARITY UNPINNED w.r.t. the real
+libmypaint/mypaint binaries: the reference has no tests/fixtures and cannot run here."""
+import ctypes
+import math
+import os
+
+import numpy as np
+import pytest
+
+from oracle import paint_oracle as po
+
+REF = "/root/reference"
+
+
+def _spec(names=("jump", "control", "end"), **kw):
+    return po.EnvSpec(action_names=list(names), **kw)
+
+
+def test_py2_dict_order_matches_survey():
+    # envs/base.py:32 -- acs = list(action_sizes.keys()) under CPython 2.7
+    assert po.py2_dict_order(["jump", "control", "end"]) == ["jump", "control", "end"]
+    assert po.py2_dict_order(["pressure", "jump", "size", "control", "end"]) == \
+        ["jump", "pressure", "control", "end", "size"]
+    assert po.py2_dict_order(["color", "shape"]) == ["color", "shape"]
+
+
+@pytest.mark.skipif(not os.path.exists(REF), reason="reference tree not mounted")
+def test_brush_table_equals_reference_brush_file():
+    ref = open(os.path.join(REF, "assets/brushes/dry_brush.myb")).read()
+    assert po.parse_myb(ref) == po.parse_myb(po.brush_to_myb())
+
+
+def test_glibc_rand_stream_matches_libc():
+    libc = ctypes.CDLL("libc.so.6")
+    libc.srand(1)
+    want = [libc.rand() for _ in range(5000)]
+    got = np.zeros(5000, np.int32)
+    po.lib().po_glibc_rand_stream(1, 5000, got.ctypes.data)
+    assert got.tolist() == want
+    t = po.dither_table()
+    assert t.min() >= 1024 and t.max() <= 1024 + 30720
+
+
+def test_uniform_locations_known_answer():
+    # envs/utils.py:12-14: index k -> (lin[k % L], lin[k // L]); last coordinate is 64.0
+    env = po.LiteralMNISTEnv(_spec())
+    lin = np.linspace(0, 64, 32)
+    for k in (0, 1, 31, 32, 629, 1023):
+        assert tuple(env.ends[k]) == (lin[k % 32], lin[k // 32])
+    assert env.ends[-1][0] == 64.0 and env.ends[-1][1] == 64.0
+
+
+def test_rng_is_lagged_fibonacci_and_restarts():
+    L = po.lib()
+    b1, b2 = L.po_brush_new(0), L.po_brush_new(1)
+    a = [L.po_brush_rng_next(b1) for _ in range(200)]
+    b = [L.po_brush_rng_next(b2) for _ in range(200)]
+    assert a == b                              # seed 1000 per Brush -> identical stream
+    assert all(0.0 <= v < 1.0 for v in a)
+    assert len(set(a)) == 200
+    # x[n] = (x[n-10] + x[n-7]) mod 1 holds inside each block of 10 outputs' generating run:
+    # block k+1's first 3 values are determined by block k through 19 recurrence steps
+    u = np.array(a[:10])
+    ext = list(u)
+    for j in range(10, 29):
+        s = ext[j - 10] + ext[j - 7]
+        ext.append(s - int(s))
+    # after a 19-long fill the new ran_u is ext[19:29]; the next block returns it
+    assert a[10:20] == ext[19:29]
+
+
+def test_blend_known_answers():
+    # white under black at opa_a gives 32768 - opa_a; alpha stays 32768
+    L = po.lib()
+    s = L.po_surface_new()
+    L.po_surface_fill_white(s)
+    b = L.po_brush_new(1)
+    names = po.setting_names()
+    # constant brush: opaque 1, hardness 1 (mask == 1 inside), radius e^1.5 = 4.48 (non-AA path)
+    for n, v in (("opaque", 1.0), ("opaque_multiply", 1.0), ("hardness", 1.0),
+                 ("radius_logarithmic", 1.5), ("dabs_per_actual_radius", 2.0), ("anti_aliasing", 0.0)):
+        L.po_brush_set_base_value(b, names.index(n), v)
+    L.po_brush_stroke_to(b, s, 32.0, 32.0, 1.0, 0, 0, 0.1)      # reset event
+    L.po_brush_stroke_to(b, s, 32.5, 32.0, 1.0, 0, 0, 0.1)      # settings_value[] still zero: no dabs
+    assert (np.ctypeslib.as_array(L.po_surface_data(s), shape=(64, 64, 4)) == 32768).all()
+    L.po_brush_stroke_to(b, s, 40.0, 32.0, 1.0, 0, 0, 0.1)
+    px = np.ctypeslib.as_array(L.po_surface_data(s), shape=(64, 64, 4))
+    assert (px[..., 3] == 32768).all()
+    assert px[32, 36, 0] == 0 and px[0, 0, 0] == 32768          # fully covered / untouched
+    assert (px[..., 0] == px[..., 1]).all() and (px[..., 1] == px[..., 2]).all()
+    L.po_surface_free(s)
+    L.po_brush_free(b)
+
+
+def test_readback_known_answers():
+    # 32768 -> 255 and 0 -> 0 for ANY dither value; round-half differs <= 1 LSB
+    L = po.lib()
+    s = L.po_surface_new()
+    L.po_surface_fill_white(s)
+    out = np.zeros((64, 64, 4), np.uint8)
+    L.po_surface_read_rgbu8(s, po.dither_table().ctypes.data, out.ctypes.data)
+    assert (out == 255).all()
+    px = np.ctypeslib.as_array(L.po_surface_data(s), shape=(64, 64, 4))
+    rng = np.random.RandomState(0)
+    px[..., :3] = rng.randint(0, 32769, size=(64, 64, 1))
+    a = np.zeros((64, 64, 4), np.uint8)
+    b = np.zeros((64, 64, 4), np.uint8)
+    L.po_surface_read_rgbu8(s, po.dither_table().ctypes.data, a.ctypes.data)
+    L.po_surface_read_rgbu8(s, None, b.ctypes.data)
+    assert np.abs(a.astype(int) - b.astype(int)).max() <= 1
+    want = (px[..., 0].astype(np.uint32) * 255 + po.dither_table().reshape(64, 64)) >> 15
+    assert (a[..., 0] == want).all()
+    L.po_surface_free(s)
+
+
+def test_first_step_and_jump_leave_canvas_bit_identical():
+    # step 0 only moves the pen; a jump step paints nothing (mnist.py:137-144)
+    env = po.OracleBatchEnv(_spec(), 4)
+    env.reset()
+    rng = np.random.RandomState(1)
+    a = np.stack([rng.randint(0, 2, 4), rng.randint(0, 1024, 4), rng.randint(0, 1024, 4)], 1)
+    o = env.step(a)
+    assert (o == 255.0).all() and (env.canvas() == 32768).all()
+    a[:, 0] = 0
+    env.step(a)
+    before = env.canvas()
+    assert (before[..., 0] < 32768).any()
+    a = np.stack([np.ones(4, int), rng.randint(0, 1024, 4), rng.randint(0, 1024, 4)], 1)
+    env.step(a)
+    assert (env.canvas() == before).all()
+
+
+def test_event_schedule_known_answers():
+    # SURVEY 8c(2,3): 102 events per curved stroke; p(25) = p2, p(100) = p3; Bezier hits the control
+    env = po.OracleBatchEnv(_spec(), 1)
+    env.reset()
+    env.enable_logs()
+    env.step(np.array([[0, 5, 40]]))
+    ev = env.pop_events(0)
+    assert len(ev) == 2 and ev[0] == (0.0, 0.0, 0.0, 0.1) and ev[1][3] == 1.0
+    ctrl, end = 7 * 32 + 20, 25 * 32 + 3
+    env.step(np.array([[0, ctrl, end]]))
+    ev = env.pop_events(0)
+    assert len(ev) == 102
+    assert all(e[3] == 0.1 for e in ev)
+    lin = np.linspace(0, 64, 32)
+    # pre-positioning event at the previous end point with the step's pressure (0.3)
+    assert ev[0][:3] == (np.float32(lin[40 % 32]), np.float32(lin[40 // 32]), np.float32(0.3))
+    # entry pressure after step 0 is 0 -> p1 = 0, p2 = 0.15, p3 = 0.3
+    assert ev[1][2] == np.float32(0.0)
+    assert ev[1 + 25][2] == np.float32(0.15)          # i = 25
+    assert ev[1 + 50][2] == np.float32(0.15)          # middle
+    assert ev[1 + 100][2] == np.float32(0.3)          # i = 100
+    # P(0.5) == selected control location (c' = m + 2 (c - m))
+    cx, cy = lin[ctrl % 32], lin[ctrl // 32]
+    assert abs(ev[1 + 50][0] - cx) < 1e-4 and abs(ev[1 + 50][1] - cy) < 1e-4
+    # last event lands on the end location
+    assert ev[-1][0] == np.float32(lin[end % 32]) and ev[-1][1] == np.float32(lin[end // 32])
+
+
+@pytest.mark.parametrize("names,mode", [
+    (("jump", "control", "end"), po.PO_MATH_DET),
+    (("jump", "control", "end"), po.PO_MATH_LIBM),
+    (("jump", "pressure", "control", "end", "size"), po.PO_MATH_DET),
+    (("end",), po.PO_MATH_DET),                                   # --jump=False --curve=False
+    (("control", "end", "color", "jump", "pressure", "size"), po.PO_MATH_DET),
+])
+def test_c_env_equals_literal_python_env(names, mode):
+    spec = _spec(names, math_mode=mode, n_color=8)
+    sizes = {"jump": 2, "pressure": 2, "size": 2, "color": 8, "control": 1024, "end": 1024}
+    rng = np.random.RandomState(7)
+    T = 5
+    lit = po.LiteralMNISTEnv(spec)
+    cenv = po.OracleBatchEnv(spec, 1)
+    for ep in range(2):
+        lit.reset()
+        cenv.reset()
+        for t in range(T):
+            a = [int(rng.randint(sizes[n])) for n in names]
+            lit.step(a)
+            cenv.step(np.array([a]))
+            assert (lit.canvas() == cenv.canvas()[0]).all()
+        st = lit.state(po.dither_table())
+        # np.dot may fuse multiply-adds (BLAS): equal after the float32 cast the reference's
+        # trajectory queue applies (main.py:42-62), <= 1 ulp of double before it
+        assert (st.astype(np.float32) == cenv.state()[0].astype(np.float32)).all()
+        assert np.abs(st - cenv.state()[0]).max() < 1e-12
+
+
+def test_det_and_libm_modes_agree_within_tolerance():
+    # the deterministic-math oracle stays within the north-star tolerance of the libm one
+    names = ("jump", "control", "end")
+    B, T = 24, 5
+    rng = np.random.RandomState(3)
+    acts = np.stack([rng.randint(0, 2, (B, T)), rng.randint(0, 1024, (B, T)),
+                     rng.randint(0, 1024, (B, T))], -1)
+    res = []
+    for mode in (po.PO_MATH_DET, po.PO_MATH_LIBM):
+        env = po.OracleBatchEnv(_spec(names, math_mode=mode), B)
+        res.append(env.run_episodes(acts, want_obs=True))
+    (ca, oa), (cb, ob) = res
+    identical = (ca == cb).all(axis=(1, 2, 3))
+    assert identical.mean() >= 0.9          # almost always bit-identical
+    err = np.abs(oa[:, -1] - ob[:, -1]) / 255.0
+    assert np.median(err.reshape(B, -1).max(1)) <= 1.0 / 255 + 1e-9
+
+
+def test_det_math_accuracy():
+    L = po.lib()
+    rng = np.random.RandomState(0)
+    xs = np.concatenate([rng.uniform(-60, 10, 4000), rng.uniform(-2, 2, 4000)]).astype(np.float32)
+    bad = 0
+    for x in xs:
+        d = L.po_det_exp(float(x))
+        assert abs(d - math.exp(float(x))) <= 2e-15 * math.exp(float(x))
+        bad += np.float32(d) != np.float32(math.exp(float(x)))
+    assert bad <= 1
+    for x in np.concatenate([rng.uniform(50, 200, 3000), rng.uniform(1e-3, 10, 3000)]).astype(np.float32):
+        d = L.po_det_log(float(x))
+        assert abs(d - math.log(float(x))) <= 2e-15 * max(1.0, abs(math.log(float(x))))
+    for a, b in rng.uniform(-100, 100, (2000, 2)).astype(np.float32):
+        assert L.po_det_hypotf(float(a), float(b)) == np.float32(math.hypot(float(a), float(b)))
+
+
+def test_dab_statistics_are_plausible():
+    # ~6.6 dabs per pixel of travel for the dry brush (6/actual_r + 6/base_r, r ~ 1.8)
+    env = po.OracleBatchEnv(_spec(("control", "end")), 1)
+    env.reset()
+    env.enable_logs()
+    lin = np.linspace(0, 64, 32)
+    env.step(np.array([[0, 10 * 32 + 2]]))         # move pen to (lin[2], lin[10])
+    env.pop_dabs(0)
+    # straight-ish stroke: control on the chord midpoint
+    e = 10 * 32 + 28
+    c = 10 * 32 + 15
+    env.step(np.array([[c, e]]))
+    d = env.pop_dabs(0)
+    travel = lin[28] - lin[2]
+    assert 5.0 < len(d) / travel < 8.5
+    assert 1.2 < d["radius"].mean() < 2.4 and (d["hardness"] == np.float32(0.2)).all()
