@@ -1,0 +1,217 @@
+/*
+ * include/spiral_b200.h -- C ABI of libspiral_b200.so (sm_100a).
+ *
+ * Drop-in boundary for the SPIRAL inner loop (render -> D reward -> A2C loss).
+ * The reference (carpedm20/SPIRAL-tensorflow) has no FFI of its own for this
+ * path: it reaches native code through the mypaint SWIG API and tf.Session.run.
+ * Each entry point below names the reference interface it replaces.
+ *
+ * Conventions
+ *   - every call returns 0 on success, a negative SPIRAL_E* code otherwise;
+ *     the message is available from spiral_last_error() (thread local)
+ *   - all `dev` pointers are DEVICE pointers owned by the caller (PyTorch
+ *     tensors: tensor.data_ptr()); the library allocates nothing on the step
+ *     path and never synchronises the device
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream)
+ *   - one handle per (process, GPU); calls on one handle are not re-entrant
+ */
+#ifndef SPIRAL_B200_H
+#define SPIRAL_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SPIRAL_ABI_VERSION 1
+
+#define SPIRAL_OK 0
+#define SPIRAL_EINVAL (-1)      /* bad argument / unsupported configuration */
+#define SPIRAL_ECUDA (-2)       /* CUDA runtime error (message has the cudaError string) */
+#define SPIRAL_EUNSUPPORTED (-3)
+
+int spiral_version(void);
+const char *spiral_last_error(void);
+
+/* ------------------------------------------------------------------ */
+/* Painting environment (K1)                                            */
+/* replaces: envs/mnist.py:81-105 reset, :107-222 draw/_draw/curve,     */
+/*           :231-260 step/state, and beneath them libmypaint 1.3.0     */
+/*           mypaint_brush_stroke_to + tiled-surface draw_dab and       */
+/*           mypaint 1.2.1 tile_convert_rgbu16_to_rgbu8                 */
+/* ------------------------------------------------------------------ */
+#define SPIRAL_MAX_POINTS 4
+#define SPIRAL_MAX_TABLE 8
+#define SPIRAL_MAX_L 64
+#define SPIRAL_TILE 64
+#define SPIRAL_BRUSH_STATE_FLOATS 16     /* per canvas, caller-owned float[B,16]  */
+#define SPIRAL_ENV_STATE_DOUBLES 16      /* per canvas, caller-owned double[B,16] */
+#define SPIRAL_DAB_FLOATS 8              /* per pending dab, caller-owned float[B,max_dabs,8] */
+
+/* settings whose value may depend on brush inputs (libmypaint "mappings") */
+enum {
+    SPIRAL_DYN_OPAQUE = 0,
+    SPIRAL_DYN_OPAQUE_MULTIPLY,
+    SPIRAL_DYN_RADIUS_LOGARITHMIC,
+    SPIRAL_DYN_HARDNESS,
+    SPIRAL_DYN_RADIUS_BY_RANDOM,
+    SPIRAL_DYN_OFFSET_BY_RANDOM,
+    SPIRAL_DYN_SPEED1_SLOWNESS,
+    SPIRAL_DYN_SPEED2_SLOWNESS,
+    SPIRAL_DYN_ANTI_ALIASING,
+    SPIRAL_DYN_COUNT
+};
+/* brush inputs a mapping may read */
+enum { SPIRAL_IN_PRESSURE = 0, SPIRAL_IN_SPEED1, SPIRAL_IN_SPEED2, SPIRAL_IN_COUNT };
+
+/* libmypaint mapping: value = base + sum_i piecewise_linear_i(input_i) */
+typedef struct {
+    float base;
+    int32_t n[SPIRAL_IN_COUNT];                       /* points per input, 0 = unused, else 2..4 */
+    float x[SPIRAL_IN_COUNT][SPIRAL_MAX_POINTS];
+    float y[SPIRAL_IN_COUNT][SPIRAL_MAX_POINTS];
+} SpiralMapping;
+
+/* the subset of a .myb brush the rasteriser implements (assets/brushes/dry_brush.myb) */
+typedef struct {
+    SpiralMapping dyn[SPIRAL_DYN_COUNT];
+    float slow_tracking;
+    float speed1_gamma, speed2_gamma;
+    float dabs_per_basic_radius, dabs_per_actual_radius, dabs_per_second;
+    float elliptical_dab_angle;                       /* degrees; ratio is fixed at 1 */
+} SpiralBrush;
+
+typedef struct {
+    int32_t abi_version;          /* SPIRAL_ABI_VERSION */
+    int32_t device;               /* CUDA device ordinal */
+    int32_t batch;                /* canvases on this GPU */
+    int32_t channels;             /* observation channels: 1 = gray (utils.py:3-5), 3 = RGB (extension) */
+    int32_t location_size;        /* L: control/end heads index an L x L grid (utils.py:10-18) */
+    int32_t n_heads;              /* K: columns of the action matrix, env.acs order (base.py:32) */
+    int32_t idx_jump, idx_control, idx_end, idx_pressure, idx_size, idx_color;   /* column or -1 */
+    int32_t n_pressures, n_sizes, n_colors;
+    int32_t colorize;             /* mnist.py:40,132-133: colour = palette[step] */
+    int32_t dither;               /* 0 = round-half, 1 = per-pixel table (pixops.cpp dithering_noise) */
+    int32_t max_dabs;             /* capacity of the per-canvas pending-dab list */
+    double lin[SPIRAL_MAX_L];     /* np.linspace(0, 64, L) */
+    double pressures[SPIRAL_MAX_TABLE];
+    double sizes[SPIRAL_MAX_TABLE];
+    uint16_t colors_fix15[SPIRAL_MAX_TABLE][4];   /* dab colour after set_color_rgb -> hsv -> rgb */
+    double default_pressure, default_size;        /* MNIST.pressure, MNIST.size (mnist.py:34-35) */
+    double head, tail;                            /* mnist.py:23-24 */
+    double entry_pressure0;                       /* np.min(self.pressures), mnist.py:82 */
+    SpiralBrush brush;
+    uint16_t dither_table[SPIRAL_TILE * SPIRAL_TILE];
+} SpiralEnvCfg;
+
+typedef struct SpiralEnv SpiralEnv;
+
+/* Validates cfg, precomputes brush constants, uploads tables to `device`. */
+int spiral_env_create(const SpiralEnvCfg *cfg, SpiralEnv **out);
+int spiral_env_destroy(SpiralEnv *env);
+
+/* envs/mnist.py:81-105.  canvas u16[B,64,64,4] <- opaque white (fix15 1.0), brush/env state
+ * re-initialised (new Brush => RNG re-seeded with 1000), obs f32[B,64,64,C] <- 255. */
+int spiral_env_reset(SpiralEnv *env, uint16_t *canvas_dev, float *brush_state_dev,
+                     double *env_state_dev, float *obs_dev, void *stream);
+
+/* envs/mnist.py:231-260 for every canvas.  actions i32[B,K].  dab_scratch f32[B,max_dabs,8] and
+ * dab_count i32[B,2] are scratch owned by the caller (contents undefined between calls).
+ * status_dev i32[1] is OR-ed with 1 if any canvas overflowed max_dabs (result then invalid). */
+int spiral_env_step(SpiralEnv *env, const int32_t *actions_dev, uint16_t *canvas_dev,
+                    float *brush_state_dev, double *env_state_dev, float *dab_scratch_dev,
+                    int32_t *dab_count_dev, float *obs_dev, int32_t *status_dev, void *stream);
+
+/* the two halves of spiral_env_step, exposed for profiling and tests:
+ *   expand    : stroke expansion (action -> events -> brush state machine -> pending dabs)
+ *   composite : dab mask + fix15 blend into the smem-resident canvas + read-back */
+int spiral_env_expand(SpiralEnv *env, const int32_t *actions_dev, float *brush_state_dev,
+                      double *env_state_dev, float *dab_scratch_dev, int32_t *dab_count_dev,
+                      int32_t *status_dev, void *stream);
+int spiral_env_composite(SpiralEnv *env, uint16_t *canvas_dev, const float *dab_scratch_dev,
+                         const int32_t *dab_count_dev, float *obs_dev, void *stream);
+
+/* test hook: finalised dabs (x, y, radius, hardness, opacity) of the pending list as they are
+ * handed to the tile, f32[B,max_dabs,5] (opacity as float), count per canvas in out_count i32[B] */
+int spiral_env_debug_dabs(SpiralEnv *env, const float *dab_scratch_dev, const int32_t *dab_count_dev,
+                          float *out_dev, int32_t *out_count_dev, void *stream);
+
+/* envs/mnist.py:235-243 + envs/utils.py:7-8: reward[b] = 1 - ||obs_b - target_b||_2 / n,
+ * n = 64*64*C elements per canvas, both in 0..255 units. */
+int spiral_l2_reward(const float *obs_dev, const float *target_dev, float *reward_dev,
+                     int32_t batch, int32_t n, void *stream);
+
+/* deterministic math used by the expansion kernel (tests compare with the oracle's copy) */
+int spiral_debug_detmath(const double *x_dev, double *exp_out_dev, double *log_out_dev, int32_t n,
+                         void *stream);
+
+/* ------------------------------------------------------------------ */
+/* A2C loss (K3)                                                        */
+/* replaces: rl_utils.py:18-57 (discount, multiple_process_rollout) and */
+/*           agent.py:161-196 (per-head log-softmax PG / value / entropy */
+/*           loss) together with its gradient w.r.t. logits and vf      */
+/* ------------------------------------------------------------------ */
+#define SPIRAL_MAX_HEADS 8
+
+/* logits_dev[k]: f32[B,T,N_k] (device pointers in a HOST array of n_heads entries);
+ * actions i32[B,T,K]; rewards, values, vf: f32[B,T].
+ * adv_out, ret_out: f32[B,T] (rl_utils.py:32-40 with bootstrap r = 0).
+ * out_scalars_dev f32[4] = {pi_loss, vf_loss, entropy, total} exactly as agent.py:172-194 sums them.
+ * dlogits_dev[k] f32[B,T,N_k] and dvf_dev f32[B,T] = d total / d input (may be NULL to skip).
+ * partial_dev: scratch f32[B*T*4]. */
+int spiral_a2c_loss(const float *const *logits_dev, const int32_t *head_sizes, int32_t n_heads,
+                    const int32_t *actions_dev, const float *rewards_dev, const float *values_dev,
+                    const float *vf_dev, int32_t batch, int32_t T, double gamma, double lambda_,
+                    float entropy_coeff, float *adv_out_dev, float *ret_out_dev,
+                    float *out_scalars_dev, float *const *dlogits_dev, float *dvf_dev,
+                    float *partial_dev, void *stream);
+
+/* ------------------------------------------------------------------ */
+/* Discriminator forward / reward (K2)                                  */
+/* replaces: models/discriminator.py:51-95 build_model and :157-163     */
+/*           predict (sigmoid(D(norm(x))), BN in training mode)          */
+/* ------------------------------------------------------------------ */
+#define SPIRAL_DISC_MAX_LAYERS 8
+
+typedef struct {
+    int32_t abi_version;
+    int32_t device;
+    int32_t max_batch;
+    int32_t in_channels;          /* C, or 2C when conditional (discriminator.py:36-38) */
+    int32_t screen_size;          /* 64 -> 6 conv layers */
+    int32_t disc_dim;
+    int32_t batch_norm;           /* args.disc_batch_norm */
+    int32_t precision;            /* 0 = fp32 SIMT, 1 = tcgen05 bf16x3 (fp32-equivalent), 2 = tcgen05 bf16 */
+} SpiralDiscCfg;
+
+typedef struct SpiralDisc SpiralDisc;
+
+/* parameter pointers (device, fp32), TF layouts: conv kernel HWIO [5,5,Cin,Cout], bias [Cout],
+ * BN gamma/beta [Cout] (layers >= 1), dense kernel [disc_dim*32, 1], dense bias [1] */
+typedef struct {
+    const float *conv_w[SPIRAL_DISC_MAX_LAYERS];
+    const float *conv_b[SPIRAL_DISC_MAX_LAYERS];
+    const float *bn_gamma[SPIRAL_DISC_MAX_LAYERS];
+    const float *bn_beta[SPIRAL_DISC_MAX_LAYERS];
+    const float *dense_w;
+    const float *dense_b;
+} SpiralDiscWeights;
+
+int spiral_disc_create(const SpiralDiscCfg *cfg, SpiralDisc **out);
+int spiral_disc_destroy(SpiralDisc *d);
+/* bytes of device workspace spiral_disc_forward needs for `batch` images */
+int64_t spiral_disc_workspace_bytes(const SpiralDisc *d, int32_t batch);
+/* (re)packs the weights into the layout the kernels read; call after every optimiser step */
+int spiral_disc_load_weights(SpiralDisc *d, const SpiralDiscWeights *w, void *workspace_dev,
+                             void *stream);
+/* x f32[B,64,64,Cin] NHWC in 0..255 (norm_fn = (x-127.5)/127.5 applied inside, base.py:51-52);
+ * logits/probs f32[B]; bn_stats_dev f32[layers,2,max Cout] receives per-layer batch mean / biased
+ * variance (may be NULL). */
+int spiral_disc_forward(SpiralDisc *d, const float *x_dev, int32_t batch, float *logits_dev,
+                        float *probs_dev, float *bn_stats_dev, void *workspace_dev, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,308 @@
+// api_env.cu -- C-ABI glue for the painting environment (include/spiral_b200.h, K1).
+//
+// Host side only: validates the configuration, precomputes the per-brush constants the kernels
+// read (the same float/double expressions libmypaint evaluates once per brush in
+// settings_base_values_have_changed / render_dab_mask), seeds the RNG block, launches kernels.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "../../include/spiral_b200.h"
+#include "common.h"
+#include "detmath.cuh"
+#include "raster.cuh"
+
+namespace spiral {
+cudaError_t launch_reset(const EnvParams &P, uint16_t *canvas, float *bs, double *es, float *obs, cudaStream_t st);
+cudaError_t launch_expand(const EnvParams &P, const int32_t *actions, float *bs, double *es, float *dabs,
+                          int32_t *dab_count, int32_t *status, cudaStream_t st);
+cudaError_t launch_composite(const EnvParams &P, uint16_t *canvas, const float *dabs, const int32_t *dab_count,
+                             const uint16_t *dither, float *obs, cudaStream_t st);
+cudaError_t launch_debug_dabs(const EnvParams &P, const float *dabs, const int32_t *dab_count, float *out,
+                              int32_t *out_count, cudaStream_t st);
+cudaError_t launch_l2_reward(const float *obs, const float *target, float *reward, int batch, int n, cudaStream_t st);
+cudaError_t launch_detmath(const double *x, double *e, double *l, int n, cudaStream_t st);
+}  // namespace spiral
+
+using namespace spiral;
+
+// ------------------------------------------------------------------------------------------
+// error plumbing
+// ------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+
+int spiral_set_error(int code, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+int spiral_cuda_error(cudaError_t e, const char *what)
+{
+    return spiral_set_error(SPIRAL_ECUDA, "%s: %s", what, cudaGetErrorString(e));
+}
+
+extern "C" int spiral_version(void) { return SPIRAL_ABI_VERSION; }
+extern "C" const char *spiral_last_error(void) { return g_err; }
+
+// ------------------------------------------------------------------------------------------
+// rng-double.c set_seed (Knuth, ranf_start with KK=10, LL=7, TT=7): state after seeding = the
+// first block of outputs
+// ------------------------------------------------------------------------------------------
+static inline double ms(double x, double y) { const double s = x + y; return s - (int)s; }
+
+static void rng_array(double *ran_u, double *aa, int n)
+{
+    const int KK = 10, LL = 7;
+    int i, j;
+    for (j = 0; j < KK; j++) aa[j] = ran_u[j];
+    for (; j < n; j++) aa[j] = ms(aa[j - KK], aa[j - LL]);
+    for (i = 0; i < LL; i++, j++) ran_u[i] = ms(aa[j - KK], aa[j - LL]);
+    for (; i < KK; i++, j++) ran_u[i] = ms(aa[j - KK], ran_u[i - LL]);
+}
+
+static void rng_seed_block(long seed, double *out10)
+{
+    const int KK = 10, LL = 7, TT = 7;
+    double u[KK + KK - 1], ran_u[KK];
+    const double ulp = (1.0 / (1L << 30)) / (1L << 22);
+    double ss = 2.0 * ulp * ((seed & 0x3fffffff) + 2);
+    int j, s, t;
+    for (j = 0; j < KK; j++) {
+        u[j] = ss;
+        ss += ss;
+        if (ss >= 1.0) ss -= 1.0 - 2 * ulp;
+    }
+    u[1] += ulp;
+    for (s = seed & 0x3fffffff, t = TT - 1; t;) {
+        for (j = KK - 1; j > 0; j--) { u[j + j] = u[j]; u[j + j - 1] = 0.0; }
+        for (j = KK + KK - 2; j >= KK; j--) {
+            u[j - (KK - LL)] = ms(u[j - (KK - LL)], u[j]);
+            u[j - KK] = ms(u[j - KK], u[j]);
+        }
+        if (s & 1) {
+            for (j = KK; j > 0; j--) u[j] = u[j - 1];
+            u[0] = u[KK];
+            u[LL] = ms(u[LL], u[KK]);
+        }
+        if (s) s >>= 1; else t--;
+    }
+    for (j = 0; j < LL; j++) ran_u[j + KK - LL] = u[j];
+    for (; j < KK; j++) ran_u[j - LL] = u[j];
+    for (j = 0; j < 10; j++) rng_array(ran_u, u, KK + KK - 1);
+    for (j = 0; j < KK; j++) out10[j] = ran_u[j];
+}
+
+// ------------------------------------------------------------------------------------------
+struct SpiralEnv {
+    EnvParams P;
+    int device;
+    uint16_t *d_dither;
+};
+
+static bool is_pow2f(float v)
+{
+    if (!(v > 0.0f) || !std::isfinite(v)) return false;
+    int e;
+    return std::frexp(v, &e) == 0.5f;
+}
+
+extern "C" int spiral_env_create(const SpiralEnvCfg *cfg, SpiralEnv **out)
+{
+    if (!cfg || !out) return spiral_set_error(SPIRAL_EINVAL, "spiral_env_create: null argument");
+    *out = nullptr;
+    if (cfg->abi_version != SPIRAL_ABI_VERSION)
+        return spiral_set_error(SPIRAL_EINVAL, "ABI version mismatch: caller %d, library %d",
+                                cfg->abi_version, SPIRAL_ABI_VERSION);
+    if (cfg->batch <= 0) return spiral_set_error(SPIRAL_EINVAL, "batch must be > 0");
+    if (cfg->channels != 1 && cfg->channels != 3)
+        return spiral_set_error(SPIRAL_EINVAL, "channels must be 1 or 3 (got %d)", cfg->channels);
+    if (cfg->location_size < 1 || cfg->location_size > SPIRAL_MAX_L)
+        return spiral_set_error(SPIRAL_EINVAL, "location_size must be in 1..%d", SPIRAL_MAX_L);
+    if (cfg->n_heads < 1 || cfg->n_heads > 8) return spiral_set_error(SPIRAL_EINVAL, "n_heads must be in 1..8");
+    const int idx[6] = {cfg->idx_jump, cfg->idx_control, cfg->idx_end, cfg->idx_pressure, cfg->idx_size, cfg->idx_color};
+    for (int i = 0; i < 6; i++)
+        if (idx[i] < -1 || idx[i] >= cfg->n_heads)
+            return spiral_set_error(SPIRAL_EINVAL, "action column index %d out of range", idx[i]);
+    if (cfg->n_pressures > SPIRAL_MAX_TABLE || cfg->n_sizes > SPIRAL_MAX_TABLE || cfg->n_colors > SPIRAL_MAX_TABLE)
+        return spiral_set_error(SPIRAL_EINVAL, "table sizes must be <= %d", SPIRAL_MAX_TABLE);
+    if ((cfg->idx_color >= 0 || cfg->colorize) && cfg->n_colors < 1)
+        return spiral_set_error(SPIRAL_EINVAL, "colour action / colorize needs a palette");
+    if (cfg->max_dabs < 32) return spiral_set_error(SPIRAL_EINVAL, "max_dabs must be >= 32");
+    {
+        const double head = 100 * cfg->head, tail = 100 * cfg->tail;
+        const int hr = (int)head + 1, tr = (int)tail + 1;
+        if (hr < 2 || tr < hr || tr > 101)
+            return spiral_set_error(SPIRAL_EUNSUPPORTED, "head/tail %.4f/%.4f outside the supported range", cfg->head, cfg->tail);
+    }
+    const SpiralBrush &br = cfg->brush;
+    for (int s = 0; s < SPIRAL_DYN_COUNT; s++)
+        for (int j = 0; j < SPIRAL_IN_COUNT; j++) {
+            const int n = br.dyn[s].n[j];
+            if (n != 0 && (n < 2 || n > SPIRAL_MAX_POINTS))
+                return spiral_set_error(SPIRAL_EINVAL, "mapping %d/%d has %d points (need 0 or 2..%d)", s, j, n, SPIRAL_MAX_POINTS);
+        }
+
+    SpiralEnv *env = new (std::nothrow) SpiralEnv();
+    if (!env) return spiral_set_error(SPIRAL_EINVAL, "out of host memory");
+    memset(env, 0, sizeof(*env));
+    EnvParams &P = env->P;
+    env->device = cfg->device;
+    P.B = cfg->batch; P.C = cfg->channels; P.L = cfg->location_size; P.K = cfg->n_heads;
+    P.idx_jump = cfg->idx_jump; P.idx_control = cfg->idx_control; P.idx_end = cfg->idx_end;
+    P.idx_pressure = cfg->idx_pressure; P.idx_size = cfg->idx_size; P.idx_color = cfg->idx_color;
+    P.n_colors = cfg->n_colors; P.colorize = cfg->colorize; P.dither = cfg->dither; P.max_dabs = cfg->max_dabs;
+    for (int i = 0; i < SPIRAL_MAX_L; i++) P.lin[i] = cfg->lin[i];
+    for (int i = 0; i < SPIRAL_MAX_TABLE; i++) {
+        P.pressures[i] = cfg->pressures[i];
+        P.sizes[i] = cfg->sizes[i];
+        for (int c = 0; c < 4; c++) P.colors[i][c] = cfg->colors_fix15[i][c];
+    }
+    P.default_pressure = cfg->default_pressure; P.default_size = cfg->default_size;
+    P.head = cfg->head; P.tail = cfg->tail; P.entry_pressure0 = cfg->entry_pressure0;
+
+    P.uses_speed1 = P.uses_speed2 = 0;
+    for (int s = 0; s < SPIRAL_DYN_COUNT; s++) {
+        MapDev &m = P.dyn[s];
+        m.base = br.dyn[s].base;
+        for (int j = 0; j < SPIRAL_IN_COUNT; j++) {
+            m.n[j] = br.dyn[s].n[j];
+            if (m.n[j] && j == SPIRAL_IN_SPEED1) P.uses_speed1 = 1;
+            if (m.n[j] && j == SPIRAL_IN_SPEED2) P.uses_speed2 = 1;
+            for (int k = 0; k < SPIRAL_MAX_POINTS; k++) {
+                m.x[j][k] = br.dyn[s].x[j][k];
+                m.y[j][k] = br.dyn[s].y[j][k];
+                m.inv[j][k] = 0.0f;
+            }
+            for (int k = 0; k + 1 < m.n[j]; k++) {
+                const float den = m.x[j][k + 1] - m.x[j][k];
+                if (is_pow2f(den)) m.inv[j][k] = 1.0f / den;
+            }
+        }
+    }
+    // base radius per size-table entry: set_base_value('radius_logarithmic', size) takes a float
+    for (int i = 0; i < 8; i++) {
+        P.base_rlog[i] = (float)cfg->sizes[i];
+        P.base_radius[i] = detmath::det_expf(P.base_rlog[i]);
+    }
+    P.base_rlog[8] = br.dyn[SPIRAL_DYN_RADIUS_LOGARITHMIC].base;
+    P.base_radius[8] = detmath::det_expf(P.base_rlog[8]);
+
+    P.slow_tracking = br.slow_tracking;
+    // settings_base_values_have_changed: speed input mapping  y = log(gamma + x) * m + q
+    const float gam[2] = {br.speed1_gamma, br.speed2_gamma};
+    for (int i = 0; i < 2; i++) {
+        float gamma = detmath::det_expf(gam[i]);
+        const float fix1_x = 45.0f, fix1_y = 0.5f, fix2_x = 45.0f, fix2_dy = 0.015f;
+        const float c1 = (float)detmath::det_log((double)(fix1_x + gamma));
+        const float m = fix2_dy * (fix2_x + gamma);
+        const float q = fix1_y - m * c1;
+        P.sp_gamma[i] = gamma; P.sp_m[i] = m; P.sp_q[i] = q;
+    }
+    P.dabs_basic = br.dabs_per_basic_radius;
+    P.dabs_actual = br.dabs_per_actual_radius;
+    P.dabs_second = br.dabs_per_second;
+    // render_dab_mask: float angle_rad = angle/360*2*M_PI; float cs = cos(angle_rad); ...
+    {
+        const float angle = br.elliptical_dab_angle;
+        const float angle_rad = angle / 360 * 2 * M_PI;
+        P.cs = (float)::cos((double)angle_rad);     // C: float cs = cos(angle_rad)  (double cos)
+        P.sn = (float)::sin((double)angle_rad);
+        P.l2 = P.cs * P.cs + P.sn * P.sn;
+        P.rad_area_1 = sqrtf(1.0f / M_PI);
+    }
+    // |rand_gauss| <= 2*sqrt(3); radius <= ACTUAL_RADIUS * exp(|g| * |radius_by_random|)
+    {
+        const SpiralMapping &rb = br.dyn[SPIRAL_DYN_RADIUS_BY_RANDOM];
+        float mx = fabsf(rb.base);
+        bool mapped = false;
+        for (int j = 0; j < SPIRAL_IN_COUNT; j++) mapped |= rb.n[j] != 0;
+        P.cull_factor = mapped ? 1e30f : (float)(::exp(3.4642 * (double)mx) * 1.001);
+    }
+    rng_seed_block(1000, P.rng_seed_block);
+
+    int prev = 0;
+    cudaError_t e = cudaGetDevice(&prev);
+    if (e == cudaSuccess) e = cudaSetDevice(cfg->device);
+    if (e == cudaSuccess) e = cudaMalloc(&env->d_dither, sizeof(cfg->dither_table));
+    if (e == cudaSuccess)
+        e = cudaMemcpy(env->d_dither, cfg->dither_table, sizeof(cfg->dither_table), cudaMemcpyHostToDevice);
+    cudaSetDevice(prev);
+    if (e != cudaSuccess) {
+        delete env;
+        return spiral_cuda_error(e, "spiral_env_create");
+    }
+    *out = env;
+    return SPIRAL_OK;
+}
+
+extern "C" int spiral_env_destroy(SpiralEnv *env)
+{
+    if (!env) return SPIRAL_OK;
+    if (env->d_dither) cudaFree(env->d_dither);
+    delete env;
+    return SPIRAL_OK;
+}
+
+#define REQUIRE(p) do { if (!(p)) return spiral_set_error(SPIRAL_EINVAL, "%s: null or invalid argument `%s`", __func__, #p); } while (0)
+
+extern "C" int spiral_env_reset(SpiralEnv *env, uint16_t *canvas, float *bs, double *es, float *obs, void *stream)
+{
+    REQUIRE(env); REQUIRE(canvas); REQUIRE(bs); REQUIRE(es); REQUIRE(obs);
+    const cudaError_t e = launch_reset(env->P, canvas, bs, es, obs, (cudaStream_t)stream);
+    return e == cudaSuccess ? SPIRAL_OK : spiral_cuda_error(e, "spiral_env_reset");
+}
+
+extern "C" int spiral_env_expand(SpiralEnv *env, const int32_t *actions, float *bs, double *es, float *dabs,
+                                 int32_t *dab_count, int32_t *status, void *stream)
+{
+    REQUIRE(env); REQUIRE(actions); REQUIRE(bs); REQUIRE(es); REQUIRE(dabs); REQUIRE(dab_count); REQUIRE(status);
+    const cudaError_t e = launch_expand(env->P, actions, bs, es, dabs, dab_count, status, (cudaStream_t)stream);
+    return e == cudaSuccess ? SPIRAL_OK : spiral_cuda_error(e, "spiral_env_expand");
+}
+
+extern "C" int spiral_env_composite(SpiralEnv *env, uint16_t *canvas, const float *dabs, const int32_t *dab_count,
+                                    float *obs, void *stream)
+{
+    REQUIRE(env); REQUIRE(canvas); REQUIRE(dabs); REQUIRE(dab_count); REQUIRE(obs);
+    const cudaError_t e = launch_composite(env->P, canvas, dabs, dab_count, env->d_dither, obs, (cudaStream_t)stream);
+    return e == cudaSuccess ? SPIRAL_OK : spiral_cuda_error(e, "spiral_env_composite");
+}
+
+extern "C" int spiral_env_step(SpiralEnv *env, const int32_t *actions, uint16_t *canvas, float *bs, double *es,
+                               float *dabs, int32_t *dab_count, float *obs, int32_t *status, void *stream)
+{
+    int rc = spiral_env_expand(env, actions, bs, es, dabs, dab_count, status, stream);
+    if (rc != SPIRAL_OK) return rc;
+    return spiral_env_composite(env, canvas, dabs, dab_count, obs, stream);
+}
+
+extern "C" int spiral_env_debug_dabs(SpiralEnv *env, const float *dabs, const int32_t *dab_count, float *out,
+                                     int32_t *out_count, void *stream)
+{
+    REQUIRE(env); REQUIRE(dabs); REQUIRE(dab_count); REQUIRE(out); REQUIRE(out_count);
+    const cudaError_t e = launch_debug_dabs(env->P, dabs, dab_count, out, out_count, (cudaStream_t)stream);
+    return e == cudaSuccess ? SPIRAL_OK : spiral_cuda_error(e, "spiral_env_debug_dabs");
+}
+
+extern "C" int spiral_l2_reward(const float *obs, const float *target, float *reward, int32_t batch, int32_t n,
+                                void *stream)
+{
+    REQUIRE(obs); REQUIRE(target); REQUIRE(reward);
+    if (batch <= 0 || n <= 0 || (n & 3)) return spiral_set_error(SPIRAL_EINVAL, "spiral_l2_reward: n must be a positive multiple of 4");
+    const cudaError_t e = launch_l2_reward(obs, target, reward, batch, n, (cudaStream_t)stream);
+    return e == cudaSuccess ? SPIRAL_OK : spiral_cuda_error(e, "spiral_l2_reward");
+}
+
+extern "C" int spiral_debug_detmath(const double *x, double *e_out, double *l_out, int32_t n, void *stream)
+{
+    REQUIRE(x); REQUIRE(e_out); REQUIRE(l_out);
+    const cudaError_t e = launch_detmath(x, e_out, l_out, n, (cudaStream_t)stream);
+    return e == cudaSuccess ? SPIRAL_OK : spiral_cuda_error(e, "spiral_debug_detmath");
+}

@@ -1,0 +1,26 @@
+#!/bin/bash
+# Builds libspiral_b200.so for sm_100a in-tree (the .so is git-ignored but travels with gpurun).
+#   --fmad=false : the rasteriser's float/double arithmetic must not be contracted (bit-exact
+#                  against the oracle); fused operations are written as explicit fma().
+set -euo pipefail
+HERE="$(cd "$(dirname "$0")" && pwd)"
+cd "$HERE"
+NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
+ARCH="-gencode arch=compute_100a,code=sm_100a"
+COMMON="-O3 -lineinfo -std=c++17 --expt-relaxed-constexpr -Xcompiler -fPIC,-ffp-contract=off,-fno-fast-math $ARCH"
+mkdir -p build
+pids=()
+compile() { # src extra-flags...
+  local src=$1; shift
+  if [ ! -f build/${src%.cu}.o ] || [ $src -nt build/${src%.cu}.o ] || [ -n "$(find . -maxdepth 1 \( -name '*.cuh' -o -name '*.h' \) -newer build/${src%.cu}.o)" ] || [ ../../include/spiral_b200.h -nt build/${src%.cu}.o ]; then
+    $NVCC $COMMON "$@" -c $src -o build/${src%.cu}.o &
+    pids+=($!)
+  fi
+}
+compile raster.cu --fmad=false ${PTXAS_V:+-Xptxas -v}
+compile api_env.cu --fmad=false
+for f in a2c.cu disc.cu disc_tc.cu; do [ -f $f ] && compile $f ${PTXAS_V:+-Xptxas -v}; done
+for p in "${pids[@]:-}"; do [ -n "$p" ] && wait $p; done
+OBJS=$(ls build/*.o)
+$NVCC $ARCH -shared -o libspiral_b200.so $OBJS -lcudart
+echo "built $HERE/libspiral_b200.so"

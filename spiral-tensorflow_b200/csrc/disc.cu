@@ -1,0 +1,370 @@
+// disc.cu -- K2: discriminator forward D(x) / reward for sm_100a.
+//
+// Replaces models/discriminator.py:51-95 (build_model: log2(S) x [conv 5x5 stride 2 'SAME' ->
+// batch-norm (training mode, layers >= 1) -> leaky-ReLU(0.2)] -> dense -> sigmoid) and
+// :157-163 (predict), with norm_fn = (x - 127.5) / 127.5 (envs/base.py:51-52) fused into the
+// first layer's load.
+//
+// TF semantics kept: NHWC activations, HWIO kernels, 'SAME' padding for
+// k=5, s=2 on even sizes = 1 before / 2 after, BN epsilon 1e-3 with the BIASED batch variance,
+// statistics of the batch being scored (training=True even in predict()).
+//
+// This file holds the host object, the fp32 SIMT path (precision 0, also the in-library
+// reference for the tensor-core path) and the kernels shared by both paths (BN finalise,
+// dense + sigmoid).  The tcgen05 implicit-GEMM path lives in disc_tc.cu.
+#include "disc.cuh"
+
+#include <cmath>
+#include <cstring>
+#include <new>
+
+namespace spiral {
+
+// ------------------------------------------------------------------------------------------
+// layer 0: direct convolution, (x - 127.5) / 127.5 on load, bias, no BN; raw output + (optional)
+// nothing else -- the consumer applies leaky-ReLU on load.   One CTA = 8x8 output pixels.
+// ------------------------------------------------------------------------------------------
+template <int COUT_PER_THREAD>
+__global__ void __launch_bounds__(256)
+conv0_kernel(const float *__restrict__ x, const float *__restrict__ w, const float *__restrict__ bias,
+             float *__restrict__ out, int B, int H, int Cin, int Cout)
+{
+    // H = W = input size; output H/2
+    extern __shared__ float sm[];
+    const int Ho = H / 2;
+    const int tiles = Ho / 8;
+    const int b = blockIdx.x / (tiles * tiles);
+    const int trem = blockIdx.x % (tiles * tiles);
+    const int oy0 = (trem / tiles) * 8, ox0 = (trem % tiles) * 8;
+    float *s_in = sm;                         // [19][19][Cin] normalised, zero padded
+    float *s_w = sm + 19 * 19 * Cin;          // [25*Cin][Cout]
+    const int tid = threadIdx.x;
+    for (int i = tid; i < 19 * 19 * Cin; i += 256) {
+        const int c = i % Cin;
+        const int p = i / Cin;
+        const int ly = p / 19, lx = p % 19;
+        const int iy = 2 * oy0 - 1 + ly, ix = 2 * ox0 - 1 + lx;
+        float v = 0.0f;
+        if (iy >= 0 && iy < H && ix >= 0 && ix < H)
+            v = (x[(((size_t)b * H + iy) * H + ix) * Cin + c] - 127.5f) / 127.5f;
+        s_in[i] = v;
+    }
+    for (int i = tid; i < 25 * Cin * Cout; i += 256) s_w[i] = w[i];
+    __syncthreads();
+    // thread -> pixel (tid % 64), channel group (tid / 64): Cout/4 channels each, strided by 4
+    const int p = tid & 63, cg = tid >> 6;
+    const int py = p >> 3, px = p & 7;
+    for (int co = cg; co < Cout; co += 4) {
+        float acc = bias[co];
+        for (int ky = 0; ky < 5; ky++)
+            for (int kx = 0; kx < 5; kx++) {
+                const float *ip = s_in + ((2 * py + ky) * 19 + (2 * px + kx)) * Cin;
+                const float *wp = s_w + ((ky * 5 + kx) * Cin) * Cout + co;
+                for (int c = 0; c < Cin; c++) acc = fmaf(ip[c], wp[c * Cout], acc);
+            }
+        out[(((size_t)b * Ho + oy0 + py) * Ho + ox0 + px) * Cout + co] = acc;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// generic layer (fp32 SIMT implicit GEMM): M = B*Ho*Wo pixels, N = Cout, K = 25*Cin.
+// 64x64 tile per CTA, 4x4 outputs per thread, K chunks of 16 channels of one tap.
+// The producer layer's BN + leaky-ReLU is applied while loading A:  a = lrelu(x*scale[c]+shift[c]).
+// Epilogue: + bias, store raw, per-CTA per-channel (sum, sum of squares) partials for this
+// layer's BN.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+conv_simt_kernel(const float *__restrict__ in, const float *__restrict__ in_scale,
+                 const float *__restrict__ in_shift, const float *__restrict__ w,
+                 const float *__restrict__ bias, float *__restrict__ out,
+                 float *__restrict__ bn_partial, int B, int H, int Cin, int Cout)
+{
+    __shared__ __align__(16) float As[16][64 + 4];
+    __shared__ __align__(16) float Bs[16][64 + 4];
+    __shared__ float s_sum[16][64], s_sq[16][64];
+    const int Ho = H / 2;
+    const int M = B * Ho * Ho;
+    const int m0 = blockIdx.x * 64, n0 = blockIdx.y * 64;
+    const int tid = threadIdx.x;
+    const int ty = tid >> 4, tx = tid & 15;
+    // A-load role: row ar (0..63), channel quad aq (0..3)
+    const int ar = tid >> 2, aq = tid & 3;
+    const int am = m0 + ar;
+    const bool a_ok = am < M;
+    const int ab = a_ok ? am / (Ho * Ho) : 0;
+    const int arem = a_ok ? am % (Ho * Ho) : 0;
+    const int aoy = arem / Ho, aox = arem % Ho;
+    // B-load role: k row bk (0..15), cout quad bq (0..15)
+    const int bk = tid >> 4, bq = tid & 15;
+
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) acc[i][j] = 0.0f;
+
+    for (int tap = 0; tap < 25; tap++) {
+        const int ky = tap / 5, kx = tap % 5;
+        const int iy = 2 * aoy + ky - 1, ix = 2 * aox + kx - 1;
+        const bool pix_ok = a_ok && iy >= 0 && iy < H && ix >= 0 && ix < H;
+        const float *ip = in + (((size_t)ab * H + iy) * H + ix) * Cin;
+        for (int c0 = 0; c0 < Cin; c0 += 16) {
+            float4 av = make_float4(0.f, 0.f, 0.f, 0.f);
+            const int c = c0 + aq * 4;
+            if (pix_ok && c < Cin) {
+                av = *reinterpret_cast<const float4 *>(ip + c);
+                const float4 sc = *reinterpret_cast<const float4 *>(in_scale + c);
+                const float4 sh = *reinterpret_cast<const float4 *>(in_shift + c);
+                av.x = fmaf(av.x, sc.x, sh.x); av.y = fmaf(av.y, sc.y, sh.y);
+                av.z = fmaf(av.z, sc.z, sh.z); av.w = fmaf(av.w, sc.w, sh.w);
+                av.x = av.x > 0.f ? av.x : 0.2f * av.x; av.y = av.y > 0.f ? av.y : 0.2f * av.y;
+                av.z = av.z > 0.f ? av.z : 0.2f * av.z; av.w = av.w > 0.f ? av.w : 0.2f * av.w;
+            }
+            float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (c0 + bk < Cin && n0 + bq * 4 < Cout)
+                bv = *reinterpret_cast<const float4 *>(w + ((size_t)(tap * Cin + c0 + bk)) * Cout + n0 + bq * 4);
+            __syncthreads();
+            As[aq * 4 + 0][ar] = av.x; As[aq * 4 + 1][ar] = av.y;
+            As[aq * 4 + 2][ar] = av.z; As[aq * 4 + 3][ar] = av.w;
+            *reinterpret_cast<float4 *>(&Bs[bk][bq * 4]) = bv;
+            __syncthreads();
+#pragma unroll
+            for (int kk = 0; kk < 16; kk++) {
+                const float4 a4 = *reinterpret_cast<const float4 *>(&As[kk][ty * 4]);
+                const float4 b4 = *reinterpret_cast<const float4 *>(&Bs[kk][tx * 4]);
+                const float a[4] = {a4.x, a4.y, a4.z, a4.w};
+                const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+                for (int i = 0; i < 4; i++)
+#pragma unroll
+                    for (int j = 0; j < 4; j++) acc[i][j] = fmaf(a[i], bb[j], acc[i][j]);
+            }
+        }
+    }
+    // epilogue
+    float csum[4] = {0, 0, 0, 0}, csq[4] = {0, 0, 0, 0};
+    const bool n_ok = n0 + tx * 4 < Cout;
+    float4 bz = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (n_ok) bz = *reinterpret_cast<const float4 *>(bias + n0 + tx * 4);
+    const float bzz[4] = {bz.x, bz.y, bz.z, bz.w};
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const int m = m0 + ty * 4 + i;
+        if (m < M && n_ok) {
+            float4 o;
+            o.x = acc[i][0] + bzz[0]; o.y = acc[i][1] + bzz[1];
+            o.z = acc[i][2] + bzz[2]; o.w = acc[i][3] + bzz[3];
+            *reinterpret_cast<float4 *>(out + (size_t)m * Cout + n0 + tx * 4) = o;
+            csum[0] += o.x; csum[1] += o.y; csum[2] += o.z; csum[3] += o.w;
+            csq[0] += o.x * o.x; csq[1] += o.y * o.y; csq[2] += o.z * o.z; csq[3] += o.w * o.w;
+        }
+    }
+    if (bn_partial) {
+#pragma unroll
+        for (int j = 0; j < 4; j++) { s_sum[ty][tx * 4 + j] = csum[j]; s_sq[ty][tx * 4 + j] = csq[j]; }
+        __syncthreads();
+        if (tid < 64 && n0 + tid < Cout) {
+            float s = 0.f, q = 0.f;
+#pragma unroll
+            for (int r = 0; r < 16; r++) { s += s_sum[r][tid]; q += s_sq[r][tid]; }
+            float *p = bn_partial + ((size_t)blockIdx.x * Cout + n0 + tid) * 2;
+            p[0] = s; p[1] = q;
+        }
+    }
+}
+
+// per-channel reduction of the partials in fixed order (float64), then the affine the consumer
+// applies on load:  scale = gamma * rsqrt(var + eps), shift = beta - mean * scale
+__global__ void bn_finalize_kernel(const float *__restrict__ partial, int n_part, int Cout, double count,
+                                   const float *__restrict__ gamma, const float *__restrict__ beta,
+                                   float eps, float *__restrict__ scale, float *__restrict__ shift,
+                                   float *__restrict__ stats)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= Cout) return;
+    double s = 0.0, q = 0.0;
+    for (int i = 0; i < n_part; i++) {
+        s += (double)partial[((size_t)i * Cout + c) * 2];
+        q += (double)partial[((size_t)i * Cout + c) * 2 + 1];
+    }
+    const double mean = s / count;
+    double var = q / count - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const float inv = (float)(1.0 / sqrt(var + (double)eps));
+    const float sc = gamma[c] * inv;
+    scale[c] = sc;
+    shift[c] = beta[c] - (float)mean * sc;
+    if (stats) { stats[c] = (float)mean; stats[Cout + c] = (float)var; }
+}
+
+__global__ void fill_affine_kernel(float *scale, float *shift, int n, float sc, float sh)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { scale[i] = sc; shift[i] = sh; }
+}
+
+// flatten (1x1xC) -> dense(1) -> logits, probs = sigmoid(logits); one warp per image
+__global__ void dense_sigmoid_kernel(const float *__restrict__ in, const float *__restrict__ in_scale,
+                                     const float *__restrict__ in_shift, const float *__restrict__ w,
+                                     const float *__restrict__ bias, float *__restrict__ logits,
+                                     float *__restrict__ probs, int B, int C)
+{
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (warp >= B) return;
+    const float *x = in + (size_t)warp * C;
+    float acc = 0.f;
+    for (int c = lane; c < C; c += 32) {
+        float v = fmaf(x[c], in_scale[c], in_shift[c]);
+        v = v > 0.f ? v : 0.2f * v;
+        acc = fmaf(v, w[c], acc);
+    }
+    for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) {
+        const float l = acc + bias[0];
+        logits[warp] = l;
+        if (probs) probs[warp] = 1.0f / (1.0f + expf(-l));
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// host object
+// ------------------------------------------------------------------------------------------
+size_t disc_align(size_t v) { return (v + 255) & ~(size_t)255; }
+
+void disc_plan(const SpiralDisc *d, int batch, DiscPlan *pl)
+{
+    size_t off = 0;
+    int H = d->cfg.screen_size;
+    int Cin = d->cfg.in_channels;
+    for (int l = 0; l < d->n_layers; l++) {
+        const int Cout = d->cfg.disc_dim << l;
+        const int Ho = H / 2;
+        pl->H[l] = H; pl->Cin[l] = Cin; pl->Cout[l] = Cout;
+        pl->act_off[l] = off; off += disc_align((size_t)batch * Ho * Ho * Cout * sizeof(float));
+        const int mtiles = (batch * Ho * Ho + 63) / 64;
+        pl->mtiles[l] = mtiles;
+        pl->part_off[l] = off; off += disc_align((size_t)mtiles * Cout * 2 * sizeof(float));
+        pl->scale_off[l] = off; off += disc_align((size_t)Cout * sizeof(float));
+        pl->shift_off[l] = off; off += disc_align((size_t)Cout * sizeof(float));
+        H = Ho; Cin = Cout;
+    }
+    pl->simt_bytes = off;
+}
+
+int disc_forward_simt(SpiralDisc *d, const float *x, int batch, float *logits, float *probs,
+                      float *bn_stats, char *ws, cudaStream_t st)
+{
+    DiscPlan pl;
+    disc_plan(d, batch, &pl);
+    const SpiralDiscWeights &W = d->w;
+    const int maxC = d->cfg.disc_dim << (d->n_layers - 1);
+    for (int l = 0; l < d->n_layers; l++) {
+        const int H = pl.H[l], Cin = pl.Cin[l], Cout = pl.Cout[l], Ho = H / 2;
+        float *out = (float *)(ws + pl.act_off[l]);
+        float *scale = (float *)(ws + pl.scale_off[l]);
+        float *shift = (float *)(ws + pl.shift_off[l]);
+        float *part = (float *)(ws + pl.part_off[l]);
+        const bool bn = l > 0 && d->cfg.batch_norm;
+        if (l == 0) {
+            const size_t smem = (size_t)(19 * 19 * Cin + 25 * Cin * Cout) * sizeof(float);
+            if (smem > 200 * 1024) return spiral_set_error(SPIRAL_EUNSUPPORTED, "layer-0 weights do not fit shared memory");
+            cudaFuncSetAttribute(conv0_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            conv0_kernel<1><<<batch * (Ho / 8) * (Ho / 8), 256, smem, st>>>(x, (const float *)W.conv_w[0],
+                                                                            (const float *)W.conv_b[0], out, batch, H, Cin, Cout);
+        } else {
+            const float *in = (const float *)(ws + pl.act_off[l - 1]);
+            const float *isc = (const float *)(ws + pl.scale_off[l - 1]);
+            const float *ish = (const float *)(ws + pl.shift_off[l - 1]);
+            dim3 grid(pl.mtiles[l], (Cout + 63) / 64);
+            conv_simt_kernel<<<grid, 256, 0, st>>>(in, isc, ish, (const float *)W.conv_w[l], (const float *)W.conv_b[l],
+                                                   out, bn ? part : nullptr, batch, H, Cin, Cout);
+        }
+        if (bn) {
+            bn_finalize_kernel<<<(Cout + 127) / 128, 128, 0, st>>>(part, pl.mtiles[l], Cout, (double)batch * Ho * Ho,
+                                                                    (const float *)W.bn_gamma[l], (const float *)W.bn_beta[l],
+                                                                    1e-3f, scale, shift,
+                                                                    bn_stats ? bn_stats + (size_t)l * 2 * maxC : nullptr);
+        } else {
+            fill_affine_kernel<<<(Cout + 127) / 128, 128, 0, st>>>(scale, shift, Cout, 1.0f, 0.0f);
+        }
+    }
+    const int last = d->n_layers - 1;
+    dense_sigmoid_kernel<<<(batch * 32 + 127) / 128, 128, 0, st>>>(
+        (const float *)(ws + pl.act_off[last]), (const float *)(ws + pl.scale_off[last]),
+        (const float *)(ws + pl.shift_off[last]), (const float *)W.dense_w, (const float *)W.dense_b, logits, probs,
+        batch, pl.Cout[last]);
+    const cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? SPIRAL_OK : spiral_cuda_error(e, "spiral_disc_forward(fp32)");
+}
+
+}  // namespace spiral
+
+using namespace spiral;
+
+extern "C" int spiral_disc_create(const SpiralDiscCfg *cfg, SpiralDisc **out)
+{
+    if (!cfg || !out) return spiral_set_error(SPIRAL_EINVAL, "spiral_disc_create: null argument");
+    *out = nullptr;
+    if (cfg->abi_version != SPIRAL_ABI_VERSION) return spiral_set_error(SPIRAL_EINVAL, "ABI version mismatch");
+    if (cfg->screen_size != 64) return spiral_set_error(SPIRAL_EUNSUPPORTED, "screen_size must be 64");
+    if (cfg->disc_dim < 8 || (cfg->disc_dim & (cfg->disc_dim - 1)))
+        return spiral_set_error(SPIRAL_EUNSUPPORTED, "disc_dim must be a power of two >= 8 (got %d)", cfg->disc_dim);
+    if (cfg->in_channels < 1 || cfg->in_channels > 8) return spiral_set_error(SPIRAL_EINVAL, "in_channels must be in 1..8");
+    if (cfg->max_batch < 1) return spiral_set_error(SPIRAL_EINVAL, "max_batch must be >= 1");
+    if (cfg->precision < 0 || cfg->precision > 2) return spiral_set_error(SPIRAL_EINVAL, "precision must be 0, 1 or 2");
+    SpiralDisc *d = new (std::nothrow) SpiralDisc();
+    if (!d) return spiral_set_error(SPIRAL_EINVAL, "out of host memory");
+    memset(d, 0, sizeof(*d));
+    d->cfg = *cfg;
+    d->n_layers = 6;       // int(log2(64))
+    if (cfg->precision != 0) {
+        const int rc = disc_tc_init(d);
+        if (rc != SPIRAL_OK) { delete d; return rc; }
+    }
+    *out = d;
+    return SPIRAL_OK;
+}
+
+extern "C" int spiral_disc_destroy(SpiralDisc *d)
+{
+    if (!d) return SPIRAL_OK;
+    delete d;
+    return SPIRAL_OK;
+}
+
+extern "C" int64_t spiral_disc_workspace_bytes(const SpiralDisc *d, int32_t batch)
+{
+    if (!d || batch < 1) return -1;
+    DiscPlan pl;
+    disc_plan(d, batch, &pl);
+    size_t total = pl.simt_bytes;
+    if (d->cfg.precision != 0) total += disc_tc_workspace_bytes(d, batch);
+    return (int64_t)total;
+}
+
+extern "C" int spiral_disc_load_weights(SpiralDisc *d, const SpiralDiscWeights *w, void *workspace, void *stream)
+{
+    SPIRAL_REQUIRE(d); SPIRAL_REQUIRE(w); SPIRAL_REQUIRE(workspace);
+    for (int l = 0; l < d->n_layers; l++) {
+        if (!w->conv_w[l] || !w->conv_b[l]) return spiral_set_error(SPIRAL_EINVAL, "missing conv weights for layer %d", l);
+        if (l > 0 && d->cfg.batch_norm && (!w->bn_gamma[l] || !w->bn_beta[l]))
+            return spiral_set_error(SPIRAL_EINVAL, "missing batch-norm parameters for layer %d", l);
+    }
+    if (!w->dense_w || !w->dense_b) return spiral_set_error(SPIRAL_EINVAL, "missing dense weights");
+    d->w = *w;
+    d->have_weights = 1;
+    if (d->cfg.precision != 0) return disc_tc_pack_weights(d, (char *)workspace, (cudaStream_t)stream);
+    return SPIRAL_OK;
+}
+
+extern "C" int spiral_disc_forward(SpiralDisc *d, const float *x, int32_t batch, float *logits, float *probs,
+                                   float *bn_stats, void *workspace, void *stream)
+{
+    SPIRAL_REQUIRE(d); SPIRAL_REQUIRE(x); SPIRAL_REQUIRE(logits); SPIRAL_REQUIRE(workspace);
+    if (!d->have_weights) return spiral_set_error(SPIRAL_EINVAL, "spiral_disc_forward: call spiral_disc_load_weights first");
+    if (batch < 1 || batch > d->cfg.max_batch) return spiral_set_error(SPIRAL_EINVAL, "batch %d outside 1..max_batch=%d", batch, d->cfg.max_batch);
+    if (d->cfg.precision == 0)
+        return disc_forward_simt(d, x, batch, logits, probs, bn_stats, (char *)workspace, (cudaStream_t)stream);
+    return disc_tc_forward(d, x, batch, logits, probs, bn_stats, (char *)workspace, (cudaStream_t)stream);
+}

@@ -1,0 +1,45 @@
+// disc.cuh -- host object of the discriminator, shared by disc.cu (fp32 SIMT path, common
+// kernels) and disc_tc.cu (tcgen05 implicit-GEMM path).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/spiral_b200.h"
+#include "common.h"
+
+struct SpiralDisc {
+    SpiralDiscCfg cfg;
+    int n_layers;
+    int have_weights;
+    SpiralDiscWeights w;
+    void *tc;                 // opaque state of the tensor-core path (disc_tc.cu)
+};
+
+namespace spiral {
+
+struct DiscPlan {
+    int H[SPIRAL_DISC_MAX_LAYERS], Cin[SPIRAL_DISC_MAX_LAYERS], Cout[SPIRAL_DISC_MAX_LAYERS];
+    int mtiles[SPIRAL_DISC_MAX_LAYERS];
+    size_t act_off[SPIRAL_DISC_MAX_LAYERS], part_off[SPIRAL_DISC_MAX_LAYERS];
+    size_t scale_off[SPIRAL_DISC_MAX_LAYERS], shift_off[SPIRAL_DISC_MAX_LAYERS];
+    size_t simt_bytes;
+};
+
+size_t disc_align(size_t v);
+void disc_plan(const SpiralDisc *d, int batch, DiscPlan *pl);
+
+// kernels shared by both paths
+__global__ void bn_finalize_kernel(const float *partial, int n_part, int Cout, double count, const float *gamma,
+                                   const float *beta, float eps, float *scale, float *shift, float *stats);
+__global__ void fill_affine_kernel(float *scale, float *shift, int n, float sc, float sh);
+__global__ void dense_sigmoid_kernel(const float *in, const float *in_scale, const float *in_shift, const float *w,
+                                     const float *bias, float *logits, float *probs, int B, int C);
+
+// tensor-core path (disc_tc.cu)
+int disc_tc_init(SpiralDisc *d);
+size_t disc_tc_workspace_bytes(const SpiralDisc *d, int batch);
+int disc_tc_pack_weights(SpiralDisc *d, char *ws, cudaStream_t st);
+int disc_tc_forward(SpiralDisc *d, const float *x, int batch, float *logits, float *probs, float *bn_stats,
+                    char *ws, cudaStream_t st);
+
+}  // namespace spiral

@@ -1,0 +1,877 @@
+// raster.cu -- K1: batched brush-stroke rasteriser for sm_100a.
+//
+// Replaces, for B canvases at once, what the reference does one canvas per process through
+// SWIG: envs/mnist.py:107-222 (action decode, Bezier stroke expansion into stroke_to events) and
+// beneath it libmypaint 1.3.0 (mypaint_brush_stroke_to state machine, rng-double, draw_dab,
+// render_dab_mask, BlendMode_Normal) and mypaint 1.2.1's rgbu16 -> rgbu8 read-back.
+//
+// Two kernels per env step:
+//   expand_kernel    one THREAD per canvas: the brush state machine is a strictly serial chain per
+//                    canvas (dab i's position/radius depend on the filtered speed, the partial-dab
+//                    carry and the RNG position after dab i-1), so parallelism comes from the
+//                    batch.  Emits "pending dabs" (8 floats) into a caller-owned list.
+//   composite_kernel one CTA per canvas: the 64x64 fix15 tile lives in shared memory (planar
+//                    u16 R,G,B, rows padded against bank conflicts) for ALL dabs of the step;
+//                    8 warps own 32x16-pixel regions and walk the dab list independently (dab
+//                    order only matters per pixel), finalising 32 dabs lane-parallel at a time.
+//                    HBM traffic is the 128-bit coalesced tile load, tile store and the fused
+//                    fix15 -> uint8 (dither) -> observation epilogue.
+//
+// Arithmetic is bit-exact against oracle/paint_oracle.c in PO_MATH_DET mode: compile with
+// --fmad=false, transcendental functions from detmath.cuh.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "detmath.cuh"
+#include "raster.cuh"
+
+namespace spiral {
+
+using detmath::det_exp;
+using detmath::det_expf;
+using detmath::det_hypotf;
+using detmath::det_log;
+
+// ------------------------------------------------------------------------------------------
+// libmypaint mapping (mypaint-mapping.c: mypaint_mapping_calculate), inputs pressure/speed1/speed2
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float map_eval(const MapDev &m, const float (&in)[kIn], float base)
+{
+    float result = base;
+#pragma unroll
+    for (int j = 0; j < kIn; j++) {
+        const int n = m.n[j];
+        if (n) {
+            const float x = in[j];
+            float x0 = m.x[j][0], y0 = m.y[j][0];
+            float x1 = m.x[j][1], y1 = m.y[j][1];
+            float inv = m.inv[j][0];
+            for (int i = 2; i < n && x > x1; i++) {
+                x0 = x1;
+                y0 = y1;
+                x1 = m.x[j][i];
+                y1 = m.y[j][i];
+                inv = m.inv[j][i - 1];
+            }
+            float y;
+            if (x0 == x1 || y0 == y1) {
+                y = y0;
+            } else {
+                const float num = y1 * (x - x0) + y0 * (x1 - x);
+                // dividing by a power of two == multiplying by its reciprocal (both exact scalings)
+                y = (inv != 0.0f) ? num * inv : num / (x1 - x0);
+            }
+            result += y;
+        }
+    }
+    return result;
+}
+
+// exp_decay (mypaint-brush.c): returns float
+__device__ __forceinline__ float exp_decay(float T_const, float t)
+{
+    if ((double)T_const <= 0.001) return 0.0f;
+    return (float)det_exp((double)(-t / T_const));
+}
+__device__ __forceinline__ float one_minus_decay(float T_const, float t)
+{
+    return (float)(1.0 - (double)exp_decay(T_const, t));
+}
+
+// ------------------------------------------------------------------------------------------
+// rng-double.c (Knuth ranf_array, KK=10, LL=7, QUALITY=19): one output block = 10 values; the
+// next block is the state 19 recurrence steps later.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ double mod_sum(double x, double y)
+{
+    const double s = x + y;              // in [0, 2)
+    return s >= 1.0 ? s - 1.0 : s;       // == s - (int)s
+}
+
+template <int NT>
+struct Rng {
+    double (*blk)[NT];   // shared [10][NT]
+    int tid;
+    int pos;
+    __device__ __forceinline__ void refill()
+    {
+        double a[29];
+#pragma unroll
+        for (int j = 0; j < 10; j++) a[j] = blk[j][tid];
+#pragma unroll
+        for (int j = 10; j < 29; j++) a[j] = mod_sum(a[j - 10], a[j - 7]);
+#pragma unroll
+        for (int j = 0; j < 10; j++) blk[j][tid] = a[19 + j];
+        pos = 0;
+    }
+    __device__ __forceinline__ double next()
+    {
+        if (pos == 10) refill();
+        return blk[pos++][tid];
+    }
+    // helpers.c rand_gauss
+    __device__ __forceinline__ float gauss()
+    {
+        double sum = 0.0;
+        sum += next();
+        sum += next();
+        sum += next();
+        sum += next();
+        return (float)(sum * 1.73205080757 - 3.46410161514);
+    }
+};
+
+// ------------------------------------------------------------------------------------------
+// K1a: stroke expansion
+// ------------------------------------------------------------------------------------------
+struct Brush {
+    float X, Y, P, partial, AR, AX, AY, s1, s2;
+    int flags;
+    // settings_value[] of the last update_states call
+    float v_opaque, v_opaque_mul, v_rlog, v_hard, v_rbr, v_obr, v_aa;
+};
+
+constexpr int kExpandThreads = 32;
+
+__device__ __forceinline__ float clamp_radius(float r)
+{
+    if ((double)r < 0.2) r = (float)0.2;
+    if ((double)r > 1000.0) r = 1000.0f;
+    return r;
+}
+
+// mypaint-brush.c count_dabs_to
+__device__ __forceinline__ float count_dabs_to(const EnvParams &P, Brush &S, float base_radius_raw,
+                                               float x, float y, float dt)
+{
+    if (S.AR == 0.0f) S.AR = base_radius_raw;
+    S.AR = clamp_radius(S.AR);
+    const float base_radius = clamp_radius(base_radius_raw);
+    const float xx = x - S.X;
+    const float yy = y - S.Y;
+    const float dist = det_hypotf(xx, yy);
+    const bool init = (S.flags & 2) != 0;
+    const float res1 = dist / S.AR * (init ? P.dabs_actual : 0.0f);
+    const float res2 = dist / base_radius * (init ? P.dabs_basic : 0.0f);
+    const float res3 = dt * (init ? P.dabs_second : 0.0f);
+    return res1 + res2 + res3;
+}
+
+// mypaint-brush.c update_states_and_setting_values, live state only (the stroke / direction /
+// custom / norm_d{x,y}_slow states feed inputs no supported mapping reads).
+template <int NT>
+__device__ __forceinline__ void update_states(const EnvParams &P, Brush &S, Rng<NT> &rng,
+                                              float base_radius, float rlog_base, float step_dx,
+                                              float step_dy, float step_dpressure, float step_dtime)
+{
+    if (step_dtime < 0.0f) step_dtime = 0.001f;
+    else if (step_dtime == 0.0f) step_dtime = 0.001f;
+
+    S.X += step_dx;
+    S.Y += step_dy;
+    S.P += step_dpressure;
+    if (S.P <= 0.0f) S.P = 0.0f;
+
+    const float norm_dx = step_dx / step_dtime / base_radius;
+    const float norm_dy = step_dy / step_dtime / base_radius;
+    const float norm_speed = det_hypotf(norm_dx, norm_dy);
+
+    float in[kIn];
+    in[0] = S.P * 1.0f;   // * expf(pressure_gain_log = 0)
+    in[1] = 0.0f;
+    in[2] = 0.0f;
+    if (P.uses_speed1)
+        in[1] = (float)(det_log((double)(P.sp_gamma[0] + S.s1)) * (double)P.sp_m[0] + (double)P.sp_q[0]);
+    if (P.uses_speed2)
+        in[2] = (float)(det_log((double)(P.sp_gamma[1] + S.s2)) * (double)P.sp_m[1] + (double)P.sp_q[1]);
+    (void)rng.next();     // inputs[RANDOM]: consumed on every call
+
+    S.v_opaque = map_eval(P.dyn[0], in, P.dyn[0].base);
+    S.v_opaque_mul = map_eval(P.dyn[1], in, P.dyn[1].base);
+    // the size action rewrites the base value of radius_logarithmic every step (mnist.py:134-135)
+    S.v_rlog = map_eval(P.dyn[2], in, rlog_base);
+    S.v_hard = map_eval(P.dyn[3], in, P.dyn[3].base);
+    S.v_rbr = map_eval(P.dyn[4], in, P.dyn[4].base);
+    S.v_obr = map_eval(P.dyn[5], in, P.dyn[5].base);
+    const float v_s1slow = map_eval(P.dyn[6], in, P.dyn[6].base);
+    const float v_s2slow = map_eval(P.dyn[7], in, P.dyn[7].base);
+    S.v_aa = map_eval(P.dyn[8], in, P.dyn[8].base);
+
+    // slow_tracking_per_dab == 0  =>  fac = 1.0 - 0.0
+    {
+        const float fac = 1.0f;
+        S.AX += (S.X - S.AX) * fac;
+        S.AY += (S.Y - S.AY) * fac;
+    }
+    if (P.uses_speed1) {
+        const float fac = one_minus_decay(v_s1slow, step_dtime);
+        S.s1 += (norm_speed - S.s1) * fac;
+    }
+    if (P.uses_speed2) {
+        const float fac = one_minus_decay(v_s2slow, step_dtime);
+        S.s2 += (norm_speed - S.s2) * fac;
+    }
+    S.AR = clamp_radius(det_expf(S.v_rlog));
+    S.flags |= 2;
+}
+
+struct StepSetup {
+    // decoded action (mnist.py:107-130)
+    double x, y, c_x, c_y, pressure;
+    int jump;
+    // curve() locals (mnist.py:173-190)
+    double cx, cy, sx, sy, x1, y1, x2, y2, bx, by;
+    double entry_p, midpoint_p, prange1, prange2, head, tail, tail_length;
+    int head_range, tail_range;
+    int n_events;
+    bool curved;
+};
+
+__device__ __forceinline__ void curve_point(const StepSetup &st, int i, double &px, double &py)
+{
+    // mypaint_utils.py:5-11 point_on_curve_1
+    const double ratio = (double)i / 100.0;
+    const double x3 = st.sx + st.x1 * ratio, y3 = st.sy + st.y1 * ratio;
+    const double x4 = st.cx + st.x2 * ratio, y4 = st.cy + st.y2 * ratio;
+    const double x5 = x4 - x3, y5 = y4 - y3;
+    px = x3 + x5 * ratio;
+    py = y3 + y5 * ratio;
+}
+
+__global__ void __launch_bounds__(kExpandThreads)
+expand_kernel(const __grid_constant__ EnvParams P, const int32_t *__restrict__ actions,
+              float *__restrict__ brush_state, double *__restrict__ env_state,
+              float *__restrict__ dabs, int32_t *__restrict__ dab_count, int32_t *__restrict__ status)
+{
+    constexpr int NT = kExpandThreads;
+    __shared__ double s_rng[10][NT];
+    const int tid = threadIdx.x;
+    const int b = blockIdx.x * NT + tid;
+    if (b >= P.B) return;
+
+    float *bs = brush_state + (size_t)b * kBrushFloats;
+    double *es = env_state + (size_t)b * kEnvDoubles;
+    Brush S;
+    S.X = bs[BS_X]; S.Y = bs[BS_Y]; S.P = bs[BS_PRESSURE]; S.partial = bs[BS_PARTIAL_DABS];
+    S.AR = bs[BS_ACTUAL_RADIUS]; S.AX = bs[BS_ACTUAL_X]; S.AY = bs[BS_ACTUAL_Y];
+    S.s1 = bs[BS_SPEED1_SLOW]; S.s2 = bs[BS_SPEED2_SLOW];
+    S.flags = __float_as_int(bs[BS_FLAGS]);
+    const int step = __float_as_int(bs[BS_STEP]);
+    S.v_opaque = S.v_opaque_mul = S.v_rlog = S.v_hard = S.v_rbr = S.v_obr = S.v_aa = 0.0f;
+    Rng<NT> rng;
+    rng.blk = s_rng;
+    rng.tid = tid;
+    rng.pos = __float_as_int(bs[BS_RNG_POS]);
+#pragma unroll
+    for (int j = 0; j < 10; j++) s_rng[j][tid] = es[ES_RNG0 + j];
+
+    // ---- action decode (mnist.py:107-135) ----
+    const int32_t *ac = actions + (size_t)b * P.K;
+    StepSetup st;
+    const int L = P.L;
+    st.x = P.lin[0]; st.y = P.lin[0]; st.c_x = P.lin[0]; st.c_y = P.lin[0];
+    st.pressure = P.default_pressure;
+    st.jump = 0;
+    int size_idx = 8;
+    int color_idx = 0;
+    if (P.idx_end >= 0) { const int a = ac[P.idx_end]; st.x = P.lin[a % L]; st.y = P.lin[a / L]; }
+    if (P.idx_control >= 0) { const int a = ac[P.idx_control]; st.c_x = P.lin[a % L]; st.c_y = P.lin[a / L]; }
+    if (P.idx_pressure >= 0) st.pressure = P.pressures[ac[P.idx_pressure]];
+    if (P.idx_size >= 0) size_idx = ac[P.idx_size];
+    if (P.idx_jump >= 0) st.jump = ac[P.idx_jump];
+    if (P.idx_color >= 0) color_idx = ac[P.idx_color];
+    else if (P.colorize) color_idx = step % P.n_colors;
+    const float base_radius = P.base_radius[size_idx];     // expf(base radius_logarithmic), unclamped
+    const float rlog_base = P.base_rlog[size_idx];         // base value of radius_logarithmic this step
+
+    // ---- pre-positioning event and stroke geometry (mnist.py:137-160) ----
+    const bool have_start = es[ES_HAVE_START] != 0.0;
+    double s_x = es[ES_SX], s_y = es[ES_SY];
+    double entry_pressure = es[ES_ENTRY_PRESSURE];
+    double pressure = st.pressure;
+    if (!have_start) { pressure = 0; s_x = 0; s_y = 0; }
+    else if (P.idx_jump >= 0 && st.jump) pressure = 0;
+    st.curved = !(P.idx_control < 0 || pressure == 0);
+    st.sx = s_x; st.sy = s_y;
+    double cur_pressure_var = pressure;     // `pressure` variable inside curve()
+    if (st.curved) {
+        // _line_settings (mnist.py:270-278)
+        double p1 = entry_pressure;
+        const double p2 = (entry_pressure + pressure) / 2;
+        const double p3 = pressure;
+        if (P.head == 0.0001) p1 = p2;
+        st.prange1 = p2 - p1;
+        st.prange2 = p3 - p2;
+        st.entry_p = p1;
+        st.midpoint_p = p2;
+        const double mx = (s_x + st.x) / 2.0, my = (s_y + st.y) / 2.0;
+        double dx = st.c_x - mx, dy = st.c_y - my;
+        double length = sqrt(dx * dx + dy * dy);
+        double nx, ny;
+        if (length == 0.0) { nx = 0.0; ny = 0.0; } else { nx = dx / length; ny = dy / length; }
+        const double l2x = length * 2;
+        st.cx = mx + nx * l2x;
+        st.cy = my + ny * l2x;
+        st.x1 = st.cx - s_x; st.y1 = st.cy - s_y;
+        st.x2 = st.x - st.cx; st.y2 = st.y - st.cy;
+        st.head = 100 * P.head;
+        st.head_range = (int)st.head + 1;
+        st.tail = 100 * P.tail;
+        st.tail_range = (int)st.tail + 1;
+        st.tail_length = 100 - st.tail;
+        double px, py;
+        curve_point(st, 1, px, py);
+        dx = px - s_x; dy = py - s_y;
+        length = sqrt(dx * dx + dy * dy);
+        if (length == 0.0) { nx = 0.0; ny = 0.0; } else { nx = dx / length; ny = dy / length; }
+        st.bx = s_x + nx * 0.25;
+        st.by = s_y + ny * 0.25;
+        st.n_events = 102;
+    } else {
+        st.n_events = 2;
+    }
+
+    float *my_dabs = dabs + (size_t)b * P.max_dabs * kDabFloats;
+    int n_dabs = 0;
+    bool overflow = false;
+
+    // ---- flattened event / dab loop: one update_states per iteration ----
+    int ev = 0;
+    bool in_event = false;
+    int split = 0;                 // stroke_to's "pressure after zero pressure" recursion
+    float ex = 0, ey = 0, ep = 0;  // raw event (float32 at the SWIG boundary)
+    double edt = 0;
+    float tx = 0, ty = 0, tp = 0;  // target after slow tracking
+    double dtime_left = 0;
+    float dabs_moved = 0, dabs_todo = 0;
+
+    while (true) {
+        if (!in_event) {
+            if (ev >= st.n_events) break;
+            if (split == 2) {
+                // second half of the recursion: same x, y, original pressure, dtime = 0.0001
+                edt = 0.0001;
+                split = 0;
+            } else {
+                double px, py, pp;
+                if (ev == 0) {
+                    px = s_x; py = s_y; pp = pressure; edt = 0.1;
+                } else if (!st.curved) {
+                    px = st.x; py = st.y; pp = pressure; edt = 1.0;
+                } else if (ev == 1) {
+                    px = st.bx; py = st.by; pp = st.entry_p; edt = 0.1;
+                } else {
+                    const int i = ev - 1;
+                    curve_point(st, i, px, py);
+                    if (i < st.head_range) {
+                        cur_pressure_var = fabs((double)i / st.head * st.prange1 + st.entry_p);
+                        pp = cur_pressure_var;
+                    } else if (i < st.tail_range) {
+                        pp = st.midpoint_p;
+                    } else {
+                        cur_pressure_var = fabs(((double)i - st.tail) / st.tail_length * st.prange2 + st.midpoint_p);
+                        pp = cur_pressure_var;
+                    }
+                    edt = 0.1;
+                }
+                ex = (float)px; ey = (float)py; ep = (float)pp;
+                if (ep <= 0.0f) ep = 0.0f;
+                if (edt > 0.100 && ep != 0.0f && S.P == 0.0f) split = 1;
+            }
+            float evp = ep;
+            double dt = edt;
+            if (split == 1) { evp = 0.0f; dt = edt - 0.0001; }
+            // slow position tracking
+            {
+                const float fac = one_minus_decay(P.slow_tracking, (float)(100.0 * dt));
+                tx = S.X + (ex - S.X) * fac;
+                ty = S.Y + (ey - S.Y) * fac;
+            }
+            tp = evp;
+            dabs_moved = S.partial;
+            dabs_todo = count_dabs_to(P, S, base_radius, tx, ty, (float)dt);
+            if (S.flags & 1) {
+                // first event after reset: initialise only (mypaint-brush.c reset_requested)
+                S.flags &= ~1;
+                S.X = tx; S.Y = ty; S.P = tp;
+                S.partial = 0; S.AR = 0; S.s1 = 0; S.s2 = 0;
+                S.AX = S.X; S.AY = S.Y;
+                if (split == 1) split = 2; else ev++;
+                continue;
+            }
+            dtime_left = dt;
+            in_event = true;
+        }
+
+        const bool is_dab = (dabs_moved + dabs_todo >= 1.0f);
+        float step_dx, step_dy, step_dp, step_dtime;
+        if (is_dab) {
+            float step_ddab;
+            if (dabs_moved > 0.0f) {
+                step_ddab = (float)(1.0 - (double)dabs_moved);
+                dabs_moved = 0.0f;
+            } else {
+                step_ddab = 1.0f;
+            }
+            const float frac = step_ddab / dabs_todo;
+            step_dx = frac * (tx - S.X);
+            step_dy = frac * (ty - S.Y);
+            step_dp = frac * (tp - S.P);
+            step_dtime = (float)((double)frac * (dtime_left - 0.0));
+        } else {
+            step_dx = tx - S.X;
+            step_dy = ty - S.Y;
+            step_dp = tp - S.P;
+            step_dtime = (float)dtime_left;
+        }
+
+        update_states<NT>(P, S, rng, base_radius, rlog_base, step_dx, step_dy, step_dp, step_dtime);
+
+        if (is_dab) {
+            // prepare_and_draw_dab, state-machine half (RNG draws, position jitter)
+            float opq = S.v_opaque;
+            if (opq < 0.0f) opq = 0.0f;
+            opq = opq * S.v_opaque_mul;
+            opq = opq > 1.0f ? 1.0f : (opq < 0.0f ? 0.0f : opq);
+            float x = S.AX, y = S.AY;
+            if (S.v_obr != 0.0f) {
+                float amp = S.v_obr;
+                if (amp < 0.0f) amp = 0.0f;
+                x += rng.gauss() * amp * base_radius;
+                y += rng.gauss() * amp * base_radius;
+            }
+            float rl = S.v_rlog;
+            const bool has_rand = S.v_rbr != 0.0f;
+            if (has_rand) rl += rng.gauss() * S.v_rbr;
+            if (opq != 0.0f) {
+                // conservative cull against tile (0,0); composite_kernel does the exact test
+                const float R = S.AR * P.cull_factor + 0.5f * fabsf(S.v_aa) + 3.0f;
+                if (x + R >= 0.0f && x - R < 64.0f && y + R >= 0.0f && y - R < 64.0f) {
+                    if (n_dabs < P.max_dabs) {
+                        float4 *d = reinterpret_cast<float4 *>(my_dabs + (size_t)n_dabs * kDabFloats);
+                        d[0] = make_float4(x, y, rl, S.AR);
+                        d[1] = make_float4(opq, S.v_hard, S.v_aa, has_rand ? 1.0f : 0.0f);
+                        n_dabs++;
+                    } else {
+                        overflow = true;
+                    }
+                }
+            }
+            dtime_left -= (double)step_dtime;
+            dabs_todo = count_dabs_to(P, S, base_radius, tx, ty, (float)dtime_left);
+        } else {
+            S.partial = dabs_moved + dabs_todo;
+            in_event = false;
+            if (split == 1) split = 2; else ev++;
+        }
+    }
+
+    // ---- write back ----
+    bs[BS_X] = S.X; bs[BS_Y] = S.Y; bs[BS_PRESSURE] = S.P; bs[BS_PARTIAL_DABS] = S.partial;
+    bs[BS_ACTUAL_RADIUS] = S.AR; bs[BS_ACTUAL_X] = S.AX; bs[BS_ACTUAL_Y] = S.AY;
+    bs[BS_SPEED1_SLOW] = S.s1; bs[BS_SPEED2_SLOW] = S.s2;
+    bs[BS_FLAGS] = __int_as_float(S.flags);
+    bs[BS_STEP] = __int_as_float(step + 1);
+    bs[BS_RNG_POS] = __int_as_float(rng.pos);
+#pragma unroll
+    for (int j = 0; j < 10; j++) es[ES_RNG0 + j] = s_rng[j][tid];
+    es[ES_SX] = st.x;
+    es[ES_SY] = st.y;
+    es[ES_ENTRY_PRESSURE] = st.curved ? cur_pressure_var : pressure;
+    es[ES_HAVE_START] = 1.0;
+    dab_count[2 * b] = n_dabs;
+    dab_count[2 * b + 1] = color_idx;
+    if (overflow) atomicOr(status, 1);
+}
+
+// ------------------------------------------------------------------------------------------
+// K1b: composite
+// ------------------------------------------------------------------------------------------
+constexpr int kCompThreads = 256;
+constexpr int kRowWords = 33;                 // 64 px * u16 = 32 words, +1 pad word
+constexpr int kPlaneWords = kTile * kRowWords;
+
+struct FinalDab {
+    float x, y, radius, hardness;
+    float one_over_r2, r_aa_start, seg1_slope, seg2_offset, seg2_slope;
+    int opacity;          // 0 => rejected
+    int x0, x1, y0, y1;   // bbox clipped to the tile
+};
+
+// prepare_and_draw_dab's second half + draw_dab_internal + render_dab_mask's per-dab constants
+__device__ __forceinline__ FinalDab finalize_dab(const float4 a, const float4 b)
+{
+    FinalDab f;
+    float x = a.x, y = a.y;
+    float radius = a.w;          // ACTUAL_RADIUS
+    float opq = b.x;
+    if (b.w != 0.0f) {
+        radius = clamp_radius(det_expf(a.z));
+        float ac = a.w / radius;
+        ac = ac * ac;
+        if (ac <= 1.0f) opq *= ac;
+    }
+    float hardness = b.y;
+    hardness = hardness > 1.0f ? 1.0f : (hardness < 0.0f ? 0.0f : hardness);
+    const float fadeout = (float)((double)radius * (1.0 - (double)hardness));
+    const float min_fadeout = b.z;
+    if (fadeout < min_fadeout) {
+        const float opt = (float)((double)radius - (1.0 - (double)hardness) * (double)radius / 2.0);
+        const float hardness_new = (float)(((double)opt - ((double)min_fadeout / 2.0)) /
+                                           ((double)opt + ((double)min_fadeout / 2.0)));
+        const float radius_new = (float)((double)min_fadeout / (1.0 - (double)hardness_new));
+        hardness = hardness_new;
+        radius = radius_new;
+    }
+    // draw_dab_internal
+    opq = opq > 1.0f ? 1.0f : (opq < 0.0f ? 0.0f : opq);
+    hardness = hardness > 1.0f ? 1.0f : (hardness < 0.0f ? 0.0f : hardness);
+    f.x = x; f.y = y; f.radius = radius; f.hardness = hardness;
+    f.opacity = 0;
+    f.x0 = 1; f.x1 = 0; f.y0 = 1; f.y1 = 0;
+    f.one_over_r2 = 0; f.r_aa_start = 0; f.seg1_slope = 0; f.seg2_offset = 0; f.seg2_slope = 0;
+    if (radius < 0.1f || hardness == 0.0f || opq == 0.0f) return f;
+    const float r_fringe = radius + 1.0f;
+    int x0 = (int)floorf(x - r_fringe), y0 = (int)floorf(y - r_fringe);
+    int x1 = (int)floorf(x + r_fringe), y1 = (int)floorf(y + r_fringe);
+    if (x0 > kTile - 1 || x1 < 0 || y0 > kTile - 1 || y1 < 0) return f;   // tile (0,0) untouched
+    if (x0 < 0) x0 = 0;
+    if (y0 < 0) y0 = 0;
+    if (x1 > kTile - 1) x1 = kTile - 1;
+    if (y1 > kTile - 1) y1 = kTile - 1;
+    f.x0 = x0; f.x1 = x1; f.y0 = y0; f.y1 = y1;
+    f.opacity = (int)(unsigned short)(1.0f * opq * 32768.0f);
+    f.seg1_slope = -(1.0f / hardness - 1.0f);
+    f.seg2_offset = hardness / (1.0f - hardness);
+    f.seg2_slope = -hardness / (1.0f - hardness);
+    f.one_over_r2 = 1.0f / (radius * radius);
+    float ras = (radius > 1.0f) ? (radius - 1.0f) : 0.0f;
+    ras *= ras / 1.0f;
+    f.r_aa_start = ras;
+    return f;
+}
+
+// mypaint-tiled-surface.c calculate_rr_antialiased / calculate_rr with aspect_ratio == 1
+__device__ __forceinline__ float dab_rr(const EnvParams &P, int xp, int yp, float x, float y,
+                                        float one_over_radius2, float r_aa_start, bool aa)
+{
+    const float cs = P.cs, sn = P.sn;
+    if (!aa) {
+        const float yy = ((float)yp + 0.5f - y);
+        const float xx = ((float)xp + 0.5f - x);
+        const float yyr = (yy * cs - xx * sn) * 1.0f;
+        const float xxr = yy * sn + xx * cs;
+        return (yyr * yyr + xxr * xxr) * one_over_radius2;
+    }
+    const float pixel_right = x - (float)xp;
+    const float pixel_bottom = y - (float)yp;
+    const float pixel_center_x = pixel_right - 0.5f;
+    const float pixel_center_y = pixel_bottom - 0.5f;
+    const float pixel_left = pixel_right - 1.0f;
+    const float pixel_top = pixel_bottom - 1.0f;
+    float nearest_x, nearest_y, rr_near;
+    if (pixel_left < 0 && pixel_right > 0 && pixel_top < 0 && pixel_bottom > 0) {
+        nearest_x = 0;
+        nearest_y = 0;
+        rr_near = 0;
+    } else {
+        const float ltp_dot = pixel_center_x * cs + pixel_center_y * sn;
+        const float t = (P.l2 == 1.0f) ? ltp_dot : ltp_dot / P.l2;
+        nearest_x = cs * t;
+        nearest_y = sn * t;
+        nearest_x = nearest_x < pixel_left ? pixel_left : (nearest_x > pixel_right ? pixel_right : nearest_x);
+        nearest_y = nearest_y < pixel_top ? pixel_top : (nearest_y > pixel_bottom ? pixel_bottom : nearest_y);
+        const float yyr = (nearest_y * cs - nearest_x * sn) * 1.0f;
+        const float xxr = nearest_y * sn + nearest_x * cs;
+        const float r_near = (yyr * yyr + xxr * xxr);
+        rr_near = r_near * one_over_radius2;
+    }
+    if (rr_near > 1.0f) return rr_near;
+    // sign_point_in_line(pcx, pcy, cs, -sn) = (px - vx) * (-vy) - vx * (py - vy)
+    const float center_sign = (pixel_center_x - cs) * (sn) - (cs) * (pixel_center_y - (-sn));
+    float farthest_x, farthest_y;
+    if (center_sign < 0) {
+        farthest_x = nearest_x - sn * P.rad_area_1;
+        farthest_y = nearest_y + cs * P.rad_area_1;
+    } else {
+        farthest_x = nearest_x + sn * P.rad_area_1;
+        farthest_y = nearest_y - cs * P.rad_area_1;
+    }
+    const float yyr = (farthest_y * cs - farthest_x * sn) * 1.0f;
+    const float xxr = farthest_y * sn + farthest_x * cs;
+    const float r_far = (yyr * yyr + xxr * xxr);
+    const float rr_far = r_far * one_over_radius2;
+    if (r_far < r_aa_start) return (rr_far + rr_near) * 0.5f;
+    float visibilityNear = 1.0f - rr_near;
+    const float delta = rr_far - rr_near;
+    const float delta2 = 1.0f + delta;
+    visibilityNear /= delta2;
+    return 1.0f - visibilityNear;
+}
+
+template <int C>
+__global__ void __launch_bounds__(kCompThreads)
+composite_kernel(const __grid_constant__ EnvParams P, uint16_t *__restrict__ canvas,
+                 const float *__restrict__ dabs, const int32_t *__restrict__ dab_count,
+                 const uint16_t *__restrict__ dither, float *__restrict__ obs)
+{
+    __shared__ uint32_t s_px[3 * kPlaneWords];      // planar R,G,B; two u16 pixels per word
+    const int b = blockIdx.x;
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int warp = tid >> 5;
+
+    // ---- coalesced 128-bit tile load: uint4 = 2 RGBA pixels ----
+    const uint4 *src = reinterpret_cast<const uint4 *>(canvas + (size_t)b * kTile * kTile * 4);
+#pragma unroll
+    for (int k = 0; k < (kTile * kTile / 2) / kCompThreads; k++) {
+        const int i = tid + k * kCompThreads;          // pixel pair index
+        const uint4 v = src[i];
+        const int row = i >> 5, colw = i & 31;
+        const int w = row * kRowWords + colw;
+        s_px[w] = (v.x & 0xffffu) | (v.z << 16);                      // R0 | R1
+        s_px[kPlaneWords + w] = (v.x >> 16) | (v.z & 0xffff0000u);     // G0 | G1
+        s_px[2 * kPlaneWords + w] = (v.y & 0xffffu) | (v.w << 16);     // B0 | B1
+    }
+    __syncthreads();
+
+    const int n_dabs = dab_count[2 * b];
+    const int color_idx = dab_count[2 * b + 1];
+    const uint32_t col_r = P.colors[color_idx][0], col_g = P.colors[color_idx][1],
+                   col_b = P.colors[color_idx][2];
+    // this warp's 32x16 region
+    const int rx0 = (warp & 1) * 32, rx1 = rx0 + 31;
+    const int ry0 = (warp >> 1) * 16, ry1 = ry0 + 15;
+    uint16_t *s16 = reinterpret_cast<uint16_t *>(s_px);
+    const float4 *dl = reinterpret_cast<const float4 *>(dabs + (size_t)b * P.max_dabs * kDabFloats);
+
+    for (int base = 0; base < n_dabs; base += 32) {
+        const int mine = base + lane;
+        FinalDab f;
+        f.opacity = 0; f.x0 = 1; f.x1 = 0; f.y0 = 1; f.y1 = 0;
+        f.x = f.y = f.radius = f.hardness = f.one_over_r2 = f.r_aa_start = 0;
+        f.seg1_slope = f.seg2_offset = f.seg2_slope = 0;
+        if (mine < n_dabs) f = finalize_dab(__ldg(dl + 2 * mine), __ldg(dl + 2 * mine + 1));
+        // clip to this warp's region
+        int cx0 = max(f.x0, rx0), cx1 = min(f.x1, rx1), cy0 = max(f.y0, ry0), cy1 = min(f.y1, ry1);
+        const bool hit = f.opacity != 0 && cx0 <= cx1 && cy0 <= cy1;
+        unsigned mask = __ballot_sync(0xffffffffu, hit);
+        while (mask) {
+            const int j = __ffs(mask) - 1;
+            mask &= mask - 1;
+            const float x = __shfl_sync(0xffffffffu, f.x, j);
+            const float y = __shfl_sync(0xffffffffu, f.y, j);
+            const float radius = __shfl_sync(0xffffffffu, f.radius, j);
+            const float hardness = __shfl_sync(0xffffffffu, f.hardness, j);
+            const float oor2 = __shfl_sync(0xffffffffu, f.one_over_r2, j);
+            const float ras = __shfl_sync(0xffffffffu, f.r_aa_start, j);
+            const float s1s = __shfl_sync(0xffffffffu, f.seg1_slope, j);
+            const float s2o = __shfl_sync(0xffffffffu, f.seg2_offset, j);
+            const float s2s = __shfl_sync(0xffffffffu, f.seg2_slope, j);
+            const uint32_t opacity = (uint32_t)__shfl_sync(0xffffffffu, f.opacity, j);
+            const int bx0 = __shfl_sync(0xffffffffu, cx0, j);
+            const int bx1 = __shfl_sync(0xffffffffu, cx1, j);
+            const int by0 = __shfl_sync(0xffffffffu, cy0, j);
+            const int by1 = __shfl_sync(0xffffffffu, cy1, j);
+            const bool aa = radius < 3.0f;
+            const int w = bx1 - bx0 + 1;
+            const int n = w * (by1 - by0 + 1);
+            for (int p = lane; p < n; p += 32) {
+                const int ry = p / w;
+                const int xp = bx0 + (p - ry * w);
+                const int yp = by0 + ry;
+                const float rr = dab_rr(P, xp, yp, x, y, oor2, ras, aa);
+                // calculate_opa
+                const float fac = rr <= hardness ? s1s : s2s;
+                float opa = rr <= hardness ? 1.0f : s2o;
+                opa += rr * fac;
+                if (rr > 1.0f) opa = 0.0f;
+                const uint32_t opa_ = (uint32_t)(unsigned short)(opa * 32768.0f);
+                if (opa_) {
+                    // draw_dab_pixels_BlendMode_Normal (alpha stays 1<<15 on an opaque canvas)
+                    const uint32_t opa_a = opa_ * opacity / (1u << 15);
+                    const uint32_t opa_b = (1u << 15) - opa_a;
+                    const int idx = yp * (kRowWords * 2) + xp;
+                    uint32_t r = s16[idx], g = s16[2 * kPlaneWords + idx], bl = s16[4 * kPlaneWords + idx];
+                    r = (opa_a * col_r + opa_b * r) / (1u << 15);
+                    g = (opa_a * col_g + opa_b * g) / (1u << 15);
+                    bl = (opa_a * col_b + opa_b * bl) / (1u << 15);
+                    s16[idx] = (uint16_t)r;
+                    s16[2 * kPlaneWords + idx] = (uint16_t)g;
+                    s16[4 * kPlaneWords + idx] = (uint16_t)bl;
+                }
+            }
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+
+    // ---- tile store + fused read-back (pixops.cpp tile_convert_rgbu16_to_rgbu8, utils.py:3-5) ----
+    uint4 *dst = reinterpret_cast<uint4 *>(canvas + (size_t)b * kTile * kTile * 4);
+    float *ob = obs + (size_t)b * kTile * kTile * C;
+#pragma unroll
+    for (int k = 0; k < (kTile * kTile / 2) / kCompThreads; k++) {
+        const int i = tid + k * kCompThreads;
+        const int row = i >> 5, colw = i & 31;
+        const int w = row * kRowWords + colw;
+        const uint32_t R = s_px[w], G = s_px[kPlaneWords + w], Bv = s_px[2 * kPlaneWords + w];
+        uint4 v;
+        v.x = (R & 0xffffu) | (G << 16);
+        v.y = (Bv & 0xffffu) | (32768u << 16);
+        v.z = (R >> 16) | (G & 0xffff0000u);
+        v.w = (Bv >> 16) | (32768u << 16);
+        dst[i] = v;
+        uint32_t add0 = 16384u, add1 = 16384u;
+        if (P.dither) {
+            const uint32_t nz = __ldg(reinterpret_cast<const uint32_t *>(dither) + i);
+            add0 = nz & 0xffffu;
+            add1 = nz >> 16;
+        }
+        const uint32_t r0 = ((R & 0xffffu) * 255u + add0) >> 15, r1 = ((R >> 16) * 255u + add1) >> 15;
+        const uint32_t g0 = ((G & 0xffffu) * 255u + add0) >> 15, g1 = ((G >> 16) * 255u + add1) >> 15;
+        const uint32_t b0 = ((Bv & 0xffffu) * 255u + add0) >> 15, b1 = ((Bv >> 16) * 255u + add1) >> 15;
+        if (C == 1) {
+            // np.dot(rgb, [0.299, 0.587, 0.114]) in float64, cast to float32
+            double a0 = (double)r0 * 0.299;
+            a0 = a0 + (double)g0 * 0.587;
+            a0 = a0 + (double)b0 * 0.114;
+            double a1 = (double)r1 * 0.299;
+            a1 = a1 + (double)g1 * 0.587;
+            a1 = a1 + (double)b1 * 0.114;
+            reinterpret_cast<float2 *>(ob)[i] = make_float2((float)a0, (float)a1);
+        } else {
+            float2 *o2 = reinterpret_cast<float2 *>(ob + (size_t)i * 6);
+            o2[0] = make_float2((float)r0, (float)g0);
+            o2[1] = make_float2((float)b0, (float)r1);
+            o2[2] = make_float2((float)g1, (float)b1);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// reset, debug, reward
+// ------------------------------------------------------------------------------------------
+__global__ void reset_kernel(const __grid_constant__ EnvParams P, uint16_t *__restrict__ canvas,
+                             float *__restrict__ brush_state, double *__restrict__ env_state,
+                             float *__restrict__ obs)
+{
+    const size_t n_words = (size_t)P.B * kTile * kTile * 4 / 8;     // uint4 = 8 u16
+    const size_t n_obs = (size_t)P.B * kTile * kTile * P.C / 4;     // float4
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t w = 32768u | (32768u << 16);
+    for (size_t i = t; i < n_words; i += stride) reinterpret_cast<uint4 *>(canvas)[i] = make_uint4(w, w, w, w);
+    for (size_t i = t; i < n_obs; i += stride)
+        reinterpret_cast<float4 *>(obs)[i] = make_float4(255.0f, 255.0f, 255.0f, 255.0f);
+    for (size_t i = t; i < (size_t)P.B; i += stride) {
+        float *bs = brush_state + i * kBrushFloats;
+        for (int j = 0; j < kBrushFloats; j++) bs[j] = 0.0f;
+        bs[BS_FLAGS] = __int_as_float(1);
+        double *es = env_state + i * kEnvDoubles;
+        for (int j = 0; j < kEnvDoubles; j++) es[j] = 0.0;
+        for (int j = 0; j < 10; j++) es[ES_RNG0 + j] = P.rng_seed_block[j];
+        es[ES_ENTRY_PRESSURE] = P.entry_pressure0;
+    }
+}
+
+__global__ void debug_dabs_kernel(const __grid_constant__ EnvParams P, const float *__restrict__ dabs,
+                                  const int32_t *__restrict__ dab_count, float *__restrict__ out,
+                                  int32_t *__restrict__ out_count)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= P.B) return;
+    const float4 *dl = reinterpret_cast<const float4 *>(dabs + (size_t)b * P.max_dabs * kDabFloats);
+    float *o = out + (size_t)b * P.max_dabs * 5;
+    const int n = dab_count[2 * b];
+    int m = 0;
+    for (int i = 0; i < n; i++) {
+        const FinalDab f = finalize_dab(dl[2 * i], dl[2 * i + 1]);
+        if (f.opacity == 0) continue;
+        o[m * 5 + 0] = f.x; o[m * 5 + 1] = f.y; o[m * 5 + 2] = f.radius; o[m * 5 + 3] = f.hardness;
+        o[m * 5 + 4] = (float)f.opacity;
+        m++;
+    }
+    out_count[b] = m;
+}
+
+// envs/utils.py:7-8 l2 + mnist.py:237-239: one CTA per canvas, float64 accumulation like numpy
+__global__ void __launch_bounds__(256)
+l2_reward_kernel(const float *__restrict__ obs, const float *__restrict__ target,
+                 float *__restrict__ reward, int n)
+{
+    __shared__ double s_part[8];
+    const int b = blockIdx.x;
+    const float4 *o = reinterpret_cast<const float4 *>(obs + (size_t)b * n);
+    const float4 *t = reinterpret_cast<const float4 *>(target + (size_t)b * n);
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < n / 4; i += blockDim.x) {
+        const float4 a = o[i], c = t[i];
+        const double d0 = (double)a.x - (double)c.x, d1 = (double)a.y - (double)c.y;
+        const double d2 = (double)a.z - (double)c.z, d3 = (double)a.w - (double)c.w;
+        acc += d0 * d0 + d1 * d1 + d2 * d2 + d3 * d3;
+    }
+    for (int off = 16; off; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+    if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+        for (int i = 0; i < (int)(blockDim.x >> 5); i++) s += s_part[i];
+        reward[b] = (float)(1.0 - sqrt(s) / (double)n);
+    }
+}
+
+__global__ void detmath_kernel(const double *__restrict__ x, double *__restrict__ e,
+                               double *__restrict__ l, int n)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    e[i] = det_exp(x[i]);
+    l[i] = x[i] > 0 ? det_log(x[i]) : 0.0;
+}
+
+// ------------------------------------------------------------------------------------------
+// host launchers (called from api.cu)
+// ------------------------------------------------------------------------------------------
+cudaError_t launch_reset(const EnvParams &P, uint16_t *canvas, float *bs, double *es, float *obs,
+                         cudaStream_t st)
+{
+    const int blocks = 148 * 8;
+    reset_kernel<<<blocks, 256, 0, st>>>(P, canvas, bs, es, obs);
+    return cudaGetLastError();
+}
+cudaError_t launch_expand(const EnvParams &P, const int32_t *actions, float *bs, double *es,
+                          float *dabs, int32_t *dab_count, int32_t *status, cudaStream_t st)
+{
+    const int blocks = (P.B + kExpandThreads - 1) / kExpandThreads;
+    expand_kernel<<<blocks, kExpandThreads, 0, st>>>(P, actions, bs, es, dabs, dab_count, status);
+    return cudaGetLastError();
+}
+cudaError_t launch_composite(const EnvParams &P, uint16_t *canvas, const float *dabs,
+                             const int32_t *dab_count, const uint16_t *dither, float *obs,
+                             cudaStream_t st)
+{
+    if (P.C == 1)
+        composite_kernel<1><<<P.B, kCompThreads, 0, st>>>(P, canvas, dabs, dab_count, dither, obs);
+    else
+        composite_kernel<3><<<P.B, kCompThreads, 0, st>>>(P, canvas, dabs, dab_count, dither, obs);
+    return cudaGetLastError();
+}
+cudaError_t launch_debug_dabs(const EnvParams &P, const float *dabs, const int32_t *dab_count,
+                              float *out, int32_t *out_count, cudaStream_t st)
+{
+    debug_dabs_kernel<<<(P.B + 63) / 64, 64, 0, st>>>(P, dabs, dab_count, out, out_count);
+    return cudaGetLastError();
+}
+cudaError_t launch_l2_reward(const float *obs, const float *target, float *reward, int batch, int n,
+                             cudaStream_t st)
+{
+    l2_reward_kernel<<<batch, 256, 0, st>>>(obs, target, reward, n);
+    return cudaGetLastError();
+}
+cudaError_t launch_detmath(const double *x, double *e, double *l, int n, cudaStream_t st)
+{
+    detmath_kernel<<<(n + 255) / 256, 256, 0, st>>>(x, e, l, n);
+    return cudaGetLastError();
+}
+
+}  // namespace spiral

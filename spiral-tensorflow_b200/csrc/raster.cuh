@@ -1,0 +1,63 @@
+// raster.cuh -- device-side parameter block shared by the K1 kernels and the C-ABI glue.
+#pragma once
+#include <cstdint>
+
+namespace spiral {
+
+constexpr int kTile = 64;
+constexpr int kBrushFloats = 16;
+constexpr int kEnvDoubles = 16;
+constexpr int kDabFloats = 8;
+
+// brush_state float[B,16]
+enum {
+    BS_X = 0, BS_Y, BS_PRESSURE, BS_PARTIAL_DABS, BS_ACTUAL_RADIUS, BS_ACTUAL_X, BS_ACTUAL_Y,
+    BS_SPEED1_SLOW, BS_SPEED2_SLOW,
+    BS_FLAGS,      // int bits: 1 = reset_requested, 2 = settings_value[] initialised
+    BS_STEP,       // int: env._step
+    BS_RNG_POS,    // int: values already consumed from the current RNG block (0..10)
+};
+// env_state double[B,16]
+enum {
+    ES_RNG0 = 0,             // [0..9] current RNG output block
+    ES_SX = 10, ES_SY = 11,  // env.s_x, env.s_y
+    ES_ENTRY_PRESSURE = 12,
+    ES_HAVE_START = 13,      // 0.0 while s_x is None
+};
+// pending dab record float[8]
+enum { DAB_X = 0, DAB_Y, DAB_RLOG, DAB_ACTUAL_RADIUS, DAB_OPAQUE, DAB_HARDNESS, DAB_AA, DAB_HAS_RAND };
+
+constexpr int kDyn = 9;
+constexpr int kIn = 3;
+constexpr int kPts = 4;
+
+struct MapDev {
+    float base;
+    int n[kIn];
+    float x[kIn][kPts];
+    float y[kIn][kPts];
+    float inv[kIn][kPts];   // 1/(x[i+1]-x[i]) when that is a power of two (division == multiplication), else 0
+};
+
+struct EnvParams {
+    int B, C, L, K;
+    int idx_jump, idx_control, idx_end, idx_pressure, idx_size, idx_color;
+    int n_colors, colorize, dither, max_dabs;
+    int uses_speed1, uses_speed2;
+    double lin[64];
+    double pressures[8];
+    double sizes[8];
+    float base_rlog[9];          // radius_logarithmic base per size entry; [8] = brush file value
+    float base_radius[9];        // expf(base_rlog)
+    unsigned short colors[8][4];
+    double default_pressure, default_size, head, tail, entry_pressure0;
+    MapDev dyn[kDyn];
+    float slow_tracking;
+    float sp_gamma[2], sp_m[2], sp_q[2];
+    float dabs_basic, dabs_actual, dabs_second;
+    float cs, sn, l2, rad_area_1;
+    float cull_factor;           // upper bound of radius / ACTUAL_RADIUS (radius_by_random)
+    double rng_seed_block[10];   // first output block of rng_double after set_seed(1000)
+};
+
+}  // namespace spiral
