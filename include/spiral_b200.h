@@ -182,6 +182,7 @@ typedef struct {
     int32_t screen_size;          /* 64 -> 6 conv layers */
     int32_t disc_dim;
     int32_t batch_norm;           /* args.disc_batch_norm */
+    int32_t normalize;            /* 1: norm_fn = (x-127.5)/127.5 fused into layer 0; 0: norm_fn=None */
     int32_t precision;            /* 0 = fp32 SIMT, 1 = tcgen05 bf16x3 (fp32-equivalent), 2 = tcgen05 bf16 */
 } SpiralDiscCfg;
 

@@ -61,7 +61,7 @@ class SpiralEnvCfg(C.Structure):
 class SpiralDiscCfg(C.Structure):
     _fields_ = [("abi_version", C.c_int32), ("device", C.c_int32), ("max_batch", C.c_int32),
                 ("in_channels", C.c_int32), ("screen_size", C.c_int32), ("disc_dim", C.c_int32),
-                ("batch_norm", C.c_int32), ("precision", C.c_int32)]
+                ("batch_norm", C.c_int32), ("normalize", C.c_int32), ("precision", C.c_int32)]
 
 
 class SpiralDiscWeights(C.Structure):

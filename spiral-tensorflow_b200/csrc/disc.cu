@@ -27,7 +27,7 @@ namespace spiral {
 template <int COUT_PER_THREAD>
 __global__ void __launch_bounds__(256)
 conv0_kernel(const float *__restrict__ x, const float *__restrict__ w, const float *__restrict__ bias,
-             float *__restrict__ out, int B, int H, int Cin, int Cout)
+             float *__restrict__ out, int B, int H, int Cin, int Cout, int normalize)
 {
     // H = W = input size; output H/2
     extern __shared__ float sm[];
@@ -45,8 +45,10 @@ conv0_kernel(const float *__restrict__ x, const float *__restrict__ w, const flo
         const int ly = p / 19, lx = p % 19;
         const int iy = 2 * oy0 - 1 + ly, ix = 2 * ox0 - 1 + lx;
         float v = 0.0f;
-        if (iy >= 0 && iy < H && ix >= 0 && ix < H)
-            v = (x[(((size_t)b * H + iy) * H + ix) * Cin + c] - 127.5f) / 127.5f;
+        if (iy >= 0 && iy < H && ix >= 0 && ix < H) {
+            v = x[(((size_t)b * H + iy) * H + ix) * Cin + c];
+            if (normalize) v = (v - 127.5f) / 127.5f;
+        }
         s_in[i] = v;
     }
     for (int i = tid; i < 25 * Cin * Cout; i += 256) s_w[i] = w[i];
@@ -178,7 +180,7 @@ conv_simt_kernel(const float *__restrict__ in, const float *__restrict__ in_scal
 __global__ void bn_finalize_kernel(const float *__restrict__ partial, int n_part, int Cout, double count,
                                    const float *__restrict__ gamma, const float *__restrict__ beta,
                                    float eps, float *__restrict__ scale, float *__restrict__ shift,
-                                   float *__restrict__ stats)
+                                   float *__restrict__ stats, int stats_stride)
 {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= Cout) return;
@@ -194,7 +196,7 @@ __global__ void bn_finalize_kernel(const float *__restrict__ partial, int n_part
     const float sc = gamma[c] * inv;
     scale[c] = sc;
     shift[c] = beta[c] - (float)mean * sc;
-    if (stats) { stats[c] = (float)mean; stats[Cout + c] = (float)var; }
+    if (stats) { stats[c] = (float)mean; stats[stats_stride + c] = (float)var; }
 }
 
 __global__ void fill_affine_kernel(float *scale, float *shift, int n, float sc, float sh)
@@ -271,7 +273,7 @@ int disc_forward_simt(SpiralDisc *d, const float *x, int batch, float *logits, f
             if (smem > 200 * 1024) return spiral_set_error(SPIRAL_EUNSUPPORTED, "layer-0 weights do not fit shared memory");
             cudaFuncSetAttribute(conv0_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             conv0_kernel<1><<<batch * (Ho / 8) * (Ho / 8), 256, smem, st>>>(x, (const float *)W.conv_w[0],
-                                                                            (const float *)W.conv_b[0], out, batch, H, Cin, Cout);
+                                                                            (const float *)W.conv_b[0], out, batch, H, Cin, Cout, d->cfg.normalize);
         } else {
             const float *in = (const float *)(ws + pl.act_off[l - 1]);
             const float *isc = (const float *)(ws + pl.scale_off[l - 1]);
@@ -284,7 +286,7 @@ int disc_forward_simt(SpiralDisc *d, const float *x, int batch, float *logits, f
             bn_finalize_kernel<<<(Cout + 127) / 128, 128, 0, st>>>(part, pl.mtiles[l], Cout, (double)batch * Ho * Ho,
                                                                     (const float *)W.bn_gamma[l], (const float *)W.bn_beta[l],
                                                                     1e-3f, scale, shift,
-                                                                    bn_stats ? bn_stats + (size_t)l * 2 * maxC : nullptr);
+                                                                    bn_stats ? bn_stats + (size_t)l * 2 * maxC : nullptr, maxC);
         } else {
             fill_affine_kernel<<<(Cout + 127) / 128, 128, 0, st>>>(scale, shift, Cout, 1.0f, 0.0f);
         }

@@ -30,7 +30,8 @@ void disc_plan(const SpiralDisc *d, int batch, DiscPlan *pl);
 
 // kernels shared by both paths
 __global__ void bn_finalize_kernel(const float *partial, int n_part, int Cout, double count, const float *gamma,
-                                   const float *beta, float eps, float *scale, float *shift, float *stats);
+                                   const float *beta, float eps, float *scale, float *shift, float *stats,
+                                   int stats_stride);
 __global__ void fill_affine_kernel(float *scale, float *shift, int n, float sc, float sh);
 __global__ void dense_sigmoid_kernel(const float *in, const float *in_scale, const float *in_shift, const float *w,
                                      const float *bias, float *logits, float *probs, int B, int C);

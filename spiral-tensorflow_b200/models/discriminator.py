@@ -1,0 +1,134 @@
+"""``Discriminator`` -- host mirror of the reference's models/discriminator.py over K2.
+
+``predict(images)`` (reference :157-163) returns ``sigmoid(D(norm(images)))`` for a batch of
+final canvases, computed by libspiral_b200.so; it is the GAN reward the learner injects at
+agent.py:336-338.  Parameters are plain float32 CUDA tensors in TensorFlow layouts (conv kernels
+HWIO, dense kernel [C,1]) so that reference checkpoints map one to one by name.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import numpy as np
+import torch
+
+from .. import _native as N
+
+PRECISIONS = {"fp32": 0, "bf16x3": 1, "bf16": 2}
+
+
+class Discriminator(object):
+    def __init__(self, args, step=None, image_shape=None, norm_fn=None, scope_name="global",
+                 device=None, max_batch=None, seed=11):
+        self.args = args
+        self.step = step
+        self.scope_name = scope_name
+        self.image_shape = list(image_shape if image_shape is not None
+                                else [args.screen_size, args.screen_size, args.color_channel])
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.conditional = bool(args.conditional)
+        self.normalize = norm_fn is not None
+        S, _, Cimg = self.image_shape
+        self.in_channels = Cimg * (2 if self.conditional else 1)
+        self.layer_num = int(math.log(S, 2))
+        self.disc_dim = int(args.disc_dim)
+        self.batch_norm = bool(args.disc_batch_norm)
+        self.max_batch = int(max_batch or max(getattr(args, "num_envs", 64), args.disc_batch_size))
+        self.precision = PRECISIONS[getattr(args, "disc_precision", "fp32")]
+
+        self.params = self._init_params(seed)
+        self.var_list = list(self.params.values())
+
+        self._lib = N.lib()
+        cfg = N.SpiralDiscCfg()
+        cfg.abi_version = N.ABI_VERSION
+        cfg.device = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        cfg.max_batch = self.max_batch
+        cfg.in_channels = self.in_channels
+        cfg.screen_size = S
+        cfg.disc_dim = self.disc_dim
+        cfg.batch_norm = int(self.batch_norm)
+        cfg.normalize = int(self.normalize)
+        cfg.precision = self.precision
+        self._handle = C.c_void_p()
+        N.check(self._lib.spiral_disc_create(C.byref(cfg), C.byref(self._handle)), "spiral_disc_create")
+        nbytes = self._lib.spiral_disc_workspace_bytes(self._handle, self.max_batch)
+        if nbytes < 0:
+            raise RuntimeError("spiral_disc_workspace_bytes failed")
+        self.workspace = torch.empty((int(nbytes),), dtype=torch.uint8, device=self.device)
+        self.bn_stats = torch.zeros((self.layer_num, 2, self.disc_dim * 2 ** (self.layer_num - 1)),
+                                    dtype=torch.float32, device=self.device)
+        self.sync_weights()
+
+    # ------------------------------------------------------------------
+    def _init_params(self, seed):
+        """he_normal conv kernels, zero biases, BN gamma 1 / beta 0, glorot_normal dense
+        (reference :71, :87); names follow the TF variable scopes."""
+        g = torch.Generator(device="cpu")
+        g.manual_seed(seed)
+        p = {}
+        cin = self.in_channels
+        for l in range(self.layer_num):
+            cout = self.disc_dim * 2 ** l
+            std = math.sqrt(2.0 / (25 * cin))
+            p["conv%d/kernel" % l] = (torch.randn((5, 5, cin, cout), generator=g) * std)
+            p["conv%d/bias" % l] = torch.zeros((cout,))
+            if l > 0 and self.batch_norm:
+                p["batch_normalization_%d/gamma" % l] = torch.ones((cout,))
+                p["batch_normalization_%d/beta" % l] = torch.zeros((cout,))
+            cin = cout
+        p["dense/kernel"] = torch.randn((cin, 1), generator=g) * math.sqrt(2.0 / (cin + 1))
+        p["dense/bias"] = torch.zeros((1,))
+        return {k: v.to(self.device, torch.float32).contiguous() for k, v in p.items()}
+
+    def load_numpy(self, weights):
+        """weights: dict in the oracle's naming (conv%d/kernel, bn%d/gamma, dense/kernel ...)."""
+        for k, v in weights.items():
+            name = k.replace("bn", "batch_normalization_") if k.startswith("bn") else k
+            self.params[name].copy_(torch.as_tensor(np.asarray(v)).to(self.params[name]))
+        self.sync_weights()
+
+    def sync_weights(self):
+        """Hand the (possibly updated) parameters to the kernels; call after every optimiser step."""
+        w = N.SpiralDiscWeights()
+        for l in range(self.layer_num):
+            w.conv_w[l] = self.params["conv%d/kernel" % l].data_ptr()
+            w.conv_b[l] = self.params["conv%d/bias" % l].data_ptr()
+            if l > 0 and self.batch_norm:
+                w.bn_gamma[l] = self.params["batch_normalization_%d/gamma" % l].data_ptr()
+                w.bn_beta[l] = self.params["batch_normalization_%d/beta" % l].data_ptr()
+        w.dense_w = self.params["dense/kernel"].data_ptr()
+        w.dense_b = self.params["dense/bias"].data_ptr()
+        N.check(self._lib.spiral_disc_load_weights(self._handle, C.byref(w), N.ptr(self.workspace), N.stream_ptr()),
+                "spiral_disc_load_weights")
+
+    def __del__(self):
+        try:
+            if getattr(self, "_handle", None) is not None and self._handle.value:
+                self._lib.spiral_disc_destroy(self._handle)
+                self._handle = C.c_void_p()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------
+    def forward(self, images, logits_out=None, probs_out=None):
+        """images f32[N,S,S,C] (0..255 when norm_fn is set) -> (probs[N], logits[N])."""
+        x = images
+        if self.conditional:
+            x = torch.cat([x, x], -1)                 # real <- concat[real, real] (reference :36-38)
+        x = x.to(device=self.device, dtype=torch.float32).contiguous()
+        n = x.shape[0]
+        if tuple(x.shape[1:]) != (self.image_shape[0], self.image_shape[1], self.in_channels):
+            raise ValueError("images must be [N,%d,%d,%d]" % (self.image_shape[0], self.image_shape[1],
+                                                              self.in_channels // (2 if self.conditional else 1)))
+        logits = logits_out if logits_out is not None else torch.empty((n,), dtype=torch.float32, device=self.device)
+        probs = probs_out if probs_out is not None else torch.empty((n,), dtype=torch.float32, device=self.device)
+        N.check(self._lib.spiral_disc_forward(self._handle, N.ptr(x), n, N.ptr(logits), N.ptr(probs),
+                                              N.ptr(self.bn_stats), N.ptr(self.workspace), N.stream_ptr()),
+                "spiral_disc_forward")
+        return probs, logits
+
+    def predict(self, images):
+        """reference :157-163."""
+        return self.forward(images)[0]

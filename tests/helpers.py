@@ -1,0 +1,31 @@
+"""Shared helpers for the test-suite."""
+import os
+
+import numpy as np
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+ENV_OF = {"simple_mnist": ["jump", "control", "end"],
+          "mnist": ["jump", "pressure", "control", "end", "size"],
+          "color_mnist": ["control", "end", "color", "jump", "pressure", "size"]}
+
+
+def make_args(env="simple_mnist", L=32, C=1, T=5, conditional=False, jump=True, curve=True, extra=()):
+    import spiral_b200 as sp
+    argv = ["--env", env, "--location_size", str(L), "--color_channel", str(C), "--episode_length", str(T),
+            "--loss", "l2" if conditional else "gan", "--jump", str(jump), "--curve", str(curve)] + list(extra)
+    return sp.get_args(argv)
+
+
+def random_actions(env, B, T, seed=0, jump_prob=None):
+    rng = np.random.RandomState(seed)
+    a = np.stack([rng.randint(n, size=(B, T)) for n in env.head_sizes], -1).astype(np.int32)
+    if jump_prob is not None and "jump" in env.ac_idx:
+        a[..., env.ac_idx["jump"]] = rng.rand(B, T) < jump_prob
+    return a
+
+
+def oracle_for(env, B, math_mode=1):
+    from oracle import paint_oracle as po
+    spec = po.EnvSpec(action_names=list(env.acs), location_size=env.location_size,
+                      n_color=len(env.colors), colorize=env.colorize, math_mode=math_mode)
+    return po.OracleBatchEnv(spec, B, channels=env.channels)

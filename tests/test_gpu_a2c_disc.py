@@ -1,0 +1,111 @@
+"""GPU parity of K3 (fused A2C loss) and K2 (discriminator forward / reward) against the
+oracles.  Tolerance: 1e-4 relative in fp32 (BASELINE.json north_star); K3 is held to 2e-5."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _sp():
+    import spiral_b200 as sp
+    return sp
+
+
+def _rel(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-12)
+
+
+@pytest.mark.parametrize("sizes,B,T", [([2, 1024, 1024], 7, 5), ([2, 2, 1024, 1024, 2], 5, 3),
+                                      ([4096, 4096, 8, 2, 2, 2], 3, 20), ([3, 5], 4, 1)])
+def test_a2c_loss_and_grads_match_oracle(sizes, B, T):
+    sp = _sp()
+    from oracle import a2c_oracle as ao
+    from importlib import import_module
+    rl = import_module(sp.__name__ + ".rl_utils")
+    rng = np.random.RandomState(0)
+    logits = [rng.randn(B, T, n).astype(np.float32) * 2 for n in sizes]
+    acts = np.stack([rng.randint(n, size=(B, T)) for n in sizes], -1).astype(np.int32)
+    rewards = np.zeros((B, T), np.float32)
+    rewards[:, -1] = rng.rand(B)
+    values = rng.randn(B, T).astype(np.float32)
+    vf = rng.randn(B, T).astype(np.float32)
+    res = rl.a2c_loss([torch.tensor(l, device="cuda") for l in logits], torch.tensor(acts, device="cuda"),
+                      torch.tensor(rewards, device="cuda"), torch.tensor(values, device="cuda"),
+                      torch.tensor(vf, device="cuda"), 0.99, 1.0, 0.01)
+    want_r, want_adv = ao.multiple_process_rollout(rewards, values, 0.99, 1.0)
+    assert _rel(res.r.cpu().numpy(), want_r) < 1e-6
+    assert _rel(res.adv.cpu().numpy(), want_adv) < 1e-6
+    # the learner feeds float32 adv / r (agent.py:347-352)
+    want = ao.a2c_loss(logits, acts, want_adv.astype(np.float32), want_r.astype(np.float32), vf, 0.01)
+    got = res.scalars.cpu().numpy()
+    for i, k in enumerate(("pi_loss", "vf_loss", "entropy", "total")):
+        assert abs(got[i] - want[k]) <= 2e-5 * max(1.0, abs(want[k])), k
+    for k in range(len(sizes)):
+        assert _rel(res.dlogits[k].cpu().numpy(), want["dlogits"][k]) < 2e-5
+    assert _rel(res.dvf.cpu().numpy(), want["dvf"]) < 2e-5
+
+
+def test_a2c_autograd_wrapper_backpropagates():
+    sp = _sp()
+    from importlib import import_module
+    rl = import_module(sp.__name__ + ".rl_utils")
+    torch.manual_seed(0)
+    B, T = 4, 3
+    l1 = torch.randn(B, T, 16, device="cuda", requires_grad=True)
+    l2 = torch.randn(B, T, 2, device="cuda", requires_grad=True)
+    vf = torch.randn(B, T, device="cuda", requires_grad=True)
+    acts = torch.stack([torch.randint(16, (B, T)), torch.randint(2, (B, T))], -1).int().cuda()
+    rew = torch.rand(B, T, device="cuda")
+    val = torch.randn(B, T, device="cuda")
+    loss = rl.a2c_loss_autograd([l1, l2], acts, rew, val, vf)
+    loss.backward()
+    # plain-PyTorch fp32 reference of the same loss
+    res = rl.a2c_loss([l1.detach(), l2.detach()], acts, rew, val, vf.detach())
+    ref = 0
+    l1r, l2r, vfr = l1.detach().clone().requires_grad_(), l2.detach().clone().requires_grad_(), vf.detach().clone().requires_grad_()
+    for k, lg in enumerate((l1r, l2r)):
+        lp = torch.log_softmax(lg, -1)
+        ref = ref - (lp.gather(-1, acts[..., k:k + 1].long())[..., 0] * res.adv).sum() \
+            + 0.25 * ((vfr - res.r) ** 2).sum() + 0.01 * (lp.exp() * lp).sum()
+    ref.backward()
+    assert torch.allclose(loss, ref, rtol=1e-5, atol=1e-5)
+    assert torch.allclose(l1.grad, l1r.grad, rtol=1e-4, atol=1e-6)
+    assert torch.allclose(l2.grad, l2r.grad, rtol=1e-4, atol=1e-6)
+    assert torch.allclose(vf.grad, vfr.grad, rtol=1e-4, atol=1e-6)
+
+
+@pytest.mark.parametrize("C,dd,bn,B,prec", [(1, 8, True, 16, "fp32"), (3, 16, True, 8, "fp32"),
+                                            (1, 8, False, 5, "fp32"), (3, 64, True, 4, "fp32")])
+def test_discriminator_forward_matches_oracle(C, dd, bn, B, prec):
+    sp = _sp()
+    from oracle import disc_oracle as do
+    from importlib import import_module
+    models = import_module(sp.__name__ + ".models")
+    args = sp.get_args(["--color_channel", str(C), "--disc_dim", str(dd), "--disc_batch_norm", str(bn),
+                        "--disc_precision", prec])
+    w = do.init_weights(C, disc_dim=dd, batch_norm=bn, seed=3)
+    D = models.Discriminator(args, None, [64, 64, C], norm_fn=lambda x: x, scope_name="global", max_batch=B)
+    D.load_numpy(w)
+    rng = np.random.RandomState(1)
+    # canvas-like images: white with dark blobs
+    imgs = np.full((B, 64, 64, C), 255.0, np.float32)
+    for b in range(B):
+        for _ in range(6):
+            y, x = rng.randint(0, 56, 2)
+            imgs[b, y:y + 8, x:x + 8] = rng.randint(0, 255)
+    probs, logits = D.forward(torch.tensor(imgs, device="cuda"))
+    want_p, want_l = do.predict(imgs, w, batch_norm=bn, dtype=torch.float64)
+    lg = logits.cpu().numpy()
+    assert np.abs(lg - want_l).max() <= 1e-4 * max(1.0, np.abs(want_l).max()), (lg, want_l)
+    assert np.abs(probs.cpu().numpy() - want_p).max() <= 1e-4
+    # BN statistics that were used (mean / biased variance of the scored batch)
+    if bn:
+        x = do.norm_fn(torch.tensor(imgs, dtype=torch.float64))
+        _, _, stats = do.build_model(x, w, bn, torch.float64, return_stats=True)
+        got = D.bn_stats.cpu().numpy()
+        for l, (m, v) in enumerate(stats, start=1):
+            n = m.numel()
+            assert np.allclose(got[l, 0, :n], m.numpy(), rtol=1e-3, atol=1e-4)
+            assert np.allclose(got[l, 1, :n], v.numpy(), rtol=1e-3, atol=1e-5)
