@@ -94,6 +94,7 @@ typedef struct {
     int32_t colorize;             /* mnist.py:40,132-133: colour = palette[step] */
     int32_t dither;               /* 0 = round-half, 1 = per-pixel table (pixops.cpp dithering_noise) */
     int32_t max_dabs;             /* capacity of the per-canvas pending-dab list */
+    int32_t rng_table_len;        /* rng-double stream positions tabulated per handle (>= draws of one episode) */
     double lin[SPIRAL_MAX_L];     /* np.linspace(0, 64, L) */
     double pressures[SPIRAL_MAX_TABLE];
     double sizes[SPIRAL_MAX_TABLE];
@@ -118,7 +119,8 @@ int spiral_env_reset(SpiralEnv *env, uint16_t *canvas_dev, float *brush_state_de
 
 /* envs/mnist.py:231-260 for every canvas.  actions i32[B,K].  dab_scratch f32[B,max_dabs,8] and
  * dab_count i32[B,2] are scratch owned by the caller (contents undefined between calls).
- * status_dev i32[1] is OR-ed with 1 if any canvas overflowed max_dabs (result then invalid). */
+ * status_dev i32[1] is OR-ed with 1 if any canvas overflowed max_dabs and with 2 if a canvas ran past
+ * rng_table_len (result then invalid). */
 int spiral_env_step(SpiralEnv *env, const int32_t *actions_dev, uint16_t *canvas_dev,
                     float *brush_state_dev, double *env_state_dev, float *dab_scratch_dev,
                     int32_t *dab_count_dev, float *obs_dev, int32_t *status_dev, void *stream);

@@ -47,6 +47,7 @@ class SpiralEnvCfg(C.Structure):
                 ("idx_pressure", C.c_int32), ("idx_size", C.c_int32), ("idx_color", C.c_int32),
                 ("n_pressures", C.c_int32), ("n_sizes", C.c_int32), ("n_colors", C.c_int32),
                 ("colorize", C.c_int32), ("dither", C.c_int32), ("max_dabs", C.c_int32),
+                ("rng_table_len", C.c_int32),
                 ("lin", C.c_double * MAX_L),
                 ("pressures", C.c_double * MAX_TABLE),
                 ("sizes", C.c_double * MAX_TABLE),

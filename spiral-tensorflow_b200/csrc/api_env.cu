@@ -19,7 +19,7 @@
 namespace spiral {
 cudaError_t launch_reset(const EnvParams &P, uint16_t *canvas, float *bs, double *es, float *obs, cudaStream_t st);
 cudaError_t launch_expand(const EnvParams &P, const int32_t *actions, float *bs, double *es, float *dabs,
-                          int32_t *dab_count, int32_t *status, cudaStream_t st);
+                          int32_t *dab_count, int32_t *status, const float *gauss_tab, cudaStream_t st);
 cudaError_t launch_composite(const EnvParams &P, uint16_t *canvas, const float *dabs, const int32_t *dab_count,
                              const uint16_t *dither, float *obs, cudaStream_t st);
 cudaError_t launch_debug_dabs(const EnvParams &P, const float *dabs, const int32_t *dab_count, float *out,
@@ -67,6 +67,35 @@ static void rng_array(double *ran_u, double *aa, int n)
     for (; i < KK; i++, j++) ran_u[i] = ms(aa[j - KK], ran_u[i - LL]);
 }
 
+static void rng_seed_block(long seed, double *out10);
+
+// rand_gauss (helpers.c) over every window u[i..i+3] of the rng-double output stream
+static void rng_gauss_table(long seed, int n, float *g)
+{
+    double cur[10];
+    rng_seed_block(seed, cur);
+    const int need = n + 3;
+    double *u = new double[(size_t)need + 10];
+    int filled = 0;
+    while (filled < need) {
+        for (int j = 0; j < 10; j++) u[filled + j] = cur[j];     // one cycle() yields the state itself
+        filled += 10;
+        double a[29];                                            // ... and advances it by QUALITY = 19 steps
+        for (int j = 0; j < 10; j++) a[j] = cur[j];
+        for (int j = 10; j < 29; j++) a[j] = ms(a[j - 10], a[j - 7]);
+        for (int j = 0; j < 10; j++) cur[j] = a[19 + j];
+    }
+    for (int i = 0; i < n; i++) {
+        double sum = 0.0;
+        sum += u[i];
+        sum += u[i + 1];
+        sum += u[i + 2];
+        sum += u[i + 3];
+        g[i] = (float)(sum * 1.73205080757 - 3.46410161514);
+    }
+    delete[] u;
+}
+
 static void rng_seed_block(long seed, double *out10)
 {
     const int KK = 10, LL = 7, TT = 7;
@@ -104,6 +133,7 @@ struct SpiralEnv {
     EnvParams P;
     int device;
     uint16_t *d_dither;
+    float *d_gauss;
 };
 
 static bool is_pow2f(float v)
@@ -135,6 +165,8 @@ extern "C" int spiral_env_create(const SpiralEnvCfg *cfg, SpiralEnv **out)
     if ((cfg->idx_color >= 0 || cfg->colorize) && cfg->n_colors < 1)
         return spiral_set_error(SPIRAL_EINVAL, "colour action / colorize needs a palette");
     if (cfg->max_dabs < 32) return spiral_set_error(SPIRAL_EINVAL, "max_dabs must be >= 32");
+    if (cfg->rng_table_len < 4096 || cfg->rng_table_len > (1 << 26))
+        return spiral_set_error(SPIRAL_EINVAL, "rng_table_len must be in 4096..2^26 (got %d)", cfg->rng_table_len);
     {
         const double head = 100 * cfg->head, tail = 100 * cfg->tail;
         const int hr = (int)head + 1, tr = (int)tail + 1;
@@ -168,11 +200,14 @@ extern "C" int spiral_env_create(const SpiralEnvCfg *cfg, SpiralEnv **out)
     P.head = cfg->head; P.tail = cfg->tail; P.entry_pressure0 = cfg->entry_pressure0;
 
     P.uses_speed1 = P.uses_speed2 = 0;
+    P.mapped_mask = 0;
+    P.rng_table_len = cfg->rng_table_len;
     for (int s = 0; s < SPIRAL_DYN_COUNT; s++) {
         MapDev &m = P.dyn[s];
         m.base = br.dyn[s].base;
         for (int j = 0; j < SPIRAL_IN_COUNT; j++) {
             m.n[j] = br.dyn[s].n[j];
+            if (m.n[j]) P.mapped_mask |= 1 << s;
             if (m.n[j] && j == SPIRAL_IN_SPEED1) P.uses_speed1 = 1;
             if (m.n[j] && j == SPIRAL_IN_SPEED2) P.uses_speed2 = 1;
             for (int k = 0; k < SPIRAL_MAX_POINTS; k++) {
@@ -195,6 +230,16 @@ extern "C" int spiral_env_create(const SpiralEnvCfg *cfg, SpiralEnv **out)
     P.base_radius[8] = detmath::det_expf(P.base_rlog[8]);
 
     P.slow_tracking = br.slow_tracking;
+    // stroke_to: fac = 1.0 - exp_decay(slow_tracking, 100.0*dtime) for the two event durations
+    {
+        const double dts[2] = {0.1, 1.0};
+        for (int i = 0; i < 2; i++) {
+            const float t = (float)(100.0 * dts[i]);
+            float ed = 0.0f;
+            if (!((double)br.slow_tracking <= 0.001)) ed = (float)detmath::det_exp((double)(-t / br.slow_tracking));
+            P.track_fac[i] = (float)(1.0 - (double)ed);
+        }
+    }
     // settings_base_values_have_changed: speed input mapping  y = log(gamma + x) * m + q
     const float gam[2] = {br.speed1_gamma, br.speed2_gamma};
     for (int i = 0; i < 2; i++) {
@@ -233,8 +278,17 @@ extern "C" int spiral_env_create(const SpiralEnvCfg *cfg, SpiralEnv **out)
     if (e == cudaSuccess) e = cudaMalloc(&env->d_dither, sizeof(cfg->dither_table));
     if (e == cudaSuccess)
         e = cudaMemcpy(env->d_dither, cfg->dither_table, sizeof(cfg->dither_table), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMalloc(&env->d_gauss, sizeof(float) * (size_t)cfg->rng_table_len);
+    if (e == cudaSuccess) {
+        float *g = new float[(size_t)cfg->rng_table_len];
+        rng_gauss_table(1000, cfg->rng_table_len, g);
+        e = cudaMemcpy(env->d_gauss, g, sizeof(float) * (size_t)cfg->rng_table_len, cudaMemcpyHostToDevice);
+        delete[] g;
+    }
     cudaSetDevice(prev);
     if (e != cudaSuccess) {
+        if (env->d_dither) cudaFree(env->d_dither);
+        if (env->d_gauss) cudaFree(env->d_gauss);
         delete env;
         return spiral_cuda_error(e, "spiral_env_create");
     }
@@ -246,6 +300,7 @@ extern "C" int spiral_env_destroy(SpiralEnv *env)
 {
     if (!env) return SPIRAL_OK;
     if (env->d_dither) cudaFree(env->d_dither);
+    if (env->d_gauss) cudaFree(env->d_gauss);
     delete env;
     return SPIRAL_OK;
 }
@@ -263,7 +318,7 @@ extern "C" int spiral_env_expand(SpiralEnv *env, const int32_t *actions, float *
                                  int32_t *dab_count, int32_t *status, void *stream)
 {
     REQUIRE(env); REQUIRE(actions); REQUIRE(bs); REQUIRE(es); REQUIRE(dabs); REQUIRE(dab_count); REQUIRE(status);
-    const cudaError_t e = launch_expand(env->P, actions, bs, es, dabs, dab_count, status, (cudaStream_t)stream);
+    const cudaError_t e = launch_expand(env->P, actions, bs, es, dabs, dab_count, status, env->d_gauss, (cudaStream_t)stream);
     return e == cudaSuccess ? SPIRAL_OK : spiral_cuda_error(e, "spiral_env_expand");
 }
 

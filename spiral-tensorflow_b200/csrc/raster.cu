@@ -33,11 +33,14 @@ using detmath::det_hypotf;
 using detmath::det_log;
 
 // ------------------------------------------------------------------------------------------
-// libmypaint mapping (mypaint-mapping.c: mypaint_mapping_calculate), inputs pressure/speed1/speed2
+// libmypaint mapping (mypaint-mapping.c: mypaint_mapping_calculate), inputs pressure/speed1/speed2.
+// Settings without any mapping are the common case: `mapped` (warp-uniform, from the parameter
+// block) skips the evaluation and returns the base value.
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ float map_eval(const MapDev &m, const float (&in)[kIn], float base)
+__device__ __forceinline__ float map_eval(const MapDev &m, bool mapped, const float (&in)[kIn], float base)
 {
     float result = base;
+    if (!mapped) return result;
 #pragma unroll
     for (int j = 0; j < kIn; j++) {
         const int n = m.n[j];
@@ -46,12 +49,14 @@ __device__ __forceinline__ float map_eval(const MapDev &m, const float (&in)[kIn
             float x0 = m.x[j][0], y0 = m.y[j][0];
             float x1 = m.x[j][1], y1 = m.y[j][1];
             float inv = m.inv[j][0];
-            for (int i = 2; i < n && x > x1; i++) {
-                x0 = x1;
-                y0 = y1;
-                x1 = m.x[j][i];
-                y1 = m.y[j][i];
-                inv = m.inv[j][i - 1];
+            if (n > 2) {
+                for (int i = 2; i < n && x > x1; i++) {
+                    x0 = x1;
+                    y0 = y1;
+                    x1 = m.x[j][i];
+                    y1 = m.y[j][i];
+                    inv = m.inv[j][i - 1];
+                }
             }
             float y;
             if (x0 == x1 || y0 == y1) {
@@ -79,50 +84,14 @@ __device__ __forceinline__ float one_minus_decay(float T_const, float t)
 }
 
 // ------------------------------------------------------------------------------------------
-// rng-double.c (Knuth ranf_array, KK=10, LL=7, QUALITY=19): one output block = 10 values; the
-// next block is the state 19 recurrence steps later.
-// ------------------------------------------------------------------------------------------
-__device__ __forceinline__ double mod_sum(double x, double y)
-{
-    const double s = x + y;              // in [0, 2)
-    return s >= 1.0 ? s - 1.0 : s;       // == s - (int)s
-}
-
-template <int NT>
-struct Rng {
-    double (*blk)[NT];   // shared [10][NT]
-    int tid;
-    int pos;
-    __device__ __forceinline__ void refill()
-    {
-        double a[29];
-#pragma unroll
-        for (int j = 0; j < 10; j++) a[j] = blk[j][tid];
-#pragma unroll
-        for (int j = 10; j < 29; j++) a[j] = mod_sum(a[j - 10], a[j - 7]);
-#pragma unroll
-        for (int j = 0; j < 10; j++) blk[j][tid] = a[19 + j];
-        pos = 0;
-    }
-    __device__ __forceinline__ double next()
-    {
-        if (pos == 10) refill();
-        return blk[pos++][tid];
-    }
-    // helpers.c rand_gauss
-    __device__ __forceinline__ float gauss()
-    {
-        double sum = 0.0;
-        sum += next();
-        sum += next();
-        sum += next();
-        sum += next();
-        return (float)(sum * 1.73205080757 - 3.46410161514);
-    }
-};
-
-// ------------------------------------------------------------------------------------------
 // K1a: stroke expansion
+//
+// RNG: every Brush is seeded with 1000 (mypaint_brush_new), so ALL canvases walk the same
+// rng-double stream u[0], u[1], ... and differ only in how far they have got.  The library
+// therefore tabulates, once per env handle, g[i] = rand_gauss over u[i..i+3] (helpers.c) for the
+// whole stream an episode can consume; a canvas keeps just its cursor.  Per dab the engine draws
+// u[c] (the RANDOM input, unused by the supported mappings), then two gaussians for the position
+// jitter (if offset_by_random != 0) and one for the radius jitter (if radius_by_random != 0).
 // ------------------------------------------------------------------------------------------
 struct Brush {
     float X, Y, P, partial, AR, AX, AY, s1, s2;
@@ -159,10 +128,9 @@ __device__ __forceinline__ float count_dabs_to(const EnvParams &P, Brush &S, flo
 
 // mypaint-brush.c update_states_and_setting_values, live state only (the stroke / direction /
 // custom / norm_d{x,y}_slow states feed inputs no supported mapping reads).
-template <int NT>
-__device__ __forceinline__ void update_states(const EnvParams &P, Brush &S, Rng<NT> &rng,
-                                              float base_radius, float rlog_base, float step_dx,
-                                              float step_dy, float step_dpressure, float step_dtime)
+__device__ __forceinline__ void update_states(const EnvParams &P, Brush &S, float base_radius,
+                                              float rlog_base, float step_dx, float step_dy,
+                                              float step_dpressure, float step_dtime)
 {
     if (step_dtime < 0.0f) step_dtime = 0.001f;
     else if (step_dtime == 0.0f) step_dtime = 0.001f;
@@ -172,10 +140,6 @@ __device__ __forceinline__ void update_states(const EnvParams &P, Brush &S, Rng<
     S.P += step_dpressure;
     if (S.P <= 0.0f) S.P = 0.0f;
 
-    const float norm_dx = step_dx / step_dtime / base_radius;
-    const float norm_dy = step_dy / step_dtime / base_radius;
-    const float norm_speed = det_hypotf(norm_dx, norm_dy);
-
     float in[kIn];
     in[0] = S.P * 1.0f;   // * expf(pressure_gain_log = 0)
     in[1] = 0.0f;
@@ -184,18 +148,16 @@ __device__ __forceinline__ void update_states(const EnvParams &P, Brush &S, Rng<
         in[1] = (float)(det_log((double)(P.sp_gamma[0] + S.s1)) * (double)P.sp_m[0] + (double)P.sp_q[0]);
     if (P.uses_speed2)
         in[2] = (float)(det_log((double)(P.sp_gamma[1] + S.s2)) * (double)P.sp_m[1] + (double)P.sp_q[1]);
-    (void)rng.next();     // inputs[RANDOM]: consumed on every call
 
-    S.v_opaque = map_eval(P.dyn[0], in, P.dyn[0].base);
-    S.v_opaque_mul = map_eval(P.dyn[1], in, P.dyn[1].base);
+    const int mm = P.mapped_mask;
+    S.v_opaque = map_eval(P.dyn[0], mm & 1, in, P.dyn[0].base);
+    S.v_opaque_mul = map_eval(P.dyn[1], mm & 2, in, P.dyn[1].base);
     // the size action rewrites the base value of radius_logarithmic every step (mnist.py:134-135)
-    S.v_rlog = map_eval(P.dyn[2], in, rlog_base);
-    S.v_hard = map_eval(P.dyn[3], in, P.dyn[3].base);
-    S.v_rbr = map_eval(P.dyn[4], in, P.dyn[4].base);
-    S.v_obr = map_eval(P.dyn[5], in, P.dyn[5].base);
-    const float v_s1slow = map_eval(P.dyn[6], in, P.dyn[6].base);
-    const float v_s2slow = map_eval(P.dyn[7], in, P.dyn[7].base);
-    S.v_aa = map_eval(P.dyn[8], in, P.dyn[8].base);
+    S.v_rlog = map_eval(P.dyn[2], mm & 4, in, rlog_base);
+    S.v_hard = map_eval(P.dyn[3], mm & 8, in, P.dyn[3].base);
+    S.v_rbr = map_eval(P.dyn[4], mm & 16, in, P.dyn[4].base);
+    S.v_obr = map_eval(P.dyn[5], mm & 32, in, P.dyn[5].base);
+    S.v_aa = map_eval(P.dyn[8], mm & 256, in, P.dyn[8].base);
 
     // slow_tracking_per_dab == 0  =>  fac = 1.0 - 0.0
     {
@@ -203,13 +165,20 @@ __device__ __forceinline__ void update_states(const EnvParams &P, Brush &S, Rng<
         S.AX += (S.X - S.AX) * fac;
         S.AY += (S.Y - S.AY) * fac;
     }
-    if (P.uses_speed1) {
-        const float fac = one_minus_decay(v_s1slow, step_dtime);
-        S.s1 += (norm_speed - S.s1) * fac;
-    }
-    if (P.uses_speed2) {
-        const float fac = one_minus_decay(v_s2slow, step_dtime);
-        S.s2 += (norm_speed - S.s2) * fac;
+    if (P.uses_speed1 | P.uses_speed2) {
+        const float norm_dx = step_dx / step_dtime / base_radius;
+        const float norm_dy = step_dy / step_dtime / base_radius;
+        const float norm_speed = det_hypotf(norm_dx, norm_dy);
+        if (P.uses_speed1) {
+            const float v_s1slow = map_eval(P.dyn[6], mm & 64, in, P.dyn[6].base);
+            const float fac = one_minus_decay(v_s1slow, step_dtime);
+            S.s1 += (norm_speed - S.s1) * fac;
+        }
+        if (P.uses_speed2) {
+            const float v_s2slow = map_eval(P.dyn[7], mm & 128, in, P.dyn[7].base);
+            const float fac = one_minus_decay(v_s2slow, step_dtime);
+            S.s2 += (norm_speed - S.s2) * fac;
+        }
     }
     S.AR = clamp_radius(det_expf(S.v_rlog));
     S.flags |= 2;
@@ -217,7 +186,7 @@ __device__ __forceinline__ void update_states(const EnvParams &P, Brush &S, Rng<
 
 struct StepSetup {
     // decoded action (mnist.py:107-130)
-    double x, y, c_x, c_y, pressure;
+    double x, y, c_x, c_y;
     int jump;
     // curve() locals (mnist.py:173-190)
     double cx, cy, sx, sy, x1, y1, x2, y2, bx, by;
@@ -241,10 +210,10 @@ __device__ __forceinline__ void curve_point(const StepSetup &st, int i, double &
 __global__ void __launch_bounds__(kExpandThreads)
 expand_kernel(const __grid_constant__ EnvParams P, const int32_t *__restrict__ actions,
               float *__restrict__ brush_state, double *__restrict__ env_state,
-              float *__restrict__ dabs, int32_t *__restrict__ dab_count, int32_t *__restrict__ status)
+              float *__restrict__ dabs, int32_t *__restrict__ dab_count, int32_t *__restrict__ status,
+              const float *__restrict__ gauss_tab)
 {
     constexpr int NT = kExpandThreads;
-    __shared__ double s_rng[10][NT];
     const int tid = threadIdx.x;
     const int b = blockIdx.x * NT + tid;
     if (b >= P.B) return;
@@ -257,26 +226,22 @@ expand_kernel(const __grid_constant__ EnvParams P, const int32_t *__restrict__ a
     S.s1 = bs[BS_SPEED1_SLOW]; S.s2 = bs[BS_SPEED2_SLOW];
     S.flags = __float_as_int(bs[BS_FLAGS]);
     const int step = __float_as_int(bs[BS_STEP]);
+    int cursor = __float_as_int(bs[BS_RNG_POS]);
+    const int cursor_max = P.rng_table_len - 16;
     S.v_opaque = S.v_opaque_mul = S.v_rlog = S.v_hard = S.v_rbr = S.v_obr = S.v_aa = 0.0f;
-    Rng<NT> rng;
-    rng.blk = s_rng;
-    rng.tid = tid;
-    rng.pos = __float_as_int(bs[BS_RNG_POS]);
-#pragma unroll
-    for (int j = 0; j < 10; j++) s_rng[j][tid] = es[ES_RNG0 + j];
 
     // ---- action decode (mnist.py:107-135) ----
     const int32_t *ac = actions + (size_t)b * P.K;
     StepSetup st;
     const int L = P.L;
     st.x = P.lin[0]; st.y = P.lin[0]; st.c_x = P.lin[0]; st.c_y = P.lin[0];
-    st.pressure = P.default_pressure;
+    double pressure = P.default_pressure;
     st.jump = 0;
     int size_idx = 8;
     int color_idx = 0;
     if (P.idx_end >= 0) { const int a = ac[P.idx_end]; st.x = P.lin[a % L]; st.y = P.lin[a / L]; }
     if (P.idx_control >= 0) { const int a = ac[P.idx_control]; st.c_x = P.lin[a % L]; st.c_y = P.lin[a / L]; }
-    if (P.idx_pressure >= 0) st.pressure = P.pressures[ac[P.idx_pressure]];
+    if (P.idx_pressure >= 0) pressure = P.pressures[ac[P.idx_pressure]];
     if (P.idx_size >= 0) size_idx = ac[P.idx_size];
     if (P.idx_jump >= 0) st.jump = ac[P.idx_jump];
     if (P.idx_color >= 0) color_idx = ac[P.idx_color];
@@ -287,13 +252,12 @@ expand_kernel(const __grid_constant__ EnvParams P, const int32_t *__restrict__ a
     // ---- pre-positioning event and stroke geometry (mnist.py:137-160) ----
     const bool have_start = es[ES_HAVE_START] != 0.0;
     double s_x = es[ES_SX], s_y = es[ES_SY];
-    double entry_pressure = es[ES_ENTRY_PRESSURE];
-    double pressure = st.pressure;
+    const double entry_pressure = es[ES_ENTRY_PRESSURE];
     if (!have_start) { pressure = 0; s_x = 0; s_y = 0; }
     else if (P.idx_jump >= 0 && st.jump) pressure = 0;
     st.curved = !(P.idx_control < 0 || pressure == 0);
     st.sx = s_x; st.sy = s_y;
-    double cur_pressure_var = pressure;     // `pressure` variable inside curve()
+    double cur_pressure_var = pressure;     // the `pressure` variable inside curve()
     if (st.curved) {
         // _line_settings (mnist.py:270-278)
         double p1 = entry_pressure;
@@ -333,11 +297,10 @@ expand_kernel(const __grid_constant__ EnvParams P, const int32_t *__restrict__ a
 
     float *my_dabs = dabs + (size_t)b * P.max_dabs * kDabFloats;
     int n_dabs = 0;
-    bool overflow = false;
+    int err = 0;
 
-    // ---- flattened event / dab loop: one update_states per iteration ----
+    // ---- event cursor ----
     int ev = 0;
-    bool in_event = false;
     int split = 0;                 // stroke_to's "pressure after zero pressure" recursion
     float ex = 0, ey = 0, ep = 0;  // raw event (float32 at the SWIG boundary)
     double edt = 0;
@@ -345,12 +308,12 @@ expand_kernel(const __grid_constant__ EnvParams P, const int32_t *__restrict__ a
     double dtime_left = 0;
     float dabs_moved = 0, dabs_todo = 0;
 
-    while (true) {
-        if (!in_event) {
-            if (ev >= st.n_events) break;
+    // begin event `ev` (mypaint_brush_stroke_to up to the dab loop); false when the step is over
+    auto begin_event = [&]() -> bool {
+        for (;;) {
+            if (ev >= st.n_events) return false;
             if (split == 2) {
-                // second half of the recursion: same x, y, original pressure, dtime = 0.0001
-                edt = 0.0001;
+                edt = 0.0001;      // second half of the recursion: same x, y, pressure
                 split = 0;
             } else {
                 double px, py, pp;
@@ -381,27 +344,34 @@ expand_kernel(const __grid_constant__ EnvParams P, const int32_t *__restrict__ a
             float evp = ep;
             double dt = edt;
             if (split == 1) { evp = 0.0f; dt = edt - 0.0001; }
-            // slow position tracking
-            {
-                const float fac = one_minus_decay(P.slow_tracking, (float)(100.0 * dt));
-                tx = S.X + (ex - S.X) * fac;
-                ty = S.Y + (ey - S.Y) * fac;
-            }
+            // slow position tracking: fac = 1 - exp_decay(slow_tracking, 100 * dtime)
+            float fac;
+            if (dt == 0.1) fac = P.track_fac[0];
+            else if (dt == 1.0) fac = P.track_fac[1];
+            else fac = one_minus_decay(P.slow_tracking, (float)(100.0 * dt));
+            tx = S.X + (ex - S.X) * fac;
+            ty = S.Y + (ey - S.Y) * fac;
             tp = evp;
             dabs_moved = S.partial;
-            dabs_todo = count_dabs_to(P, S, base_radius, tx, ty, (float)dt);
-            if (S.flags & 1) {
-                // first event after reset: initialise only (mypaint-brush.c reset_requested)
-                S.flags &= ~1;
-                S.X = tx; S.Y = ty; S.P = tp;
-                S.partial = 0; S.AR = 0; S.s1 = 0; S.s2 = 0;
-                S.AX = S.X; S.AY = S.Y;
-                if (split == 1) split = 2; else ev++;
-                continue;
-            }
             dtime_left = dt;
-            in_event = true;
+            if (!(S.flags & 1)) return true;
+            // first event after reset: initialise only (mypaint-brush.c reset_requested)
+            S.flags &= ~1;
+            S.X = tx; S.Y = ty; S.P = tp;
+            S.partial = 0; S.AR = 0; S.s1 = 0; S.s2 = 0;
+            S.AX = S.X; S.AY = S.Y;
+            if (split == 1) split = 2; else ev++;
         }
+    };
+
+    bool live = begin_event();
+    if (live) dabs_todo = count_dabs_to(P, S, base_radius, tx, ty, (float)dtime_left);
+
+    // ---- one update_states_and_setting_values per iteration (dab, or end of event) ----
+    while (live) {
+        // gaussians this iteration may need (independent of the state chain: issue the loads early)
+        const int c0 = min(cursor, cursor_max);
+        const float g1 = __ldg(gauss_tab + c0 + 1), g5 = __ldg(gauss_tab + c0 + 5), g9 = __ldg(gauss_tab + c0 + 9);
 
         const bool is_dab = (dabs_moved + dabs_todo >= 1.0f);
         float step_dx, step_dy, step_dp, step_dtime;
@@ -425,7 +395,8 @@ expand_kernel(const __grid_constant__ EnvParams P, const int32_t *__restrict__ a
             step_dtime = (float)dtime_left;
         }
 
-        update_states<NT>(P, S, rng, base_radius, rlog_base, step_dx, step_dy, step_dp, step_dtime);
+        update_states(P, S, base_radius, rlog_base, step_dx, step_dy, step_dp, step_dtime);
+        cursor += 1;                     // inputs[RANDOM] = rng_double_next(): consumed on every call
 
         if (is_dab) {
             // prepare_and_draw_dab, state-machine half (RNG draws, position jitter)
@@ -434,15 +405,21 @@ expand_kernel(const __grid_constant__ EnvParams P, const int32_t *__restrict__ a
             opq = opq * S.v_opaque_mul;
             opq = opq > 1.0f ? 1.0f : (opq < 0.0f ? 0.0f : opq);
             float x = S.AX, y = S.AY;
+            float gr = g1;
             if (S.v_obr != 0.0f) {
                 float amp = S.v_obr;
                 if (amp < 0.0f) amp = 0.0f;
-                x += rng.gauss() * amp * base_radius;
-                y += rng.gauss() * amp * base_radius;
+                x += g1 * amp * base_radius;
+                y += g5 * amp * base_radius;
+                cursor += 8;
+                gr = g9;
             }
             float rl = S.v_rlog;
             const bool has_rand = S.v_rbr != 0.0f;
-            if (has_rand) rl += rng.gauss() * S.v_rbr;
+            if (has_rand) {
+                rl += gr * S.v_rbr;
+                cursor += 4;
+            }
             if (opq != 0.0f) {
                 // conservative cull against tile (0,0); composite_kernel does the exact test
                 const float R = S.AR * P.cull_factor + 0.5f * fabsf(S.v_aa) + 3.0f;
@@ -453,18 +430,19 @@ expand_kernel(const __grid_constant__ EnvParams P, const int32_t *__restrict__ a
                         d[1] = make_float4(opq, S.v_hard, S.v_aa, has_rand ? 1.0f : 0.0f);
                         n_dabs++;
                     } else {
-                        overflow = true;
+                        err |= 1;
                     }
                 }
             }
             dtime_left -= (double)step_dtime;
-            dabs_todo = count_dabs_to(P, S, base_radius, tx, ty, (float)dtime_left);
         } else {
             S.partial = dabs_moved + dabs_todo;
-            in_event = false;
             if (split == 1) split = 2; else ev++;
+            live = begin_event();
         }
+        if (live) dabs_todo = count_dabs_to(P, S, base_radius, tx, ty, (float)dtime_left);
     }
+    if (cursor > cursor_max) err |= 2;
 
     // ---- write back ----
     bs[BS_X] = S.X; bs[BS_Y] = S.Y; bs[BS_PRESSURE] = S.P; bs[BS_PARTIAL_DABS] = S.partial;
@@ -472,16 +450,14 @@ expand_kernel(const __grid_constant__ EnvParams P, const int32_t *__restrict__ a
     bs[BS_SPEED1_SLOW] = S.s1; bs[BS_SPEED2_SLOW] = S.s2;
     bs[BS_FLAGS] = __int_as_float(S.flags);
     bs[BS_STEP] = __int_as_float(step + 1);
-    bs[BS_RNG_POS] = __int_as_float(rng.pos);
-#pragma unroll
-    for (int j = 0; j < 10; j++) es[ES_RNG0 + j] = s_rng[j][tid];
+    bs[BS_RNG_POS] = __int_as_float(cursor);
     es[ES_SX] = st.x;
     es[ES_SY] = st.y;
     es[ES_ENTRY_PRESSURE] = st.curved ? cur_pressure_var : pressure;
     es[ES_HAVE_START] = 1.0;
     dab_count[2 * b] = n_dabs;
     dab_count[2 * b + 1] = color_idx;
-    if (overflow) atomicOr(status, 1);
+    if (err) atomicOr(status, err);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -840,10 +816,11 @@ cudaError_t launch_reset(const EnvParams &P, uint16_t *canvas, float *bs, double
     return cudaGetLastError();
 }
 cudaError_t launch_expand(const EnvParams &P, const int32_t *actions, float *bs, double *es,
-                          float *dabs, int32_t *dab_count, int32_t *status, cudaStream_t st)
+                          float *dabs, int32_t *dab_count, int32_t *status, const float *gauss_tab,
+                          cudaStream_t st)
 {
     const int blocks = (P.B + kExpandThreads - 1) / kExpandThreads;
-    expand_kernel<<<blocks, kExpandThreads, 0, st>>>(P, actions, bs, es, dabs, dab_count, status);
+    expand_kernel<<<blocks, kExpandThreads, 0, st>>>(P, actions, bs, es, dabs, dab_count, status, gauss_tab);
     return cudaGetLastError();
 }
 cudaError_t launch_composite(const EnvParams &P, uint16_t *canvas, const float *dabs,

@@ -15,11 +15,11 @@ enum {
     BS_SPEED1_SLOW, BS_SPEED2_SLOW,
     BS_FLAGS,      // int bits: 1 = reset_requested, 2 = settings_value[] initialised
     BS_STEP,       // int: env._step
-    BS_RNG_POS,    // int: values already consumed from the current RNG block (0..10)
+    BS_RNG_POS,    // int: rng-double stream position (values consumed since the Brush was created)
 };
 // env_state double[B,16]
 enum {
-    ES_RNG0 = 0,             // [0..9] current RNG output block
+    ES_RNG0 = 0,             // [0..9] first RNG output block after seeding (informational)
     ES_SX = 10, ES_SY = 11,  // env.s_x, env.s_y
     ES_ENTRY_PRESSURE = 12,
     ES_HAVE_START = 13,      // 0.0 while s_x is None
@@ -44,6 +44,8 @@ struct EnvParams {
     int idx_jump, idx_control, idx_end, idx_pressure, idx_size, idx_color;
     int n_colors, colorize, dither, max_dabs;
     int uses_speed1, uses_speed2;
+    int mapped_mask;             // bit s set: dyn[s] has at least one input mapping
+    int rng_table_len;           // entries of the rand_gauss table (stream positions)
     double lin[64];
     double pressures[8];
     double sizes[8];
@@ -53,6 +55,7 @@ struct EnvParams {
     double default_pressure, default_size, head, tail, entry_pressure0;
     MapDev dyn[kDyn];
     float slow_tracking;
+    float track_fac[2];          // 1 - exp_decay(slow_tracking, 100*dtime) for dtime = 0.1, 1.0
     float sp_gamma[2], sp_m[2], sp_q[2];
     float dabs_basic, dabs_actual, dabs_second;
     float cs, sn, l2, rad_area_1;

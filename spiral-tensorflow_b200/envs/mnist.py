@@ -107,6 +107,7 @@ class MNIST(Environment):
         self.status = torch.zeros((1,), dtype=torch.int32, device=dev)
         self._actions = torch.empty((B, len(self.acs)), dtype=torch.int32, device=dev)
         self._reward = torch.zeros((B,), dtype=torch.float32, device=dev)
+        self._zero_reward = torch.zeros((B,), dtype=torch.float32, device=dev)
         self._step = 0
         self.random_target = None
         self.z = None
@@ -129,6 +130,8 @@ class MNIST(Environment):
         cfg.colorize = int(self.colorize)
         cfg.dither = 1 if getattr(self.args, "dither", True) else 0
         cfg.max_dabs = self.max_dabs
+        # every Brush walks the same seed-1000 stream; one episode draws at most ~64k values per step
+        cfg.rng_table_len = int(min(1 << 24, max(1 << 16, (self.episode_length + 1) * 65536)))
         lin = np.linspace(0, self.screen_size - 0, self.location_size)
         for i, v in enumerate(lin):
             cfg.lin[i] = v
@@ -205,14 +208,18 @@ class MNIST(Environment):
                                                self.num_envs, n, N.stream_ptr()), "spiral_l2_reward")
             reward = self._reward
         else:
-            reward = torch.zeros_like(self._reward)
+            reward = self._zero_reward
         return self.state, reward, terminal, {}
 
     def check_status(self):
         """Synchronising check of the device-side overflow flag (pending-dab list too small)."""
-        if int(self.status.item()) != 0:
+        st = int(self.status.item())
+        if st & 1:
             raise RuntimeError("a canvas produced more than max_dabs=%d dabs in one step; "
                                "re-create the env with a larger max_dabs" % self.max_dabs)
+        if st & 2:
+            raise RuntimeError("a canvas consumed more random numbers than the tabulated stream holds "
+                               "(episode longer than episode_length=%d?)" % self.episode_length)
 
     @property
     def image(self):
