@@ -1,0 +1,203 @@
+"""CPU-only checks (-m "not gpu"): the C-ABI library loads and exports every symbol the header
+declares, the product fails loudly without a CUDA device, and the host-side logic (brush
+compilation, colours, dither table, action order, config, debug env, sharding + gloo all-reduce)
+agrees with the oracle / the reference's documented behaviour."""
+import ctypes as C
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+import spiral_b200 as sp
+from oracle import paint_oracle as po
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _mod(name):
+    from importlib import import_module
+    return import_module(sp.__name__ + "." + name)
+
+
+def test_library_exports_every_header_symbol():
+    hdr = open(os.path.join(ROOT, "include", "spiral_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(spiral_[a-z0-9_]+)\s*\(", hdr))
+    assert declared == set(sp._native.SYMBOLS), declared ^ set(sp._native.SYMBOLS)
+    lib = sp._native.lib()                    # raises if the .so is missing or a symbol is absent
+    for name in declared:
+        assert getattr(lib, name) is not None
+    assert lib.spiral_version() == sp._native.ABI_VERSION
+    # struct layouts agree with the header's field lists (catches a forgotten field)
+    for cname, cls in (("SpiralEnvCfg", sp._native.SpiralEnvCfg), ("SpiralDiscCfg", sp._native.SpiralDiscCfg),
+                       ("SpiralBrush", sp._native.SpiralBrush), ("SpiralMapping", sp._native.SpiralMapping)):
+        end = hdr.index("} %s;" % cname)
+        body = hdr[hdr.rindex("typedef struct {", 0, end) + len("typedef struct {"):end]
+        fields = re.findall(r"([a-z_0-9]+)(?:\[[^\]]*\])*\s*[,;]", body)
+        assert fields == [f[0] for f in cls._fields_], cname
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="only meaningful on a box without a GPU")
+def test_product_fails_loudly_without_cuda():
+    args = sp.get_args(["--env", "simple_mnist", "--color_channel", "1"])
+    with pytest.raises(Exception):
+        sp.create_env(args, num_envs=2, device="cuda:0")
+
+
+def test_no_oracle_import_in_product():
+    """The oracle is test infrastructure: nothing under the product may import, link or execute it."""
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "spiral-tensorflow_b200")):
+        for f in files:
+            path = os.path.join(dirpath, f)
+            if f.endswith(".py"):
+                text = open(path).read()
+                for needle in ("from oracle", "import oracle", "libpaint_oracle", "paint_oracle"):
+                    assert needle not in text, (f, needle)
+            elif f.endswith((".cu", ".cuh", ".h", ".sh")):
+                text = open(path).read()
+                assert not re.search(r'#include\s*[<"][^>"]*oracle', text), f
+                assert "libpaint_oracle" not in text, f
+
+
+def test_py2_action_order():
+    base = _mod("envs.base")
+    assert base.py2_dict_order(["jump", "control", "end"]) == ["jump", "control", "end"]
+    assert base.py2_dict_order(["pressure", "jump", "size", "control", "end"]) == \
+        ["jump", "pressure", "control", "end", "size"]
+    assert base.py2_dict_order(["color", "shape"]) == ["color", "shape"]
+    for names in (["pressure", "jump", "size", "color", "control", "end"], ["a", "bb", "ccc", "dddd", "e", "f", "g"]):
+        assert base.py2_dict_order(names) == po.py2_dict_order(names)
+
+
+def test_environment_bookkeeping():
+    base = _mod("envs.base")
+
+    class Dummy(base.Environment):
+        action_sizes = [('pressure', [2]), ('jump', [2]), ('size', [2]), ('control', None), ('end', None)]
+
+    args = sp.get_args(["--jump", "False", "--location_size", "8"])
+    env = Dummy(args, num_envs=3)
+    assert env.acs == ["pressure", "control", "end", "size"]          # 'jump' deleted, order kept
+    assert env.action_sizes["control"] == [8, 8] and env.head_sizes == [2, 64, 64, 2]
+    assert env.observation_shape == [64, 64, 3]
+    a = env.random_action(np.random.RandomState(0))
+    assert a.shape == (3, 4) and (a >= 0).all() and (a < np.array(env.head_sizes)).all()
+    assert (env.initial_action == -1).all() and env.initial_action.shape == (3, 4)
+    assert np.allclose(env.denorm(env.norm(np.array([0.0, 127.5, 255.0]))), [0.0, 127.5, 255.0])
+    assert Dummy.action_sizes[1][0] == 'jump'                           # class attribute not mutated
+
+
+def test_config_defaults_and_conditional_override():
+    a = sp.get_args([])
+    assert (a.screen_size, a.location_size, a.color_channel, a.episode_length) == (64, 32, 3, 5)
+    assert (a.lstm_size, a.z_dim, a.disc_dim, a.wgan_lambda, a.entropy_coeff, a.grad_clip) == (256, 10, 64, 20, 0.01, 40)
+    assert a.loss == "gan" and a.conditional is False                  # config.py:91-93
+    assert sp.get_args(["--loss", "l2", "--conditional", "False"]).conditional is True
+    assert sp.config.str2bool("True") and sp.config.str2bool("t") and not sp.config.str2bool("False")
+
+
+def test_brush_compile_and_rejects_unsupported():
+    info = sp.brush.BrushInfo()
+    br = info.compile()
+    assert abs(br.dyn[2].base - 0.6) < 1e-7 and br.dyn[2].n[2] == 2 and br.dyn[0].n[0] == 2
+    assert br.dabs_per_actual_radius == 6.0 and br.slow_tracking == 2.0 and br.elliptical_dab_angle == 90.0
+    assert sp.brush.BrushInfo(info.to_myb()).settings == info.settings   # text round trip
+    assert po.parse_myb(info.to_myb()) == po.parse_myb(po.brush_to_myb())
+    bad = sp.brush.BrushInfo()
+    bad.set_base_value("smudge", 0.5)
+    with pytest.raises(NotImplementedError):
+        bad.compile()
+    bad = sp.brush.BrushInfo(info.to_myb().replace("hardness 0.2", "hardness 0.2 | stroke (0.0 0.0), (1.0 0.5)"))
+    with pytest.raises(NotImplementedError):
+        bad.compile()
+
+
+def test_colours_and_dither_table_match_oracle():
+    assert (sp.brush.dither_table() == po.dither_table()).all()
+    names = ["control", "end", "color", "jump", "pressure", "size"]
+    env = po.OracleBatchEnv(po.EnvSpec(action_names=names, location_size=32, n_color=8), 1, channels=3)
+    env.enable_logs()
+    for ci in range(8):
+        env.reset()
+        env.step(np.array([[0, 100, ci, 0, 0, 0]]))
+        env.pop_dabs(0)
+        env.step(np.array([[300, 900, ci, 0, 0, 0]]))
+        d = env.pop_dabs(0)
+        assert len(d) > 10
+        want = sp.brush.color_fix15(po.PALETTE[ci])
+        assert (d["r"] == want[0]).all() and (d["g"] == want[1]).all() and (d["b"] == want[2]).all(), ci
+    assert sp.brush.brush_color_fix15(sp.brush.BrushInfo()) == [0, 0, 0]
+
+
+def test_simple_debug_env_runs_on_cpu():
+    # BASELINE "debug" config: --env simple --episode_length=1 --location_size=8 --conditional=True --loss=l2
+    args = sp.get_args(["--env", "simple", "--episode_length", "1", "--location_size", "8", "--loss", "l2"])
+    env = sp.create_env(args, num_envs=2)
+    assert env.acs == ["color", "shape"]
+    state, target, z = env.reset()
+    assert state.shape == (2, 64, 64, 3) and z is None and float(state.min()) == 1.0
+    state, reward, terminal, _ = env.step(np.array([[0, 0], [0, 1]]))
+    assert terminal and state.min() == -1.0
+    # shape 0 = PIL ellipse, shape 1 = rectangle, both black, bbox (0,0,6,6) (simple.py:68,82-85)
+    assert (state[1, :7, :7] == -1.0).all() and state[1, 7, 7, 0] == 1.0
+    assert state[0, 3, 3, 0] == -1.0 and state[0, 0, 0, 0] == 1.0
+    assert ((reward < 0) | (reward == 1.0)).all()                       # simple.py:132-133 override
+
+
+def test_discount_numpy_mirror():
+    rl = _mod("rl_utils")
+    assert np.allclose(rl.discount(np.array([[0.0, 0.0, 1.0]]), 0.99), [[0.9801, 0.99, 1.0]])
+
+
+def test_shard_partitions_cover_the_batch():
+    dm = _mod("distributed")
+    for total, world in ((1024, 8), (1000, 8), (5, 2), (7, 4)):
+        spans = [dm.shard(total, r, world) for r in range(world)]
+        assert spans[0][0] == 0 and sum(c for _, c in spans) == total
+        for (s0, c0), (s1, _) in zip(spans, spans[1:]):
+            assert s0 + c0 == s1
+        assert max(c for _, c in spans) - min(c for _, c in spans) <= 1
+
+
+_WORKER = r'''
+import os, sys, torch, torch.distributed as dist
+sys.path.insert(0, %r)
+import spiral_b200 as sp
+from importlib import import_module
+dm = import_module(sp.__name__ + ".distributed")
+rank, world, _ = dm.init(backend="gloo")
+assert world == 2
+start, count = dm.shard(10, rank, world)
+# per-rank "sum over the local shard" gradients of f(w) = sum_i w * x_i
+x = torch.arange(10, dtype=torch.float32)[start:start + count]
+grads = [x.sum().reshape(1) * torch.ones(3), torch.full((2, 2), float(rank + 1))]
+dm.allreduce_grads_(grads, bucket_bytes=8)
+assert torch.allclose(grads[0], torch.full((3,), 45.0 / 2)), grads[0]     # global sum / world
+assert torch.allclose(grads[1], torch.full((2, 2), 1.5)), grads[1]
+norm = dm.clip_by_global_norm_(grads, 10.0)
+tot = torch.sqrt(sum((g ** 2).sum() for g in grads))
+assert abs(float(tot) - 10.0) < 1e-4 and float(norm) > 10.0
+# global-batch BN statistics from shards == statistics of the gathered batch
+full = torch.arange(20, dtype=torch.float64).reshape(10, 2) ** 1.5
+mine = full[start:start + count]
+ss = torch.stack([mine.sum(0), (mine ** 2).sum(0)])
+mean, var, n = dm.allreduce_bn_stats_(ss, mine.shape[0])
+assert n == 10 and torch.allclose(mean, full.mean(0)) and torch.allclose(var, full.var(0, unbiased=False))
+dist.destroy_process_group()
+print("rank", rank, "ok")
+'''
+
+
+def test_gloo_world2_allreduce_and_sharding(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER % ROOT)
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29517", CUDA_VISIBLE_DEVICES="")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29517", str(script)],
+                         capture_output=True, text=True, env=env, timeout=240)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert out.stdout.count("ok") == 2
