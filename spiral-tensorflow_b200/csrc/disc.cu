@@ -254,6 +254,17 @@ void disc_plan(const SpiralDisc *d, int batch, DiscPlan *pl)
     pl->simt_bytes = off;
 }
 
+int disc_conv0(SpiralDisc *d, const float *x, int batch, float *out, cudaStream_t st)
+{
+    const int H = d->cfg.screen_size, Cin = d->cfg.in_channels, Cout = d->cfg.disc_dim, Ho = H / 2;
+    const size_t smem = (size_t)(19 * 19 * Cin + 25 * Cin * Cout) * sizeof(float);
+    if (smem > 200 * 1024) return spiral_set_error(SPIRAL_EUNSUPPORTED, "layer-0 weights do not fit shared memory");
+    cudaFuncSetAttribute(conv0_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    conv0_kernel<1><<<batch * (Ho / 8) * (Ho / 8), 256, smem, st>>>(x, (const float *)d->w.conv_w[0], (const float *)d->w.conv_b[0],
+                                                                    out, batch, H, Cin, Cout, d->cfg.normalize);
+    return SPIRAL_OK;
+}
+
 int disc_forward_simt(SpiralDisc *d, const float *x, int batch, float *logits, float *probs,
                       float *bn_stats, char *ws, cudaStream_t st)
 {
@@ -269,11 +280,8 @@ int disc_forward_simt(SpiralDisc *d, const float *x, int batch, float *logits, f
         float *part = (float *)(ws + pl.part_off[l]);
         const bool bn = l > 0 && d->cfg.batch_norm;
         if (l == 0) {
-            const size_t smem = (size_t)(19 * 19 * Cin + 25 * Cin * Cout) * sizeof(float);
-            if (smem > 200 * 1024) return spiral_set_error(SPIRAL_EUNSUPPORTED, "layer-0 weights do not fit shared memory");
-            cudaFuncSetAttribute(conv0_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            conv0_kernel<1><<<batch * (Ho / 8) * (Ho / 8), 256, smem, st>>>(x, (const float *)W.conv_w[0],
-                                                                            (const float *)W.conv_b[0], out, batch, H, Cin, Cout, d->cfg.normalize);
+            const int rc = disc_conv0(d, x, batch, out, st);
+            if (rc != SPIRAL_OK) return rc;
         } else {
             const float *in = (const float *)(ws + pl.act_off[l - 1]);
             const float *isc = (const float *)(ws + pl.scale_off[l - 1]);

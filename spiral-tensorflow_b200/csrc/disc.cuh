@@ -36,6 +36,8 @@ __global__ void fill_affine_kernel(float *scale, float *shift, int n, float sc, 
 __global__ void dense_sigmoid_kernel(const float *in, const float *in_scale, const float *in_shift, const float *w,
                                      const float *bias, float *logits, float *probs, int B, int C);
 
+int disc_conv0(SpiralDisc *d, const float *x, int batch, float *out, cudaStream_t st);
+
 // tensor-core path (disc_tc.cu)
 int disc_tc_init(SpiralDisc *d);
 size_t disc_tc_workspace_bytes(const SpiralDisc *d, int batch);

@@ -1,10 +1,540 @@
-// disc_tc.cu -- tcgen05 / TMEM / TMA implicit-GEMM path of the discriminator (placeholder until
-// the kernels land: creating a discriminator with precision != 0 fails loudly).
+// disc_tc.cu -- K2 on the 5th-generation tensor cores: tcgen05.mma + TMEM accumulators, TMA-fed
+// implicit GEMM for the discriminator's 5x5 / stride-2 / 'SAME' convolutions (layers >= 1).
+//
+//   D[M, N] = sum_k A[m, k] * W[n, k]      M = B*Ho*Wo output pixels, N = Cout, K = 25 * Cin
+//
+// * A is never materialised: for kernel tap (ky, kx) and channel chunk c0 the 128 x 64 operand tile
+//   is ONE 4-D TMA box over the NHWC activation tensor, {64 channels, Wo pixels with element
+//   stride 2, rows with element stride 2, images}, whose start coordinate may be -1 or run past
+//   the edge: TMA zero-fills, which is exactly TF 'SAME' padding (1 before / 2 after).
+// * W is packed once per weight update as a K-major [Cout][25*Cin] matrix (2-D TMA).
+// * fp32-equivalent arithmetic from bf16 tensor cores: every fp32 value is split as
+//   x = hi + lo (hi = bf16(x), lo = bf16(x - hi)) and each K step issues three MMAs
+//   (hi*hi + hi*lo + lo*hi) into the same fp32 TMEM accumulator (dropped lo*lo term ~2^-18).
+//   precision 2 issues only hi*hi.
+// * warp roles per CTA (one 128 x BN output tile): warp 0 = TMA producer, warp 1 = MMA issuer
+//   (one elected lane) + TMEM allocator, warps 2..5 = epilogue (tcgen05.ld -> + bias -> fp32 store,
+//   per-channel sum / sum-of-squares partials for the training-mode batch norm that follows).
+//   smem ring of kStages {A_hi, A_lo, W_hi, W_lo} tiles in the 128-byte-swizzled K-major UMMA
+//   layout, full/empty mbarriers, tcgen05.commit releases a stage back to the producer.
+// * kernel taps that fall entirely into the padding for a tile are skipped (layer 5 uses 4 of 25).
 #include "disc.cuh"
 
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include <cstdio>
+#include <cstring>
+#include <new>
+
 namespace spiral {
-int disc_tc_init(SpiralDisc *) { return spiral_set_error(SPIRAL_EUNSUPPORTED, "tensor-core discriminator path not built yet"); }
-size_t disc_tc_workspace_bytes(const SpiralDisc *, int) { return 0; }
-int disc_tc_pack_weights(SpiralDisc *, char *, cudaStream_t) { return SPIRAL_EUNSUPPORTED; }
-int disc_tc_forward(SpiralDisc *, const float *, int, float *, float *, float *, char *, cudaStream_t) { return SPIRAL_EUNSUPPORTED; }
+
+constexpr int kBM = 128;          // tile rows (output pixels)  == UMMA M
+constexpr int kBN = 128;          // tile cols (output channels) == UMMA N
+constexpr int kBK = 64;           // K per stage: 64 bf16 = one 128-byte swizzle row
+constexpr int kStages = 3;
+constexpr int kTcThreads = 192;
+constexpr uint32_t kTileBytes = kBM * kBK * 2;                 // 16 KB (A and W tiles have the same shape)
+constexpr uint32_t kStageBytes = 4 * kTileBytes;               // A_hi, A_lo, W_hi, W_lo
+constexpr uint32_t kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+
+// ---------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t"
+        "}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1, int c2, int c3)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap *map)
+{
+    asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+// K-major, 128-byte swizzle, rows of 128 B, 8-row groups 1024 B apart (cute::UMMA::SmemDescriptor)
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr)
+{
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3fff);        // start address
+    d |= (uint64_t)1 << 16;                            // leading byte offset (unused for swizzled K-major)
+    d |= (uint64_t)(1024 >> 4) << 32;                  // stride byte offset: 8 rows * 128 B
+    d |= (uint64_t)1 << 46;                            // descriptor version (sm_100)
+    d |= (uint64_t)2 << 61;                            // SWIZZLE_128B
+    return d;
+}
+// kind::f16 instruction descriptor: BF16 x BF16 -> FP32, both operands K-major, M x N
+__host__ __device__ constexpr uint32_t umma_idesc(int M, int N)
+{
+    return (1u << 4)                  // c_format  = F32
+           | (1u << 7)                // a_format  = BF16
+           | (1u << 10)               // b_format  = BF16
+           | ((uint32_t)(N >> 3) << 17)
+           | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32])
+{
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; i++) v[i] = __uint_as_float(r[i]);
+}
+
+struct ConvTcParams {
+    int B, H, Cin, Cout;      // input NHWC [B,H,H,Cin]; output [B,H/2,H/2,Cout]
+    int bw, bh, bb;           // A box: Wo pixels, rows, images (bw*bh*bb == 128)
+    int M;                    // B * Ho * Wo
+    int x3;                   // 1: hi*hi + hi*lo + lo*hi ; 0: hi*hi only
+};
+
+__global__ void __launch_bounds__(kTcThreads, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
+               const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
+               const __grid_constant__ ConvTcParams p, const float *__restrict__ bias,
+               float *__restrict__ out, float *__restrict__ bn_partial)
+{
+    extern __shared__ uint8_t smem_raw[];
+    // 1024-byte alignment for the 128-byte swizzle atoms
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t *gen_base = smem_raw + (base - smem_u32(smem_raw));
+    const uint32_t bar_base = base + kStages * kStageBytes;
+    uint64_t *bar_gen = reinterpret_cast<uint64_t *>(gen_base + kStages * kStageBytes);
+    const uint32_t full0 = bar_base, empty0 = bar_base + 8 * kStages, accum_bar = bar_base + 16 * kStages;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bar_gen + 2 * kStages + 1);
+    __shared__ float s_red[4][2][kBN];      // per-epilogue-warp column sums
+    __shared__ float s_tr[4][32][33];       // transpose staging
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m_tile = blockIdx.x, n_tile = blockIdx.y;
+    const int Ho = p.H / 2;
+
+    // tile origin in (image, output row); tiles cover whole output rows
+    const int m0 = m_tile * kBM;
+    const int img0 = m0 / (Ho * Ho);
+    const int oy0 = (m0 % (Ho * Ho)) / Ho;
+    // taps (ky, kx) that touch at least one real input pixel for this tile
+    uint32_t tap_mask = 0;
+    {
+        const int oy_lo = oy0, oy_hi = (p.bb > 1) ? Ho - 1 : oy0 + p.bh - 1;
+        for (int ky = 0; ky < 5; ky++) {
+            const bool y_ok = (2 * oy_hi + ky - 1 >= 0) && (2 * oy_lo + ky - 1 < p.H);
+            for (int kx = 0; kx < 5; kx++) {
+                const bool x_ok = (2 * (Ho - 1) + kx - 1 >= 0) && (kx - 1 < p.H);
+                if (y_ok && x_ok) tap_mask |= 1u << (ky * 5 + kx);
+            }
+        }
+    }
+    const int chunks = p.Cin / kBK;
+    const int n_iter = __popc(tap_mask) * chunks;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStages; s++) {
+            mbar_init(full0 + 8 * s, 1);
+            mbar_init(empty0 + 8 * s, 1);
+        }
+        mbar_init(accum_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        // TMEM: 128 lanes x kBN fp32 columns
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(kBN) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&map_a_hi);
+        tma_prefetch_desc(&map_a_lo);
+        tma_prefetch_desc(&map_w_hi);
+        tma_prefetch_desc(&map_w_lo);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_acc = *tmem_slot;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            int it = 0;
+            for (int tap = 0; tap < 25; tap++) {
+                if (!((tap_mask >> tap) & 1)) continue;
+                const int ky = tap / 5, kx = tap % 5;
+                for (int ch = 0; ch < chunks; ch++, it++) {
+                    const int s = it % kStages;
+                    if (it >= kStages) mbar_wait(empty0 + 8 * s, ((it / kStages) - 1) & 1);
+                    const uint32_t full = full0 + 8 * s;
+                    const uint32_t stage = base + s * kStageBytes;
+                    mbar_expect_tx(full, p.x3 ? kStageBytes : 2 * kTileBytes);
+                    const int c0 = ch * kBK;
+                    const int ix0 = kx - 1, iy0 = 2 * oy0 + ky - 1;
+                    tma_load_4d(stage, &map_a_hi, full, c0, ix0, iy0, img0);
+                    tma_load_2d(stage + 2 * kTileBytes, &map_w_hi, full, tap * p.Cin + c0, n_tile * kBN);
+                    if (p.x3) {
+                        tma_load_4d(stage + kTileBytes, &map_a_lo, full, c0, ix0, iy0, img0);
+                        tma_load_2d(stage + 3 * kTileBytes, &map_w_lo, full, tap * p.Cin + c0, n_tile * kBN);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc(kBM, kBN);
+            for (int it = 0; it < n_iter; it++) {
+                const int s = it % kStages;
+                mbar_wait(full0 + 8 * s, (it / kStages) & 1);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t stage = base + s * kStageBytes;
+                const uint64_t a_hi = umma_desc(stage), a_lo = umma_desc(stage + kTileBytes);
+                const uint64_t w_hi = umma_desc(stage + 2 * kTileBytes), w_lo = umma_desc(stage + 3 * kTileBytes);
+#pragma unroll
+                for (int k = 0; k < kBK / 16; k++) {
+                    const uint64_t adv = (uint64_t)((k * 32) >> 4);       // 16 bf16 = 32 bytes along K
+                    if (p.x3) {
+                        umma_bf16(tmem_acc, a_lo + adv, w_hi + adv, idesc, (it | k) != 0);
+                        umma_bf16(tmem_acc, a_hi + adv, w_lo + adv, idesc, 1);
+                        umma_bf16(tmem_acc, a_hi + adv, w_hi + adv, idesc, 1);
+                    } else {
+                        umma_bf16(tmem_acc, a_hi + adv, w_hi + adv, idesc, (it | k) != 0);
+                    }
+                }
+                umma_commit(empty0 + 8 * s);          // stage free once these MMAs have read it
+            }
+            umma_commit(accum_bar);                   // accumulator complete
+        }
+    } else {
+        // ===== epilogue: warps 2..5 own TMEM lane quarters (warp % 4) =====
+        const int q = warp & 3;
+        mbar_wait(accum_bar, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int row = q * 32 + lane;
+        const int m = m0 + row;
+        const bool row_ok = m < p.M;
+        float *orow = out + (size_t)m * p.Cout + (size_t)n_tile * kBN;
+#pragma unroll 1
+        for (int cb = 0; cb < kBN; cb += 32) {
+            float v[32];
+            tmem_ld32(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)cb, v);
+#pragma unroll
+            for (int j = 0; j < 32; j++) v[j] = row_ok ? v[j] + __ldg(bias + n_tile * kBN + cb + j) : 0.0f;
+            if (row_ok) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4)
+                    *reinterpret_cast<float4 *>(orow + cb + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            }
+            if (bn_partial) {
+                // column sums over this warp's 32 rows via an smem transpose
+#pragma unroll
+                for (int j = 0; j < 32; j++) s_tr[q][lane][j] = v[j];
+                __syncwarp();
+                float s = 0.f, sq = 0.f;
+#pragma unroll
+                for (int r = 0; r < 32; r++) {
+                    const float x = s_tr[q][r][lane];
+                    s += x;
+                    sq += x * x;
+                }
+                s_red[q][0][cb + lane] = s;
+                s_red[q][1][cb + lane] = sq;
+                __syncwarp();
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (bn_partial && threadIdx.x < kBN) {
+        const int c = threadIdx.x;
+        const float s = (s_red[0][0][c] + s_red[1][0][c]) + (s_red[2][0][c] + s_red[3][0][c]);
+        const float sq = (s_red[0][1][c] + s_red[1][1][c]) + (s_red[2][1][c] + s_red[3][1][c]);
+        float *pp = bn_partial + ((size_t)m_tile * p.Cout + n_tile * kBN + c) * 2;
+        pp[0] = s;
+        pp[1] = sq;
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "n"(kBN) : "memory");
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// elementwise helpers: hi/lo split of activations (with the producer's BN + leaky-ReLU applied)
+// and of the packed weights
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void split_bf16(float x, __nv_bfloat16 &hi, __nv_bfloat16 &lo)
+{
+    hi = __float2bfloat16_rn(x);
+    lo = __float2bfloat16_rn(x - __bfloat162float(hi));
+}
+
+// a = lrelu(raw * scale[c] + shift[c]);  raw fp32 NHWC with C channels (C % 4 == 0)
+__global__ void act_split_kernel(const float *__restrict__ raw, const float *__restrict__ scale,
+                                 const float *__restrict__ shift, __nv_bfloat16 *__restrict__ hi,
+                                 __nv_bfloat16 *__restrict__ lo, size_t n4, int C)
+{
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        const float4 v = reinterpret_cast<const float4 *>(raw)[i];
+        const int c = (int)((i * 4) % (size_t)C);
+        const float4 sc = *reinterpret_cast<const float4 *>(scale + c);
+        const float4 sh = *reinterpret_cast<const float4 *>(shift + c);
+        float a[4] = {fmaf(v.x, sc.x, sh.x), fmaf(v.y, sc.y, sh.y), fmaf(v.z, sc.z, sh.z), fmaf(v.w, sc.w, sh.w)};
+        __nv_bfloat16 h[4], l[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            a[j] = a[j] > 0.f ? a[j] : 0.2f * a[j];
+            split_bf16(a[j], h[j], l[j]);
+        }
+        reinterpret_cast<uint2 *>(hi)[i] = make_uint2(
+            (uint32_t)__bfloat16_as_ushort(h[0]) | ((uint32_t)__bfloat16_as_ushort(h[1]) << 16),
+            (uint32_t)__bfloat16_as_ushort(h[2]) | ((uint32_t)__bfloat16_as_ushort(h[3]) << 16));
+        reinterpret_cast<uint2 *>(lo)[i] = make_uint2(
+            (uint32_t)__bfloat16_as_ushort(l[0]) | ((uint32_t)__bfloat16_as_ushort(l[1]) << 16),
+            (uint32_t)__bfloat16_as_ushort(l[2]) | ((uint32_t)__bfloat16_as_ushort(l[3]) << 16));
+    }
+}
+
+// HWIO [25][Cin][Cout] fp32 -> K-major [Cout][25*Cin] bf16 hi / lo
+__global__ void weight_pack_kernel(const float *__restrict__ w, __nv_bfloat16 *__restrict__ hi,
+                                   __nv_bfloat16 *__restrict__ lo, int Cin, int Cout)
+{
+    const size_t total = (size_t)25 * Cin * Cout;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const int n = (int)(i / ((size_t)25 * Cin));
+        const int k = (int)(i % ((size_t)25 * Cin));        // tap * Cin + c
+        const float x = w[(size_t)k * Cout + n];
+        split_bf16(x, hi[i], lo[i]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+struct DiscTc {
+    EncodeTiledFn encode;
+    int first_tc_layer;       // layers >= this use tensor cores (needs Cin % 64 == 0 and Cout % 128 == 0)
+};
+
+static size_t tc_layer_act_elems(const DiscPlan &pl, int l, int batch) { return (size_t)batch * pl.H[l] * pl.H[l] * pl.Cin[l]; }
+
+struct TcOffsets {
+    size_t act_hi[SPIRAL_DISC_MAX_LAYERS], act_lo[SPIRAL_DISC_MAX_LAYERS];
+    size_t w_hi[SPIRAL_DISC_MAX_LAYERS], w_lo[SPIRAL_DISC_MAX_LAYERS];
+    size_t bytes;
+};
+
+static void tc_plan(const SpiralDisc *d, int batch, const DiscPlan &pl, TcOffsets *o)
+{
+    // the tensor-core region follows the fp32 region; weights first (their offsets must not depend on batch)
+    size_t off = 0;
+    for (int l = 1; l < d->n_layers; l++) {
+        const size_t wn = (size_t)25 * pl.Cin[l] * pl.Cout[l];
+        o->w_hi[l] = off; off += disc_align(wn * 2);
+        o->w_lo[l] = off; off += disc_align(wn * 2);
+    }
+    for (int l = 1; l < d->n_layers; l++) {
+        const size_t an = tc_layer_act_elems(pl, l, batch);
+        o->act_hi[l] = off; off += disc_align(an * 2);
+        o->act_lo[l] = off; off += disc_align(an * 2);
+    }
+    o->bytes = off;
+}
+
+int disc_tc_init(SpiralDisc *d)
+{
+    if (d->cfg.disc_dim < 64 || (d->cfg.disc_dim % 64) != 0)
+        return spiral_set_error(SPIRAL_EUNSUPPORTED,
+                                "tensor-core discriminator needs disc_dim %% 64 == 0 (got %d); use precision 0", d->cfg.disc_dim);
+    DiscTc *t = new (std::nothrow) DiscTc();
+    if (!t) return spiral_set_error(SPIRAL_EINVAL, "out of host memory");
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || !fn || qres != cudaDriverEntryPointSuccess) {
+        delete t;
+        return spiral_set_error(SPIRAL_ECUDA, "cuTensorMapEncodeTiled is not available from the driver");
+    }
+    t->encode = (EncodeTiledFn)fn;
+    t->first_tc_layer = 1;
+    e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+    if (e != cudaSuccess) {
+        delete t;
+        return spiral_cuda_error(e, "cudaFuncSetAttribute(conv_tc_kernel)");
+    }
+    d->tc = t;
+    return SPIRAL_OK;
+}
+
+size_t disc_tc_workspace_bytes(const SpiralDisc *d, int batch)
+{
+    DiscPlan pl;
+    disc_plan(d, batch, &pl);
+    TcOffsets o;
+    tc_plan(d, batch, pl, &o);
+    return o.bytes;
+}
+
+// the fp32 region is sized for max_batch so that the tensor-core region (and the packed weights in
+// it) sits at a fixed offset regardless of the batch of a particular call
+static char *tc_region(const SpiralDisc *d, char *ws)
+{
+    DiscPlan plmax;
+    disc_plan(d, d->cfg.max_batch, &plmax);
+    return ws + plmax.simt_bytes;
+}
+
+int disc_tc_pack_weights(SpiralDisc *d, char *ws, cudaStream_t st)
+{
+    DiscPlan pl;
+    disc_plan(d, d->cfg.max_batch, &pl);
+    TcOffsets o;
+    tc_plan(d, d->cfg.max_batch, pl, &o);
+    char *tc = tc_region(d, ws);
+    for (int l = 1; l < d->n_layers; l++) {
+        weight_pack_kernel<<<148 * 4, 256, 0, st>>>((const float *)d->w.conv_w[l], (__nv_bfloat16 *)(tc + o.w_hi[l]),
+                                                    (__nv_bfloat16 *)(tc + o.w_lo[l]), pl.Cin[l], pl.Cout[l]);
+    }
+    const cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? SPIRAL_OK : spiral_cuda_error(e, "disc_tc_pack_weights");
+}
+
+static int encode_act_map(const DiscTc *t, CUtensorMap *map, void *ptr, int B, int H, int C, int bw, int bh, int bb)
+{
+    const cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)H, (cuuint64_t)H, (cuuint64_t)B};
+    const cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)C * 2 * H, (cuuint64_t)C * 2 * H * H};
+    // traversal stride 2 in W and H: boxDim = elements loaded * elementStride
+    const cuuint32_t box[4] = {(cuuint32_t)kBK, (cuuint32_t)(bw * 2), (cuuint32_t)(bh * 2), (cuuint32_t)bb};
+    const cuuint32_t estr[4] = {1, 2, 2, 1};
+    const CUresult r = t->encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, ptr, dims, strides, box, estr,
+                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                 CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : (int)r;
+}
+
+static int encode_w_map(const DiscTc *t, CUtensorMap *map, void *ptr, int K, int N)
+{
+    const cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)N};
+    const cuuint64_t strides[1] = {(cuuint64_t)K * 2};
+    const cuuint32_t box[2] = {(cuuint32_t)kBK, (cuuint32_t)kBN};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = t->encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, ptr, dims, strides, box, estr,
+                                 CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                 CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : (int)r;
+}
+
+int disc_tc_forward(SpiralDisc *d, const float *x, int batch, float *logits, float *probs, float *bn_stats,
+                    char *ws, cudaStream_t st)
+{
+    const DiscTc *t = (const DiscTc *)d->tc;
+    DiscPlan pl;
+    disc_plan(d, batch, &pl);                       // fp32 raw outputs, partials, scale/shift (offsets for this batch)
+    DiscPlan plmax;
+    disc_plan(d, d->cfg.max_batch, &plmax);
+    TcOffsets o;
+    tc_plan(d, d->cfg.max_batch, plmax, &o);        // offsets fixed by max_batch
+    char *tc = tc_region(d, ws);
+    const SpiralDiscWeights &W = d->w;
+    const int maxC = d->cfg.disc_dim << (d->n_layers - 1);
+    const int x3 = d->cfg.precision == 1;
+
+    // layer 0 (K = 25 * C, C in {1,3,6}): direct fp32 convolution
+    int rc = disc_conv0(d, x, batch, (float *)(ws + pl.act_off[0]), st);
+    if (rc != SPIRAL_OK) return rc;
+    fill_affine_kernel<<<(pl.Cout[0] + 127) / 128, 128, 0, st>>>((float *)(ws + pl.scale_off[0]), (float *)(ws + pl.shift_off[0]),
+                                                                  pl.Cout[0], 1.0f, 0.0f);
+    for (int l = 1; l < d->n_layers; l++) {
+        const int H = pl.H[l], Cin = pl.Cin[l], Cout = pl.Cout[l], Ho = H / 2;
+        // producer's BN + leaky-ReLU, then hi/lo split of this layer's input
+        const size_t n4 = tc_layer_act_elems(pl, l, batch) / 4;
+        __nv_bfloat16 *ahi = (__nv_bfloat16 *)(tc + o.act_hi[l]), *alo = (__nv_bfloat16 *)(tc + o.act_lo[l]);
+        const int blocks = (int)((n4 + 255) / 256 < (size_t)(148 * 8) ? (n4 + 255) / 256 : (size_t)(148 * 8));
+        act_split_kernel<<<blocks, 256, 0, st>>>((const float *)(ws + pl.act_off[l - 1]), (const float *)(ws + pl.scale_off[l - 1]),
+                                                  (const float *)(ws + pl.shift_off[l - 1]), ahi, alo, n4, Cin);
+        ConvTcParams p;
+        p.B = batch; p.H = H; p.Cin = Cin; p.Cout = Cout; p.M = batch * Ho * Ho; p.x3 = x3;
+        if (Ho * Ho >= kBM) { p.bw = Ho; p.bh = kBM / Ho; p.bb = 1; }
+        else { p.bw = Ho; p.bh = Ho; p.bb = kBM / (Ho * Ho); }
+        CUtensorMap ma_hi, ma_lo, mw_hi, mw_lo;
+        int er = encode_act_map(t, &ma_hi, ahi, batch, H, Cin, p.bw, p.bh, p.bb);
+        er |= encode_act_map(t, &ma_lo, alo, batch, H, Cin, p.bw, p.bh, p.bb);
+        er |= encode_w_map(t, &mw_hi, tc + o.w_hi[l], 25 * Cin, Cout);
+        er |= encode_w_map(t, &mw_lo, tc + o.w_lo[l], 25 * Cin, Cout);
+        if (er) return spiral_set_error(SPIRAL_ECUDA, "cuTensorMapEncodeTiled failed for layer %d (CUresult %d)", l, er);
+        const int mtiles = (p.M + kBM - 1) / kBM;
+        const bool bn = d->cfg.batch_norm != 0;
+        float *part = (float *)(ws + pl.part_off[l]);
+        dim3 grid(mtiles, Cout / kBN);
+        conv_tc_kernel<<<grid, kTcThreads, kSmemBytes, st>>>(ma_hi, ma_lo, mw_hi, mw_lo, p, (const float *)W.conv_b[l],
+                                                            (float *)(ws + pl.act_off[l]), bn ? part : nullptr);
+        float *scale = (float *)(ws + pl.scale_off[l]), *shift = (float *)(ws + pl.shift_off[l]);
+        if (bn) {
+            bn_finalize_kernel<<<(Cout + 127) / 128, 128, 0, st>>>(part, mtiles, Cout, (double)batch * Ho * Ho,
+                                                                    (const float *)W.bn_gamma[l], (const float *)W.bn_beta[l], 1e-3f,
+                                                                    scale, shift, bn_stats ? bn_stats + (size_t)l * 2 * maxC : nullptr, maxC);
+        } else {
+            fill_affine_kernel<<<(Cout + 127) / 128, 128, 0, st>>>(scale, shift, Cout, 1.0f, 0.0f);
+        }
+    }
+    const int last = d->n_layers - 1;
+    dense_sigmoid_kernel<<<(batch * 32 + 127) / 128, 128, 0, st>>>(
+        (const float *)(ws + pl.act_off[last]), (const float *)(ws + pl.scale_off[last]), (const float *)(ws + pl.shift_off[last]),
+        (const float *)W.dense_w, (const float *)W.dense_b, logits, probs, batch, pl.Cout[last]);
+    const cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? SPIRAL_OK : spiral_cuda_error(e, "spiral_disc_forward(tensor cores)");
+}
+
 }  // namespace spiral

@@ -77,7 +77,9 @@ def test_a2c_autograd_wrapper_backpropagates():
 
 
 @pytest.mark.parametrize("C,dd,bn,B,prec", [(1, 8, True, 16, "fp32"), (3, 16, True, 8, "fp32"),
-                                            (1, 8, False, 5, "fp32"), (3, 64, True, 4, "fp32")])
+                                            (1, 8, False, 5, "fp32"), (3, 64, True, 4, "fp32"),
+                                            (3, 64, True, 16, "bf16x3"), (1, 64, True, 130, "bf16x3"),
+                                            (3, 64, False, 8, "bf16x3"), (3, 64, True, 16, "bf16")])
 def test_discriminator_forward_matches_oracle(C, dd, bn, B, prec):
     sp = _sp()
     from oracle import disc_oracle as do
@@ -98,8 +100,11 @@ def test_discriminator_forward_matches_oracle(C, dd, bn, B, prec):
     probs, logits = D.forward(torch.tensor(imgs, device="cuda"))
     want_p, want_l = do.predict(imgs, w, batch_norm=bn, dtype=torch.float64)
     lg = logits.cpu().numpy()
-    assert np.abs(lg - want_l).max() <= 1e-4 * max(1.0, np.abs(want_l).max()), (lg, want_l)
-    assert np.abs(probs.cpu().numpy() - want_p).max() <= 1e-4
+    # fp32 and bf16x3 (fp32-equivalent split) meet the north-star 1e-4; plain bf16 is the fast,
+    # non-parity mode and is only held to 3e-2
+    tol = 3e-2 if prec == "bf16" else 1e-4
+    assert np.abs(lg - want_l).max() <= tol * max(1.0, np.abs(want_l).max()), (lg, want_l)
+    assert np.abs(probs.cpu().numpy() - want_p).max() <= tol
     # BN statistics that were used (mean / biased variance of the scored batch)
     if bn:
         x = do.norm_fn(torch.tensor(imgs, dtype=torch.float64))
@@ -107,5 +112,6 @@ def test_discriminator_forward_matches_oracle(C, dd, bn, B, prec):
         got = D.bn_stats.cpu().numpy()
         for l, (m, v) in enumerate(stats, start=1):
             n = m.numel()
-            assert np.allclose(got[l, 0, :n], m.numpy(), rtol=1e-3, atol=1e-4)
-            assert np.allclose(got[l, 1, :n], v.numpy(), rtol=1e-3, atol=1e-5)
+            rt = 5e-2 if prec == "bf16" else 1e-3
+            assert np.allclose(got[l, 0, :n], m.numpy(), rtol=rt, atol=rt * 0.1), l
+            assert np.allclose(got[l, 1, :n], v.numpy(), rtol=rt, atol=rt * 0.01), l
