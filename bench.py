@@ -46,7 +46,7 @@ def parse():
     p.add_argument("--impl", default="ours", choices=["ours", "reference"])
     p.add_argument("--canvases", type=int, default=WORKLOAD["canvases_per_gpu"], help="canvases per GPU")
     p.add_argument("--episode_length", type=int, default=WORKLOAD["episode_length"])
-    p.add_argument("--disc_precision", default=os.environ.get("SPIRAL_DISC_PRECISION", "fp32"))
+    p.add_argument("--disc_precision", default=os.environ.get("SPIRAL_DISC_PRECISION", "bf16x3"))
     p.add_argument("--no_cpu_baseline", action="store_true")
     p.add_argument("--cpu_seconds", type=float, default=15.0, help="target seconds of the bounded CPU sample")
     p.add_argument("--jump", default="True")

@@ -8,6 +8,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -202,6 +203,11 @@ extern "C" int spiral_env_create(const SpiralEnvCfg *cfg, SpiralEnv **out)
     P.uses_speed1 = P.uses_speed2 = 0;
     P.mapped_mask = 0;
     P.rng_table_len = cfg->rng_table_len;
+    {
+        const char *e = getenv("SPIRAL_EXPAND_LANES");      // tuning knob for profiling
+        P.expand_lanes = e ? atoi(e) : 0;
+        if (P.expand_lanes < 0 || P.expand_lanes > 32) P.expand_lanes = 0;
+    }
     for (int s = 0; s < SPIRAL_DYN_COUNT; s++) {
         MapDev &m = P.dyn[s];
         m.base = br.dyn[s].base;

@@ -14,6 +14,8 @@
 // dense + sigmoid).  The tcgen05 implicit-GEMM path lives in disc_tc.cu.
 #include "disc.cuh"
 
+#include <cuda_bf16.h>
+
 #include <cmath>
 #include <cstring>
 #include <new>
@@ -24,12 +26,15 @@ namespace spiral {
 // layer 0: direct convolution, (x - 127.5) / 127.5 on load, bias, no BN; raw output + (optional)
 // nothing else -- the consumer applies leaky-ReLU on load.   One CTA = 8x8 output pixels.
 // ------------------------------------------------------------------------------------------
-template <int COUT_PER_THREAD>
+// Thread = one output pixel x G (8 or 16) output channels (register tile), CTA = 8x8 pixels x Cout.
+// SPLIT = true writes leaky-ReLU(out) directly as the bf16 hi/lo pair the tensor-core layer 1
+// reads (no BN at layer 0), SPLIT = false writes the raw fp32 output.
+template <bool SPLIT, int G>
 __global__ void __launch_bounds__(256)
 conv0_kernel(const float *__restrict__ x, const float *__restrict__ w, const float *__restrict__ bias,
-             float *__restrict__ out, int B, int H, int Cin, int Cout, int normalize)
+             float *__restrict__ out, __nv_bfloat16 *__restrict__ out_hi, __nv_bfloat16 *__restrict__ out_lo,
+             int B, int H, int Cin, int Cout, int normalize)
 {
-    // H = W = input size; output H/2
     extern __shared__ float sm[];
     const int Ho = H / 2;
     const int tiles = Ho / 8;
@@ -37,7 +42,7 @@ conv0_kernel(const float *__restrict__ x, const float *__restrict__ w, const flo
     const int trem = blockIdx.x % (tiles * tiles);
     const int oy0 = (trem / tiles) * 8, ox0 = (trem % tiles) * 8;
     float *s_in = sm;                         // [19][19][Cin] normalised, zero padded
-    float *s_w = sm + 19 * 19 * Cin;          // [25*Cin][Cout]
+    float *s_w = sm + ((19 * 19 * Cin + 3) & ~3);   // [25*Cin][Cout], 16-byte aligned
     const int tid = threadIdx.x;
     for (int i = tid; i < 19 * 19 * Cin; i += 256) {
         const int c = i % Cin;
@@ -51,20 +56,56 @@ conv0_kernel(const float *__restrict__ x, const float *__restrict__ w, const flo
         }
         s_in[i] = v;
     }
-    for (int i = tid; i < 25 * Cin * Cout; i += 256) s_w[i] = w[i];
+    for (int i = tid; i < 25 * Cin * Cout / 4; i += 256)
+        reinterpret_cast<float4 *>(s_w)[i] = reinterpret_cast<const float4 *>(w)[i];
     __syncthreads();
-    // thread -> pixel (tid % 64), channel group (tid / 64): Cout/4 channels each, strided by 4
-    const int p = tid & 63, cg = tid >> 6;
-    const int py = p >> 3, px = p & 7;
-    for (int co = cg; co < Cout; co += 4) {
-        float acc = bias[co];
+    const int ngroups = Cout / G;                        // channel groups of G
+    // warp = 32 pixels of one channel group (weights broadcast across the warp)
+    for (int item = tid; item < 64 * ngroups; item += 256) {
+        const int p = item & 63, cg = item >> 6;
+        const int py = p >> 3, px = p & 7;
+        float acc[G];
+#pragma unroll
+        for (int j = 0; j < G; j++) acc[j] = bias[cg * G + j];
         for (int ky = 0; ky < 5; ky++)
             for (int kx = 0; kx < 5; kx++) {
                 const float *ip = s_in + ((2 * py + ky) * 19 + (2 * px + kx)) * Cin;
-                const float *wp = s_w + ((ky * 5 + kx) * Cin) * Cout + co;
-                for (int c = 0; c < Cin; c++) acc = fmaf(ip[c], wp[c * Cout], acc);
+                const float *wp = s_w + ((ky * 5 + kx) * Cin) * Cout + cg * G;
+                for (int c = 0; c < Cin; c++) {
+                    const float a = ip[c];
+#pragma unroll
+                    for (int j = 0; j < G; j += 4) {
+                        const float4 w4 = *reinterpret_cast<const float4 *>(wp + c * Cout + j);
+                        acc[j] = fmaf(a, w4.x, acc[j]); acc[j + 1] = fmaf(a, w4.y, acc[j + 1]);
+                        acc[j + 2] = fmaf(a, w4.z, acc[j + 2]); acc[j + 3] = fmaf(a, w4.w, acc[j + 3]);
+                    }
+                }
             }
-        out[(((size_t)b * Ho + oy0 + py) * Ho + ox0 + px) * Cout + co] = acc;
+        const size_t o = (((size_t)b * Ho + oy0 + py) * Ho + ox0 + px) * Cout + cg * G;
+        if (SPLIT) {
+            uint32_t h[G / 2], l[G / 2];
+#pragma unroll
+            for (int j = 0; j < G / 2; j++) {
+                float a0 = acc[2 * j], a1 = acc[2 * j + 1];
+                a0 = a0 > 0.f ? a0 : 0.2f * a0;
+                a1 = a1 > 0.f ? a1 : 0.2f * a1;
+                const __nv_bfloat16 h0 = __float2bfloat16_rn(a0), h1 = __float2bfloat16_rn(a1);
+                const __nv_bfloat16 l0 = __float2bfloat16_rn(a0 - __bfloat162float(h0));
+                const __nv_bfloat16 l1 = __float2bfloat16_rn(a1 - __bfloat162float(h1));
+                h[j] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+                l[j] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+            }
+            uint4 *ph = reinterpret_cast<uint4 *>(out_hi + o), *pl = reinterpret_cast<uint4 *>(out_lo + o);
+#pragma unroll
+            for (int j = 0; j < G / 8; j++) {
+                ph[j] = make_uint4(h[4 * j], h[4 * j + 1], h[4 * j + 2], h[4 * j + 3]);
+                pl[j] = make_uint4(l[4 * j], l[4 * j + 1], l[4 * j + 2], l[4 * j + 3]);
+            }
+        } else {
+            float4 *po = reinterpret_cast<float4 *>(out + o);
+#pragma unroll
+            for (int j = 0; j < G / 4; j++) po[j] = make_float4(acc[4 * j], acc[4 * j + 1], acc[4 * j + 2], acc[4 * j + 3]);
+        }
     }
 }
 
@@ -175,20 +216,31 @@ conv_simt_kernel(const float *__restrict__ in, const float *__restrict__ in_scal
     }
 }
 
-// per-channel reduction of the partials in fixed order (float64), then the affine the consumer
-// applies on load:  scale = gamma * rsqrt(var + eps), shift = beta - mean * scale
-__global__ void bn_finalize_kernel(const float *__restrict__ partial, int n_part, int Cout, double count,
-                                   const float *__restrict__ gamma, const float *__restrict__ beta,
-                                   float eps, float *__restrict__ scale, float *__restrict__ shift,
-                                   float *__restrict__ stats, int stats_stride)
+// per-channel reduction of the partials in a fixed order (float64: deterministic, no atomics), then
+// the affine the consumer applies on load:  scale = gamma * rsqrt(var + eps), shift = beta - mean * scale
+// CTA = 32 channels x 8 partial-groups; loads are coalesced float2 (sum, sum of squares).
+__global__ void __launch_bounds__(256)
+bn_finalize_kernel(const float *__restrict__ partial, int n_part, int Cout, double count,
+                   const float *__restrict__ gamma, const float *__restrict__ beta,
+                   float eps, float *__restrict__ scale, float *__restrict__ shift,
+                   float *__restrict__ stats, int stats_stride)
 {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= Cout) return;
+    __shared__ double s_s[8][32], s_q[8][32];
+    const int cl = threadIdx.x & 31, g = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + cl;
     double s = 0.0, q = 0.0;
-    for (int i = 0; i < n_part; i++) {
-        s += (double)partial[((size_t)i * Cout + c) * 2];
-        q += (double)partial[((size_t)i * Cout + c) * 2 + 1];
+    if (c < Cout) {
+        for (int i = g; i < n_part; i += 8) {
+            const float2 v = *reinterpret_cast<const float2 *>(partial + ((size_t)i * Cout + c) * 2);
+            s += (double)v.x;
+            q += (double)v.y;
+        }
     }
+    s_s[g][cl] = s;
+    s_q[g][cl] = q;
+    __syncthreads();
+    if (g != 0 || c >= Cout) return;
+    for (int k = 1; k < 8; k++) { s += s_s[k][cl]; q += s_q[k][cl]; }
     const double mean = s / count;
     double var = q / count - mean * mean;
     if (var < 0.0) var = 0.0;
@@ -254,14 +306,24 @@ void disc_plan(const SpiralDisc *d, int batch, DiscPlan *pl)
     pl->simt_bytes = off;
 }
 
-int disc_conv0(SpiralDisc *d, const float *x, int batch, float *out, cudaStream_t st)
+int disc_conv0(SpiralDisc *d, const float *x, int batch, float *out, void *out_hi, void *out_lo, cudaStream_t st)
 {
     const int H = d->cfg.screen_size, Cin = d->cfg.in_channels, Cout = d->cfg.disc_dim, Ho = H / 2;
-    const size_t smem = (size_t)(19 * 19 * Cin + 25 * Cin * Cout) * sizeof(float);
+    const size_t smem = (size_t)(((19 * 19 * Cin + 3) & ~3) + 25 * Cin * Cout) * sizeof(float);
     if (smem > 200 * 1024) return spiral_set_error(SPIRAL_EUNSUPPORTED, "layer-0 weights do not fit shared memory");
-    cudaFuncSetAttribute(conv0_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    conv0_kernel<1><<<batch * (Ho / 8) * (Ho / 8), 256, smem, st>>>(x, (const float *)d->w.conv_w[0], (const float *)d->w.conv_b[0],
-                                                                    out, batch, H, Cin, Cout, d->cfg.normalize);
+    const int grid = batch * (Ho / 8) * (Ho / 8);
+    const float *w0 = (const float *)d->w.conv_w[0], *b0 = (const float *)d->w.conv_b[0];
+    if (out_hi) {        // tensor-core path: disc_dim % 64 == 0
+        cudaFuncSetAttribute(conv0_kernel<true, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        conv0_kernel<true, 16><<<grid, 256, smem, st>>>(x, w0, b0, nullptr, (__nv_bfloat16 *)out_hi, (__nv_bfloat16 *)out_lo,
+                                                        batch, H, Cin, Cout, d->cfg.normalize);
+    } else if (Cout % 16 == 0) {
+        cudaFuncSetAttribute(conv0_kernel<false, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        conv0_kernel<false, 16><<<grid, 256, smem, st>>>(x, w0, b0, out, nullptr, nullptr, batch, H, Cin, Cout, d->cfg.normalize);
+    } else {
+        cudaFuncSetAttribute(conv0_kernel<false, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        conv0_kernel<false, 8><<<grid, 256, smem, st>>>(x, w0, b0, out, nullptr, nullptr, batch, H, Cin, Cout, d->cfg.normalize);
+    }
     return SPIRAL_OK;
 }
 
@@ -280,7 +342,7 @@ int disc_forward_simt(SpiralDisc *d, const float *x, int batch, float *logits, f
         float *part = (float *)(ws + pl.part_off[l]);
         const bool bn = l > 0 && d->cfg.batch_norm;
         if (l == 0) {
-            const int rc = disc_conv0(d, x, batch, out, st);
+            const int rc = disc_conv0(d, x, batch, out, nullptr, nullptr, st);
             if (rc != SPIRAL_OK) return rc;
         } else {
             const float *in = (const float *)(ws + pl.act_off[l - 1]);
@@ -291,7 +353,7 @@ int disc_forward_simt(SpiralDisc *d, const float *x, int batch, float *logits, f
                                                    out, bn ? part : nullptr, batch, H, Cin, Cout);
         }
         if (bn) {
-            bn_finalize_kernel<<<(Cout + 127) / 128, 128, 0, st>>>(part, pl.mtiles[l], Cout, (double)batch * Ho * Ho,
+            bn_finalize_kernel<<<(Cout + 31) / 32, 256, 0, st>>>(part, pl.mtiles[l], Cout, (double)batch * Ho * Ho,
                                                                     (const float *)W.bn_gamma[l], (const float *)W.bn_beta[l],
                                                                     1e-3f, scale, shift,
                                                                     bn_stats ? bn_stats + (size_t)l * 2 * maxC : nullptr, maxC);

@@ -36,7 +36,7 @@ __global__ void fill_affine_kernel(float *scale, float *shift, int n, float sc, 
 __global__ void dense_sigmoid_kernel(const float *in, const float *in_scale, const float *in_shift, const float *w,
                                      const float *bias, float *logits, float *probs, int B, int C);
 
-int disc_conv0(SpiralDisc *d, const float *x, int batch, float *out, cudaStream_t st);
+int disc_conv0(SpiralDisc *d, const float *x, int batch, float *out, void *out_hi, void *out_lo, cudaStream_t st);
 
 // tensor-core path (disc_tc.cu)
 int disc_tc_init(SpiralDisc *d);

@@ -491,18 +491,18 @@ int disc_tc_forward(SpiralDisc *d, const float *x, int batch, float *logits, flo
     const int maxC = d->cfg.disc_dim << (d->n_layers - 1);
     const int x3 = d->cfg.precision == 1;
 
-    // layer 0 (K = 25 * C, C in {1,3,6}): direct fp32 convolution
-    int rc = disc_conv0(d, x, batch, (float *)(ws + pl.act_off[0]), st);
+    // layer 0 (K = 25 * C, C in {1,3,6}): direct fp32 convolution whose epilogue applies the leaky-ReLU
+    // (no BN at layer 0) and writes the bf16 hi/lo pair layer 1 reads
+    int rc = disc_conv0(d, x, batch, nullptr, tc + o.act_hi[1], tc + o.act_lo[1], st);
     if (rc != SPIRAL_OK) return rc;
-    fill_affine_kernel<<<(pl.Cout[0] + 127) / 128, 128, 0, st>>>((float *)(ws + pl.scale_off[0]), (float *)(ws + pl.shift_off[0]),
-                                                                  pl.Cout[0], 1.0f, 0.0f);
     for (int l = 1; l < d->n_layers; l++) {
         const int H = pl.H[l], Cin = pl.Cin[l], Cout = pl.Cout[l], Ho = H / 2;
         // producer's BN + leaky-ReLU, then hi/lo split of this layer's input
         const size_t n4 = tc_layer_act_elems(pl, l, batch) / 4;
         __nv_bfloat16 *ahi = (__nv_bfloat16 *)(tc + o.act_hi[l]), *alo = (__nv_bfloat16 *)(tc + o.act_lo[l]);
         const int blocks = (int)((n4 + 255) / 256 < (size_t)(148 * 8) ? (n4 + 255) / 256 : (size_t)(148 * 8));
-        act_split_kernel<<<blocks, 256, 0, st>>>((const float *)(ws + pl.act_off[l - 1]), (const float *)(ws + pl.scale_off[l - 1]),
+        if (l > 1)
+            act_split_kernel<<<blocks, 256, 0, st>>>((const float *)(ws + pl.act_off[l - 1]), (const float *)(ws + pl.scale_off[l - 1]),
                                                   (const float *)(ws + pl.shift_off[l - 1]), ahi, alo, n4, Cin);
         ConvTcParams p;
         p.B = batch; p.H = H; p.Cin = Cin; p.Cout = Cout; p.M = batch * Ho * Ho; p.x3 = x3;
@@ -522,7 +522,7 @@ int disc_tc_forward(SpiralDisc *d, const float *x, int batch, float *logits, flo
                                                             (float *)(ws + pl.act_off[l]), bn ? part : nullptr);
         float *scale = (float *)(ws + pl.scale_off[l]), *shift = (float *)(ws + pl.shift_off[l]);
         if (bn) {
-            bn_finalize_kernel<<<(Cout + 127) / 128, 128, 0, st>>>(part, mtiles, Cout, (double)batch * Ho * Ho,
+            bn_finalize_kernel<<<(Cout + 31) / 32, 256, 0, st>>>(part, mtiles, Cout, (double)batch * Ho * Ho,
                                                                     (const float *)W.bn_gamma[l], (const float *)W.bn_beta[l], 1e-3f,
                                                                     scale, shift, bn_stats ? bn_stats + (size_t)l * 2 * maxC : nullptr, maxC);
         } else {

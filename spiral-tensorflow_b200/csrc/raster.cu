@@ -211,11 +211,14 @@ __global__ void __launch_bounds__(kExpandThreads)
 expand_kernel(const __grid_constant__ EnvParams P, const int32_t *__restrict__ actions,
               float *__restrict__ brush_state, double *__restrict__ env_state,
               float *__restrict__ dabs, int32_t *__restrict__ dab_count, int32_t *__restrict__ status,
-              const float *__restrict__ gauss_tab)
+              const float *__restrict__ gauss_tab, int lanes)
 {
-    constexpr int NT = kExpandThreads;
+    // `lanes` canvases per warp (1..32, host-chosen): the brush state machine is a latency-bound
+    // serial chain, so with few canvases it pays to give each its own warp (no intra-warp divergence
+    // or load imbalance, more resident warps per SM to hide latency) and leave the other lanes idle.
     const int tid = threadIdx.x;
-    const int b = blockIdx.x * NT + tid;
+    if (tid >= lanes) return;
+    const int b = blockIdx.x * lanes + tid;
     if (b >= P.B) return;
 
     float *bs = brush_state + (size_t)b * kBrushFloats;
@@ -819,8 +822,14 @@ cudaError_t launch_expand(const EnvParams &P, const int32_t *actions, float *bs,
                           float *dabs, int32_t *dab_count, int32_t *status, const float *gauss_tab,
                           cudaStream_t st)
 {
-    const int blocks = (P.B + kExpandThreads - 1) / kExpandThreads;
-    expand_kernel<<<blocks, kExpandThreads, 0, st>>>(P, actions, bs, es, dabs, dab_count, status, gauss_tab);
+    // aim for >= 16 warps per SM before packing more than one canvas into a warp
+    int lanes = P.B / (148 * 16);
+    if (lanes < 1) lanes = 1;
+    if (lanes > 32) lanes = 32;
+    while (lanes & (lanes - 1)) lanes &= lanes - 1;      // round down to a power of two
+    if (P.expand_lanes > 0) lanes = P.expand_lanes;
+    const int blocks = (P.B + lanes - 1) / lanes;
+    expand_kernel<<<blocks, kExpandThreads, 0, st>>>(P, actions, bs, es, dabs, dab_count, status, gauss_tab, lanes);
     return cudaGetLastError();
 }
 cudaError_t launch_composite(const EnvParams &P, uint16_t *canvas, const float *dabs,

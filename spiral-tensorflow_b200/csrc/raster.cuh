@@ -46,6 +46,7 @@ struct EnvParams {
     int uses_speed1, uses_speed2;
     int mapped_mask;             // bit s set: dyn[s] has at least one input mapping
     int rng_table_len;           // entries of the rand_gauss table (stream positions)
+    int expand_lanes;            // canvases per warp in expand_kernel (0 = choose from the batch size)
     double lin[64];
     double pressures[8];
     double sizes[8];

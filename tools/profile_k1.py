@@ -2,6 +2,8 @@
 import sys
 import numpy as np
 import torch
+import os
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
 import spiral_b200 as sp
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
