@@ -588,6 +588,11 @@ __device__ __forceinline__ float dab_rr(const EnvParams &P, int xp, int yp, floa
     return 1.0f - visibilityNear;
 }
 
+// floor(p / w) == (p * kRcpW[w]) >> 16 for p < 2048, w in 1..32
+__constant__ unsigned int kRcpW[33] = {0, 65536, 32768, 21846, 16384, 13108, 10923, 9363, 8192, 7282, 6554, 5958,
+                                       5462, 5042, 4682, 4370, 4096, 3856, 3641, 3450, 3277, 3121, 2979, 2850,
+                                       2731, 2622, 2521, 2428, 2341, 2260, 2185, 2115, 2048};
+
 template <int C>
 __global__ void __launch_bounds__(kCompThreads)
 composite_kernel(const __grid_constant__ EnvParams P, uint16_t *__restrict__ canvas,
@@ -653,10 +658,11 @@ composite_kernel(const __grid_constant__ EnvParams P, uint16_t *__restrict__ can
             const int by0 = __shfl_sync(0xffffffffu, cy0, j);
             const int by1 = __shfl_sync(0xffffffffu, cy1, j);
             const bool aa = radius < 3.0f;
-            const int w = bx1 - bx0 + 1;
-            const int n = w * (by1 - by0 + 1);
+            const int w = bx1 - bx0 + 1;                       // <= 32 (region width)
+            const int n = w * (by1 - by0 + 1);                  // <= 512
+            const uint32_t rcpw = kRcpW[w];
             for (int p = lane; p < n; p += 32) {
-                const int ry = p / w;
+                const int ry = (int)(((uint32_t)p * rcpw) >> 16);
                 const int xp = bx0 + (p - ry * w);
                 const int yp = by0 + ry;
                 const float rr = dab_rr(P, xp, yp, x, y, oor2, ras, aa);
@@ -822,8 +828,8 @@ cudaError_t launch_expand(const EnvParams &P, const int32_t *actions, float *bs,
                           float *dabs, int32_t *dab_count, int32_t *status, const float *gauss_tab,
                           cudaStream_t st)
 {
-    // aim for >= 16 warps per SM before packing more than one canvas into a warp
-    int lanes = P.B / (148 * 16);
+    // aim for >= 4 warps per SM before packing more than one canvas into a warp (tools/sweep_expand_lanes.sh)
+    int lanes = P.B / (148 * 4);
     if (lanes < 1) lanes = 1;
     if (lanes > 32) lanes = 32;
     while (lanes & (lanes - 1)) lanes &= lanes - 1;      // round down to a power of two
