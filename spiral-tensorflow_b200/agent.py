@@ -1,0 +1,174 @@
+"""``Agent`` -- synchronous, batched counterpart of the reference's agent.py / rl_utils.env_runner.
+
+The reference runs N-2 CPU actor processes with one env each, a policy learner and a discriminator
+learner talking through TF queues on a parameter server (agent.py:38-59, trainer.py:107-118).  Here
+one process per GPU owns B canvases; a step of the loop is
+
+    rollout()        rl_utils.py:185-238   policy.act -> env.step, T times, everything on the GPU
+    train_policy()   agent.py:333-403      GAN reward (K2) -> fused A2C loss (K3) -> backward through
+                                           the PyTorch policy -> all-reduce -> clip 40 -> Adam
+    train_gan()      agent.py:409-437      WGAN-GP step on (replay fakes, real targets)
+
+Only the three kernel families of the north-star path are native; the policy trunk and the
+discriminator's backward pass are the next rows and run through PyTorch autograd.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+import torch.nn.functional as F
+
+from . import distributed as dist_utils
+from . import rl_utils
+from .models.discriminator import Discriminator
+from .models.policy import Policy
+from .replay import ReplayBuffer
+
+
+class TFAdam(torch.optim.Optimizer):
+    """tf.train.AdamOptimizer: lr_t = lr * sqrt(1 - b2^t) / (1 - b1^t);  p -= lr_t * m / (sqrt(v) + eps)."""
+
+    def __init__(self, params, lr, beta1=0.9, beta2=0.999, eps=1e-8):
+        super().__init__(params, dict(lr=lr, beta1=beta1, beta2=beta2, eps=eps))
+
+    @torch.no_grad()
+    def step(self):
+        for g in self.param_groups:
+            for p in g["params"]:
+                if p.grad is None:
+                    continue
+                st = self.state[p]
+                if not st:
+                    st["t"] = 0
+                    st["m"] = torch.zeros_like(p)
+                    st["v"] = torch.zeros_like(p)
+                st["t"] += 1
+                t, b1, b2 = st["t"], g["beta1"], g["beta2"]
+                st["m"].mul_(b1).add_(p.grad, alpha=1 - b1)
+                st["v"].mul_(b2).addcmul_(p.grad, p.grad, value=1 - b2)
+                lr_t = g["lr"] * math.sqrt(1 - b2 ** t) / (1 - b1 ** t)
+                p.addcdiv_(st["m"], st["v"].sqrt().add_(g["eps"]), value=-lr_t)
+
+
+def disc_forward_torch(params, x, layer_num, batch_norm, normalize=True):
+    """Differentiable plain-PyTorch D (TF semantics: SAME pad 1/2, BN eps 1e-3 biased variance,
+    leaky-ReLU 0.2) over the SAME parameter tensors the native forward reads; used for the WGAN-GP
+    training step until the tensor-core backward lands."""
+    if normalize:
+        x = (x - 127.5) / 127.5
+    x = x.permute(0, 3, 1, 2)
+    for l in range(layer_num):
+        k = params["conv%d/kernel" % l].permute(3, 2, 0, 1)
+        x = F.conv2d(F.pad(x, (1, 2, 1, 2)), k, params["conv%d/bias" % l], stride=2)
+        if l > 0 and batch_norm:
+            mean = x.mean(dim=(0, 2, 3), keepdim=True)
+            var = x.var(dim=(0, 2, 3), unbiased=False, keepdim=True)
+            x = (x - mean) * torch.rsqrt(var + 1e-3) * params["batch_normalization_%d/gamma" % l].view(1, -1, 1, 1) \
+                + params["batch_normalization_%d/beta" % l].view(1, -1, 1, 1)
+        x = F.leaky_relu(x, 0.2)
+    logits = (x.flatten(1) @ params["dense/kernel"] + params["dense/bias"]).reshape(-1)
+    return torch.sigmoid(logits), logits
+
+
+class Agent(object):
+    def __init__(self, args, env, device=None):
+        self.args = args
+        self.env = env
+        self.device = env.device if device is None else torch.device(device)
+        self.policy = Policy(args, env, "global", env.observation_shape, env.action_sizes).to(self.device)
+        self.policy_opt = TFAdam(self.policy.parameters(), args.policy_lr)
+        self.gan = args.loss == "gan"
+        if self.gan:
+            self.disc = Discriminator(args, None, env.observation_shape, norm_fn=env.norm, scope_name="global",
+                                      device=self.device, max_batch=max(env.num_envs, args.disc_batch_size))
+            for p in self.disc.params.values():
+                p.requires_grad_(True)
+            self.disc_opt = TFAdam(list(self.disc.params.values()), args.disc_lr, beta1=0.5, beta2=0.9)
+            self.replay = ReplayBuffer(args, env.observation_shape, device=self.device)
+        self.rng = torch.Generator(device=self.device)
+        self.rng.manual_seed(int(args.seed))
+        self.world = dist_utils.dist.get_world_size() if dist_utils.dist.is_initialized() else 1
+
+    # ------------------------------------------------------------------
+    @torch.no_grad()
+    def rollout(self):
+        """rl_utils.env_runner (rl_utils.py:185-238) for B canvases at once."""
+        env, pi, T, B = self.env, self.policy, self.env.episode_length, self.env.num_envs
+        state, condition, z = env.reset()
+        c, h = pi.get_initial_features(B)
+        features0 = torch.stack([c, h], 1)
+        last_action = torch.as_tensor(env.initial_action, device=self.device)
+        states = torch.empty((B, T + 1) + tuple(state.shape[1:]), device=self.device)
+        actions = torch.empty((B, T, len(env.acs)), dtype=torch.int32, device=self.device)
+        rewards = torch.zeros((B, T), device=self.device)
+        values = torch.zeros((B, T, 1), device=self.device)
+        for t in range(T):
+            states[:, t] = state
+            action, value, c, h = pi.act(state, last_action, c, h, condition, z, self.rng)
+            state, reward, terminal, _ = env.step(action)
+            actions[:, t] = action
+            rewards[:, t] = reward
+            values[:, t, 0] = value
+            last_action = action
+        states[:, T] = state
+        out = dict(states=states, actions=actions, rewards=rewards, values=values,
+                   features=features0.unsqueeze(1).expand(B, T, 2, pi.lstm_size))
+        if condition is not None:
+            out["conditions"] = condition.unsqueeze(1).expand((B, T) + tuple(condition.shape[1:]))
+        else:
+            out["z"] = z.unsqueeze(1).expand(B, T, z.shape[-1])
+        if self.gan:
+            self.replay.push(states[:, T])
+        return out
+
+    def train_policy(self, rollout):
+        """agent.py:333-403."""
+        args, pi = self.args, self.policy
+        if self.gan:
+            with torch.no_grad():
+                self.disc.sync_weights()
+                rollout["rewards"][:, -1] = self.disc.predict(rollout["states"][:, -1])       # agent.py:336-338
+        acts = rollout["actions"]
+        samples = {name: acts[:, :, i] for i, name in enumerate(pi.acs)}                      # teacher forcing, agent.py:357-365
+        feats = rollout["features"][:, 0]
+        logits, _, vf, _ = pi(rollout["states"], acts.float(), (feats[:, 0], feats[:, 1]),
+                              rollout.get("conditions"), rollout.get("z"), samples)
+        loss = rl_utils.a2c_loss_autograd([logits[n].contiguous() for n in pi.acs], acts, rollout["rewards"],
+                                          rollout["values"][:, :, 0], vf, 0.99, 1.0, args.entropy_coeff)
+        self.policy_opt.zero_grad(set_to_none=True)
+        loss.backward()
+        grads = [p.grad for p in pi.parameters() if p.grad is not None]
+        dist_utils.allreduce_grads_(grads, self.world)                                        # explicit 1/world
+        gnorm = dist_utils.clip_by_global_norm_(grads, float(args.grad_clip))                  # agent.py:231
+        self.policy_opt.step()
+        B = acts.shape[0]
+        return {"model/total_loss": loss.detach(), "model/grad_global_norm": gnorm,
+                "env/r": rollout["rewards"][:, -1].mean(), "batch": B}
+
+    def train_gan(self, reals=None):
+        """agent.py:409-437 + discriminator.py:97-136 (WGAN-GP, penalty on the sigmoid output)."""
+        args, D = self.args, self.disc
+        n = args.disc_batch_size
+        fake = self.replay.sample(n)
+        real = self.env.get_random_target(n) if reals is None else reals
+        p = D.params
+        _, real_logits = disc_forward_torch(p, real, D.layer_num, D.batch_norm, D.normalize)
+        _, fake_logits = disc_forward_torch(p, fake, D.layer_num, D.batch_norm, D.normalize)
+        critic = fake_logits.mean() - real_logits.mean()
+        alpha = torch.rand((n, 1), generator=self.rng, device=self.device)
+        fn = (fake - 127.5) / 127.5 if D.normalize else fake
+        rn = (real - 127.5) / 127.5 if D.normalize else real
+        inter = (rn.flatten(1) + alpha * (fn.flatten(1) - rn.flatten(1))).detach().requires_grad_(True)
+        probs, _ = disc_forward_torch(p, inter.view_as(fn), D.layer_num, D.batch_norm, normalize=False)
+        g = torch.autograd.grad(probs.sum(), inter, create_graph=True)[0]
+        slopes = torch.sqrt(1e-8 + (g ** 2).sum(1))
+        gp = ((slopes - 1.0) ** 2).mean()
+        d_loss = critic + args.wgan_lambda * gp
+        self.disc_opt.zero_grad(set_to_none=True)
+        d_loss.backward()
+        dist_utils.allreduce_grads_([q.grad for q in p.values() if q.grad is not None], self.world)
+        self.disc_opt.step()
+        D.sync_weights()
+        return {"gan/critic_loss": critic.detach(), "gan/disc_loss": d_loss.detach(), "gan/penalty": gp.detach(),
+                "gan/gen_loss": -fake_logits.mean().detach()}
