@@ -227,6 +227,18 @@ extern "C" int spiral_env_create(const SpiralEnvCfg *cfg, SpiralEnv **out)
             }
         }
     }
+    // dry_brush.myb structure: {opaque, opaque_multiply, offset_by_random} <- pressure, radius_logarithmic <- speed2,
+    // 2 points each, nothing else mapped
+    {
+        bool ok = true;
+        for (int s = 0; s < SPIRAL_DYN_COUNT; s++)
+            for (int j = 0; j < SPIRAL_IN_COUNT; j++) {
+                const bool want = (j == SPIRAL_IN_PRESSURE && (s == SPIRAL_DYN_OPAQUE || s == SPIRAL_DYN_OPAQUE_MULTIPLY || s == SPIRAL_DYN_OFFSET_BY_RANDOM)) ||
+                                  (j == SPIRAL_IN_SPEED2 && s == SPIRAL_DYN_RADIUS_LOGARITHMIC);
+                ok &= (br.dyn[s].n[j] == (want ? 2 : 0));
+            }
+        P.dry_structure = ok ? 1 : 0;
+    }
     // base radius per size-table entry: set_base_value('radius_logarithmic', size) takes a float
     for (int i = 0; i < 8; i++) {
         P.base_rlog[i] = (float)cfg->sizes[i];

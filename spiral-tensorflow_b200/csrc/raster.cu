@@ -72,10 +72,19 @@ __device__ __forceinline__ float map_eval(const MapDev &m, bool mapped, const fl
     return result;
 }
 
+// one 2-point segment of a mapping (the n == 2 case of mypaint_mapping_calculate)
+__device__ __forceinline__ float map_seg(const MapDev &m, int j, float x)
+{
+    const float x0 = m.x[j][0], y0 = m.y[j][0], x1 = m.x[j][1], y1 = m.y[j][1], inv = m.inv[j][0];
+    if (x0 == x1 || y0 == y1) return y0;
+    const float num = y1 * (x - x0) + y0 * (x1 - x);
+    return (inv != 0.0f) ? num * inv : num / (x1 - x0);
+}
+
 // exp_decay (mypaint-brush.c): returns float
 __device__ __forceinline__ float exp_decay(float T_const, float t)
 {
-    if ((double)T_const <= 0.001) return 0.0f;
+    if (T_const < 0.001f) return 0.0f;      // (double)T <= 0.001  <=>  T < 0.001f  ((float)0.001 > 0.001)
     return (float)det_exp((double)(-t / T_const));
 }
 __device__ __forceinline__ float one_minus_decay(float T_const, float t)
@@ -104,8 +113,9 @@ constexpr int kExpandThreads = 32;
 
 __device__ __forceinline__ float clamp_radius(float r)
 {
-    if ((double)r < 0.2) r = (float)0.2;
-    if ((double)r > 1000.0) r = 1000.0f;
+    // (double)r < 0.2  <=>  r < 0.2f : no float lies in [0.2, (float)0.2)
+    if (r < 0.2f) r = 0.2f;
+    if (r > 1000.0f) r = 1000.0f;
     return r;
 }
 
@@ -150,14 +160,27 @@ __device__ __forceinline__ void update_states(const EnvParams &P, Brush &S, floa
         in[2] = (float)(det_log((double)(P.sp_gamma[1] + S.s2)) * (double)P.sp_m[1] + (double)P.sp_q[1]);
 
     const int mm = P.mapped_mask;
-    S.v_opaque = map_eval(P.dyn[0], mm & 1, in, P.dyn[0].base);
-    S.v_opaque_mul = map_eval(P.dyn[1], mm & 2, in, P.dyn[1].base);
-    // the size action rewrites the base value of radius_logarithmic every step (mnist.py:134-135)
-    S.v_rlog = map_eval(P.dyn[2], mm & 4, in, rlog_base);
-    S.v_hard = map_eval(P.dyn[3], mm & 8, in, P.dyn[3].base);
-    S.v_rbr = map_eval(P.dyn[4], mm & 16, in, P.dyn[4].base);
-    S.v_obr = map_eval(P.dyn[5], mm & 32, in, P.dyn[5].base);
-    S.v_aa = map_eval(P.dyn[8], mm & 256, in, P.dyn[8].base);
+    if (P.dry_structure) {
+        // the default brush's mapping structure (assets/brushes/dry_brush.myb): opaque, opaque_multiply
+        // and offset_by_random read pressure, radius_logarithmic reads speed2, each through one
+        // 2-point segment; everything else is constant.  Straight-line code, constants hoisted.
+        S.v_opaque = P.dyn[0].base + map_seg(P.dyn[0], 0, in[0]);
+        S.v_opaque_mul = P.dyn[1].base + map_seg(P.dyn[1], 0, in[0]);
+        S.v_rlog = rlog_base + map_seg(P.dyn[2], 2, in[2]);
+        S.v_hard = P.dyn[3].base;
+        S.v_rbr = P.dyn[4].base;
+        S.v_obr = P.dyn[5].base + map_seg(P.dyn[5], 0, in[0]);
+        S.v_aa = P.dyn[8].base;
+    } else {
+        S.v_opaque = map_eval(P.dyn[0], mm & 1, in, P.dyn[0].base);
+        S.v_opaque_mul = map_eval(P.dyn[1], mm & 2, in, P.dyn[1].base);
+        // the size action rewrites the base value of radius_logarithmic every step (mnist.py:134-135)
+        S.v_rlog = map_eval(P.dyn[2], mm & 4, in, rlog_base);
+        S.v_hard = map_eval(P.dyn[3], mm & 8, in, P.dyn[3].base);
+        S.v_rbr = map_eval(P.dyn[4], mm & 16, in, P.dyn[4].base);
+        S.v_obr = map_eval(P.dyn[5], mm & 32, in, P.dyn[5].base);
+        S.v_aa = map_eval(P.dyn[8], mm & 256, in, P.dyn[8].base);
+    }
 
     // slow_tracking_per_dab == 0  =>  fac = 1.0 - 0.0
     {

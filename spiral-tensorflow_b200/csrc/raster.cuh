@@ -45,6 +45,7 @@ struct EnvParams {
     int n_colors, colorize, dither, max_dabs;
     int uses_speed1, uses_speed2;
     int mapped_mask;             // bit s set: dyn[s] has at least one input mapping
+    int dry_structure;           // 1: mapping structure of dry_brush.myb (fast path in update_states)
     int rng_table_len;           // entries of the rand_gauss table (stream positions)
     int expand_lanes;            // canvases per warp in expand_kernel (0 = choose from the batch size)
     double lin[64];
