@@ -33,8 +33,12 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-WORKLOAD = dict(workload="rgb64", env="color_mnist", color_channel=3, location_size=64, episode_length=20,
-                canvases_per_gpu=1024, disc_dim=64)
+# BASELINE.json configs[3] gives the shape (64x64 RGB, L=64, T=20, colour head); configs[4] ("rendering+reward
+# throughput sweep: 4096-65536 canvases x 20 strokes at 1/2/4/8 GPUs") gives the batch the throughput metric is
+# quoted on.  Default: 16384 canvases per GPU (weak scaling); the 1024-canvas point of configs[3] is reported in
+# the same JSON line under "rgb64_b1024".
+WORKLOAD = dict(workload="rgb64-sweep (configs[3] shape at configs[4] scale)", env="color_mnist", color_channel=3,
+                location_size=64, episode_length=20, canvases_per_gpu=16384, disc_dim=64)
 BYTES_PER_CANVAS_STEP = {1: 81920, 3: 114688}       # BASELINE.md section 3 (K1 algorithmic bytes)
 
 
@@ -50,6 +54,7 @@ def parse():
     p.add_argument("--no_cpu_baseline", action="store_true")
     p.add_argument("--cpu_seconds", type=float, default=15.0, help="target seconds of the bounded CPU sample")
     p.add_argument("--jump", default="True")
+    p.add_argument("--no_secondary", action="store_true", help="skip the 1024-canvas secondary measurement")
     return p.parse_args()
 
 
@@ -193,152 +198,166 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
 
-    B, T = args.canvases, args.episode_length
-    C, L = WORKLOAD["color_channel"], WORKLOAD["location_size"]
-    a = sp.get_args(["--env", WORKLOAD["env"], "--location_size", str(L), "--color_channel", str(C),
-                     "--episode_length", str(T), "--loss", "gan", "--disc_dim", str(WORKLOAD["disc_dim"]),
-                     "--disc_precision", args.disc_precision, "--jump", args.jump, "--seed", str(123 + rank)])
-    env = sp.create_env(a, num_envs=B, device=dev)
-    disc = models.Discriminator(a, None, [64, 64, C], norm_fn=env.norm, scope_name="global", device=dev, max_batch=B)
-    K = len(env.acs)
-    g = torch.Generator(device="cpu")
-    g.manual_seed(123 + rank)                     # seed + task, as main.py:21
-    acts_host = torch.stack([torch.randint(0, n, (B, T), generator=g) for n in env.head_sizes], -1).to(torch.int32)
-    acts_host = acts_host.permute(1, 0, 2).contiguous().pin_memory()      # [T,B,K]
-    acts_dev = acts_host.to(dev)
-    gg = torch.Generator(device=dev)
-    gg.manual_seed(7 + rank)
-    logits = [torch.randn((B, T, n), generator=gg, device=dev) for n in env.head_sizes]
-    dlogits_bytes = sum(l.numel() * 4 for l in logits)
-    values_host = torch.randn((B, T), generator=g).pin_memory()
-    vf_host = torch.randn((B, T), generator=g).pin_memory()
-    values_dev, vf_dev = values_host.to(dev), vf_host.to(dev)
-    rewards = torch.zeros((B, T), device=dev)
-    a2c_out = rl.a2c_loss(logits, acts_dev.permute(1, 0, 2).contiguous(), rewards, values_dev, vf_dev)   # allocates outputs
-    acts_bt = acts_dev.permute(1, 0, 2).contiguous()
-    probs = torch.empty((B,), device=dev)
-    lg = torch.empty((B,), device=dev)
-    host_out = torch.empty((B + 4,), dtype=torch.float32).pin_memory()
+    def measure(B):
+        T = args.episode_length
+        C, L = WORKLOAD["color_channel"], WORKLOAD["location_size"]
+        a = sp.get_args(["--env", WORKLOAD["env"], "--location_size", str(L), "--color_channel", str(C),
+                         "--episode_length", str(T), "--loss", "gan", "--disc_dim", str(WORKLOAD["disc_dim"]),
+                         "--disc_precision", args.disc_precision, "--jump", args.jump, "--seed", str(123 + rank)])
+        env = sp.create_env(a, num_envs=B, device=dev)
+        disc = models.Discriminator(a, None, [64, 64, C], norm_fn=env.norm, scope_name="global", device=dev, max_batch=B)
+        K = len(env.acs)
+        acs_list, head_list = list(env.acs), list(env.head_sizes)
+        g = torch.Generator(device="cpu")
+        g.manual_seed(123 + rank)                     # seed + task, as main.py:21
+        acts_host = torch.stack([torch.randint(0, n, (B, T), generator=g) for n in env.head_sizes], -1).to(torch.int32)
+        acts_host = acts_host.permute(1, 0, 2).contiguous().pin_memory()      # [T,B,K]
+        acts_dev = acts_host.to(dev)
+        gg = torch.Generator(device=dev)
+        gg.manual_seed(7 + rank)
+        logits = [torch.randn((B, T, n), generator=gg, device=dev) for n in env.head_sizes]
+        dlogits_bytes = sum(l.numel() * 4 for l in logits)
+        values_host = torch.randn((B, T), generator=g).pin_memory()
+        vf_host = torch.randn((B, T), generator=g).pin_memory()
+        values_dev, vf_dev = values_host.to(dev), vf_host.to(dev)
+        rewards = torch.zeros((B, T), device=dev)
+        a2c_out = rl.a2c_loss(logits, acts_dev.permute(1, 0, 2).contiguous(), rewards, values_dev, vf_dev)   # allocates outputs
+        acts_bt = acts_dev.permute(1, 0, 2).contiguous()
+        probs = torch.empty((B,), device=dev)
+        lg = torch.empty((B,), device=dev)
+        host_out = torch.empty((B + 4,), dtype=torch.float32).pin_memory()
 
-    ev = lambda: torch.cuda.Event(enable_timing=True)
-    kern_ev = {"expand": [], "composite": [], "disc": [], "a2c": []}
-    N = sp._native
-    lib = N.lib()
+        ev = lambda: torch.cuda.Event(enable_timing=True)
+        kern_ev = {"expand": [], "composite": [], "disc": [], "a2c": []}
+        N = sp._native
+        lib = N.lib()
 
-    def episode(resident=True, record=False):
-        env.reset()
-        for t in range(T):
-            act = acts_dev[t] if resident else acts_host[t].to(dev, non_blocking=True)
+        def episode(resident=True, record=False):
+            env.reset()
+            for t in range(T):
+                act = acts_dev[t] if resident else acts_host[t].to(dev, non_blocking=True)
+                if record:
+                    e0, e1, e2 = ev(), ev(), ev()
+                    e0.record()
+                    N.check(lib.spiral_env_expand(env._handle, N.ptr(act), N.ptr(env.brush_state), N.ptr(env.env_state),
+                                                  N.ptr(env.dab_scratch), N.ptr(env.dab_count), N.ptr(env.status),
+                                                  N.stream_ptr()))
+                    e1.record()
+                    N.check(lib.spiral_env_composite(env._handle, N.ptr(env.canvas), N.ptr(env.dab_scratch),
+                                                     N.ptr(env.dab_count), N.ptr(env.obs), N.stream_ptr()))
+                    e2.record()
+                    kern_ev["expand"].append((e0, e1))
+                    kern_ev["composite"].append((e1, e2))
+                    env._step += 1
+                else:
+                    env.step(act)
             if record:
-                e0, e1, e2 = ev(), ev(), ev()
-                e0.record()
-                N.check(lib.spiral_env_expand(env._handle, N.ptr(act), N.ptr(env.brush_state), N.ptr(env.env_state),
-                                              N.ptr(env.dab_scratch), N.ptr(env.dab_count), N.ptr(env.status),
-                                              N.stream_ptr()))
-                e1.record()
-                N.check(lib.spiral_env_composite(env._handle, N.ptr(env.canvas), N.ptr(env.dab_scratch),
-                                                 N.ptr(env.dab_count), N.ptr(env.obs), N.stream_ptr()))
-                e2.record()
-                kern_ev["expand"].append((e0, e1))
-                kern_ev["composite"].append((e1, e2))
-                env._step += 1
+                d0, d1, d2 = ev(), ev(), ev()
+                d0.record()
+            disc.forward(env.state, logits_out=lg, probs_out=probs)          # agent.py:336-338: GAN reward
+            rewards[:, -1] = probs
+            if record:
+                d1.record()
+            if resident:
+                v, f = values_dev, vf_dev
             else:
-                env.step(act)
-        if record:
-            d0, d1, d2 = ev(), ev(), ev()
-            d0.record()
-        disc.forward(env.state, logits_out=lg, probs_out=probs)          # agent.py:336-338: GAN reward
-        rewards[:, -1] = probs
-        if record:
-            d1.record()
-        if resident:
-            v, f = values_dev, vf_dev
-        else:
-            v, f = values_host.to(dev, non_blocking=True), vf_host.to(dev, non_blocking=True)
-        rl.a2c_loss(logits, acts_bt, rewards, v, f, 0.99, 1.0, 0.01, out=a2c_out)
-        if record:
-            d2.record()
-            kern_ev["disc"].append((d0, d1))
-            kern_ev["a2c"].append((d1, d2))
-        if not resident:
-            host_out[:B].copy_(probs, non_blocking=True)
-            host_out[B:].copy_(a2c_out.scalars, non_blocking=True)
+                v, f = values_host.to(dev, non_blocking=True), vf_host.to(dev, non_blocking=True)
+            rl.a2c_loss(logits, acts_bt, rewards, v, f, 0.99, 1.0, 0.01, out=a2c_out)
+            if record:
+                d2.record()
+                kern_ev["disc"].append((d0, d1))
+                kern_ev["a2c"].append((d1, d2))
+            if not resident:
+                host_out[:B].copy_(probs, non_blocking=True)
+                host_out[B:].copy_(a2c_out.scalars, non_blocking=True)
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+        def barrier():
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
 
-    def timed(resident, record):
-        for _ in range(args.warmup):
-            episode(resident)
-        barrier()
-        s, e = ev(), ev()
-        s.record()
-        for _ in range(args.steps):
-            episode(resident, record)
-        e.record()
-        barrier()
-        ms = s.elapsed_time(e)
-        if world > 1:
-            t = torch.tensor([ms], device=dev, dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-        return ms
+        def timed(resident, record):
+            for _ in range(args.warmup):
+                episode(resident)
+            barrier()
+            s, e = ev(), ev()
+            s.record()
+            for _ in range(args.steps):
+                episode(resident, record)
+            e.record()
+            barrier()
+            ms = s.elapsed_time(e)
+            if world > 1:
+                t = torch.tensor([ms], device=dev, dtype=torch.float64)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                ms = float(t.item())
+            return ms
 
-    sampler = ClockSampler(local) if rank == 0 else None
-    if sampler:
-        sampler.start()
-    ms = timed(resident=True, record=True)
-    ms_e2e = timed(resident=False, record=False)
-    if sampler:
-        sampler.stop_flag = True
-        sampler.join(timeout=2)
-    env.check_status()
+        sampler = ClockSampler(local) if rank == 0 else None
+        if sampler:
+            sampler.start()
+        ms = timed(resident=True, record=True)
+        ms_e2e = timed(resident=False, record=False)
+        if sampler:
+            sampler.stop_flag = True
+            sampler.join(timeout=2)
+        env.check_status()
 
-    steps_total = world * B * T * args.steps
-    value = steps_total / (ms * 1e-3)
-    e2e_value = steps_total / (ms_e2e * 1e-3)
+        steps_total = world * B * T * args.steps
+        value = steps_total / (ms * 1e-3)
+        e2e_value = steps_total / (ms_e2e * 1e-3)
+        if rank != 0:
+            return None
+
+        def avg_ms(name):
+            return float(np.mean([a_.elapsed_time(b_) for a_, b_ in kern_ev[name]]))
+
+        t_exp, t_comp, t_disc, t_a2c = avg_ms("expand"), avg_ms("composite"), avg_ms("disc"), avg_ms("a2c")
+        peak, peak_src = load_peaks()
+        bytes_launch = BYTES_PER_CANVAS_STEP[C] * B
+        share = {"expand": t_exp * T, "composite": t_comp * T, "disc": t_disc, "a2c": t_a2c}
+        pair_gbs = bytes_launch / ((t_exp + t_comp) * 1e-3) / 1e9
+        dominant = max(("expand", "composite"), key=lambda k: share[k])
+        dom_ms = t_exp if dominant == "expand" else t_comp
+        roof = dict(bound="hbm", kernel="spiral::%s_kernel" % dominant, achieved=bytes_launch / (dom_ms * 1e-3) / 1e9,
+                    peak=peak, unit="GB/s", frac=bytes_launch / (dom_ms * 1e-3) / 1e9 / peak, traffic=None,
+                    peak_source=peak_src,
+                    note="algorithmic bytes = %d B/canvas-step x %d canvases per launch; K1 is ALU/latency-bound "
+                         "(serial brush state machine, ~550 dabs x ~64 px per painted step), see DESIGN.md" % (BYTES_PER_CANVAS_STEP[C], B),
+                    k1_pair=dict(achieved=pair_gbs, frac=pair_gbs / peak, ms_expand=t_exp, ms_composite=t_comp),
+                    a2c=dict(achieved=2.0 * dlogits_bytes / (t_a2c * 1e-3) / 1e9, unit="GB/s",
+                             frac=2.0 * dlogits_bytes / (t_a2c * 1e-3) / 1e9 / peak, ms=t_a2c),
+                    disc=dict(ms=t_disc, tflops=340.25e6 * B / (t_disc * 1e-3) / 1e12, precision=args.disc_precision))
+        launches_per_episode = 1 + 2 * T + (1 + 5 * 2 + 1 + 1) + 3
+        footprint = (env.canvas.numel() * 2 + env.obs.numel() * 4 + env.dab_scratch.numel() * 4 + 2 * dlogits_bytes
+                     + disc.workspace.numel()) / 2 ** 20
+        out = dict(metric="env-steps/sec (render+D reward+A2C) on 64x64 canvases", value=value, unit="env-steps/s",
+                   n_gpus=world, steps=args.steps, warmup=args.warmup, ms_per_step=ms / args.steps,
+                   higher_is_better=True, scaling="weak", vs_baseline=None, dtype="fix15/u16 render, f32 reward+loss",
+                   data="synthetic",
+                   config=dict(WORKLOAD, canvases_per_gpu=B, episode_length=T, heads=dict(zip(env.acs, env.head_sizes)),
+                               jump=args.jump, disc_precision=args.disc_precision, parallelism="dp%d (actor partitions, no data-path collective)" % world,
+                               l2="working set %.0f MiB per GPU > 126 MiB L2 (inputs larger than L2)" % footprint),
+                   e2e=dict(value=e2e_value, unit="env-steps/s", h2d_bytes_per_step=int(B * T * K * 4 + 2 * B * T * 4),
+                            d2h_bytes_per_step=int((B + 4) * 4), ms_per_step=ms_e2e / args.steps),
+                   gpu_launches=launches_per_episode * args.steps,
+                   kernel_ms_per_step=share, roofline=roof, clocks=sampler.summary() if sampler else None)
+        del env, disc, logits, a2c_out
+        torch.cuda.empty_cache()
+        return out, (acs_list, head_list, C, L, T)
+
+    res = measure(args.canvases)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
-
-    def avg_ms(name):
-        return float(np.mean([a_.elapsed_time(b_) for a_, b_ in kern_ev[name]]))
-
-    t_exp, t_comp, t_disc, t_a2c = avg_ms("expand"), avg_ms("composite"), avg_ms("disc"), avg_ms("a2c")
-    peak, peak_src = load_peaks()
-    bytes_launch = BYTES_PER_CANVAS_STEP[C] * B
-    share = {"expand": t_exp * T, "composite": t_comp * T, "disc": t_disc, "a2c": t_a2c}
-    pair_gbs = bytes_launch / ((t_exp + t_comp) * 1e-3) / 1e9
-    dominant = max(("expand", "composite"), key=lambda k: share[k])
-    dom_ms = t_exp if dominant == "expand" else t_comp
-    roof = dict(bound="hbm", kernel="spiral::%s_kernel" % dominant, achieved=bytes_launch / (dom_ms * 1e-3) / 1e9,
-                peak=peak, unit="GB/s", frac=bytes_launch / (dom_ms * 1e-3) / 1e9 / peak, traffic=None,
-                peak_source=peak_src,
-                note="algorithmic bytes = %d B/canvas-step x %d canvases per launch; K1 is ALU/latency-bound "
-                     "(serial brush state machine, ~550 dabs x ~64 px per painted step), see DESIGN.md" % (BYTES_PER_CANVAS_STEP[C], B),
-                k1_pair=dict(achieved=pair_gbs, frac=pair_gbs / peak, ms_expand=t_exp, ms_composite=t_comp),
-                a2c=dict(achieved=2.0 * dlogits_bytes / (t_a2c * 1e-3) / 1e9, unit="GB/s",
-                         frac=2.0 * dlogits_bytes / (t_a2c * 1e-3) / 1e9 / peak, ms=t_a2c),
-                disc=dict(ms=t_disc, tflops=340.25e6 * B / (t_disc * 1e-3) / 1e12, precision=args.disc_precision))
-    launches_per_episode = 1 + 2 * T + (1 + 5 * 2 + 1 + 1) + 3
-    footprint = (env.canvas.numel() * 2 + env.obs.numel() * 4 + env.dab_scratch.numel() * 4 + 2 * dlogits_bytes
-                 + disc.workspace.numel()) / 2 ** 20
-    out = dict(metric="env-steps/sec (render+D reward+A2C) on 64x64 canvases", value=value, unit="env-steps/s",
-               n_gpus=world, steps=args.steps, warmup=args.warmup, ms_per_step=ms / args.steps,
-               higher_is_better=True, scaling="weak", vs_baseline=None, dtype="fix15/u16 render, f32 reward+loss",
-               data="synthetic",
-               config=dict(WORKLOAD, canvases_per_gpu=B, episode_length=T, heads=dict(zip(env.acs, env.head_sizes)),
-                           jump=args.jump, disc_precision=args.disc_precision, parallelism="dp%d (actor partitions, no data-path collective)" % world,
-                           l2="working set %.0f MiB per GPU > 126 MiB L2 (inputs larger than L2)" % footprint),
-               e2e=dict(value=e2e_value, unit="env-steps/s", h2d_bytes_per_step=int(B * T * K * 4 + 2 * B * T * 4),
-                        d2h_bytes_per_step=int((B + 4) * 4), ms_per_step=ms_e2e / args.steps),
-               gpu_launches=launches_per_episode * args.steps,
-               kernel_ms_per_step=share, roofline=roof, clocks=sampler.summary() if sampler else None)
+    out, (acs_list, head_list, C, L, T) = res
+    if world == 1 and not args.no_secondary and args.canvases != 1024:
+        sec, _ = measure(1024)
+        out["rgb64_b1024"] = {k: sec[k] for k in ("value", "unit", "ms_per_step", "e2e", "kernel_ms_per_step")}
+        out["rgb64_b1024"]["config"] = "BASELINE.json configs[3]: 1024 canvases per GPU (latency-bound: the longest canvas's serial brush chain)"
     if world == 1 and not args.no_cpu_baseline:
-        out["cpu_baseline"] = cpu_baseline(args, list(env.acs), list(env.head_sizes), C, L, T, WORKLOAD["disc_dim"])
+        out["cpu_baseline"] = cpu_baseline(args, acs_list, head_list, C, L, T, WORKLOAD["disc_dim"])
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
@@ -354,7 +373,7 @@ def run_reference(args):
     sizes = {"jump": 2, "pressure": 2, "size": 2, "color": 8, "control": L * L, "end": L * L}
     head_sizes = [sizes[a] for a in acs]
     cores = os.cpu_count() or 1
-    episodes = 2 * cores                       # bounded sample of the workload per step
+    episodes = 8 * cores                       # bounded sample of the workload per step
     for _ in range(min(args.warmup, 1)):
         cpu_reference_run(acs, L, C, T, head_sizes, WORKLOAD["disc_dim"], episodes=cores, cores=cores)
     t0 = time.perf_counter()
