@@ -279,6 +279,7 @@ extern "C" int spiral_env_create(const SpiralEnvCfg *cfg, SpiralEnv **out)
         P.sn = (float)::sin((double)angle_rad);
         P.l2 = P.cs * P.cs + P.sn * P.sn;
         P.rad_area_1 = sqrtf(1.0f / M_PI);
+        P.fast_spans = (P.sn == 1.0f && fabsf(P.cs) < 1e-6f) ? 1 : 0;   // aspect ratio is always 1 here
     }
     // |rand_gauss| <= 2*sqrt(3); radius <= ACTUAL_RADIUS * exp(|g| * |radius_by_random|)
     {

@@ -10,12 +10,10 @@
 //                    canvas (dab i's position/radius depend on the filtered speed, the partial-dab
 //                    carry and the RNG position after dab i-1), so parallelism comes from the
 //                    batch.  Emits "pending dabs" (8 floats) into a caller-owned list.
-//   composite_kernel one CTA per canvas: the 64x64 fix15 tile lives in shared memory (planar
-//                    u16 R,G,B, rows padded against bank conflicts) for ALL dabs of the step;
-//                    8 warps own 32x16-pixel regions and walk the dab list independently (dab
-//                    order only matters per pixel), finalising 32 dabs lane-parallel at a time.
-//                    HBM traffic is the 128-bit coalesced tile load, tile store and the fused
-//                    fix15 -> uint8 (dither) -> observation epilogue.
+//   composite_kernel one WARP per canvas walks the dab list in order, one lane per candidate pixel,
+//                    read-modify-writing the fix15 tile in place (64-bit RGBA words through L1/L2);
+//                    only the rows a step dirtied are converted (fix15 -> uint8 with dither ->
+//                    observation).  32 independent canvases per SM hide the per-dab latency.
 //
 // Arithmetic is bit-exact against oracle/paint_oracle.c in PO_MATH_DET mode: compile with
 // --fmad=false, transcendental functions from detmath.cuh.
@@ -489,10 +487,6 @@ expand_kernel(const __grid_constant__ EnvParams P, const int32_t *__restrict__ a
 // ------------------------------------------------------------------------------------------
 // K1b: composite
 // ------------------------------------------------------------------------------------------
-constexpr int kCompThreads = 256;
-constexpr int kRowWords = 33;                 // 64 px * u16 = 32 words, +1 pad word
-constexpr int kPlaneWords = kTile * kRowWords;
-
 struct FinalDab {
     float x, y, radius, hardness;
     float one_over_r2, r_aa_start, seg1_slope, seg2_offset, seg2_slope;
@@ -611,46 +605,82 @@ __device__ __forceinline__ float dab_rr(const EnvParams &P, int xp, int yp, floa
     return 1.0f - visibilityNear;
 }
 
-// floor(p / w) == (p * kRcpW[w]) >> 16 for p < 2048, w in 1..32
-__constant__ unsigned int kRcpW[33] = {0, 65536, 32768, 21846, 16384, 13108, 10923, 9363, 8192, 7282, 6554, 5958,
-                                       5462, 5042, 4682, 4370, 4096, 3856, 3641, 3450, 3277, 3121, 2979, 2850,
-                                       2731, 2622, 2521, 2428, 2341, 2260, 2185, 2115, 2048};
+// Sparse in-place compositing: ONE WARP per canvas.
+//
+// A stroke is a serial chain of heavily overlapping dabs (6 + 6 per radius), each touching fewer than
+// 32 pixels, so the natural unit is a warp that walks its canvas's dab list in order with one lane
+// per candidate pixel; throughput comes from 32 independent canvases resident per SM, not from
+// splitting a tile among warps (which leaves most of them waiting at the barrier: ncu, round 1).
+// The fix15 tile stays where it lives -- in HBM/L2, pixels read-modify-written through L1 as one
+// 64-bit RGBA word -- so a step only touches the sectors under the stroke and only the rows it
+// dirtied are converted into the observation (the observation buffer is persistent: it already
+// holds the previous step's image).  Canvases without dabs (jump steps, the first step) cost one
+// 8-byte load.
+//
+// Candidate pixels: libmypaint walks the whole (r+1) bounding box, but for the round dabs this
+// engine draws (ratio 1, angle 90) calculate_rr_antialiased returns rr_near > 1 -- opacity 0 --
+// exactly when  dx_near^2 + dyc^2 > r^2  (dx_near: distance in x from the dab centre to the pixel's
+// [xp, xp+1] extent, dyc: distance in y to the pixel-centre row).  The dab's owner lane lists the
+// pixels inside that disc (radius inflated by 0.1 % + 0.01 px, far above float rounding) once, in
+// shared memory; skipped pixels are exactly pixels the reference blends with opa_ == 0.
+constexpr int kCompWarps = 1;                 // canvases (warps) per CTA
+constexpr int kListCap = 64;                  // candidate pixels per dab on the fast path
+constexpr int kListStride = 68;               // bytes; 17 words: conflict-free per-lane appends
+constexpr uint32_t kGeneric = 0xffffffffu;
+
+struct __align__(16) SharedDab {
+    float x, y, hardness, one_over_r2;
+    float r_aa_start, seg1_slope, seg2_offset, seg2_slope;
+    uint32_t opacity;       // fix15
+    uint32_t box;           // x0 | y0 << 8 | x1 << 16 | y1 << 24, clipped to the tile
+    uint32_t npx;           // entries in the pixel list, or kGeneric: walk the bounding box
+    uint32_t aa;            // radius < 3: anti-aliased rr
+};
 
 template <int C>
-__global__ void __launch_bounds__(kCompThreads)
+__global__ void __launch_bounds__(32 * kCompWarps)
 composite_kernel(const __grid_constant__ EnvParams P, uint16_t *__restrict__ canvas,
                  const float *__restrict__ dabs, const int32_t *__restrict__ dab_count,
                  const uint16_t *__restrict__ dither, float *__restrict__ obs)
 {
-    __shared__ uint32_t s_px[3 * kPlaneWords];      // planar R,G,B; two u16 pixels per word
-    const int b = blockIdx.x;
-    const int tid = threadIdx.x;
-    const int lane = tid & 31;
-    const int warp = tid >> 5;
-
-    // ---- coalesced 128-bit tile load: uint4 = 2 RGBA pixels ----
-    const uint4 *src = reinterpret_cast<const uint4 *>(canvas + (size_t)b * kTile * kTile * 4);
-#pragma unroll
-    for (int k = 0; k < (kTile * kTile / 2) / kCompThreads; k++) {
-        const int i = tid + k * kCompThreads;          // pixel pair index
-        const uint4 v = src[i];
-        const int row = i >> 5, colw = i & 31;
-        const int w = row * kRowWords + colw;
-        s_px[w] = (v.x & 0xffffu) | (v.z << 16);                      // R0 | R1
-        s_px[kPlaneWords + w] = (v.x >> 16) | (v.z & 0xffff0000u);     // G0 | G1
-        s_px[2 * kPlaneWords + w] = (v.y & 0xffffu) | (v.w << 16);     // B0 | B1
-    }
-    __syncthreads();
-
+    __shared__ SharedDab s_dab[kCompWarps][32];
+    __shared__ __align__(4) uint8_t s_list[kCompWarps][32 * kListStride];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int b = blockIdx.x * kCompWarps + warp;
+    if (b >= P.B) return;
     const int n_dabs = dab_count[2 * b];
+    if (n_dabs == 0) return;                         // canvas and observation unchanged
     const int color_idx = dab_count[2 * b + 1];
     const uint32_t col_r = P.colors[color_idx][0], col_g = P.colors[color_idx][1],
                    col_b = P.colors[color_idx][2];
-    // this warp's 32x16 region
-    const int rx0 = (warp & 1) * 32, rx1 = rx0 + 31;
-    const int ry0 = (warp >> 1) * 16, ry1 = ry0 + 15;
-    uint16_t *s16 = reinterpret_cast<uint16_t *>(s_px);
+    uint2 *tile = reinterpret_cast<uint2 *>(canvas + (size_t)b * kTile * kTile * 4);   // RGBA u16x4 per pixel
     const float4 *dl = reinterpret_cast<const float4 *>(dabs + (size_t)b * P.max_dabs * kDabFloats);
+    SharedDab *sd = s_dab[warp];
+    uint8_t *sl = s_list[warp];
+    int ymin = kTile, ymax = -1;
+
+    // calculate_opa + draw_dab_pixels_BlendMode_Normal for one pixel
+    auto pixel = [&](const SharedDab &d, int xp, int yp) {
+        const int idx = yp * kTile + xp;
+        const uint2 px = tile[idx];
+        const float rr = dab_rr(P, xp, yp, d.x, d.y, d.one_over_r2, d.r_aa_start, d.aa != 0);
+        const float fac = rr <= d.hardness ? d.seg1_slope : d.seg2_slope;
+        float opa = rr <= d.hardness ? 1.0f : d.seg2_offset;
+        opa += rr * fac;
+        if (rr > 1.0f) opa = 0.0f;
+        const uint32_t opa_ = (uint32_t)(unsigned short)(opa * 32768.0f);
+        if (opa_) {
+            const uint32_t opa_a = opa_ * d.opacity / (1u << 15);
+            const uint32_t opa_b = (1u << 15) - opa_a;
+            uint32_t r = px.x & 0xffffu, g = px.x >> 16, bl = px.y & 0xffffu, al = px.y >> 16;
+            r = (opa_a * col_r + opa_b * r) / (1u << 15);
+            g = (opa_a * col_g + opa_b * g) / (1u << 15);
+            bl = (opa_a * col_b + opa_b * bl) / (1u << 15);
+            al = opa_a + opa_b * al / (1u << 15);
+            tile[idx] = make_uint2(r | (g << 16), bl | (al << 16));
+        }
+    };
 
     for (int base = 0; base < n_dabs; base += 32) {
         const int mine = base + lane;
@@ -659,85 +689,90 @@ composite_kernel(const __grid_constant__ EnvParams P, uint16_t *__restrict__ can
         f.x = f.y = f.radius = f.hardness = f.one_over_r2 = f.r_aa_start = 0;
         f.seg1_slope = f.seg2_offset = f.seg2_slope = 0;
         if (mine < n_dabs) f = finalize_dab(__ldg(dl + 2 * mine), __ldg(dl + 2 * mine + 1));
-        // clip to this warp's region
-        int cx0 = max(f.x0, rx0), cx1 = min(f.x1, rx1), cy0 = max(f.y0, ry0), cy1 = min(f.y1, ry1);
-        const bool hit = f.opacity != 0 && cx0 <= cx1 && cy0 <= cy1;
+        const bool hit = f.opacity != 0;             // 0 also when the dab misses tile (0,0)
+        uint32_t npx = kGeneric;
+        if (hit) {
+            ymin = min(ymin, f.y0);
+            ymax = max(ymax, f.y1);
+            if (P.fast_spans && f.radius < 3.0f && f.x1 - f.x0 < 16 && f.y1 - f.y0 < 16) {
+                const float rlim = f.radius * 1.001f + 0.01f;
+                const float rlim2 = rlim * rlim;
+                uint8_t *lst = sl + lane * kListStride;
+                int n = 0;
+                for (int yp = f.y0; yp <= f.y1; yp++) {
+                    const float dyc = f.y - ((float)yp + 0.5f);
+                    const float h2 = rlim2 - dyc * dyc;
+                    if (h2 < 0.0f) continue;
+                    const float h = sqrtf(h2);
+                    const int xa = max(f.x0, (int)floorf(f.x - h - 1.0f));
+                    const int xb = min(f.x1, (int)floorf(f.x + h));
+                    for (int xp = xa; xp <= xb; xp++) {
+                        if (n < kListCap) lst[n] = (uint8_t)(((yp - f.y0) << 4) | (xp - f.x0));
+                        n++;
+                    }
+                }
+                if (n <= kListCap) npx = (uint32_t)n;
+            }
+        }
+        SharedDab d;
+        d.x = f.x; d.y = f.y; d.hardness = f.hardness; d.one_over_r2 = f.one_over_r2;
+        d.r_aa_start = f.r_aa_start; d.seg1_slope = f.seg1_slope; d.seg2_offset = f.seg2_offset;
+        d.seg2_slope = f.seg2_slope;
+        d.opacity = (uint32_t)f.opacity;
+        d.box = (uint32_t)f.x0 | ((uint32_t)f.y0 << 8) | ((uint32_t)f.x1 << 16) | ((uint32_t)f.y1 << 24);
+        d.npx = npx;
+        d.aa = f.radius < 3.0f ? 1u : 0u;
+        if (hit) sd[lane] = d;
         unsigned mask = __ballot_sync(0xffffffffu, hit);
+        __syncwarp();
         while (mask) {
             const int j = __ffs(mask) - 1;
             mask &= mask - 1;
-            const float x = __shfl_sync(0xffffffffu, f.x, j);
-            const float y = __shfl_sync(0xffffffffu, f.y, j);
-            const float radius = __shfl_sync(0xffffffffu, f.radius, j);
-            const float hardness = __shfl_sync(0xffffffffu, f.hardness, j);
-            const float oor2 = __shfl_sync(0xffffffffu, f.one_over_r2, j);
-            const float ras = __shfl_sync(0xffffffffu, f.r_aa_start, j);
-            const float s1s = __shfl_sync(0xffffffffu, f.seg1_slope, j);
-            const float s2o = __shfl_sync(0xffffffffu, f.seg2_offset, j);
-            const float s2s = __shfl_sync(0xffffffffu, f.seg2_slope, j);
-            const uint32_t opacity = (uint32_t)__shfl_sync(0xffffffffu, f.opacity, j);
-            const int bx0 = __shfl_sync(0xffffffffu, cx0, j);
-            const int bx1 = __shfl_sync(0xffffffffu, cx1, j);
-            const int by0 = __shfl_sync(0xffffffffu, cy0, j);
-            const int by1 = __shfl_sync(0xffffffffu, cy1, j);
-            const bool aa = radius < 3.0f;
-            const int w = bx1 - bx0 + 1;                       // <= 32 (region width)
-            const int n = w * (by1 - by0 + 1);                  // <= 512
-            const uint32_t rcpw = kRcpW[w];
-            for (int p = lane; p < n; p += 32) {
-                const int ry = (int)(((uint32_t)p * rcpw) >> 16);
-                const int xp = bx0 + (p - ry * w);
-                const int yp = by0 + ry;
-                const float rr = dab_rr(P, xp, yp, x, y, oor2, ras, aa);
-                // calculate_opa
-                const float fac = rr <= hardness ? s1s : s2s;
-                float opa = rr <= hardness ? 1.0f : s2o;
-                opa += rr * fac;
-                if (rr > 1.0f) opa = 0.0f;
-                const uint32_t opa_ = (uint32_t)(unsigned short)(opa * 32768.0f);
-                if (opa_) {
-                    // draw_dab_pixels_BlendMode_Normal (alpha stays 1<<15 on an opaque canvas)
-                    const uint32_t opa_a = opa_ * opacity / (1u << 15);
-                    const uint32_t opa_b = (1u << 15) - opa_a;
-                    const int idx = yp * (kRowWords * 2) + xp;
-                    uint32_t r = s16[idx], g = s16[2 * kPlaneWords + idx], bl = s16[4 * kPlaneWords + idx];
-                    r = (opa_a * col_r + opa_b * r) / (1u << 15);
-                    g = (opa_a * col_g + opa_b * g) / (1u << 15);
-                    bl = (opa_a * col_b + opa_b * bl) / (1u << 15);
-                    s16[idx] = (uint16_t)r;
-                    s16[2 * kPlaneWords + idx] = (uint16_t)g;
-                    s16[4 * kPlaneWords + idx] = (uint16_t)bl;
+            const SharedDab cur = sd[j];                 // broadcast loads
+            const int bx0 = cur.box & 0xff, by0 = (cur.box >> 8) & 0xff;
+            if (cur.npx != kGeneric) {
+                const uint8_t *lst = sl + j * kListStride;
+                for (int p = lane; p < (int)cur.npx; p += 32) {
+                    const int q = lst[p];
+                    pixel(cur, bx0 + (q & 15), by0 + (q >> 4));
+                }
+            } else {
+                const int bx1 = (cur.box >> 16) & 0xff, by1 = cur.box >> 24;
+                const int w = bx1 - bx0 + 1;
+                const int n = w * (by1 - by0 + 1);
+                for (int p = lane; p < n; p += 32) {
+                    const int ry = p / w;
+                    pixel(cur, bx0 + (p - ry * w), by0 + ry);
                 }
             }
-            __syncwarp();
+            __syncwarp();                                // orders this dab's stores before the next dab's loads
         }
     }
-    __syncthreads();
 
-    // ---- tile store + fused read-back (pixops.cpp tile_convert_rgbu16_to_rgbu8, utils.py:3-5) ----
-    uint4 *dst = reinterpret_cast<uint4 *>(canvas + (size_t)b * kTile * kTile * 4);
-    float *ob = obs + (size_t)b * kTile * kTile * C;
+    // ---- fused read-back of the dirtied rows (pixops.cpp tile_convert_rgbu16_to_rgbu8, utils.py:3-5) ----
 #pragma unroll
-    for (int k = 0; k < (kTile * kTile / 2) / kCompThreads; k++) {
-        const int i = tid + k * kCompThreads;
-        const int row = i >> 5, colw = i & 31;
-        const int w = row * kRowWords + colw;
-        const uint32_t R = s_px[w], G = s_px[kPlaneWords + w], Bv = s_px[2 * kPlaneWords + w];
-        uint4 v;
-        v.x = (R & 0xffffu) | (G << 16);
-        v.y = (Bv & 0xffffu) | (32768u << 16);
-        v.z = (R >> 16) | (G & 0xffff0000u);
-        v.w = (Bv >> 16) | (32768u << 16);
-        dst[i] = v;
+    for (int off = 16; off; off >>= 1) {
+        ymin = min(ymin, __shfl_xor_sync(0xffffffffu, ymin, off));
+        ymax = max(ymax, __shfl_xor_sync(0xffffffffu, ymax, off));
+    }
+    if (ymax < ymin) return;
+    const uint4 *src = reinterpret_cast<const uint4 *>(tile);        // uint4 = 2 RGBA pixels
+    float *ob = obs + (size_t)b * kTile * kTile * C;
+#pragma unroll 4
+    for (int y = ymin; y <= ymax; y++) {
+        const int i = y * (kTile / 2) + lane;                          // pixel-pair index
+        const uint4 v = src[i];
+        const uint32_t R0 = v.x & 0xffffu, G0 = v.x >> 16, B0 = v.y & 0xffffu;
+        const uint32_t R1 = v.z & 0xffffu, G1 = v.z >> 16, B1 = v.w & 0xffffu;
         uint32_t add0 = 16384u, add1 = 16384u;
         if (P.dither) {
             const uint32_t nz = __ldg(reinterpret_cast<const uint32_t *>(dither) + i);
             add0 = nz & 0xffffu;
             add1 = nz >> 16;
         }
-        const uint32_t r0 = ((R & 0xffffu) * 255u + add0) >> 15, r1 = ((R >> 16) * 255u + add1) >> 15;
-        const uint32_t g0 = ((G & 0xffffu) * 255u + add0) >> 15, g1 = ((G >> 16) * 255u + add1) >> 15;
-        const uint32_t b0 = ((Bv & 0xffffu) * 255u + add0) >> 15, b1 = ((Bv >> 16) * 255u + add1) >> 15;
+        const uint32_t r0 = (R0 * 255u + add0) >> 15, r1 = (R1 * 255u + add1) >> 15;
+        const uint32_t g0 = (G0 * 255u + add0) >> 15, g1 = (G1 * 255u + add1) >> 15;
+        const uint32_t b0 = (B0 * 255u + add0) >> 15, b1 = (B1 * 255u + add1) >> 15;
         if (C == 1) {
             // np.dot(rgb, [0.299, 0.587, 0.114]) in float64, cast to float32
             double a0 = (double)r0 * 0.299;
@@ -865,10 +900,11 @@ cudaError_t launch_composite(const EnvParams &P, uint16_t *canvas, const float *
                              const int32_t *dab_count, const uint16_t *dither, float *obs,
                              cudaStream_t st)
 {
+    const int blocks = (P.B + kCompWarps - 1) / kCompWarps;
     if (P.C == 1)
-        composite_kernel<1><<<P.B, kCompThreads, 0, st>>>(P, canvas, dabs, dab_count, dither, obs);
+        composite_kernel<1><<<blocks, 32 * kCompWarps, 0, st>>>(P, canvas, dabs, dab_count, dither, obs);
     else
-        composite_kernel<3><<<P.B, kCompThreads, 0, st>>>(P, canvas, dabs, dab_count, dither, obs);
+        composite_kernel<3><<<blocks, 32 * kCompWarps, 0, st>>>(P, canvas, dabs, dab_count, dither, obs);
     return cudaGetLastError();
 }
 cudaError_t launch_debug_dabs(const EnvParams &P, const float *dabs, const int32_t *dab_count,

@@ -61,6 +61,7 @@ struct EnvParams {
     float sp_gamma[2], sp_m[2], sp_q[2];
     float dabs_basic, dabs_actual, dabs_second;
     float cs, sn, l2, rad_area_1;
+    int fast_spans;              // round upright dabs (ratio 1, sn == 1, |cs| ~ 0): composite may list candidate pixels
     float cull_factor;           // upper bound of radius / ACTUAL_RADIUS (radius_by_random)
     double rng_seed_block[10];   // first output block of rng_double after set_seed(1000)
 };
