@@ -214,6 +214,30 @@ int spiral_disc_load_weights(SpiralDisc *d, const SpiralDiscWeights *w, void *wo
 int spiral_disc_forward(SpiralDisc *d, const float *x_dev, int32_t batch, float *logits_dev,
                         float *probs_dev, float *bn_stats_dev, void *workspace_dev, void *stream);
 
+/* ------------------------------------------------------------------ */
+/* Convolution layer and its gradients (K2b)                            */
+/* replaces: what tf.gradients(d_loss) executes for                     */
+/*           models/discriminator.py:97-136 (WGAN-GP step: three        */
+/*           shared-weight passes :44-47,:113-114 and the double        */
+/*           backward of the penalty on d sigmoid(D(x^))/dx^ :116-120)   */
+/*           through tf.layers.conv2d(5x5, stride 2, 'same') :65-72      */
+/* ------------------------------------------------------------------ */
+/* x f32[B,H,H,Cin] NHWC, w f32 HWIO [5,5,Cin,Cout], y f32[B,H/2,H/2,Cout]; no bias (the host adds it).
+ * 'SAME' padding = 1 before / 2 after.  The three maps are bilinear and closed under differentiation,
+ * so first- and second-order gradients of the whole stack are compositions of them.
+ * precision: 0 = fp32 SIMT; 1 = tcgen05 bf16x3 (fp32-equivalent) where the channel counts allow
+ * (forward: Cin % 64 == 0 and Cout % 128 == 0; dgrad: Cout % 64 == 0; wgrad: any), else fp32 SIMT;
+ * 2 = tcgen05 plain bf16.  workspace: spiral_conv_workspace_bytes() bytes, caller-owned. */
+int64_t spiral_conv_workspace_bytes(int32_t B, int32_t H, int32_t Cin, int32_t Cout, int32_t precision);
+int spiral_conv_forward(const float *x_dev, const float *w_dev, float *y_dev, int32_t B, int32_t H,
+                        int32_t Cin, int32_t Cout, int32_t precision, void *workspace_dev, void *stream);
+/* dx f32[B,H,H,Cin] = gradient of sum(y * dy) w.r.t. x */
+int spiral_conv_dgrad(const float *dy_dev, const float *w_dev, float *dx_dev, int32_t B, int32_t H,
+                      int32_t Cin, int32_t Cout, int32_t precision, void *workspace_dev, void *stream);
+/* dw f32 HWIO [5,5,Cin,Cout] = gradient of sum(y * dy) w.r.t. w */
+int spiral_conv_wgrad(const float *x_dev, const float *dy_dev, float *dw_dev, int32_t B, int32_t H,
+                      int32_t Cin, int32_t Cout, int32_t precision, void *workspace_dev, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

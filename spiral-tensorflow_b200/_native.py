@@ -93,6 +93,10 @@ SYMBOLS = {
     "spiral_disc_workspace_bytes": (C.c_int64, [_vp, C.c_int32]),
     "spiral_disc_load_weights": (C.c_int, [_vp, C.POINTER(SpiralDiscWeights), _vp, _vp]),
     "spiral_disc_forward": (C.c_int, [_vp, _vp, C.c_int32, _vp, _vp, _vp, _vp, _vp]),
+    "spiral_conv_workspace_bytes": (C.c_int64, [C.c_int32] * 5),
+    "spiral_conv_forward": (C.c_int, [_vp, _vp, _vp] + [C.c_int32] * 5 + [_vp, _vp]),
+    "spiral_conv_dgrad": (C.c_int, [_vp, _vp, _vp] + [C.c_int32] * 5 + [_vp, _vp]),
+    "spiral_conv_wgrad": (C.c_int, [_vp, _vp, _vp] + [C.c_int32] * 5 + [_vp, _vp]),
 }
 
 _lib = None

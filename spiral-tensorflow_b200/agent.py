@@ -9,15 +9,15 @@ one process per GPU owns B canvases; a step of the loop is
                                            the PyTorch policy -> all-reduce -> clip 40 -> Adam
     train_gan()      agent.py:409-437      WGAN-GP step on (replay fakes, real targets)
 
-Only the three kernel families of the north-star path are native; the policy trunk and the
-discriminator's backward pass are the next rows and run through PyTorch autograd.
+The three kernel families of the north-star path are native, including the discriminator's
+backward / double-backward convolutions (models/conv_ops.py, K2b); the policy trunk is the next row
+ and runs through PyTorch autograd.
 """
 from __future__ import annotations
 
 import math
 
 import torch
-import torch.nn.functional as F
 
 from . import distributed as dist_utils
 from . import rl_utils
@@ -49,26 +49,6 @@ class TFAdam(torch.optim.Optimizer):
                 st["v"].mul_(b2).addcmul_(p.grad, p.grad, value=1 - b2)
                 lr_t = g["lr"] * math.sqrt(1 - b2 ** t) / (1 - b1 ** t)
                 p.addcdiv_(st["m"], st["v"].sqrt().add_(g["eps"]), value=-lr_t)
-
-
-def disc_forward_torch(params, x, layer_num, batch_norm, normalize=True):
-    """Differentiable plain-PyTorch D (TF semantics: SAME pad 1/2, BN eps 1e-3 biased variance,
-    leaky-ReLU 0.2) over the SAME parameter tensors the native forward reads; used for the WGAN-GP
-    training step until the tensor-core backward lands."""
-    if normalize:
-        x = (x - 127.5) / 127.5
-    x = x.permute(0, 3, 1, 2)
-    for l in range(layer_num):
-        k = params["conv%d/kernel" % l].permute(3, 2, 0, 1)
-        x = F.conv2d(F.pad(x, (1, 2, 1, 2)), k, params["conv%d/bias" % l], stride=2)
-        if l > 0 and batch_norm:
-            mean = x.mean(dim=(0, 2, 3), keepdim=True)
-            var = x.var(dim=(0, 2, 3), unbiased=False, keepdim=True)
-            x = (x - mean) * torch.rsqrt(var + 1e-3) * params["batch_normalization_%d/gamma" % l].view(1, -1, 1, 1) \
-                + params["batch_normalization_%d/beta" % l].view(1, -1, 1, 1)
-        x = F.leaky_relu(x, 0.2)
-    logits = (x.flatten(1) @ params["dense/kernel"] + params["dense/bias"]).reshape(-1)
-    return torch.sigmoid(logits), logits
 
 
 class Agent(object):
@@ -153,22 +133,13 @@ class Agent(object):
         fake = self.replay.sample(n)
         real = self.env.get_random_target(n) if reals is None else reals
         p = D.params
-        _, real_logits = disc_forward_torch(p, real, D.layer_num, D.batch_norm, D.normalize)
-        _, fake_logits = disc_forward_torch(p, fake, D.layer_num, D.batch_norm, D.normalize)
-        critic = fake_logits.mean() - real_logits.mean()
         alpha = torch.rand((n, 1), generator=self.rng, device=self.device)
-        fn = (fake - 127.5) / 127.5 if D.normalize else fake
-        rn = (real - 127.5) / 127.5 if D.normalize else real
-        inter = (rn.flatten(1) + alpha * (fn.flatten(1) - rn.flatten(1))).detach().requires_grad_(True)
-        probs, _ = disc_forward_torch(p, inter.view_as(fn), D.layer_num, D.batch_norm, normalize=False)
-        g = torch.autograd.grad(probs.sum(), inter, create_graph=True)[0]
-        slopes = torch.sqrt(1e-8 + (g ** 2).sum(1))
-        gp = ((slopes - 1.0) ** 2).mean()
-        d_loss = critic + args.wgan_lambda * gp
+        out = D.wgan_gp_loss(fake, real, alpha)          # convolutions + every gradient on K2b
+        d_loss, critic, gp, fake_logits_mean = out["d_loss"], out["critic_loss"], out["gradient_penalty"], -out["g_loss"]
         self.disc_opt.zero_grad(set_to_none=True)
         d_loss.backward()
         dist_utils.allreduce_grads_([q.grad for q in p.values() if q.grad is not None], self.world)
         self.disc_opt.step()
         D.sync_weights()
         return {"gan/critic_loss": critic.detach(), "gan/disc_loss": d_loss.detach(), "gan/penalty": gp.detach(),
-                "gan/gen_loss": -fake_logits.mean().detach()}
+                "gan/gen_loss": -fake_logits_mean.detach()}

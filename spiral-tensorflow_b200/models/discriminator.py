@@ -14,6 +14,7 @@ import numpy as np
 import torch
 
 from .. import _native as N
+from . import conv_ops
 
 PRECISIONS = {"fp32": 0, "bf16x3": 1, "bf16": 2}
 
@@ -132,3 +133,35 @@ class Discriminator(object):
     def predict(self, images):
         """reference :157-163."""
         return self.forward(images)[0]
+
+    # ------------------------------------------------------------------
+    def logits_fn(self, x_normed):
+        """Differentiable D on already-normalised NHWC input; convolutions and all their gradients
+        run on libspiral_b200.so (models/conv_ops.py)."""
+        prec = 0 if self.precision == 0 else self.precision
+        return conv_ops.disc_forward_native(self.params, x_normed, self.layer_num, self.batch_norm,
+                                            normalize=False, precision=prec)
+
+    def wgan_gp_loss(self, fake, real, alpha, wgan_lambda=None):
+        """reference :97-122 (build_optim): critic + lambda * gradient penalty, the penalty on the
+        gradient of the sigmoid OUTPUT w.r.t. the interpolates.  fake / real f32[N,S,S,C] in the
+        env's 0..255 units (norm_fn applied here when set), alpha f32[N,1] ~ U[0,1).
+        Returns a dict of differentiable scalars: d_loss, critic_loss, gradient_penalty, g_loss."""
+        lam = float(self.args.wgan_lambda if wgan_lambda is None else wgan_lambda)
+        f = fake.to(self.device, torch.float32)
+        r = real.to(self.device, torch.float32)
+        if self.normalize:
+            f, r = (f - 127.5) / 127.5, (r - 127.5) / 127.5
+        if self.conditional:                       # reference :36-38
+            f = torch.cat([f, r], -1)
+            r = torch.cat([r, r], -1)
+        _, real_logits = self.logits_fn(r)
+        _, fake_logits = self.logits_fn(f)
+        g_loss = -fake_logits.mean()
+        critic = fake_logits.mean() - real_logits.mean()
+        inter = (r.flatten(1) + alpha * (f.flatten(1) - r.flatten(1))).detach().requires_grad_(True)
+        probs, _ = self.logits_fn(inter.view_as(f))
+        grads = torch.autograd.grad(probs.sum(), inter, create_graph=True)[0]
+        slopes = torch.sqrt(1e-8 + (grads ** 2).sum(1))
+        gp = ((slopes - 1.0) ** 2).mean()
+        return dict(d_loss=critic + lam * gp, critic_loss=critic, gradient_penalty=gp, g_loss=g_loss)
