@@ -19,9 +19,7 @@
 //   layout, full/empty mbarriers, tcgen05.commit releases a stage back to the producer.
 // * kernel taps that fall entirely into the padding for a tile are skipped (layer 5 uses 4 of 25).
 #include "disc.cuh"
-
-#include <cuda.h>
-#include <cuda_bf16.h>
+#include "tc_ptx.cuh"
 
 #include <cstdio>
 #include <cstring>
@@ -37,98 +35,6 @@ constexpr int kTcThreads = 192;
 constexpr uint32_t kTileBytes = kBM * kBK * 2;                 // 16 KB (A and W tiles have the same shape)
 constexpr uint32_t kStageBytes = 4 * kTileBytes;               // A_hi, A_lo, W_hi, W_lo
 constexpr uint32_t kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
-
-// ---------------------------------------------------------------------------------------------
-// PTX wrappers
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
-{
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "WAIT_%=:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-        "@p bra DONE_%=;\n\t"
-        "bra WAIT_%=;\n\t"
-        "DONE_%=:\n\t"
-        "}" ::"r"(bar), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1, int c2, int c3)
-{
-    asm volatile(
-        "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int c0, int c1)
-{
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
-}
-__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap *map)
-{
-    asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
-}
-
-// K-major, 128-byte swizzle, rows of 128 B, 8-row groups 1024 B apart (cute::UMMA::SmemDescriptor)
-__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr)
-{
-    uint64_t d = 0;
-    d |= (uint64_t)((smem_addr >> 4) & 0x3fff);        // start address
-    d |= (uint64_t)1 << 16;                            // leading byte offset (unused for swizzled K-major)
-    d |= (uint64_t)(1024 >> 4) << 32;                  // stride byte offset: 8 rows * 128 B
-    d |= (uint64_t)1 << 46;                            // descriptor version (sm_100)
-    d |= (uint64_t)2 << 61;                            // SWIZZLE_128B
-    return d;
-}
-// kind::f16 instruction descriptor: BF16 x BF16 -> FP32, both operands K-major, M x N
-__host__ __device__ constexpr uint32_t umma_idesc(int M, int N)
-{
-    return (1u << 4)                  // c_format  = F32
-           | (1u << 7)                // a_format  = BF16
-           | (1u << 10)               // b_format  = BF16
-           | ((uint32_t)(N >> 3) << 17)
-           | ((uint32_t)(M >> 4) << 24);
-}
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate)
-{
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
-        "}" ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar)
-{
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32])
-{
-    uint32_t r[32];
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-        : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 32; i++) v[i] = __uint_as_float(r[i]);
-}
 
 struct ConvTcParams {
     int B, H, Cin, Cout;      // input NHWC [B,H,H,Cin]; output [B,H/2,H/2,Cout]
@@ -265,7 +171,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
             float v[32];
             tmem_ld32(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)cb, v);
 #pragma unroll
-            for (int j = 0; j < 32; j++) v[j] = row_ok ? v[j] + __ldg(bias + n_tile * kBN + cb + j) : 0.0f;
+            for (int j = 0; j < 32; j++) v[j] = row_ok ? v[j] + (bias ? __ldg(bias + n_tile * kBN + cb + j) : 0.0f) : 0.0f;
             if (row_ok) {
 #pragma unroll
                 for (int j = 0; j < 32; j += 4)
@@ -309,12 +215,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
 // elementwise helpers: hi/lo split of activations (with the producer's BN + leaky-ReLU applied)
 // and of the packed weights
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void split_bf16(float x, __nv_bfloat16 &hi, __nv_bfloat16 &lo)
-{
-    hi = __float2bfloat16_rn(x);
-    lo = __float2bfloat16_rn(x - __bfloat162float(hi));
-}
-
 // a = lrelu(raw * scale[c] + shift[c]);  raw fp32 NHWC with C channels (C % 4 == 0)
 __global__ void act_split_kernel(const float *__restrict__ raw, const float *__restrict__ scale,
                                  const float *__restrict__ shift, __nv_bfloat16 *__restrict__ hi,
@@ -359,9 +259,19 @@ __global__ void weight_pack_kernel(const float *__restrict__ w, __nv_bfloat16 *_
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
-                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn tc_encode_fn()
+{
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        const cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres);
+        if (e == cudaSuccess && p && qres == cudaDriverEntryPointSuccess) fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
 
 struct DiscTc {
     EncodeTiledFn encode;
@@ -400,16 +310,13 @@ int disc_tc_init(SpiralDisc *d)
                                 "tensor-core discriminator needs disc_dim %% 64 == 0 (got %d); use precision 0", d->cfg.disc_dim);
     DiscTc *t = new (std::nothrow) DiscTc();
     if (!t) return spiral_set_error(SPIRAL_EINVAL, "out of host memory");
-    void *fn = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
-    if (e != cudaSuccess || !fn || qres != cudaDriverEntryPointSuccess) {
+    t->encode = tc_encode_fn();
+    if (!t->encode) {
         delete t;
         return spiral_set_error(SPIRAL_ECUDA, "cuTensorMapEncodeTiled is not available from the driver");
     }
-    t->encode = (EncodeTiledFn)fn;
     t->first_tc_layer = 1;
-    e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
     if (e != cudaSuccess) {
         delete t;
         return spiral_cuda_error(e, "cudaFuncSetAttribute(conv_tc_kernel)");
@@ -535,6 +442,43 @@ int disc_tc_forward(SpiralDisc *d, const float *x, int batch, float *logits, flo
         (const float *)W.dense_w, (const float *)W.dense_b, logits, probs, batch, pl.Cout[last]);
     const cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? SPIRAL_OK : spiral_cuda_error(e, "spiral_disc_forward(tensor cores)");
+}
+
+// ---------------------------------------------------------------------------------------------
+// standalone layer (conv_tc.cu / spiral_conv_forward): same kernel, no bias, no BN partials
+// ---------------------------------------------------------------------------------------------
+void conv_tc_pack_weights(const float *w, void *w_hi, void *w_lo, int Cin, int Cout, cudaStream_t st)
+{
+    weight_pack_kernel<<<148 * 4, 256, 0, st>>>(w, (__nv_bfloat16 *)w_hi, (__nv_bfloat16 *)w_lo, Cin, Cout);
+}
+
+int conv_tc_layer(void *a_hi, void *a_lo, void *w_hi, void *w_lo, float *out, int B, int H, int Cin, int Cout,
+                  int x3, cudaStream_t st)
+{
+    static bool attr_set = false;
+    DiscTc t;
+    t.encode = tc_encode_fn();
+    t.first_tc_layer = 1;
+    if (!t.encode) return spiral_set_error(SPIRAL_ECUDA, "cuTensorMapEncodeTiled is not available from the driver");
+    if (!attr_set) {
+        const cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+        if (e != cudaSuccess) return spiral_cuda_error(e, "cudaFuncSetAttribute(conv_tc_kernel)");
+        attr_set = true;
+    }
+    const int Ho = H / 2;
+    ConvTcParams p;
+    p.B = B; p.H = H; p.Cin = Cin; p.Cout = Cout; p.M = B * Ho * Ho; p.x3 = x3;
+    if (Ho * Ho >= kBM) { p.bw = Ho; p.bh = kBM / Ho; p.bb = 1; }
+    else { p.bw = Ho; p.bh = Ho; p.bb = kBM / (Ho * Ho); }
+    CUtensorMap ma_hi, ma_lo, mw_hi, mw_lo;
+    int er = encode_act_map(&t, &ma_hi, a_hi, B, H, Cin, p.bw, p.bh, p.bb);
+    er |= encode_act_map(&t, &ma_lo, a_lo, B, H, Cin, p.bw, p.bh, p.bb);
+    er |= encode_w_map(&t, &mw_hi, w_hi, 25 * Cin, Cout);
+    er |= encode_w_map(&t, &mw_lo, w_lo, 25 * Cin, Cout);
+    if (er) return spiral_set_error(SPIRAL_ECUDA, "cuTensorMapEncodeTiled failed (CUresult %d)", er);
+    dim3 grid((p.M + kBM - 1) / kBM, Cout / kBN);
+    conv_tc_kernel<<<grid, kTcThreads, kSmemBytes, st>>>(ma_hi, ma_lo, mw_hi, mw_lo, p, nullptr, out, nullptr);
+    return SPIRAL_OK;
 }
 
 }  // namespace spiral
