@@ -4,10 +4,13 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 
 One "step" = one pass of the hot path over one batch of synthetic input: an episode of T=20 env
-steps for B=1024 canvases per GPU (reset + 20 x spiral_env_step), the discriminator reward on the
+steps for B canvases per GPU (reset + 20 x spiral_env_step), the discriminator reward on the
 final canvases (spiral_disc_forward), and the fused A2C loss + gradient over [B,T]
-(spiral_a2c_loss).  Workload = BASELINE.json configs[3] "rgb64": color_channel=3,
-location_size=64, episode_length=20, heads control/end 4096, color 8, jump/pressure/size 2.
+(spiral_a2c_loss).  Workload = BASELINE.json configs[3] "rgb64" shape (color_channel=3,
+location_size=64, episode_length=20, heads control/end 4096, color 8, jump/pressure/size 2) at the
+largest single-GPU batch of configs[4]'s sweep, B = 65536 canvases per GPU; the 16384- and
+1024-canvas points are reported beside it.  `disc_train` = one WGAN-GP discriminator step
+(batch 64, reference disc_batch_size) through the K2b gradient kernels.
 
 `value`  : whole-job env-steps/s, inputs resident in HBM, CUDA-event timed, max over ranks.
 `e2e`    : same metric through the Python env/model API with HOST (pinned) actions/values per
@@ -37,8 +40,11 @@ sys.path.insert(0, ROOT)
 # throughput sweep: 4096-65536 canvases x 20 strokes at 1/2/4/8 GPUs") gives the batch the throughput metric is
 # quoted on.  Default: 16384 canvases per GPU (weak scaling); the 1024-canvas point of configs[3] is reported in
 # the same JSON line under "rgb64_b1024".
-WORKLOAD = dict(workload="rgb64-sweep (configs[3] shape at configs[4] scale)", env="color_mnist", color_channel=3,
-                location_size=64, episode_length=20, canvases_per_gpu=16384, disc_dim=64)
+WORKLOAD = dict(workload="rgb64-sweep (configs[3] shape at configs[4]'s largest single-GPU batch)", env="color_mnist",
+                color_channel=3, location_size=64, episode_length=20, canvases_per_gpu=65536, disc_dim=64)
+# DRAM bytes per canvas-step of composite_kernel from the ncu --set full capture in profiles/ (B=16384:
+# dram__bytes_read 356.4 MB + dram__bytes_write 263.2 MB per launch)
+COMPOSITE_TRAFFIC_PER_CANVAS_STEP = (356.434688e6 + 263.226880e6) / 16384
 BYTES_PER_CANVAS_STEP = {1: 81920, 3: 114688}       # BASELINE.md section 3 (K1 algorithmic bytes)
 
 
@@ -320,10 +326,13 @@ def run_ours(args):
         dominant = max(("expand", "composite"), key=lambda k: share[k])
         dom_ms = t_exp if dominant == "expand" else t_comp
         roof = dict(bound="hbm", kernel="spiral::%s_kernel" % dominant, achieved=bytes_launch / (dom_ms * 1e-3) / 1e9,
-                    peak=peak, unit="GB/s", frac=bytes_launch / (dom_ms * 1e-3) / 1e9 / peak, traffic=None,
+                    peak=peak, unit="GB/s", frac=bytes_launch / (dom_ms * 1e-3) / 1e9 / peak,
+                    traffic=(COMPOSITE_TRAFFIC_PER_CANVAS_STEP * B if dominant == "composite" else 94.0e6 * B / 16384),
+                    traffic_source="ncu --set full at B=16384 (profiles/r1_path_b16384_ncu_summary.md), scaled by B",
                     peak_source=peak_src,
-                    note="algorithmic bytes = %d B/canvas-step x %d canvases per launch; K1 is ALU/latency-bound "
-                         "(serial brush state machine, ~550 dabs x ~64 px per painted step), see DESIGN.md" % (BYTES_PER_CANVAS_STEP[C], B),
+                    note="algorithmic bytes = %d B/canvas-step x %d canvases per launch; K1 is instruction-issue / "
+                         "latency-bound (serial brush state machine, ~270 dabs x ~20 px per painted step), its DRAM "
+                         "traffic is BELOW the algorithmic bytes (sparse in-place compositing), see DESIGN.md" % (BYTES_PER_CANVAS_STEP[C], B),
                     k1_pair=dict(achieved=pair_gbs, frac=pair_gbs / peak, ms_expand=t_exp, ms_composite=t_comp),
                     a2c=dict(achieved=2.0 * dlogits_bytes / (t_a2c * 1e-3) / 1e9, unit="GB/s",
                              frac=2.0 * dlogits_bytes / (t_a2c * 1e-3) / 1e9 / peak, ms=t_a2c),
@@ -346,16 +355,56 @@ def run_ours(args):
         torch.cuda.empty_cache()
         return out, (acs_list, head_list, C, L, T)
 
+    def disc_train_step(args, dev, C, n=64, iters=5):
+        """One WGAN-GP discriminator step (models/discriminator.py:97-136) at the reference's
+        disc_batch_size: 3 shared-weight passes, gradient penalty with its double backward, all
+        convolutions and their gradients on the library's kernels."""
+        a = sp.get_args(["--env", WORKLOAD["env"], "--color_channel", str(C), "--loss", "gan", "--disc_dim",
+                         str(WORKLOAD["disc_dim"]), "--disc_precision", args.disc_precision])
+        D = models.Discriminator(a, None, [64, 64, C], norm_fn=lambda x: x, scope_name="global", device=dev, max_batch=n)
+        for q in D.params.values():
+            q.requires_grad_(True)
+        g = torch.Generator(device=dev)
+        g.manual_seed(3)
+        fake = torch.rand((n, 64, 64, C), generator=g, device=dev) * 255
+        real = torch.rand((n, 64, 64, C), generator=g, device=dev) * 255
+        alpha = torch.rand((n, 1), generator=g, device=dev)
+
+        def step():
+            for q in D.params.values():
+                q.grad = None
+            out = D.wgan_gp_loss(fake, real, alpha, 20.0)
+            out["d_loss"].backward()
+            return out
+        for _ in range(2):
+            step()
+        torch.cuda.synchronize()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(iters):
+            out = step()
+        e.record()
+        torch.cuda.synchronize()
+        return dict(ms_per_step=s.elapsed_time(e) / iters, batch=n, precision=args.disc_precision,
+                    d_loss=float(out["d_loss"]), note="WGAN-GP step incl. double backward; conv fwd/dgrad/wgrad on K2b kernels, "
+                                                      "BN/leaky-ReLU/dense glue in PyTorch")
+
     res = measure(args.canvases)
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
     out, (acs_list, head_list, C, L, T) = res
-    if world == 1 and not args.no_secondary and args.canvases != 1024:
-        sec, _ = measure(1024)
-        out["rgb64_b1024"] = {k: sec[k] for k in ("value", "unit", "ms_per_step", "e2e", "kernel_ms_per_step")}
-        out["rgb64_b1024"]["config"] = "BASELINE.json configs[3]: 1024 canvases per GPU (latency-bound: the longest canvas's serial brush chain)"
+    if world == 1 and not args.no_secondary:
+        for nb, key, desc in ((16384, "rgb64_b16384", "configs[4] sweep point: 16384 canvases per GPU"),
+                              (1024, "rgb64_b1024", "BASELINE.json configs[3]: 1024 canvases per GPU (latency-bound: "
+                                                    "the longest canvas's serial brush chain)")):
+            if nb == args.canvases:
+                continue
+            sec, _ = measure(nb)
+            out[key] = {k: sec[k] for k in ("value", "unit", "ms_per_step", "e2e", "kernel_ms_per_step")}
+            out[key]["config"] = desc
+        out["disc_train"] = disc_train_step(args, dev, C)
     if world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline(args, acs_list, head_list, C, L, T, WORKLOAD["disc_dim"])
     print(json.dumps(out))
