@@ -608,33 +608,40 @@ __device__ __forceinline__ float dab_rr(const EnvParams &P, int xp, int yp, floa
 // Sparse in-place compositing: ONE WARP per canvas.
 //
 // A stroke is a serial chain of heavily overlapping dabs (6 + 6 per radius), each touching fewer than
-// 32 pixels, so the natural unit is a warp that walks its canvas's dab list in order with one lane
-// per candidate pixel; throughput comes from 32 independent canvases resident per SM, not from
-// splitting a tile among warps (which leaves most of them waiting at the barrier: ncu, round 1).
-// The fix15 tile stays where it lives -- in HBM/L2, pixels read-modify-written through L1 as one
-// 64-bit RGBA word -- so a step only touches the sectors under the stroke and only the rows it
-// dirtied are converted into the observation (the observation buffer is persistent: it already
-// holds the previous step's image).  Canvases without dabs (jump steps, the first step) cost one
-// 8-byte load.
+// 32 pixels, so the natural unit is a warp that walks its canvas's dab list in order; throughput
+// comes from 32 independent canvases resident per SM, not from splitting a tile among warps (which
+// leaves most of them waiting at the barrier: ncu, round 1).  The fix15 tile stays where it lives --
+// in HBM/L2, pixels read-modify-written through L1 as one 64-bit RGBA word -- so a step only touches
+// the sectors under the stroke and only the rows it dirtied are converted into the observation (the
+// observation buffer is persistent: it already holds the previous step's image).  Canvases without
+// dabs (jump steps, the first step) cost one 8-byte load.
 //
 // Candidate pixels: libmypaint walks the whole (r+1) bounding box, but for the round dabs this
 // engine draws (ratio 1, angle 90) calculate_rr_antialiased returns rr_near > 1 -- opacity 0 --
 // exactly when  dx_near^2 + dyc^2 > r^2  (dx_near: distance in x from the dab centre to the pixel's
-// [xp, xp+1] extent, dyc: distance in y to the pixel-centre row).  The dab's owner lane lists the
-// pixels inside that disc (radius inflated by 0.1 % + 0.01 px, far above float rounding) once, in
-// shared memory; skipped pixels are exactly pixels the reference blends with opa_ == 0.
+// [xp, xp+1] extent, dyc: distance in y to the pixel-centre row).  Only pixels inside that disc
+// (radius inflated by 0.1 % + 0.01 px, far above float rounding) are evaluated; skipped pixels are
+// exactly pixels the reference blends with opa_ == 0.
+//
+// Per round of up to 32 dabs:
+//   phase 0  lane-parallel: finalise one dab per lane, count its candidate pixels, warp-scan the
+//            counts, write (owner dab, pixel) pairs into one DENSE list in shared memory
+//   phase 1  the expensive, canvas-independent part -- the anti-aliased coverage rr, the opacity
+//            ramp, opa_a = mask * opacity -- for ALL (dab, pixel) pairs of the round, 32 per warp
+//            instruction regardless of dab boundaries (a dab alone fills ~17 of 32 lanes)
+//   phase 2  the cheap, order-dependent part: dab by dab, blend the pixels whose opa_a != 0
+// Dabs the disc test does not cover (radius >= 3, elliptical brushes) take the bounding-box walk.
 constexpr int kCompWarps = 1;                 // canvases (warps) per CTA
 constexpr int kListCap = 64;                  // candidate pixels per dab on the fast path
-constexpr int kListStride = 68;               // bytes; 17 words: conflict-free per-lane appends
-constexpr uint32_t kGeneric = 0xffffffffu;
+constexpr int kDense = 1024;                  // (dab, pixel) pairs per round: 16 dabs always fit
 
 struct __align__(16) SharedDab {
     float x, y, hardness, one_over_r2;
     float r_aa_start, seg1_slope, seg2_offset, seg2_slope;
     uint32_t opacity;       // fix15
     uint32_t box;           // x0 | y0 << 8 | x1 << 16 | y1 << 24, clipped to the tile
-    uint32_t npx;           // entries in the pixel list, or kGeneric: walk the bounding box
     uint32_t aa;            // radius < 3: anti-aliased rr
+    uint32_t pad;
 };
 
 template <int C>
@@ -644,7 +651,9 @@ composite_kernel(const __grid_constant__ EnvParams P, uint16_t *__restrict__ can
                  const uint16_t *__restrict__ dither, float *__restrict__ obs)
 {
     __shared__ SharedDab s_dab[kCompWarps][32];
-    __shared__ __align__(4) uint8_t s_list[kCompWarps][32 * kListStride];
+    __shared__ uint16_t s_pair[kCompWarps][kDense];     // owner dab << 8 | (yp - y0) << 4 | (xp - x0)
+    __shared__ uint16_t s_opa[kCompWarps][kDense];      // opa_a of the pair
+    __shared__ int s_off[kCompWarps][33];               // first pair of each dab of the round
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const int b = blockIdx.x * kCompWarps + warp;
@@ -657,32 +666,34 @@ composite_kernel(const __grid_constant__ EnvParams P, uint16_t *__restrict__ can
     uint2 *tile = reinterpret_cast<uint2 *>(canvas + (size_t)b * kTile * kTile * 4);   // RGBA u16x4 per pixel
     const float4 *dl = reinterpret_cast<const float4 *>(dabs + (size_t)b * P.max_dabs * kDabFloats);
     SharedDab *sd = s_dab[warp];
-    uint8_t *sl = s_list[warp];
+    uint16_t *sp = s_pair[warp], *so = s_opa[warp];
+    int *soff = s_off[warp];
     int ymin = kTile, ymax = -1;
 
-    // calculate_opa + draw_dab_pixels_BlendMode_Normal for one pixel
-    auto pixel = [&](const SharedDab &d, int xp, int yp) {
-        const int idx = yp * kTile + xp;
-        const uint2 px = tile[idx];
+    // calculate_opa: mask value (fix15) of one pixel of a dab
+    auto mask_of = [&](const SharedDab &d, int xp, int yp) -> uint32_t {
         const float rr = dab_rr(P, xp, yp, d.x, d.y, d.one_over_r2, d.r_aa_start, d.aa != 0);
         const float fac = rr <= d.hardness ? d.seg1_slope : d.seg2_slope;
         float opa = rr <= d.hardness ? 1.0f : d.seg2_offset;
         opa += rr * fac;
         if (rr > 1.0f) opa = 0.0f;
-        const uint32_t opa_ = (uint32_t)(unsigned short)(opa * 32768.0f);
-        if (opa_) {
-            const uint32_t opa_a = opa_ * d.opacity / (1u << 15);
-            const uint32_t opa_b = (1u << 15) - opa_a;
-            uint32_t r = px.x & 0xffffu, g = px.x >> 16, bl = px.y & 0xffffu, al = px.y >> 16;
-            r = (opa_a * col_r + opa_b * r) / (1u << 15);
-            g = (opa_a * col_g + opa_b * g) / (1u << 15);
-            bl = (opa_a * col_b + opa_b * bl) / (1u << 15);
-            al = opa_a + opa_b * al / (1u << 15);
-            tile[idx] = make_uint2(r | (g << 16), bl | (al << 16));
-        }
+        return (uint32_t)(unsigned short)(opa * 32768.0f);
+    };
+    // draw_dab_pixels_BlendMode_Normal for one pixel
+    auto blend = [&](int idx, uint32_t opa_a) {
+        const uint2 px = tile[idx];
+        const uint32_t opa_b = (1u << 15) - opa_a;
+        uint32_t r = px.x & 0xffffu, g = px.x >> 16, bl = px.y & 0xffffu, al = px.y >> 16;
+        r = (opa_a * col_r + opa_b * r) / (1u << 15);
+        g = (opa_a * col_g + opa_b * g) / (1u << 15);
+        bl = (opa_a * col_b + opa_b * bl) / (1u << 15);
+        al = opa_a + opa_b * al / (1u << 15);
+        tile[idx] = make_uint2(r | (g << 16), bl | (al << 16));
     };
 
-    for (int base = 0; base < n_dabs; base += 32) {
+    int base = 0;
+    while (base < n_dabs) {
+        // ---- phase 0: finalise, count candidates ----
         const int mine = base + lane;
         FinalDab f;
         f.opacity = 0; f.x0 = 1; f.x1 = 0; f.y0 = 1; f.y1 = 0;
@@ -690,15 +701,12 @@ composite_kernel(const __grid_constant__ EnvParams P, uint16_t *__restrict__ can
         f.seg1_slope = f.seg2_offset = f.seg2_slope = 0;
         if (mine < n_dabs) f = finalize_dab(__ldg(dl + 2 * mine), __ldg(dl + 2 * mine + 1));
         const bool hit = f.opacity != 0;             // 0 also when the dab misses tile (0,0)
-        uint32_t npx = kGeneric;
+        const float rlim = f.radius * 1.001f + 0.01f;
+        const float rlim2 = rlim * rlim;
+        int cnt = 0;
+        bool generic = false;
         if (hit) {
-            ymin = min(ymin, f.y0);
-            ymax = max(ymax, f.y1);
             if (P.fast_spans && f.radius < 3.0f && f.x1 - f.x0 < 16 && f.y1 - f.y0 < 16) {
-                const float rlim = f.radius * 1.001f + 0.01f;
-                const float rlim2 = rlim * rlim;
-                uint8_t *lst = sl + lane * kListStride;
-                int n = 0;
                 for (int yp = f.y0; yp <= f.y1; yp++) {
                     const float dyc = f.y - ((float)yp + 0.5f);
                     const float h2 = rlim2 - dyc * dyc;
@@ -706,47 +714,104 @@ composite_kernel(const __grid_constant__ EnvParams P, uint16_t *__restrict__ can
                     const float h = sqrtf(h2);
                     const int xa = max(f.x0, (int)floorf(f.x - h - 1.0f));
                     const int xb = min(f.x1, (int)floorf(f.x + h));
-                    for (int xp = xa; xp <= xb; xp++) {
-                        if (n < kListCap) lst[n] = (uint8_t)(((yp - f.y0) << 4) | (xp - f.x0));
-                        n++;
-                    }
+                    cnt += max(0, xb - xa + 1);
                 }
-                if (n <= kListCap) npx = (uint32_t)n;
+                if (cnt > kListCap) { generic = true; cnt = 0; }
+            } else {
+                generic = true;
             }
         }
+        int incl = cnt;                              // inclusive warp scan of the counts
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        // this round takes dabs [0, m): up to the first bounding-box dab, and while the pairs fit
+        const unsigned stop = __ballot_sync(0xffffffffu, generic || incl > kDense);
+        const int m = stop ? __ffs(stop) - 1 : 32;
+
         SharedDab d;
         d.x = f.x; d.y = f.y; d.hardness = f.hardness; d.one_over_r2 = f.one_over_r2;
         d.r_aa_start = f.r_aa_start; d.seg1_slope = f.seg1_slope; d.seg2_offset = f.seg2_offset;
         d.seg2_slope = f.seg2_slope;
         d.opacity = (uint32_t)f.opacity;
         d.box = (uint32_t)f.x0 | ((uint32_t)f.y0 << 8) | ((uint32_t)f.x1 << 16) | ((uint32_t)f.y1 << 24);
-        d.npx = npx;
         d.aa = f.radius < 3.0f ? 1u : 0u;
-        if (hit) sd[lane] = d;
-        unsigned mask = __ballot_sync(0xffffffffu, hit);
-        __syncwarp();
-        while (mask) {
-            const int j = __ffs(mask) - 1;
-            mask &= mask - 1;
-            const SharedDab cur = sd[j];                 // broadcast loads
+        d.pad = 0;
+
+        if (m == 0) {
+            // the first dab of the round walks its bounding box (libmypaint's own loop)
+            if (lane == 0) {
+                sd[0] = d;
+                ymin = min(ymin, f.y0);
+                ymax = max(ymax, f.y1);
+            }
+            __syncwarp();
+            const SharedDab cur = sd[0];
             const int bx0 = cur.box & 0xff, by0 = (cur.box >> 8) & 0xff;
-            if (cur.npx != kGeneric) {
-                const uint8_t *lst = sl + j * kListStride;
-                for (int p = lane; p < (int)cur.npx; p += 32) {
-                    const int q = lst[p];
-                    pixel(cur, bx0 + (q & 15), by0 + (q >> 4));
-                }
-            } else {
-                const int bx1 = (cur.box >> 16) & 0xff, by1 = cur.box >> 24;
-                const int w = bx1 - bx0 + 1;
-                const int n = w * (by1 - by0 + 1);
-                for (int p = lane; p < n; p += 32) {
-                    const int ry = p / w;
-                    pixel(cur, bx0 + (p - ry * w), by0 + ry);
+            const int bx1 = (cur.box >> 16) & 0xff, by1 = cur.box >> 24;
+            const int w = bx1 - bx0 + 1;
+            const int n = w * (by1 - by0 + 1);
+            for (int p = lane; p < n; p += 32) {
+                const int ry = p / w;
+                const int xp = bx0 + (p - ry * w), yp = by0 + ry;
+                const uint32_t opa_ = mask_of(cur, xp, yp);
+                if (opa_) blend(yp * kTile + xp, opa_ * cur.opacity / (1u << 15));
+            }
+            __syncwarp();
+            base += 1;
+            continue;
+        }
+
+        const int off = incl - cnt;
+        const int total = __shfl_sync(0xffffffffu, incl, m - 1);
+        soff[lane] = lane < m ? off : total;
+        if (lane == 0) soff[32] = total;
+        if (lane < m && hit) {
+            ymin = min(ymin, f.y0);
+            ymax = max(ymax, f.y1);
+            sd[lane] = d;
+            int n = off;
+            for (int yp = f.y0; yp <= f.y1; yp++) {
+                const float dyc = f.y - ((float)yp + 0.5f);
+                const float h2 = rlim2 - dyc * dyc;
+                if (h2 < 0.0f) continue;
+                const float h = sqrtf(h2);
+                const int xa = max(f.x0, (int)floorf(f.x - h - 1.0f));
+                const int xb = min(f.x1, (int)floorf(f.x + h));
+                for (int xp = xa; xp <= xb; xp++) sp[n++] = (uint16_t)((lane << 8) | ((yp - f.y0) << 4) | (xp - f.x0));
+            }
+        }
+        __syncwarp();
+
+        // ---- phase 1: coverage and opacity of every (dab, pixel) pair, densely packed ----
+        for (int k = lane; k < total; k += 32) {
+            const uint32_t e = sp[k];
+            const SharedDab &cur = sd[e >> 8];
+            const uint32_t box = cur.box;
+            const int xp = (int)(box & 0xff) + (int)(e & 15), yp = (int)((box >> 8) & 0xff) + (int)((e >> 4) & 15);
+            const uint32_t opa_ = mask_of(cur, xp, yp);
+            so[k] = (uint16_t)(opa_ * cur.opacity / (1u << 15));
+        }
+        __syncwarp();
+
+        // ---- phase 2: ordered blend ----
+        for (int j = 0; j < m; j++) {
+            const int o0 = soff[j], o1 = soff[j + 1];
+            if (o0 == o1) continue;
+            const uint32_t box = sd[j].box;
+            const int bx0 = box & 0xff, by0 = (box >> 8) & 0xff;
+            for (int k = o0 + lane; k < o1; k += 32) {
+                const uint32_t opa_a = so[k];
+                if (opa_a) {
+                    const uint32_t e = sp[k];
+                    blend((by0 + (int)((e >> 4) & 15)) * kTile + bx0 + (int)(e & 15), opa_a);
                 }
             }
             __syncwarp();                                // orders this dab's stores before the next dab's loads
         }
+        base += m;
     }
 
     // ---- fused read-back of the dirtied rows (pixops.cpp tile_convert_rgbu16_to_rgbu8, utils.py:3-5) ----
@@ -901,6 +966,12 @@ cudaError_t launch_composite(const EnvParams &P, uint16_t *canvas, const float *
                              cudaStream_t st)
 {
     const int blocks = (P.B + kCompWarps - 1) / kCompWarps;
+    static bool carveout = false;
+    if (!carveout) {      // 32 resident warps need 32 x 5.8 KB of shared memory: ask for the large carve-out
+        cudaFuncSetAttribute(composite_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaFuncSetAttribute(composite_kernel<3>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        carveout = true;
+    }
     if (P.C == 1)
         composite_kernel<1><<<blocks, 32 * kCompWarps, 0, st>>>(P, canvas, dabs, dab_count, dither, obs);
     else
