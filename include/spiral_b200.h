@@ -127,7 +127,9 @@ int spiral_env_step(SpiralEnv *env, const int32_t *actions_dev, uint16_t *canvas
 
 /* the two halves of spiral_env_step, exposed for profiling and tests:
  *   expand    : stroke expansion (action -> events -> brush state machine -> pending dabs)
- *   composite : dab mask + fix15 blend into the smem-resident canvas + read-back */
+ *   composite : dab mask + fix15 blend into the canvas tile (in place) + read-back of the rows it
+ *               dirtied.  obs_dev is PERSISTENT: it must be the buffer the previous step / reset wrote
+ *               (canvases a step does not paint keep their observation without being touched). */
 int spiral_env_expand(SpiralEnv *env, const int32_t *actions_dev, float *brush_state_dev,
                       double *env_state_dev, float *dab_scratch_dev, int32_t *dab_count_dev,
                       int32_t *status_dev, void *stream);
