@@ -20,7 +20,8 @@
 namespace spiral {
 cudaError_t launch_reset(const EnvParams &P, uint16_t *canvas, float *bs, double *es, float *obs, cudaStream_t st);
 cudaError_t launch_expand(const EnvParams &P, const int32_t *actions, float *bs, double *es, float *dabs,
-                          int32_t *dab_count, int32_t *status, const float *gauss_tab, cudaStream_t st);
+                          int32_t *dab_count, int32_t *status, const float *gauss_tab, int32_t *plan_scratch,
+                          cudaStream_t st);
 cudaError_t launch_composite(const EnvParams &P, uint16_t *canvas, const float *dabs, const int32_t *dab_count,
                              const uint16_t *dither, float *obs, cudaStream_t st);
 cudaError_t launch_debug_dabs(const EnvParams &P, const float *dabs, const int32_t *dab_count, float *out,
@@ -135,6 +136,7 @@ struct SpiralEnv {
     int device;
     uint16_t *d_dither;
     float *d_gauss;
+    int32_t *d_plan;          // expand scheduling scratch: histogram, permutation, keys
 };
 
 static bool is_pow2f(float v)
@@ -207,6 +209,8 @@ extern "C" int spiral_env_create(const SpiralEnvCfg *cfg, SpiralEnv **out)
         const char *e = getenv("SPIRAL_EXPAND_LANES");      // tuning knob for profiling
         P.expand_lanes = e ? atoi(e) : 0;
         if (P.expand_lanes < 0 || P.expand_lanes > 32) P.expand_lanes = 0;
+        const char *so = getenv("SPIRAL_EXPAND_SORT");       // 0 disables the work-sorted schedule (profiling)
+        P.expand_sort = so ? (atoi(so) != 0) : 1;
     }
     for (int s = 0; s < SPIRAL_DYN_COUNT; s++) {
         MapDev &m = P.dyn[s];
@@ -298,6 +302,7 @@ extern "C" int spiral_env_create(const SpiralEnvCfg *cfg, SpiralEnv **out)
     if (e == cudaSuccess)
         e = cudaMemcpy(env->d_dither, cfg->dither_table, sizeof(cfg->dither_table), cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMalloc(&env->d_gauss, sizeof(float) * (size_t)cfg->rng_table_len);
+    if (e == cudaSuccess) e = cudaMalloc(&env->d_plan, sizeof(int32_t) * (512 + (size_t)cfg->batch) + (size_t)cfg->batch + 16);
     if (e == cudaSuccess) {
         float *g = new float[(size_t)cfg->rng_table_len];
         rng_gauss_table(1000, cfg->rng_table_len, g);
@@ -308,6 +313,7 @@ extern "C" int spiral_env_create(const SpiralEnvCfg *cfg, SpiralEnv **out)
     if (e != cudaSuccess) {
         if (env->d_dither) cudaFree(env->d_dither);
         if (env->d_gauss) cudaFree(env->d_gauss);
+        if (env->d_plan) cudaFree(env->d_plan);
         delete env;
         return spiral_cuda_error(e, "spiral_env_create");
     }
@@ -320,6 +326,7 @@ extern "C" int spiral_env_destroy(SpiralEnv *env)
     if (!env) return SPIRAL_OK;
     if (env->d_dither) cudaFree(env->d_dither);
     if (env->d_gauss) cudaFree(env->d_gauss);
+    if (env->d_plan) cudaFree(env->d_plan);
     delete env;
     return SPIRAL_OK;
 }
@@ -337,7 +344,7 @@ extern "C" int spiral_env_expand(SpiralEnv *env, const int32_t *actions, float *
                                  int32_t *dab_count, int32_t *status, void *stream)
 {
     REQUIRE(env); REQUIRE(actions); REQUIRE(bs); REQUIRE(es); REQUIRE(dabs); REQUIRE(dab_count); REQUIRE(status);
-    const cudaError_t e = launch_expand(env->P, actions, bs, es, dabs, dab_count, status, env->d_gauss, (cudaStream_t)stream);
+    const cudaError_t e = launch_expand(env->P, actions, bs, es, dabs, dab_count, status, env->d_gauss, env->d_plan, (cudaStream_t)stream);
     return e == cudaSuccess ? SPIRAL_OK : spiral_cuda_error(e, "spiral_env_expand");
 }
 

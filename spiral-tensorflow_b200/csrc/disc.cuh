@@ -38,6 +38,13 @@ __global__ void dense_sigmoid_kernel(const float *in, const float *in_scale, con
 
 int disc_conv0(SpiralDisc *d, const float *x, int batch, float *out, void *out_hi, void *out_lo, cudaStream_t st);
 
+// layer 0 on tensor cores (disc_conv0_mma.cu)
+size_t conv0_mma_pack_bytes(int Cin);
+bool conv0_mma_supported(const SpiralDisc *d);
+void conv0_mma_pack(const SpiralDisc *d, void *w_hi, void *w_lo, cudaStream_t st);
+int conv0_mma_forward(const SpiralDisc *d, const float *x, int batch, const void *w_hi, const void *w_lo, void *out_hi,
+                      void *out_lo, int x3, cudaStream_t st);
+
 // tensor-core path (disc_tc.cu)
 int disc_tc_init(SpiralDisc *d);
 size_t disc_tc_workspace_bytes(const SpiralDisc *d, int batch);

@@ -1,0 +1,229 @@
+// disc_conv0_mma.cu -- K2, layer 0 on tensor cores.
+//
+// Layer 0 of the discriminator (models/discriminator.py:61-81, i = 0) is a 5x5 / stride-2 / 'SAME'
+// convolution with K = 25 * C (C = 1, 3 or 6 input channels): too narrow for a TMA-fed tcgen05
+// pipeline (a 3-channel NHWC pixel is 6 bytes of bf16; TMA boxes need 16-byte inner extents), and as
+// a register-tiled SIMT kernel it was the single most expensive kernel of the reward forward (ncu,
+// round 1: 7.6 of 27 ms at B = 16384, issue-bound at 21 TFLOP/s).  Here the im2col never exists in
+// memory: the normalised input tile is staged once in shared memory as bf16 hi/lo, every thread
+// gathers its mma.m16n8k16 A fragment straight from it through a per-k offset table, B fragments come
+// from the pre-split, pre-transposed kernel in shared memory, and the same bf16x3 split as the other
+// layers (hi*hi + hi*lo + lo*hi, fp32 accumulate) keeps fp32-equivalent accuracy.  Epilogue: + bias,
+// leaky-ReLU (no BN at layer 0), hi/lo split, staged through shared memory into the fully coalesced
+// bf16 NHWC pair layer 1's TMA reads.
+//
+// CTA = 8 warps = 8 output rows x 16 output pixels x 64 channels; warp = one row of 16 pixels (M = 16)
+// x all 64 channels (8 n-tiles), K padded to a multiple of 16 with zero weights.
+#include "disc.cuh"
+
+#include <cuda_bf16.h>
+
+namespace spiral {
+
+constexpr int kC0Tw = 16, kC0Th = 8;                    // output tile
+constexpr int kC0Iw = 2 * kC0Tw + 3, kC0Ih = 2 * kC0Th + 3;   // input tile 35 x 19
+constexpr int kC0Cout = 64;
+
+__host__ __device__ constexpr int c0_kpad(int cin) { return (25 * cin + 15) / 16 * 16; }
+__host__ __device__ constexpr int c0_kstride(int cin) { return c0_kpad(cin) + 8; }   // bf16 per row; conflict-free
+
+__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2])
+{
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
+__device__ __forceinline__ uint32_t pack2(uint16_t lo, uint16_t hi) { return (uint32_t)lo | ((uint32_t)hi << 16); }
+
+// HWIO [25][CIN][64] fp32 -> [64][KS] bf16 hi / lo with k = tap * CIN + c (zero padded)
+__global__ void conv0_pack_kernel(const float *__restrict__ w, __nv_bfloat16 *__restrict__ hi,
+                                  __nv_bfloat16 *__restrict__ lo, int Cin)
+{
+    const int K = 25 * Cin, KS = c0_kstride(Cin);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < kC0Cout * KS; i += gridDim.x * blockDim.x) {
+        const int n = i / KS, k = i % KS;
+        const float v = k < K ? w[(size_t)k * kC0Cout + n] : 0.0f;
+        const __nv_bfloat16 h = __float2bfloat16_rn(v);
+        hi[i] = h;
+        lo[i] = __float2bfloat16_rn(v - __bfloat162float(h));
+    }
+}
+
+template <int CIN>
+__global__ void __launch_bounds__(256)
+conv0_mma_kernel(const float *__restrict__ x, const __nv_bfloat16 *__restrict__ w_hi, const __nv_bfloat16 *__restrict__ w_lo,
+                 const float *__restrict__ bias, __nv_bfloat16 *__restrict__ out_hi, __nv_bfloat16 *__restrict__ out_lo,
+                 int B, int H, int normalize, int x3)
+{
+    constexpr int K = 25 * CIN, KP = c0_kpad(CIN), KS = c0_kstride(CIN);
+    constexpr int NIN = kC0Ih * kC0Iw * CIN;
+    extern __shared__ __align__(16) uint8_t sm_raw[];
+    uint16_t *s_wh = reinterpret_cast<uint16_t *>(sm_raw);                 // [64][KS]
+    uint16_t *s_wl = s_wh + kC0Cout * KS;
+    uint16_t *s_ih = s_wl + kC0Cout * KS;                                  // [19][35][CIN]
+    uint16_t *s_il = s_ih + ((NIN + 7) & ~7);
+    int *s_koff = reinterpret_cast<int *>(s_il + ((NIN + 7) & ~7));        // [KP]
+    uint16_t *s_out = reinterpret_cast<uint16_t *>(s_koff + KP);           // [8 warps][2][16 px][64 ch]
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int Ho = H / 2;
+    const int tiles_x = Ho / kC0Tw, tiles_y = Ho / kC0Th;
+    const int img = blockIdx.x / (tiles_x * tiles_y);
+    const int trem = blockIdx.x % (tiles_x * tiles_y);
+    const int oy0 = (trem / tiles_x) * kC0Th, ox0 = (trem % tiles_x) * kC0Tw;
+
+    // ---- stage the packed kernel (16-byte copies), the k -> input-offset table and the input tile ----
+    {
+        const uint4 *gh = reinterpret_cast<const uint4 *>(w_hi), *gl = reinterpret_cast<const uint4 *>(w_lo);
+        uint4 *sh = reinterpret_cast<uint4 *>(s_wh), *sl = reinterpret_cast<uint4 *>(s_wl);
+        constexpr int n16 = kC0Cout * KS * 2 / 16;
+        for (int i = tid; i < n16; i += 256) {
+            sh[i] = __ldg(gh + i);
+            sl[i] = __ldg(gl + i);
+        }
+        for (int k = tid; k < KP; k += 256) {
+            int off = 0;
+            if (k < K) {
+                const int tap = k / CIN, c = k - tap * CIN;
+                const int ky = tap / 5, kx = tap - 5 * ky;
+                off = (ky * kC0Iw + kx) * CIN + c;
+            }
+            s_koff[k] = off;
+        }
+        const float *xi = x + (size_t)img * H * H * CIN;
+        for (int i = tid; i < NIN; i += 256) {
+            const int c = i % CIN, p = i / CIN;
+            const int ly = p / kC0Iw, lx = p - ly * kC0Iw;
+            const int iy = 2 * oy0 - 1 + ly, ix = 2 * ox0 - 1 + lx;
+            float v = 0.0f;
+            if (iy >= 0 && iy < H && ix >= 0 && ix < H) {
+                v = __ldg(xi + ((size_t)iy * H + ix) * CIN + c);
+                if (normalize) v = (v - 127.5f) / 127.5f;
+            }
+            const __nv_bfloat16 h = __float2bfloat16_rn(v);
+            s_ih[i] = __bfloat16_as_ushort(h);
+            s_il[i] = __bfloat16_as_ushort(__float2bfloat16_rn(v - __bfloat162float(h)));
+        }
+    }
+    __syncthreads();
+
+    // ---- main loop: warp = output row `warp` of the tile, 16 pixels x 64 channels ----
+    const int g = lane >> 2, t = lane & 3;
+    const int base0 = ((2 * warp) * kC0Iw + 2 * g) * CIN;              // pixel g
+    const int base1 = base0 + 16 * CIN;                                  // pixel g + 8
+    float acc[8][4];
+#pragma unroll
+    for (int nt = 0; nt < 8; nt++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) acc[nt][j] = 0.0f;
+
+#pragma unroll 1
+    for (int ks = 0; ks < KP / 16; ks++) {
+        const int k0 = ks * 16 + 2 * t;
+        const int o0 = s_koff[k0], o1 = s_koff[k0 + 1], o8 = s_koff[k0 + 8], o9 = s_koff[k0 + 9];
+        uint32_t ah[4], al[4];
+        ah[0] = pack2(s_ih[base0 + o0], s_ih[base0 + o1]);
+        ah[1] = pack2(s_ih[base1 + o0], s_ih[base1 + o1]);
+        ah[2] = pack2(s_ih[base0 + o8], s_ih[base0 + o9]);
+        ah[3] = pack2(s_ih[base1 + o8], s_ih[base1 + o9]);
+        if (x3) {
+            al[0] = pack2(s_il[base0 + o0], s_il[base0 + o1]);
+            al[1] = pack2(s_il[base1 + o0], s_il[base1 + o1]);
+            al[2] = pack2(s_il[base0 + o8], s_il[base0 + o9]);
+            al[3] = pack2(s_il[base1 + o8], s_il[base1 + o9]);
+        }
+#pragma unroll
+        for (int nt = 0; nt < 8; nt++) {
+            const int wrow = (nt * 8 + g) * KS + k0;
+            uint32_t bh[2], bl[2];
+            bh[0] = *reinterpret_cast<const uint32_t *>(s_wh + wrow);
+            bh[1] = *reinterpret_cast<const uint32_t *>(s_wh + wrow + 8);
+            if (x3) {
+                bl[0] = *reinterpret_cast<const uint32_t *>(s_wl + wrow);
+                bl[1] = *reinterpret_cast<const uint32_t *>(s_wl + wrow + 8);
+                mma_bf16_16816(acc[nt], al, bh);
+                mma_bf16_16816(acc[nt], ah, bl);
+            }
+            mma_bf16_16816(acc[nt], ah, bh);
+        }
+    }
+
+    // ---- epilogue: + bias, leaky-ReLU, hi/lo split, staged so that the warp writes 2 KB contiguous ----
+    uint16_t *so_h = s_out + warp * (2 * 16 * kC0Cout), *so_l = so_h + 16 * kC0Cout;
+#pragma unroll
+    for (int nt = 0; nt < 8; nt++) {
+        const int ch = nt * 8 + 2 * t;
+        const float b0 = __ldg(bias + ch), b1 = __ldg(bias + ch + 1);
+#pragma unroll
+        for (int half = 0; half < 2; half++) {
+            float v0 = acc[nt][2 * half] + b0, v1 = acc[nt][2 * half + 1] + b1;
+            v0 = v0 > 0.f ? v0 : 0.2f * v0;
+            v1 = v1 > 0.f ? v1 : 0.2f * v1;
+            const __nv_bfloat16 h0 = __float2bfloat16_rn(v0), h1 = __float2bfloat16_rn(v1);
+            const __nv_bfloat16 l0 = __float2bfloat16_rn(v0 - __bfloat162float(h0));
+            const __nv_bfloat16 l1 = __float2bfloat16_rn(v1 - __bfloat162float(h1));
+            const int px = g + 8 * half;
+            *reinterpret_cast<uint32_t *>(so_h + px * kC0Cout + ch) = pack2(__bfloat16_as_ushort(h0), __bfloat16_as_ushort(h1));
+            *reinterpret_cast<uint32_t *>(so_l + px * kC0Cout + ch) = pack2(__bfloat16_as_ushort(l0), __bfloat16_as_ushort(l1));
+        }
+    }
+    __syncwarp();
+    const size_t opix = ((size_t)img * Ho + oy0 + warp) * Ho + ox0;        // 16 consecutive pixels
+    uint4 *gh = reinterpret_cast<uint4 *>(out_hi + opix * kC0Cout), *gl = reinterpret_cast<uint4 *>(out_lo + opix * kC0Cout);
+    const uint4 *sh = reinterpret_cast<const uint4 *>(so_h), *sl = reinterpret_cast<const uint4 *>(so_l);
+#pragma unroll
+    for (int i = 0; i < 4; i++) {                                          // 16 px * 128 B = 128 x 16 B
+        gh[lane + 32 * i] = sh[lane + 32 * i];
+        gl[lane + 32 * i] = sl[lane + 32 * i];
+    }
+}
+
+size_t conv0_mma_pack_bytes(int Cin) { return (size_t)kC0Cout * c0_kstride(Cin) * 2; }
+
+bool conv0_mma_supported(const SpiralDisc *d)
+{
+    const int Cin = d->cfg.in_channels, Ho = d->cfg.screen_size / 2;
+    return d->cfg.disc_dim == kC0Cout && (Cin == 1 || Cin == 3 || Cin == 6) && (Ho % kC0Tw) == 0 && (Ho % kC0Th) == 0;
+}
+
+void conv0_mma_pack(const SpiralDisc *d, void *w_hi, void *w_lo, cudaStream_t st)
+{
+    conv0_pack_kernel<<<8, 256, 0, st>>>((const float *)d->w.conv_w[0], (__nv_bfloat16 *)w_hi, (__nv_bfloat16 *)w_lo,
+                                         d->cfg.in_channels);
+}
+
+template <int CIN>
+static int conv0_launch(const SpiralDisc *d, const float *x, int batch, const void *w_hi, const void *w_lo, void *out_hi,
+                        void *out_lo, int x3, cudaStream_t st)
+{
+    constexpr int KP = c0_kpad(CIN), KS = c0_kstride(CIN), NIN = kC0Ih * kC0Iw * CIN;
+    constexpr size_t smem = (size_t)2 * kC0Cout * KS * 2 + (size_t)2 * ((NIN + 7) & ~7) * 2 + (size_t)KP * 4 +
+                            (size_t)8 * 2 * 16 * kC0Cout * 2;
+    static bool attr = false;
+    if (!attr) {
+        const cudaError_t e = cudaFuncSetAttribute(conv0_mma_kernel<CIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return spiral_cuda_error(e, "cudaFuncSetAttribute(conv0_mma_kernel)");
+        attr = true;
+    }
+    const int H = d->cfg.screen_size, Ho = H / 2;
+    const int grid = batch * (Ho / kC0Tw) * (Ho / kC0Th);
+    conv0_mma_kernel<CIN><<<grid, 256, smem, st>>>(x, (const __nv_bfloat16 *)w_hi, (const __nv_bfloat16 *)w_lo,
+                                                   (const float *)d->w.conv_b[0], (__nv_bfloat16 *)out_hi,
+                                                   (__nv_bfloat16 *)out_lo, batch, H, d->cfg.normalize, x3);
+    return SPIRAL_OK;
+}
+
+int conv0_mma_forward(const SpiralDisc *d, const float *x, int batch, const void *w_hi, const void *w_lo, void *out_hi,
+                      void *out_lo, int x3, cudaStream_t st)
+{
+    switch (d->cfg.in_channels) {
+    case 1: return conv0_launch<1>(d, x, batch, w_hi, w_lo, out_hi, out_lo, x3, st);
+    case 3: return conv0_launch<3>(d, x, batch, w_hi, w_lo, out_hi, out_lo, x3, st);
+    case 6: return conv0_launch<6>(d, x, batch, w_hi, w_lo, out_hi, out_lo, x3, st);
+    }
+    return spiral_set_error(SPIRAL_EUNSUPPORTED, "conv0_mma: in_channels must be 1, 3 or 6");
+}
+
+}  // namespace spiral

@@ -283,6 +283,7 @@ static size_t tc_layer_act_elems(const DiscPlan &pl, int l, int batch) { return 
 struct TcOffsets {
     size_t act_hi[SPIRAL_DISC_MAX_LAYERS], act_lo[SPIRAL_DISC_MAX_LAYERS];
     size_t w_hi[SPIRAL_DISC_MAX_LAYERS], w_lo[SPIRAL_DISC_MAX_LAYERS];
+    size_t w0_hi, w0_lo;      // layer 0: [64][K + pad] bf16 (disc_conv0_mma.cu)
     size_t bytes;
 };
 
@@ -290,6 +291,8 @@ static void tc_plan(const SpiralDisc *d, int batch, const DiscPlan &pl, TcOffset
 {
     // the tensor-core region follows the fp32 region; weights first (their offsets must not depend on batch)
     size_t off = 0;
+    o->w0_hi = off; off += disc_align(conv0_mma_pack_bytes(d->cfg.in_channels));
+    o->w0_lo = off; off += disc_align(conv0_mma_pack_bytes(d->cfg.in_channels));
     for (int l = 1; l < d->n_layers; l++) {
         const size_t wn = (size_t)25 * pl.Cin[l] * pl.Cout[l];
         o->w_hi[l] = off; off += disc_align(wn * 2);
@@ -350,6 +353,7 @@ int disc_tc_pack_weights(SpiralDisc *d, char *ws, cudaStream_t st)
     TcOffsets o;
     tc_plan(d, d->cfg.max_batch, pl, &o);
     char *tc = tc_region(d, ws);
+    if (conv0_mma_supported(d)) conv0_mma_pack(d, tc + o.w0_hi, tc + o.w0_lo, st);
     for (int l = 1; l < d->n_layers; l++) {
         weight_pack_kernel<<<148 * 4, 256, 0, st>>>((const float *)d->w.conv_w[l], (__nv_bfloat16 *)(tc + o.w_hi[l]),
                                                     (__nv_bfloat16 *)(tc + o.w_lo[l]), pl.Cin[l], pl.Cout[l]);
@@ -398,9 +402,12 @@ int disc_tc_forward(SpiralDisc *d, const float *x, int batch, float *logits, flo
     const int maxC = d->cfg.disc_dim << (d->n_layers - 1);
     const int x3 = d->cfg.precision == 1;
 
-    // layer 0 (K = 25 * C, C in {1,3,6}): direct fp32 convolution whose epilogue applies the leaky-ReLU
+    // layer 0 (K = 25 * C, C in {1,3,6}): mma.sync implicit GEMM gathered from a shared-memory input tile
+    // (disc_conv0_mma.cu; direct fp32 convolution when disc_dim != 64); the epilogue applies the leaky-ReLU
     // (no BN at layer 0) and writes the bf16 hi/lo pair layer 1 reads
-    int rc = disc_conv0(d, x, batch, nullptr, tc + o.act_hi[1], tc + o.act_lo[1], st);
+    int rc = conv0_mma_supported(d)
+                 ? conv0_mma_forward(d, x, batch, tc + o.w0_hi, tc + o.w0_lo, tc + o.act_hi[1], tc + o.act_lo[1], x3, st)
+                 : disc_conv0(d, x, batch, nullptr, tc + o.act_hi[1], tc + o.act_lo[1], st);
     if (rc != SPIRAL_OK) return rc;
     for (int l = 1; l < d->n_layers; l++) {
         const int H = pl.H[l], Cin = pl.Cin[l], Cout = pl.Cout[l], Ho = H / 2;

@@ -48,6 +48,7 @@ struct EnvParams {
     int dry_structure;           // 1: mapping structure of dry_brush.myb (fast path in update_states)
     int rng_table_len;           // entries of the rand_gauss table (stream positions)
     int expand_lanes;            // canvases per warp in expand_kernel (0 = choose from the batch size)
+    int expand_sort;             // 1: sort canvases by predicted chain length before expansion
     double lin[64];
     double pressures[8];
     double sizes[8];
