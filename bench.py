@@ -199,6 +199,8 @@ def run_ours(args):
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+        os.environ["NCCL_DEBUG"] = "WARN"          # keep stdout to the one JSON line (NCCL prints its version there)
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -337,7 +339,9 @@ def run_ours(args):
                     a2c=dict(achieved=2.0 * dlogits_bytes / (t_a2c * 1e-3) / 1e9, unit="GB/s",
                              frac=2.0 * dlogits_bytes / (t_a2c * 1e-3) / 1e9 / peak, ms=t_a2c),
                     disc=dict(ms=t_disc, tflops=340.25e6 * B / (t_disc * 1e-3) / 1e12, precision=args.disc_precision))
-        launches_per_episode = 1 + 2 * T + (1 + 5 * 2 + 1 + 1) + 3
+        # reset + T x (expand [+ plan + scatter when the work-sorted schedule is on] + composite)
+        # + D forward (conv0, 5 x conv_tc, 5 x bn_finalize, 4 x act_split, dense_sigmoid) + A2C (gae, row, final)
+        launches_per_episode = 1 + (4 if B >= 32768 else 2) * T + (1 + 5 + 5 + 4 + 1) + 3
         footprint = (env.canvas.numel() * 2 + env.obs.numel() * 4 + env.dab_scratch.numel() * 4 + 2 * dlogits_bytes
                      + disc.workspace.numel()) / 2 ** 20
         out = dict(metric="env-steps/sec (render+D reward+A2C) on 64x64 canvases", value=value, unit="env-steps/s",
