@@ -240,6 +240,19 @@ int spiral_conv_dgrad(const float *dy_dev, const float *w_dev, float *dx_dev, in
 int spiral_conv_wgrad(const float *x_dev, const float *dy_dev, float *dw_dev, int32_t B, int32_t H,
                       int32_t Cin, int32_t Cout, int32_t precision, void *workspace_dev, void *stream);
 
+/* ------------------------------------------------------------------ */
+/* Categorical sampling for the action heads (K4)                       */
+/* replaces: models/policy.py:364-368 categorical_sample                */
+/*           (tf.multinomial(logits - max, 1)), one call per head per   */
+/*           env step (policy.py:302-303)                               */
+/* ------------------------------------------------------------------ */
+/* logits f32[rows, n] -> out_idx i32[rows] ~ softmax(logits).  Gumbel-max over Philox4x32-10
+ * uniforms: key = seed, counter = (class / 4, row, offset); a (seed, offset) pair must not be reused. */
+int spiral_categorical_sample(const float *logits_dev, int32_t rows, int32_t n, uint64_t seed,
+                              uint64_t offset, int32_t *out_idx_dev, void *stream);
+/* test hook: one Philox4x32-10 block; ctr_key6 is a HOST array {c0,c1,c2,c3,k0,k1} */
+int spiral_debug_philox(const uint32_t *ctr_key6_host, uint32_t *out4_dev, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -91,6 +91,26 @@ class _LocationHead(nn.Module):
         return self.out(x).flatten(1)
 
 
+def categorical_sample(logits, generator=None, owner=None):
+    """policy.py:364-368 (``tf.multinomial(logits - max, 1)``) on the GPU: K4, Gumbel-max over
+    Philox4x32-10 keyed by the generator's seed; every call advances a per-owner offset so a
+    (seed, offset) pair is never reused.  logits f32[R,N] CUDA -> int32[R]."""
+    import ctypes as C
+
+    from .. import _native as N
+    if not logits.is_cuda:
+        raise RuntimeError("categorical_sample needs CUDA logits (there is no CPU fallback)")
+    lg = logits.to(torch.float32).contiguous()
+    seed = int(generator.initial_seed()) if generator is not None else int(torch.initial_seed())
+    holder = owner if owner is not None else categorical_sample
+    off = getattr(holder, "_sample_offset", 0)
+    setattr(holder, "_sample_offset", off + 1)
+    out = torch.empty((lg.shape[0],), dtype=torch.int32, device=lg.device)
+    N.check(N.lib().spiral_categorical_sample(N.ptr(lg), lg.shape[0], lg.shape[1], C.c_uint64(seed & (2 ** 64 - 1)),
+                                              C.c_uint64(off), N.ptr(out), N.stream_ptr()), "spiral_categorical_sample")
+    return out
+
+
 class Policy(nn.Module):
     def __init__(self, args, env, scope_name="global", image_shape=None, action_sizes=None, data_format="channels_last"):
         super().__init__()
@@ -175,8 +195,7 @@ class Policy(nn.Module):
             if samples is not None and name in samples:
                 s = samples[name].reshape(B * T).long()
             else:
-                s = torch.multinomial(torch.softmax(logit - logit.max(1, keepdim=True).values, -1), 1,
-                                      generator=generator).squeeze(1)
+                s = categorical_sample(logit.detach(), generator, self).long()
             out_samples[name] = s.view(B, T)
             if idx < len(self.acs) - 1:
                 emb = self.sample_mlp[name](s.view(B, T, 1).to(z.dtype))

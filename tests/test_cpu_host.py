@@ -201,3 +201,25 @@ def test_gloo_world2_allreduce_and_sharding(tmp_path):
                          capture_output=True, text=True, env=env, timeout=240)
     assert out.returncode == 0, out.stdout + out.stderr
     assert out.stdout.count("ok") == 2
+
+
+def test_philox_oracle_matches_random123_known_answers():
+    """Pins oracle/sample_oracle.py's Philox4x32-10 (the RNG behind the K4 sampler) to Random123's KAT file."""
+    from oracle import sample_oracle as so
+    for ctr, key, want in (([0] * 4, [0] * 2, [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]),
+                           ([0xffffffff] * 4, [0xffffffff] * 2, [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]),
+                           ([0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344], [0xa4093822, 0x299f31d0],
+                            [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1])):
+        got = so.philox4x32_10(np.array([ctr], np.uint32), np.array([key], np.uint32))[0]
+        assert [int(v) for v in got] == want
+
+
+def test_sampler_oracle_distribution_is_softmax():
+    from oracle import sample_oracle as so
+    base = np.array([0.3, -1.2, 2.0, 0.0], np.float32)
+    rows = 40000
+    idx = so.categorical_sample(np.tile(base, (rows, 1)), seed=5, offset=1)
+    freq = np.bincount(idx, minlength=4) / rows
+    p = np.exp(base - base.max())
+    p /= p.sum()
+    assert rows * ((freq - p) ** 2 / p).sum() < 16.3          # chi-square, 3 dof, 99.9 %
