@@ -23,7 +23,7 @@ cudaError_t launch_expand(const EnvParams &P, const int32_t *actions, float *bs,
                           int32_t *dab_count, int32_t *status, const float *gauss_tab, int32_t *plan_scratch,
                           cudaStream_t st);
 cudaError_t launch_composite(const EnvParams &P, uint16_t *canvas, const float *dabs, const int32_t *dab_count,
-                             const uint16_t *dither, float *obs, cudaStream_t st);
+                             const uint16_t *dither, float *obs, int32_t *work_counter, cudaStream_t st);
 cudaError_t launch_debug_dabs(const EnvParams &P, const float *dabs, const int32_t *dab_count, float *out,
                               int32_t *out_count, cudaStream_t st);
 cudaError_t launch_l2_reward(const float *obs, const float *target, float *reward, int batch, int n, cudaStream_t st);
@@ -131,6 +131,9 @@ static void rng_seed_block(long seed, double *out10)
 }
 
 // ------------------------------------------------------------------------------------------
+// d_plan: i32 [64] work counters | i32 [512] plan histogram + cursors | i32 [B] permutation | u8 [B] keys
+constexpr size_t kPlanHeader = 64 + 512;
+
 struct SpiralEnv {
     EnvParams P;
     int device;
@@ -302,7 +305,7 @@ extern "C" int spiral_env_create(const SpiralEnvCfg *cfg, SpiralEnv **out)
     if (e == cudaSuccess)
         e = cudaMemcpy(env->d_dither, cfg->dither_table, sizeof(cfg->dither_table), cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMalloc(&env->d_gauss, sizeof(float) * (size_t)cfg->rng_table_len);
-    if (e == cudaSuccess) e = cudaMalloc(&env->d_plan, sizeof(int32_t) * (512 + (size_t)cfg->batch) + (size_t)cfg->batch + 16);
+    if (e == cudaSuccess) e = cudaMalloc(&env->d_plan, sizeof(int32_t) * (kPlanHeader + (size_t)cfg->batch) + (size_t)cfg->batch + 16);
     if (e == cudaSuccess) {
         float *g = new float[(size_t)cfg->rng_table_len];
         rng_gauss_table(1000, cfg->rng_table_len, g);
@@ -344,7 +347,7 @@ extern "C" int spiral_env_expand(SpiralEnv *env, const int32_t *actions, float *
                                  int32_t *dab_count, int32_t *status, void *stream)
 {
     REQUIRE(env); REQUIRE(actions); REQUIRE(bs); REQUIRE(es); REQUIRE(dabs); REQUIRE(dab_count); REQUIRE(status);
-    const cudaError_t e = launch_expand(env->P, actions, bs, es, dabs, dab_count, status, env->d_gauss, env->d_plan, (cudaStream_t)stream);
+    const cudaError_t e = launch_expand(env->P, actions, bs, es, dabs, dab_count, status, env->d_gauss, env->d_plan + 64, (cudaStream_t)stream);
     return e == cudaSuccess ? SPIRAL_OK : spiral_cuda_error(e, "spiral_env_expand");
 }
 
@@ -352,7 +355,7 @@ extern "C" int spiral_env_composite(SpiralEnv *env, uint16_t *canvas, const floa
                                     float *obs, void *stream)
 {
     REQUIRE(env); REQUIRE(canvas); REQUIRE(dabs); REQUIRE(dab_count); REQUIRE(obs);
-    const cudaError_t e = launch_composite(env->P, canvas, dabs, dab_count, env->d_dither, obs, (cudaStream_t)stream);
+    const cudaError_t e = launch_composite(env->P, canvas, dabs, dab_count, env->d_dither, obs, env->d_plan, (cudaStream_t)stream);
     return e == cudaSuccess ? SPIRAL_OK : spiral_cuda_error(e, "spiral_env_composite");
 }
 

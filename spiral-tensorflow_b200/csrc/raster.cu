@@ -746,7 +746,7 @@ template <int C>
 __global__ void __launch_bounds__(32 * kCompWarps)
 composite_kernel(const __grid_constant__ EnvParams P, uint16_t *__restrict__ canvas,
                  const float *__restrict__ dabs, const int32_t *__restrict__ dab_count,
-                 const uint16_t *__restrict__ dither, float *__restrict__ obs)
+                 const uint16_t *__restrict__ dither, float *__restrict__ obs, int32_t *__restrict__ work_counter)
 {
     __shared__ SharedDab s_dab[kCompWarps][32];
     __shared__ uint16_t s_pair[kCompWarps][kDense];     // owner dab << 8 | (yp - y0) << 4 | (xp - x0)
@@ -754,10 +754,15 @@ composite_kernel(const __grid_constant__ EnvParams P, uint16_t *__restrict__ can
     __shared__ int s_off[kCompWarps][33];               // first pair of each dab of the round
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
-    const int b = blockIdx.x * kCompWarps + warp;
+    // persistent warps: canvases differ by 1000x in work (0 .. ~1750 dabs), so every warp pulls the next
+    // canvas from a global counter until the batch is drained instead of owning a fixed one
+    for (;;) {
+    int b = 0;
+    if (lane == 0) b = atomicAdd(work_counter, 1);
+    b = __shfl_sync(0xffffffffu, b, 0);
     if (b >= P.B) return;
     const int n_dabs = dab_count[2 * b];
-    if (n_dabs == 0) return;                         // canvas and observation unchanged
+    if (n_dabs == 0) continue;                       // canvas and observation unchanged
     const int color_idx = dab_count[2 * b + 1];
     const uint32_t col_r = P.colors[color_idx][0], col_g = P.colors[color_idx][1],
                    col_b = P.colors[color_idx][2];
@@ -918,7 +923,7 @@ composite_kernel(const __grid_constant__ EnvParams P, uint16_t *__restrict__ can
         ymin = min(ymin, __shfl_xor_sync(0xffffffffu, ymin, off));
         ymax = max(ymax, __shfl_xor_sync(0xffffffffu, ymax, off));
     }
-    if (ymax < ymin) return;
+    if (ymax < ymin) continue;
     const uint4 *src = reinterpret_cast<const uint4 *>(tile);        // uint4 = 2 RGBA pixels
     float *ob = obs + (size_t)b * kTile * kTile * C;
 #pragma unroll 4
@@ -952,6 +957,8 @@ composite_kernel(const __grid_constant__ EnvParams P, uint16_t *__restrict__ can
             o2[2] = make_float2((float)g1, (float)b1);
         }
     }
+    __syncwarp();
+    }   // next canvas
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1073,9 +1080,11 @@ cudaError_t launch_expand(const EnvParams &P, const int32_t *actions, float *bs,
 }
 cudaError_t launch_composite(const EnvParams &P, uint16_t *canvas, const float *dabs,
                              const int32_t *dab_count, const uint16_t *dither, float *obs,
-                             cudaStream_t st)
+                             int32_t *work_counter, cudaStream_t st)
 {
-    const int blocks = (P.B + kCompWarps - 1) / kCompWarps;
+    int blocks = (P.B + kCompWarps - 1) / kCompWarps;
+    if (blocks > 148 * 32 / kCompWarps) blocks = 148 * 32 / kCompWarps;       // one resident warp per slot
+    cudaMemsetAsync(work_counter, 0, sizeof(int32_t), st);
     static bool carveout = false;
     if (!carveout) {      // 32 resident warps need 32 x 5.8 KB of shared memory: ask for the large carve-out
         cudaFuncSetAttribute(composite_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
@@ -1083,9 +1092,9 @@ cudaError_t launch_composite(const EnvParams &P, uint16_t *canvas, const float *
         carveout = true;
     }
     if (P.C == 1)
-        composite_kernel<1><<<blocks, 32 * kCompWarps, 0, st>>>(P, canvas, dabs, dab_count, dither, obs);
+        composite_kernel<1><<<blocks, 32 * kCompWarps, 0, st>>>(P, canvas, dabs, dab_count, dither, obs, work_counter);
     else
-        composite_kernel<3><<<blocks, 32 * kCompWarps, 0, st>>>(P, canvas, dabs, dab_count, dither, obs);
+        composite_kernel<3><<<blocks, 32 * kCompWarps, 0, st>>>(P, canvas, dabs, dab_count, dither, obs, work_counter);
     return cudaGetLastError();
 }
 cudaError_t launch_debug_dabs(const EnvParams &P, const float *dabs, const int32_t *dab_count,
