@@ -214,6 +214,9 @@ extern "C" int spiral_env_create(const SpiralEnvCfg *cfg, SpiralEnv **out)
         if (P.expand_lanes < 0 || P.expand_lanes > 32) P.expand_lanes = 0;
         const char *so = getenv("SPIRAL_EXPAND_SORT");       // 0 disables the work-sorted schedule (profiling)
         P.expand_sort = so ? (atoi(so) != 0) : 1;
+        const char *sd = getenv("SPIRAL_EXPAND_SOLO_DIV");
+        P.expand_solo_div = sd ? atoi(sd) : 128;
+        if (P.expand_solo_div < 1) P.expand_solo_div = 128;
     }
     for (int s = 0; s < SPIRAL_DYN_COUNT; s++) {
         MapDev &m = P.dyn[s];

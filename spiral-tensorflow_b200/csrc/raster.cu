@@ -232,14 +232,23 @@ __global__ void __launch_bounds__(kExpandThreads)
 expand_kernel(const __grid_constant__ EnvParams P, const int32_t *__restrict__ actions,
               float *__restrict__ brush_state, double *__restrict__ env_state,
               float *__restrict__ dabs, int32_t *__restrict__ dab_count, int32_t *__restrict__ status,
-              const float *__restrict__ gauss_tab, int lanes, const int32_t *__restrict__ perm)
+              const float *__restrict__ gauss_tab, int lanes, const int32_t *__restrict__ perm, int n_solo)
 {
     // `lanes` canvases per warp (1..32, host-chosen): the brush state machine is a latency-bound
     // serial chain, so with few canvases it pays to give each its own warp (no intra-warp divergence
     // or load imbalance, more resident warps per SM to hide latency) and leave the other lanes idle.
     const int tid = threadIdx.x;
-    if (tid >= lanes) return;
-    const int slot = blockIdx.x * lanes + tid;
+    // slots are in order of decreasing predicted chain length (perm): the first n_solo canvases -- the ones
+    // that decide the kernel's duration -- get a warp each (no divergence against shorter neighbours, lowest
+    // per-iteration latency), the rest are packed `lanes` per warp next to canvases of similar length
+    int slot;
+    if ((int)blockIdx.x < n_solo) {
+        if (tid != 0) return;
+        slot = blockIdx.x;
+    } else {
+        if (tid >= lanes) return;
+        slot = n_solo + ((int)blockIdx.x - n_solo) * lanes + tid;
+    }
     if (slot >= P.B) return;
     // canvases sorted by predicted chain length (plan_kernel / scatter_kernel): the lanes of a warp walk
     // chains of similar length instead of idling behind the longest one
@@ -1063,7 +1072,8 @@ cudaError_t launch_expand(const EnvParams &P, const int32_t *actions, float *bs,
     while (lanes & (lanes - 1)) lanes &= lanes - 1;      // round down to a power of two
     if (P.expand_lanes > 0) lanes = P.expand_lanes;
     const int32_t *perm = nullptr;
-    if (lanes == 32 && P.B >= 32768 && plan_scratch && P.expand_sort) {   // measured: +3 % at 64k canvases, none below
+    int n_solo = 0;
+    if (lanes > 1 && plan_scratch && P.expand_sort) {
         // plan_scratch: i32 [512] histogram + cursors | i32 [B] permutation | u8 [B] keys
         int32_t *hist = plan_scratch;
         int32_t *pm = plan_scratch + 2 * kPlanBuckets;
@@ -1073,9 +1083,13 @@ cudaError_t launch_expand(const EnvParams &P, const int32_t *actions, float *bs,
         plan_kernel<<<pb, 256, 0, st>>>(P, actions, es, key, hist);
         scatter_kernel<<<pb, 256, 0, st>>>(P.B, key, hist, pm);
         perm = pm;
+        // measured (B200): 128 solo warps at B = 16384, 256 at B = 65536; more of them exceed the 16 resident
+        // 128-register warps per SM and push the packed warps into a second wave
+        n_solo = P.B / P.expand_solo_div;
+        if (n_solo > 256) n_solo = 256;
     }
-    const int blocks = (P.B + lanes - 1) / lanes;
-    expand_kernel<<<blocks, kExpandThreads, 0, st>>>(P, actions, bs, es, dabs, dab_count, status, gauss_tab, lanes, perm);
+    const int blocks = n_solo + (P.B - n_solo + lanes - 1) / lanes;
+    expand_kernel<<<blocks, kExpandThreads, 0, st>>>(P, actions, bs, es, dabs, dab_count, status, gauss_tab, lanes, perm, n_solo);
     return cudaGetLastError();
 }
 cudaError_t launch_composite(const EnvParams &P, uint16_t *canvas, const float *dabs,

@@ -49,6 +49,7 @@ struct EnvParams {
     int rng_table_len;           // entries of the rand_gauss table (stream positions)
     int expand_lanes;            // canvases per warp in expand_kernel (0 = choose from the batch size)
     int expand_sort;             // 1: sort canvases by predicted chain length before expansion
+    int expand_solo_div;         // the B / expand_solo_div longest canvases get a warp each
     double lin[64];
     double pressures[8];
     double sizes[8];
