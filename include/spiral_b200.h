@@ -163,7 +163,7 @@ int spiral_debug_detmath(const double *x_dev, double *exp_out_dev, double *log_o
  * adv_out, ret_out: f32[B,T] (rl_utils.py:32-40 with bootstrap r = 0).
  * out_scalars_dev f32[4] = {pi_loss, vf_loss, entropy, total} exactly as agent.py:172-194 sums them.
  * dlogits_dev[k] f32[B,T,N_k] and dvf_dev f32[B,T] = d total / d input (may be NULL to skip).
- * partial_dev: scratch f32[B*T*4]. */
+ * partial_dev: scratch f32[B*T*4 + 2048], 16-byte aligned. */
 int spiral_a2c_loss(const float *const *logits_dev, const int32_t *head_sizes, int32_t n_heads,
                     const int32_t *actions_dev, const float *rewards_dev, const float *values_dev,
                     const float *vf_dev, int32_t batch, int32_t T, double gamma, double lambda_,

@@ -52,6 +52,10 @@ __global__ void gae_kernel(const float *__restrict__ rewards, const float *__res
 }
 
 constexpr int kRowThreads = 128;
+constexpr int kRegVec = 8;          // float4 per thread held in registers: heads up to 4096 classes
+
+// e^x for x <= 0 via ex2.approx: relative error ~1e-6 at |x| = 20, far inside the 2e-5 the parity tests hold
+__device__ __forceinline__ float fast_exp(float x) { return __expf(x); }
 
 __device__ __forceinline__ float warp_max(float v)
 {
@@ -105,6 +109,68 @@ a2c_row_kernel(const __grid_constant__ A2CHeads H, const int32_t *__restrict__ a
         float *dx = H.dlogits[k] ? H.dlogits[k] + (size_t)row * n : nullptr;
         const int act = actions[(size_t)row * H.K + k];
         const bool vec = (n & 3) == 0;
+
+        if (vec && n / 4 <= kRowThreads * kRegVec) {
+            // register path (every head of the rgb64 / mnist workloads): the row is read ONCE and kept in registers
+            const float4 *x4 = reinterpret_cast<const float4 *>(x);
+            const int n4 = n / 4;
+            float4 xv[kRegVec];
+            float m = -INFINITY;
+#pragma unroll
+            for (int c = 0; c < kRegVec; c++) {
+                const int i = tid + c * kRowThreads;
+                if (i < n4) {
+                    xv[c] = x4[i];
+                    m = fmaxf(fmaxf(m, fmaxf(xv[c].x, xv[c].y)), fmaxf(xv[c].z, xv[c].w));
+                }
+            }
+            m = block_max(m, s_red);
+            float S = 0.0f, D = 0.0f;
+#pragma unroll
+            for (int c = 0; c < kRegVec; c++) {
+                const int i = tid + c * kRowThreads;
+                if (i < n4) {
+                    xv[c].x -= m; xv[c].y -= m; xv[c].z -= m; xv[c].w -= m;
+                    const float e0 = fast_exp(xv[c].x), e1 = fast_exp(xv[c].y), e2 = fast_exp(xv[c].z), e3 = fast_exp(xv[c].w);
+                    S += (e0 + e1) + (e2 + e3);
+                    D += (e0 * xv[c].x + e1 * xv[c].y) + (e2 * xv[c].z + e3 * xv[c].w);
+                }
+            }
+            S = block_sum(S, s_red);
+            D = block_sum(D, s_red);
+            const float logS = logf(S);
+            const float invS = 1.0f / S;
+            const float ent = logS - D * invS;
+            const float logp_a = x[act] - m - logS;
+            pi_acc += -(logp_a * a);
+            ent_acc += ent;
+            if (dx) {
+                float4 *d4 = reinterpret_cast<float4 *>(dx);
+                const float c0 = ent - logS;                   // logp_j + ent = z_j + (ent - logS)
+#pragma unroll
+                for (int c = 0; c < kRegVec; c++) {
+                    const int i = tid + c * kRowThreads;
+                    if (i < n4) {
+                        float4 g;
+                        float p;
+                        // the exponential is 2 instructions (ex2.approx): cheaper to redo than to keep 32 registers
+                        p = fast_exp(xv[c].x) * invS; g.x = a * p + entropy_coeff * p * (xv[c].x + c0);
+                        p = fast_exp(xv[c].y) * invS; g.y = a * p + entropy_coeff * p * (xv[c].y + c0);
+                        p = fast_exp(xv[c].z) * invS; g.z = a * p + entropy_coeff * p * (xv[c].z + c0);
+                        p = fast_exp(xv[c].w) * invS; g.w = a * p + entropy_coeff * p * (xv[c].w + c0);
+                        const int j = i * 4;
+                        if (act >= j && act < j + 4) {
+                            if (act == j) g.x -= a;
+                            else if (act == j + 1) g.y -= a;
+                            else if (act == j + 2) g.z -= a;
+                            else g.w -= a;
+                        }
+                        d4[i] = g;
+                    }
+                }
+            }
+            continue;
+        }
 
         // sweep 1: max
         float m = -INFINITY;
@@ -190,19 +256,43 @@ a2c_row_kernel(const __grid_constant__ A2CHeads H, const int32_t *__restrict__ a
     }
 }
 
+// stage 1: kFinalBlocks CTAs reduce contiguous chunks of the per-row partials (float64, fixed order)
+constexpr int kFinalBlocks = 256;
+
 __global__ void __launch_bounds__(256)
-a2c_final_kernel(const float *__restrict__ partial, int rows, int K, float entropy_coeff,
-                 float *__restrict__ out)
+a2c_partial_kernel(const float *__restrict__ partial, int rows, double *__restrict__ scratch)
 {
     __shared__ double s[3][256];
+    const int per = (rows + kFinalBlocks - 1) / kFinalBlocks;
+    const int r0 = blockIdx.x * per, r1 = min(rows, r0 + per);
     double pi = 0.0, en = 0.0, vf = 0.0;
-    for (int i = threadIdx.x; i < rows; i += 256) {
+    for (int i = r0 + threadIdx.x; i < r1; i += 256) {
         const float4 p = reinterpret_cast<const float4 *>(partial)[i];
         pi += (double)p.x;
         en += (double)p.y;
         vf += (double)p.z;
     }
     s[0][threadIdx.x] = pi; s[1][threadIdx.x] = en; s[2][threadIdx.x] = vf;
+    __syncthreads();
+    for (int o = 128; o; o >>= 1) {
+        if (threadIdx.x < o) {
+            s[0][threadIdx.x] += s[0][threadIdx.x + o];
+            s[1][threadIdx.x] += s[1][threadIdx.x + o];
+            s[2][threadIdx.x] += s[2][threadIdx.x + o];
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x < 3) scratch[blockIdx.x * 4 + threadIdx.x] = s[threadIdx.x][0];
+}
+
+// stage 2: one CTA, fixed-order float64 reduction of the kFinalBlocks chunk sums -> 4 scalars
+__global__ void __launch_bounds__(256)
+a2c_final_kernel(const double *__restrict__ scratch, int K, float entropy_coeff, float *__restrict__ out)
+{
+    __shared__ double s[3][256];
+    s[0][threadIdx.x] = scratch[threadIdx.x * 4 + 0];
+    s[1][threadIdx.x] = scratch[threadIdx.x * 4 + 1];
+    s[2][threadIdx.x] = scratch[threadIdx.x * 4 + 2];
     __syncthreads();
     for (int o = 128; o; o >>= 1) {
         if (threadIdx.x < o) {
@@ -252,7 +342,10 @@ extern "C" int spiral_a2c_loss(const float *const *logits, const int32_t *head_s
     const double g = gamma, gl = gamma * lambda_;     // agent.py:340-341: gamma=0.99, lambda_=1.0
     gae_kernel<<<(batch + 127) / 128, 128, 0, st>>>(rewards, values, adv_out, ret_out, batch, T, g, gl);
     a2c_row_kernel<<<batch * T, kRowThreads, 0, st>>>(H, actions, adv_out, ret_out, vf, entropy_coeff, dvf, partial);
-    a2c_final_kernel<<<1, 256, 0, st>>>(partial, batch * T, n_heads, entropy_coeff, out_scalars);
+    // scratch for the two-stage reduction: the 2048 floats that follow the per-row partials
+    double *scratch = reinterpret_cast<double *>(partial + (size_t)batch * T * 4);
+    a2c_partial_kernel<<<kFinalBlocks, 256, 0, st>>>(partial, batch * T, scratch);
+    a2c_final_kernel<<<1, 256, 0, st>>>(scratch, n_heads, entropy_coeff, out_scalars);
     const cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? SPIRAL_OK : spiral_cuda_error(e, "spiral_a2c_loss");
 }

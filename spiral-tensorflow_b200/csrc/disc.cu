@@ -216,11 +216,40 @@ conv_simt_kernel(const float *__restrict__ in, const float *__restrict__ in_scal
     }
 }
 
-// per-channel reduction of the partials in a fixed order (float64: deterministic, no atomics), then
-// the affine the consumer applies on load:  scale = gamma * rsqrt(var + eps), shift = beta - mean * scale
-// CTA = 32 channels x 8 partial-groups; loads are coalesced float2 (sum, sum of squares).
+// Batch-norm statistics in two deterministic float64 stages (no atomics):
+//   bn_reduce_kernel    kBnSlices x (Cout / 32) CTAs each sum a contiguous slice of the per-tile partials
+//   bn_finalize_kernel  (Cout / 32) CTAs sum the slices in a fixed order, then emit the affine the consumer
+//                       applies on load:  scale = gamma * rsqrt(var + eps), shift = beta - mean * scale
+// Loads are coalesced float2 (sum, sum of squares); CTA = 32 channels x 8 partial-groups.
+constexpr int kBnSlices = 64;
+
 __global__ void __launch_bounds__(256)
-bn_finalize_kernel(const float *__restrict__ partial, int n_part, int Cout, double count,
+bn_reduce_kernel(const float *__restrict__ partial, int n_part, int Cout, double *__restrict__ sliced)
+{
+    __shared__ double s_s[8][32], s_q[8][32];
+    const int cl = threadIdx.x & 31, g = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + cl;
+    const int per = (n_part + kBnSlices - 1) / kBnSlices;
+    const int i0 = blockIdx.y * per, i1 = min(n_part, i0 + per);
+    double s = 0.0, q = 0.0;
+    if (c < Cout) {
+        for (int i = i0 + g; i < i1; i += 8) {
+            const float2 v = *reinterpret_cast<const float2 *>(partial + ((size_t)i * Cout + c) * 2);
+            s += (double)v.x;
+            q += (double)v.y;
+        }
+    }
+    s_s[g][cl] = s;
+    s_q[g][cl] = q;
+    __syncthreads();
+    if (g != 0 || c >= Cout) return;
+    for (int k = 1; k < 8; k++) { s += s_s[k][cl]; q += s_q[k][cl]; }
+    sliced[((size_t)blockIdx.y * Cout + c) * 2] = s;
+    sliced[((size_t)blockIdx.y * Cout + c) * 2 + 1] = q;
+}
+
+__global__ void __launch_bounds__(256)
+bn_finalize_kernel(const double *__restrict__ sliced, int Cout, double count,
                    const float *__restrict__ gamma, const float *__restrict__ beta,
                    float eps, float *__restrict__ scale, float *__restrict__ shift,
                    float *__restrict__ stats, int stats_stride)
@@ -230,10 +259,9 @@ bn_finalize_kernel(const float *__restrict__ partial, int n_part, int Cout, doub
     const int c = blockIdx.x * 32 + cl;
     double s = 0.0, q = 0.0;
     if (c < Cout) {
-        for (int i = g; i < n_part; i += 8) {
-            const float2 v = *reinterpret_cast<const float2 *>(partial + ((size_t)i * Cout + c) * 2);
-            s += (double)v.x;
-            q += (double)v.y;
+        for (int i = g; i < kBnSlices; i += 8) {
+            s += sliced[((size_t)i * Cout + c) * 2];
+            q += sliced[((size_t)i * Cout + c) * 2 + 1];
         }
     }
     s_s[g][cl] = s;
@@ -249,6 +277,21 @@ bn_finalize_kernel(const float *__restrict__ partial, int n_part, int Cout, doub
     scale[c] = sc;
     shift[c] = beta[c] - (float)mean * sc;
     if (stats) { stats[c] = (float)mean; stats[stats_stride + c] = (float)var; }
+}
+
+size_t bn_partial_bytes(int n_part, int Cout)
+{
+    // per-tile float partials, then the kBnSlices x Cout x 2 float64 slice sums
+    return disc_align((size_t)n_part * Cout * 2 * sizeof(float)) + disc_align((size_t)kBnSlices * Cout * 2 * sizeof(double));
+}
+
+void launch_bn_finalize(float *part, int n_part, int Cout, double count, const float *gamma, const float *beta, float eps,
+                        float *scale, float *shift, float *stats, int stats_stride, cudaStream_t st)
+{
+    double *sliced = reinterpret_cast<double *>(reinterpret_cast<char *>(part) + disc_align((size_t)n_part * Cout * 2 * sizeof(float)));
+    dim3 g1((Cout + 31) / 32, kBnSlices);
+    bn_reduce_kernel<<<g1, 256, 0, st>>>(part, n_part, Cout, sliced);
+    bn_finalize_kernel<<<(Cout + 31) / 32, 256, 0, st>>>(sliced, Cout, count, gamma, beta, eps, scale, shift, stats, stats_stride);
 }
 
 __global__ void fill_affine_kernel(float *scale, float *shift, int n, float sc, float sh)
@@ -298,7 +341,7 @@ void disc_plan(const SpiralDisc *d, int batch, DiscPlan *pl)
         pl->act_off[l] = off; off += disc_align((size_t)batch * Ho * Ho * Cout * sizeof(float));
         const int mtiles = (batch * Ho * Ho + 63) / 64;
         pl->mtiles[l] = mtiles;
-        pl->part_off[l] = off; off += disc_align((size_t)mtiles * Cout * 2 * sizeof(float));
+        pl->part_off[l] = off; off += bn_partial_bytes(mtiles, Cout);
         pl->scale_off[l] = off; off += disc_align((size_t)Cout * sizeof(float));
         pl->shift_off[l] = off; off += disc_align((size_t)Cout * sizeof(float));
         H = Ho; Cin = Cout;
@@ -353,10 +396,9 @@ int disc_forward_simt(SpiralDisc *d, const float *x, int batch, float *logits, f
                                                    out, bn ? part : nullptr, batch, H, Cin, Cout);
         }
         if (bn) {
-            bn_finalize_kernel<<<(Cout + 31) / 32, 256, 0, st>>>(part, pl.mtiles[l], Cout, (double)batch * Ho * Ho,
-                                                                    (const float *)W.bn_gamma[l], (const float *)W.bn_beta[l],
-                                                                    1e-3f, scale, shift,
-                                                                    bn_stats ? bn_stats + (size_t)l * 2 * maxC : nullptr, maxC);
+            launch_bn_finalize(part, pl.mtiles[l], Cout, (double)batch * Ho * Ho, (const float *)W.bn_gamma[l],
+                               (const float *)W.bn_beta[l], 1e-3f, scale, shift,
+                               bn_stats ? bn_stats + (size_t)l * 2 * maxC : nullptr, maxC, st);
         } else {
             fill_affine_kernel<<<(Cout + 127) / 128, 128, 0, st>>>(scale, shift, Cout, 1.0f, 0.0f);
         }

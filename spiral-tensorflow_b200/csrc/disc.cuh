@@ -29,9 +29,9 @@ size_t disc_align(size_t v);
 void disc_plan(const SpiralDisc *d, int batch, DiscPlan *pl);
 
 // kernels shared by both paths
-__global__ void bn_finalize_kernel(const float *partial, int n_part, int Cout, double count, const float *gamma,
-                                   const float *beta, float eps, float *scale, float *shift, float *stats,
-                                   int stats_stride);
+size_t bn_partial_bytes(int n_part, int Cout);
+void launch_bn_finalize(float *part, int n_part, int Cout, double count, const float *gamma, const float *beta, float eps,
+                        float *scale, float *shift, float *stats, int stats_stride, cudaStream_t st);
 __global__ void fill_affine_kernel(float *scale, float *shift, int n, float sc, float sh);
 __global__ void dense_sigmoid_kernel(const float *in, const float *in_scale, const float *in_shift, const float *w,
                                      const float *bias, float *logits, float *probs, int B, int C);

@@ -12,8 +12,9 @@
 // leaky-ReLU (no BN at layer 0), hi/lo split, staged through shared memory into the fully coalesced
 // bf16 NHWC pair layer 1's TMA reads.
 //
-// CTA = 8 warps = 8 output rows x 16 output pixels x 64 channels; warp = one row of 16 pixels (M = 16)
-// x all 64 channels (8 n-tiles), K padded to a multiple of 16 with zero weights.
+// CTA = one image, 8 warps, looping over its 8 tiles of 8 output rows x 16 output pixels x 64 channels (the
+// packed kernel is staged once per CTA); warp = one row of 16 pixels (M = 16) x all 64 channels (8 n-tiles),
+// K padded to a multiple of 16 with zero weights.
 #include "disc.cuh"
 
 #include <cuda_bf16.h>
@@ -23,6 +24,7 @@ namespace spiral {
 constexpr int kC0Tw = 16, kC0Th = 8;                    // output tile
 constexpr int kC0Iw = 2 * kC0Tw + 3, kC0Ih = 2 * kC0Th + 3;   // input tile 35 x 19
 constexpr int kC0Cout = 64;
+constexpr int kC0OutStride = 72;                       // bf16 per staged output pixel: conflict-free fragment stores
 
 __host__ __device__ constexpr int c0_kpad(int cin) { return (25 * cin + 15) / 16 * 16; }
 __host__ __device__ constexpr int c0_kstride(int cin) { return c0_kpad(cin) + 8; }   // bf16 per row; conflict-free
@@ -65,16 +67,14 @@ conv0_mma_kernel(const float *__restrict__ x, const __nv_bfloat16 *__restrict__ 
     uint16_t *s_ih = s_wl + kC0Cout * KS;                                  // [19][35][CIN]
     uint16_t *s_il = s_ih + ((NIN + 7) & ~7);
     int *s_koff = reinterpret_cast<int *>(s_il + ((NIN + 7) & ~7));        // [KP]
-    uint16_t *s_out = reinterpret_cast<uint16_t *>(s_koff + KP);           // [8 warps][2][16 px][64 ch]
+    uint16_t *s_out = reinterpret_cast<uint16_t *>(s_koff + KP);           // [8 warps][2][16 px][72]
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int Ho = H / 2;
     const int tiles_x = Ho / kC0Tw, tiles_y = Ho / kC0Th;
-    const int img = blockIdx.x / (tiles_x * tiles_y);
-    const int trem = blockIdx.x % (tiles_x * tiles_y);
-    const int oy0 = (trem / tiles_x) * kC0Th, ox0 = (trem % tiles_x) * kC0Tw;
+    const int img = blockIdx.x;
 
-    // ---- stage the packed kernel (16-byte copies), the k -> input-offset table and the input tile ----
+    // ---- once per CTA (= one image): the packed kernel (16-byte copies) and the k -> input-offset table ----
     {
         const uint4 *gh = reinterpret_cast<const uint4 *>(w_hi), *gl = reinterpret_cast<const uint4 *>(w_lo);
         uint4 *sh = reinterpret_cast<uint4 *>(s_wh), *sl = reinterpret_cast<uint4 *>(s_wl);
@@ -92,6 +92,15 @@ conv0_mma_kernel(const float *__restrict__ x, const __nv_bfloat16 *__restrict__ 
             }
             s_koff[k] = off;
         }
+    }
+    const int g = lane >> 2, t = lane & 3;
+    const int base0 = ((2 * warp) * kC0Iw + 2 * g) * CIN;              // pixel g
+    const int base1 = base0 + 16 * CIN;                                  // pixel g + 8
+#pragma unroll 1
+    for (int tile = 0; tile < tiles_x * tiles_y; tile++) {
+    const int oy0 = (tile / tiles_x) * kC0Th, ox0 = (tile % tiles_x) * kC0Tw;
+    __syncthreads();                                                     // previous tile's input is consumed
+    {
         const float *xi = x + (size_t)img * H * H * CIN;
         for (int i = tid; i < NIN; i += 256) {
             const int c = i % CIN, p = i / CIN;
@@ -110,9 +119,6 @@ conv0_mma_kernel(const float *__restrict__ x, const __nv_bfloat16 *__restrict__ 
     __syncthreads();
 
     // ---- main loop: warp = output row `warp` of the tile, 16 pixels x 64 channels ----
-    const int g = lane >> 2, t = lane & 3;
-    const int base0 = ((2 * warp) * kC0Iw + 2 * g) * CIN;              // pixel g
-    const int base1 = base0 + 16 * CIN;                                  // pixel g + 8
     float acc[8][4];
 #pragma unroll
     for (int nt = 0; nt < 8; nt++)
@@ -151,7 +157,7 @@ conv0_mma_kernel(const float *__restrict__ x, const __nv_bfloat16 *__restrict__ 
     }
 
     // ---- epilogue: + bias, leaky-ReLU, hi/lo split, staged so that the warp writes 2 KB contiguous ----
-    uint16_t *so_h = s_out + warp * (2 * 16 * kC0Cout), *so_l = so_h + 16 * kC0Cout;
+    uint16_t *so_h = s_out + warp * (2 * 16 * kC0OutStride), *so_l = so_h + 16 * kC0OutStride;
 #pragma unroll
     for (int nt = 0; nt < 8; nt++) {
         const int ch = nt * 8 + 2 * t;
@@ -165,19 +171,21 @@ conv0_mma_kernel(const float *__restrict__ x, const __nv_bfloat16 *__restrict__ 
             const __nv_bfloat16 l0 = __float2bfloat16_rn(v0 - __bfloat162float(h0));
             const __nv_bfloat16 l1 = __float2bfloat16_rn(v1 - __bfloat162float(h1));
             const int px = g + 8 * half;
-            *reinterpret_cast<uint32_t *>(so_h + px * kC0Cout + ch) = pack2(__bfloat16_as_ushort(h0), __bfloat16_as_ushort(h1));
-            *reinterpret_cast<uint32_t *>(so_l + px * kC0Cout + ch) = pack2(__bfloat16_as_ushort(l0), __bfloat16_as_ushort(l1));
+            *reinterpret_cast<uint32_t *>(so_h + px * kC0OutStride + ch) = pack2(__bfloat16_as_ushort(h0), __bfloat16_as_ushort(h1));
+            *reinterpret_cast<uint32_t *>(so_l + px * kC0OutStride + ch) = pack2(__bfloat16_as_ushort(l0), __bfloat16_as_ushort(l1));
         }
     }
     __syncwarp();
     const size_t opix = ((size_t)img * Ho + oy0 + warp) * Ho + ox0;        // 16 consecutive pixels
     uint4 *gh = reinterpret_cast<uint4 *>(out_hi + opix * kC0Cout), *gl = reinterpret_cast<uint4 *>(out_lo + opix * kC0Cout);
-    const uint4 *sh = reinterpret_cast<const uint4 *>(so_h), *sl = reinterpret_cast<const uint4 *>(so_l);
 #pragma unroll
     for (int i = 0; i < 4; i++) {                                          // 16 px * 128 B = 128 x 16 B
-        gh[lane + 32 * i] = sh[lane + 32 * i];
-        gl[lane + 32 * i] = sl[lane + 32 * i];
+        const int q = lane + 32 * i, px = q >> 3, chunk = q & 7;
+        gh[q] = *reinterpret_cast<const uint4 *>(so_h + px * kC0OutStride + chunk * 8);
+        gl[q] = *reinterpret_cast<const uint4 *>(so_l + px * kC0OutStride + chunk * 8);
     }
+    __syncwarp();
+    }   // next tile
 }
 
 size_t conv0_mma_pack_bytes(int Cin) { return (size_t)kC0Cout * c0_kstride(Cin) * 2; }
@@ -200,7 +208,7 @@ static int conv0_launch(const SpiralDisc *d, const float *x, int batch, const vo
 {
     constexpr int KP = c0_kpad(CIN), KS = c0_kstride(CIN), NIN = kC0Ih * kC0Iw * CIN;
     constexpr size_t smem = (size_t)2 * kC0Cout * KS * 2 + (size_t)2 * ((NIN + 7) & ~7) * 2 + (size_t)KP * 4 +
-                            (size_t)8 * 2 * 16 * kC0Cout * 2;
+                            (size_t)8 * 2 * 16 * kC0OutStride * 2;
     static bool attr = false;
     if (!attr) {
         const cudaError_t e = cudaFuncSetAttribute(conv0_mma_kernel<CIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -208,7 +216,7 @@ static int conv0_launch(const SpiralDisc *d, const float *x, int batch, const vo
         attr = true;
     }
     const int H = d->cfg.screen_size, Ho = H / 2;
-    const int grid = batch * (Ho / kC0Tw) * (Ho / kC0Th);
+    const int grid = batch;                         // one CTA per image: the kernel is staged once for its 8 tiles
     conv0_mma_kernel<CIN><<<grid, 256, smem, st>>>(x, (const __nv_bfloat16 *)w_hi, (const __nv_bfloat16 *)w_lo,
                                                    (const float *)d->w.conv_b[0], (__nv_bfloat16 *)out_hi,
                                                    (__nv_bfloat16 *)out_lo, batch, H, d->cfg.normalize, x3);

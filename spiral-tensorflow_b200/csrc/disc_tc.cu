@@ -436,9 +436,9 @@ int disc_tc_forward(SpiralDisc *d, const float *x, int batch, float *logits, flo
                                                             (float *)(ws + pl.act_off[l]), bn ? part : nullptr);
         float *scale = (float *)(ws + pl.scale_off[l]), *shift = (float *)(ws + pl.shift_off[l]);
         if (bn) {
-            bn_finalize_kernel<<<(Cout + 31) / 32, 256, 0, st>>>(part, mtiles, Cout, (double)batch * Ho * Ho,
-                                                                    (const float *)W.bn_gamma[l], (const float *)W.bn_beta[l], 1e-3f,
-                                                                    scale, shift, bn_stats ? bn_stats + (size_t)l * 2 * maxC : nullptr, maxC);
+            launch_bn_finalize(part, mtiles, Cout, (double)batch * Ho * Ho, (const float *)W.bn_gamma[l],
+                               (const float *)W.bn_beta[l], 1e-3f, scale, shift,
+                               bn_stats ? bn_stats + (size_t)l * 2 * maxC : nullptr, maxC, st);
         } else {
             fill_affine_kernel<<<(Cout + 127) / 128, 128, 0, st>>>(scale, shift, Cout, 1.0f, 0.0f);
         }

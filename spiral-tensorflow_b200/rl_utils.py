@@ -64,7 +64,7 @@ def a2c_loss(logits, actions, rewards, values, vf, gamma=0.99, lambda_=1.0, entr
         res.dlogits = [torch.empty_like(l) for l in logits] if want_grads else None
         res.dvf = torch.empty((B, T), dtype=torch.float32, device=dev) if want_grads else None
         res.pi_loss = res.vf_loss = res.entropy = res.total = None
-    partial = torch.empty((B * T * 4,), dtype=torch.float32, device=dev)
+    partial = torch.empty((B * T * 4 + 2048,), dtype=torch.float32, device=dev)
     lp = (C.c_void_p * K)(*[l.data_ptr() for l in logits])
     sizes = (C.c_int32 * K)(*[int(l.shape[2]) for l in logits])
     dp = (C.c_void_p * K)(*[d.data_ptr() for d in res.dlogits]) if want_grads else None
@@ -114,7 +114,7 @@ def multiple_process_rollout(rollout, gamma, lambda_=1.0):
     dummy = torch.zeros((B, T, 1), dtype=torch.float32, device=dev)
     acts = torch.zeros((B, T, 1), dtype=torch.int32, device=dev)
     scal = torch.empty((4,), dtype=torch.float32, device=dev)
-    partial = torch.empty((B * T * 4,), dtype=torch.float32, device=dev)
+    partial = torch.empty((B * T * 4 + 2048,), dtype=torch.float32, device=dev)
     lp = (C.c_void_p * 1)(dummy.data_ptr())
     sizes = (C.c_int32 * 1)(1)
     N.check(lib.spiral_a2c_loss(lp, sizes, 1, N.ptr(acts), N.ptr(rewards), N.ptr(values), N.ptr(values), B, T,
