@@ -34,7 +34,7 @@ constexpr int kStages = 3;
 constexpr int kTcThreads = 192;
 constexpr uint32_t kTileBytes = kBM * kBK * 2;                 // 16 KB (A and W tiles have the same shape)
 constexpr uint32_t kStageBytes = 4 * kTileBytes;               // A_hi, A_lo, W_hi, W_lo
-constexpr uint32_t kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+constexpr uint32_t kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers: ring, 2 x accumulator full/empty, TMEM slot*/;
 
 struct ConvTcParams {
     int B, H, Cin, Cout;      // input NHWC [B,H,H,Cin]; output [B,H/2,H/2,Cout]
@@ -42,6 +42,34 @@ struct ConvTcParams {
     int M;                    // B * Ho * Wo
     int x3;                   // 1: hi*hi + hi*lo + lo*hi ; 0: hi*hi only
 };
+
+// Persistent: gridDim.x CTAs (one per SM) walk the (m_tile, n_tile) space; the TMEM accumulator is double
+// buffered (2 x kBN columns), so while the four epilogue warps drain tile i (tcgen05.ld, + bias, fp32 stores,
+// BN partials) the MMA warp is already accumulating tile i+1 and the TMA warp is a few stages further --
+// the tensor pipe no longer idles through every tile's epilogue and prologue (round-1 ncu: 53-78 % busy).
+__device__ __forceinline__ void mbar_arrive(uint32_t bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void epilogue_bar_sync()       // the 4 epilogue warps only (named barrier 1)
+{
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+}
+
+__device__ __forceinline__ uint32_t conv_tap_mask(const ConvTcParams &p, int Ho, int oy0)
+{
+    // taps (ky, kx) that touch at least one real input pixel for this tile
+    uint32_t tap_mask = 0;
+    const int oy_lo = oy0, oy_hi = (p.bb > 1) ? Ho - 1 : oy0 + p.bh - 1;
+    for (int ky = 0; ky < 5; ky++) {
+        const bool y_ok = (2 * oy_hi + ky - 1 >= 0) && (2 * oy_lo + ky - 1 < p.H);
+        for (int kx = 0; kx < 5; kx++) {
+            const bool x_ok = (2 * (Ho - 1) + kx - 1 >= 0) && (kx - 1 < p.H);
+            if (y_ok && x_ok) tap_mask |= 1u << (ky * 5 + kx);
+        }
+    }
+    return tap_mask;
+}
 
 __global__ void __launch_bounds__(kTcThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
@@ -55,45 +83,32 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     uint8_t *gen_base = smem_raw + (base - smem_u32(smem_raw));
     const uint32_t bar_base = base + kStages * kStageBytes;
     uint64_t *bar_gen = reinterpret_cast<uint64_t *>(gen_base + kStages * kStageBytes);
-    const uint32_t full0 = bar_base, empty0 = bar_base + 8 * kStages, accum_bar = bar_base + 16 * kStages;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bar_gen + 2 * kStages + 1);
+    const uint32_t full0 = bar_base, empty0 = bar_base + 8 * kStages;
+    const uint32_t acc_full0 = bar_base + 16 * kStages, acc_empty0 = acc_full0 + 16;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bar_gen + 2 * kStages + 4);
     __shared__ float s_red[4][2][kBN];      // per-epilogue-warp column sums
     __shared__ float s_tr[4][32][33];       // transpose staging
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m_tile = blockIdx.x, n_tile = blockIdx.y;
     const int Ho = p.H / 2;
-
-    // tile origin in (image, output row); tiles cover whole output rows
-    const int m0 = m_tile * kBM;
-    const int img0 = m0 / (Ho * Ho);
-    const int oy0 = (m0 % (Ho * Ho)) / Ho;
-    // taps (ky, kx) that touch at least one real input pixel for this tile
-    uint32_t tap_mask = 0;
-    {
-        const int oy_lo = oy0, oy_hi = (p.bb > 1) ? Ho - 1 : oy0 + p.bh - 1;
-        for (int ky = 0; ky < 5; ky++) {
-            const bool y_ok = (2 * oy_hi + ky - 1 >= 0) && (2 * oy_lo + ky - 1 < p.H);
-            for (int kx = 0; kx < 5; kx++) {
-                const bool x_ok = (2 * (Ho - 1) + kx - 1 >= 0) && (kx - 1 < p.H);
-                if (y_ok && x_ok) tap_mask |= 1u << (ky * 5 + kx);
-            }
-        }
-    }
+    const int m_tiles = (p.M + kBM - 1) / kBM, n_tiles = p.Cout / kBN;
+    const int n_work = m_tiles * n_tiles;
     const int chunks = p.Cin / kBK;
-    const int n_iter = __popc(tap_mask) * chunks;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < kStages; s++) {
             mbar_init(full0 + 8 * s, 1);
             mbar_init(empty0 + 8 * s, 1);
         }
-        mbar_init(accum_bar, 1);
+        for (int b = 0; b < 2; b++) {
+            mbar_init(acc_full0 + 8 * b, 1);
+            mbar_init(acc_empty0 + 8 * b, 4);       // one arrival per epilogue warp
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
-        // TMEM: 128 lanes x kBN fp32 columns
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(kBN) : "memory");
+        // TMEM: 128 lanes x 2 accumulators x kBN fp32 columns
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(2 * kBN) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     if (warp == 0 && lane == 0) {
@@ -105,28 +120,35 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t tmem_acc = *tmem_slot;
+    const uint32_t tmem_base = *tmem_slot;
 
     if (warp == 0) {
         // ===== TMA producer =====
         if (lane == 0) {
             int it = 0;
-            for (int tap = 0; tap < 25; tap++) {
-                if (!((tap_mask >> tap) & 1)) continue;
-                const int ky = tap / 5, kx = tap % 5;
-                for (int ch = 0; ch < chunks; ch++, it++) {
-                    const int s = it % kStages;
-                    if (it >= kStages) mbar_wait(empty0 + 8 * s, ((it / kStages) - 1) & 1);
-                    const uint32_t full = full0 + 8 * s;
-                    const uint32_t stage = base + s * kStageBytes;
-                    mbar_expect_tx(full, p.x3 ? kStageBytes : 2 * kTileBytes);
-                    const int c0 = ch * kBK;
-                    const int ix0 = kx - 1, iy0 = 2 * oy0 + ky - 1;
-                    tma_load_4d(stage, &map_a_hi, full, c0, ix0, iy0, img0);
-                    tma_load_2d(stage + 2 * kTileBytes, &map_w_hi, full, tap * p.Cin + c0, n_tile * kBN);
-                    if (p.x3) {
-                        tma_load_4d(stage + kTileBytes, &map_a_lo, full, c0, ix0, iy0, img0);
-                        tma_load_2d(stage + 3 * kTileBytes, &map_w_lo, full, tap * p.Cin + c0, n_tile * kBN);
+            for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+                const int m_tile = w / n_tiles, n_tile = w % n_tiles;     // neighbouring CTAs share the A tile in L2
+                const int m0 = m_tile * kBM;
+                const int img0 = m0 / (Ho * Ho);
+                const int oy0 = (m0 % (Ho * Ho)) / Ho;
+                const uint32_t tap_mask = conv_tap_mask(p, Ho, oy0);
+                for (int tap = 0; tap < 25; tap++) {
+                    if (!((tap_mask >> tap) & 1)) continue;
+                    const int ky = tap / 5, kx = tap % 5;
+                    for (int ch = 0; ch < chunks; ch++, it++) {
+                        const int s = it % kStages;
+                        if (it >= kStages) mbar_wait(empty0 + 8 * s, ((it / kStages) - 1) & 1);
+                        const uint32_t full = full0 + 8 * s;
+                        const uint32_t stage = base + s * kStageBytes;
+                        mbar_expect_tx(full, p.x3 ? kStageBytes : 2 * kTileBytes);
+                        const int c0 = ch * kBK;
+                        const int ix0 = kx - 1, iy0 = 2 * oy0 + ky - 1;
+                        tma_load_4d(stage, &map_a_hi, full, c0, ix0, iy0, img0);
+                        tma_load_2d(stage + 2 * kTileBytes, &map_w_hi, full, tap * p.Cin + c0, n_tile * kBN);
+                        if (p.x3) {
+                            tma_load_4d(stage + kTileBytes, &map_a_lo, full, c0, ix0, iy0, img0);
+                            tma_load_2d(stage + 3 * kTileBytes, &map_w_lo, full, tap * p.Cin + c0, n_tile * kBN);
+                        }
                     }
                 }
             }
@@ -135,79 +157,106 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         // ===== MMA issuer =====
         if (lane == 0) {
             constexpr uint32_t idesc = umma_idesc(kBM, kBN);
-            for (int it = 0; it < n_iter; it++) {
-                const int s = it % kStages;
-                mbar_wait(full0 + 8 * s, (it / kStages) & 1);
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t stage = base + s * kStageBytes;
-                const uint64_t a_hi = umma_desc(stage), a_lo = umma_desc(stage + kTileBytes);
-                const uint64_t w_hi = umma_desc(stage + 2 * kTileBytes), w_lo = umma_desc(stage + 3 * kTileBytes);
-#pragma unroll
-                for (int k = 0; k < kBK / 16; k++) {
-                    const uint64_t adv = (uint64_t)((k * 32) >> 4);       // 16 bf16 = 32 bytes along K
-                    if (p.x3) {
-                        umma_bf16(tmem_acc, a_lo + adv, w_hi + adv, idesc, (it | k) != 0);
-                        umma_bf16(tmem_acc, a_hi + adv, w_lo + adv, idesc, 1);
-                        umma_bf16(tmem_acc, a_hi + adv, w_hi + adv, idesc, 1);
-                    } else {
-                        umma_bf16(tmem_acc, a_hi + adv, w_hi + adv, idesc, (it | k) != 0);
-                    }
+            int it = 0, tile_i = 0;
+            for (int w = blockIdx.x; w < n_work; w += gridDim.x, tile_i++) {
+                const int m0 = (w / n_tiles) * kBM;
+                const int oy0 = (m0 % (Ho * Ho)) / Ho;
+                const int n_iter = __popc(conv_tap_mask(p, Ho, oy0)) * chunks;
+                const int b = tile_i & 1, use = tile_i >> 1;
+                if (use > 0) {                                    // the epilogue has drained this accumulator
+                    mbar_wait(acc_empty0 + 8 * b, (use - 1) & 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 }
-                umma_commit(empty0 + 8 * s);          // stage free once these MMAs have read it
+                const uint32_t tmem_acc = tmem_base + (uint32_t)(b * kBN);
+                for (int j = 0; j < n_iter; j++, it++) {
+                    const int s = it % kStages;
+                    mbar_wait(full0 + 8 * s, (it / kStages) & 1);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t stage = base + s * kStageBytes;
+                    const uint64_t a_hi = umma_desc(stage), a_lo = umma_desc(stage + kTileBytes);
+                    const uint64_t w_hi = umma_desc(stage + 2 * kTileBytes), w_lo = umma_desc(stage + 3 * kTileBytes);
+#pragma unroll
+                    for (int k = 0; k < kBK / 16; k++) {
+                        const uint64_t adv = (uint64_t)((k * 32) >> 4);       // 16 bf16 = 32 bytes along K
+                        if (p.x3) {
+                            umma_bf16(tmem_acc, a_lo + adv, w_hi + adv, idesc, (j | k) != 0);
+                            umma_bf16(tmem_acc, a_hi + adv, w_lo + adv, idesc, 1);
+                            umma_bf16(tmem_acc, a_hi + adv, w_hi + adv, idesc, 1);
+                        } else {
+                            umma_bf16(tmem_acc, a_hi + adv, w_hi + adv, idesc, (j | k) != 0);
+                        }
+                    }
+                    umma_commit(empty0 + 8 * s);          // stage free once these MMAs have read it
+                }
+                umma_commit(acc_full0 + 8 * b);           // accumulator complete
             }
-            umma_commit(accum_bar);                   // accumulator complete
         }
     } else {
         // ===== epilogue: warps 2..5 own TMEM lane quarters (warp % 4) =====
         const int q = warp & 3;
-        mbar_wait(accum_bar, 0);
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const int row = q * 32 + lane;
-        const int m = m0 + row;
-        const bool row_ok = m < p.M;
-        float *orow = out + (size_t)m * p.Cout + (size_t)n_tile * kBN;
+        const int et = threadIdx.x - 64;                  // 0..127 among the epilogue threads
+        int tile_i = 0;
+        for (int w = blockIdx.x; w < n_work; w += gridDim.x, tile_i++) {
+            const int m_tile = w / n_tiles, n_tile = w % n_tiles;
+            const int m0 = m_tile * kBM;
+            const int b = tile_i & 1, use = tile_i >> 1;
+            mbar_wait(acc_full0 + 8 * b, use & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t tmem_acc = tmem_base + (uint32_t)(b * kBN);
+            const int row = q * 32 + lane;
+            const int m = m0 + row;
+            const bool row_ok = m < p.M;
+            float *orow = out + (size_t)m * p.Cout + (size_t)n_tile * kBN;
 #pragma unroll 1
-        for (int cb = 0; cb < kBN; cb += 32) {
-            float v[32];
-            tmem_ld32(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)cb, v);
+            for (int cb = 0; cb < kBN; cb += 32) {
+                float v[32];
+                tmem_ld32(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)cb, v);
 #pragma unroll
-            for (int j = 0; j < 32; j++) v[j] = row_ok ? v[j] + (bias ? __ldg(bias + n_tile * kBN + cb + j) : 0.0f) : 0.0f;
-            if (row_ok) {
+                for (int j = 0; j < 32; j++) v[j] = row_ok ? v[j] + (bias ? __ldg(bias + n_tile * kBN + cb + j) : 0.0f) : 0.0f;
+                if (row_ok) {
 #pragma unroll
-                for (int j = 0; j < 32; j += 4)
-                    *reinterpret_cast<float4 *>(orow + cb + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-            }
-            if (bn_partial) {
-                // column sums over this warp's 32 rows via an smem transpose
-#pragma unroll
-                for (int j = 0; j < 32; j++) s_tr[q][lane][j] = v[j];
-                __syncwarp();
-                float s = 0.f, sq = 0.f;
-#pragma unroll
-                for (int r = 0; r < 32; r++) {
-                    const float x = s_tr[q][r][lane];
-                    s += x;
-                    sq += x * x;
+                    for (int j = 0; j < 32; j += 4)
+                        *reinterpret_cast<float4 *>(orow + cb + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
                 }
-                s_red[q][0][cb + lane] = s;
-                s_red[q][1][cb + lane] = sq;
-                __syncwarp();
+                if (bn_partial) {
+                    // column sums over this warp's 32 rows via an smem transpose
+#pragma unroll
+                    for (int j = 0; j < 32; j++) s_tr[q][lane][j] = v[j];
+                    __syncwarp();
+                    float s = 0.f, sq = 0.f;
+#pragma unroll
+                    for (int r = 0; r < 32; r++) {
+                        const float x = s_tr[q][r][lane];
+                        s += x;
+                        sq += x * x;
+                    }
+                    s_red[q][0][cb + lane] = s;
+                    s_red[q][1][cb + lane] = sq;
+                    __syncwarp();
+                }
+            }
+            // this warp's TMEM reads are complete (tcgen05.wait::ld inside tmem_ld32): release the accumulator
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            if (lane == 0) mbar_arrive(acc_empty0 + 8 * b);
+            if (bn_partial) {
+                epilogue_bar_sync();
+                if (et < kBN) {
+                    const int c = et;
+                    const float s = (s_red[0][0][c] + s_red[1][0][c]) + (s_red[2][0][c] + s_red[3][0][c]);
+                    const float sq = (s_red[0][1][c] + s_red[1][1][c]) + (s_red[2][1][c] + s_red[3][1][c]);
+                    float *pp = bn_partial + ((size_t)m_tile * p.Cout + n_tile * kBN + c) * 2;
+                    pp[0] = s;
+                    pp[1] = sq;
+                }
+                epilogue_bar_sync();                      // s_red is free for the next tile
             }
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (bn_partial && threadIdx.x < kBN) {
-        const int c = threadIdx.x;
-        const float s = (s_red[0][0][c] + s_red[1][0][c]) + (s_red[2][0][c] + s_red[3][0][c]);
-        const float sq = (s_red[0][1][c] + s_red[1][1][c]) + (s_red[2][1][c] + s_red[3][1][c]);
-        float *pp = bn_partial + ((size_t)m_tile * p.Cout + n_tile * kBN + c) * 2;
-        pp[0] = s;
-        pp[1] = sq;
-    }
     if (warp == 1) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_acc), "n"(kBN) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(2 * kBN) : "memory");
     }
 }
 
@@ -431,7 +480,8 @@ int disc_tc_forward(SpiralDisc *d, const float *x, int batch, float *logits, flo
         const int mtiles = (p.M + kBM - 1) / kBM;
         const bool bn = d->cfg.batch_norm != 0;
         float *part = (float *)(ws + pl.part_off[l]);
-        dim3 grid(mtiles, Cout / kBN);
+        const int n_work = mtiles * (Cout / kBN);
+        dim3 grid(n_work < 148 ? n_work : 148);
         conv_tc_kernel<<<grid, kTcThreads, kSmemBytes, st>>>(ma_hi, ma_lo, mw_hi, mw_lo, p, (const float *)W.conv_b[l],
                                                             (float *)(ws + pl.act_off[l]), bn ? part : nullptr);
         float *scale = (float *)(ws + pl.scale_off[l]), *shift = (float *)(ws + pl.shift_off[l]);
@@ -483,7 +533,8 @@ int conv_tc_layer(void *a_hi, void *a_lo, void *w_hi, void *w_lo, float *out, in
     er |= encode_w_map(&t, &mw_hi, w_hi, 25 * Cin, Cout);
     er |= encode_w_map(&t, &mw_lo, w_lo, 25 * Cin, Cout);
     if (er) return spiral_set_error(SPIRAL_ECUDA, "cuTensorMapEncodeTiled failed (CUresult %d)", er);
-    dim3 grid((p.M + kBM - 1) / kBM, Cout / kBN);
+    const int n_work = ((p.M + kBM - 1) / kBM) * (Cout / kBN);
+    dim3 grid(n_work < 148 ? n_work : 148);
     conv_tc_kernel<<<grid, kTcThreads, kSmemBytes, st>>>(ma_hi, ma_lo, mw_hi, mw_lo, p, nullptr, out, nullptr);
     return SPIRAL_OK;
 }
