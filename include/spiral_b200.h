@@ -253,6 +253,24 @@ int spiral_categorical_sample(const float *logits_dev, int32_t rows, int32_t n, 
 /* test hook: one Philox4x32-10 block; ctr_key6 is a HOST array {c0,c1,c2,c3,k0,k1} */
 int spiral_debug_philox(const uint32_t *ctr_key6_host, uint32_t *out4_dev, void *stream);
 
+/* ------------------------------------------------------------------ */
+/* Learner update (K5)                                                  */
+/* replaces: agent.py:231-239 (tf.clip_by_global_norm(grads, 40) +      */
+/*           tf.train.AdamOptimizer(policy_lr)) and                     */
+/*           models/discriminator.py:124-126 (Adam, beta1 .5, beta2 .9) */
+/* ------------------------------------------------------------------ */
+/* Pointer tables are HOST arrays of device pointers, sizes in elements.
+ * spiral_grad_global_norm: norm_out_dev f32[1] = sqrt(sum of squares of every tensor); scratch_dev f64[32 * n_tensors].
+ * spiral_adam_step: g' = g * grad_scale * clip / max(norm * grad_scale, clip)  (skipped when norm_dev is NULL or
+ * clip_norm <= 0);  m = b1 m + (1-b1) g';  v = b2 v + (1-b2) g'^2;  p -= lr_t * m / (sqrt(v) + eps), with
+ * lr_t = lr * sqrt(1 - b2^t) / (1 - b1^t) computed by the caller (TensorFlow's formulation).  No host sync. */
+int spiral_grad_global_norm(const float *const *grads_dev, const int64_t *sizes, int32_t n_tensors,
+                            double *scratch_dev, float *norm_out_dev, void *stream);
+int spiral_adam_step(float *const *params_dev, const float *const *grads_dev, float *const *m_dev,
+                     float *const *v_dev, const int64_t *sizes, int32_t n_tensors, float lr_t, float beta1,
+                     float beta2, float eps, float grad_scale, const float *norm_dev, float clip_norm,
+                     void *stream);
+
 #ifdef __cplusplus
 }
 #endif

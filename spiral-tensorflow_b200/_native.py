@@ -95,6 +95,9 @@ SYMBOLS = {
     "spiral_disc_forward": (C.c_int, [_vp, _vp, C.c_int32, _vp, _vp, _vp, _vp, _vp]),
     "spiral_categorical_sample": (C.c_int, [_vp, C.c_int32, C.c_int32, C.c_uint64, C.c_uint64, _vp, _vp]),
     "spiral_debug_philox": (C.c_int, [C.POINTER(C.c_uint32), _vp, _vp]),
+    "spiral_grad_global_norm": (C.c_int, [C.POINTER(_vp), C.POINTER(C.c_int64), C.c_int32, _vp, _vp, _vp]),
+    "spiral_adam_step": (C.c_int, [C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(C.c_int64),
+                                   C.c_int32, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, _vp, C.c_float, _vp]),
     "spiral_conv_workspace_bytes": (C.c_int64, [C.c_int32] * 5),
     "spiral_conv_forward": (C.c_int, [_vp, _vp, _vp] + [C.c_int32] * 5 + [_vp, _vp]),
     "spiral_conv_dgrad": (C.c_int, [_vp, _vp, _vp] + [C.c_int32] * 5 + [_vp, _vp]),

@@ -15,40 +15,14 @@ backward / double-backward convolutions (models/conv_ops.py, K2b); the policy tr
 """
 from __future__ import annotations
 
-import math
-
 import torch
 
 from . import distributed as dist_utils
 from . import rl_utils
 from .models.discriminator import Discriminator
 from .models.policy import Policy
+from .optim import FusedTFAdam
 from .replay import ReplayBuffer
-
-
-class TFAdam(torch.optim.Optimizer):
-    """tf.train.AdamOptimizer: lr_t = lr * sqrt(1 - b2^t) / (1 - b1^t);  p -= lr_t * m / (sqrt(v) + eps)."""
-
-    def __init__(self, params, lr, beta1=0.9, beta2=0.999, eps=1e-8):
-        super().__init__(params, dict(lr=lr, beta1=beta1, beta2=beta2, eps=eps))
-
-    @torch.no_grad()
-    def step(self):
-        for g in self.param_groups:
-            for p in g["params"]:
-                if p.grad is None:
-                    continue
-                st = self.state[p]
-                if not st:
-                    st["t"] = 0
-                    st["m"] = torch.zeros_like(p)
-                    st["v"] = torch.zeros_like(p)
-                st["t"] += 1
-                t, b1, b2 = st["t"], g["beta1"], g["beta2"]
-                st["m"].mul_(b1).add_(p.grad, alpha=1 - b1)
-                st["v"].mul_(b2).addcmul_(p.grad, p.grad, value=1 - b2)
-                lr_t = g["lr"] * math.sqrt(1 - b2 ** t) / (1 - b1 ** t)
-                p.addcdiv_(st["m"], st["v"].sqrt().add_(g["eps"]), value=-lr_t)
 
 
 class Agent(object):
@@ -57,14 +31,14 @@ class Agent(object):
         self.env = env
         self.device = env.device if device is None else torch.device(device)
         self.policy = Policy(args, env, "global", env.observation_shape, env.action_sizes).to(self.device)
-        self.policy_opt = TFAdam(self.policy.parameters(), args.policy_lr)
+        self.policy_opt = FusedTFAdam(self.policy.parameters(), args.policy_lr)
         self.gan = args.loss == "gan"
         if self.gan:
             self.disc = Discriminator(args, None, env.observation_shape, norm_fn=env.norm, scope_name="global",
                                       device=self.device, max_batch=max(env.num_envs, args.disc_batch_size))
             for p in self.disc.params.values():
                 p.requires_grad_(True)
-            self.disc_opt = TFAdam(list(self.disc.params.values()), args.disc_lr, beta1=0.5, beta2=0.9)
+            self.disc_opt = FusedTFAdam(list(self.disc.params.values()), args.disc_lr, beta1=0.5, beta2=0.9)
             self.replay = ReplayBuffer(args, env.observation_shape, device=self.device)
         self.rng = torch.Generator(device=self.device)
         self.rng.manual_seed(int(args.seed))
@@ -119,9 +93,8 @@ class Agent(object):
         self.policy_opt.zero_grad(set_to_none=True)
         loss.backward()
         grads = [p.grad for p in pi.parameters() if p.grad is not None]
-        dist_utils.allreduce_grads_(grads, self.world)                                        # explicit 1/world
-        gnorm = dist_utils.clip_by_global_norm_(grads, float(args.grad_clip))                  # agent.py:231
-        self.policy_opt.step()
+        dist_utils.allreduce_grads_(grads, self.world, average=False)                         # sum; 1/world is folded into K5
+        gnorm = self.policy_opt.step(clip_norm=float(args.grad_clip), grad_scale=1.0 / self.world)   # agent.py:231-239
         B = acts.shape[0]
         return {"model/total_loss": loss.detach(), "model/grad_global_norm": gnorm,
                 "env/r": rollout["rewards"][:, -1].mean(), "batch": B}
@@ -138,8 +111,8 @@ class Agent(object):
         d_loss, critic, gp, fake_logits_mean = out["d_loss"], out["critic_loss"], out["gradient_penalty"], -out["g_loss"]
         self.disc_opt.zero_grad(set_to_none=True)
         d_loss.backward()
-        dist_utils.allreduce_grads_([q.grad for q in p.values() if q.grad is not None], self.world)
-        self.disc_opt.step()
+        dist_utils.allreduce_grads_([q.grad for q in p.values() if q.grad is not None], self.world, average=False)
+        self.disc_opt.step(grad_scale=1.0 / self.world)                                       # discriminator.py:124-126
         D.sync_weights()
         return {"gan/critic_loss": critic.detach(), "gan/disc_loss": d_loss.detach(), "gan/penalty": gp.detach(),
                 "gan/gen_loss": -fake_logits_mean.detach()}

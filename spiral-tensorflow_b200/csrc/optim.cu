@@ -1,0 +1,131 @@
+// optim.cu -- K5: the learner's update step as multi-tensor kernels.
+//
+// Replaces what TensorFlow runs for agent.py:231-239 (tf.clip_by_global_norm(grads, 40) followed by
+// tf.train.AdamOptimizer(policy_lr).apply_gradients) and models/discriminator.py:124-126
+// (AdamOptimizer(disc_lr, beta1=0.5, beta2=0.9)):
+//
+//   grad_sumsq   sum of squares of every gradient tensor -> global norm, two deterministic float64 stages
+//   adam_step    g' = g * grad_scale * clip / max(norm, clip)        (grad_scale = 1 / world after the all-reduce)
+//                m = b1 m + (1 - b1) g';  v = b2 v + (1 - b2) g'^2;  p -= lr_t * m / (sqrt(v) + eps)
+//                with TensorFlow's epsilon placement and lr_t = lr sqrt(1 - b2^t) / (1 - b1^t) (host side)
+//
+// One launch covers up to kMaxTensors parameter tensors (pointer table passed by value); the norm stays on
+// the device, so a whole optimiser step issues no host synchronisation.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/spiral_b200.h"
+#include "common.h"
+
+namespace spiral {
+
+constexpr int kMaxTensors = 48;
+constexpr int kOptBlocksX = 32;
+
+struct TensorTable {
+    float *p[kMaxTensors];
+    const float *g[kMaxTensors];
+    float *m[kMaxTensors];
+    float *v[kMaxTensors];
+    long long n[kMaxTensors];
+    int count;
+};
+
+__global__ void __launch_bounds__(256)
+grad_sumsq_kernel(const __grid_constant__ TensorTable T, double *__restrict__ partial)
+{
+    __shared__ double s[256];
+    const int t = blockIdx.y;
+    const float *g = T.g[t];
+    const long long n = T.n[t];
+    double acc = 0.0;
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
+        const double x = (double)g[i];
+        acc += x * x;
+    }
+    s[threadIdx.x] = acc;
+    __syncthreads();
+    for (int o = 128; o; o >>= 1) {
+        if (threadIdx.x < o) s[threadIdx.x] += s[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) partial[(size_t)t * gridDim.x + blockIdx.x] = s[0];
+}
+
+__global__ void __launch_bounds__(256)
+norm_final_kernel(const double *__restrict__ partial, int n_partial, float *__restrict__ norm_out)
+{
+    __shared__ double s[256];
+    double acc = 0.0;
+    for (int i = threadIdx.x; i < n_partial; i += 256) acc += partial[i];
+    s[threadIdx.x] = acc;
+    __syncthreads();
+    for (int o = 128; o; o >>= 1) {
+        if (threadIdx.x < o) s[threadIdx.x] += s[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) norm_out[0] = (float)sqrt(s[0]);
+}
+
+__global__ void __launch_bounds__(256)
+adam_step_kernel(const __grid_constant__ TensorTable T, float lr_t, float b1, float b2, float eps, float grad_scale,
+                 const float *__restrict__ norm, float clip_norm)
+{
+    const int t = blockIdx.y;
+    float scale = grad_scale;
+    if (norm && clip_norm > 0.0f) scale *= clip_norm / fmaxf(norm[0] * grad_scale, clip_norm);   // the norm of the SCALED gradient
+    float *p = T.p[t], *m = T.m[t], *v = T.v[t];
+    const float *g = T.g[t];
+    const long long n = T.n[t];
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
+        const float gi = g[i] * scale;
+        const float mi = b1 * m[i] + (1.0f - b1) * gi;
+        const float vi = b2 * v[i] + (1.0f - b2) * gi * gi;
+        m[i] = mi;
+        v[i] = vi;
+        p[i] -= lr_t * mi / (sqrtf(vi) + eps);
+    }
+}
+
+}  // namespace spiral
+
+using namespace spiral;
+
+extern "C" int spiral_grad_global_norm(const float *const *grads, const int64_t *sizes, int32_t n_tensors,
+                                       double *scratch, float *norm_out, void *stream)
+{
+    SPIRAL_REQUIRE(grads); SPIRAL_REQUIRE(sizes); SPIRAL_REQUIRE(scratch); SPIRAL_REQUIRE(norm_out);
+    if (n_tensors <= 0 || n_tensors > 4096 / kOptBlocksX * 8)
+        return spiral_set_error(SPIRAL_EINVAL, "grad_global_norm: 1..1024 tensors (scratch holds 32 partials each)");
+    cudaStream_t st = (cudaStream_t)stream;
+    for (int t0 = 0; t0 < n_tensors; t0 += kMaxTensors) {
+        TensorTable T;
+        T.count = n_tensors - t0 < kMaxTensors ? n_tensors - t0 : kMaxTensors;
+        for (int i = 0; i < T.count; i++) { T.g[i] = grads[t0 + i]; T.n[i] = sizes[t0 + i]; T.p[i] = nullptr; T.m[i] = nullptr; T.v[i] = nullptr; }
+        dim3 grid(kOptBlocksX, T.count);
+        grad_sumsq_kernel<<<grid, 256, 0, st>>>(T, scratch + (size_t)t0 * kOptBlocksX);
+    }
+    norm_final_kernel<<<1, 256, 0, st>>>(scratch, n_tensors * kOptBlocksX, norm_out);
+    const cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? SPIRAL_OK : spiral_cuda_error(e, "spiral_grad_global_norm");
+}
+
+extern "C" int spiral_adam_step(float *const *params, const float *const *grads, float *const *m, float *const *v,
+                                const int64_t *sizes, int32_t n_tensors, float lr_t, float beta1, float beta2, float eps,
+                                float grad_scale, const float *norm_dev, float clip_norm, void *stream)
+{
+    SPIRAL_REQUIRE(params); SPIRAL_REQUIRE(grads); SPIRAL_REQUIRE(m); SPIRAL_REQUIRE(v); SPIRAL_REQUIRE(sizes);
+    if (n_tensors <= 0) return spiral_set_error(SPIRAL_EINVAL, "adam_step: no tensors");
+    cudaStream_t st = (cudaStream_t)stream;
+    for (int t0 = 0; t0 < n_tensors; t0 += kMaxTensors) {
+        TensorTable T;
+        T.count = n_tensors - t0 < kMaxTensors ? n_tensors - t0 : kMaxTensors;
+        for (int i = 0; i < T.count; i++) {
+            T.p[i] = params[t0 + i]; T.g[i] = grads[t0 + i]; T.m[i] = m[t0 + i]; T.v[i] = v[t0 + i]; T.n[i] = sizes[t0 + i];
+        }
+        dim3 grid(kOptBlocksX, T.count);
+        adam_step_kernel<<<grid, 256, 0, st>>>(T, lr_t, beta1, beta2, eps, grad_scale, norm_dev, clip_norm);
+    }
+    const cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? SPIRAL_OK : spiral_cuda_error(e, "spiral_adam_step");
+}

@@ -29,3 +29,35 @@ def oracle_for(env, B, math_mode=1):
     spec = po.EnvSpec(action_names=list(env.acs), location_size=env.location_size,
                       n_color=len(env.colors), colorize=env.colorize, math_mode=math_mode)
     return po.OracleBatchEnv(spec, B, channels=env.channels)
+
+
+import math
+
+import torch
+
+
+class TFAdam(torch.optim.Optimizer):
+    """Plain-PyTorch reference of K5 (tests only).  tf.train.AdamOptimizer: lr_t = lr * sqrt(1 - b2^t) / (1 - b1^t);  p -= lr_t * m / (sqrt(v) + eps)."""
+
+    def __init__(self, params, lr, beta1=0.9, beta2=0.999, eps=1e-8):
+        super().__init__(params, dict(lr=lr, beta1=beta1, beta2=beta2, eps=eps))
+
+    @torch.no_grad()
+    def step(self):
+        for g in self.param_groups:
+            for p in g["params"]:
+                if p.grad is None:
+                    continue
+                st = self.state[p]
+                if not st:
+                    st["t"] = 0
+                    st["m"] = torch.zeros_like(p)
+                    st["v"] = torch.zeros_like(p)
+                st["t"] += 1
+                t, b1, b2 = st["t"], g["beta1"], g["beta2"]
+                st["m"].mul_(b1).add_(p.grad, alpha=1 - b1)
+                st["v"].mul_(b2).addcmul_(p.grad, p.grad, value=1 - b2)
+                lr_t = g["lr"] * math.sqrt(1 - b2 ** t) / (1 - b1 ** t)
+                p.addcdiv_(st["m"], st["v"].sqrt().add_(g["eps"]), value=-lr_t)
+
+

@@ -75,3 +75,31 @@ def test_agent_loop_runs_and_updates_parameters(loss):
         assert torch.allclose(ag.disc.predict(x), pt, atol=1e-4)
     else:
         assert float(ro["rewards"][:, :-1].abs().max()) == 0.0 and float(ro["rewards"][:, -1].max()) <= 1.0
+
+
+def test_fused_clip_adam_matches_reference_formulas():
+    """K5 (agent.py:231-239): clip-by-global-norm + TensorFlow-style Adam against the plain PyTorch
+    restatements (tests/helpers.TFAdam, distributed.clip_by_global_norm_) on identical gradients."""
+    import spiral_b200 as sp
+    from importlib import import_module
+    from helpers import TFAdam
+    optim = import_module(sp.__name__ + ".optim")
+    du = import_module(sp.__name__ + ".distributed")
+    g = torch.Generator(device="cuda").manual_seed(0)
+    shapes = [(5, 5, 3, 64), (64,), (1152, 256), (7,), (300, 33)] * 12          # 60 tensors: more than one launch
+    pa = [torch.randn(s, generator=g, device="cuda") for s in shapes]
+    pb = [p.clone() for p in pa]
+    ref = TFAdam(pb, 1e-3, beta1=0.5, beta2=0.9)
+    fused = optim.FusedTFAdam(pa, 1e-3, beta1=0.5, beta2=0.9)
+    world = 4
+    for step in range(3):
+        grads = [torch.randn(s, generator=g, device="cuda") * (10.0 if step == 1 else 0.01) for s in shapes]
+        for p, q, gr in zip(pa, pb, grads):
+            p.grad = gr.clone()
+            q.grad = gr.clone() / world
+        want_norm = du.clip_by_global_norm_([q.grad for q in pb], 40.0)
+        ref.step()
+        got_norm = fused.step(clip_norm=40.0, grad_scale=1.0 / world)
+        assert abs(float(got_norm) - float(want_norm)) <= 1e-5 * float(want_norm)
+        for p, q in zip(pa, pb):
+            assert torch.allclose(p, q, rtol=1e-5, atol=1e-7)
