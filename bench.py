@@ -393,6 +393,38 @@ def run_ours(args):
                     d_loss=float(out["d_loss"]), note="WGAN-GP step incl. double backward; conv fwd/dgrad/wgrad on K2b kernels, "
                                                       "BN/leaky-ReLU/dense glue in PyTorch")
 
+    def agent_loop(args, dev, n=128, iters=3):
+        """The whole synchronous loop at a small batch, for context: policy.act (PyTorch module + K4 sampling)
+        -> env.step (K1) x T, D reward (K2) -> fused A2C (K3) -> policy backward -> K5 update, and one WGAN-GP
+        step (K2b + K5).  NOT the headline metric: the policy trunk is a plain PyTorch module."""
+        agent_mod = import_module(sp.__name__ + ".agent")
+        a = sp.get_args(["--env", WORLD_ENV, "--location_size", str(WORKLOAD["location_size"]), "--color_channel",
+                         str(WORKLOAD["color_channel"]), "--episode_length", str(args.episode_length), "--loss", "gan",
+                         "--disc_dim", str(WORKLOAD["disc_dim"]), "--disc_precision", args.disc_precision,
+                         "--disc_batch_size", "64"])
+        env = sp.create_env(a, num_envs=n, device=dev)
+        ag = agent_mod.Agent(a, env)
+        times = {"rollout": 0.0, "train_policy": 0.0, "train_gan": 0.0}
+        ev = lambda: torch.cuda.Event(enable_timing=True)
+        for i in range(iters + 1):
+            e0, e1, e2, e3 = ev(), ev(), ev(), ev()
+            e0.record()
+            ro = ag.rollout()
+            e1.record()
+            ag.train_policy(ro)
+            e2.record()
+            ag.train_gan()
+            e3.record()
+            torch.cuda.synchronize()
+            if i > 0:
+                times["rollout"] += e0.elapsed_time(e1) / iters
+                times["train_policy"] += e1.elapsed_time(e2) / iters
+                times["train_gan"] += e2.elapsed_time(e3) / iters
+        total = sum(times.values())
+        return dict(canvases=n, ms=times, env_steps_per_s=n * args.episode_length / (total * 1e-3),
+                    note="full loop incl. the PyTorch policy (not the headline metric)")
+
+    WORLD_ENV = WORKLOAD["env"]
     res = measure(args.canvases)
     if rank != 0:
         if world > 1:
@@ -409,6 +441,7 @@ def run_ours(args):
             out[key] = {k: sec[k] for k in ("value", "unit", "ms_per_step", "e2e", "kernel_ms_per_step")}
             out[key]["config"] = desc
         out["disc_train"] = disc_train_step(args, dev, C)
+        out["agent_loop"] = agent_loop(args, dev)
     if world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline(args, acs_list, head_list, C, L, T, WORKLOAD["disc_dim"])
     print(json.dumps(out))
