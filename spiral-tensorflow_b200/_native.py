@@ -12,7 +12,7 @@ import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
-LIB_PATH = os.path.join(CSRC, "libspiral_b200.so")
+LIB_PATH = os.environ.get("SPIRAL_B200_LIB") or os.path.join(CSRC, "libspiral_b200.so")   # override: tuning builds
 
 ABI_VERSION = 1
 MAX_POINTS, MAX_TABLE, MAX_L, TILE = 4, 8, 64, 64

@@ -108,6 +108,9 @@ struct Brush {
 };
 
 constexpr int kExpandThreads = 32;
+#ifndef EXPAND_MIN_BLOCKS
+#define EXPAND_MIN_BLOCKS 16
+#endif
 
 __device__ __forceinline__ float clamp_radius(float r)
 {
@@ -228,7 +231,7 @@ __device__ __forceinline__ void curve_point(const StepSetup &st, int i, double &
     py = y3 + y5 * ratio;
 }
 
-__global__ void __launch_bounds__(kExpandThreads)
+__global__ void __launch_bounds__(kExpandThreads, EXPAND_MIN_BLOCKS)
 expand_kernel(const __grid_constant__ EnvParams P, const int32_t *__restrict__ actions,
               float *__restrict__ brush_state, double *__restrict__ env_state,
               float *__restrict__ dabs, int32_t *__restrict__ dab_count, int32_t *__restrict__ status,
@@ -738,9 +741,13 @@ __device__ __forceinline__ float dab_rr(const EnvParams &P, int xp, int yp, floa
 //            instruction regardless of dab boundaries (a dab alone fills ~17 of 32 lanes)
 //   phase 2  the cheap, order-dependent part: dab by dab, blend the pixels whose opa_a != 0
 // Dabs the disc test does not cover (radius >= 3, elliptical brushes) take the bounding-box walk.
-constexpr int kCompWarps = 1;                 // canvases (warps) per CTA
+#ifndef COMP_WARPS_PER_SM
+#define COMP_WARPS_PER_SM 40
+#endif
+constexpr int kCompWarps = COMP_WARPS_PER_SM > 32 ? 2 : 1;   // canvases (warps) per CTA (at most 32 CTAs per SM)
 constexpr int kListCap = 64;                  // candidate pixels per dab on the fast path
-constexpr int kDense = 1024;                  // (dab, pixel) pairs per round: 16 dabs always fit
+constexpr int kCompResident = COMP_WARPS_PER_SM;   // resident warps (= canvases in flight) per SM
+constexpr int kDense = kCompResident > 40 ? 512 : (kCompResident > 32 ? 768 : 1024);   // (dab, pixel) pairs per round
 
 struct __align__(16) SharedDab {
     float x, y, hardness, one_over_r2;
@@ -752,7 +759,7 @@ struct __align__(16) SharedDab {
 };
 
 template <int C>
-__global__ void __launch_bounds__(32 * kCompWarps)
+__global__ void __launch_bounds__(32 * kCompWarps, kCompResident / kCompWarps)
 composite_kernel(const __grid_constant__ EnvParams P, uint16_t *__restrict__ canvas,
                  const float *__restrict__ dabs, const int32_t *__restrict__ dab_count,
                  const uint16_t *__restrict__ dither, float *__restrict__ obs, int32_t *__restrict__ work_counter)
@@ -1097,7 +1104,7 @@ cudaError_t launch_composite(const EnvParams &P, uint16_t *canvas, const float *
                              int32_t *work_counter, cudaStream_t st)
 {
     int blocks = (P.B + kCompWarps - 1) / kCompWarps;
-    if (blocks > 148 * 32 / kCompWarps) blocks = 148 * 32 / kCompWarps;       // one resident warp per slot
+    if (blocks > 148 * kCompResident / kCompWarps) blocks = 148 * kCompResident / kCompWarps;   // one resident warp per slot
     cudaMemsetAsync(work_counter, 0, sizeof(int32_t), st);
     static bool carveout = false;
     if (!carveout) {      // 32 resident warps need 32 x 5.8 KB of shared memory: ask for the large carve-out
