@@ -57,7 +57,12 @@ constexpr int kRowThreads = 128;
 // peak; holding the row in registers (80 registers, 24 warps per SM) and a persistent bulk-async (cp.async.bulk +
 // mbarrier) double-buffered variant were both slower on B200 (25 and 44 ms vs 19 ms at B = 65536): the kernel
 // is bounded by instruction issue as much as by bandwidth, and occupancy wins.
-__device__ __forceinline__ float fast_exp(float x) { return __expf(x); }
+__device__ __forceinline__ float fast_exp(float x)
+{
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x * 1.4426950408889634f));      // 2 instructions (__expf adds denormal handling)
+    return y;
+}
 
 __device__ __forceinline__ float warp_max(float v)
 {
