@@ -9,8 +9,9 @@
 // gathers its mma.m16n8k16 A fragment straight from it through a per-k offset table, B fragments come
 // from the pre-split, pre-transposed kernel in shared memory, and the same bf16x3 split as the other
 // layers (hi*hi + hi*lo + lo*hi, fp32 accumulate) keeps fp32-equivalent accuracy.  Epilogue: + bias,
-// leaky-ReLU (no BN at layer 0), hi/lo split, staged through shared memory into the fully coalesced
-// bf16 NHWC pair layer 1's TMA reads.
+// leaky-ReLU (no BN at layer 0), hi/lo split, and -- the packed kernel's rows are permuted so that a thread's
+// accumulator fragment is 16 consecutive channels -- 128-bit stores straight from registers into the bf16
+// NHWC pair layer 1's TMA reads.
 //
 // CTA = one image, 8 warps, looping over its 8 tiles of 8 output rows x 16 output pixels x 64 channels (the
 // packed kernel is staged once per CTA); warp = one row of 16 pixels (M = 16) x all 64 channels (8 n-tiles),
@@ -24,7 +25,6 @@ namespace spiral {
 constexpr int kC0Tw = 16, kC0Th = 8;                    // output tile
 constexpr int kC0Iw = 2 * kC0Tw + 3, kC0Ih = 2 * kC0Th + 3;   // input tile 35 x 19
 constexpr int kC0Cout = 64;
-constexpr int kC0OutStride = 72;                       // bf16 per staged output pixel: conflict-free fragment stores
 
 __host__ __device__ constexpr int c0_kpad(int cin) { return (25 * cin + 15) / 16 * 16; }
 __host__ __device__ constexpr int c0_kstride(int cin) { return c0_kpad(cin) + 8; }   // bf16 per row; conflict-free
@@ -37,6 +37,12 @@ __device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a
         : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
 }
 
+// Row n = nt * 8 + j of the packed kernel (column j of n-tile nt of the MMA) holds output channel
+//   (j >> 1) * 16 + nt * 2 + (j & 1)
+// so that the accumulator fragment of thread t (columns 2t, 2t+1 of every n-tile) is the 16 CONSECUTIVE
+// channels t*16 .. t*16+15 of its pixel: the epilogue stores 128-bit words straight from registers.
+__host__ __device__ constexpr int c0_channel_of_row(int n) { return ((n & 7) >> 1) * 16 + (n >> 3) * 2 + (n & 1); }
+
 __device__ __forceinline__ uint32_t pack2(uint16_t lo, uint16_t hi) { return (uint32_t)lo | ((uint32_t)hi << 16); }
 
 // HWIO [25][CIN][64] fp32 -> [64][KS] bf16 hi / lo with k = tap * CIN + c (zero padded)
@@ -46,7 +52,8 @@ __global__ void conv0_pack_kernel(const float *__restrict__ w, __nv_bfloat16 *__
     const int K = 25 * Cin, KS = c0_kstride(Cin);
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < kC0Cout * KS; i += gridDim.x * blockDim.x) {
         const int n = i / KS, k = i % KS;
-        const float v = k < K ? w[(size_t)k * kC0Cout + n] : 0.0f;
+        const int ch = c0_channel_of_row(n);
+        const float v = k < K ? w[(size_t)k * kC0Cout + ch] : 0.0f;
         const __nv_bfloat16 h = __float2bfloat16_rn(v);
         hi[i] = h;
         lo[i] = __float2bfloat16_rn(v - __bfloat162float(h));
@@ -54,7 +61,7 @@ __global__ void conv0_pack_kernel(const float *__restrict__ w, __nv_bfloat16 *__
 }
 
 template <int CIN>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 conv0_mma_kernel(const float *__restrict__ x, const __nv_bfloat16 *__restrict__ w_hi, const __nv_bfloat16 *__restrict__ w_lo,
                  const float *__restrict__ bias, __nv_bfloat16 *__restrict__ out_hi, __nv_bfloat16 *__restrict__ out_lo,
                  int B, int H, int normalize, int x3)
@@ -67,7 +74,6 @@ conv0_mma_kernel(const float *__restrict__ x, const __nv_bfloat16 *__restrict__ 
     uint16_t *s_ih = s_wl + kC0Cout * KS;                                  // [19][35][CIN]
     uint16_t *s_il = s_ih + ((NIN + 7) & ~7);
     int *s_koff = reinterpret_cast<int *>(s_il + ((NIN + 7) & ~7));        // [KP]
-    uint16_t *s_out = reinterpret_cast<uint16_t *>(s_koff + KP);           // [8 warps][2][16 px][72]
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int Ho = H / 2;
@@ -156,35 +162,30 @@ conv0_mma_kernel(const float *__restrict__ x, const __nv_bfloat16 *__restrict__ 
         }
     }
 
-    // ---- epilogue: + bias, leaky-ReLU, hi/lo split, staged so that the warp writes 2 KB contiguous ----
-    uint16_t *so_h = s_out + warp * (2 * 16 * kC0OutStride), *so_l = so_h + 16 * kC0OutStride;
+    // ---- epilogue: + bias, leaky-ReLU, hi/lo split; thread t owns channels t*16 .. t*16+15 of pixels g and g+8 ----
+    const size_t opix = ((size_t)img * Ho + oy0 + warp) * Ho + ox0;        // 16 consecutive pixels
 #pragma unroll
-    for (int nt = 0; nt < 8; nt++) {
-        const int ch = nt * 8 + 2 * t;
-        const float b0 = __ldg(bias + ch), b1 = __ldg(bias + ch + 1);
+    for (int half = 0; half < 2; half++) {
+        uint32_t h[8], l[8];
 #pragma unroll
-        for (int half = 0; half < 2; half++) {
-            float v0 = acc[nt][2 * half] + b0, v1 = acc[nt][2 * half + 1] + b1;
+        for (int nt = 0; nt < 8; nt++) {
+            const int ch = t * 16 + nt * 2;
+            float v0 = acc[nt][2 * half] + __ldg(bias + ch), v1 = acc[nt][2 * half + 1] + __ldg(bias + ch + 1);
             v0 = v0 > 0.f ? v0 : 0.2f * v0;
             v1 = v1 > 0.f ? v1 : 0.2f * v1;
             const __nv_bfloat16 h0 = __float2bfloat16_rn(v0), h1 = __float2bfloat16_rn(v1);
             const __nv_bfloat16 l0 = __float2bfloat16_rn(v0 - __bfloat162float(h0));
             const __nv_bfloat16 l1 = __float2bfloat16_rn(v1 - __bfloat162float(h1));
-            const int px = g + 8 * half;
-            *reinterpret_cast<uint32_t *>(so_h + px * kC0OutStride + ch) = pack2(__bfloat16_as_ushort(h0), __bfloat16_as_ushort(h1));
-            *reinterpret_cast<uint32_t *>(so_l + px * kC0OutStride + ch) = pack2(__bfloat16_as_ushort(l0), __bfloat16_as_ushort(l1));
+            h[nt] = pack2(__bfloat16_as_ushort(h0), __bfloat16_as_ushort(h1));
+            l[nt] = pack2(__bfloat16_as_ushort(l0), __bfloat16_as_ushort(l1));
         }
+        const size_t o = (opix + g + 8 * half) * kC0Cout + t * 16;
+        uint4 *gh = reinterpret_cast<uint4 *>(out_hi + o), *gl = reinterpret_cast<uint4 *>(out_lo + o);
+        gh[0] = make_uint4(h[0], h[1], h[2], h[3]);
+        gh[1] = make_uint4(h[4], h[5], h[6], h[7]);
+        gl[0] = make_uint4(l[0], l[1], l[2], l[3]);
+        gl[1] = make_uint4(l[4], l[5], l[6], l[7]);
     }
-    __syncwarp();
-    const size_t opix = ((size_t)img * Ho + oy0 + warp) * Ho + ox0;        // 16 consecutive pixels
-    uint4 *gh = reinterpret_cast<uint4 *>(out_hi + opix * kC0Cout), *gl = reinterpret_cast<uint4 *>(out_lo + opix * kC0Cout);
-#pragma unroll
-    for (int i = 0; i < 4; i++) {                                          // 16 px * 128 B = 128 x 16 B
-        const int q = lane + 32 * i, px = q >> 3, chunk = q & 7;
-        gh[q] = *reinterpret_cast<const uint4 *>(so_h + px * kC0OutStride + chunk * 8);
-        gl[q] = *reinterpret_cast<const uint4 *>(so_l + px * kC0OutStride + chunk * 8);
-    }
-    __syncwarp();
     }   // next tile
 }
 
@@ -207,8 +208,7 @@ static int conv0_launch(const SpiralDisc *d, const float *x, int batch, const vo
                         void *out_lo, int x3, cudaStream_t st)
 {
     constexpr int KP = c0_kpad(CIN), KS = c0_kstride(CIN), NIN = kC0Ih * kC0Iw * CIN;
-    constexpr size_t smem = (size_t)2 * kC0Cout * KS * 2 + (size_t)2 * ((NIN + 7) & ~7) * 2 + (size_t)KP * 4 +
-                            (size_t)8 * 2 * 16 * kC0OutStride * 2;
+    constexpr size_t smem = (size_t)2 * kC0Cout * KS * 2 + (size_t)2 * ((NIN + 7) & ~7) * 2 + (size_t)KP * 4;
     static bool attr = false;
     if (!attr) {
         const cudaError_t e = cudaFuncSetAttribute(conv0_mma_kernel<CIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
