@@ -227,9 +227,9 @@ int spiral_disc_forward(SpiralDisc *d, const float *x_dev, int32_t batch, float 
 /* x f32[B,H,H,Cin] NHWC, w f32 HWIO [5,5,Cin,Cout], y f32[B,H/2,H/2,Cout]; no bias (the host adds it).
  * 'SAME' padding = 1 before / 2 after.  The three maps are bilinear and closed under differentiation,
  * so first- and second-order gradients of the whole stack are compositions of them.
- * precision: 0 = fp32 SIMT; 1 = tcgen05 bf16x3 (fp32-equivalent) where the channel counts allow
- * (forward: Cin % 64 == 0 and Cout % 128 == 0; dgrad: Cout % 64 == 0; wgrad: any), else fp32 SIMT;
- * 2 = tcgen05 plain bf16.  workspace: spiral_conv_workspace_bytes() bytes, caller-owned. */
+ * precision: 0 = fp32 SIMT; 1 = tcgen05 bf16x3 (16 operand bits, what the reward forward uses) where the
+ * channel counts allow (forward: Cin % 64 == 0 and Cout % 128 == 0; dgrad / wgrad: Cout % 64 == 0), else
+ * fp32 SIMT; 2 = tcgen05 plain bf16; 3 = tcgen05 bf16x6 (24 operand bits: fp32-exact products, for gradients).  workspace: spiral_conv_workspace_bytes() bytes, caller-owned. */
 int64_t spiral_conv_workspace_bytes(int32_t B, int32_t H, int32_t Cin, int32_t Cout, int32_t precision);
 int spiral_conv_forward(const float *x_dev, const float *w_dev, float *y_dev, int32_t B, int32_t H,
                         int32_t Cin, int32_t Cout, int32_t precision, void *workspace_dev, void *stream);

@@ -70,6 +70,10 @@ def build_parser():
     parser.add_argument('--max_dabs', type=int, default=2560)
     parser.add_argument('--dither', type=str2bool, default=True)
     parser.add_argument('--disc_precision', type=str, default='bf16x3', choices=['fp32', 'bf16x3', 'bf16'])
+    # arithmetic of the WGAN-GP step's convolutions and their gradients (K2b); 'auto' = bf16x6 (24 operand bits,
+    # fp32-exact products on the tensor cores) when the reward forward runs on tensor cores, else fp32
+    parser.add_argument('--disc_grad_precision', type=str, default='auto',
+                        choices=['auto', 'fp32', 'bf16x3', 'bf16', 'bf16x6'])
     return parser
 
 

@@ -251,11 +251,14 @@ int conv_wgrad_simt(const float *x, const float *dy, float *dw, int B, int H, in
 // ------------------------------------------------------------------------------------------
 using namespace spiral;
 
+// precision -> bf16 planes per operand: 1 = bf16x3 (2 planes), 2 = bf16 (1 plane), 3 = bf16x6 (3 planes)
+static int precision_planes(int precision) { return precision == 3 ? 3 : (precision == 2 ? 1 : 2); }
+
 static int check_shape(int B, int H, int Cin, int Cout, int precision)
 {
     if (B <= 0 || H < 2 || (H & 1) || Cin <= 0 || Cout <= 0)
         return spiral_set_error(SPIRAL_EINVAL, "conv: bad shape B=%d H=%d Cin=%d Cout=%d (H must be even)", B, H, Cin, Cout);
-    if (precision < 0 || precision > 2) return spiral_set_error(SPIRAL_EINVAL, "conv: precision must be 0, 1 or 2");
+    if (precision < 0 || precision > 3) return spiral_set_error(SPIRAL_EINVAL, "conv: precision must be 0, 1, 2 or 3");
     if ((long long)B * H * H * (long long)(Cin > Cout ? Cin : Cout) >= (1LL << 31) * 8)
         return spiral_set_error(SPIRAL_EINVAL, "conv: tensor too large");
     return SPIRAL_OK;
@@ -281,7 +284,7 @@ extern "C" int spiral_conv_forward(const float *x, const float *w, float *y, int
     cudaStream_t st = (cudaStream_t)stream;
     if (precision != 0 && conv_tc_supported(0, B, H, Cin, Cout)) {
         SPIRAL_REQUIRE(ws);
-        rc = conv_tc_forward(x, w, y, B, H, Cin, Cout, precision == 1, (char *)ws, st);
+        rc = conv_tc_forward(x, w, y, B, H, Cin, Cout, precision_planes(precision), (char *)ws, st);
         if (rc != SPIRAL_OK) return rc;
     } else {
         conv_forward_simt(x, w, y, B, H, Cin, Cout, st);
@@ -298,7 +301,7 @@ extern "C" int spiral_conv_dgrad(const float *dy, const float *w, float *dx, int
     if (rc != SPIRAL_OK) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     if (precision != 0 && conv_tc_supported(1, B, H, Cin, Cout)) {
-        rc = conv_tc_dgrad(dy, w, dx, B, H, Cin, Cout, precision == 1, (char *)ws, st);
+        rc = conv_tc_dgrad(dy, w, dx, B, H, Cin, Cout, precision_planes(precision), (char *)ws, st);
         if (rc != SPIRAL_OK) return rc;
     } else {
         conv_dgrad_simt(dy, w, dx, B, H, Cin, Cout, (char *)ws, st);
@@ -315,7 +318,7 @@ extern "C" int spiral_conv_wgrad(const float *x, const float *dy, float *dw, int
     if (rc != SPIRAL_OK) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     if (precision != 0 && conv_tc_supported(2, B, H, Cin, Cout)) {
-        rc = conv_tc_wgrad(x, dy, dw, B, H, Cin, Cout, precision == 1, (char *)ws, st);
+        rc = conv_tc_wgrad(x, dy, dw, B, H, Cin, Cout, precision_planes(precision), (char *)ws, st);
         if (rc != SPIRAL_OK) return rc;
     } else {
         conv_wgrad_simt(x, dy, dw, B, H, Cin, Cout, (char *)ws, st);

@@ -9,11 +9,11 @@ namespace spiral {
 // op: 0 forward, 1 dgrad, 2 wgrad
 bool conv_tc_supported(int op, int B, int H, int Cin, int Cout);
 size_t conv_tc_workspace_bytes(int B, int H, int Cin, int Cout);
-int conv_tc_forward(const float *x, const float *w, float *y, int B, int H, int Cin, int Cout, bool x3, char *ws,
+int conv_tc_forward(const float *x, const float *w, float *y, int B, int H, int Cin, int Cout, int ns, char *ws,
                     cudaStream_t st);
-int conv_tc_dgrad(const float *dy, const float *w, float *dx, int B, int H, int Cin, int Cout, bool x3, char *ws,
+int conv_tc_dgrad(const float *dy, const float *w, float *dx, int B, int H, int Cin, int Cout, int ns, char *ws,
                   cudaStream_t st);
-int conv_tc_wgrad(const float *x, const float *dy, float *dw, int B, int H, int Cin, int Cout, bool x3, char *ws,
+int conv_tc_wgrad(const float *x, const float *dy, float *dw, int B, int H, int Cin, int Cout, int ns, char *ws,
                   cudaStream_t st);
 
 }  // namespace spiral

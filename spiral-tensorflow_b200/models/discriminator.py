@@ -16,7 +16,7 @@ import torch
 from .. import _native as N
 from . import conv_ops
 
-PRECISIONS = {"fp32": 0, "bf16x3": 1, "bf16": 2}
+PRECISIONS = {"fp32": 0, "bf16x3": 1, "bf16": 2, "bf16x6": 3}
 
 
 class Discriminator(object):
@@ -37,6 +37,8 @@ class Discriminator(object):
         self.batch_norm = bool(args.disc_batch_norm)
         self.max_batch = int(max_batch or max(getattr(args, "num_envs", 64), args.disc_batch_size))
         self.precision = PRECISIONS[getattr(args, "disc_precision", "fp32")]
+        gp = getattr(args, "disc_grad_precision", "auto")
+        self.grad_precision = (3 if self.precision != 0 else 0) if gp == "auto" else PRECISIONS[gp]
 
         self.params = self._init_params(seed)
         self.var_list = list(self.params.values())
@@ -138,9 +140,8 @@ class Discriminator(object):
     def logits_fn(self, x_normed):
         """Differentiable D on already-normalised NHWC input; convolutions and all their gradients
         run on libspiral_b200.so (models/conv_ops.py)."""
-        prec = 0 if self.precision == 0 else self.precision
         return conv_ops.disc_forward_native(self.params, x_normed, self.layer_num, self.batch_norm,
-                                            normalize=False, precision=prec)
+                                            normalize=False, precision=self.grad_precision)
 
     def wgan_gp_loss(self, fake, real, alpha, wgan_lambda=None):
         """reference :97-122 (build_optim): critic + lambda * gradient penalty, the penalty on the

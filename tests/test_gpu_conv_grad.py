@@ -35,6 +35,7 @@ SHAPES = [  # B, H, Cin, Cout, precision
     (3, 8, 3, 8, 0), (2, 16, 16, 24, 0), (5, 2, 40, 130, 0), (2, 64, 1, 8, 0), (2, 4, 64, 128, 0),
     (4, 32, 64, 128, 1), (9, 16, 128, 256, 1), (40, 4, 512, 1024, 1), (70, 2, 1024, 2048, 1),
     (3, 64, 3, 64, 1), (3, 64, 6, 64, 1), (4, 8, 256, 512, 2),
+    (4, 32, 64, 128, 3), (9, 16, 128, 256, 3), (40, 4, 512, 1024, 3), (70, 2, 1024, 2048, 3), (3, 64, 3, 64, 3),
 ]
 
 
@@ -49,7 +50,9 @@ def test_conv_forward_dgrad_wgrad_match_float64(B, H, Cin, Cout, prec):
     y_ref = _ref_conv(xr, wr)
     dx_ref, dw_ref = torch.autograd.grad((y_ref * dy).sum(), (xr, wr))
     xc, wc, dyc = x.float().cuda(), w.float().cuda(), dy.float().cuda()
-    tol = 2e-2 if prec == 2 else 1e-4
+    # bf16x6: fp32-exact products, four TMEM accumulators against the tensor core's truncating accumulation
+    # (measured <= 5e-6, better than the fp32 SIMT kernels)
+    tol = {0: 1e-4, 1: 1e-4, 2: 2e-2, 3: 1e-5}[prec]
     assert _rel(ops.conv_forward(xc, wc, prec).cpu(), y_ref.detach()) < tol
     assert _rel(ops.conv_dgrad(dyc, wc, prec).cpu(), dx_ref) < tol
     assert _rel(ops.conv_wgrad(xc, dyc, prec).cpu(), dw_ref) < tol
@@ -81,7 +84,8 @@ def test_conv_autograd_first_and_second_order():
 
 
 @pytest.mark.parametrize("C,dd,bn,B,prec,cond", [(1, 8, True, 6, "fp32", False), (3, 8, False, 5, "fp32", False),
-                                                 (1, 8, True, 4, "fp32", True), (3, 64, True, 8, "bf16x3", False)])
+                                                 (1, 8, True, 4, "fp32", True), (3, 64, True, 8, "bf16x3", False),
+                                                 (3, 64, True, 8, "bf16x6", False)])
 def test_wgan_gp_step_matches_oracle(C, dd, bn, B, prec, cond):
     """d_loss, critic, penalty and every parameter gradient of the WGAN-GP step vs the float64 oracle."""
     sp = _sp()
@@ -89,8 +93,8 @@ def test_wgan_gp_step_matches_oracle(C, dd, bn, B, prec, cond):
 
     from oracle import disc_oracle as do
     models = import_module(sp.__name__ + ".models")
-    argv = ["--color_channel", str(C), "--disc_dim", str(dd), "--disc_batch_norm", str(bn), "--disc_precision", prec,
-            "--loss", "l2" if cond else "gan"]
+    argv = ["--color_channel", str(C), "--disc_dim", str(dd), "--disc_batch_norm", str(bn), "--disc_precision",
+            "bf16x3" if prec == "bf16x6" else prec, "--disc_grad_precision", prec, "--loss", "l2" if cond else "gan"]
     args = sp.get_args(argv)
     w = do.init_weights(C * (2 if cond else 1), disc_dim=dd, batch_norm=bn, seed=5)
     D = models.Discriminator(args, None, [64, 64, C], norm_fn=lambda x: x, scope_name="global", max_batch=B)
@@ -124,10 +128,13 @@ def test_wgan_gp_step_matches_oracle(C, dd, bn, B, prec, cond):
         else:
             # The losses hold 1e-4 in both modes.  The gradient of the penalty through training-mode BN
             # at batch 4-8 is ill-conditioned (it amplifies operand round-off ~100x: plain bf16 is 20 % off):
-            # fp32 kernels stay within 1e-3 of the float64 oracle, the bf16x3 tensor-core split (16
-            # mantissa bits per operand) within 2e-2 in the l2 sense (measured 1e-3..1e-2, tools/grad_err_probe.py)
+            # fp32 kernels and the bf16x6 tensor-core split (24 operand bits) stay within 1e-3 of the float64
+            # oracle, the bf16x3 split (16 bits) within 2e-2 in the l2 sense (measured 1e-3..1e-2,
+            # tools/grad_err_probe.py)
             if prec == "fp32":
                 assert _rel(got, gref) < 1e-3, (k, _rel(got, gref))
+            elif prec == "bf16x6":
+                assert _rel(got, gref) < 2e-4, (k, _rel(got, gref))       # measured 1e-5 .. 2e-5
             else:
                 l2 = np.linalg.norm(got.astype(np.float64) - gref) / np.linalg.norm(gref)
                 assert l2 < 2e-2, (k, l2)

@@ -19,8 +19,9 @@ def canvases():
 fake, real = canvases(), canvases()
 alpha = rng.rand(B, 1).astype(np.float32)
 want = do.d_loss(fake, real, alpha, w, batch_norm=True, wgan_lambda=20.0)
-for prec in ("fp32", "bf16x3", "bf16"):
-    args = sp.get_args(["--color_channel", str(C), "--disc_dim", str(dd), "--disc_precision", prec])
+for prec in ("fp32", "bf16x6", "bf16x3", "bf16"):
+    args = sp.get_args(["--color_channel", str(C), "--disc_dim", str(dd), "--disc_precision", "bf16x3" if prec == "bf16x6" else prec,
+                        "--disc_grad_precision", prec])
     D = models.Discriminator(args, None, [64, 64, C], norm_fn=lambda x: x, scope_name="global", max_batch=B)
     D.load_numpy(w)
     for p in D.params.values():
