@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define SPIRAL_ABI_VERSION 1
+#define SPIRAL_ABI_VERSION 2
 
 #define SPIRAL_OK 0
 #define SPIRAL_EINVAL (-1)      /* bad argument / unsupported configuration */
@@ -247,9 +247,12 @@ int spiral_conv_wgrad(const float *x_dev, const float *dy_dev, float *dw_dev, in
 /*           env step (policy.py:302-303)                               */
 /* ------------------------------------------------------------------ */
 /* logits f32[rows, n] -> out_idx i32[rows] ~ softmax(logits).  Gumbel-max over Philox4x32-10
- * uniforms: key = seed, counter = (class / 4, row, offset); a (seed, offset) pair must not be reused. */
+ * uniforms: key = seed, counter = (class / 4, row, offset + *offset_dev); a (seed, offset) pair must not be
+ * reused.  offset_dev (may be NULL) is a device-resident call counter the caller increments, so that a captured
+ * CUDA graph draws fresh numbers on every replay. */
 int spiral_categorical_sample(const float *logits_dev, int32_t rows, int32_t n, uint64_t seed,
-                              uint64_t offset, int32_t *out_idx_dev, void *stream);
+                              uint64_t offset, const uint64_t *offset_dev, int32_t *out_idx_dev,
+                              void *stream);
 /* test hook: one Philox4x32-10 block; ctr_key6 is a HOST array {c0,c1,c2,c3,k0,k1} */
 int spiral_debug_philox(const uint32_t *ctr_key6_host, uint32_t *out4_dev, void *stream);
 

@@ -14,7 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.environ.get("SPIRAL_B200_LIB") or os.path.join(CSRC, "libspiral_b200.so")   # override: tuning builds
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 MAX_POINTS, MAX_TABLE, MAX_L, TILE = 4, 8, 64, 64
 BRUSH_STATE_FLOATS, ENV_STATE_DOUBLES, DAB_FLOATS = 16, 16, 8
 DYN_NAMES = ["opaque", "opaque_multiply", "radius_logarithmic", "hardness", "radius_by_random",
@@ -93,7 +93,7 @@ SYMBOLS = {
     "spiral_disc_workspace_bytes": (C.c_int64, [_vp, C.c_int32]),
     "spiral_disc_load_weights": (C.c_int, [_vp, C.POINTER(SpiralDiscWeights), _vp, _vp]),
     "spiral_disc_forward": (C.c_int, [_vp, _vp, C.c_int32, _vp, _vp, _vp, _vp, _vp]),
-    "spiral_categorical_sample": (C.c_int, [_vp, C.c_int32, C.c_int32, C.c_uint64, C.c_uint64, _vp, _vp]),
+    "spiral_categorical_sample": (C.c_int, [_vp, C.c_int32, C.c_int32, C.c_uint64, C.c_uint64, _vp, _vp, _vp]),
     "spiral_debug_philox": (C.c_int, [C.POINTER(C.c_uint32), _vp, _vp]),
     "spiral_grad_global_norm": (C.c_int, [C.POINTER(_vp), C.POINTER(C.c_int64), C.c_int32, _vp, _vp, _vp]),
     "spiral_adam_step": (C.c_int, [C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(C.c_int64),

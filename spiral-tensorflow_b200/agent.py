@@ -43,16 +43,63 @@ class Agent(object):
         self.rng = torch.Generator(device=self.device)
         self.rng.manual_seed(int(args.seed))
         self.world = dist_utils.dist.get_world_size() if dist_utils.dist.is_initialized() else 1
+        self._graph, self._graph_failed, self._g_out, self._g_target, self._g_z = None, False, {}, None, None
 
     # ------------------------------------------------------------------
     @torch.no_grad()
     def rollout(self):
-        """rl_utils.env_runner (rl_utils.py:185-238) for B canvases at once."""
+        """rl_utils.env_runner (rl_utils.py:185-238) for B canvases at once.  With ``--cuda_graphs`` (default) the
+        whole T-step episode -- reset, T x (policy.act, K4 sampling, K1 env.step, bookkeeping) -- is captured once
+        into a CUDA graph and replayed: at the reference's batch sizes the loop is launch-bound (about 150 small
+        kernels per step), the graph removes that overhead and the Python interpreter from the critical path."""
+        if not (getattr(self.args, "cuda_graphs", True) and self.device.type == "cuda") or self._graph_failed:
+            return self._finish_rollout(self._rollout_body(None, None))
+        env = self.env
+        if self._graph is None:
+            try:
+                self._capture_rollout()
+            except Exception as e:                       # capture is an optimisation: fall back to eager launches
+                self._graph_failed = True
+                self._graph = None
+                torch.cuda.synchronize()
+                import warnings
+                warnings.warn("CUDA-graph capture of the rollout failed (%s); running eagerly" % (e,))
+                return self._finish_rollout(self._rollout_body(None, None))
+        # fresh condition / latent into the graph's static inputs (drawn as env.reset does)
+        if self._g_target is not None:
+            self._g_target.copy_(env.get_random_target(num=env.num_envs))
+        if self._g_z is not None:
+            self._g_z.copy_(torch.rand(self._g_z.shape, generator=env._rng, device=self.device) - 0.5)
+        self._graph.replay()
+        env._step = env.episode_length
+        return self._finish_rollout(self._g_out, clone=True)
+
+    def _capture_rollout(self):
+        env, pi = self.env, self.policy
+        B = env.num_envs
+        self._g_target = env.get_random_target(num=B).clone() if env.conditional else None
+        self._g_z = None if env.conditional else torch.zeros((B, env.z_dim), device=self.device)
+        if getattr(pi, "_sample_counter_dev", None) is None:
+            pi._sample_counter_dev = torch.zeros((1,), dtype=torch.int64, device=self.device)
+        self._g_init_action = torch.as_tensor(env.initial_action, device=self.device).to(torch.int32).expand(B, -1).contiguous()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):                      # warm-up: lazy initialisation (function attributes, cuBLAS) outside capture
+            self._rollout_body(self._g_target, self._g_z)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self._g_out = self._rollout_body(self._g_target, self._g_z)
+        self._graph = g
+
+    def _rollout_body(self, target, z_in):
         env, pi, T, B = self.env, self.policy, self.env.episode_length, self.env.num_envs
-        state, condition, z = env.reset()
+        state, condition, z = env.reset(target=target, z=z_in)
         c, h = pi.get_initial_features(B)
         features0 = torch.stack([c, h], 1)
-        last_action = torch.as_tensor(env.initial_action, device=self.device)
+        last_action = self._g_init_action if getattr(self, "_g_init_action", None) is not None \
+            else torch.as_tensor(env.initial_action, device=self.device)
         states = torch.empty((B, T + 1) + tuple(state.shape[1:]), device=self.device)
         actions = torch.empty((B, T, len(env.acs)), dtype=torch.int32, device=self.device)
         rewards = torch.zeros((B, T), device=self.device)
@@ -72,8 +119,13 @@ class Agent(object):
             out["conditions"] = condition.unsqueeze(1).expand((B, T) + tuple(condition.shape[1:]))
         else:
             out["z"] = z.unsqueeze(1).expand(B, T, z.shape[-1])
+        return out
+
+    def _finish_rollout(self, out, clone=False):
+        if clone:                                         # the graph's static buffers are overwritten by the next replay
+            out = {k: (v.clone() if isinstance(v, torch.Tensor) else v) for k, v in out.items()}
         if self.gan:
-            self.replay.push(states[:, T])
+            self.replay.push(out["states"][:, self.env.episode_length])
         return out
 
     def train_policy(self, rollout):

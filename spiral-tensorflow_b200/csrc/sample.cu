@@ -32,9 +32,11 @@ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t
 }
 
 __global__ void __launch_bounds__(128)
-categorical_sample_kernel(const float *__restrict__ logits, int rows, int n, uint32_t k0, uint32_t k1, uint32_t off_lo,
-                          uint32_t off_hi, int32_t *__restrict__ out)
+categorical_sample_kernel(const float *__restrict__ logits, int rows, int n, uint32_t k0, uint32_t k1, uint64_t offset,
+                          const uint64_t *__restrict__ offset_dev, int32_t *__restrict__ out)
 {
+    if (offset_dev) offset += *offset_dev;                 // device-resident call counter (CUDA-graph replays)
+    const uint32_t off_lo = (uint32_t)offset, off_hi = (uint32_t)(offset >> 32);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int row = blockIdx.x * 4 + warp;
     if (row >= rows) return;
@@ -73,12 +75,12 @@ __global__ void philox_debug_kernel(uint32_t c0, uint32_t c1, uint32_t c2, uint3
 }  // namespace spiral
 
 extern "C" int spiral_categorical_sample(const float *logits, int32_t rows, int32_t n, uint64_t seed, uint64_t offset,
-                                         int32_t *out_idx, void *stream)
+                                         const uint64_t *offset_dev, int32_t *out_idx, void *stream)
 {
     SPIRAL_REQUIRE(logits); SPIRAL_REQUIRE(out_idx);
     if (rows <= 0 || n <= 0) return spiral_set_error(SPIRAL_EINVAL, "categorical_sample: rows and n must be positive");
     spiral::categorical_sample_kernel<<<(rows + 3) / 4, 128, 0, (cudaStream_t)stream>>>(
-        logits, rows, n, (uint32_t)seed, (uint32_t)(seed >> 32), (uint32_t)offset, (uint32_t)(offset >> 32), out_idx);
+        logits, rows, n, (uint32_t)seed, (uint32_t)(seed >> 32), offset, offset_dev, out_idx);
     const cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? SPIRAL_OK : spiral_cuda_error(e, "spiral_categorical_sample");
 }

@@ -163,10 +163,12 @@ class MNIST(Environment):
             pass
 
     # ------------------------------------------------------------------
-    def reset(self):
-        """mnist.py:81-105 for every canvas: white surface, fresh Brush (RNG re-seeded), step 0."""
+    def reset(self, target=None, z=None):
+        """mnist.py:81-105 for every canvas: white surface, fresh Brush (RNG re-seeded), step 0.
+        ``target`` / ``z`` may be handed in (static buffers of a captured CUDA graph); otherwise they are
+        drawn here as the reference does (:84-87, :100-103)."""
         if self.conditional:
-            self.random_target = self.get_random_target(num=self.num_envs)
+            self.random_target = self.get_random_target(num=self.num_envs) if target is None else target
         else:
             self.random_target = None
         N.check(self._lib.spiral_env_reset(self._handle, N.ptr(self.canvas), N.ptr(self.brush_state),
@@ -176,7 +178,7 @@ class MNIST(Environment):
         if self.args.conditional:
             self.z = None
         else:
-            self.z = torch.rand((self.num_envs, self.z_dim), generator=self._rng, device=self.device) - 0.5
+            self.z = (torch.rand((self.num_envs, self.z_dim), generator=self._rng, device=self.device) - 0.5) if z is None else z
         return self.state, self.random_target, self.z
 
     def _to_actions(self, acs):

@@ -103,11 +103,19 @@ def categorical_sample(logits, generator=None, owner=None):
     lg = logits.to(torch.float32).contiguous()
     seed = int(generator.initial_seed()) if generator is not None else int(torch.initial_seed())
     holder = owner if owner is not None else categorical_sample
+    out = torch.empty((lg.shape[0],), dtype=torch.int32, device=lg.device)
+    ctr = getattr(holder, "_sample_counter_dev", None)
+    if ctr is not None:
+        # device-resident call counter: graph-capturable, every replay draws fresh numbers
+        N.check(N.lib().spiral_categorical_sample(N.ptr(lg), lg.shape[0], lg.shape[1], C.c_uint64(seed & (2 ** 64 - 1)),
+                                                  C.c_uint64(0), N.ptr(ctr), N.ptr(out), N.stream_ptr()),
+                "spiral_categorical_sample")
+        ctr.add_(1)
+        return out
     off = getattr(holder, "_sample_offset", 0)
     setattr(holder, "_sample_offset", off + 1)
-    out = torch.empty((lg.shape[0],), dtype=torch.int32, device=lg.device)
     N.check(N.lib().spiral_categorical_sample(N.ptr(lg), lg.shape[0], lg.shape[1], C.c_uint64(seed & (2 ** 64 - 1)),
-                                              C.c_uint64(off), N.ptr(out), N.stream_ptr()), "spiral_categorical_sample")
+                                              C.c_uint64(off), None, N.ptr(out), N.stream_ptr()), "spiral_categorical_sample")
     return out
 
 

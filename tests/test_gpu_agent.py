@@ -103,3 +103,31 @@ def test_fused_clip_adam_matches_reference_formulas():
         assert abs(float(got_norm) - float(want_norm)) <= 1e-5 * float(want_norm)
         for p, q in zip(pa, pb):
             assert torch.allclose(p, q, rtol=1e-5, atol=1e-7)
+
+
+def test_cuda_graph_rollout_matches_the_env_and_draws_fresh_actions():
+    """The captured rollout (policy.act + K4 sampling + K1 env.step x T in one CUDA graph) must (1) record a
+    trajectory that the env reproduces from the recorded actions alone, (2) draw new random numbers on every
+    replay, (3) agree in distribution with the eager loop."""
+    import spiral_b200 as sp
+    from importlib import import_module
+    agent_mod = import_module(sp.__name__ + ".agent")
+    args = sp.get_args(["--env", "simple_mnist", "--color_channel", "1", "--episode_length", "4", "--loss", "gan",
+                        "--disc_dim", "8", "--disc_precision", "fp32", "--cuda_graphs", "True"])
+    B = 16
+    env = sp.create_env(args, num_envs=B)
+    ag = agent_mod.Agent(args, env)
+    ro1 = ag.rollout()
+    assert ag._graph is not None and not ag._graph_failed, "the rollout was not captured"
+    ro2 = ag.rollout()
+    assert not torch.equal(ro1["actions"], ro2["actions"]), "replay reused the random numbers"
+    assert not torch.equal(ro1["z"], ro2["z"])
+    for ro in (ro1, ro2):
+        env.reset()
+        for t in range(4):
+            assert torch.equal(env.state, ro["states"][:, t])
+            env.step(ro["actions"][:, t])
+        assert torch.equal(env.state, ro["states"][:, 4])
+        assert int(ro["actions"].min()) >= 0
+    m = ag.train_policy(ro2)
+    assert torch.isfinite(m["model/total_loss"])

@@ -17,7 +17,7 @@ def _sample(logits, seed, offset):
     N = _sp()._native
     lg = torch.tensor(logits, device="cuda")
     out = torch.empty((lg.shape[0],), dtype=torch.int32, device="cuda")
-    N.check(N.lib().spiral_categorical_sample(N.ptr(lg), lg.shape[0], lg.shape[1], C.c_uint64(seed), C.c_uint64(offset),
+    N.check(N.lib().spiral_categorical_sample(N.ptr(lg), lg.shape[0], lg.shape[1], C.c_uint64(seed), C.c_uint64(offset), None,
                                               N.ptr(out), N.stream_ptr()))
     return out.cpu().numpy()
 
@@ -62,3 +62,16 @@ def test_sampler_distribution_is_softmax():
     # chi-square with n-1 = 5 degrees of freedom: 99.9 % quantile = 20.5
     chi2 = rows * ((freq - p) ** 2 / p).sum()
     assert chi2 < 20.5, (chi2, freq, p)
+
+
+def test_device_offset_counter_equals_host_offset():
+    """The device-resident call counter (CUDA-graph replays) addresses the same Philox stream as the host offset."""
+    N = _sp()._native
+    rng = np.random.RandomState(3)
+    logits = (rng.randn(40, 512) * 2).astype(np.float32)
+    lg = torch.tensor(logits, device="cuda")
+    out = torch.empty((40,), dtype=torch.int32, device="cuda")
+    ctr = torch.tensor([5], dtype=torch.int64, device="cuda")
+    N.check(N.lib().spiral_categorical_sample(N.ptr(lg), 40, 512, C.c_uint64(11), C.c_uint64(2), N.ptr(ctr), N.ptr(out),
+                                              N.stream_ptr()))
+    assert (out.cpu().numpy() == _sample(logits, 11, 7)).all()
