@@ -206,12 +206,13 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
 
-    def measure(B):
+    def measure(B, jump=None):
         T = args.episode_length
+        jump = args.jump if jump is None else jump
         C, L = WORKLOAD["color_channel"], WORKLOAD["location_size"]
         a = sp.get_args(["--env", WORKLOAD["env"], "--location_size", str(L), "--color_channel", str(C),
                          "--episode_length", str(T), "--loss", "gan", "--disc_dim", str(WORKLOAD["disc_dim"]),
-                         "--disc_precision", args.disc_precision, "--jump", args.jump, "--seed", str(123 + rank)])
+                         "--disc_precision", args.disc_precision, "--jump", jump, "--seed", str(123 + rank)])
         env = sp.create_env(a, num_envs=B, device=dev)
         disc = models.Discriminator(a, None, [64, 64, C], norm_fn=env.norm, scope_name="global", device=dev, max_batch=B)
         K = len(env.acs)
@@ -349,7 +350,7 @@ def run_ours(args):
                    higher_is_better=True, scaling="weak", vs_baseline=None, dtype="fix15/u16 render, f32 reward+loss",
                    data="synthetic",
                    config=dict(WORKLOAD, canvases_per_gpu=B, episode_length=T, heads=dict(zip(env.acs, env.head_sizes)),
-                               jump=args.jump, disc_precision=args.disc_precision, parallelism="dp%d (actor partitions, no data-path collective)" % world,
+                               jump=jump, disc_precision=args.disc_precision, parallelism="dp%d (actor partitions, no data-path collective)" % world,
                                l2="working set %.0f MiB per GPU > 126 MiB L2 (inputs larger than L2)" % footprint),
                    e2e=dict(value=e2e_value, unit="env-steps/s", h2d_bytes_per_step=int(B * T * K * 4 + 2 * B * T * 4),
                             d2h_bytes_per_step=int((B + 4) * 4), ms_per_step=ms_e2e / args.steps),
@@ -440,6 +441,12 @@ def run_ours(args):
             sec, _ = measure(nb)
             out[key] = {k: sec[k] for k in ("value", "unit", "ms_per_step", "e2e", "kernel_ms_per_step")}
             out[key]["config"] = desc
+        if args.jump == "True":
+            # the jump head is uniform over {0,1}, so half of the steps paint nothing; --jump=False is
+            # the worst-case paint load (every step after the first draws a stroke)
+            sec, _ = measure(16384, jump="False")
+            out["rgb64_b16384_nojump"] = {k: sec[k] for k in ("value", "unit", "ms_per_step", "kernel_ms_per_step")}
+            out["rgb64_b16384_nojump"]["config"] = "16384 canvases per GPU, --jump=False (worst-case paint load)"
         out["disc_train"] = disc_train_step(args, dev, C)
         out["agent_loop"] = agent_loop(args, dev)
     if world == 1 and not args.no_cpu_baseline:

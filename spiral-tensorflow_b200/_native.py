@@ -8,6 +8,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import shutil
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
@@ -122,6 +123,9 @@ def lib():
     global _lib
     if _lib is not None:
         return _lib
+    if not os.path.exists(LIB_PATH) and not os.environ.get("SPIRAL_B200_LIB") and shutil.which(
+            os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")):
+        build()                      # in-tree build (csrc/build.sh, sm_100a); raises loudly when nvcc fails
     if not os.path.exists(LIB_PATH):
         raise RuntimeError(
             "libspiral_b200.so is not built (%s). Run `python -c 'import __graft_entry__ as g; "
