@@ -22,6 +22,7 @@
 #include "tc_ptx.cuh"
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -41,6 +42,7 @@ struct ConvTcParams {
     int bw, bh, bb;           // A box: Wo pixels, rows, images (bw*bh*bb == 128)
     int M;                    // B * Ho * Wo
     int x3;                   // 1: hi*hi + hi*lo + lo*hi ; 0: hi*hi only
+    int mt, nt;               // output tiles per work item along M / N: (1,1), (2,1) or (1,2)
 };
 
 // Persistent: gridDim.x CTAs (one per SM) walk the (m_tile, n_tile) space; the TMEM accumulator is double
@@ -71,6 +73,12 @@ __device__ __forceinline__ uint32_t conv_tap_mask(const ConvTcParams &p, int Ho,
     return tap_mask;
 }
 
+// Work item = mt x nt output tiles that share operands: two n-tiles reuse one A tile (Cout >= 256), or two
+// m-tiles reuse one W tile (Cout = 128).  With the bf16x3 split a single 128x128 tile needs 64 KB of operands
+// per 12 MMAs (0.42 us of tensor time) -- about 155 GB/s per SM, which three 64 KB stages in flight cannot
+// sustain against ~1 us of L2 latency (ncu, round 1: tensor pipe 64-83 % busy).  A pair needs 96 KB per 24
+// MMAs: 25 % fewer bytes per flop and twice the tensor time per stage to cover the same latency.
+template <int mt, int nt>
 __global__ void __launch_bounds__(kTcThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_constant__ CUtensorMap map_a_lo,
                const __grid_constant__ CUtensorMap map_w_hi, const __grid_constant__ CUtensorMap map_w_lo,
@@ -81,8 +89,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     // 1024-byte alignment for the 128-byte swizzle atoms
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t *gen_base = smem_raw + (base - smem_u32(smem_raw));
-    const uint32_t bar_base = base + kStages * kStageBytes;
-    uint64_t *bar_gen = reinterpret_cast<uint64_t *>(gen_base + kStages * kStageBytes);
+    constexpr int n_stages = (mt + nt == 2) ? 3 : 2;
+    constexpr uint32_t stage_bytes = (uint32_t)(mt + nt) * 2u * kTileBytes;   // {A_hi, A_lo} x mt, {W_hi, W_lo} x nt
+    constexpr uint32_t kRing = kStages * kStageBytes;                          // 192 KB either way
+    const uint32_t bar_base = base + kRing;
+    uint64_t *bar_gen = reinterpret_cast<uint64_t *>(gen_base + kRing);
     const uint32_t full0 = bar_base, empty0 = bar_base + 8 * kStages;
     const uint32_t acc_full0 = bar_base + 16 * kStages, acc_empty0 = acc_full0 + 16;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bar_gen + 2 * kStages + 4);
@@ -92,11 +103,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int Ho = p.H / 2;
     const int m_tiles = (p.M + kBM - 1) / kBM, n_tiles = p.Cout / kBN;
-    const int n_work = m_tiles * n_tiles;
+    const int m_groups = (m_tiles + mt - 1) / mt, n_groups = n_tiles / nt;
+    const int n_work = m_groups * n_groups;
     const int chunks = p.Cin / kBK;
+    constexpr int per_acc = mt * nt;          // accumulators per buffer
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kStages; s++) {
+        for (int s = 0; s < n_stages; s++) {
             mbar_init(full0 + 8 * s, 1);
             mbar_init(empty0 + 8 * s, 1);
         }
@@ -107,8 +120,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
-        // TMEM: 128 lanes x 2 accumulators x kBN fp32 columns
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(2 * kBN) : "memory");
+        // TMEM: 128 lanes x 2 buffers x (mt * nt <= 2) accumulators x kBN fp32 columns
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(4 * kBN) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     if (warp == 0 && lane == 0) {
@@ -122,32 +135,47 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
 
+    // union of the member tiles' tap masks (a tap that is pure padding for one member just loads zeros for it)
+    auto group_taps = [&](int mg, int &mt_here) -> uint32_t {
+        mt_here = min(mt, m_tiles - mg * mt);
+        uint32_t mask = 0;
+        for (int i = 0; i < mt_here; i++) {
+            const int m0 = (mg * mt + i) * kBM;
+            mask |= conv_tap_mask(p, Ho, (m0 % (Ho * Ho)) / Ho);
+        }
+        return mask;
+    };
+
     if (warp == 0) {
         // ===== TMA producer =====
         if (lane == 0) {
             int it = 0;
             for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
-                const int m_tile = w / n_tiles, n_tile = w % n_tiles;     // neighbouring CTAs share the A tile in L2
-                const int m0 = m_tile * kBM;
-                const int img0 = m0 / (Ho * Ho);
-                const int oy0 = (m0 % (Ho * Ho)) / Ho;
-                const uint32_t tap_mask = conv_tap_mask(p, Ho, oy0);
+                const int mg = w / n_groups, ng = w % n_groups;       // neighbouring CTAs share the A tiles in L2
+                int mt_here;
+                const uint32_t tap_mask = group_taps(mg, mt_here);
+                const uint32_t tiles_bytes = (uint32_t)(mt_here + nt) * (p.x3 ? 2u : 1u) * kTileBytes;
                 for (int tap = 0; tap < 25; tap++) {
                     if (!((tap_mask >> tap) & 1)) continue;
                     const int ky = tap / 5, kx = tap % 5;
                     for (int ch = 0; ch < chunks; ch++, it++) {
-                        const int s = it % kStages;
-                        if (it >= kStages) mbar_wait(empty0 + 8 * s, ((it / kStages) - 1) & 1);
+                        const int s = it % n_stages;
+                        if (it >= n_stages) mbar_wait(empty0 + 8 * s, ((it / n_stages) - 1) & 1);
                         const uint32_t full = full0 + 8 * s;
-                        const uint32_t stage = base + s * kStageBytes;
-                        mbar_expect_tx(full, p.x3 ? kStageBytes : 2 * kTileBytes);
+                        const uint32_t stage = base + s * stage_bytes;
+                        mbar_expect_tx(full, tiles_bytes);
                         const int c0 = ch * kBK;
-                        const int ix0 = kx - 1, iy0 = 2 * oy0 + ky - 1;
-                        tma_load_4d(stage, &map_a_hi, full, c0, ix0, iy0, img0);
-                        tma_load_2d(stage + 2 * kTileBytes, &map_w_hi, full, tap * p.Cin + c0, n_tile * kBN);
-                        if (p.x3) {
-                            tma_load_4d(stage + kTileBytes, &map_a_lo, full, c0, ix0, iy0, img0);
-                            tma_load_2d(stage + 3 * kTileBytes, &map_w_lo, full, tap * p.Cin + c0, n_tile * kBN);
+                        for (int i = 0; i < mt_here; i++) {
+                            const int m0 = (mg * mt + i) * kBM;
+                            const int img0 = m0 / (Ho * Ho), oy0 = (m0 % (Ho * Ho)) / Ho;
+                            const int ix0 = kx - 1, iy0 = 2 * oy0 + ky - 1;
+                            tma_load_4d(stage + (2 * i) * kTileBytes, &map_a_hi, full, c0, ix0, iy0, img0);
+                            if (p.x3) tma_load_4d(stage + (2 * i + 1) * kTileBytes, &map_a_lo, full, c0, ix0, iy0, img0);
+                        }
+                        for (int j = 0; j < nt; j++) {
+                            const int n0 = (ng * nt + j) * kBN;
+                            tma_load_2d(stage + (2 * mt + 2 * j) * kTileBytes, &map_w_hi, full, tap * p.Cin + c0, n0);
+                            if (p.x3) tma_load_2d(stage + (2 * mt + 2 * j + 1) * kTileBytes, &map_w_lo, full, tap * p.Cin + c0, n0);
                         }
                     }
                 }
@@ -159,36 +187,43 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
             constexpr uint32_t idesc = umma_idesc(kBM, kBN);
             int it = 0, tile_i = 0;
             for (int w = blockIdx.x; w < n_work; w += gridDim.x, tile_i++) {
-                const int m0 = (w / n_tiles) * kBM;
-                const int oy0 = (m0 % (Ho * Ho)) / Ho;
-                const int n_iter = __popc(conv_tap_mask(p, Ho, oy0)) * chunks;
+                int mt_here;
+                const int n_iter = __popc(group_taps(w / n_groups, mt_here)) * chunks;
                 const int b = tile_i & 1, use = tile_i >> 1;
-                if (use > 0) {                                    // the epilogue has drained this accumulator
+                if (use > 0) {                                    // the epilogue has drained this buffer
                     mbar_wait(acc_empty0 + 8 * b, (use - 1) & 1);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 }
-                const uint32_t tmem_acc = tmem_base + (uint32_t)(b * kBN);
-                for (int j = 0; j < n_iter; j++, it++) {
-                    const int s = it % kStages;
-                    mbar_wait(full0 + 8 * s, (it / kStages) & 1);
+                for (int j_it = 0; j_it < n_iter; j_it++, it++) {
+                    const int s = it % n_stages;
+                    mbar_wait(full0 + 8 * s, (it / n_stages) & 1);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    const uint32_t stage = base + s * kStageBytes;
-                    const uint64_t a_hi = umma_desc(stage), a_lo = umma_desc(stage + kTileBytes);
-                    const uint64_t w_hi = umma_desc(stage + 2 * kTileBytes), w_lo = umma_desc(stage + 3 * kTileBytes);
+                    const uint32_t stage = base + s * stage_bytes;
 #pragma unroll
-                    for (int k = 0; k < kBK / 16; k++) {
-                        const uint64_t adv = (uint64_t)((k * 32) >> 4);       // 16 bf16 = 32 bytes along K
-                        if (p.x3) {
-                            umma_bf16(tmem_acc, a_lo + adv, w_hi + adv, idesc, (j | k) != 0);
-                            umma_bf16(tmem_acc, a_hi + adv, w_lo + adv, idesc, 1);
-                            umma_bf16(tmem_acc, a_hi + adv, w_hi + adv, idesc, 1);
-                        } else {
-                            umma_bf16(tmem_acc, a_hi + adv, w_hi + adv, idesc, (j | k) != 0);
+                    for (int i = 0; i < mt; i++) {
+                        if (i >= mt_here) break;
+                        const uint64_t a_hi = umma_desc(stage + (2 * i) * kTileBytes), a_lo = umma_desc(stage + (2 * i + 1) * kTileBytes);
+#pragma unroll
+                        for (int j = 0; j < nt; j++) {
+                            const uint64_t w_hi = umma_desc(stage + (2 * mt + 2 * j) * kTileBytes);
+                            const uint64_t w_lo = umma_desc(stage + (2 * mt + 2 * j + 1) * kTileBytes);
+                            const uint32_t tmem_acc = tmem_base + (uint32_t)((b * per_acc + i * nt + j) * kBN);
+#pragma unroll
+                            for (int k = 0; k < kBK / 16; k++) {
+                                const uint64_t adv = (uint64_t)((k * 32) >> 4);       // 16 bf16 = 32 bytes along K
+                                if (p.x3) {
+                                    umma_bf16(tmem_acc, a_lo + adv, w_hi + adv, idesc, (j_it | k) != 0);
+                                    umma_bf16(tmem_acc, a_hi + adv, w_lo + adv, idesc, 1);
+                                    umma_bf16(tmem_acc, a_hi + adv, w_hi + adv, idesc, 1);
+                                } else {
+                                    umma_bf16(tmem_acc, a_hi + adv, w_hi + adv, idesc, (j_it | k) != 0);
+                                }
+                            }
                         }
                     }
                     umma_commit(empty0 + 8 * s);          // stage free once these MMAs have read it
                 }
-                umma_commit(acc_full0 + 8 * b);           // accumulator complete
+                umma_commit(acc_full0 + 8 * b);           // accumulators complete
             }
         }
     } else {
@@ -197,67 +232,107 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         const int et = threadIdx.x - 64;                  // 0..127 among the epilogue threads
         int tile_i = 0;
         for (int w = blockIdx.x; w < n_work; w += gridDim.x, tile_i++) {
-            const int m_tile = w / n_tiles, n_tile = w % n_tiles;
-            const int m0 = m_tile * kBM;
+            const int mg = w / n_groups, ng = w % n_groups;
+            const int mt_here = min(mt, m_tiles - mg * mt);
             const int b = tile_i & 1, use = tile_i >> 1;
             mbar_wait(acc_full0 + 8 * b, use & 1);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t tmem_acc = tmem_base + (uint32_t)(b * kBN);
-            const int row = q * 32 + lane;
-            const int m = m0 + row;
-            const bool row_ok = m < p.M;
-            float *orow = out + (size_t)m * p.Cout + (size_t)n_tile * kBN;
+            for (int i = 0; i < mt_here; i++) {
+                for (int j = 0; j < nt; j++) {
+                    const int m_tile = mg * mt + i, n_tile = ng * nt + j;
+                    const int m0 = m_tile * kBM;
+                    const uint32_t tmem_acc = tmem_base + (uint32_t)((b * per_acc + i * nt + j) * kBN);
+                    const int row = q * 32 + lane;
+                    const int m = m0 + row;
+                    const bool row_ok = m < p.M;
+                    float *orow = out + (size_t)m * p.Cout + (size_t)n_tile * kBN;
 #pragma unroll 1
-            for (int cb = 0; cb < kBN; cb += 32) {
-                float v[32];
-                tmem_ld32(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)cb, v);
+                    for (int cb = 0; cb < kBN; cb += 32) {
+                        float v[32];
+                        tmem_ld32(tmem_acc + ((uint32_t)(q * 32) << 16) + (uint32_t)cb, v);
 #pragma unroll
-                for (int j = 0; j < 32; j++) v[j] = row_ok ? v[j] + (bias ? __ldg(bias + n_tile * kBN + cb + j) : 0.0f) : 0.0f;
-                if (row_ok) {
+                        for (int jj = 0; jj < 32; jj++)
+                            v[jj] = row_ok ? v[jj] + (bias ? __ldg(bias + n_tile * kBN + cb + jj) : 0.0f) : 0.0f;
+                        if (row_ok) {
 #pragma unroll
-                    for (int j = 0; j < 32; j += 4)
-                        *reinterpret_cast<float4 *>(orow + cb + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-                }
-                if (bn_partial) {
-                    // column sums over this warp's 32 rows via an smem transpose
+                            for (int jj = 0; jj < 32; jj += 4)
+                                *reinterpret_cast<float4 *>(orow + cb + jj) = make_float4(v[jj], v[jj + 1], v[jj + 2], v[jj + 3]);
+                        }
+                        if (bn_partial) {
+                            // column sums over this warp's 32 rows via an smem transpose
 #pragma unroll
-                    for (int j = 0; j < 32; j++) s_tr[q][lane][j] = v[j];
-                    __syncwarp();
-                    float s = 0.f, sq = 0.f;
+                            for (int jj = 0; jj < 32; jj++) s_tr[q][lane][jj] = v[jj];
+                            __syncwarp();
+                            float sm = 0.f, sq = 0.f;
 #pragma unroll
-                    for (int r = 0; r < 32; r++) {
-                        const float x = s_tr[q][r][lane];
-                        s += x;
-                        sq += x * x;
+                            for (int r = 0; r < 32; r++) {
+                                const float x = s_tr[q][r][lane];
+                                sm += x;
+                                sq += x * x;
+                            }
+                            s_red[q][0][cb + lane] = sm;
+                            s_red[q][1][cb + lane] = sq;
+                            __syncwarp();
+                        }
                     }
-                    s_red[q][0][cb + lane] = s;
-                    s_red[q][1][cb + lane] = sq;
-                    __syncwarp();
+                    if (bn_partial) {
+                        epilogue_bar_sync();
+                        if (et < kBN) {
+                            const int c = et;
+                            const float sm = (s_red[0][0][c] + s_red[1][0][c]) + (s_red[2][0][c] + s_red[3][0][c]);
+                            const float sq = (s_red[0][1][c] + s_red[1][1][c]) + (s_red[2][1][c] + s_red[3][1][c]);
+                            float *pp = bn_partial + ((size_t)m_tile * p.Cout + n_tile * kBN + c) * 2;
+                            pp[0] = sm;
+                            pp[1] = sq;
+                        }
+                        epilogue_bar_sync();                      // s_red is free for the next tile
+                    }
                 }
             }
-            // this warp's TMEM reads are complete (tcgen05.wait::ld inside tmem_ld32): release the accumulator
+            // this warp's TMEM reads are complete (tcgen05.wait::ld inside tmem_ld32): release the buffer
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             if (lane == 0) mbar_arrive(acc_empty0 + 8 * b);
-            if (bn_partial) {
-                epilogue_bar_sync();
-                if (et < kBN) {
-                    const int c = et;
-                    const float s = (s_red[0][0][c] + s_red[1][0][c]) + (s_red[2][0][c] + s_red[3][0][c]);
-                    const float sq = (s_red[0][1][c] + s_red[1][1][c]) + (s_red[2][1][c] + s_red[3][1][c]);
-                    float *pp = bn_partial + ((size_t)m_tile * p.Cout + n_tile * kBN + c) * 2;
-                    pp[0] = s;
-                    pp[1] = sq;
-                }
-                epilogue_bar_sync();                      // s_red is free for the next tile
-            }
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 1) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(2 * kBN) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(4 * kBN) : "memory");
     }
+}
+
+static void conv_tc_launch(dim3 grid, cudaStream_t st, const CUtensorMap &ma_hi, const CUtensorMap &ma_lo, const CUtensorMap &mw_hi,
+                           const CUtensorMap &mw_lo, const ConvTcParams &p, const float *bias, float *out, float *part)
+{
+    if (p.nt == 2) conv_tc_kernel<1, 2><<<grid, kTcThreads, kSmemBytes, st>>>(ma_hi, ma_lo, mw_hi, mw_lo, p, bias, out, part);
+    else if (p.mt == 2) conv_tc_kernel<2, 1><<<grid, kTcThreads, kSmemBytes, st>>>(ma_hi, ma_lo, mw_hi, mw_lo, p, bias, out, part);
+    else conv_tc_kernel<1, 1><<<grid, kTcThreads, kSmemBytes, st>>>(ma_hi, ma_lo, mw_hi, mw_lo, p, bias, out, part);
+}
+
+static cudaError_t conv_tc_set_smem()
+{
+    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(conv_tc_kernel<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+    return e;
+}
+
+// tiles per work item: two n-tiles share A when Cout >= 256, two m-tiles share W when Cout = 128 -- as long as
+// enough work items remain to fill the 148 SMs (SPIRAL_CONV_PAIR=0 disables: profiling)
+static void conv_tc_pairing(ConvTcParams *p, int mtiles)
+{
+    p->mt = 1;
+    p->nt = 1;
+    static int enabled = -1;
+    if (enabled < 0) {
+        const char *e = getenv("SPIRAL_CONV_PAIR");
+        enabled = e ? (atoi(e) != 0) : 1;
+    }
+    if (!enabled) return;
+    const int ntiles = p->Cout / kBN;
+    if (ntiles >= 2 && (ntiles % 2) == 0 && (long long)mtiles * (ntiles / 2) >= 148) p->nt = 2;
+    else if (mtiles >= 2 * 148) p->mt = 2;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -368,7 +443,7 @@ int disc_tc_init(SpiralDisc *d)
         return spiral_set_error(SPIRAL_ECUDA, "cuTensorMapEncodeTiled is not available from the driver");
     }
     t->first_tc_layer = 1;
-    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+    cudaError_t e = conv_tc_set_smem();
     if (e != cudaSuccess) {
         delete t;
         return spiral_cuda_error(e, "cudaFuncSetAttribute(conv_tc_kernel)");
@@ -480,10 +555,11 @@ int disc_tc_forward(SpiralDisc *d, const float *x, int batch, float *logits, flo
         const int mtiles = (p.M + kBM - 1) / kBM;
         const bool bn = d->cfg.batch_norm != 0;
         float *part = (float *)(ws + pl.part_off[l]);
-        const int n_work = mtiles * (Cout / kBN);
+        conv_tc_pairing(&p, mtiles);
+        const int n_work = ((mtiles + p.mt - 1) / p.mt) * ((Cout / kBN) / p.nt);
         dim3 grid(n_work < 148 ? n_work : 148);
-        conv_tc_kernel<<<grid, kTcThreads, kSmemBytes, st>>>(ma_hi, ma_lo, mw_hi, mw_lo, p, (const float *)W.conv_b[l],
-                                                            (float *)(ws + pl.act_off[l]), bn ? part : nullptr);
+        conv_tc_launch(grid, st, ma_hi, ma_lo, mw_hi, mw_lo, p, (const float *)W.conv_b[l], (float *)(ws + pl.act_off[l]),
+                       bn ? part : nullptr);
         float *scale = (float *)(ws + pl.scale_off[l]), *shift = (float *)(ws + pl.shift_off[l]);
         if (bn) {
             launch_bn_finalize(part, mtiles, Cout, (double)batch * Ho * Ho, (const float *)W.bn_gamma[l],
@@ -518,7 +594,7 @@ int conv_tc_layer(void *a_hi, void *a_lo, void *w_hi, void *w_lo, float *out, in
     t.first_tc_layer = 1;
     if (!t.encode) return spiral_set_error(SPIRAL_ECUDA, "cuTensorMapEncodeTiled is not available from the driver");
     if (!attr_set) {
-        const cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+        const cudaError_t e = conv_tc_set_smem();
         if (e != cudaSuccess) return spiral_cuda_error(e, "cudaFuncSetAttribute(conv_tc_kernel)");
         attr_set = true;
     }
@@ -533,9 +609,11 @@ int conv_tc_layer(void *a_hi, void *a_lo, void *w_hi, void *w_lo, float *out, in
     er |= encode_w_map(&t, &mw_hi, w_hi, 25 * Cin, Cout);
     er |= encode_w_map(&t, &mw_lo, w_lo, 25 * Cin, Cout);
     if (er) return spiral_set_error(SPIRAL_ECUDA, "cuTensorMapEncodeTiled failed (CUresult %d)", er);
-    const int n_work = ((p.M + kBM - 1) / kBM) * (Cout / kBN);
+    const int mtiles = (p.M + kBM - 1) / kBM;
+    conv_tc_pairing(&p, mtiles);
+    const int n_work = ((mtiles + p.mt - 1) / p.mt) * ((Cout / kBN) / p.nt);
     dim3 grid(n_work < 148 ? n_work : 148);
-    conv_tc_kernel<<<grid, kTcThreads, kSmemBytes, st>>>(ma_hi, ma_lo, mw_hi, mw_lo, p, nullptr, out, nullptr);
+    conv_tc_launch(grid, st, ma_hi, ma_lo, mw_hi, mw_lo, p, nullptr, out, nullptr);
     return SPIRAL_OK;
 }
 
