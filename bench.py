@@ -199,8 +199,6 @@ def run_ours(args):
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
-    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-        os.environ["NCCL_DEBUG"] = "WARN"          # keep stdout to the one JSON line (NCCL prints its version there)
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -451,7 +449,7 @@ def run_ours(args):
         out["agent_loop"] = agent_loop(args, dev)
     if world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline(args, acs_list, head_list, C, L, T, WORKLOAD["disc_dim"])
-    print(json.dumps(out))
+    _emit(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
 
@@ -490,10 +488,19 @@ def run_reference(args):
                cpu_baseline=dict(value=value, unit="env-steps/s", cores=cores, kind="port", sample=sample),
                e2e=dict(value=value, unit="env-steps/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0),
                seconds=parts)
-    print(json.dumps(out))
+    _emit(json.dumps(out))
+
+
+def _emit(line):
+    os.write(_REAL_STDOUT, (line + "\n").encode())
 
 
 if __name__ == "__main__":
+    # stdout carries exactly ONE JSON line: libraries that chat on fd 1 (NCCL prints its version banner there when a
+    # communicator is created) are sent to stderr for the whole run, the result goes to the saved descriptor
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     a = parse()
     if a.impl == "reference":
         run_reference(a)
