@@ -244,3 +244,16 @@ def test_bench_reference_arm_prints_one_contract_line():
     out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1",
                           "--warmup", "0"], capture_output=True, text=True, timeout=60, cwd=root, env=env)
     assert out.returncode == 0 and out.stdout.strip() == ""
+
+
+def test_params_json_roundtrip(tmp_path):
+    """utils/train.py:66-120: flags are saved sorted as JSON and restored on resume, except the skip list."""
+    from importlib import import_module
+    ck = import_module(sp.__name__ + ".checkpoint")
+    a = sp.get_args(["--env", "simple_mnist", "--episode_length", "7", "--disc_dim", "8"])
+    path = ck.save_args(a, str(tmp_path))
+    assert os.path.basename(path) == "params.json"
+    b = sp.get_args(["--env", "mnist"])
+    changed = ck.load_args(b, str(tmp_path))
+    assert b.env == "simple_mnist" and b.episode_length == 7 and b.disc_dim == 8
+    assert "episode_length" in changed and "load_path" not in changed

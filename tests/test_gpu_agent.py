@@ -131,3 +131,29 @@ def test_cuda_graph_rollout_matches_the_env_and_draws_fresh_actions():
         assert int(ro["actions"].min()) >= 0
     m = ag.train_policy(ro2)
     assert torch.isfinite(m["model/total_loss"])
+
+
+def test_checkpoint_resume_restores_weights_and_optimizer(tmp_path):
+    """trainer.py:23-29,66-80: the chief saves the global variables; the same --load_path resumes them."""
+    import spiral_b200 as sp
+    from importlib import import_module
+    agent_mod = import_module(sp.__name__ + ".agent")
+    ck = import_module(sp.__name__ + ".checkpoint")
+    args = sp.get_args(["--env", "simple_mnist", "--color_channel", "1", "--episode_length", "3", "--loss", "gan",
+                        "--disc_dim", "8", "--disc_precision", "fp32", "--cuda_graphs", "False"])
+    env = sp.create_env(args, num_envs=8)
+    ag = agent_mod.Agent(args, env)
+    ag.train_policy(ag.rollout())
+    ag.train_gan()
+    path = ck.save_checkpoint(ag, str(tmp_path), step=5)
+    assert ck.latest_checkpoint(str(tmp_path)) == path
+    want_p = [p.detach().clone() for p in ag.policy.parameters()]
+    want_d = {k: v.detach().clone() for k, v in ag.disc.params.items()}
+    x = ag.rollout()["states"][:, -1]
+    want_reward = ag.disc.predict(x).clone()
+    ag2 = agent_mod.Agent(args, sp.create_env(args, num_envs=8))
+    assert ck.load_checkpoint(ag2, str(tmp_path)) == 5
+    assert all(torch.equal(a, b) for a, b in zip(want_p, ag2.policy.parameters()))
+    assert all(torch.equal(want_d[k], ag2.disc.params[k]) for k in want_d)
+    assert ag2.policy_opt.t == ag.policy_opt.t and torch.equal(ag2.disc_opt.m[0], ag.disc_opt.m[0])
+    assert torch.equal(ag2.disc.predict(x), want_reward)              # the packed kernel weights were refreshed
