@@ -30,6 +30,9 @@ class Agent(object):
         self.args = args
         self.env = env
         self.device = env.device if device is None else torch.device(device)
+        tf32 = bool(getattr(args, "policy_tf32", True))
+        torch.backends.cudnn.allow_tf32 = tf32            # policy trunk only: K1-K5 do not go through cuDNN / cuBLAS
+        torch.backends.cuda.matmul.allow_tf32 = tf32
         self.policy = Policy(args, env, "global", env.observation_shape, env.action_sizes).to(self.device)
         self.policy_opt = FusedTFAdam(self.policy.parameters(), args.policy_lr)
         self.gan = args.loss == "gan"

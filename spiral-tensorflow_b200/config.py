@@ -72,6 +72,9 @@ def build_parser():
     parser.add_argument('--disc_precision', type=str, default='bf16x3', choices=['fp32', 'bf16x3', 'bf16'])
     # arithmetic of the WGAN-GP step's convolutions and their gradients (K2b); 'auto' = bf16x6 (24 operand bits,
     # fp32-exact products on the tensor cores) when the reward forward runs on tensor cores, else fp32
+    # PyTorch policy trunk (the next row): TF32 convolutions / matmuls (4x faster on B200, ~1e-3 relative);
+    # False = strict fp32 like the reference's TF-1.6 cuDNN path
+    parser.add_argument('--policy_tf32', type=str2bool, default=True)
     # capture the T-step rollout (policy.act + env.step) into one CUDA graph and replay it
     parser.add_argument('--cuda_graphs', type=str2bool, default=True)
     parser.add_argument('--disc_grad_precision', type=str, default='auto',
