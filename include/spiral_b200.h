@@ -274,6 +274,26 @@ int spiral_adam_step(float *const *params_dev, const float *const *grads_dev, fl
                      float beta2, float eps, float grad_scale, const float *norm_dev, float clip_norm,
                      void *stream);
 
+/* ------------------------------------------------------------------ */
+/* Policy convolutions for the acting path                              */
+/* replaces: what TensorFlow runs inside policy.act                     */
+/*           (models/policy.py:196-215) for the trunk's convolutions:   */
+/*           :94-99 conv 5x5, :103-109 conv 4x4/2 valid, :349-362       */
+/*           res-block conv 3x3, :242-247/:275-281 conv2d_transpose     */
+/*           4x4/2 (as four parity-class 2x2 convolutions), :290-295     */
+/* ------------------------------------------------------------------ */
+/* x bf16 NHWC [B,Hin,Win,Cin] (Cin in 1,2,3,6,16,32); w_packed bf16 [round8(Cout)][KH*KW*Cin rounded up to 16, + 8]
+ * with k = (ky*KW + kx)*Cin + c (rows channel-permuted when Cout == 32: row nt*8 + j holds channel (j>>1)*8 + nt*2 + (j&1));
+ * out = relu?(conv + bias + residual) + post_add, written bf16 (or fp32) at pixel (oy*o_sy + o_oy, ox*o_sx + o_ox)
+ * of an [oH,oW] map per frame.  residual (bf16, output layout) and post_add (f32 [B,Cout]) may be NULL.
+ * bf16 operands, fp32 accumulation (mma.sync). */
+int spiral_pconv_forward(const void *x_bf16_dev, const void *w_packed_bf16_dev, const float *bias_dev,
+                         const void *residual_bf16_dev, const float *post_add_dev, void *out_dev, int32_t B,
+                         int32_t Hin, int32_t Win, int32_t Cin, int32_t Hout, int32_t Wout, int32_t Cout,
+                         int32_t KH, int32_t KW, int32_t stride, int32_t pad_t, int32_t pad_l, int32_t relu,
+                         int32_t oH, int32_t oW, int32_t o_sy, int32_t o_sx, int32_t o_oy, int32_t o_ox,
+                         int32_t out_f32, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,269 @@
+// policy_conv.cu -- the policy network's convolutions for the ACTING path (rollouts), bf16 tensor cores.
+//
+// Replaces, for policy.act (models/policy.py:196-215, one call per env step on every actor), what TensorFlow runs for
+// the trunk's convolutions: conv 5x5 'same' (policy.py:94-99), three conv 4x4 / stride 2 'valid' (:103-109), the
+// res-blocks' conv 3x3 'same' (:349-362), and in the location heads the conv2d_transpose 4x4 / stride 2 'same'
+// (:242-247, :275-281) and the final conv 3x3 -> 1 channel (:290-295).  Every one of them is a <= 32-channel
+// convolution over a <= 64x64 map: K = taps * Cin <= 512, N = Cout <= 32 -- far too narrow for a TMA / tcgen05
+// pipeline, and what cuDNN runs at ~35 TFLOP/s (tools/policy_act_probe.py).  One kernel covers them all:
+//
+//   * NHWC bf16 activations; a CTA computes an 8 x 16 tile of output pixels x all output channels of one frame
+//   * the input tile (with halo, zero padded) is staged once in shared memory; the im2col is never built: each
+//     thread gathers its mma.sync.m16n8k16 A fragment from the tile through a k -> offset table (as in
+//     disc_conv0_mma.cu); B fragments come from the packed kernel [Cout][K] staged in shared memory
+//   * epilogue: + bias, + residual (res-blocks), ReLU, + per-frame vector (the action embedding of policy.py:101),
+//     bf16 (or fp32 for the logits) stores; output pixels may be scattered with a stride / offset, which turns the
+//     four parity classes of a stride-2 transposed convolution into four 2x2 stride-1 convolutions
+//
+// Plain bf16 operands with fp32 accumulation: this is the actors' behaviour policy, whose samples need no fp32
+// parity (the learner's logits / loss go through the fp32 PyTorch module and K3).
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/spiral_b200.h"
+#include "common.h"
+
+namespace spiral {
+
+constexpr int kPcTw = 16, kPcTh = 8;             // output tile: 8 warps x 16 pixels
+
+struct PConvParams {
+    int B, Hin, Win, Hout, Wout;                 // input map and the grid of outputs this launch computes, per frame
+    int Cout, CoutPad;                           // CoutPad: multiple of 8, <= 32
+    int KH, KW, stride, pad_t, pad_l;
+    int K, KP, KS;                               // K = KH*KW*Cin; KP = K rounded up to 16; KS = KP + 8 (row stride, bf16)
+    int IH, IW;                                  // staged input tile
+    int tiles_x, tiles_y;
+    int relu;
+    int oH, oW, o_sy, o_sx, o_oy, o_ox;          // output pixel (oy, ox) -> (oy*o_sy + o_oy, ox*o_sx + o_ox) of an [oH, oW] map
+    int out_f32;                                 // 1: fp32 output [.., Cout]; 0: bf16
+    int permuted;                                // packed rows are channel-permuted (CoutPad == 32): 128-bit stores
+};
+
+__device__ __forceinline__ void pc_mma(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2])
+{
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
+template <int CIN>
+__global__ void __launch_bounds__(256)
+pconv_kernel(const __grid_constant__ PConvParams p, const __nv_bfloat16 *__restrict__ x, const __nv_bfloat16 *__restrict__ wpk,
+             const float *__restrict__ bias, const __nv_bfloat16 *__restrict__ residual, const float *__restrict__ post_add,
+             void *__restrict__ out)
+{
+    extern __shared__ __align__(16) uint8_t sm_raw[];
+    uint16_t *s_w = reinterpret_cast<uint16_t *>(sm_raw);                     // [CoutPad][KS]
+    const int n_w = p.CoutPad * p.KS;
+    uint16_t *s_in = s_w + ((n_w + 7) & ~7);                                   // [IH][IW][CIN]
+    const int n_in = p.IH * p.IW * CIN;
+    int *s_koff = reinterpret_cast<int *>(s_in + ((n_in + 7) & ~7));           // [KP]
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tiles = p.tiles_x * p.tiles_y;
+    const int img = blockIdx.x / tiles;
+    const int trem = blockIdx.x % tiles;
+    const int oy0 = (trem / p.tiles_x) * kPcTh, ox0 = (trem % p.tiles_x) * kPcTw;
+
+    // ---- stage: packed kernel (16-byte copies), k -> offset table, input tile ----
+    {
+        const uint4 *gw = reinterpret_cast<const uint4 *>(wpk);
+        uint4 *sw = reinterpret_cast<uint4 *>(s_w);
+        for (int i = tid; i < n_w / 8; i += 256) sw[i] = __ldg(gw + i);
+        for (int k = tid; k < p.KP; k += 256) {
+            int off = 0;
+            if (k < p.K) {
+                const int tap = k / CIN, c = k - tap * CIN;
+                const int ky = tap / p.KW, kx = tap - ky * p.KW;
+                off = (ky * p.IW + kx) * CIN + c;
+            }
+            s_koff[k] = off;
+        }
+        const uint16_t *xi = reinterpret_cast<const uint16_t *>(x) + (size_t)img * p.Hin * p.Win * CIN;
+        const int iy0 = oy0 * p.stride - p.pad_t, ix0 = ox0 * p.stride - p.pad_l;
+        if (CIN % 8 == 0) {
+            constexpr int V = CIN / 8 > 0 ? CIN / 8 : 1;                       // uint4 per pixel
+            for (int i = tid; i < p.IH * p.IW * V; i += 256) {
+                const int pix = i / V, v = i - pix * V;
+                const int ly = pix / p.IW, lx = pix - ly * p.IW;
+                const int iy = iy0 + ly, ix = ix0 + lx;
+                uint4 val = make_uint4(0, 0, 0, 0);
+                if (iy >= 0 && iy < p.Hin && ix >= 0 && ix < p.Win)
+                    val = __ldg(reinterpret_cast<const uint4 *>(xi + ((size_t)iy * p.Win + ix) * CIN) + v);
+                reinterpret_cast<uint4 *>(s_in)[i] = val;
+            }
+        } else {
+            for (int i = tid; i < n_in; i += 256) {
+                const int pix = i / CIN, c = i - pix * CIN;
+                const int ly = pix / p.IW, lx = pix - ly * p.IW;
+                const int iy = iy0 + ly, ix = ix0 + lx;
+                uint16_t val = 0;
+                if (iy >= 0 && iy < p.Hin && ix >= 0 && ix < p.Win) val = __ldg(xi + ((size_t)iy * p.Win + ix) * CIN + c);
+                s_in[i] = val;
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- main loop: warp = output row `warp` of the tile, 16 pixels x CoutPad channels ----
+    const int g = lane >> 2, t = lane & 3;
+    const int base0 = ((warp * p.stride) * p.IW + g * p.stride) * CIN;         // pixel g
+    const int base1 = base0 + 8 * p.stride * CIN;                               // pixel g + 8
+    const int NT = p.CoutPad >> 3;
+    float acc[4][4];
+#pragma unroll
+    for (int nt = 0; nt < 4; nt++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) acc[nt][j] = 0.0f;
+
+#pragma unroll 1
+    for (int ks = 0; ks < p.KP / 16; ks++) {
+        const int k0 = ks * 16 + 2 * t;
+        uint32_t a[4];
+        if (CIN % 2 == 0) {
+            // k0 is even and CIN is even: k0 and k0+1 are adjacent channels of one tap -> one 32-bit load
+            const int o0 = s_koff[k0], o8 = s_koff[k0 + 8];
+            a[0] = *reinterpret_cast<const uint32_t *>(s_in + base0 + o0);
+            a[1] = *reinterpret_cast<const uint32_t *>(s_in + base1 + o0);
+            a[2] = *reinterpret_cast<const uint32_t *>(s_in + base0 + o8);
+            a[3] = *reinterpret_cast<const uint32_t *>(s_in + base1 + o8);
+            if (k0 >= p.K) { a[0] = 0; a[1] = 0; }                              // padded k (weights are zero there, keep NaN-free)
+            if (k0 + 8 >= p.K) { a[2] = 0; a[3] = 0; }
+        } else {
+            const int o0 = s_koff[k0], o1 = s_koff[k0 + 1], o8 = s_koff[k0 + 8], o9 = s_koff[k0 + 9];
+            a[0] = (uint32_t)s_in[base0 + o0] | ((uint32_t)s_in[base0 + o1] << 16);
+            a[1] = (uint32_t)s_in[base1 + o0] | ((uint32_t)s_in[base1 + o1] << 16);
+            a[2] = (uint32_t)s_in[base0 + o8] | ((uint32_t)s_in[base0 + o9] << 16);
+            a[3] = (uint32_t)s_in[base1 + o8] | ((uint32_t)s_in[base1 + o9] << 16);
+        }
+#pragma unroll
+        for (int nt = 0; nt < 4; nt++) {
+            if (nt < NT) {
+                const int wrow = (nt * 8 + g) * p.KS + k0;
+                uint32_t b[2];
+                b[0] = *reinterpret_cast<const uint32_t *>(s_w + wrow);
+                b[1] = *reinterpret_cast<const uint32_t *>(s_w + wrow + 8);
+                pc_mma(acc[nt], a, b);
+            }
+        }
+    }
+
+    // ---- epilogue ----
+    const int oy = oy0 + warp;
+    if (oy >= p.Hout) return;
+    const size_t frame_out = (size_t)img * p.oH * p.oW;
+#pragma unroll
+    for (int half = 0; half < 2; half++) {
+        const int ox = ox0 + g + 8 * half;
+        if (ox >= p.Wout) continue;
+        const size_t pix = frame_out + (size_t)(oy * p.o_sy + p.o_oy) * p.oW + (ox * p.o_sx + p.o_ox);
+        if (p.permuted) {
+            // thread t owns channels t*8 .. t*8+7 (column (nt, 2t+e) of the MMA <-> channel t*8 + nt*2 + e)
+            float v[8];
+#pragma unroll
+            for (int nt = 0; nt < 4; nt++) {
+                v[2 * nt] = acc[nt][2 * half] + __ldg(bias + t * 8 + 2 * nt);
+                v[2 * nt + 1] = acc[nt][2 * half + 1] + __ldg(bias + t * 8 + 2 * nt + 1);
+            }
+            if (residual) {
+                const uint4 r = __ldg(reinterpret_cast<const uint4 *>(residual + pix * p.Cout + t * 8));
+                const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    v[2 * j] += __bfloat162float(__ushort_as_bfloat16((unsigned short)(rr[j] & 0xffffu)));
+                    v[2 * j + 1] += __bfloat162float(__ushort_as_bfloat16((unsigned short)(rr[j] >> 16)));
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                if (p.relu) v[j] = fmaxf(v[j], 0.0f);
+                if (post_add) v[j] += __ldg(post_add + (size_t)img * p.Cout + t * 8 + j);
+            }
+            if (p.out_f32) {
+                float4 *o = reinterpret_cast<float4 *>(reinterpret_cast<float *>(out) + pix * p.Cout + t * 8);
+                o[0] = make_float4(v[0], v[1], v[2], v[3]);
+                o[1] = make_float4(v[4], v[5], v[6], v[7]);
+            } else {
+                uint32_t w[4];
+#pragma unroll
+                for (int j = 0; j < 4; j++)
+                    w[j] = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(v[2 * j])) |
+                           ((uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(v[2 * j + 1])) << 16);
+                *reinterpret_cast<uint4 *>(reinterpret_cast<__nv_bfloat16 *>(out) + pix * p.Cout + t * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+            }
+        } else {
+            // generic (narrow) output: column (nt, 2t+e) <-> channel nt*8 + 2t + e
+#pragma unroll
+            for (int nt = 0; nt < 4; nt++) {
+                if (nt >= NT) continue;
+#pragma unroll
+                for (int e = 0; e < 2; e++) {
+                    const int ch = nt * 8 + 2 * t + e;
+                    if (ch >= p.Cout) continue;
+                    float v = acc[nt][2 * half + e] + __ldg(bias + ch);
+                    if (residual) v += __bfloat162float(residual[pix * p.Cout + ch]);
+                    if (p.relu) v = fmaxf(v, 0.0f);
+                    if (post_add) v += __ldg(post_add + (size_t)img * p.Cout + ch);
+                    if (p.out_f32) reinterpret_cast<float *>(out)[pix * p.Cout + ch] = v;
+                    else reinterpret_cast<__nv_bfloat16 *>(out)[pix * p.Cout + ch] = __float2bfloat16_rn(v);
+                }
+            }
+        }
+    }
+}
+
+}  // namespace spiral
+
+using namespace spiral;
+
+extern "C" int spiral_pconv_forward(const void *x_bf16, const void *w_packed_bf16, const float *bias, const void *residual_bf16,
+                                    const float *post_add, void *out, int32_t B, int32_t Hin, int32_t Win, int32_t Cin,
+                                    int32_t Hout, int32_t Wout, int32_t Cout, int32_t KH, int32_t KW, int32_t stride,
+                                    int32_t pad_t, int32_t pad_l, int32_t relu, int32_t oH, int32_t oW, int32_t o_sy,
+                                    int32_t o_sx, int32_t o_oy, int32_t o_ox, int32_t out_f32, void *stream)
+{
+    SPIRAL_REQUIRE(x_bf16); SPIRAL_REQUIRE(w_packed_bf16); SPIRAL_REQUIRE(bias); SPIRAL_REQUIRE(out);
+    if (B <= 0 || Cout <= 0 || Cout > 32 || !(Cin == 1 || Cin == 2 || Cin == 3 || Cin == 6 || Cin == 16 || Cin == 32))
+        return spiral_set_error(SPIRAL_EINVAL, "pconv: unsupported channels Cin=%d Cout=%d", Cin, Cout);
+    PConvParams p;
+    p.B = B; p.Hin = Hin; p.Win = Win; p.Hout = Hout; p.Wout = Wout;
+    p.Cout = Cout; p.CoutPad = (Cout + 7) & ~7;
+    p.KH = KH; p.KW = KW; p.stride = stride; p.pad_t = pad_t; p.pad_l = pad_l;
+    p.K = KH * KW * Cin; p.KP = (p.K + 15) & ~15; p.KS = p.KP + 8;
+    p.IH = (kPcTh - 1) * stride + KH; p.IW = (kPcTw - 1) * stride + KW;
+    p.tiles_x = (Wout + kPcTw - 1) / kPcTw; p.tiles_y = (Hout + kPcTh - 1) / kPcTh;
+    p.relu = relu;
+    p.oH = oH; p.oW = oW; p.o_sy = o_sy; p.o_sx = o_sx; p.o_oy = o_oy; p.o_ox = o_ox;
+    p.out_f32 = out_f32;
+    p.permuted = (Cout == 32) ? 1 : 0;
+    const size_t n_w = (size_t)p.CoutPad * p.KS, n_in = (size_t)p.IH * p.IW * Cin;
+    const size_t smem = (((n_w + 7) & ~(size_t)7) + ((n_in + 7) & ~(size_t)7)) * 2 + (size_t)p.KP * 4;
+    if (smem > 200 * 1024) return spiral_set_error(SPIRAL_EUNSUPPORTED, "pconv: tile does not fit shared memory (%zu bytes)", smem);
+    const int grid = B * p.tiles_x * p.tiles_y;
+    cudaStream_t st = (cudaStream_t)stream;
+#define PCONV_LAUNCH(C)                                                                                                     \
+    do {                                                                                                                    \
+        static size_t attr = 0;                                                                                             \
+        if (smem > attr) {                                                                                                  \
+            const cudaError_t e = cudaFuncSetAttribute(pconv_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); \
+            if (e != cudaSuccess) return spiral_cuda_error(e, "cudaFuncSetAttribute(pconv_kernel)");                        \
+            attr = 200 * 1024;                                                                                              \
+        }                                                                                                                   \
+        pconv_kernel<C><<<grid, 256, smem, st>>>(p, (const __nv_bfloat16 *)x_bf16, (const __nv_bfloat16 *)w_packed_bf16, bias, \
+                                                 (const __nv_bfloat16 *)residual_bf16, post_add, out);                     \
+    } while (0)
+    switch (Cin) {
+    case 1: PCONV_LAUNCH(1); break;
+    case 2: PCONV_LAUNCH(2); break;
+    case 3: PCONV_LAUNCH(3); break;
+    case 6: PCONV_LAUNCH(6); break;
+    case 16: PCONV_LAUNCH(16); break;
+    default: PCONV_LAUNCH(32); break;
+    }
+#undef PCONV_LAUNCH
+    const cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? SPIRAL_OK : spiral_cuda_error(e, "spiral_pconv_forward");
+}

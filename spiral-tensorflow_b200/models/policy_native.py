@@ -1,0 +1,187 @@
+"""``NativeActor`` -- policy.act with the trunk's convolutions on libspiral_b200.so (bf16 tensor cores).
+
+The acting path of the reference (models/policy.py:196-215: one ``sess.run`` per env step on every actor) spends
+its time in ~45 small convolutions (<= 32 channels, <= 64x64 maps).  Once rendering, reward and loss are native
+they are >90 % of a rollout (tools/policy_act_probe.py).  This module runs them through ``spiral_pconv_forward``
+(csrc/policy_conv.cu: NHWC bf16, implicit GEMM gathered from a shared-memory tile, fused bias / residual / ReLU
+epilogues; transposed convolutions as four parity-class 2x2 convolutions) and keeps the rest of ``Policy`` --
+the dense layers, the LSTM cell, the autoregressive head wiring, K4 sampling -- exactly as in ``models/policy.py``.
+
+It reads the SAME parameters as the PyTorch module (call ``sync()`` after every learner update); the learner keeps
+using the fp32 PyTorch module (it needs gradients and fp32 parity).  bf16 operands: logits agree with the fp32
+module to ~1e-2, which only perturbs the actors' behaviour policy.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn.functional as F
+
+from .. import _native as N
+from .policy import categorical_sample
+
+
+def _pack(w_khkwcico, permute):
+    """[KH,KW,Cin,Cout] fp32 -> bf16 [round8(Cout)][KP + 8], k = (ky*KW + kx)*Cin + c, zero padded."""
+    KH, KW, Cin, Cout = w_khkwcico.shape
+    K = KH * KW * Cin
+    KP = (K + 15) // 16 * 16
+    KS = KP + 8
+    cp = (Cout + 7) // 8 * 8
+    m = w_khkwcico.reshape(K, Cout).t().contiguous()                 # [Cout][K]
+    out = torch.zeros((cp, KS), dtype=torch.float32, device=m.device)
+    if permute:                                                      # row nt*8 + j holds channel (j>>1)*8 + nt*2 + (j&1)
+        rows = torch.arange(cp, device=m.device)
+        nt, j = rows // 8, rows % 8
+        ch = (j // 2) * 8 + nt * 2 + (j % 2)
+        out[:, :K] = m[ch]
+    else:
+        out[:Cout, :K] = m
+    return out.to(torch.bfloat16).contiguous()
+
+
+class _Conv(object):
+    """One launch of spiral_pconv_forward; weights packed from a torch Conv2d."""
+
+    def __init__(self, weight_oihw, bias, stride, pad, relu, scatter=None):
+        w = weight_oihw.detach().permute(2, 3, 1, 0).contiguous().float()          # [KH,KW,Cin,Cout]
+        self.KH, self.KW, self.Cin, self.Cout = w.shape
+        self.stride, self.pad_t, self.pad_l, self.relu = stride, pad[0], pad[1], int(relu)
+        self.wpk = _pack(w, self.Cout == 32)
+        self.bias = torch.zeros(((self.Cout + 7) // 8 * 8,), dtype=torch.float32, device=w.device)
+        self.bias[:self.Cout] = bias.detach().float()
+        self.scatter = scatter                                                       # (sy, sx, oy, ox) for transposed-conv classes
+
+    def out_hw(self, Hin, Win, same):
+        if same:
+            return (Hin + self.stride - 1) // self.stride, (Win + self.stride - 1) // self.stride
+        return (Hin - self.KH) // self.stride + 1, (Win - self.KW) // self.stride + 1
+
+    def __call__(self, x, out, Hout, Wout, residual=None, post_add=None, out_map=None, out_f32=False):
+        B, Hin, Win, _ = x.shape
+        oH, oW = out_map if out_map is not None else (Hout, Wout)
+        sy, sx, oy, ox = self.scatter if self.scatter is not None else (1, 1, 0, 0)
+        N.check(N.lib().spiral_pconv_forward(N.ptr(x), N.ptr(self.wpk), N.ptr(self.bias), N.ptr(residual), N.ptr(post_add),
+                                             N.ptr(out), B, Hin, Win, self.Cin, Hout, Wout, self.Cout, self.KH, self.KW,
+                                             self.stride, self.pad_t, self.pad_l, self.relu, oH, oW, sy, sx, oy, ox,
+                                             int(out_f32), N.stream_ptr()), "spiral_pconv_forward")
+        return out
+
+
+class _Deconv(object):
+    """ConvTranspose2d(k=4, s=2, p=1) == TF conv2d_transpose(4, strides 2, 'same') as four parity-class 2x2
+    convolutions: out[2a+py, 2b+px] = sum over the two kernel rows kk with the parity of py+1 (kk = 1,3 / 0,2) of
+    x[a + (py + 1 - kk) / 2] * w[kk] (same along x)."""
+
+    def __init__(self, weight_iohw, bias, relu):
+        w = weight_iohw.detach().float()                                             # [Cin, Cout, 4, 4]
+        self.classes = []
+        for py in (0, 1):
+            for px in (0, 1):
+                kys = (3, 1) if py == 0 else (2, 0)          # tap row 0, 1 of the 2x2 window (input rows a-1,a / a,a+1)
+                kxs = (3, 1) if px == 0 else (2, 0)
+                sub = w[:, :, kys, :][:, :, :, kxs]                                   # [Cin, Cout, 2, 2]
+                conv = _Conv(sub.permute(1, 0, 2, 3), bias, 1, (1 if py == 0 else 0, 1 if px == 0 else 0), relu,
+                             scatter=(2, 2, py, px))
+                self.classes.append(conv)
+
+    def __call__(self, x, out):
+        B, Hin, Win, _ = x.shape
+        for conv in self.classes:
+            conv(x, out, Hin, Win, out_map=(2 * Hin, 2 * Win))
+        return out
+
+
+class NativeActor(object):
+    def __init__(self, policy):
+        self.pi = policy
+        self.device = next(policy.parameters()).device
+        self._bufs = {}
+        self.sync()
+
+    # ------------------------------------------------------------------
+    def sync(self):
+        """(Re)pack the convolution kernels from the PyTorch module's current parameters."""
+        pi = self.pi
+        self.x_enc = _Conv(pi.x_enc.weight, pi.x_enc.bias, 1, (2, 2), True)
+        self.add_enc = [_Conv(c.weight, c.bias, 2, (0, 0), True) for c in pi.add_enc]
+        self.enc_res = [(_Conv(r.c1.weight, r.c1.bias, 1, (1, 1), True), _Conv(r.c2.weight, r.c2.bias, 1, (1, 1), False))
+                        for r in pi.encoder_res]
+        self.loc = {}
+        for name in pi.acs:
+            head = pi.heads[name]
+            if hasattr(head, "deconv0"):
+                self.loc[name] = dict(
+                    deconv0=_Deconv(head.deconv0.weight, head.deconv0.bias, True),
+                    res=[(_Conv(r.c1.weight, r.c1.bias, 1, (1, 1), True), _Conv(r.c2.weight, r.c2.bias, 1, (1, 1), False))
+                         for r in head.res],
+                    ups=[_Deconv(u.weight, u.bias, True) for u in head.ups],
+                    out=_Conv(head.out.weight, head.out.bias, 1, (1, 1), False), c0=head.c0)
+
+    def _buf(self, key, shape, dtype=torch.bfloat16):
+        b = self._bufs.get(key)
+        if b is None or tuple(b.shape) != tuple(shape) or b.dtype != dtype:
+            b = torch.empty(shape, dtype=dtype, device=self.device)
+            self._bufs[key] = b
+        return b
+
+    def _res_stack(self, x, blocks, tag):
+        B, H, W, C = x.shape
+        for i, (c1, c2) in enumerate(blocks):
+            t = c1(x, self._buf((tag, "t", H), (B, H, W, C)), H, W)
+            x = c2(t, self._buf((tag, i % 2, H), (B, H, W, C)), H, W, residual=x)
+        return x
+
+    # ------------------------------------------------------------------
+    @torch.no_grad()
+    def encode(self, ob, ac, condition=None, z=None):
+        """Policy.encode for T = 1: ob f32 [B,S,S,C] -> [B, lstm_size]."""
+        pi = self.pi
+        B, S = ob.shape[0], ob.shape[1]
+        x = ob if condition is None else torch.cat([ob, condition], -1)
+        x = x.to(torch.bfloat16).contiguous()                                      # NHWC already
+        a = pi.a_enc(ac.float().unsqueeze(-1)).reshape(B, -1)
+        a = F.relu(pi.a_concat_fc(a)).float().contiguous()                         # [B,32], added after the ReLU (policy.py:101)
+        h = self.x_enc(x, self._buf("e0", (B, S, S, 32)), S, S, post_add=a)
+        H = S
+        for i, conv in enumerate(self.add_enc):
+            Ho, Wo = conv.out_hw(H, H, same=False)
+            h = conv(h, self._buf(("e", i), (B, Ho, Wo, 32)), Ho, Wo)
+            H = Ho
+        h = self._res_stack(h, self.enc_res, "er")
+        flat = h.reshape(B, -1).float()                                            # NHWC flatten (tl.flatten)
+        out = F.relu(pi.flat_fc(flat))
+        if not pi.conditional:
+            out = out + pi.z_enc(z)
+        return out
+
+    @torch.no_grad()
+    def location_logits(self, name, z_flat):
+        L = self.loc[name]
+        B = z_flat.shape[0]
+        x = z_flat.view(B, 4, 4, L["c0"]).to(torch.bfloat16).contiguous()          # NHWC reshape of the reference
+        h = L["deconv0"](x, self._buf((name, "d0"), (B, 8, 8, 32)))
+        h = self._res_stack(h, L["res"], name + "r")
+        H = 8
+        for i, up in enumerate(L["ups"]):
+            h = up(h, self._buf((name, "u", i), (B, 2 * H, 2 * H, 32)))
+            H *= 2
+        logits = L["out"](h, self._buf((name, "o"), (B, H, H, 1), torch.float32), H, H, out_f32=True)
+        return logits.view(B, H * H)
+
+    @torch.no_grad()
+    def act(self, ob, ac, c, h, condition=None, z=None, generator=None):
+        """Same contract as Policy.act (models/policy.py:196-215)."""
+        pi = self.pi
+        enc = self.encode(ob, ac, condition, z)
+        hid, (nc, nh) = pi.lstm(enc, (c, h))
+        zz = F.relu(hid)
+        actions = []
+        for idx, name in enumerate(pi.acs):
+            logit = self.location_logits(name, zz) if name in self.loc else pi.heads[name](zz)
+            s = categorical_sample(logit, generator, pi).long()
+            actions.append(s)
+            if idx < len(pi.acs) - 1:
+                emb = pi.sample_mlp[name](s.view(-1, 1).to(zz.dtype))
+                zz = F.relu(pi.concat_z_fc[name](torch.cat([zz, emb], -1)))
+        vf = pi.value(hid)[:, 0]
+        return torch.stack(actions, 1).to(torch.int32), vf, nc, nh
