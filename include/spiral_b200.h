@@ -294,6 +294,12 @@ int spiral_pconv_forward(const void *x_bf16_dev, const void *w_packed_bf16_dev, 
                          int32_t oH, int32_t oW, int32_t o_sy, int32_t o_sx, int32_t o_oy, int32_t o_ox,
                          int32_t out_f32, void *stream);
 
+/* Fused res-block stack (policy.py:111-114, :255-258, :349-362): n_convs / 2 blocks of [conv3x3 -> ReLU -> conv3x3, + x]
+ * on bf16 NHWC [B,S,S,32] maps with S = 6 or 8; w_packed = n_convs kernels packed as for spiral_pconv_forward
+ * (Cout = 32, channel-permuted rows), bias f32 [n_convs][32].  Whole frames stay in shared memory across all layers. */
+int spiral_pres_stack(const void *x_bf16_dev, const void *w_packed_bf16_dev, const float *bias_dev,
+                      void *out_bf16_dev, int32_t B, int32_t S, int32_t n_convs, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

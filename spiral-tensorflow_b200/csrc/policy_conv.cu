@@ -267,3 +267,181 @@ extern "C" int spiral_pconv_forward(const void *x_bf16, const void *w_packed_bf1
     const cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? SPIRAL_OK : spiral_cuda_error(e, "spiral_pconv_forward");
 }
+
+// ------------------------------------------------------------------------------------------
+// Fused res-block stack (policy.py:111-114 encoder, :255-258 location heads): n_blocks x [conv3x3 -> ReLU -> conv3x3,
+// + x] on a tiny map (6x6 after the encoder, 8x8 in the heads), 32 channels.  As separate launches these are 16
+// convolutions per stack whose CTAs are mostly empty (36 or 64 of 128 pixels) and whose activations bounce through
+// L2 between every pair; here a CTA keeps several whole frames (7 at 6x6, 4 at 8x8: ~256 pixels = two m16 tiles
+// per warp) in shared memory across ALL layers, streams each layer's packed kernel in with cp.async while the
+// previous layer computes, and touches global memory once in and once out.
+// ------------------------------------------------------------------------------------------
+namespace spiral {
+
+constexpr int kRsC = 32;
+constexpr int kRsK = 9 * kRsC;                   // 288
+constexpr int kRsKS = kRsK + 8;                  // 296: conflict-free row stride (bf16)
+constexpr int kRsWElems = kRsC * kRsKS;          // one packed kernel
+
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem)
+{
+    const uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+template <int S>
+__global__ void __launch_bounds__(256)
+pres_stack_kernel(const __nv_bfloat16 *__restrict__ x, const __nv_bfloat16 *__restrict__ wpk, const float *__restrict__ bias,
+                  __nv_bfloat16 *__restrict__ out, int B, int n_convs)
+{
+    constexpr int P = S + 2;                      // padded frame
+    constexpr int F = 256 / (S * S);              // frames per CTA
+    constexpr int FE = P * P * kRsC;              // elements per padded frame
+    extern __shared__ __align__(16) uint8_t sm_raw[];
+    uint16_t *s_x = reinterpret_cast<uint16_t *>(sm_raw);          // [F][P][P][32] block input / output (residual)
+    uint16_t *s_t = s_x + F * FE;                                  // [F][P][P][32] after the first conv
+    uint16_t *s_w = s_t + F * FE;                                  // [2][32][KS] double-buffered packed kernel
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int f0 = blockIdx.x * F;
+    const int nf = min(F, B - f0);
+
+    // zero both activation buffers (halo stays zero), start the first kernel's copy, load the frames
+    for (int i = tid; i < 2 * F * FE / 8; i += 256) reinterpret_cast<uint4 *>(s_x)[i] = make_uint4(0, 0, 0, 0);
+    for (int i = tid; i < kRsWElems / 8; i += 256) cp_async16(s_w + i * 8, wpk + i * 8);
+    __syncthreads();
+    for (int i = tid; i < nf * S * S * (kRsC / 8); i += 256) {
+        const int v = i % (kRsC / 8), pix = i / (kRsC / 8);
+        const int f = pix / (S * S), r = pix % (S * S);
+        const int y = r / S, xx = r % S;
+        const uint4 val = __ldg(reinterpret_cast<const uint4 *>(x + ((size_t)(f0 + f) * S * S + r) * kRsC) + v);
+        *reinterpret_cast<uint4 *>(s_x + f * FE + ((y + 1) * P + xx + 1) * kRsC + v * 8) = val;
+    }
+
+    // this warp's 32 pixels: two m16 tiles; lane (g, t) handles rows g and g+8 of each
+    const int g = lane >> 2, t = lane & 3;
+    int pbase[4];                                 // top-left of the 3x3 window in the padded frame, per fragment row
+    int pint[4];                                  // interior offset of the pixel itself (for residual / stores)
+    bool pok[4];
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+        const int p = warp * 32 + (r >> 1) * 16 + g + 8 * (r & 1);
+        const int f = p / (S * S), q = p % (S * S);
+        const int y = q / S, xx = q % S;
+        pok[r] = p < nf * S * S;
+        const int fo = (pok[r] ? f : 0) * FE;
+        pbase[r] = fo + (y * P + xx) * kRsC;
+        pint[r] = fo + ((y + 1) * P + xx + 1) * kRsC;
+    }
+
+    for (int l = 0; l < n_convs; l++) {
+        cp_async_wait_all();
+        __syncthreads();                          // kernel l is in s_w[l & 1]; the previous layer's stores are visible
+        if (l + 1 < n_convs) {
+            uint16_t *dst = s_w + ((l + 1) & 1) * kRsWElems;
+            const __nv_bfloat16 *srcw = wpk + (size_t)(l + 1) * kRsWElems;
+            for (int i = tid; i < kRsWElems / 8; i += 256) cp_async16(dst + i * 8, srcw + i * 8);
+        }
+        const uint16_t *src = (l & 1) ? s_t : s_x;       // conv1 reads x, conv2 reads t
+        uint16_t *dstb = (l & 1) ? s_x : s_t;            // conv1 writes t, conv2 writes x (in place: + its own residual)
+        const uint16_t *w = s_w + (l & 1) * kRsWElems;
+        float acc[2][4][4];
+#pragma unroll
+        for (int m = 0; m < 2; m++)
+#pragma unroll
+            for (int nt = 0; nt < 4; nt++)
+#pragma unroll
+                for (int j = 0; j < 4; j++) acc[m][nt][j] = 0.0f;
+#pragma unroll 1
+        for (int ks = 0; ks < kRsK / 16; ks++) {
+            const int k0 = ks * 16 + 2 * t;
+            // k -> (tap, c): c = k % 32 (even), tap = k / 32; offsets inside the padded frame
+            const int tap0 = k0 >> 5, c0 = k0 & 31, tap8 = (k0 + 8) >> 5, c8 = (k0 + 8) & 31;
+            const int o0 = ((tap0 / 3) * P + tap0 % 3) * kRsC + c0, o8 = ((tap8 / 3) * P + tap8 % 3) * kRsC + c8;
+            uint32_t a[2][4];
+#pragma unroll
+            for (int m = 0; m < 2; m++) {
+                a[m][0] = *reinterpret_cast<const uint32_t *>(src + pbase[2 * m] + o0);
+                a[m][1] = *reinterpret_cast<const uint32_t *>(src + pbase[2 * m + 1] + o0);
+                a[m][2] = *reinterpret_cast<const uint32_t *>(src + pbase[2 * m] + o8);
+                a[m][3] = *reinterpret_cast<const uint32_t *>(src + pbase[2 * m + 1] + o8);
+            }
+#pragma unroll
+            for (int nt = 0; nt < 4; nt++) {
+                const int wrow = (nt * 8 + g) * kRsKS + k0;
+                uint32_t b[2];
+                b[0] = *reinterpret_cast<const uint32_t *>(w + wrow);
+                b[1] = *reinterpret_cast<const uint32_t *>(w + wrow + 8);
+                pc_mma(acc[0][nt], a[0], b);
+                pc_mma(acc[1][nt], a[1], b);
+            }
+        }
+        __syncthreads();                          // everyone has read `src` (conv2 overwrites x in place only at own pixels,
+                                                  // but conv1 of the NEXT block reads x's neighbours: keep the barrier simple)
+        const float *bl = bias + (size_t)l * kRsC;
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+            if (!pok[r]) continue;
+            const int m = r >> 1, half = r & 1;
+            float v[8];
+#pragma unroll
+            for (int nt = 0; nt < 4; nt++) {
+                v[2 * nt] = acc[m][nt][2 * half] + __ldg(bl + t * 8 + 2 * nt);
+                v[2 * nt + 1] = acc[m][nt][2 * half + 1] + __ldg(bl + t * 8 + 2 * nt + 1);
+            }
+            uint16_t *o = dstb + pint[r] + t * 8;
+            if (l & 1) {                          // second conv of the block: + x, no ReLU
+                const uint4 rv = *reinterpret_cast<const uint4 *>(o);
+                const uint32_t rr[4] = {rv.x, rv.y, rv.z, rv.w};
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    v[2 * j] += __bfloat162float(__ushort_as_bfloat16((unsigned short)(rr[j] & 0xffffu)));
+                    v[2 * j + 1] += __bfloat162float(__ushort_as_bfloat16((unsigned short)(rr[j] >> 16)));
+                }
+            } else {
+#pragma unroll
+                for (int j = 0; j < 8; j++) v[j] = fmaxf(v[j], 0.0f);
+            }
+            uint32_t wv[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+                wv[j] = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(v[2 * j])) |
+                        ((uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(v[2 * j + 1])) << 16);
+            *reinterpret_cast<uint4 *>(o) = make_uint4(wv[0], wv[1], wv[2], wv[3]);
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < nf * S * S * (kRsC / 8); i += 256) {
+        const int v = i % (kRsC / 8), pix = i / (kRsC / 8);
+        const int f = pix / (S * S), r = pix % (S * S);
+        const int y = r / S, xx = r % S;
+        const uint4 val = *reinterpret_cast<const uint4 *>(s_x + f * FE + ((y + 1) * P + xx + 1) * kRsC + v * 8);
+        reinterpret_cast<uint4 *>(out + ((size_t)(f0 + f) * S * S + r) * kRsC)[v] = val;
+    }
+}
+
+}  // namespace spiral
+
+extern "C" int spiral_pres_stack(const void *x_bf16, const void *w_packed_bf16, const float *bias, void *out_bf16, int32_t B,
+                                 int32_t S, int32_t n_convs, void *stream)
+{
+    SPIRAL_REQUIRE(x_bf16); SPIRAL_REQUIRE(w_packed_bf16); SPIRAL_REQUIRE(bias); SPIRAL_REQUIRE(out_bf16);
+    if (B <= 0 || n_convs <= 0 || (n_convs & 1) || !(S == 6 || S == 8))
+        return spiral_set_error(SPIRAL_EINVAL, "pres_stack: S must be 6 or 8 and n_convs even (got S=%d n_convs=%d)", S, n_convs);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int F = 256 / (S * S), P = S + 2;
+    const size_t smem = ((size_t)2 * F * P * P * kRsC + (size_t)2 * kRsWElems) * 2;
+    const int grid = (B + F - 1) / F;
+    static bool attr6 = false, attr8 = false;
+    if (S == 6) {
+        if (!attr6) { cudaFuncSetAttribute(pres_stack_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr6 = true; }
+        pres_stack_kernel<6><<<grid, 256, smem, st>>>((const __nv_bfloat16 *)x_bf16, (const __nv_bfloat16 *)w_packed_bf16, bias,
+                                                      (__nv_bfloat16 *)out_bf16, B, n_convs);
+    } else {
+        if (!attr8) { cudaFuncSetAttribute(pres_stack_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr8 = true; }
+        pres_stack_kernel<8><<<grid, 256, smem, st>>>((const __nv_bfloat16 *)x_bf16, (const __nv_bfloat16 *)w_packed_bf16, bias,
+                                                      (__nv_bfloat16 *)out_bf16, B, n_convs);
+    }
+    const cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? SPIRAL_OK : spiral_cuda_error(e, "spiral_pres_stack");
+}

@@ -102,6 +102,7 @@ class NativeActor(object):
     def sync(self):
         """(Re)pack the convolution kernels from the PyTorch module's current parameters."""
         pi = self.pi
+        self._stacks = {}
         self.x_enc = _Conv(pi.x_enc.weight, pi.x_enc.bias, 1, (2, 2), True)
         self.add_enc = [_Conv(c.weight, c.bias, 2, (0, 0), True) for c in pi.add_enc]
         self.enc_res = [(_Conv(r.c1.weight, r.c1.bias, 1, (1, 1), True), _Conv(r.c2.weight, r.c2.bias, 1, (1, 1), False))
@@ -126,6 +127,17 @@ class NativeActor(object):
 
     def _res_stack(self, x, blocks, tag):
         B, H, W, C = x.shape
+        if H == W and H in (6, 8) and C == 32 and len(blocks) > 0:
+            # fused: the whole stack in one launch, frames resident in shared memory (spiral_pres_stack)
+            pk = self._stacks.get(tag)
+            if pk is None:
+                wpk = torch.cat([c.wpk.reshape(-1) for blk in blocks for c in blk]).contiguous()
+                bias = torch.cat([c.bias[:32] for blk in blocks for c in blk]).contiguous()
+                pk = self._stacks[tag] = (wpk, bias)
+            out = self._buf((tag, "fused", H), (B, H, W, C))
+            N.check(N.lib().spiral_pres_stack(N.ptr(x), N.ptr(pk[0]), N.ptr(pk[1]), N.ptr(out), B, H, 2 * len(blocks),
+                                              N.stream_ptr()), "spiral_pres_stack")
+            return out
         for i, (c1, c2) in enumerate(blocks):
             t = c1(x, self._buf((tag, "t", H), (B, H, W, C)), H, W)
             x = c2(t, self._buf((tag, i % 2, H), (B, H, W, C)), H, W, residual=x)

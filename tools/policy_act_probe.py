@@ -4,6 +4,7 @@ sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."
 from importlib import import_module
 import spiral_b200 as sp
 pol = import_module(sp.__name__ + ".models.policy")
+pn = import_module(sp.__name__ + ".models.policy_native")
 a = sp.get_args(["--env", "color_mnist", "--location_size", "64", "--color_channel", "3", "--episode_length", "20", "--loss", "gan"])
 for B in (128, 1024, 8192):
     env = sp.create_env(a, num_envs=B)
@@ -12,13 +13,14 @@ for B in (128, 1024, 8192):
     c, h = pi.get_initial_features(B)
     la = torch.full((B, len(env.acs)), -1, dtype=torch.int32, device="cuda")
     g = torch.Generator(device="cuda"); g.manual_seed(0)
-    for mode in ("fp32", "tf32", "bf16", "bf16+cl"):
+    actor = pn.NativeActor(pi)
+    for mode in ("fp32", "tf32", "bf16", "native"):
         torch.backends.cudnn.allow_tf32 = mode != "fp32"
         torch.backends.cuda.matmul.allow_tf32 = mode != "fp32"
         m = pi
-        if mode == "bf16+cl":
-            m = pi.to(memory_format=torch.channels_last)
         def run():
+            if mode == "native":
+                return actor.act(state, la, c, h, cond, z, g)
             if mode.startswith("bf16"):
                 with torch.autocast("cuda", dtype=torch.bfloat16):
                     return m.act(state, la, c, h, cond, z, g)
