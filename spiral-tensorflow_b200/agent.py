@@ -21,6 +21,7 @@ from . import distributed as dist_utils
 from . import rl_utils
 from .models.discriminator import Discriminator
 from .models.policy import Policy
+from .models.policy_native import NativeActor
 from .optim import FusedTFAdam
 from .replay import ReplayBuffer
 
@@ -35,6 +36,8 @@ class Agent(object):
         torch.backends.cuda.matmul.allow_tf32 = tf32
         self.policy = Policy(args, env, "global", env.observation_shape, env.action_sizes).to(self.device)
         self.policy_opt = FusedTFAdam(self.policy.parameters(), args.policy_lr)
+        # acting path: the trunk's convolutions on libspiral_b200.so (bf16 tensor cores); the learner keeps the fp32 module
+        self.actor = NativeActor(self.policy) if (getattr(args, "policy_act_native", True) and self.device.type == "cuda") else None
         self.gan = args.loss == "gan"
         if self.gan:
             self.disc = Discriminator(args, None, env.observation_shape, norm_fn=env.norm, scope_name="global",
@@ -109,7 +112,7 @@ class Agent(object):
         values = torch.zeros((B, T, 1), device=self.device)
         for t in range(T):
             states[:, t] = state
-            action, value, c, h = pi.act(state, last_action, c, h, condition, z, self.rng)
+            action, value, c, h = (self.actor or pi).act(state, last_action, c, h, condition, z, self.rng)
             state, reward, terminal, _ = env.step(action)
             actions[:, t] = action
             rewards[:, t] = reward
@@ -150,6 +153,8 @@ class Agent(object):
         grads = [p.grad for p in pi.parameters() if p.grad is not None]
         dist_utils.allreduce_grads_(grads, self.world, average=False)                         # sum; 1/world is folded into K5
         gnorm = self.policy_opt.step(clip_norm=float(args.grad_clip), grad_scale=1.0 / self.world)   # agent.py:231-239
+        if self.actor is not None:
+            self.actor.sync()                             # actors pull the new weights (trainer.py:117 policy_sync)
         B = acts.shape[0]
         return {"model/total_loss": loss.detach(), "model/grad_global_norm": gnorm,
                 "env/r": rollout["rewards"][:, -1].mean(), "batch": B}

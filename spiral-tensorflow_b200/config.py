@@ -75,6 +75,8 @@ def build_parser():
     # PyTorch policy trunk (the next row): TF32 convolutions / matmuls (4x faster on B200, ~1e-3 relative);
     # False = strict fp32 like the reference's TF-1.6 cuDNN path
     parser.add_argument('--policy_tf32', type=str2bool, default=True)
+    # acting path (policy.act in the rollout): trunk convolutions through libspiral_b200.so in bf16 (the learner stays fp32)
+    parser.add_argument('--policy_act_native', type=str2bool, default=True)
     # capture the T-step rollout (policy.act + env.step) into one CUDA graph and replay it
     parser.add_argument('--cuda_graphs', type=str2bool, default=True)
     parser.add_argument('--disc_grad_precision', type=str, default='auto',

@@ -51,6 +51,12 @@ class _Conv(object):
         self.bias[:self.Cout] = bias.detach().float()
         self.scatter = scatter                                                       # (sy, sx, oy, ox) for transposed-conv classes
 
+    def repack(self, weight_oihw, bias):
+        """Refresh the packed kernel IN PLACE (a captured CUDA graph keeps pointing at these buffers)."""
+        w = weight_oihw.detach().permute(2, 3, 1, 0).contiguous().float()
+        self.wpk.copy_(_pack(w, self.Cout == 32))
+        self.bias[:self.Cout].copy_(bias.detach().float())
+
     def out_hw(self, Hin, Win, same):
         if same:
             return (Hin + self.stride - 1) // self.stride, (Win + self.stride - 1) // self.stride
@@ -84,6 +90,16 @@ class _Deconv(object):
                              scatter=(2, 2, py, px))
                 self.classes.append(conv)
 
+    def repack(self, weight_iohw, bias):
+        w = weight_iohw.detach().float()
+        i = 0
+        for py in (0, 1):
+            for px in (0, 1):
+                kys = (3, 1) if py == 0 else (2, 0)
+                kxs = (3, 1) if px == 0 else (2, 0)
+                self.classes[i].repack(w[:, :, kys, :][:, :, :, kxs].permute(1, 0, 2, 3), bias)
+                i += 1
+
     def __call__(self, x, out):
         B, Hin, Win, _ = x.shape
         for conv in self.classes:
@@ -100,8 +116,29 @@ class NativeActor(object):
 
     # ------------------------------------------------------------------
     def sync(self):
-        """(Re)pack the convolution kernels from the PyTorch module's current parameters."""
+        """(Re)pack the convolution kernels from the PyTorch module's current parameters; after the first call the
+        packed buffers are refreshed in place, so a captured CUDA graph of the rollout sees the new weights."""
         pi = self.pi
+        if getattr(self, "x_enc", None) is not None:
+            self.x_enc.repack(pi.x_enc.weight, pi.x_enc.bias)
+            for layer, c in zip(self.add_enc, pi.add_enc):
+                layer.repack(c.weight, c.bias)
+            for (l1, l2), r in zip(self.enc_res, pi.encoder_res):
+                l1.repack(r.c1.weight, r.c1.bias)
+                l2.repack(r.c2.weight, r.c2.bias)
+            for name, L in self.loc.items():
+                head = pi.heads[name]
+                L["deconv0"].repack(head.deconv0.weight, head.deconv0.bias)
+                for (l1, l2), r in zip(L["res"], head.res):
+                    l1.repack(r.c1.weight, r.c1.bias)
+                    l2.repack(r.c2.weight, r.c2.bias)
+                for u, m in zip(L["ups"], head.ups):
+                    u.repack(m.weight, m.bias)
+                L["out"].repack(head.out.weight, head.out.bias)
+            for tag, (wpk, bias, blocks) in self._stacks.items():
+                wpk.copy_(torch.cat([c.wpk.reshape(-1) for blk in blocks for c in blk]))
+                bias.copy_(torch.cat([c.bias[:32] for blk in blocks for c in blk]))
+            return
         self._stacks = {}
         self.x_enc = _Conv(pi.x_enc.weight, pi.x_enc.bias, 1, (2, 2), True)
         self.add_enc = [_Conv(c.weight, c.bias, 2, (0, 0), True) for c in pi.add_enc]
@@ -133,7 +170,7 @@ class NativeActor(object):
             if pk is None:
                 wpk = torch.cat([c.wpk.reshape(-1) for blk in blocks for c in blk]).contiguous()
                 bias = torch.cat([c.bias[:32] for blk in blocks for c in blk]).contiguous()
-                pk = self._stacks[tag] = (wpk, bias)
+                pk = self._stacks[tag] = (wpk, bias, blocks)
             out = self._buf((tag, "fused", H), (B, H, W, C))
             N.check(N.lib().spiral_pres_stack(N.ptr(x), N.ptr(pk[0]), N.ptr(pk[1]), N.ptr(out), B, H, 2 * len(blocks),
                                               N.stream_ptr()), "spiral_pres_stack")

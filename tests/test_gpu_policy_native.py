@@ -97,3 +97,33 @@ def test_native_actor_agrees_with_the_pytorch_policy(envname, L, C, cond):
         assert int(a[:, i].min()) >= 0 and int(a[:, i].max()) < n
     env.step(a)                                       # the sampled actions drive the env
     env.check_status()
+
+
+def test_agent_rollout_with_native_actor_sees_weight_updates():
+    """The (graph-captured) rollout acts through NativeActor; after a learner step sync() refreshes the packed kernels in
+    place, so the next replay uses the new weights."""
+    sp, pol, pn = _mods()
+    from importlib import import_module
+    agent_mod = import_module(sp.__name__ + ".agent")
+    args = sp.get_args(["--env", "simple_mnist", "--color_channel", "1", "--episode_length", "3", "--loss", "gan",
+                        "--disc_dim", "8", "--disc_precision", "fp32", "--policy_act_native", "True", "--cuda_graphs", "True"])
+    env = sp.create_env(args, num_envs=8)
+    ag = agent_mod.Agent(args, env)
+    assert ag.actor is not None
+    ro = ag.rollout()
+    assert ag._graph is not None and not ag._graph_failed
+    before = ag.actor.x_enc.wpk.clone()
+    ptr = ag.actor.x_enc.wpk.data_ptr()
+    ag.train_policy(ro)
+    assert ag.actor.x_enc.wpk.data_ptr() == ptr                      # same buffer (the graph points at it)
+    with torch.no_grad():
+        for p_ in ag.policy.parameters():
+            p_.add_(0.05 * torch.randn_like(p_))                    # a visible update
+    ag.actor.sync()
+    assert not torch.equal(ag.actor.x_enc.wpk, before)
+    ro2 = ag.rollout()
+    env.reset()
+    for t in range(3):
+        assert torch.equal(env.state, ro2["states"][:, t])
+        env.step(ro2["actions"][:, t])
+    assert torch.equal(env.state, ro2["states"][:, 3])
