@@ -300,6 +300,13 @@ int spiral_pconv_forward(const void *x_bf16_dev, const void *w_packed_bf16_dev, 
 int spiral_pres_stack(const void *x_bf16_dev, const void *w_packed_bf16_dev, const float *bias_dev,
                       void *out_bf16_dev, int32_t B, int32_t S, int32_t n_convs, void *stream);
 
+/* Location head, last stage fused (policy.py:275-281 last conv2d_transpose 4x4/2 + ReLU, :290-295 conv 3x3 -> 1 logits):
+ * u bf16 NHWC [B,Hh,Hh,32] -> logits f32 [B,2Hh,2Hh].  w_up: the four parity-class kernels [4][32][2*2*32 + 8] packed as
+ * for spiral_pconv_forward (class py*2+px, channel-permuted rows); w_out: [8][3*3*32 + 8] (row 0 = the kernel). */
+int spiral_phead_last(const void *u_bf16_dev, const void *w_up_packed_dev, const float *bias_up_dev,
+                      const void *w_out_packed_dev, const float *bias_out_dev, float *logits_dev, int32_t B, int32_t Hh,
+                      void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -101,6 +101,7 @@ SYMBOLS = {
                                    C.c_int32, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, _vp, C.c_float, _vp]),
     "spiral_pconv_forward": (C.c_int, [_vp] * 6 + [C.c_int32] * 20 + [_vp]),
     "spiral_pres_stack": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int32, C.c_int32, C.c_int32, _vp]),
+    "spiral_phead_last": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, C.c_int32, C.c_int32, _vp]),
     "spiral_conv_workspace_bytes": (C.c_int64, [C.c_int32] * 5),
     "spiral_conv_forward": (C.c_int, [_vp, _vp, _vp] + [C.c_int32] * 5 + [_vp, _vp]),
     "spiral_conv_dgrad": (C.c_int, [_vp, _vp, _vp] + [C.c_int32] * 5 + [_vp, _vp]),

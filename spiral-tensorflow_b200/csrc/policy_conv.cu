@@ -445,3 +445,175 @@ extern "C" int spiral_pres_stack(const void *x_bf16, const void *w_packed_bf16, 
     const cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? SPIRAL_OK : spiral_cuda_error(e, "spiral_pres_stack");
 }
+
+// ------------------------------------------------------------------------------------------
+// Location head, last stage (policy.py:275-281 last conv2d_transpose 4x4/2 + ReLU, then :290-295 the 3x3 -> 1 channel
+// "conv_1x1" logits): fused.  As two layers the L x L x 32 activation between them is written and read back -- 4 GB
+// per head per step at 8,192 canvases and L = 64 -- to produce 33 MB of logits.  Here a CTA computes a 16 x 16 tile
+// of logits: the transposed convolution's outputs for the 18 x 18 region the 3x3 needs (81 pixels of each of the four
+// parity classes = 24 m16 tiles, three per warp, all of one class) go to shared memory as bf16, then the logits
+// convolution runs from there (N = 8 MMA, one useful column).
+// ------------------------------------------------------------------------------------------
+namespace spiral {
+
+constexpr int kHlT = 16;                         // logits tile
+constexpr int kHlR = kHlT + 2;                   // region of up-conv outputs
+constexpr int kHlI = kHlT / 2 + 2;               // input tile (10 x 10)
+constexpr int kHlKu = 4 * 32, kHlKSu = kHlKu + 8;    // up-conv class kernel: K = 2*2*32
+constexpr int kHlKo = 9 * 32, kHlKSo = kHlKo + 8;    // logits kernel: K = 3*3*32
+
+__global__ void __launch_bounds__(256)
+phead_last_kernel(const __nv_bfloat16 *__restrict__ u, const __nv_bfloat16 *__restrict__ w_up /*[4][32][KSu] permuted*/,
+                  const float *__restrict__ bias_up, const __nv_bfloat16 *__restrict__ w_out /*[8][KSo]*/, const float *__restrict__ bias_out_p,
+                  float *__restrict__ logits, int B, int Hh /* input map = L/2 */)
+{
+    extern __shared__ __align__(16) uint8_t sm_raw[];
+    uint16_t *s_in = reinterpret_cast<uint16_t *>(sm_raw);                  // [10][10][32]
+    uint16_t *s_wu = s_in + kHlI * kHlI * 32;                                // [4][32][KSu]
+    uint16_t *s_up = s_wu + 4 * 32 * kHlKSu;                                 // [18][18][32]
+    uint16_t *s_wo = s_up + kHlR * kHlR * 32;                                // [8][KSo]
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int L = 2 * Hh, tiles = L / kHlT;
+    const int img = blockIdx.x / (tiles * tiles);
+    const int trem = blockIdx.x % (tiles * tiles);
+    const int Y0 = (trem / tiles) * kHlT, X0 = (trem % tiles) * kHlT;
+    const int a0 = Y0 / 2 - 1, b0 = X0 / 2 - 1;                              // input tile origin
+
+    for (int i = tid; i < 4 * 32 * kHlKSu / 8; i += 256) reinterpret_cast<uint4 *>(s_wu)[i] = __ldg(reinterpret_cast<const uint4 *>(w_up) + i);
+    for (int i = tid; i < 8 * kHlKSo / 8; i += 256) reinterpret_cast<uint4 *>(s_wo)[i] = __ldg(reinterpret_cast<const uint4 *>(w_out) + i);
+    const uint16_t *ui = reinterpret_cast<const uint16_t *>(u) + (size_t)img * Hh * Hh * 32;
+    for (int i = tid; i < kHlI * kHlI * 4; i += 256) {
+        const int pix = i >> 2, v = i & 3;
+        const int ly = pix / kHlI, lx = pix % kHlI;
+        const int iy = a0 + ly, ix = b0 + lx;
+        uint4 val = make_uint4(0, 0, 0, 0);
+        if (iy >= 0 && iy < Hh && ix >= 0 && ix < Hh) val = __ldg(reinterpret_cast<const uint4 *>(ui + ((size_t)iy * Hh + ix) * 32) + v);
+        reinterpret_cast<uint4 *>(s_in)[i] = val;
+    }
+    __syncthreads();
+
+    const int g = lane >> 2, t = lane & 3;
+    // ---- transposed convolution: warp -> class (warp / 2), m-tiles 3 * (warp & 1) .. +2 of that class's 81 pixels ----
+    {
+        const int cls = warp >> 1, py = cls >> 1, px = cls & 1;
+        const uint16_t *w = s_wu + cls * 32 * kHlKSu;
+        int base[6];
+        int q[6];
+#pragma unroll
+        for (int r = 0; r < 6; r++) {
+            q[r] = ((warp & 1) * 3 + (r >> 1)) * 16 + g + 8 * (r & 1);
+            const int qq = q[r] < 81 ? q[r] : 0;
+            base[r] = ((qq / 9) * kHlI + (qq % 9)) * 32;
+        }
+        float acc[3][4][4];
+#pragma unroll
+        for (int m = 0; m < 3; m++)
+#pragma unroll
+            for (int nt = 0; nt < 4; nt++)
+#pragma unroll
+                for (int j = 0; j < 4; j++) acc[m][nt][j] = 0.0f;
+#pragma unroll 1
+        for (int ks = 0; ks < kHlKu / 16; ks++) {
+            const int k0 = ks * 16 + 2 * t;
+            const int tap0 = k0 >> 5, tap8 = (k0 + 8) >> 5;
+            const int o0 = ((tap0 >> 1) * kHlI + (tap0 & 1)) * 32 + (k0 & 31), o8 = ((tap8 >> 1) * kHlI + (tap8 & 1)) * 32 + ((k0 + 8) & 31);
+            uint32_t a[3][4];
+#pragma unroll
+            for (int m = 0; m < 3; m++) {
+                a[m][0] = *reinterpret_cast<const uint32_t *>(s_in + base[2 * m] + o0);
+                a[m][1] = *reinterpret_cast<const uint32_t *>(s_in + base[2 * m + 1] + o0);
+                a[m][2] = *reinterpret_cast<const uint32_t *>(s_in + base[2 * m] + o8);
+                a[m][3] = *reinterpret_cast<const uint32_t *>(s_in + base[2 * m + 1] + o8);
+            }
+#pragma unroll
+            for (int nt = 0; nt < 4; nt++) {
+                const int wrow = (nt * 8 + g) * kHlKSu + k0;
+                uint32_t b[2];
+                b[0] = *reinterpret_cast<const uint32_t *>(w + wrow);
+                b[1] = *reinterpret_cast<const uint32_t *>(w + wrow + 8);
+#pragma unroll
+                for (int m = 0; m < 3; m++) pc_mma(acc[m][nt], a[m], b);
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < 6; r++) {
+            if (q[r] >= 81) continue;
+            const int m = r >> 1, half = r & 1;
+            const int i = q[r] / 9, j = q[r] % 9;
+            const int ry = 2 * i + (py == 0 ? 1 : 0), rx = 2 * j + (px == 0 ? 1 : 0);      // position in the 18 x 18 region
+            const int Y = Y0 - 1 + ry, X = X0 - 1 + rx;
+            const bool inside = Y >= 0 && Y < L && X >= 0 && X < L;                          // outside the map: the 3x3's zero padding
+            uint32_t wv[4];
+#pragma unroll
+            for (int nt = 0; nt < 4; nt++) {
+                float v0 = acc[m][nt][2 * half] + __ldg(bias_up + t * 8 + 2 * nt);
+                float v1 = acc[m][nt][2 * half + 1] + __ldg(bias_up + t * 8 + 2 * nt + 1);
+                v0 = inside ? fmaxf(v0, 0.0f) : 0.0f;
+                v1 = inside ? fmaxf(v1, 0.0f) : 0.0f;
+                wv[nt] = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(v0)) | ((uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(v1)) << 16);
+            }
+            *reinterpret_cast<uint4 *>(s_up + (ry * kHlR + rx) * 32 + t * 8) = make_uint4(wv[0], wv[1], wv[2], wv[3]);
+        }
+    }
+    __syncthreads();
+
+    // ---- logits: 3x3 over the region, 256 pixels = 16 m-tiles, two per warp; column 0 of an N = 8 MMA ----
+    {
+        int base[4];
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+            const int p = (warp * 2 + (r >> 1)) * 16 + g + 8 * (r & 1);       // pixel of the 16 x 16 tile
+            base[r] = ((p >> 4) * kHlR + (p & 15)) * 32;                      // top-left of its 3x3 window in the region
+        }
+        float acc[2][4];
+#pragma unroll
+        for (int m = 0; m < 2; m++)
+#pragma unroll
+            for (int j = 0; j < 4; j++) acc[m][j] = 0.0f;
+#pragma unroll 1
+        for (int ks = 0; ks < kHlKo / 16; ks++) {
+            const int k0 = ks * 16 + 2 * t;
+            const int tap0 = k0 >> 5, tap8 = (k0 + 8) >> 5;
+            const int o0 = ((tap0 / 3) * kHlR + tap0 % 3) * 32 + (k0 & 31), o8 = ((tap8 / 3) * kHlR + tap8 % 3) * 32 + ((k0 + 8) & 31);
+            const int wrow = g * kHlKSo + k0;
+            uint32_t b[2];
+            b[0] = *reinterpret_cast<const uint32_t *>(s_wo + wrow);
+            b[1] = *reinterpret_cast<const uint32_t *>(s_wo + wrow + 8);
+#pragma unroll
+            for (int m = 0; m < 2; m++) {
+                uint32_t a[4];
+                a[0] = *reinterpret_cast<const uint32_t *>(s_up + base[2 * m] + o0);
+                a[1] = *reinterpret_cast<const uint32_t *>(s_up + base[2 * m + 1] + o0);
+                a[2] = *reinterpret_cast<const uint32_t *>(s_up + base[2 * m] + o8);
+                a[3] = *reinterpret_cast<const uint32_t *>(s_up + base[2 * m + 1] + o8);
+                pc_mma(acc[m], a, b);
+            }
+        }
+        if (t == 0) {                                                          // column 0 of the accumulator tile
+            const float bias_out = __ldg(bias_out_p);
+            float *lo = logits + (size_t)img * L * L;
+#pragma unroll
+            for (int r = 0; r < 4; r++) {
+                const int p = (warp * 2 + (r >> 1)) * 16 + g + 8 * (r & 1);
+                lo[(size_t)(Y0 + (p >> 4)) * L + X0 + (p & 15)] = acc[r >> 1][2 * (r & 1)] + bias_out;
+            }
+        }
+    }
+}
+
+}  // namespace spiral
+
+extern "C" int spiral_phead_last(const void *u_bf16, const void *w_up_packed, const float *bias_up, const void *w_out_packed,
+                                 const float *bias_out, float *logits, int32_t B, int32_t Hh, void *stream)
+{
+    SPIRAL_REQUIRE(u_bf16); SPIRAL_REQUIRE(w_up_packed); SPIRAL_REQUIRE(bias_up); SPIRAL_REQUIRE(w_out_packed); SPIRAL_REQUIRE(bias_out); SPIRAL_REQUIRE(logits);
+    if (B <= 0 || Hh < 8 || (Hh % 8) != 0) return spiral_set_error(SPIRAL_EINVAL, "phead_last: input map must be a multiple of 8 (got %d)", Hh);
+    const size_t smem = ((size_t)kHlI * kHlI * 32 + 4 * 32 * kHlKSu + kHlR * kHlR * 32 + 8 * kHlKSo) * 2;
+    static bool attr = false;
+    if (!attr) { cudaFuncSetAttribute(phead_last_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
+    const int tiles = (2 * Hh) / kHlT;
+    phead_last_kernel<<<B * tiles * tiles, 256, smem, (cudaStream_t)stream>>>((const __nv_bfloat16 *)u_bf16, (const __nv_bfloat16 *)w_up_packed,
+                                                                            bias_up, (const __nv_bfloat16 *)w_out_packed, bias_out, logits, B, Hh);
+    const cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? SPIRAL_OK : spiral_cuda_error(e, "spiral_phead_last");
+}

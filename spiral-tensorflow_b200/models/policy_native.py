@@ -136,6 +136,9 @@ class NativeActor(object):
                     u.repack(m.weight, m.bias)
                 L["out"].repack(head.out.weight, head.out.bias)
             for tag, (wpk, bias, blocks) in self._stacks.items():
+                if bias is None:                            # fused last stage of a location head: the four class kernels
+                    wpk.copy_(torch.cat([c.wpk.reshape(-1) for c in blocks.classes]))
+                    continue
                 wpk.copy_(torch.cat([c.wpk.reshape(-1) for blk in blocks for c in blk]))
                 bias.copy_(torch.cat([c.bias[:32] for blk in blocks for c in blk]))
             return
@@ -211,9 +214,20 @@ class NativeActor(object):
         h = L["deconv0"](x, self._buf((name, "d0"), (B, 8, 8, 32)))
         h = self._res_stack(h, L["res"], name + "r")
         H = 8
-        for i, up in enumerate(L["ups"]):
+        ups = L["ups"]
+        fuse_last = len(ups) > 0                         # last up-convolution + the 3x3 -> 1 logits convolution in one kernel
+        for i, up in enumerate(ups[:-1] if fuse_last else ups):
             h = up(h, self._buf((name, "u", i), (B, 2 * H, 2 * H, 32)))
             H *= 2
+        if fuse_last:
+            pk = self._stacks.get((name, "last"))
+            if pk is None:
+                w_up = torch.cat([c.wpk.reshape(-1) for c in ups[-1].classes]).contiguous()
+                pk = self._stacks[(name, "last")] = (w_up, None, ups[-1])
+            logits = self._buf((name, "o"), (B, 2 * H, 2 * H), torch.float32)
+            N.check(N.lib().spiral_phead_last(N.ptr(h), N.ptr(pk[0]), N.ptr(ups[-1].classes[0].bias), N.ptr(L["out"].wpk),
+                                              N.ptr(L["out"].bias), N.ptr(logits), B, H, N.stream_ptr()), "spiral_phead_last")
+            return logits.view(B, 4 * H * H)
         logits = L["out"](h, self._buf((name, "o"), (B, H, H, 1), torch.float32), H, H, out_f32=True)
         return logits.view(B, H * H)
 
