@@ -61,6 +61,7 @@ def parse():
     p.add_argument("--cpu_seconds", type=float, default=15.0, help="target seconds of the bounded CPU sample")
     p.add_argument("--jump", default="True")
     p.add_argument("--no_secondary", action="store_true", help="skip the 1024-canvas secondary measurement")
+    p.add_argument("--pipeline", action="store_true", help="also time the two-stream pipelined schedule")
     return p.parse_args()
 
 
@@ -283,6 +284,53 @@ def run_ours(args):
                 dist.barrier()
             torch.cuda.synchronize()
 
+        def timed_pipelined():
+            """Two-stage software pipeline over consecutive batches, the reference's actor / learner split
+            (actors render episode i+1 while the learner scores episode i, agent.py:336-374 vs rl_utils.py:185-238):
+            stream R renders, stream S runs the D reward + A2C loss on a snapshot of the final observations.  All K
+            renders and all K reward/loss passes (pipeline fill and drain included) are inside the timed region."""
+            sR, sS = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+            snap = torch.empty_like(env.state)
+            cur = torch.cuda.current_stream()
+
+            def run(n):
+                sR.wait_stream(cur)
+                sS.wait_stream(cur)
+                scored = None
+                for _ in range(n):
+                    with torch.cuda.stream(sR):
+                        env.reset()
+                        for t in range(T):
+                            env.step(acts_dev[t])
+                        if scored is not None:
+                            sR.wait_event(scored)          # the previous snapshot has been consumed
+                        snap.copy_(env.state)
+                        rendered = torch.cuda.Event()
+                        rendered.record(sR)
+                    with torch.cuda.stream(sS):
+                        sS.wait_event(rendered)
+                        disc.forward(snap, logits_out=lg, probs_out=probs)
+                        rewards[:, -1] = probs
+                        rl.a2c_loss(logits, acts_bt, rewards, values_dev, vf_dev, 0.99, 1.0, 0.01, out=a2c_out)
+                        scored = torch.cuda.Event()
+                        scored.record(sS)
+                cur.wait_stream(sR)
+                cur.wait_stream(sS)
+
+            run(args.warmup)
+            barrier()
+            s, e = ev(), ev()
+            s.record()
+            run(args.steps)
+            e.record()
+            barrier()
+            ms = s.elapsed_time(e)
+            if world > 1:
+                t = torch.tensor([ms], device=dev, dtype=torch.float64)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                ms = float(t.item())
+            return ms
+
         def timed(resident, record):
             for _ in range(args.warmup):
                 episode(resident)
@@ -305,6 +353,7 @@ def run_ours(args):
             sampler.start()
         ms = timed(resident=True, record=True)
         ms_e2e = timed(resident=False, record=False)
+        ms_pipe = timed_pipelined() if args.pipeline else None
         if sampler:
             sampler.stop_flag = True
             sampler.join(timeout=2)
@@ -354,6 +403,9 @@ def run_ours(args):
                             d2h_bytes_per_step=int((B + 4) * 4), ms_per_step=ms_e2e / args.steps),
                    gpu_launches=launches_per_episode * args.steps,
                    kernel_ms_per_step=share, roofline=roof, clocks=sampler.summary() if sampler else None)
+        if ms_pipe is not None:
+            out["pipelined"] = dict(value=steps_total / (ms_pipe * 1e-3), unit="env-steps/s", ms_per_step=ms_pipe / args.steps,
+                                    note="render(i+1) on one stream overlapped with D reward + A2C(i) on another")
         del env, disc, logits, a2c_out
         torch.cuda.empty_cache()
         return out, (acs_list, head_list, C, L, T)

@@ -715,6 +715,56 @@ __device__ __forceinline__ float dab_rr(const EnvParams &P, int xp, int yp, floa
     return 1.0f - visibilityNear;
 }
 
+// calculate_rr_antialiased for the upright round dab (P.fast_spans: sn == 1.0f, l2 == cs*cs + 1 == 1.0f): the same
+// expression tree as dab_rr with the multiplications by sn / l2 (exact identities in IEEE arithmetic: x * 1.0f == x,
+// x / 1.0f == x, a - (-1.0f) == a + 1.0f) removed and the uniform product cs * rad_area_1 hoisted.  Bit-identical.
+__device__ __forceinline__ float dab_rr_round(float cs, float rad_area_1, float cs_rad_area_1, int xp, int yp, float x, float y,
+                                              float one_over_radius2, float r_aa_start)
+{
+    const float pixel_right = x - (float)xp;
+    const float pixel_bottom = y - (float)yp;
+    const float pixel_center_x = pixel_right - 0.5f;
+    const float pixel_center_y = pixel_bottom - 0.5f;
+    const float pixel_left = pixel_right - 1.0f;
+    const float pixel_top = pixel_bottom - 1.0f;
+    float nearest_x, nearest_y, rr_near;
+    if (pixel_left < 0 && pixel_right > 0 && pixel_top < 0 && pixel_bottom > 0) {
+        nearest_x = 0;
+        nearest_y = 0;
+        rr_near = 0;
+    } else {
+        const float t = pixel_center_x * cs + pixel_center_y;
+        nearest_x = cs * t;
+        nearest_y = t;
+        nearest_x = nearest_x < pixel_left ? pixel_left : (nearest_x > pixel_right ? pixel_right : nearest_x);
+        nearest_y = nearest_y < pixel_top ? pixel_top : (nearest_y > pixel_bottom ? pixel_bottom : nearest_y);
+        const float yyr = nearest_y * cs - nearest_x;
+        const float xxr = nearest_y + nearest_x * cs;
+        const float r_near = (yyr * yyr + xxr * xxr);
+        rr_near = r_near * one_over_radius2;
+    }
+    if (rr_near > 1.0f) return rr_near;
+    const float center_sign = (pixel_center_x - cs) - cs * (pixel_center_y + 1.0f);
+    float farthest_x, farthest_y;
+    if (center_sign < 0) {
+        farthest_x = nearest_x - rad_area_1;
+        farthest_y = nearest_y + cs_rad_area_1;
+    } else {
+        farthest_x = nearest_x + rad_area_1;
+        farthest_y = nearest_y - cs_rad_area_1;
+    }
+    const float yyr = farthest_y * cs - farthest_x;
+    const float xxr = farthest_y + farthest_x * cs;
+    const float r_far = (yyr * yyr + xxr * xxr);
+    const float rr_far = r_far * one_over_radius2;
+    if (r_far < r_aa_start) return (rr_far + rr_near) * 0.5f;
+    float visibilityNear = 1.0f - rr_near;
+    const float delta = rr_far - rr_near;
+    const float delta2 = 1.0f + delta;
+    visibilityNear /= delta2;
+    return 1.0f - visibilityNear;
+}
+
 // Sparse in-place compositing: ONE WARP per canvas.
 //
 // A stroke is a serial chain of heavily overlapping dabs (6 + 6 per radius), each touching fewer than
@@ -810,6 +860,7 @@ composite_kernel(const __grid_constant__ EnvParams P, uint16_t *__restrict__ can
         tile[idx] = make_uint2(r | (g << 16), bl | (al << 16));
     };
 
+    const float cs_rad_area_1 = P.cs * P.rad_area_1;
     int base = 0;
     while (base < n_dabs) {
         // ---- phase 0: finalise, count candidates ----
@@ -910,8 +961,15 @@ composite_kernel(const __grid_constant__ EnvParams P, uint16_t *__restrict__ can
             const SharedDab &cur = sd[e >> 8];
             const uint32_t box = cur.box;
             const int xp = (int)(box & 0xff) + (int)(e & 15), yp = (int)((box >> 8) & 0xff) + (int)((e >> 4) & 15);
-            const uint32_t opa_ = mask_of(cur, xp, yp);
+            // pairs only exist on the fast path: upright round dabs with radius < 3 (anti-aliased rr)
+            const float rr = dab_rr_round(P.cs, P.rad_area_1, cs_rad_area_1, xp, yp, cur.x, cur.y, cur.one_over_r2, cur.r_aa_start);
+            const float fac = rr <= cur.hardness ? cur.seg1_slope : cur.seg2_slope;
+            float opa = rr <= cur.hardness ? 1.0f : cur.seg2_offset;
+            opa += rr * fac;
+            if (rr > 1.0f) opa = 0.0f;
+            const uint32_t opa_ = (uint32_t)(unsigned short)(opa * 32768.0f);
             so[k] = (uint16_t)(opa_ * cur.opacity / (1u << 15));
+            sp[k] = (uint16_t)(yp * kTile + xp);             // phase 2 only needs the pixel's index in the tile
         }
         __syncwarp();
 
@@ -919,14 +977,9 @@ composite_kernel(const __grid_constant__ EnvParams P, uint16_t *__restrict__ can
         for (int j = 0; j < m; j++) {
             const int o0 = soff[j], o1 = soff[j + 1];
             if (o0 == o1) continue;
-            const uint32_t box = sd[j].box;
-            const int bx0 = box & 0xff, by0 = (box >> 8) & 0xff;
             for (int k = o0 + lane; k < o1; k += 32) {
                 const uint32_t opa_a = so[k];
-                if (opa_a) {
-                    const uint32_t e = sp[k];
-                    blend((by0 + (int)((e >> 4) & 15)) * kTile + bx0 + (int)(e & 15), opa_a);
-                }
+                if (opa_a) blend((int)sp[k], opa_a);
             }
             __syncwarp();                                // orders this dab's stores before the next dab's loads
         }
