@@ -765,6 +765,16 @@ __device__ __forceinline__ float dab_rr_round(float cs, float rad_area_1, float 
     return 1.0f - visibilityNear;
 }
 
+// Half-width of a candidate span.  The candidate list only has to be a SUPERSET of the pixels with a non-zero mask
+// (the disc is inflated by 0.1 % + 0.01 px), so the hardware's approximate square root (error ~2^-22) is enough; the
+// list is built twice (count, write) from the same instruction, so both passes agree.
+__device__ __forceinline__ float span_sqrt(float h2)
+{
+    float h;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(h) : "f"(h2));
+    return h;
+}
+
 // Sparse in-place compositing: ONE WARP per canvas.
 //
 // A stroke is a serial chain of heavily overlapping dabs (6 + 6 per radius), each touching fewer than
@@ -881,7 +891,7 @@ composite_kernel(const __grid_constant__ EnvParams P, uint16_t *__restrict__ can
                     const float dyc = f.y - ((float)yp + 0.5f);
                     const float h2 = rlim2 - dyc * dyc;
                     if (h2 < 0.0f) continue;
-                    const float h = sqrtf(h2);
+                    const float h = span_sqrt(h2);
                     const int xa = max(f.x0, (int)floorf(f.x - h - 1.0f));
                     const int xb = min(f.x1, (int)floorf(f.x + h));
                     cnt += max(0, xb - xa + 1);
@@ -947,7 +957,7 @@ composite_kernel(const __grid_constant__ EnvParams P, uint16_t *__restrict__ can
                 const float dyc = f.y - ((float)yp + 0.5f);
                 const float h2 = rlim2 - dyc * dyc;
                 if (h2 < 0.0f) continue;
-                const float h = sqrtf(h2);
+                const float h = span_sqrt(h2);
                 const int xa = max(f.x0, (int)floorf(f.x - h - 1.0f));
                 const int xb = min(f.x1, (int)floorf(f.x + h));
                 for (int xp = xa; xp <= xb; xp++) sp[n++] = (uint16_t)((lane << 8) | ((yp - f.y0) << 4) | (xp - f.x0));
@@ -977,9 +987,18 @@ composite_kernel(const __grid_constant__ EnvParams P, uint16_t *__restrict__ can
         for (int j = 0; j < m; j++) {
             const int o0 = soff[j], o1 = soff[j + 1];
             if (o0 == o1) continue;
-            for (int k = o0 + lane; k < o1; k += 32) {
+            // a dab on this path has at most kListCap = 64 candidate pixels: two passes, no loop
+            int k = o0 + lane;
+            if (k < o1) {
                 const uint32_t opa_a = so[k];
                 if (opa_a) blend((int)sp[k], opa_a);
+            }
+            if (o1 - o0 > 32) {                          // warp-uniform, rare (radius > ~2.5)
+                k += 32;
+                if (k < o1) {
+                    const uint32_t opa_a = so[k];
+                    if (opa_a) blend((int)sp[k], opa_a);
+                }
             }
             __syncwarp();                                // orders this dab's stores before the next dab's loads
         }
