@@ -43,7 +43,33 @@ struct ConvTcParams {
     int M;                    // B * Ho * Wo
     int x3;                   // 1: hi*hi + hi*lo + lo*hi ; 0: hi*hi only
     int mt, nt;               // output tiles per work item along M / N: (1,1), (2,1) or (1,2)
+    int pos;                  // 1: position-pure tiles -- 128 images at ONE output pixel (small maps, B % 128 == 0)
 };
+
+// Where an m-tile sits.  Row-major tiles (pos == 0) are 128 consecutive rows of [B, Ho, Wo]: whole rows of one image
+// or whole small images.  On the small maps of the deep layers (Ho <= 8) such a tile mixes every output position, so
+// no kernel tap is padding for ALL of its rows and the SAME-padding zeros are multiplied like data (layer 4: 51 % of
+// the MMAs).  Position-pure tiles take 128 images at one output pixel -- the TMA box is {64 ch, 1 px, 1 row, 128
+// images} -- so the tap mask is exact per tile and the padding taps are neither loaded nor multiplied.
+struct TileOrigin { int img0, oy0, ox0, posi; };
+__device__ __forceinline__ TileOrigin tile_origin(const ConvTcParams &p, int Ho, int m_tile)
+{
+    TileOrigin t;
+    if (p.pos) {
+        const int hw = Ho * Ho;
+        t.posi = m_tile % hw;                       // positions interleaved: every CTA sees the same mix of tap counts
+        t.img0 = (m_tile / hw) * kBM;
+        t.oy0 = t.posi / Ho;
+        t.ox0 = t.posi % Ho;
+    } else {
+        const int m0 = m_tile * kBM;
+        t.img0 = m0 / (Ho * Ho);
+        t.oy0 = (m0 % (Ho * Ho)) / Ho;
+        t.ox0 = 0;
+        t.posi = 0;
+    }
+    return t;
+}
 
 // Persistent: gridDim.x CTAs (one per SM) walk the (m_tile, n_tile) space; the TMEM accumulator is double
 // buffered (2 x kBN columns), so while the four epilogue warps drain tile i (tcgen05.ld, + bias, fp32 stores,
@@ -58,10 +84,20 @@ __device__ __forceinline__ void epilogue_bar_sync()       // the 4 epilogue warp
     asm volatile("bar.sync 1, 128;" ::: "memory");
 }
 
-__device__ __forceinline__ uint32_t conv_tap_mask(const ConvTcParams &p, int Ho, int oy0)
+__device__ __forceinline__ uint32_t conv_tap_mask(const ConvTcParams &p, int Ho, int oy0, int ox0)
 {
     // taps (ky, kx) that touch at least one real input pixel for this tile
     uint32_t tap_mask = 0;
+    if (p.pos) {
+        for (int ky = 0; ky < 5; ky++) {
+            const int iy = 2 * oy0 + ky - 1;
+            for (int kx = 0; kx < 5; kx++) {
+                const int ix = 2 * ox0 + kx - 1;
+                if (iy >= 0 && iy < p.H && ix >= 0 && ix < p.H) tap_mask |= 1u << (ky * 5 + kx);
+            }
+        }
+        return tap_mask;
+    }
     const int oy_lo = oy0, oy_hi = (p.bb > 1) ? Ho - 1 : oy0 + p.bh - 1;
     for (int ky = 0; ky < 5; ky++) {
         const bool y_ok = (2 * oy_hi + ky - 1 >= 0) && (2 * oy_lo + ky - 1 < p.H);
@@ -140,8 +176,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
         mt_here = min(mt, m_tiles - mg * mt);
         uint32_t mask = 0;
         for (int i = 0; i < mt_here; i++) {
-            const int m0 = (mg * mt + i) * kBM;
-            mask |= conv_tap_mask(p, Ho, (m0 % (Ho * Ho)) / Ho);
+            const TileOrigin to = tile_origin(p, Ho, mg * mt + i);
+            mask |= conv_tap_mask(p, Ho, to.oy0, to.ox0);
         }
         return mask;
     };
@@ -166,11 +202,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
                         mbar_expect_tx(full, tiles_bytes);
                         const int c0 = ch * kBK;
                         for (int i = 0; i < mt_here; i++) {
-                            const int m0 = (mg * mt + i) * kBM;
-                            const int img0 = m0 / (Ho * Ho), oy0 = (m0 % (Ho * Ho)) / Ho;
-                            const int ix0 = kx - 1, iy0 = 2 * oy0 + ky - 1;
-                            tma_load_4d(stage + (2 * i) * kTileBytes, &map_a_hi, full, c0, ix0, iy0, img0);
-                            if (p.x3) tma_load_4d(stage + (2 * i + 1) * kTileBytes, &map_a_lo, full, c0, ix0, iy0, img0);
+                            const TileOrigin to = tile_origin(p, Ho, mg * mt + i);
+                            const int ix0 = 2 * to.ox0 + kx - 1, iy0 = 2 * to.oy0 + ky - 1;
+                            tma_load_4d(stage + (2 * i) * kTileBytes, &map_a_hi, full, c0, ix0, iy0, to.img0);
+                            if (p.x3) tma_load_4d(stage + (2 * i + 1) * kTileBytes, &map_a_lo, full, c0, ix0, iy0, to.img0);
                         }
                         for (int j = 0; j < nt; j++) {
                             const int n0 = (ng * nt + j) * kBN;
@@ -240,11 +275,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a_hi, const __grid_consta
             for (int i = 0; i < mt_here; i++) {
                 for (int j = 0; j < nt; j++) {
                     const int m_tile = mg * mt + i, n_tile = ng * nt + j;
-                    const int m0 = m_tile * kBM;
                     const uint32_t tmem_acc = tmem_base + (uint32_t)((b * per_acc + i * nt + j) * kBN);
                     const int row = q * 32 + lane;
-                    const int m = m0 + row;
-                    const bool row_ok = m < p.M;
+                    int m = m_tile * kBM + row;
+                    bool row_ok = m < p.M;
+                    if (p.pos) {                                   // row = image, all at output pixel posi
+                        const TileOrigin to = tile_origin(p, Ho, m_tile);
+                        row_ok = to.img0 + row < p.B;
+                        m = (to.img0 + row) * (Ho * Ho) + to.posi;
+                    }
                     float *orow = out + (size_t)m * p.Cout + (size_t)n_tile * kBN;
 #pragma unroll 1
                     for (int cb = 0; cb < kBN; cb += 32) {
@@ -320,6 +359,18 @@ static cudaError_t conv_tc_set_smem()
 
 // tiles per work item: two n-tiles share A when Cout >= 256, two m-tiles share W when Cout = 128 -- as long as
 // enough work items remain to fill the 148 SMs (SPIRAL_CONV_PAIR=0 disables: profiling)
+// position-pure tiles (see TileOrigin): maps of 2x2 .. 8x8 output pixels, whole tiles of 128 images
+// (SPIRAL_CONV_POS=0 disables: profiling)
+static int conv_tc_position_tiles(int batch, int Ho)
+{
+    static int enabled = -1;
+    if (enabled < 0) {
+        const char *e = getenv("SPIRAL_CONV_POS");
+        enabled = e ? (atoi(e) != 0) : 1;
+    }
+    return (enabled && Ho >= 2 && Ho <= 8 && batch >= kBM && (batch % kBM) == 0) ? 1 : 0;
+}
+
 static void conv_tc_pairing(ConvTcParams *p, int mtiles)
 {
     p->mt = 1;
@@ -332,7 +383,7 @@ static void conv_tc_pairing(ConvTcParams *p, int mtiles)
     if (!enabled) return;
     const int ntiles = p->Cout / kBN;
     if (ntiles >= 2 && (ntiles % 2) == 0 && (long long)mtiles * (ntiles / 2) >= 148) p->nt = 2;
-    else if (mtiles >= 2 * 148) p->mt = 2;
+    else if (mtiles >= 2 * 148) p->mt = 2;      // with position-pure tiles the pair's tap masks differ: the union is loaded
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -546,6 +597,8 @@ int disc_tc_forward(SpiralDisc *d, const float *x, int batch, float *logits, flo
         p.B = batch; p.H = H; p.Cin = Cin; p.Cout = Cout; p.M = batch * Ho * Ho; p.x3 = x3;
         if (Ho * Ho >= kBM) { p.bw = Ho; p.bh = kBM / Ho; p.bb = 1; }
         else { p.bw = Ho; p.bh = Ho; p.bb = kBM / (Ho * Ho); }
+        p.pos = conv_tc_position_tiles(batch, Ho);
+        if (p.pos) { p.bw = 1; p.bh = 1; p.bb = kBM; }
         CUtensorMap ma_hi, ma_lo, mw_hi, mw_lo;
         int er = encode_act_map(t, &ma_hi, ahi, batch, H, Cin, p.bw, p.bh, p.bb);
         er |= encode_act_map(t, &ma_lo, alo, batch, H, Cin, p.bw, p.bh, p.bb);
@@ -603,6 +656,8 @@ int conv_tc_layer(void *a_hi, void *a_lo, void *w_hi, void *w_lo, float *out, in
     p.B = B; p.H = H; p.Cin = Cin; p.Cout = Cout; p.M = B * Ho * Ho; p.x3 = x3;
     if (Ho * Ho >= kBM) { p.bw = Ho; p.bh = kBM / Ho; p.bb = 1; }
     else { p.bw = Ho; p.bh = Ho; p.bb = kBM / (Ho * Ho); }
+    p.pos = conv_tc_position_tiles(B, Ho);
+    if (p.pos) { p.bw = 1; p.bh = 1; p.bb = kBM; }
     CUtensorMap ma_hi, ma_lo, mw_hi, mw_lo;
     int er = encode_act_map(&t, &ma_hi, a_hi, B, H, Cin, p.bw, p.bh, p.bb);
     er |= encode_act_map(&t, &ma_lo, a_lo, B, H, Cin, p.bw, p.bh, p.bb);

@@ -79,7 +79,9 @@ def test_a2c_autograd_wrapper_backpropagates():
 @pytest.mark.parametrize("C,dd,bn,B,prec", [(1, 8, True, 16, "fp32"), (3, 16, True, 8, "fp32"),
                                             (1, 8, False, 5, "fp32"), (3, 64, True, 4, "fp32"),
                                             (3, 64, True, 16, "bf16x3"), (1, 64, True, 130, "bf16x3"),
-                                            (3, 64, False, 8, "bf16x3"), (3, 64, True, 16, "bf16")])
+                                            (3, 64, False, 8, "bf16x3"), (3, 64, True, 16, "bf16"),
+                                            # whole tiles of 128 images: position-pure tiles on the 2x2 .. 8x8 maps
+                                            (3, 64, True, 128, "bf16x3"), (1, 64, True, 256, "bf16x3")])
 def test_discriminator_forward_matches_oracle(C, dd, bn, B, prec):
     sp = _sp()
     from oracle import disc_oracle as do
