@@ -52,9 +52,14 @@ DM_HD double pow2i(int k) { return bits_to_double((uint64_t)(k + 1023) << 52); }
 
 DM_HD double det_exp(double x)
 {
-    if (x != x) return x;
-    if (x > 709.0) return bits_to_double(0x7ff0000000000000ULL);
-    if (x < -745.0) return 0.0;
+    // |x| <= 700 (false for NaN) is the only case the rasteriser ever sees: one comparison instead of three, and the
+    // result 2^k * p is a normal number, so ONE exact scaling gives the same bits as the two-step one below
+    const bool small = fabs(x) <= 700.0;
+    if (!small) {
+        if (x != x) return x;
+        if (x > 709.0) return bits_to_double(0x7ff0000000000000ULL);
+        if (x < -745.0) return 0.0;
+    }
     const double kd = rint(x * 0x1.71547652b82fep+0);
     double r = fma(-kd, 0x1.62e42fee00000p-1, x);
     r = fma(-kd, 0x1.a39ef35793c76p-33, r);
@@ -74,6 +79,7 @@ DM_HD double det_exp(double x)
     double p = fma(b1, r4, b0);
     p = fma(b2, r8, p);
     const int ki = (int)kd;
+    if (small) return p * pow2i(ki);
     const int k1 = ki / 2;
     const int k2 = ki - k1;
     return p * pow2i(k1) * pow2i(k2);

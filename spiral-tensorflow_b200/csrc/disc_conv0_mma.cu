@@ -102,27 +102,56 @@ conv0_mma_kernel(const float *__restrict__ x, const __nv_bfloat16 *__restrict__ 
     const int g = lane >> 2, t = lane & 3;
     const int base0 = ((2 * warp) * kC0Iw + 2 * g) * CIN;              // pixel g
     const int base1 = base0 + 16 * CIN;                                  // pixel g + 8
+    __shared__ float s_bias[kC0Cout];
+    if (tid < kC0Cout) s_bias[tid] = __ldg(bias + tid);
+    const float *bias_r = s_bias + t * 16;                               // the thread's channels t*16 .. t*16+15
+
+    // Input tile staging, software-pipelined: the raw fp32 values of tile i+1 are fetched with cp.async into a
+    // shared staging buffer while tile i's MMAs run, and converted to bf16 hi/lo after them, so the global-load
+    // latency (ncu, round 1: 4.1 of 12 stall cycles per issue were long-scoreboard waits in this loop) overlaps the
+    // tensor work.  A thread converts exactly the elements it fetched: its own cp.async.wait_group is enough.
+    constexpr int NPT = (NIN + 255) / 256;                               // staged elements per thread
+    float *s_raw = reinterpret_cast<float *>(s_koff + KP);               // [NIN] raw input of the NEXT tile
+    const float *xi = x + (size_t)img * H * H * CIN;
+    auto fetch = [&](int tile) {
+        const int oy0 = (tile / tiles_x) * kC0Th, ox0 = (tile % tiles_x) * kC0Tw;
+#pragma unroll
+        for (int e = 0; e < NPT; e++) {
+            const int i = tid + e * 256;
+            if (i < NIN) {
+                const int c = i % CIN, p = i / CIN;
+                const int ly = p / kC0Iw, lx = p - ly * kC0Iw;
+                const int iy = 2 * oy0 - 1 + ly, ix = 2 * ox0 - 1 + lx;
+                if (iy >= 0 && iy < H && ix >= 0 && ix < H) {
+                    const uint32_t dst = (uint32_t)__cvta_generic_to_shared(s_raw + i);
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(xi + ((size_t)iy * H + ix) * CIN + c) : "memory");
+                } else {
+                    s_raw[i] = __int_as_float(0x7fc00000);               // NaN marks padding: exactly 0 after normalisation
+                }
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    fetch(0);
 #pragma unroll 1
     for (int tile = 0; tile < tiles_x * tiles_y; tile++) {
     const int oy0 = (tile / tiles_x) * kC0Th, ox0 = (tile % tiles_x) * kC0Tw;
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();                                                     // previous tile's input is consumed
-    {
-        const float *xi = x + (size_t)img * H * H * CIN;
-        for (int i = tid; i < NIN; i += 256) {
-            const int c = i % CIN, p = i / CIN;
-            const int ly = p / kC0Iw, lx = p - ly * kC0Iw;
-            const int iy = 2 * oy0 - 1 + ly, ix = 2 * ox0 - 1 + lx;
-            float v = 0.0f;
-            if (iy >= 0 && iy < H && ix >= 0 && ix < H) {
-                v = __ldg(xi + ((size_t)iy * H + ix) * CIN + c);
-                if (normalize) v = (v - 127.5f) / 127.5f;
-            }
+#pragma unroll
+    for (int e = 0; e < NPT; e++) {
+        const int i = tid + e * 256;
+        if (i < NIN) {
+            float v = s_raw[i];
+            if (v != v) v = 0.0f;
+            else if (normalize) v = (v - 127.5f) / 127.5f;
             const __nv_bfloat16 h = __float2bfloat16_rn(v);
             s_ih[i] = __bfloat16_as_ushort(h);
             s_il[i] = __bfloat16_as_ushort(__float2bfloat16_rn(v - __bfloat162float(h)));
         }
     }
     __syncthreads();
+    if (tile + 1 < tiles_x * tiles_y) fetch(tile + 1);
 
     // ---- main loop: warp = output row `warp` of the tile, 16 pixels x 64 channels ----
     float acc[8][4];
@@ -169,15 +198,15 @@ conv0_mma_kernel(const float *__restrict__ x, const __nv_bfloat16 *__restrict__ 
         uint32_t h[8], l[8];
 #pragma unroll
         for (int nt = 0; nt < 8; nt++) {
-            const int ch = t * 16 + nt * 2;
-            float v0 = acc[nt][2 * half] + __ldg(bias + ch), v1 = acc[nt][2 * half + 1] + __ldg(bias + ch + 1);
+            float v0 = acc[nt][2 * half] + bias_r[nt * 2], v1 = acc[nt][2 * half + 1] + bias_r[nt * 2 + 1];
             v0 = v0 > 0.f ? v0 : 0.2f * v0;
             v1 = v1 > 0.f ? v1 : 0.2f * v1;
-            const __nv_bfloat16 h0 = __float2bfloat16_rn(v0), h1 = __float2bfloat16_rn(v1);
-            const __nv_bfloat16 l0 = __float2bfloat16_rn(v0 - __bfloat162float(h0));
-            const __nv_bfloat16 l1 = __float2bfloat16_rn(v1 - __bfloat162float(h1));
-            h[nt] = pack2(__bfloat16_as_ushort(h0), __bfloat16_as_ushort(h1));
-            l[nt] = pack2(__bfloat16_as_ushort(l0), __bfloat16_as_ushort(l1));
+            // packed conversions: one cvt.rn.bf16x2.f32 per pair (same round-to-nearest-even as the scalar form)
+            const __nv_bfloat162 h2 = __floats2bfloat162_rn(v0, v1);
+            const uint32_t hb = *reinterpret_cast<const uint32_t *>(&h2);
+            const __nv_bfloat162 l2 = __floats2bfloat162_rn(v0 - __uint_as_float(hb << 16), v1 - __uint_as_float(hb & 0xffff0000u));
+            h[nt] = hb;
+            l[nt] = *reinterpret_cast<const uint32_t *>(&l2);
         }
         const size_t o = (opix + g + 8 * half) * kC0Cout + t * 16;
         uint4 *gh = reinterpret_cast<uint4 *>(out_hi + o), *gl = reinterpret_cast<uint4 *>(out_lo + o);
@@ -208,7 +237,7 @@ static int conv0_launch(const SpiralDisc *d, const float *x, int batch, const vo
                         void *out_lo, int x3, cudaStream_t st)
 {
     constexpr int KP = c0_kpad(CIN), KS = c0_kstride(CIN), NIN = kC0Ih * kC0Iw * CIN;
-    constexpr size_t smem = (size_t)2 * kC0Cout * KS * 2 + (size_t)2 * ((NIN + 7) & ~7) * 2 + (size_t)KP * 4;
+    constexpr size_t smem = (size_t)2 * kC0Cout * KS * 2 + (size_t)2 * ((NIN + 7) & ~7) * 2 + (size_t)KP * 4 + (size_t)NIN * 4;
     static bool attr = false;
     if (!attr) {
         const cudaError_t e = cudaFuncSetAttribute(conv0_mma_kernel<CIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
