@@ -43,8 +43,8 @@ sys.path.insert(0, ROOT)
 WORKLOAD = dict(workload="rgb64-sweep (configs[3] shape at configs[4]'s largest single-GPU batch)", env="color_mnist",
                 color_channel=3, location_size=64, episode_length=20, canvases_per_gpu=65536, disc_dim=64)
 # DRAM bytes per canvas-step of composite_kernel from the ncu --set full capture in profiles/ (B=16384:
-# dram__bytes_read 356.4 MB + dram__bytes_write 263.2 MB per launch)
-COMPOSITE_TRAFFIC_PER_CANVAS_STEP = (356.434688e6 + 263.226880e6) / 16384
+# dram__bytes_read 368.1 MB + dram__bytes_write 266.9 MB per launch, profiles/r1_final_k1_ncu_summary_v2.md)
+COMPOSITE_TRAFFIC_PER_CANVAS_STEP = (368.139008e6 + 266.859520e6) / 16384
 BYTES_PER_CANVAS_STEP = {1: 81920, 3: 114688}       # BASELINE.md section 3 (K1 algorithmic bytes)
 
 
@@ -378,7 +378,7 @@ def run_ours(args):
         roof = dict(bound="hbm", kernel="spiral::%s_kernel" % dominant, achieved=bytes_launch / (dom_ms * 1e-3) / 1e9,
                     peak=peak, unit="GB/s", frac=bytes_launch / (dom_ms * 1e-3) / 1e9 / peak,
                     traffic=(COMPOSITE_TRAFFIC_PER_CANVAS_STEP * B if dominant == "composite" else 94.0e6 * B / 16384),
-                    traffic_source="ncu --set full at B=16384 (profiles/r1_path_b16384_ncu_summary.md), scaled by B",
+                    traffic_source="ncu --set full at B=16384 (profiles/r1_final_k1_ncu_summary_v2.md), scaled by B",
                     peak_source=peak_src,
                     note="algorithmic bytes = %d B/canvas-step x %d canvases per launch; K1 is instruction-issue / "
                          "latency-bound (serial brush state machine, ~270 dabs x ~20 px per painted step), its DRAM "
