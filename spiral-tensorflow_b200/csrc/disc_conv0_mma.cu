@@ -26,8 +26,14 @@ constexpr int kC0Tw = 16, kC0Th = 8;                    // output tile
 constexpr int kC0Iw = 2 * kC0Tw + 3, kC0Ih = 2 * kC0Th + 3;   // input tile 35 x 19
 constexpr int kC0Cout = 64;
 
-__host__ __device__ constexpr int c0_kpad(int cin) { return (25 * cin + 15) / 16 * 16; }
-__host__ __device__ constexpr int c0_kstride(int cin) { return c0_kpad(cin) + 8; }   // bf16 per row; conflict-free
+// K order: k' = ky * SEG + (kx * CIN + c), every kernel row ky padded from 5*CIN to SEG = 8 / 16 / 32 entries (zero
+// weights).  The 5*CIN inputs of one kernel row are CONSECUTIVE elements of the staged NHWC input row, so an MMA
+// A-fragment pair (k', k'+1) is one aligned 32-bit shared-memory load at a compile-time offset -- no k -> offset
+// table, no 16-bit loads, no packing -- and the pad entries read finite neighbours that meet zero weights.
+__host__ __device__ constexpr int c0_seg(int cin) { return cin == 1 ? 8 : (cin == 3 ? 16 : 32); }
+__host__ __device__ constexpr int c0_kpad(int cin) { return (5 * c0_seg(cin) + 15) / 16 * 16; }
+__host__ __device__ constexpr int c0_kstride(int cin) { return c0_kpad(cin) + 8; }   // bf16 per row; conflict-free, 16-byte rows
+__host__ __device__ constexpr int c0_rowstride(int cin) { return (kC0Iw * cin + 1) & ~1; }   // staged input row, even
 
 __device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2])
 {
@@ -49,11 +55,12 @@ __device__ __forceinline__ uint32_t pack2(uint16_t lo, uint16_t hi) { return (ui
 __global__ void conv0_pack_kernel(const float *__restrict__ w, __nv_bfloat16 *__restrict__ hi,
                                   __nv_bfloat16 *__restrict__ lo, int Cin)
 {
-    const int K = 25 * Cin, KS = c0_kstride(Cin);
+    const int KS = c0_kstride(Cin), SEG = c0_seg(Cin);
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < kC0Cout * KS; i += gridDim.x * blockDim.x) {
-        const int n = i / KS, k = i % KS;
+        const int n = i / KS, kp = i % KS;
         const int ch = c0_channel_of_row(n);
-        const float v = k < K ? w[(size_t)k * kC0Cout + ch] : 0.0f;
+        const int ky = kp / SEG, j = kp % SEG;                      // j = kx * Cin + c
+        const float v = (ky < 5 && j < 5 * Cin) ? w[(size_t)(ky * 5 * Cin + j) * kC0Cout + ch] : 0.0f;
         const __nv_bfloat16 h = __float2bfloat16_rn(v);
         hi[i] = h;
         lo[i] = __float2bfloat16_rn(v - __bfloat162float(h));
@@ -66,21 +73,24 @@ conv0_mma_kernel(const float *__restrict__ x, const __nv_bfloat16 *__restrict__ 
                  const float *__restrict__ bias, __nv_bfloat16 *__restrict__ out_hi, __nv_bfloat16 *__restrict__ out_lo,
                  int B, int H, int normalize, int x3)
 {
-    constexpr int K = 25 * CIN, KP = c0_kpad(CIN), KS = c0_kstride(CIN);
-    constexpr int NIN = kC0Ih * kC0Iw * CIN;
+    constexpr int KP = c0_kpad(CIN), KS = c0_kstride(CIN), SEG = c0_seg(CIN), ROW = c0_rowstride(CIN);
+    constexpr int RW = kC0Iw * CIN;                                        // real elements per staged input row
+    constexpr int NIN = kC0Ih * RW;                                        // elements fetched per tile
+    constexpr int NST = (kC0Ih * ROW + 32 + 7) & ~7;                       // staged plane incl. slack for the pad reads
     extern __shared__ __align__(16) uint8_t sm_raw[];
     uint16_t *s_wh = reinterpret_cast<uint16_t *>(sm_raw);                 // [64][KS]
     uint16_t *s_wl = s_wh + kC0Cout * KS;
-    uint16_t *s_ih = s_wl + kC0Cout * KS;                                  // [19][35][CIN]
-    uint16_t *s_il = s_ih + ((NIN + 7) & ~7);
-    int *s_koff = reinterpret_cast<int *>(s_il + ((NIN + 7) & ~7));        // [KP]
+    uint16_t *s_ih = s_wl + kC0Cout * KS;                                  // [19][ROW]: rows of 35 NHWC pixels
+    uint16_t *s_il = s_ih + NST;
+    float *s_raw = reinterpret_cast<float *>(s_il + NST);                  // [NIN] raw input of the NEXT tile
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int Ho = H / 2;
     const int tiles_x = Ho / kC0Tw, tiles_y = Ho / kC0Th;
     const int img = blockIdx.x;
 
-    // ---- once per CTA (= one image): the packed kernel (16-byte copies) and the k -> input-offset table ----
+    // ---- once per CTA (= one image): the packed kernel (16-byte copies); pad / slack entries of the staged planes
+    //      are read (against zero weights) and must be finite ----
     {
         const uint4 *gh = reinterpret_cast<const uint4 *>(w_hi), *gl = reinterpret_cast<const uint4 *>(w_lo);
         uint4 *sh = reinterpret_cast<uint4 *>(s_wh), *sl = reinterpret_cast<uint4 *>(s_wl);
@@ -89,29 +99,24 @@ conv0_mma_kernel(const float *__restrict__ x, const __nv_bfloat16 *__restrict__ 
             sh[i] = __ldg(gh + i);
             sl[i] = __ldg(gl + i);
         }
-        for (int k = tid; k < KP; k += 256) {
-            int off = 0;
-            if (k < K) {
-                const int tap = k / CIN, c = k - tap * CIN;
-                const int ky = tap / 5, kx = tap - 5 * ky;
-                off = (ky * kC0Iw + kx) * CIN + c;
-            }
-            s_koff[k] = off;
-        }
+        for (int i = tid; i < 2 * NST / 2; i += 256) reinterpret_cast<uint32_t *>(s_ih)[i] = 0u;     // both planes
     }
     const int g = lane >> 2, t = lane & 3;
-    const int base0 = ((2 * warp) * kC0Iw + 2 * g) * CIN;              // pixel g
+    const int base0 = (2 * warp) * ROW + 2 * g * CIN + 2 * t;            // pixel g, fragment columns 2t, 2t+1
     const int base1 = base0 + 16 * CIN;                                  // pixel g + 8
     __shared__ float s_bias[kC0Cout];
     if (tid < kC0Cout) s_bias[tid] = __ldg(bias + tid);
     const float *bias_r = s_bias + t * 16;                               // the thread's channels t*16 .. t*16+15
+    // ldmatrix.x4 row address of this lane: matrices {n-tile 2p: k 0-7, k 8-15, n-tile 2p+1: k 0-7, k 8-15}
+    const uint32_t ldm_off = (uint32_t)((((lane >> 4) * 8 + (lane & 7)) * KS + ((lane >> 3) & 1) * 8) * 2);
+    const uint32_t s_wh_u32 = (uint32_t)__cvta_generic_to_shared(s_wh) + ldm_off;
+    const uint32_t s_wl_u32 = (uint32_t)__cvta_generic_to_shared(s_wl) + ldm_off;
 
     // Input tile staging, software-pipelined: the raw fp32 values of tile i+1 are fetched with cp.async into a
     // shared staging buffer while tile i's MMAs run, and converted to bf16 hi/lo after them, so the global-load
     // latency (ncu, round 1: 4.1 of 12 stall cycles per issue were long-scoreboard waits in this loop) overlaps the
     // tensor work.  A thread converts exactly the elements it fetched: its own cp.async.wait_group is enough.
     constexpr int NPT = (NIN + 255) / 256;                               // staged elements per thread
-    float *s_raw = reinterpret_cast<float *>(s_koff + KP);               // [NIN] raw input of the NEXT tile
     const float *xi = x + (size_t)img * H * H * CIN;
     auto fetch = [&](int tile) {
         const int oy0 = (tile / tiles_x) * kC0Th, ox0 = (tile % tiles_x) * kC0Tw;
@@ -119,12 +124,11 @@ conv0_mma_kernel(const float *__restrict__ x, const __nv_bfloat16 *__restrict__ 
         for (int e = 0; e < NPT; e++) {
             const int i = tid + e * 256;
             if (i < NIN) {
-                const int c = i % CIN, p = i / CIN;
-                const int ly = p / kC0Iw, lx = p - ly * kC0Iw;
-                const int iy = 2 * oy0 - 1 + ly, ix = 2 * ox0 - 1 + lx;
-                if (iy >= 0 && iy < H && ix >= 0 && ix < H) {
+                const int ly = i / RW, rem = i - ly * RW;                // a staged row is RW consecutive floats of the image
+                const int iy = 2 * oy0 - 1 + ly, col = (2 * ox0 - 1) * CIN + rem;
+                if (iy >= 0 && iy < H && col >= 0 && col < H * CIN) {
                     const uint32_t dst = (uint32_t)__cvta_generic_to_shared(s_raw + i);
-                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(xi + ((size_t)iy * H + ix) * CIN + c) : "memory");
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(xi + (size_t)iy * H * CIN + col) : "memory");
                 } else {
                     s_raw[i] = __int_as_float(0x7fc00000);               // NaN marks padding: exactly 0 after normalisation
                 }
@@ -145,9 +149,10 @@ conv0_mma_kernel(const float *__restrict__ x, const __nv_bfloat16 *__restrict__ 
             float v = s_raw[i];
             if (v != v) v = 0.0f;
             else if (normalize) v = (v - 127.5f) / 127.5f;
+            const int ly = i / RW, o = ly * ROW + (i - ly * RW);
             const __nv_bfloat16 h = __float2bfloat16_rn(v);
-            s_ih[i] = __bfloat16_as_ushort(h);
-            s_il[i] = __bfloat16_as_ushort(__float2bfloat16_rn(v - __bfloat162float(h)));
+            s_ih[o] = __bfloat16_as_ushort(h);
+            s_il[o] = __bfloat16_as_ushort(__float2bfloat16_rn(v - __bfloat162float(h)));
         }
     }
     __syncthreads();
@@ -160,34 +165,39 @@ conv0_mma_kernel(const float *__restrict__ x, const __nv_bfloat16 *__restrict__ 
 #pragma unroll
         for (int j = 0; j < 4; j++) acc[nt][j] = 0.0f;
 
-#pragma unroll 1
+#pragma unroll
     for (int ks = 0; ks < KP / 16; ks++) {
-        const int k0 = ks * 16 + 2 * t;
-        const int o0 = s_koff[k0], o1 = s_koff[k0 + 1], o8 = s_koff[k0 + 8], o9 = s_koff[k0 + 9];
+        // compile-time offsets of the two 8-wide halves of this k-step inside the staged input
+        const int kA = ks * 16, kB = ks * 16 + 8;
+        const int kyA = (kA / SEG) < 5 ? (kA / SEG) : 4, kyB = (kB / SEG) < 5 ? (kB / SEG) : 4;   // beyond 5*SEG: zero weights
+        const int oA = kyA * ROW + (kA % SEG), oB = kyB * ROW + (kB % SEG);
         uint32_t ah[4], al[4];
-        ah[0] = pack2(s_ih[base0 + o0], s_ih[base0 + o1]);
-        ah[1] = pack2(s_ih[base1 + o0], s_ih[base1 + o1]);
-        ah[2] = pack2(s_ih[base0 + o8], s_ih[base0 + o9]);
-        ah[3] = pack2(s_ih[base1 + o8], s_ih[base1 + o9]);
+        ah[0] = *reinterpret_cast<const uint32_t *>(s_ih + base0 + oA);
+        ah[1] = *reinterpret_cast<const uint32_t *>(s_ih + base1 + oA);
+        ah[2] = *reinterpret_cast<const uint32_t *>(s_ih + base0 + oB);
+        ah[3] = *reinterpret_cast<const uint32_t *>(s_ih + base1 + oB);
         if (x3) {
-            al[0] = pack2(s_il[base0 + o0], s_il[base0 + o1]);
-            al[1] = pack2(s_il[base1 + o0], s_il[base1 + o1]);
-            al[2] = pack2(s_il[base0 + o8], s_il[base0 + o9]);
-            al[3] = pack2(s_il[base1 + o8], s_il[base1 + o9]);
+            al[0] = *reinterpret_cast<const uint32_t *>(s_il + base0 + oA);
+            al[1] = *reinterpret_cast<const uint32_t *>(s_il + base1 + oA);
+            al[2] = *reinterpret_cast<const uint32_t *>(s_il + base0 + oB);
+            al[3] = *reinterpret_cast<const uint32_t *>(s_il + base1 + oB);
         }
 #pragma unroll
-        for (int nt = 0; nt < 8; nt++) {
-            const int wrow = (nt * 8 + g) * KS + k0;
-            uint32_t bh[2], bl[2];
-            bh[0] = *reinterpret_cast<const uint32_t *>(s_wh + wrow);
-            bh[1] = *reinterpret_cast<const uint32_t *>(s_wh + wrow + 8);
+        for (int np = 0; np < 4; np++) {                                 // two n-tiles per ldmatrix.x4
+            const uint32_t woff = (uint32_t)((np * 16 * KS + ks * 16) * 2);
+            uint32_t bh[4], bl[4];
+            asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+                         : "=r"(bh[0]), "=r"(bh[1]), "=r"(bh[2]), "=r"(bh[3]) : "r"(s_wh_u32 + woff));
             if (x3) {
-                bl[0] = *reinterpret_cast<const uint32_t *>(s_wl + wrow);
-                bl[1] = *reinterpret_cast<const uint32_t *>(s_wl + wrow + 8);
-                mma_bf16_16816(acc[nt], al, bh);
-                mma_bf16_16816(acc[nt], ah, bl);
+                asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+                             : "=r"(bl[0]), "=r"(bl[1]), "=r"(bl[2]), "=r"(bl[3]) : "r"(s_wl_u32 + woff));
+                mma_bf16_16816(acc[2 * np], al, *reinterpret_cast<const uint32_t(*)[2]>(&bh[0]));
+                mma_bf16_16816(acc[2 * np], ah, *reinterpret_cast<const uint32_t(*)[2]>(&bl[0]));
+                mma_bf16_16816(acc[2 * np + 1], al, *reinterpret_cast<const uint32_t(*)[2]>(&bh[2]));
+                mma_bf16_16816(acc[2 * np + 1], ah, *reinterpret_cast<const uint32_t(*)[2]>(&bl[2]));
             }
-            mma_bf16_16816(acc[nt], ah, bh);
+            mma_bf16_16816(acc[2 * np], ah, *reinterpret_cast<const uint32_t(*)[2]>(&bh[0]));
+            mma_bf16_16816(acc[2 * np + 1], ah, *reinterpret_cast<const uint32_t(*)[2]>(&bh[2]));
         }
     }
 
@@ -236,8 +246,9 @@ template <int CIN>
 static int conv0_launch(const SpiralDisc *d, const float *x, int batch, const void *w_hi, const void *w_lo, void *out_hi,
                         void *out_lo, int x3, cudaStream_t st)
 {
-    constexpr int KP = c0_kpad(CIN), KS = c0_kstride(CIN), NIN = kC0Ih * kC0Iw * CIN;
-    constexpr size_t smem = (size_t)2 * kC0Cout * KS * 2 + (size_t)2 * ((NIN + 7) & ~7) * 2 + (size_t)KP * 4 + (size_t)NIN * 4;
+    constexpr int KS = c0_kstride(CIN), NIN = kC0Ih * kC0Iw * CIN;
+    constexpr int NST = (kC0Ih * c0_rowstride(CIN) + 32 + 7) & ~7;
+    constexpr size_t smem = (size_t)2 * kC0Cout * KS * 2 + (size_t)2 * NST * 2 + (size_t)NIN * 4;
     static bool attr = false;
     if (!attr) {
         const cudaError_t e = cudaFuncSetAttribute(conv0_mma_kernel<CIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -81,15 +81,20 @@ def test_a2c_autograd_wrapper_backpropagates():
                                             (3, 64, True, 16, "bf16x3"), (1, 64, True, 130, "bf16x3"),
                                             (3, 64, False, 8, "bf16x3"), (3, 64, True, 16, "bf16"),
                                             # whole tiles of 128 images: position-pure tiles on the 2x2 .. 8x8 maps
-                                            (3, 64, True, 128, "bf16x3"), (1, 64, True, 256, "bf16x3")])
+                                            (3, 64, True, 128, "bf16x3"), (1, 64, True, 256, "bf16x3"),
+                                            # 6 input channels: the conditional discriminator's concat[fake, real]
+                                            (6, 64, True, 8, "bf16x3")])
 def test_discriminator_forward_matches_oracle(C, dd, bn, B, prec):
     sp = _sp()
     from oracle import disc_oracle as do
     from importlib import import_module
     models = import_module(sp.__name__ + ".models")
+    cond = C == 6                                   # conditional D: 3-channel images, fed as concat[x, x] (reference :36-38)
+    Cnet, C = C, (3 if cond else C)
     args = sp.get_args(["--color_channel", str(C), "--disc_dim", str(dd), "--disc_batch_norm", str(bn),
                         "--disc_precision", prec])
-    w = do.init_weights(C, disc_dim=dd, batch_norm=bn, seed=3)
+    args.conditional = cond                         # config.py:83-101 forces False with --loss gan; the D graph itself supports it
+    w = do.init_weights(Cnet, disc_dim=dd, batch_norm=bn, seed=3)
     D = models.Discriminator(args, None, [64, 64, C], norm_fn=lambda x: x, scope_name="global", max_batch=B)
     D.load_numpy(w)
     rng = np.random.RandomState(1)
@@ -100,6 +105,8 @@ def test_discriminator_forward_matches_oracle(C, dd, bn, B, prec):
             y, x = rng.randint(0, 56, 2)
             imgs[b, y:y + 8, x:x + 8] = rng.randint(0, 255)
     probs, logits = D.forward(torch.tensor(imgs, device="cuda"))
+    if cond:
+        imgs = np.concatenate([imgs, imgs], -1)
     want_p, want_l = do.predict(imgs, w, batch_norm=bn, dtype=torch.float64)
     lg = logits.cpu().numpy()
     # fp32 and bf16x3 (fp32-equivalent split) meet the north-star 1e-4; plain bf16 is the fast,
