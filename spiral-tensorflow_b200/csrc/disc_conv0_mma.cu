@@ -51,19 +51,31 @@ __host__ __device__ constexpr int c0_channel_of_row(int n) { return ((n & 7) >> 
 
 __device__ __forceinline__ uint32_t pack2(uint16_t lo, uint16_t hi) { return (uint32_t)lo | ((uint32_t)hi << 16); }
 
-// HWIO [25][CIN][64] fp32 -> [64][KS] bf16 hi / lo with k = tap * CIN + c (zero padded)
-__global__ void conv0_pack_kernel(const float *__restrict__ w, __nv_bfloat16 *__restrict__ hi,
-                                  __nv_bfloat16 *__restrict__ lo, int Cin)
+// HWIO [25][CIN][64] fp32 -> [64][KS] bf16 hi / lo in the k' order above (zero padded), followed by the 64 effective
+// biases.  With `normalize` (set in the bf16x3 parity mode) the input normalisation (x - 127.5) / 127.5 (envs/base.py:51-52) is folded into the layer:
+//   sum_k W_k (x_k - 127.5) / 127.5 + b  =  sum_k (W_k / 127.5) x_k + (b - sum_k W_k)        (padding: x_k = 127.5)
+// so the kernel multiplies RAW pixel values -- integers 0..255 and the padding value 127.5 are exact in bf16, the
+// activations' lo plane is identically zero and one of the three bf16x3 products disappears (checked per tile).
+__global__ void conv0_pack_kernel(const float *__restrict__ w, const float *__restrict__ bias, __nv_bfloat16 *__restrict__ hi,
+                                  __nv_bfloat16 *__restrict__ lo, float *__restrict__ bias_eff, int Cin, int normalize)
 {
     const int KS = c0_kstride(Cin), SEG = c0_seg(Cin);
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < kC0Cout * KS; i += gridDim.x * blockDim.x) {
         const int n = i / KS, kp = i % KS;
         const int ch = c0_channel_of_row(n);
         const int ky = kp / SEG, j = kp % SEG;                      // j = kx * Cin + c
-        const float v = (ky < 5 && j < 5 * Cin) ? w[(size_t)(ky * 5 * Cin + j) * kC0Cout + ch] : 0.0f;
+        float v = (ky < 5 && j < 5 * Cin) ? w[(size_t)(ky * 5 * Cin + j) * kC0Cout + ch] : 0.0f;
+        if (normalize) v = v / 127.5f;
         const __nv_bfloat16 h = __float2bfloat16_rn(v);
         hi[i] = h;
         lo[i] = __float2bfloat16_rn(v - __bfloat162float(h));
+    }
+    const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ch < kC0Cout) {
+        double acc = 0.0;
+        if (normalize)
+            for (int k = 0; k < 25 * Cin; k++) acc += (double)w[(size_t)k * kC0Cout + ch];
+        bias_eff[ch] = (float)((double)bias[ch] - acc);
     }
 }
 
@@ -105,7 +117,7 @@ conv0_mma_kernel(const float *__restrict__ x, const __nv_bfloat16 *__restrict__ 
     const int base0 = (2 * warp) * ROW + 2 * g * CIN + 2 * t;            // pixel g, fragment columns 2t, 2t+1
     const int base1 = base0 + 16 * CIN;                                  // pixel g + 8
     __shared__ float s_bias[kC0Cout];
-    if (tid < kC0Cout) s_bias[tid] = __ldg(bias + tid);
+    if (tid < kC0Cout) s_bias[tid] = __ldg(reinterpret_cast<const float *>(w_hi + kC0Cout * KS) + tid);   // effective bias (conv0_pack_kernel)
     const float *bias_r = s_bias + t * 16;                               // the thread's channels t*16 .. t*16+15
     // ldmatrix.x4 row address of this lane: matrices {n-tile 2p: k 0-7, k 8-15, n-tile 2p+1: k 0-7, k 8-15}
     const uint32_t ldm_off = (uint32_t)((((lane >> 4) * 8 + (lane & 7)) * KS + ((lane >> 3) & 1) * 8) * 2);
@@ -130,7 +142,7 @@ conv0_mma_kernel(const float *__restrict__ x, const __nv_bfloat16 *__restrict__ 
                     const uint32_t dst = (uint32_t)__cvta_generic_to_shared(s_raw + i);
                     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(xi + (size_t)iy * H * CIN + col) : "memory");
                 } else {
-                    s_raw[i] = __int_as_float(0x7fc00000);               // NaN marks padding: exactly 0 after normalisation
+                    s_raw[i] = normalize ? 127.5f : 0.0f;                // SAME padding: zero in normalised units
                 }
             }
         }
@@ -142,20 +154,31 @@ conv0_mma_kernel(const float *__restrict__ x, const __nv_bfloat16 *__restrict__ 
     const int oy0 = (tile / tiles_x) * kC0Th, ox0 = (tile % tiles_x) * kC0Tw;
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();                                                     // previous tile's input is consumed
+    int lo_nonzero = 0;
 #pragma unroll
     for (int e = 0; e < NPT; e++) {
         const int i = tid + e * 256;
         if (i < NIN) {
-            float v = s_raw[i];
-            if (v != v) v = 0.0f;
-            else if (normalize) v = (v - 127.5f) / 127.5f;
+            float v = s_raw[i];                                          // stays a raw pixel value when the normalisation is folded
+            if (normalize && !x3) {
+                // plain-bf16 mode keeps the normalised operand (a single rounded product has no room for the fold's
+                // cancellation): (v - 127.5) / 127.5 correctly rounded without the division sequence -- with
+                // rc = RN(1/127.5), q0 = a*rc, r = fma(-q0, 127.5, a), q = fma(r, rc, q0) equals a / 127.5 for EVERY finite
+                // float a with |a| >= 2^-118 (exhaustive check: tools/verify_const_div.c); a = v - 127.5 is 0 or >= 2^-17
+                const float a = v - 127.5f, rc = 1.0f / 127.5f;
+                const float q0 = a * rc;
+                v = fmaf(fmaf(-q0, 127.5f, a), rc, q0);
+            }
             const int ly = i / RW, o = ly * ROW + (i - ly * RW);
             const __nv_bfloat16 h = __float2bfloat16_rn(v);
+            const uint16_t lb = __bfloat16_as_ushort(__float2bfloat16_rn(v - __bfloat162float(h)));
             s_ih[o] = __bfloat16_as_ushort(h);
-            s_il[o] = __bfloat16_as_ushort(__float2bfloat16_rn(v - __bfloat162float(h)));
+            s_il[o] = lb;
+            lo_nonzero |= lb & 0x7fff;
         }
     }
-    __syncthreads();
+    // block-uniform: does any staged value of this tile need its lo plane?  (never for 8-bit images)
+    const bool need_lo = __syncthreads_or(lo_nonzero) != 0 && x3;
     if (tile + 1 < tiles_x * tiles_y) fetch(tile + 1);
 
     // ---- main loop: warp = output row `warp` of the tile, 16 pixels x 64 channels ----
@@ -176,7 +199,7 @@ conv0_mma_kernel(const float *__restrict__ x, const __nv_bfloat16 *__restrict__ 
         ah[1] = *reinterpret_cast<const uint32_t *>(s_ih + base1 + oA);
         ah[2] = *reinterpret_cast<const uint32_t *>(s_ih + base0 + oB);
         ah[3] = *reinterpret_cast<const uint32_t *>(s_ih + base1 + oB);
-        if (x3) {
+        if (need_lo) {
             al[0] = *reinterpret_cast<const uint32_t *>(s_il + base0 + oA);
             al[1] = *reinterpret_cast<const uint32_t *>(s_il + base1 + oA);
             al[2] = *reinterpret_cast<const uint32_t *>(s_il + base0 + oB);
@@ -191,9 +214,11 @@ conv0_mma_kernel(const float *__restrict__ x, const __nv_bfloat16 *__restrict__ 
             if (x3) {
                 asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
                              : "=r"(bl[0]), "=r"(bl[1]), "=r"(bl[2]), "=r"(bl[3]) : "r"(s_wl_u32 + woff));
-                mma_bf16_16816(acc[2 * np], al, *reinterpret_cast<const uint32_t(*)[2]>(&bh[0]));
+                if (need_lo) {
+                    mma_bf16_16816(acc[2 * np], al, *reinterpret_cast<const uint32_t(*)[2]>(&bh[0]));
+                    mma_bf16_16816(acc[2 * np + 1], al, *reinterpret_cast<const uint32_t(*)[2]>(&bh[2]));
+                }
                 mma_bf16_16816(acc[2 * np], ah, *reinterpret_cast<const uint32_t(*)[2]>(&bl[0]));
-                mma_bf16_16816(acc[2 * np + 1], al, *reinterpret_cast<const uint32_t(*)[2]>(&bh[2]));
                 mma_bf16_16816(acc[2 * np + 1], ah, *reinterpret_cast<const uint32_t(*)[2]>(&bl[2]));
             }
             mma_bf16_16816(acc[2 * np], ah, *reinterpret_cast<const uint32_t(*)[2]>(&bh[0]));
@@ -228,7 +253,7 @@ conv0_mma_kernel(const float *__restrict__ x, const __nv_bfloat16 *__restrict__ 
     }   // next tile
 }
 
-size_t conv0_mma_pack_bytes(int Cin) { return (size_t)kC0Cout * c0_kstride(Cin) * 2; }
+size_t conv0_mma_pack_bytes(int Cin) { return (size_t)kC0Cout * c0_kstride(Cin) * 2 + kC0Cout * sizeof(float); }   // + effective bias
 
 bool conv0_mma_supported(const SpiralDisc *d)
 {
@@ -238,8 +263,10 @@ bool conv0_mma_supported(const SpiralDisc *d)
 
 void conv0_mma_pack(const SpiralDisc *d, void *w_hi, void *w_lo, cudaStream_t st)
 {
-    conv0_pack_kernel<<<8, 256, 0, st>>>((const float *)d->w.conv_w[0], (__nv_bfloat16 *)w_hi, (__nv_bfloat16 *)w_lo,
-                                         d->cfg.in_channels);
+    const int Cin = d->cfg.in_channels;
+    float *bias_eff = reinterpret_cast<float *>((char *)w_hi + (size_t)kC0Cout * c0_kstride(Cin) * 2);
+    conv0_pack_kernel<<<8, 256, 0, st>>>((const float *)d->w.conv_w[0], (const float *)d->w.conv_b[0], (__nv_bfloat16 *)w_hi,
+                                         (__nv_bfloat16 *)w_lo, bias_eff, Cin, d->cfg.normalize && d->cfg.precision == 1);
 }
 
 template <int CIN>
