@@ -273,6 +273,12 @@ int spiral_adam_step(float *const *params_dev, const float *const *grads_dev, fl
                      float *const *v_dev, const int64_t *sizes, int32_t n_tensors, float lr_t, float beta1,
                      float beta2, float eps, float grad_scale, const float *norm_dev, float clip_norm,
                      void *stream);
+/* Same update with lr_t read from device memory (f32[1]): a learner step captured into a CUDA graph then sees the
+ * step size of every replay (the bias-correction factor changes with t) instead of the value baked in at capture. */
+int spiral_adam_step_lr_dev(float *const *params_dev, const float *const *grads_dev, float *const *m_dev,
+                            float *const *v_dev, const int64_t *sizes, int32_t n_tensors, const float *lr_t_dev,
+                            float beta1, float beta2, float eps, float grad_scale, const float *norm_dev,
+                            float clip_norm, void *stream);
 
 /* ------------------------------------------------------------------ */
 /* Policy convolutions for the acting path                              */

@@ -50,6 +50,7 @@ class Agent(object):
         self.rng.manual_seed(int(args.seed))
         self.world = dist_utils.dist.get_world_size() if dist_utils.dist.is_initialized() else 1
         self._graph, self._graph_failed, self._g_out, self._g_target, self._g_z = None, False, {}, None, None
+        self._tp_graph, self._tp_failed, self._tp_calls, self._tp_in, self._tp_out = None, False, 0, None, None
 
     # ------------------------------------------------------------------
     @torch.no_grad()
@@ -135,12 +136,53 @@ class Agent(object):
         return out
 
     def train_policy(self, rollout):
-        """agent.py:333-403."""
-        args, pi = self.args, self.policy
+        """agent.py:333-403.  With ``--cuda_graphs`` (default) the learner step -- policy forward over [B*T] frames with
+        teacher forcing, the fused A2C loss, backward, gradient all-reduce, clip + Adam, the actors' weight pull -- is
+        captured into ONE CUDA graph after two eager steps and replayed: like the rollout it is launch-bound at the
+        reference's batch sizes (about 1,500 small kernels).  The step size of every replay comes from device memory
+        (``FusedTFAdam.advance``); the GAN reward is injected before the graph (the discriminator re-packs its weights
+        only when they changed, a host-side decision)."""
         if self.gan:
             with torch.no_grad():
                 self.disc.sync_weights()
                 rollout["rewards"][:, -1] = self.disc.predict(rollout["states"][:, -1])       # agent.py:336-338
+        use_graph = (getattr(self.args, "cuda_graphs", True) and self.device.type == "cuda" and not self._tp_failed
+                     and self.world == 1)                # several ranks: eager (the all-reduce stays outside any capture)
+        if not use_graph:
+            return self._train_policy_body(rollout)
+        self._tp_calls += 1
+        if self._tp_graph is None and self._tp_calls <= 2:
+            # eager steps double as the warm-up capture needs (cuDNN / cuBLAS handles, autograd's lazy state), on a side stream
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                out = self._train_policy_body(rollout)
+            torch.cuda.current_stream().wait_stream(side)
+            return out
+        keys = [k for k in ("states", "actions", "rewards", "values", "features", "conditions", "z") if k in rollout]
+        if self._tp_graph is None:
+            try:
+                self._tp_in = {k: rollout[k].clone() for k in keys}
+                self.policy_opt.zero_grad(set_to_none=True)
+                torch.cuda.synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._tp_out = self._train_policy_body(self._tp_in, advance=False)
+                self._tp_graph = g
+            except Exception as e:                       # capture is an optimisation: fall back to eager steps
+                self._tp_failed, self._tp_graph = True, None
+                torch.cuda.synchronize()
+                import warnings
+                warnings.warn("CUDA-graph capture of the learner step failed (%s); running eagerly" % (e,))
+                return self._train_policy_body(rollout)
+        for k in keys:
+            self._tp_in[k].copy_(rollout[k])
+        self.policy_opt.advance()
+        self._tp_graph.replay()
+        return {k: (v.clone() if torch.is_tensor(v) else v) for k, v in self._tp_out.items()}
+
+    def _train_policy_body(self, rollout, advance=True):
+        args, pi = self.args, self.policy
         acts = rollout["actions"]
         samples = {name: acts[:, :, i] for i, name in enumerate(pi.acs)}                      # teacher forcing, agent.py:357-365
         feats = rollout["features"][:, 0]
@@ -152,7 +194,7 @@ class Agent(object):
         loss.backward()
         grads = [p.grad for p in pi.parameters() if p.grad is not None]
         dist_utils.allreduce_grads_(grads, self.world, average=False)                         # sum; 1/world is folded into K5
-        gnorm = self.policy_opt.step(clip_norm=float(args.grad_clip), grad_scale=1.0 / self.world)   # agent.py:231-239
+        gnorm = self.policy_opt.step(clip_norm=float(args.grad_clip), grad_scale=1.0 / self.world, advance=advance)   # agent.py:231-239
         if self.actor is not None:
             self.actor.sync()                             # actors pull the new weights (trainer.py:117 policy_sync)
         B = acts.shape[0]

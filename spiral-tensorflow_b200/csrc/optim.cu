@@ -68,10 +68,11 @@ norm_final_kernel(const double *__restrict__ partial, int n_partial, float *__re
 }
 
 __global__ void __launch_bounds__(256)
-adam_step_kernel(const __grid_constant__ TensorTable T, float lr_t, float b1, float b2, float eps, float grad_scale,
-                 const float *__restrict__ norm, float clip_norm)
+adam_step_kernel(const __grid_constant__ TensorTable T, float lr_val, const float *__restrict__ lr_dev, float b1, float b2,
+                 float eps, float grad_scale, const float *__restrict__ norm, float clip_norm)
 {
     const int t = blockIdx.y;
+    const float lr_t = lr_dev ? lr_dev[0] : lr_val;        // device-resident step size: a captured CUDA graph sees each step's value
     float scale = grad_scale;
     if (norm && clip_norm > 0.0f) scale *= clip_norm / fmaxf(norm[0] * grad_scale, clip_norm);   // the norm of the SCALED gradient
     float *p = T.p[t], *m = T.m[t], *v = T.v[t];
@@ -110,9 +111,9 @@ extern "C" int spiral_grad_global_norm(const float *const *grads, const int64_t 
     return e == cudaSuccess ? SPIRAL_OK : spiral_cuda_error(e, "spiral_grad_global_norm");
 }
 
-extern "C" int spiral_adam_step(float *const *params, const float *const *grads, float *const *m, float *const *v,
-                                const int64_t *sizes, int32_t n_tensors, float lr_t, float beta1, float beta2, float eps,
-                                float grad_scale, const float *norm_dev, float clip_norm, void *stream)
+static int adam_step_impl(float *const *params, const float *const *grads, float *const *m, float *const *v,
+                          const int64_t *sizes, int32_t n_tensors, float lr_t, const float *lr_t_dev, float beta1, float beta2,
+                          float eps, float grad_scale, const float *norm_dev, float clip_norm, void *stream)
 {
     SPIRAL_REQUIRE(params); SPIRAL_REQUIRE(grads); SPIRAL_REQUIRE(m); SPIRAL_REQUIRE(v); SPIRAL_REQUIRE(sizes);
     if (n_tensors <= 0) return spiral_set_error(SPIRAL_EINVAL, "adam_step: no tensors");
@@ -124,8 +125,23 @@ extern "C" int spiral_adam_step(float *const *params, const float *const *grads,
             T.p[i] = params[t0 + i]; T.g[i] = grads[t0 + i]; T.m[i] = m[t0 + i]; T.v[i] = v[t0 + i]; T.n[i] = sizes[t0 + i];
         }
         dim3 grid(kOptBlocksX, T.count);
-        adam_step_kernel<<<grid, 256, 0, st>>>(T, lr_t, beta1, beta2, eps, grad_scale, norm_dev, clip_norm);
+        adam_step_kernel<<<grid, 256, 0, st>>>(T, lr_t, lr_t_dev, beta1, beta2, eps, grad_scale, norm_dev, clip_norm);
     }
     const cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? SPIRAL_OK : spiral_cuda_error(e, "spiral_adam_step");
+}
+
+extern "C" int spiral_adam_step(float *const *params, const float *const *grads, float *const *m, float *const *v,
+                                const int64_t *sizes, int32_t n_tensors, float lr_t, float beta1, float beta2, float eps,
+                                float grad_scale, const float *norm_dev, float clip_norm, void *stream)
+{
+    return adam_step_impl(params, grads, m, v, sizes, n_tensors, lr_t, nullptr, beta1, beta2, eps, grad_scale, norm_dev, clip_norm, stream);
+}
+
+extern "C" int spiral_adam_step_lr_dev(float *const *params, const float *const *grads, float *const *m, float *const *v,
+                                       const int64_t *sizes, int32_t n_tensors, const float *lr_t_dev, float beta1, float beta2,
+                                       float eps, float grad_scale, const float *norm_dev, float clip_norm, void *stream)
+{
+    SPIRAL_REQUIRE(lr_t_dev);
+    return adam_step_impl(params, grads, m, v, sizes, n_tensors, 0.0f, lr_t_dev, beta1, beta2, eps, grad_scale, norm_dev, clip_norm, stream);
 }

@@ -97,7 +97,10 @@ class _Deconv(object):
             for px in (0, 1):
                 kys = (3, 1) if py == 0 else (2, 0)
                 kxs = (3, 1) if px == 0 else (2, 0)
-                self.classes[i].repack(w[:, :, kys, :][:, :, :, kxs].permute(1, 0, 2, 3), bias)
+                # slices, not index lists: an index list is a host tensor copied to the device on every call, which a
+                # CUDA-graph capture of the learner step (Agent.train_policy) cannot record
+                sub = torch.stack([torch.stack([w[:, :, ky, kx] for kx in kxs], -1) for ky in kys], -2)   # [Cin, Cout, 2, 2]
+                self.classes[i].repack(sub.permute(1, 0, 2, 3), bias)
                 i += 1
 
     def __call__(self, x, out):

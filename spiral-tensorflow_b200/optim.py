@@ -29,6 +29,14 @@ class FusedTFAdam(object):
         dev = self.params[0].device
         self._scratch = torch.empty((32 * len(self.params),), dtype=torch.float64, device=dev)
         self._norm = torch.zeros((1,), dtype=torch.float32, device=dev)
+        self._lr_t = torch.zeros((1,), dtype=torch.float32, device=dev)     # this step's lr_t, device-resident (CUDA graphs)
+
+    def advance(self):
+        """Host half of a step: t += 1 and this step's ``lr_t = lr * sqrt(1 - b2^t) / (1 - b1^t)`` into device memory.
+        ``step()`` calls it itself; a step that is replayed from a CUDA graph calls it before the replay and captures
+        ``step(advance=False)``, so the graph reads each replay's own value."""
+        self.t += 1
+        self._lr_t.fill_(self.lr * math.sqrt(1.0 - self.beta2 ** self.t) / (1.0 - self.beta1 ** self.t))
 
     def zero_grad(self, set_to_none=True):
         for p in self.params:
@@ -38,7 +46,7 @@ class FusedTFAdam(object):
                 p.grad.zero_()
 
     @torch.no_grad()
-    def step(self, clip_norm=0.0, grad_scale=1.0):
+    def step(self, clip_norm=0.0, grad_scale=1.0, advance=True):
         """One update.  Returns the global norm of the (scaled) gradient as a device scalar
         (``model/grad_global_norm`` in the reference's summaries, agent.py:213)."""
         lib = N.lib()
@@ -56,8 +64,8 @@ class FusedTFAdam(object):
         st = N.stream_ptr()
         N.check(lib.spiral_grad_global_norm(gp, sizes, n, N.ptr(self._scratch), N.ptr(self._norm), st),
                 "spiral_grad_global_norm")
-        self.t += 1
-        lr_t = self.lr * math.sqrt(1.0 - self.beta2 ** self.t) / (1.0 - self.beta1 ** self.t)
-        N.check(lib.spiral_adam_step(pp, gp, mp, vv, sizes, n, lr_t, self.beta1, self.beta2, self.eps, float(grad_scale),
-                                     N.ptr(self._norm), float(clip_norm), st), "spiral_adam_step")
+        if advance:
+            self.advance()
+        N.check(lib.spiral_adam_step_lr_dev(pp, gp, mp, vv, sizes, n, N.ptr(self._lr_t), self.beta1, self.beta2, self.eps,
+                                            float(grad_scale), N.ptr(self._norm), float(clip_norm), st), "spiral_adam_step_lr_dev")
         return self._norm[0] * float(grad_scale)

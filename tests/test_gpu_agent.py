@@ -157,3 +157,40 @@ def test_checkpoint_resume_restores_weights_and_optimizer(tmp_path):
     assert all(torch.equal(want_d[k], ag2.disc.params[k]) for k in want_d)
     assert ag2.policy_opt.t == ag.policy_opt.t and torch.equal(ag2.disc_opt.m[0], ag.disc_opt.m[0])
     assert torch.equal(ag2.disc.predict(x), want_reward)              # the packed kernel weights were refreshed
+
+
+@pytest.mark.parametrize("native", [False, True])
+def test_graph_captured_learner_step_matches_eager_steps(native):
+    """The CUDA graph of train_policy (captured at the third call) must update the policy exactly like eager steps:
+    two agents with identical weights are fed the same rollouts for five learner steps; the graph reads each step's
+    bias-corrected Adam step size from device memory (FusedTFAdam.advance)."""
+    sp, agent_mod, _ = _mods()
+
+    def make(graphs):
+        args = make_args("simple_mnist", L=32, C=1, T=3, conditional=True,
+                         extra=["--cuda_graphs", str(graphs), "--policy_act_native", str(native), "--policy_lr", "1e-3"])
+        env = sp.create_env(args, num_envs=8)
+        torch.manual_seed(0)
+        return agent_mod.Agent(args, env)
+
+    a_graph, a_eager = make(True), make(False)
+    a_eager.policy.load_state_dict(a_graph.policy.state_dict())
+    start = [p.detach().clone() for p in a_graph.policy.parameters()]
+    rollouts = []
+    for i in range(5):
+        ro = a_eager.rollout()
+        ro["rewards"][:, -1] = torch.linspace(0, 1, 8, device="cuda") * (i + 1) / 5.0     # distinct, deterministic rewards
+        rollouts.append({k: v.clone() for k, v in ro.items()})
+    for i, ro in enumerate(rollouts):
+        m_g = a_graph.train_policy({k: v.clone() for k, v in ro.items()})
+        m_e = a_eager.train_policy({k: v.clone() for k, v in ro.items()})
+        # cuDNN may pick other algorithms under capture and Adam turns last-bit gradient differences of near-zero
+        # gradients into lr-sized steps, so the two trajectories agree closely, not bitwise
+        assert torch.allclose(m_g["model/total_loss"], m_e["model/total_loss"], rtol=5e-3), i
+        assert torch.allclose(m_g["model/grad_global_norm"], m_e["model/grad_global_norm"], rtol=1e-1), i
+    assert a_graph._tp_graph is not None and not a_graph._tp_failed           # steps 3-5 were graph replays
+    assert a_graph.policy_opt.t == a_eager.policy_opt.t == 5
+    moved = sum(float((p.detach() - s0).pow(2).sum()) for p, s0 in zip(a_graph.policy.parameters(), start)) ** 0.5
+    apart = sum(float((p.detach() - q.detach()).pow(2).sum())
+                for p, q in zip(a_graph.policy.parameters(), a_eager.policy.parameters())) ** 0.5
+    assert moved > 0 and apart < 0.05 * moved, (moved, apart)
