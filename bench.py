@@ -447,7 +447,8 @@ def run_ours(args):
     def agent_loop(args, dev, n=128, iters=3):
         """The whole synchronous loop at a small batch, for context: policy.act (PyTorch module + K4 sampling)
         -> env.step (K1) x T, D reward (K2) -> fused A2C (K3) -> policy backward -> K5 update, and one WGAN-GP
-        step (K2b + K5).  NOT the headline metric: the policy trunk is a plain PyTorch module."""
+        step (K2b + K5).  NOT the headline metric: the learner's policy forward / backward is a PyTorch module
+        (SURVEY 8f); rollout and learner step are CUDA graphs."""
         agent_mod = import_module(sp.__name__ + ".agent")
         a = sp.get_args(["--env", WORLD_ENV, "--location_size", str(WORKLOAD["location_size"]), "--color_channel",
                          str(WORKLOAD["color_channel"]), "--episode_length", str(args.episode_length), "--loss", "gan",
@@ -457,7 +458,8 @@ def run_ours(args):
         ag = agent_mod.Agent(a, env)
         times = {"rollout": 0.0, "train_policy": 0.0, "train_gan": 0.0}
         ev = lambda: torch.cuda.Event(enable_timing=True)
-        for i in range(iters + 1):
+        warm = 3                                      # the rollout graph is captured at call 1, the learner graph at call 3
+        for i in range(iters + warm):
             e0, e1, e2, e3 = ev(), ev(), ev(), ev()
             e0.record()
             ro = ag.rollout()
@@ -467,7 +469,7 @@ def run_ours(args):
             ag.train_gan()
             e3.record()
             torch.cuda.synchronize()
-            if i > 0:
+            if i >= warm:
                 times["rollout"] += e0.elapsed_time(e1) / iters
                 times["train_policy"] += e1.elapsed_time(e2) / iters
                 times["train_gan"] += e2.elapsed_time(e3) / iters
