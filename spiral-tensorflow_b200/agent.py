@@ -51,6 +51,7 @@ class Agent(object):
         self.world = dist_utils.dist.get_world_size() if dist_utils.dist.is_initialized() else 1
         self._graph, self._graph_failed, self._g_out, self._g_target, self._g_z = None, False, {}, None, None
         self._tp_graph, self._tp_failed, self._tp_calls, self._tp_in, self._tp_out = None, False, 0, None, None
+        self._tg_graph, self._tg_failed, self._tg_calls, self._tg_in, self._tg_out = None, False, 0, None, None
 
     # ------------------------------------------------------------------
     @torch.no_grad()
@@ -202,19 +203,57 @@ class Agent(object):
                 "env/r": rollout["rewards"][:, -1].mean(), "batch": B}
 
     def train_gan(self, reals=None):
-        """agent.py:409-437 + discriminator.py:97-136 (WGAN-GP, penalty on the sigmoid output)."""
+        """agent.py:409-437 + discriminator.py:97-136 (WGAN-GP, penalty on the sigmoid output).  The batch (replay
+        sample, real images, interpolation factors) is drawn eagerly; the step itself -- three shared-weight passes, the
+        penalty's double backward, Adam, the kernels' weight re-pack -- is a CUDA graph from the third call on, like
+        ``train_policy``."""
         args, D = self.args, self.disc
         n = args.disc_batch_size
         fake = self.replay.sample(n)
         real = self.env.get_random_target(n) if reals is None else reals
-        p = D.params
         alpha = torch.rand((n, 1), generator=self.rng, device=self.device)
+        use_graph = (getattr(args, "cuda_graphs", True) and self.device.type == "cuda" and not self._tg_failed
+                     and self.world == 1)
+        if not use_graph:
+            return self._train_gan_body(fake, real, alpha)
+        self._tg_calls += 1
+        if self._tg_graph is None and self._tg_calls <= 2:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                out = self._train_gan_body(fake, real, alpha)
+            torch.cuda.current_stream().wait_stream(side)
+            return out
+        if self._tg_graph is None:
+            try:
+                self._tg_in = [t.to(self.device, torch.float32).clone() for t in (fake, real, alpha)]
+                self.disc_opt.zero_grad(set_to_none=True)
+                torch.cuda.synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._tg_out = self._train_gan_body(*self._tg_in, advance=False)
+                self._tg_graph = g
+            except Exception as e:
+                self._tg_failed, self._tg_graph = True, None
+                torch.cuda.synchronize()
+                import warnings
+                warnings.warn("CUDA-graph capture of the discriminator step failed (%s); running eagerly" % (e,))
+                return self._train_gan_body(fake, real, alpha)
+        for dst, src in zip(self._tg_in, (fake, real, alpha)):
+            dst.copy_(src)
+        self.disc_opt.advance()
+        self._tg_graph.replay()
+        return {k: v.clone() for k, v in self._tg_out.items()}
+
+    def _train_gan_body(self, fake, real, alpha, advance=True):
+        D = self.disc
+        p = D.params
         out = D.wgan_gp_loss(fake, real, alpha)          # convolutions + every gradient on K2b
         d_loss, critic, gp, fake_logits_mean = out["d_loss"], out["critic_loss"], out["gradient_penalty"], -out["g_loss"]
         self.disc_opt.zero_grad(set_to_none=True)
         d_loss.backward()
         dist_utils.allreduce_grads_([q.grad for q in p.values() if q.grad is not None], self.world, average=False)
-        self.disc_opt.step(grad_scale=1.0 / self.world)                                       # discriminator.py:124-126
+        self.disc_opt.step(grad_scale=1.0 / self.world, advance=advance)                      # discriminator.py:124-126
         D.sync_weights()
         return {"gan/critic_loss": critic.detach(), "gan/disc_loss": d_loss.detach(), "gan/penalty": gp.detach(),
                 "gan/gen_loss": -fake_logits_mean.detach()}

@@ -194,3 +194,38 @@ def test_graph_captured_learner_step_matches_eager_steps(native):
     apart = sum(float((p.detach() - q.detach()).pow(2).sum())
                 for p, q in zip(a_graph.policy.parameters(), a_eager.policy.parameters())) ** 0.5
     assert moved > 0 and apart < 0.05 * moved, (moved, apart)
+
+
+def test_graph_captured_discriminator_step_matches_eager_steps():
+    """Same check for train_gan: identical batches through a graph-replaying and an eager agent for five WGAN-GP steps."""
+    sp, agent_mod, _ = _mods()
+
+    def make(graphs):
+        args = make_args("simple_mnist", L=32, C=1, T=3,
+                         extra=["--cuda_graphs", str(graphs), "--disc_dim", "8", "--disc_batch_size", "8",
+                                "--disc_precision", "fp32", "--disc_lr", "1e-3"])
+        env = sp.create_env(args, num_envs=8)
+        torch.manual_seed(0)
+        return agent_mod.Agent(args, env)
+
+    a_graph, a_eager = make(True), make(False)
+    for k, v in a_graph.disc.params.items():
+        a_eager.disc.params[k].data.copy_(v.data)
+    a_eager.disc.sync_weights()
+    start = {k: v.detach().clone() for k, v in a_graph.disc.params.items()}
+    g = torch.Generator(device="cuda")
+    g.manual_seed(3)
+    for i in range(5):
+        fake = torch.rand((8, 64, 64, 1), generator=g, device="cuda") * 255
+        real = torch.rand((8, 64, 64, 1), generator=g, device="cuda") * 255
+        for ag in (a_graph, a_eager):
+            ag.replay.sample = lambda n, f=fake: f          # same fakes for both
+            ag.rng.manual_seed(100 + i)                     # same interpolation factors
+        m_g, m_e = a_graph.train_gan(real), a_eager.train_gan(real)
+        assert torch.allclose(m_g["gan/disc_loss"], m_e["gan/disc_loss"], rtol=2e-2, atol=1e-3), i
+    assert a_graph._tg_graph is not None and not a_graph._tg_failed
+    assert a_graph.disc_opt.t == a_eager.disc_opt.t == 5
+    moved = sum(float((v.detach() - start[k]).pow(2).sum()) for k, v in a_graph.disc.params.items()) ** 0.5
+    apart = sum(float((v.detach() - a_eager.disc.params[k].detach()).pow(2).sum())
+                for k, v in a_graph.disc.params.items()) ** 0.5
+    assert moved > 0 and apart < 0.05 * moved, (moved, apart)
