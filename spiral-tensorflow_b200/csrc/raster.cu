@@ -19,6 +19,7 @@
 // --fmad=false, transcendental functions from detmath.cuh.
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "detmath.cuh"
 #include "raster.cuh"
@@ -818,12 +819,17 @@ struct __align__(16) SharedDab {
     uint32_t pad;
 };
 
-template <int C>
-__global__ void __launch_bounds__(32 * kCompWarps, kCompResident / kCompWarps)
+// SMT (small batches): the warp's whole fix15 tile (32 KB) lives in shared memory for the step.  With few canvases per SM
+// nothing hides the latency of the ordered blend's load -> blend -> store chain through L1/L2 (two thirds of the longest
+// canvas's time at 1,024 canvases per GPU); from shared memory the chain is ~4x shorter, and the 64 KB in / dirty rows out
+// per canvas are noise when the batch is small.  Same arithmetic, bit-identical canvases.
+template <int C, bool SMT>
+__global__ void __launch_bounds__(32 * kCompWarps, SMT ? 3 : kCompResident / kCompWarps)
 composite_kernel(const __grid_constant__ EnvParams P, uint16_t *__restrict__ canvas,
                  const float *__restrict__ dabs, const int32_t *__restrict__ dab_count,
                  const uint16_t *__restrict__ dither, float *__restrict__ obs, int32_t *__restrict__ work_counter)
 {
+    extern __shared__ __align__(16) uint8_t s_tiles[];   // SMT: [kCompWarps][64*64] RGBA u16x4
     __shared__ SharedDab s_dab[kCompWarps][32];
     __shared__ uint16_t s_pair[kCompWarps][kDense];     // owner dab << 8 | (yp - y0) << 4 | (xp - x0)
     __shared__ uint16_t s_opa[kCompWarps][kDense];      // opa_a of the pair
@@ -842,7 +848,16 @@ composite_kernel(const __grid_constant__ EnvParams P, uint16_t *__restrict__ can
     const int color_idx = dab_count[2 * b + 1];
     const uint32_t col_r = P.colors[color_idx][0], col_g = P.colors[color_idx][1],
                    col_b = P.colors[color_idx][2];
-    uint2 *tile = reinterpret_cast<uint2 *>(canvas + (size_t)b * kTile * kTile * 4);   // RGBA u16x4 per pixel
+    uint2 *gtile = reinterpret_cast<uint2 *>(canvas + (size_t)b * kTile * kTile * 4);   // RGBA u16x4 per pixel
+    uint2 *tile = gtile;
+    if (SMT) {
+        tile = reinterpret_cast<uint2 *>(s_tiles) + warp * (kTile * kTile);
+        const uint4 *g4 = reinterpret_cast<const uint4 *>(gtile);
+        uint4 *t4 = reinterpret_cast<uint4 *>(tile);
+#pragma unroll 8
+        for (int i = lane; i < kTile * kTile / 2; i += 32) t4[i] = g4[i];
+        __syncwarp();
+    }
     const float4 *dl = reinterpret_cast<const float4 *>(dabs + (size_t)b * P.max_dabs * kDabFloats);
     SharedDab *sd = s_dab[warp];
     uint16_t *sp = s_pair[warp], *so = s_opa[warp];
@@ -1018,6 +1033,7 @@ composite_kernel(const __grid_constant__ EnvParams P, uint16_t *__restrict__ can
     for (int y = ymin; y <= ymax; y++) {
         const int i = y * (kTile / 2) + lane;                          // pixel-pair index
         const uint4 v = src[i];
+        if (SMT) reinterpret_cast<uint4 *>(gtile)[i] = v;            // dirty rows back to the canvas
         const uint32_t R0 = v.x & 0xffffu, G0 = v.x >> 16, B0 = v.y & 0xffffu;
         const uint32_t R1 = v.z & 0xffffu, G1 = v.z >> 16, B1 = v.w & 0xffffu;
         uint32_t add0 = 16384u, add1 = 16384u;
@@ -1175,19 +1191,34 @@ cudaError_t launch_composite(const EnvParams &P, uint16_t *canvas, const float *
                              const int32_t *dab_count, const uint16_t *dither, float *obs,
                              int32_t *work_counter, cudaStream_t st)
 {
-    int blocks = (P.B + kCompWarps - 1) / kCompWarps;
-    if (blocks > 148 * kCompResident / kCompWarps) blocks = 148 * kCompResident / kCompWarps;   // one resident warp per slot
     cudaMemsetAsync(work_counter, 0, sizeof(int32_t), st);
     static bool carveout = false;
+    constexpr int kSmtBytes = kCompWarps * kTile * kTile * 8;
     if (!carveout) {      // 32 resident warps need 32 x 5.8 KB of shared memory: ask for the large carve-out
-        cudaFuncSetAttribute(composite_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        cudaFuncSetAttribute(composite_kernel<3>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaFuncSetAttribute(composite_kernel<1, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaFuncSetAttribute(composite_kernel<3, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        cudaFuncSetAttribute(composite_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmtBytes);
+        cudaFuncSetAttribute(composite_kernel<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmtBytes);
         carveout = true;
     }
+    // small batches: tiles in shared memory (SPIRAL_COMPOSITE_SMEM_MAX overrides the largest batch that uses it; 0 = never)
+    int smt_max = 2048;
+    if (const char *e = getenv("SPIRAL_COMPOSITE_SMEM_MAX")) smt_max = atoi(e);
+    if (P.B <= smt_max) {
+        int blocks = (P.B + kCompWarps - 1) / kCompWarps;
+        if (blocks > 148 * 3) blocks = 148 * 3;
+        if (P.C == 1)
+            composite_kernel<1, true><<<blocks, 32 * kCompWarps, kSmtBytes, st>>>(P, canvas, dabs, dab_count, dither, obs, work_counter);
+        else
+            composite_kernel<3, true><<<blocks, 32 * kCompWarps, kSmtBytes, st>>>(P, canvas, dabs, dab_count, dither, obs, work_counter);
+        return cudaGetLastError();
+    }
+    int blocks = (P.B + kCompWarps - 1) / kCompWarps;
+    if (blocks > 148 * kCompResident / kCompWarps) blocks = 148 * kCompResident / kCompWarps;   // one resident warp per slot
     if (P.C == 1)
-        composite_kernel<1><<<blocks, 32 * kCompWarps, 0, st>>>(P, canvas, dabs, dab_count, dither, obs, work_counter);
+        composite_kernel<1, false><<<blocks, 32 * kCompWarps, 0, st>>>(P, canvas, dabs, dab_count, dither, obs, work_counter);
     else
-        composite_kernel<3><<<blocks, 32 * kCompWarps, 0, st>>>(P, canvas, dabs, dab_count, dither, obs, work_counter);
+        composite_kernel<3, false><<<blocks, 32 * kCompWarps, 0, st>>>(P, canvas, dabs, dab_count, dither, obs, work_counter);
     return cudaGetLastError();
 }
 cudaError_t launch_debug_dabs(const EnvParams &P, const float *dabs, const int32_t *dab_count,
