@@ -232,32 +232,16 @@ __device__ __forceinline__ void curve_point(const StepSetup &st, int i, double &
     py = y3 + y5 * ratio;
 }
 
-__global__ void __launch_bounds__(kExpandThreads, EXPAND_MIN_BLOCKS)
-expand_kernel(const __grid_constant__ EnvParams P, const int32_t *__restrict__ actions,
-              float *__restrict__ brush_state, double *__restrict__ env_state,
-              float *__restrict__ dabs, int32_t *__restrict__ dab_count, int32_t *__restrict__ status,
-              const float *__restrict__ gauss_tab, int lanes, const int32_t *__restrict__ perm, int n_solo)
+// One canvas's env step of the brush state machine (the body of expand_kernel).  STREAM: the fused small-batch step
+// (step_small_kernel) runs this in one thread while a second warp of the CTA composites the dabs as they appear;
+// prog = {dabs published, done, colour index, started} in shared memory.
+template <bool STREAM>
+__device__ __forceinline__ void expand_one(const EnvParams &P, const int b, const int32_t *__restrict__ actions,
+                                           float *__restrict__ brush_state, double *__restrict__ env_state,
+                                           float *__restrict__ dabs, int32_t *__restrict__ dab_count,
+                                           int32_t *__restrict__ status, const float *__restrict__ gauss_tab,
+                                           volatile int *prog)
 {
-    // `lanes` canvases per warp (1..32, host-chosen): the brush state machine is a latency-bound
-    // serial chain, so with few canvases it pays to give each its own warp (no intra-warp divergence
-    // or load imbalance, more resident warps per SM to hide latency) and leave the other lanes idle.
-    const int tid = threadIdx.x;
-    // slots are in order of decreasing predicted chain length (perm): the first n_solo canvases -- the ones
-    // that decide the kernel's duration -- get a warp each (no divergence against shorter neighbours, lowest
-    // per-iteration latency), the rest are packed `lanes` per warp next to canvases of similar length
-    int slot;
-    if ((int)blockIdx.x < n_solo) {
-        if (tid != 0) return;
-        slot = blockIdx.x;
-    } else {
-        if (tid >= lanes) return;
-        slot = n_solo + ((int)blockIdx.x - n_solo) * lanes + tid;
-    }
-    if (slot >= P.B) return;
-    // canvases sorted by predicted chain length (plan_kernel / scatter_kernel): the lanes of a warp walk
-    // chains of similar length instead of idling behind the longest one
-    const int b = perm ? perm[slot] : slot;
-
     float *bs = brush_state + (size_t)b * kBrushFloats;
     double *es = env_state + (size_t)b * kEnvDoubles;
     Brush S;
@@ -335,6 +319,11 @@ expand_kernel(const __grid_constant__ EnvParams P, const int32_t *__restrict__ a
         st.n_events = 2;
     }
 
+    if (STREAM) {                                        // the consumer needs the colour before the first dab
+        prog[2] = color_idx;
+        __threadfence_block();
+        prog[3] = 1;
+    }
     float *my_dabs = dabs + (size_t)b * P.max_dabs * kDabFloats;
     int n_dabs = 0;
     int err = 0;
@@ -469,6 +458,10 @@ expand_kernel(const __grid_constant__ EnvParams P, const int32_t *__restrict__ a
                         d[0] = make_float4(x, y, rl, S.AR);
                         d[1] = make_float4(opq, S.v_hard, S.v_aa, has_rand ? 1.0f : 0.0f);
                         n_dabs++;
+                        if (STREAM) {                    // publish the dab to the compositing warp of this CTA
+                            __threadfence_block();
+                            prog[0] = n_dabs;
+                        }
                     } else {
                         err |= 1;
                     }
@@ -498,6 +491,39 @@ expand_kernel(const __grid_constant__ EnvParams P, const int32_t *__restrict__ a
     dab_count[2 * b] = n_dabs;
     dab_count[2 * b + 1] = color_idx;
     if (err) atomicOr(status, err);
+    if (STREAM) {
+        __threadfence_block();
+        prog[1] = 1;                                     // done: prog[0] is final
+    }
+}
+
+__global__ void __launch_bounds__(kExpandThreads, EXPAND_MIN_BLOCKS)
+expand_kernel(const __grid_constant__ EnvParams P, const int32_t *__restrict__ actions,
+              float *__restrict__ brush_state, double *__restrict__ env_state,
+              float *__restrict__ dabs, int32_t *__restrict__ dab_count, int32_t *__restrict__ status,
+              const float *__restrict__ gauss_tab, int lanes, const int32_t *__restrict__ perm, int n_solo)
+{
+    // `lanes` canvases per warp (1..32, host-chosen): the brush state machine is a latency-bound
+    // serial chain, so with few canvases it pays to give each its own warp (no intra-warp divergence
+    // or load imbalance, more resident warps per SM to hide latency) and leave the other lanes idle.
+    const int tid = threadIdx.x;
+    // slots are in order of decreasing predicted chain length (perm): the first n_solo canvases -- the ones
+    // that decide the kernel's duration -- get a warp each (no divergence against shorter neighbours, lowest
+    // per-iteration latency), the rest are packed `lanes` per warp next to canvases of similar length
+    int slot;
+    if ((int)blockIdx.x < n_solo) {
+        if (tid != 0) return;
+        slot = blockIdx.x;
+    } else {
+        if (tid >= lanes) return;
+        slot = n_solo + ((int)blockIdx.x - n_solo) * lanes + tid;
+    }
+    if (slot >= P.B) return;
+    // canvases sorted by predicted chain length (plan_kernel / scatter_kernel): the lanes of a warp walk
+    // chains of similar length instead of idling behind the longest one
+    const int b = perm ? perm[slot] : slot;
+
+    expand_one<false>(P, b, actions, brush_state, env_state, dabs, dab_count, status, gauss_tab, nullptr);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -819,39 +845,33 @@ struct __align__(16) SharedDab {
     uint32_t pad;
 };
 
-// SMT (small batches): the warp's whole fix15 tile (32 KB) lives in shared memory for the step.  With few canvases per SM
-// nothing hides the latency of the ordered blend's load -> blend -> store chain through L1/L2 (two thirds of the longest
-// canvas's time at 1,024 canvases per GPU); from shared memory the chain is ~4x shorter, and the 64 KB in / dirty rows out
-// per canvas are noise when the batch is small.  Same arithmetic, bit-identical canvases.
-template <int C, bool SMT>
-__global__ void __launch_bounds__(32 * kCompWarps, SMT ? 3 : kCompResident / kCompWarps)
-composite_kernel(const __grid_constant__ EnvParams P, uint16_t *__restrict__ canvas,
-                 const float *__restrict__ dabs, const int32_t *__restrict__ dab_count,
-                 const uint16_t *__restrict__ dither, float *__restrict__ obs, int32_t *__restrict__ work_counter)
+// One canvas's compositing step (the body of composite_kernel): walks the canvas's dab list in order.  STREAM: the
+// list is still being written by this CTA's expansion thread (step_small_kernel); prog = {dabs published, done,
+// colour index, started} in shared memory.
+template <int C, bool SMT, bool STREAM>
+__device__ __forceinline__ void composite_one(const EnvParams &P, const int b, uint16_t *__restrict__ canvas,
+                                              const float *__restrict__ dabs, const int32_t *__restrict__ dab_count,
+                                              const uint16_t *__restrict__ dither, float *__restrict__ obs,
+                                              SharedDab *sd, uint16_t *sp, uint16_t *so, int *soff, uint2 *stile,
+                                              const int lane, volatile int *prog)
 {
-    extern __shared__ __align__(16) uint8_t s_tiles[];   // SMT: [kCompWarps][64*64] RGBA u16x4
-    __shared__ SharedDab s_dab[kCompWarps][32];
-    __shared__ uint16_t s_pair[kCompWarps][kDense];     // owner dab << 8 | (yp - y0) << 4 | (xp - x0)
-    __shared__ uint16_t s_opa[kCompWarps][kDense];      // opa_a of the pair
-    __shared__ int s_off[kCompWarps][33];               // first pair of each dab of the round
-    const int lane = threadIdx.x & 31;
-    const int warp = threadIdx.x >> 5;
-    // persistent warps: canvases differ by 1000x in work (0 .. ~1750 dabs), so every warp pulls the next
-    // canvas from a global counter until the batch is drained instead of owning a fixed one
-    for (;;) {
-    int b = 0;
-    if (lane == 0) b = atomicAdd(work_counter, 1);
-    b = __shfl_sync(0xffffffffu, b, 0);
-    if (b >= P.B) return;
-    const int n_dabs = dab_count[2 * b];
-    if (n_dabs == 0) continue;                       // canvas and observation unchanged
-    const int color_idx = dab_count[2 * b + 1];
+    int n_dabs = STREAM ? 0 : dab_count[2 * b];
+    if (!STREAM && n_dabs == 0) return;              // canvas and observation unchanged
+    int color_idx;
+    if (STREAM) {                                    // the producer publishes the colour before its first dab
+        if (lane == 0) while (prog[3] == 0) __nanosleep(50);
+        __syncwarp();
+        color_idx = prog[2];
+    } else {
+        color_idx = dab_count[2 * b + 1];
+    }
+    bool done = !STREAM;
     const uint32_t col_r = P.colors[color_idx][0], col_g = P.colors[color_idx][1],
                    col_b = P.colors[color_idx][2];
     uint2 *gtile = reinterpret_cast<uint2 *>(canvas + (size_t)b * kTile * kTile * 4);   // RGBA u16x4 per pixel
     uint2 *tile = gtile;
     if (SMT) {
-        tile = reinterpret_cast<uint2 *>(s_tiles) + warp * (kTile * kTile);
+        tile = stile;
         const uint4 *g4 = reinterpret_cast<const uint4 *>(gtile);
         uint4 *t4 = reinterpret_cast<uint4 *>(tile);
 #pragma unroll 8
@@ -859,9 +879,6 @@ composite_kernel(const __grid_constant__ EnvParams P, uint16_t *__restrict__ can
         __syncwarp();
     }
     const float4 *dl = reinterpret_cast<const float4 *>(dabs + (size_t)b * P.max_dabs * kDabFloats);
-    SharedDab *sd = s_dab[warp];
-    uint16_t *sp = s_pair[warp], *so = s_opa[warp];
-    int *soff = s_off[warp];
     int ymin = kTile, ymax = -1;
 
     // calculate_opa: mask value (fix15) of one pixel of a dab
@@ -887,14 +904,33 @@ composite_kernel(const __grid_constant__ EnvParams P, uint16_t *__restrict__ can
 
     const float cs_rad_area_1 = P.cs * P.rad_area_1;
     int base = 0;
-    while (base < n_dabs) {
+    for (;;) {
+        if (STREAM && !done && n_dabs - base < 32) {
+            // wait until a full round of dabs is published, or the producer is done (read `done` first: its store
+            // follows the last update of the count)
+            int d = 0, a = 0;
+            if (lane == 0) {
+                for (;;) {
+                    d = prog[1];
+                    a = prog[0];
+                    if (d || a - base >= 32) break;
+                    __nanosleep(100);
+                }
+            }
+            done = __shfl_sync(0xffffffffu, d, 0) != 0;
+            n_dabs = __shfl_sync(0xffffffffu, a, 0);
+            __threadfence_block();                   // the dab loads below come after the count they depend on
+        }
+        if (base >= n_dabs) break;
         // ---- phase 0: finalise, count candidates ----
         const int mine = base + lane;
         FinalDab f;
         f.opacity = 0; f.x0 = 1; f.x1 = 0; f.y0 = 1; f.y1 = 0;
         f.x = f.y = f.radius = f.hardness = f.one_over_r2 = f.r_aa_start = 0;
         f.seg1_slope = f.seg2_offset = f.seg2_slope = 0;
-        if (mine < n_dabs) f = finalize_dab(__ldg(dl + 2 * mine), __ldg(dl + 2 * mine + 1));
+        if (mine < n_dabs)
+            f = STREAM ? finalize_dab(__ldcg(dl + 2 * mine), __ldcg(dl + 2 * mine + 1))     // written by this CTA's producer
+                       : finalize_dab(__ldg(dl + 2 * mine), __ldg(dl + 2 * mine + 1));
         const bool hit = f.opacity != 0;             // 0 also when the dab misses tile (0,0)
         const float rlim = f.radius * 1.001f + 0.01f;
         const float rlim2 = rlim * rlim;
@@ -1026,7 +1062,7 @@ composite_kernel(const __grid_constant__ EnvParams P, uint16_t *__restrict__ can
         ymin = min(ymin, __shfl_xor_sync(0xffffffffu, ymin, off));
         ymax = max(ymax, __shfl_xor_sync(0xffffffffu, ymax, off));
     }
-    if (ymax < ymin) continue;
+    if (ymax < ymin) return;
     const uint4 *src = reinterpret_cast<const uint4 *>(tile);        // uint4 = 2 RGBA pixels
     float *ob = obs + (size_t)b * kTile * kTile * C;
 #pragma unroll 4
@@ -1061,8 +1097,66 @@ composite_kernel(const __grid_constant__ EnvParams P, uint16_t *__restrict__ can
             o2[2] = make_float2((float)g1, (float)b1);
         }
     }
+}
+
+// SMT (small batches): the warp's whole fix15 tile (32 KB) lives in shared memory for the step.  With few canvases per SM
+// nothing hides the latency of the ordered blend's load -> blend -> store chain through L1/L2 (two thirds of the longest
+// canvas's time at 1,024 canvases per GPU); from shared memory the chain is ~4x shorter, and the 64 KB in / dirty rows out
+// per canvas are noise when the batch is small.  Same arithmetic, bit-identical canvases.
+template <int C, bool SMT>
+__global__ void __launch_bounds__(32 * kCompWarps, SMT ? 3 : kCompResident / kCompWarps)
+composite_kernel(const __grid_constant__ EnvParams P, uint16_t *__restrict__ canvas,
+                 const float *__restrict__ dabs, const int32_t *__restrict__ dab_count,
+                 const uint16_t *__restrict__ dither, float *__restrict__ obs, int32_t *__restrict__ work_counter)
+{
+    extern __shared__ __align__(16) uint8_t s_tiles[];   // SMT: [kCompWarps][64*64] RGBA u16x4
+    __shared__ SharedDab s_dab[kCompWarps][32];
+    __shared__ uint16_t s_pair[kCompWarps][kDense];     // owner dab << 8 | (yp - y0) << 4 | (xp - x0)
+    __shared__ uint16_t s_opa[kCompWarps][kDense];      // opa_a of the pair
+    __shared__ int s_off[kCompWarps][33];               // first pair of each dab of the round
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    // persistent warps: canvases differ by 1000x in work (0 .. ~1750 dabs), so every warp pulls the next
+    // canvas from a global counter until the batch is drained instead of owning a fixed one
+    for (;;) {
+    int b = 0;
+    if (lane == 0) b = atomicAdd(work_counter, 1);
+    b = __shfl_sync(0xffffffffu, b, 0);
+    if (b >= P.B) return;
+    composite_one<C, SMT, false>(P, b, canvas, dabs, dab_count, dither, obs, s_dab[warp], s_pair[warp], s_opa[warp], s_off[warp],
+                                 SMT ? reinterpret_cast<uint2 *>(s_tiles) + warp * (kTile * kTile) : nullptr, lane, nullptr);
     __syncwarp();
     }   // next canvas
+}
+
+// ------------------------------------------------------------------------------------------
+// Fused env step for small batches: CTA = one canvas, warp 0 (one thread) runs the brush state machine, warp 1
+// composites the dabs while they are being produced.  With a few canvases per SM the step is the longest canvas's
+// serial chain -- expansion (~1.9 ms) and THEN its compositing (~0.5 ms) as two kernels; here the consumer keeps up
+// with the producer (it is ~4x faster per dab), so the step ends a round of dabs after the chain does.  Same device
+// functions as the two-kernel path: bit-identical canvases, dab lists and observations.
+// ------------------------------------------------------------------------------------------
+template <int C>
+__global__ void __launch_bounds__(64, 8)
+step_small_kernel(const __grid_constant__ EnvParams P, const int32_t *__restrict__ actions,
+                  float *__restrict__ brush_state, double *__restrict__ env_state, float *__restrict__ dabs,
+                  int32_t *__restrict__ dab_count, int32_t *__restrict__ status, const float *__restrict__ gauss_tab,
+                  uint16_t *__restrict__ canvas, const uint16_t *__restrict__ dither, float *__restrict__ obs)
+{
+    __shared__ SharedDab s_dab[32];
+    __shared__ uint16_t s_pair[kDense];
+    __shared__ uint16_t s_opa[kDense];
+    __shared__ int s_off[33];
+    __shared__ int s_prog[4];              // dabs published, done, colour index, started
+    const int b = blockIdx.x;
+    if (threadIdx.x < 4) s_prog[threadIdx.x] = 0;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        expand_one<true>(P, b, actions, brush_state, env_state, dabs, dab_count, status, gauss_tab, s_prog);
+    } else if (threadIdx.x >= 32) {
+        composite_one<C, false, true>(P, b, canvas, dabs, dab_count, dither, obs, s_dab, s_pair, s_opa, s_off, nullptr,
+                                      threadIdx.x & 31, s_prog);
+    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1219,6 +1313,23 @@ cudaError_t launch_composite(const EnvParams &P, uint16_t *canvas, const float *
         composite_kernel<1, false><<<blocks, 32 * kCompWarps, 0, st>>>(P, canvas, dabs, dab_count, dither, obs, work_counter);
     else
         composite_kernel<3, false><<<blocks, 32 * kCompWarps, 0, st>>>(P, canvas, dabs, dab_count, dither, obs, work_counter);
+    return cudaGetLastError();
+}
+// fused small-batch step (SPIRAL_FUSED_STEP_MAX: largest batch that uses it, default 148 x 8 = one wave; 0 = never)
+bool fused_step_applies(const EnvParams &P)
+{
+    int mx = 148 * 8;
+    if (const char *e = getenv("SPIRAL_FUSED_STEP_MAX")) mx = atoi(e);
+    return P.B <= mx;
+}
+cudaError_t launch_step_small(const EnvParams &P, const int32_t *actions, float *bs, double *es, float *dabs,
+                              int32_t *dab_count, int32_t *status, const float *gauss_tab, uint16_t *canvas,
+                              const uint16_t *dither, float *obs, cudaStream_t st)
+{
+    if (P.C == 1)
+        step_small_kernel<1><<<P.B, 64, 0, st>>>(P, actions, bs, es, dabs, dab_count, status, gauss_tab, canvas, dither, obs);
+    else
+        step_small_kernel<3><<<P.B, 64, 0, st>>>(P, actions, bs, es, dabs, dab_count, status, gauss_tab, canvas, dither, obs);
     return cudaGetLastError();
 }
 cudaError_t launch_debug_dabs(const EnvParams &P, const float *dabs, const int32_t *dab_count,
