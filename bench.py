@@ -353,7 +353,7 @@ def run_ours(args):
             sampler.start()
         # batches of at most one wave take spiral_env_step's fused kernel (include/spiral_b200.h): `value` is then timed
         # through spiral_env_step itself and the expand / composite split comes from a separate, untimed recorded pass
-        fused = B <= int(os.environ.get("SPIRAL_FUSED_STEP_MAX", 148 * 8))
+        fused = B <= int(os.environ.get("SPIRAL_FUSED_STEP_MAX", 148 * 8 * 2))
         ms = timed(resident=True, record=not fused)
         if fused:
             for _ in range(args.steps):
@@ -396,7 +396,7 @@ def run_ours(args):
                     disc=dict(ms=t_disc, tflops=340.25e6 * B / (t_disc * 1e-3) / 1e12, precision=args.disc_precision))
         # reset + T x (expand [+ plan + scatter when the work-sorted schedule is on] + composite)
         # + D forward (conv0, 5 x conv_tc, 5 x bn_finalize, 4 x act_split, dense_sigmoid) + A2C (gae, row, final)
-        launches_per_episode = 1 + (1 if fused else 4 if B >= 32768 else 2) * T + (1 + 5 + 5 + 4 + 1) + 3
+        launches_per_episode = 1 + ((1 if B <= 148 * 8 else 3) if fused else 4 if B >= 32768 else 2) * T + (1 + 5 + 5 + 4 + 1) + 3
         footprint = (env.canvas.numel() * 2 + env.obs.numel() * 4 + env.dab_scratch.numel() * 4 + 2 * dlogits_bytes
                      + disc.workspace.numel()) / 2 ** 20
         out = dict(metric="env-steps/sec (render+D reward+A2C) on 64x64 canvases", value=value, unit="env-steps/s",

@@ -27,7 +27,7 @@ cudaError_t launch_composite(const EnvParams &P, uint16_t *canvas, const float *
 bool fused_step_applies(const EnvParams &P);
 cudaError_t launch_step_small(const EnvParams &P, const int32_t *actions, float *bs, double *es, float *dabs,
                               int32_t *dab_count, int32_t *status, const float *gauss_tab, uint16_t *canvas,
-                              const uint16_t *dither, float *obs, cudaStream_t st);
+                              const uint16_t *dither, float *obs, int32_t *plan_scratch, cudaStream_t st);
 cudaError_t launch_debug_dabs(const EnvParams &P, const float *dabs, const int32_t *dab_count, float *out,
                               int32_t *out_count, cudaStream_t st);
 cudaError_t launch_l2_reward(const float *obs, const float *target, float *reward, int batch, int n, cudaStream_t st);
@@ -373,7 +373,7 @@ extern "C" int spiral_env_step(SpiralEnv *env, const int32_t *actions, uint16_t 
         // small batches: one kernel, a canvas's dabs are composited while its brush chain is still producing them
         REQUIRE(actions); REQUIRE(canvas); REQUIRE(bs); REQUIRE(es); REQUIRE(dabs); REQUIRE(dab_count); REQUIRE(obs); REQUIRE(status);
         const cudaError_t e = launch_step_small(env->P, actions, bs, es, dabs, dab_count, status, env->d_gauss, canvas,
-                                                env->d_dither, obs, (cudaStream_t)stream);
+                                                env->d_dither, obs, env->d_plan + 64, (cudaStream_t)stream);
         return e == cudaSuccess ? SPIRAL_OK : spiral_cuda_error(e, "spiral_env_step");
     }
     int rc = spiral_env_expand(env, actions, bs, es, dabs, dab_count, status, stream);

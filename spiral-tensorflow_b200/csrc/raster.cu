@@ -828,6 +828,9 @@ __device__ __forceinline__ float span_sqrt(float h2)
 //            instruction regardless of dab boundaries (a dab alone fills ~17 of 32 lanes)
 //   phase 2  the cheap, order-dependent part: dab by dab, blend the pixels whose opa_a != 0
 // Dabs the disc test does not cover (radius >= 3, elliptical brushes) take the bounding-box walk.
+#ifndef FUSED_STEP_MAX_DEFAULT
+#define FUSED_STEP_MAX_DEFAULT (148 * 8 * 2)      // measured (B200): wins up to ~3k canvases, loses from 4k
+#endif
 #ifndef COMP_WARPS_PER_SM
 #define COMP_WARPS_PER_SM 40
 #endif
@@ -1141,14 +1144,17 @@ __global__ void __launch_bounds__(64, 8)
 step_small_kernel(const __grid_constant__ EnvParams P, const int32_t *__restrict__ actions,
                   float *__restrict__ brush_state, double *__restrict__ env_state, float *__restrict__ dabs,
                   int32_t *__restrict__ dab_count, int32_t *__restrict__ status, const float *__restrict__ gauss_tab,
-                  uint16_t *__restrict__ canvas, const uint16_t *__restrict__ dither, float *__restrict__ obs)
+                  uint16_t *__restrict__ canvas, const uint16_t *__restrict__ dither, float *__restrict__ obs,
+                  const int32_t *__restrict__ perm)
 {
     __shared__ SharedDab s_dab[32];
     __shared__ uint16_t s_pair[kDense];
     __shared__ uint16_t s_opa[kDense];
     __shared__ int s_off[33];
     __shared__ int s_prog[4];              // dabs published, done, colour index, started
-    const int b = blockIdx.x;
+    // more than one wave of CTAs: canvases in order of decreasing predicted chain length (plan_kernel / scatter_kernel),
+    // so the longest chains start first and the short ones fill the slots they leave (the mean chain is ~1/5 of the longest)
+    const int b = perm ? perm[blockIdx.x] : blockIdx.x;
     if (threadIdx.x < 4) s_prog[threadIdx.x] = 0;
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -1315,21 +1321,34 @@ cudaError_t launch_composite(const EnvParams &P, uint16_t *canvas, const float *
         composite_kernel<3, false><<<blocks, 32 * kCompWarps, 0, st>>>(P, canvas, dabs, dab_count, dither, obs, work_counter);
     return cudaGetLastError();
 }
-// fused small-batch step (SPIRAL_FUSED_STEP_MAX: largest batch that uses it, default 148 x 8 = one wave; 0 = never)
+// fused small-batch step (SPIRAL_FUSED_STEP_MAX: largest batch that uses it; 0 = never)
+constexpr int kFusedWave = 148 * 8;        // CTAs of step_small_kernel resident at once
 bool fused_step_applies(const EnvParams &P)
 {
-    int mx = 148 * 8;
+    int mx = FUSED_STEP_MAX_DEFAULT;
     if (const char *e = getenv("SPIRAL_FUSED_STEP_MAX")) mx = atoi(e);
     return P.B <= mx;
 }
 cudaError_t launch_step_small(const EnvParams &P, const int32_t *actions, float *bs, double *es, float *dabs,
                               int32_t *dab_count, int32_t *status, const float *gauss_tab, uint16_t *canvas,
-                              const uint16_t *dither, float *obs, cudaStream_t st)
+                              const uint16_t *dither, float *obs, int32_t *plan_scratch, cudaStream_t st)
 {
+    const int32_t *perm = nullptr;
+    if (P.B > kFusedWave && plan_scratch) {
+        // plan_scratch: i32 [512] histogram + cursors | i32 [B] permutation | u8 [B] keys  (as in launch_expand)
+        int32_t *hist = plan_scratch;
+        int32_t *pm = plan_scratch + 2 * kPlanBuckets;
+        uint8_t *key = reinterpret_cast<uint8_t *>(pm + P.B);
+        cudaMemsetAsync(hist, 0, 2 * kPlanBuckets * sizeof(int32_t), st);
+        const int pb = (P.B + 255) / 256;
+        plan_kernel<<<pb, 256, 0, st>>>(P, actions, es, key, hist);
+        scatter_kernel<<<pb, 256, 0, st>>>(P.B, key, hist, pm);
+        perm = pm;
+    }
     if (P.C == 1)
-        step_small_kernel<1><<<P.B, 64, 0, st>>>(P, actions, bs, es, dabs, dab_count, status, gauss_tab, canvas, dither, obs);
+        step_small_kernel<1><<<P.B, 64, 0, st>>>(P, actions, bs, es, dabs, dab_count, status, gauss_tab, canvas, dither, obs, perm);
     else
-        step_small_kernel<3><<<P.B, 64, 0, st>>>(P, actions, bs, es, dabs, dab_count, status, gauss_tab, canvas, dither, obs);
+        step_small_kernel<3><<<P.B, 64, 0, st>>>(P, actions, bs, es, dabs, dab_count, status, gauss_tab, canvas, dither, obs, perm);
     return cudaGetLastError();
 }
 cudaError_t launch_debug_dabs(const EnvParams &P, const float *dabs, const int32_t *dab_count,
