@@ -52,6 +52,13 @@ __global__ void gae_kernel(const float *__restrict__ rewards, const float *__res
 }
 
 constexpr int kRowThreads = 128;
+#ifndef A2C_MIN_BLOCKS
+#define A2C_MIN_BLOCKS 12      // 40 registers, 48 warps per SM, no spills (16 -> 32 registers with spills)
+#endif
+#ifndef A2C_UNROLL
+#define A2C_UNROLL 4
+#endif
+constexpr int kGradUnroll = A2C_UNROLL;
 // e^x for x <= 0 via ex2.approx: relative error ~1e-6 at |x| = 20, far inside the 2e-5 the parity tests hold.
 // Three sweeps through L1 with this exponential reach 85 % (B = 16384) / 70 % (B = 65536) of the measured HBM
 // peak; holding the row in registers (80 registers, 24 warps per SM) and a persistent bulk-async (cp.async.bulk +
@@ -98,23 +105,74 @@ __device__ __forceinline__ float block_sum(float v, float *s)
     return r;
 }
 
-__global__ void __launch_bounds__(kRowThreads)
+// both sums of sweep 2 in one pass over the barrier pair
+__device__ __forceinline__ float2 block_sum2(float a, float b, float2 *s)
+{
+    a = warp_sum(a);
+    b = warp_sum(b);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = make_float2(a, b);
+    __syncthreads();
+    float2 r = s[0];
+#pragma unroll
+    for (int i = 1; i < kRowThreads / 32; i++) { r.x += s[i].x; r.y += s[i].y; }
+    return r;
+}
+
+// Instruction budget (ncu, round 1: 44 thread-instructions per logit, issue slots 91 % busy at 67 % of DRAM
+// throughput -- the kernel was issue-bound).  Two things took most of it and are gone: (1) the scalar heads
+// (jump / pressure / size / colour: 2..8 logits) ran the block path -- three block reductions with two barriers each
+// for 128 threads, ~45 % of a row's instructions for 0.2 % of its logits; a head of <= 32 logits is now one WARP's
+// work (warp k % 4, lane = logit, shuffles only), concurrent with the other warps' heads; (2) the gradient sweep
+// evaluates  g = p (a + c (ent - logS) + c z)  with the row constants hoisted (5 instructions per logit instead of
+// 15) and the taken action's  -a  applied after the loop by the thread that wrote that element.
+__global__ void __launch_bounds__(kRowThreads, A2C_MIN_BLOCKS)
 a2c_row_kernel(const __grid_constant__ A2CHeads H, const int32_t *__restrict__ actions,
                const float *__restrict__ adv, const float *__restrict__ ret,
                const float *__restrict__ vf, float entropy_coeff, float *__restrict__ dvf,
                float *__restrict__ partial)
 {
     __shared__ float s_red[kRowThreads / 32];
+    __shared__ float2 s_red2[kRowThreads / 32];
+    __shared__ float2 s_warp[kRowThreads / 32];
     const int row = blockIdx.x;
     const int tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
     const float a = adv[row];
-    float pi_acc = 0.0f, ent_acc = 0.0f;
+    float pi_acc = 0.0f, ent_acc = 0.0f;        // block-path heads: the same value in every thread
+    float pi_w = 0.0f, ent_w = 0.0f;            // warp-path heads: the same value in every lane of the owning warp
+    constexpr float kLog2e = 1.4426950408889634f;
 
     for (int k = 0; k < H.K; k++) {
         const int n = H.size[k];
         const float *x = H.logits[k] + (size_t)row * n;
         float *dx = H.dlogits[k] ? H.dlogits[k] + (size_t)row * n : nullptr;
         const int act = actions[(size_t)row * H.K + k];
+
+        if (n <= 32) {
+            // ---- scalar heads: one warp, one logit per lane ----
+            if (warp != (k & (kRowThreads / 32 - 1))) continue;
+            const bool on = lane < n;
+            const float xv = on ? x[lane] : -INFINITY;
+            const float m = warp_max(xv);
+            const float z = on ? xv - m : 0.0f;
+            const float e = on ? fast_exp(z) : 0.0f;
+            const float S = warp_sum(e);
+            const float D = warp_sum(e * z);
+            const float logS = logf(S);
+            const float invS = 1.0f / S;
+            const float ent = logS - D * invS;
+            const float logp_a = __shfl_sync(0xffffffffu, z, act) - logS;
+            pi_w += -(logp_a * a);
+            ent_w += ent;
+            if (dx && on) {
+                const float p = e * invS;
+                float g = a * p + entropy_coeff * p * ((z - logS) + ent);
+                if (lane == act) g -= a;
+                dx[lane] = g;
+            }
+            continue;
+        }
         const bool vec = (n & 3) == 0;
 
         // sweep 1: max
@@ -149,9 +207,11 @@ a2c_row_kernel(const __grid_constant__ A2CHeads H, const int32_t *__restrict__ a
                 D += e * z;
             }
         }
-        S = block_sum(S, s_red);
-        D = block_sum(D, s_red);
-        const float logS = logf(S);
+        const float2 SD = block_sum2(S, D, s_red2);
+        S = SD.x;
+        D = SD.y;
+        const float log2S = log2f(S);
+        const float logS = log2S * 0.6931471805599453f;
         const float invS = 1.0f / S;
         // entropy = -sum p logp = logS - D/S ;  logp[act] = x[act] - m - logS
         const float ent = logS - D * invS;
@@ -160,39 +220,40 @@ a2c_row_kernel(const __grid_constant__ A2CHeads H, const int32_t *__restrict__ a
         ent_acc += ent;
 
         // sweep 3: d total / d logit_j = adv (p_j - 1[j==act]) + coeff p_j (logp_j + ent)
+        //        = p_j (c1 + coeff z_j) - adv 1[j==act],   p_j = 2^(z_j log2e - log2 S),  c1 = adv + coeff (ent - logS)
         if (dx) {
+            const float c1 = a + entropy_coeff * (ent - logS);
+            const float nl2S = -log2S;
+#define A2C_GRAD(xv) ({ const float z_ = (xv) - m; float p_; \
+                        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(p_) : "f"(fmaf(z_, kLog2e, nl2S))); \
+                        p_ * fmaf(entropy_coeff, z_, c1); })
             if (vec) {
                 const float4 *x4 = reinterpret_cast<const float4 *>(x);
                 float4 *d4 = reinterpret_cast<float4 *>(dx);
+#pragma unroll kGradUnroll
                 for (int i = tid; i < n / 4; i += kRowThreads) {
                     const float4 v = x4[i];
                     float4 g;
-                    float z, p;
-                    z = v.x - m; p = fast_exp(z) * invS; g.x = a * p + entropy_coeff * p * ((z - logS) + ent);
-                    z = v.y - m; p = fast_exp(z) * invS; g.y = a * p + entropy_coeff * p * ((z - logS) + ent);
-                    z = v.z - m; p = fast_exp(z) * invS; g.z = a * p + entropy_coeff * p * ((z - logS) + ent);
-                    z = v.w - m; p = fast_exp(z) * invS; g.w = a * p + entropy_coeff * p * ((z - logS) + ent);
-                    const int j = i * 4;
-                    if (act >= j && act < j + 4) {
-                        if (act == j) g.x -= a;
-                        else if (act == j + 1) g.y -= a;
-                        else if (act == j + 2) g.z -= a;
-                        else g.w -= a;
-                    }
+                    g.x = A2C_GRAD(v.x);
+                    g.y = A2C_GRAD(v.y);
+                    g.z = A2C_GRAD(v.z);
+                    g.w = A2C_GRAD(v.w);
                     d4[i] = g;
                 }
+                if (((act >> 2) & (kRowThreads - 1)) == tid) dx[act] -= a;     // this thread wrote element `act`
             } else {
-                for (int i = tid; i < n; i += kRowThreads) {
-                    const float z = x[i] - m;
-                    const float p = fast_exp(z) * invS;
-                    float g = a * p + entropy_coeff * p * ((z - logS) + ent);
-                    if (i == act) g -= a;
-                    dx[i] = g;
-                }
+                for (int i = tid; i < n; i += kRowThreads) dx[i] = A2C_GRAD(x[i]);
+                if ((act & (kRowThreads - 1)) == tid) dx[act] -= a;
             }
+#undef A2C_GRAD
         }
     }
+    // scalar heads were summed by their warps: combine in a fixed order
+    if (lane == 0) s_warp[warp] = make_float2(pi_w, ent_w);
+    __syncthreads();
     if (tid == 0) {
+#pragma unroll
+        for (int w = 0; w < kRowThreads / 32; w++) { pi_acc += s_warp[w].x; ent_acc += s_warp[w].y; }
         const float d = vf[row] - ret[row];
         // vf_loss = 0.5 * sum (vf - r)^2 is added (x 0.5) once per head: agent.py:186-190
         if (dvf) dvf[row] = 0.5f * (float)H.K * d;
