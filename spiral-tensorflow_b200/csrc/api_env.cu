@@ -221,12 +221,6 @@ extern "C" int spiral_env_create(const SpiralEnvCfg *cfg, SpiralEnv **out)
         const char *sd = getenv("SPIRAL_EXPAND_SOLO_DIV");
         P.expand_solo_div = sd ? atoi(sd) : 128;
         if (P.expand_solo_div < 1) P.expand_solo_div = 128;
-        const char *sm = getenv("SPIRAL_EXPAND_SOLO_MAX");
-        P.expand_solo_max = sm ? atoi(sm) : 256;
-        if (P.expand_solo_max < 0) P.expand_solo_max = 256;
-        const char *wp = getenv("SPIRAL_EXPAND_WPS");        // persistent-lane schedule: expansion warps per SM (0 = off)
-        P.expand_wps = wp ? atoi(wp) : 0;
-        if (P.expand_wps < 0 || P.expand_wps > 16) P.expand_wps = 0;
     }
     for (int s = 0; s < SPIRAL_DYN_COUNT; s++) {
         MapDev &m = P.dyn[s];

@@ -232,50 +232,102 @@ __device__ __forceinline__ void curve_point(const StepSetup &st, int i, double &
     py = y3 + y5 * ratio;
 }
 
-// Where a lane of the expansion gets its canvases from: one fixed canvas (solo warps, the fused small-batch step), or
-// the work-sorted queue (persistent lanes: when a lane's canvas ends it pulls the next-longest one, so the lanes of a
-// warp stay busy instead of idling behind the warp's longest chain).
-struct CanvasFeed {
-    int fixed;                  // the one canvas when queue == nullptr; -1 once taken
-    int32_t *queue;             // global cursor over the slots [base, B)
-    const int32_t *perm;        // slot -> canvas (decreasing predicted chain length); nullptr = identity
-    int base, B;
-    __device__ __forceinline__ int next()
-    {
-        if (queue) {
-            const int slot = base + atomicAdd(queue, 1);
-            if (slot >= B) return -1;
-            return perm ? perm[slot] : slot;
-        }
-        const int b = fixed;
-        fixed = -1;
-        return b;
-    }
-};
-
-// The brush state machine of one lane (the body of expand_kernel), as ONE flat loop: an iteration either runs one
-// update_states_and_setting_values call of the lane's current canvas, or -- when that canvas's step is over -- writes
-// its state back and sets up the next canvas from the feed, so lanes at different canvases reconverge every iteration.
-// STREAM: the fused small-batch step (step_small_kernel) runs this in one thread while a second warp of the CTA
-// composites the dabs as they appear; prog = {dabs published, done, colour index, started} in shared memory.
+// One canvas's env step of the brush state machine (the body of expand_kernel).  STREAM: the fused small-batch step
+// (step_small_kernel) runs this in one thread while a second warp of the CTA composites the dabs as they appear;
+// prog = {dabs published, done, colour index, started} in shared memory.
 template <bool STREAM>
-__device__ __forceinline__ void expand_run(const EnvParams &P, CanvasFeed feed, const int32_t *__restrict__ actions,
+__device__ __forceinline__ void expand_one(const EnvParams &P, const int b, const int32_t *__restrict__ actions,
                                            float *__restrict__ brush_state, double *__restrict__ env_state,
                                            float *__restrict__ dabs, int32_t *__restrict__ dab_count,
                                            int32_t *__restrict__ status, const float *__restrict__ gauss_tab,
                                            volatile int *prog)
 {
-    const int cursor_max = P.rng_table_len - 16;
-    const int L = P.L;
-    int b = -1;
-    float *bs = nullptr;
-    double *es = nullptr;
-    float *my_dabs = nullptr;
+    float *bs = brush_state + (size_t)b * kBrushFloats;
+    double *es = env_state + (size_t)b * kEnvDoubles;
     Brush S;
+    S.X = bs[BS_X]; S.Y = bs[BS_Y]; S.P = bs[BS_PRESSURE]; S.partial = bs[BS_PARTIAL_DABS];
+    S.AR = bs[BS_ACTUAL_RADIUS]; S.AX = bs[BS_ACTUAL_X]; S.AY = bs[BS_ACTUAL_Y];
+    S.s1 = bs[BS_SPEED1_SLOW]; S.s2 = bs[BS_SPEED2_SLOW];
+    S.flags = __float_as_int(bs[BS_FLAGS]);
+    const int step = __float_as_int(bs[BS_STEP]);
+    int cursor = __float_as_int(bs[BS_RNG_POS]);
+    const int cursor_max = P.rng_table_len - 16;
+    S.v_opaque = S.v_opaque_mul = S.v_rlog = S.v_hard = S.v_rbr = S.v_obr = S.v_aa = 0.0f;
+
+    // ---- action decode (mnist.py:107-135) ----
+    const int32_t *ac = actions + (size_t)b * P.K;
     StepSetup st;
-    int step = 0, cursor = 0, color_idx = 0, n_dabs = 0, err = 0;
-    float base_radius = 0, rlog_base = 0;
-    double pressure = 0, s_x = 0, s_y = 0, cur_pressure_var = 0;
+    const int L = P.L;
+    st.x = P.lin[0]; st.y = P.lin[0]; st.c_x = P.lin[0]; st.c_y = P.lin[0];
+    double pressure = P.default_pressure;
+    st.jump = 0;
+    int size_idx = 8;
+    int color_idx = 0;
+    if (P.idx_end >= 0) { const int a = ac[P.idx_end]; st.x = P.lin[a % L]; st.y = P.lin[a / L]; }
+    if (P.idx_control >= 0) { const int a = ac[P.idx_control]; st.c_x = P.lin[a % L]; st.c_y = P.lin[a / L]; }
+    if (P.idx_pressure >= 0) pressure = P.pressures[ac[P.idx_pressure]];
+    if (P.idx_size >= 0) size_idx = ac[P.idx_size];
+    if (P.idx_jump >= 0) st.jump = ac[P.idx_jump];
+    if (P.idx_color >= 0) color_idx = ac[P.idx_color];
+    else if (P.colorize) color_idx = step % P.n_colors;
+    const float base_radius = P.base_radius[size_idx];     // expf(base radius_logarithmic), unclamped
+    const float rlog_base = P.base_rlog[size_idx];         // base value of radius_logarithmic this step
+
+    // ---- pre-positioning event and stroke geometry (mnist.py:137-160) ----
+    const bool have_start = es[ES_HAVE_START] != 0.0;
+    double s_x = es[ES_SX], s_y = es[ES_SY];
+    const double entry_pressure = es[ES_ENTRY_PRESSURE];
+    if (!have_start) { pressure = 0; s_x = 0; s_y = 0; }
+    else if (P.idx_jump >= 0 && st.jump) pressure = 0;
+    st.curved = !(P.idx_control < 0 || pressure == 0);
+    st.sx = s_x; st.sy = s_y;
+    double cur_pressure_var = pressure;     // the `pressure` variable inside curve()
+    if (st.curved) {
+        // _line_settings (mnist.py:270-278)
+        double p1 = entry_pressure;
+        const double p2 = (entry_pressure + pressure) / 2;
+        const double p3 = pressure;
+        if (P.head == 0.0001) p1 = p2;
+        st.prange1 = p2 - p1;
+        st.prange2 = p3 - p2;
+        st.entry_p = p1;
+        st.midpoint_p = p2;
+        const double mx = (s_x + st.x) / 2.0, my = (s_y + st.y) / 2.0;
+        double dx = st.c_x - mx, dy = st.c_y - my;
+        double length = sqrt(dx * dx + dy * dy);
+        double nx, ny;
+        if (length == 0.0) { nx = 0.0; ny = 0.0; } else { nx = dx / length; ny = dy / length; }
+        const double l2x = length * 2;
+        st.cx = mx + nx * l2x;
+        st.cy = my + ny * l2x;
+        st.x1 = st.cx - s_x; st.y1 = st.cy - s_y;
+        st.x2 = st.x - st.cx; st.y2 = st.y - st.cy;
+        st.head = 100 * P.head;
+        st.head_range = (int)st.head + 1;
+        st.tail = 100 * P.tail;
+        st.tail_range = (int)st.tail + 1;
+        st.tail_length = 100 - st.tail;
+        double px, py;
+        curve_point(st, 1, px, py);
+        dx = px - s_x; dy = py - s_y;
+        length = sqrt(dx * dx + dy * dy);
+        if (length == 0.0) { nx = 0.0; ny = 0.0; } else { nx = dx / length; ny = dy / length; }
+        st.bx = s_x + nx * 0.25;
+        st.by = s_y + ny * 0.25;
+        st.n_events = 102;
+    } else {
+        st.n_events = 2;
+    }
+
+    if (STREAM) {                                        // the consumer needs the colour before the first dab
+        prog[2] = color_idx;
+        __threadfence_block();
+        prog[3] = 1;
+    }
+    float *my_dabs = dabs + (size_t)b * P.max_dabs * kDabFloats;
+    int n_dabs = 0;
+    int err = 0;
+
     // ---- event cursor ----
     int ev = 0;
     int split = 0;                 // stroke_to's "pressure after zero pressure" recursion
@@ -284,7 +336,6 @@ __device__ __forceinline__ void expand_run(const EnvParams &P, CanvasFeed feed, 
     float tx = 0, ty = 0, tp = 0;  // target after slow tracking
     double dtime_left = 0;
     float dabs_moved = 0, dabs_todo = 0;
-    bool live = false;
 
     // begin event `ev` (mypaint_brush_stroke_to up to the dab loop); false when the step is over
     auto begin_event = [&]() -> bool {
@@ -342,119 +393,11 @@ __device__ __forceinline__ void expand_run(const EnvParams &P, CanvasFeed feed, 
         }
     };
 
-    for (;;) {
-        if (!live) {
-            if (b >= 0) {
-                // ---- write back ----
-                bs[BS_X] = S.X; bs[BS_Y] = S.Y; bs[BS_PRESSURE] = S.P; bs[BS_PARTIAL_DABS] = S.partial;
-                bs[BS_ACTUAL_RADIUS] = S.AR; bs[BS_ACTUAL_X] = S.AX; bs[BS_ACTUAL_Y] = S.AY;
-                bs[BS_SPEED1_SLOW] = S.s1; bs[BS_SPEED2_SLOW] = S.s2;
-                bs[BS_FLAGS] = __int_as_float(S.flags);
-                bs[BS_STEP] = __int_as_float(step + 1);
-                bs[BS_RNG_POS] = __int_as_float(cursor);
-                es[ES_SX] = st.x;
-                es[ES_SY] = st.y;
-                es[ES_ENTRY_PRESSURE] = st.curved ? cur_pressure_var : pressure;
-                es[ES_HAVE_START] = 1.0;
-                dab_count[2 * b] = n_dabs;
-                dab_count[2 * b + 1] = color_idx;
-                if (cursor > cursor_max) err |= 2;
-                if (err) atomicOr(status, err);
-                err = 0;
-                if (STREAM) {
-                    __threadfence_block();
-                    prog[1] = 1;                                     // done: prog[0] is final
-                }
-            }
-            b = feed.next();
-            if (b < 0) break;
-            bs = brush_state + (size_t)b * kBrushFloats;
-            es = env_state + (size_t)b * kEnvDoubles;
-            S.X = bs[BS_X]; S.Y = bs[BS_Y]; S.P = bs[BS_PRESSURE]; S.partial = bs[BS_PARTIAL_DABS];
-            S.AR = bs[BS_ACTUAL_RADIUS]; S.AX = bs[BS_ACTUAL_X]; S.AY = bs[BS_ACTUAL_Y];
-            S.s1 = bs[BS_SPEED1_SLOW]; S.s2 = bs[BS_SPEED2_SLOW];
-            S.flags = __float_as_int(bs[BS_FLAGS]);
-            step = __float_as_int(bs[BS_STEP]);
-            cursor = __float_as_int(bs[BS_RNG_POS]);
-            S.v_opaque = S.v_opaque_mul = S.v_rlog = S.v_hard = S.v_rbr = S.v_obr = S.v_aa = 0.0f;
+    bool live = begin_event();
+    if (live) dabs_todo = count_dabs_to(P, S, base_radius, tx, ty, (float)dtime_left);
 
-            // ---- action decode (mnist.py:107-135) ----
-            const int32_t *ac = actions + (size_t)b * P.K;
-            st.x = P.lin[0]; st.y = P.lin[0]; st.c_x = P.lin[0]; st.c_y = P.lin[0];
-            pressure = P.default_pressure;
-            st.jump = 0;
-            int size_idx = 8;
-            color_idx = 0;
-            if (P.idx_end >= 0) { const int a = ac[P.idx_end]; st.x = P.lin[a % L]; st.y = P.lin[a / L]; }
-            if (P.idx_control >= 0) { const int a = ac[P.idx_control]; st.c_x = P.lin[a % L]; st.c_y = P.lin[a / L]; }
-            if (P.idx_pressure >= 0) pressure = P.pressures[ac[P.idx_pressure]];
-            if (P.idx_size >= 0) size_idx = ac[P.idx_size];
-            if (P.idx_jump >= 0) st.jump = ac[P.idx_jump];
-            if (P.idx_color >= 0) color_idx = ac[P.idx_color];
-            else if (P.colorize) color_idx = step % P.n_colors;
-            base_radius = P.base_radius[size_idx];     // expf(base radius_logarithmic), unclamped
-            rlog_base = P.base_rlog[size_idx];         // base value of radius_logarithmic this step
-
-            // ---- pre-positioning event and stroke geometry (mnist.py:137-160) ----
-            const bool have_start = es[ES_HAVE_START] != 0.0;
-            s_x = es[ES_SX]; s_y = es[ES_SY];
-            const double entry_pressure = es[ES_ENTRY_PRESSURE];
-            if (!have_start) { pressure = 0; s_x = 0; s_y = 0; }
-            else if (P.idx_jump >= 0 && st.jump) pressure = 0;
-            st.curved = !(P.idx_control < 0 || pressure == 0);
-            st.sx = s_x; st.sy = s_y;
-            cur_pressure_var = pressure;     // the `pressure` variable inside curve()
-            if (st.curved) {
-                // _line_settings (mnist.py:270-278)
-                double p1 = entry_pressure;
-                const double p2 = (entry_pressure + pressure) / 2;
-                const double p3 = pressure;
-                if (P.head == 0.0001) p1 = p2;
-                st.prange1 = p2 - p1;
-                st.prange2 = p3 - p2;
-                st.entry_p = p1;
-                st.midpoint_p = p2;
-                const double mx = (s_x + st.x) / 2.0, my = (s_y + st.y) / 2.0;
-                double dx = st.c_x - mx, dy = st.c_y - my;
-                double length = sqrt(dx * dx + dy * dy);
-                double nx, ny;
-                if (length == 0.0) { nx = 0.0; ny = 0.0; } else { nx = dx / length; ny = dy / length; }
-                const double l2x = length * 2;
-                st.cx = mx + nx * l2x;
-                st.cy = my + ny * l2x;
-                st.x1 = st.cx - s_x; st.y1 = st.cy - s_y;
-                st.x2 = st.x - st.cx; st.y2 = st.y - st.cy;
-                st.head = 100 * P.head;
-                st.head_range = (int)st.head + 1;
-                st.tail = 100 * P.tail;
-                st.tail_range = (int)st.tail + 1;
-                st.tail_length = 100 - st.tail;
-                double px, py;
-                curve_point(st, 1, px, py);
-                dx = px - s_x; dy = py - s_y;
-                length = sqrt(dx * dx + dy * dy);
-                if (length == 0.0) { nx = 0.0; ny = 0.0; } else { nx = dx / length; ny = dy / length; }
-                st.bx = s_x + nx * 0.25;
-                st.by = s_y + ny * 0.25;
-                st.n_events = 102;
-            } else {
-                st.n_events = 2;
-            }
-
-            if (STREAM) {                                        // the consumer needs the colour before the first dab
-                prog[2] = color_idx;
-                __threadfence_block();
-                prog[3] = 1;
-            }
-            my_dabs = dabs + (size_t)b * P.max_dabs * kDabFloats;
-            n_dabs = 0;
-            ev = 0; split = 0;
-
-            live = begin_event();
-            if (live) dabs_todo = count_dabs_to(P, S, base_radius, tx, ty, (float)dtime_left);
-            continue;
-        }
-        // ---- one update_states_and_setting_values per iteration (dab, or end of event) ----
+    // ---- one update_states_and_setting_values per iteration (dab, or end of event) ----
+    while (live) {
         // gaussians this iteration may need (independent of the state chain: issue the loads early)
         const int c0 = min(cursor, cursor_max);
         const float g1 = __ldg(gauss_tab + c0 + 1), g5 = __ldg(gauss_tab + c0 + 5), g9 = __ldg(gauss_tab + c0 + 9);
@@ -532,14 +475,33 @@ __device__ __forceinline__ void expand_run(const EnvParams &P, CanvasFeed feed, 
         }
         if (live) dabs_todo = count_dabs_to(P, S, base_radius, tx, ty, (float)dtime_left);
     }
+    if (cursor > cursor_max) err |= 2;
+
+    // ---- write back ----
+    bs[BS_X] = S.X; bs[BS_Y] = S.Y; bs[BS_PRESSURE] = S.P; bs[BS_PARTIAL_DABS] = S.partial;
+    bs[BS_ACTUAL_RADIUS] = S.AR; bs[BS_ACTUAL_X] = S.AX; bs[BS_ACTUAL_Y] = S.AY;
+    bs[BS_SPEED1_SLOW] = S.s1; bs[BS_SPEED2_SLOW] = S.s2;
+    bs[BS_FLAGS] = __int_as_float(S.flags);
+    bs[BS_STEP] = __int_as_float(step + 1);
+    bs[BS_RNG_POS] = __int_as_float(cursor);
+    es[ES_SX] = st.x;
+    es[ES_SY] = st.y;
+    es[ES_ENTRY_PRESSURE] = st.curved ? cur_pressure_var : pressure;
+    es[ES_HAVE_START] = 1.0;
+    dab_count[2 * b] = n_dabs;
+    dab_count[2 * b + 1] = color_idx;
+    if (err) atomicOr(status, err);
+    if (STREAM) {
+        __threadfence_block();
+        prog[1] = 1;                                     // done: prog[0] is final
+    }
 }
 
 __global__ void __launch_bounds__(kExpandThreads, EXPAND_MIN_BLOCKS)
 expand_kernel(const __grid_constant__ EnvParams P, const int32_t *__restrict__ actions,
               float *__restrict__ brush_state, double *__restrict__ env_state,
               float *__restrict__ dabs, int32_t *__restrict__ dab_count, int32_t *__restrict__ status,
-              const float *__restrict__ gauss_tab, int lanes, const int32_t *__restrict__ perm, int n_solo,
-              int32_t *__restrict__ queue)
+              const float *__restrict__ gauss_tab, int lanes, const int32_t *__restrict__ perm, int n_solo)
 {
     // `lanes` canvases per warp (1..32, host-chosen): the brush state machine is a latency-bound
     // serial chain, so with few canvases it pays to give each its own warp (no intra-warp divergence
@@ -547,25 +509,21 @@ expand_kernel(const __grid_constant__ EnvParams P, const int32_t *__restrict__ a
     const int tid = threadIdx.x;
     // slots are in order of decreasing predicted chain length (perm): the first n_solo canvases -- the ones
     // that decide the kernel's duration -- get a warp each (no divergence against shorter neighbours, lowest
-    // per-iteration latency); the rest are packed `lanes` per warp, either statically next to canvases of
-    // similar length or (queue != nullptr) pulled lane by lane from the sorted queue by persistent warps
-    CanvasFeed feed;
-    feed.fixed = -1; feed.queue = nullptr; feed.perm = perm; feed.base = n_solo; feed.B = P.B;
+    // per-iteration latency), the rest are packed `lanes` per warp next to canvases of similar length
+    int slot;
     if ((int)blockIdx.x < n_solo) {
         if (tid != 0) return;
-        feed.fixed = perm ? perm[blockIdx.x] : (int)blockIdx.x;
-    } else if (queue) {
-        if (tid >= lanes) return;
-        feed.queue = queue;
+        slot = blockIdx.x;
     } else {
         if (tid >= lanes) return;
-        const int slot = n_solo + ((int)blockIdx.x - n_solo) * lanes + tid;
-        if (slot >= P.B) return;
-        // canvases sorted by predicted chain length (plan_kernel / scatter_kernel): the lanes of a warp walk
-        // chains of similar length instead of idling behind the longest one
-        feed.fixed = perm ? perm[slot] : slot;
+        slot = n_solo + ((int)blockIdx.x - n_solo) * lanes + tid;
     }
-    expand_run<false>(P, feed, actions, brush_state, env_state, dabs, dab_count, status, gauss_tab, nullptr);
+    if (slot >= P.B) return;
+    // canvases sorted by predicted chain length (plan_kernel / scatter_kernel): the lanes of a warp walk
+    // chains of similar length instead of idling behind the longest one
+    const int b = perm ? perm[slot] : slot;
+
+    expand_one<false>(P, b, actions, brush_state, env_state, dabs, dab_count, status, gauss_tab, nullptr);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1200,9 +1158,7 @@ step_small_kernel(const __grid_constant__ EnvParams P, const int32_t *__restrict
     if (threadIdx.x < 4) s_prog[threadIdx.x] = 0;
     __syncthreads();
     if (threadIdx.x == 0) {
-        CanvasFeed feed;
-        feed.fixed = b; feed.queue = nullptr; feed.perm = nullptr; feed.base = 0; feed.B = P.B;
-        expand_run<true>(P, feed, actions, brush_state, env_state, dabs, dab_count, status, gauss_tab, s_prog);
+        expand_one<true>(P, b, actions, brush_state, env_state, dabs, dab_count, status, gauss_tab, s_prog);
     } else if (threadIdx.x >= 32) {
         composite_one<C, false, true>(P, b, canvas, dabs, dab_count, dither, obs, s_dab, s_pair, s_opa, s_off, nullptr,
                                       threadIdx.x & 31, s_prog);
@@ -1325,17 +1281,10 @@ cudaError_t launch_expand(const EnvParams &P, const int32_t *actions, float *bs,
         // measured (B200): 128 solo warps at B = 16384, 256 at B = 65536; more of them exceed the 16 resident
         // 128-register warps per SM and push the packed warps into a second wave
         n_solo = P.B / P.expand_solo_div;
-        if (n_solo > P.expand_solo_max) n_solo = P.expand_solo_max;
+        if (n_solo > 256) n_solo = 256;
     }
-    int blocks = n_solo + (P.B - n_solo + lanes - 1) / lanes;
-    int32_t *queue = nullptr;
-    if (perm && P.expand_wps > 0 && blocks > n_solo + 148 * P.expand_wps) {
-        // persistent lanes: fewer warps than canvases / lanes, each lane pulls its next canvas from the sorted queue
-        blocks = n_solo + 148 * P.expand_wps;
-        queue = plan_scratch - 63;               // d_plan[1] (d_plan[0] is composite_kernel's work counter)
-        cudaMemsetAsync(queue, 0, sizeof(int32_t), st);
-    }
-    expand_kernel<<<blocks, kExpandThreads, 0, st>>>(P, actions, bs, es, dabs, dab_count, status, gauss_tab, lanes, perm, n_solo, queue);
+    const int blocks = n_solo + (P.B - n_solo + lanes - 1) / lanes;
+    expand_kernel<<<blocks, kExpandThreads, 0, st>>>(P, actions, bs, es, dabs, dab_count, status, gauss_tab, lanes, perm, n_solo);
     return cudaGetLastError();
 }
 cudaError_t launch_composite(const EnvParams &P, uint16_t *canvas, const float *dabs,

@@ -50,8 +50,6 @@ struct EnvParams {
     int expand_lanes;            // canvases per warp in expand_kernel (0 = choose from the batch size)
     int expand_sort;             // 1: sort canvases by predicted chain length before expansion
     int expand_solo_div;         // the B / expand_solo_div longest canvases get a warp each
-    int expand_solo_max;         // cap of the number of solo warps (256: all expansion warps stay in one wave at B = 65536)
-    int expand_wps;              // > 0: at most this many expansion warps per SM, lanes pull canvases from the sorted queue
     double lin[64];
     double pressures[8];
     double sizes[8];

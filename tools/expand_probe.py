@@ -1,7 +1,7 @@
 """Times a 20-step episode of spiral_env_expand / spiral_env_composite at large batches (B200); the tuning knobs are
-the library's environment variables (SPIRAL_EXPAND_WPS, SPIRAL_EXPAND_LANES, SPIRAL_EXPAND_SOLO_DIV, ...).
+the library's environment variables (SPIRAL_EXPAND_LANES, SPIRAL_EXPAND_SORT, SPIRAL_EXPAND_SOLO_DIV).
 
-    SPIRAL_EXPAND_WPS=8 python tools/expand_probe.py 16384 65536
+    SPIRAL_EXPAND_SOLO_DIV=64 python tools/expand_probe.py 16384 65536
 """
 import hashlib
 import os
