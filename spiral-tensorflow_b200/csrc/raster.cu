@@ -235,6 +235,7 @@ __device__ __forceinline__ void curve_point(const StepSetup &st, int i, double &
 // One canvas's env step of the brush state machine (the body of expand_kernel).  STREAM: the fused small-batch step
 // (step_small_kernel) runs this in one thread while a second warp of the CTA composites the dabs as they appear;
 // prog = {dabs published, done, colour index, started} in shared memory.
+constexpr int kPublishEvery = 8;        // STREAM: dabs between two publications of the count (power of two)
 template <bool STREAM>
 __device__ __forceinline__ void expand_one(const EnvParams &P, const int b, const int32_t *__restrict__ actions,
                                            float *__restrict__ brush_state, double *__restrict__ env_state,
@@ -458,7 +459,10 @@ __device__ __forceinline__ void expand_one(const EnvParams &P, const int b, cons
                         d[0] = make_float4(x, y, rl, S.AR);
                         d[1] = make_float4(opq, S.v_hard, S.v_aa, has_rand ? 1.0f : 0.0f);
                         n_dabs++;
-                        if (STREAM) {                    // publish the dab to the compositing warp of this CTA
+                        if (STREAM && (n_dabs & (kPublishEvery - 1)) == 0) {
+                            // publish to the compositing warp of this CTA -- every 8th dab only: the fence waits for the
+                            // dab stores above, ~150 cycles on a chain of ~1,000 per iteration, and the consumer works
+                            // in rounds of 32 anyway
                             __threadfence_block();
                             prog[0] = n_dabs;
                         }
@@ -492,6 +496,8 @@ __device__ __forceinline__ void expand_one(const EnvParams &P, const int b, cons
     dab_count[2 * b + 1] = color_idx;
     if (err) atomicOr(status, err);
     if (STREAM) {
+        __threadfence_block();
+        prog[0] = n_dabs;                                // the final count (dabs since the last publication included)
         __threadfence_block();
         prog[1] = 1;                                     // done: prog[0] is final
     }
@@ -1139,8 +1145,11 @@ composite_kernel(const __grid_constant__ EnvParams P, uint16_t *__restrict__ can
 // with the producer (it is ~4x faster per dab), so the step ends a round of dabs after the chain does.  Same device
 // functions as the two-kernel path: bit-identical canvases, dab lists and observations.
 // ------------------------------------------------------------------------------------------
-template <int C>
-__global__ void __launch_bounds__(64, 8)
+// SMT: the canvas's tile lives in shared memory for the step (32 KB, 5 CTAs per SM), as in composite_kernel<C, true>: alone
+// on its canvas the compositing warp is bound by the latency of the ordered blend's load -> blend -> store chain, which is
+// several times shorter from shared memory than through L1/L2, so it keeps up with the chain on the densest canvases.
+template <int C, bool SMT>
+__global__ void __launch_bounds__(64, SMT ? 5 : 8)
 step_small_kernel(const __grid_constant__ EnvParams P, const int32_t *__restrict__ actions,
                   float *__restrict__ brush_state, double *__restrict__ env_state, float *__restrict__ dabs,
                   int32_t *__restrict__ dab_count, int32_t *__restrict__ status, const float *__restrict__ gauss_tab,
@@ -1152,6 +1161,7 @@ step_small_kernel(const __grid_constant__ EnvParams P, const int32_t *__restrict
     __shared__ uint16_t s_opa[kDense];
     __shared__ int s_off[33];
     __shared__ int s_prog[4];              // dabs published, done, colour index, started
+    extern __shared__ __align__(16) uint8_t s_fused_tile[];   // SMT: [64*64] RGBA u16x4
     // more than one wave of CTAs: canvases in order of decreasing predicted chain length (plan_kernel / scatter_kernel),
     // so the longest chains start first and the short ones fill the slots they leave (the mean chain is ~1/5 of the longest)
     const int b = perm ? perm[blockIdx.x] : blockIdx.x;
@@ -1160,8 +1170,8 @@ step_small_kernel(const __grid_constant__ EnvParams P, const int32_t *__restrict
     if (threadIdx.x == 0) {
         expand_one<true>(P, b, actions, brush_state, env_state, dabs, dab_count, status, gauss_tab, s_prog);
     } else if (threadIdx.x >= 32) {
-        composite_one<C, false, true>(P, b, canvas, dabs, dab_count, dither, obs, s_dab, s_pair, s_opa, s_off, nullptr,
-                                      threadIdx.x & 31, s_prog);
+        composite_one<C, SMT, true>(P, b, canvas, dabs, dab_count, dither, obs, s_dab, s_pair, s_opa, s_off,
+                                    SMT ? reinterpret_cast<uint2 *>(s_fused_tile) : nullptr, threadIdx.x & 31, s_prog);
     }
 }
 
@@ -1322,7 +1332,8 @@ cudaError_t launch_composite(const EnvParams &P, uint16_t *canvas, const float *
     return cudaGetLastError();
 }
 // fused small-batch step (SPIRAL_FUSED_STEP_MAX: largest batch that uses it; 0 = never)
-constexpr int kFusedWave = 148 * 8;        // CTAs of step_small_kernel resident at once
+constexpr int kFusedWave = 148 * 8;        // CTAs of step_small_kernel resident at once (registers)
+constexpr int kFusedWaveSmt = 148 * 5;     // with the 32 KB tile in shared memory (37.5 KB per CTA)
 bool fused_step_applies(const EnvParams &P)
 {
     int mx = FUSED_STEP_MAX_DEFAULT;
@@ -1333,8 +1344,11 @@ cudaError_t launch_step_small(const EnvParams &P, const int32_t *actions, float 
                               int32_t *dab_count, int32_t *status, const float *gauss_tab, uint16_t *canvas,
                               const uint16_t *dither, float *obs, int32_t *plan_scratch, cudaStream_t st)
 {
+    // tile in shared memory while two waves of 5 CTAs per SM hold the batch (SPIRAL_FUSED_SMEM=0: always in place)
+    bool smt = P.B <= 2 * kFusedWaveSmt;
+    if (const char *e = getenv("SPIRAL_FUSED_SMEM")) smt = smt && atoi(e) != 0;
     const int32_t *perm = nullptr;
-    if (P.B > kFusedWave && plan_scratch) {
+    if (P.B > (smt ? kFusedWaveSmt : kFusedWave) && plan_scratch) {
         // plan_scratch: i32 [512] histogram + cursors | i32 [B] permutation | u8 [B] keys  (as in launch_expand)
         int32_t *hist = plan_scratch;
         int32_t *pm = plan_scratch + 2 * kPlanBuckets;
@@ -1345,10 +1359,23 @@ cudaError_t launch_step_small(const EnvParams &P, const int32_t *actions, float 
         scatter_kernel<<<pb, 256, 0, st>>>(P.B, key, hist, pm);
         perm = pm;
     }
-    if (P.C == 1)
-        step_small_kernel<1><<<P.B, 64, 0, st>>>(P, actions, bs, es, dabs, dab_count, status, gauss_tab, canvas, dither, obs, perm);
-    else
-        step_small_kernel<3><<<P.B, 64, 0, st>>>(P, actions, bs, es, dabs, dab_count, status, gauss_tab, canvas, dither, obs, perm);
+    constexpr int kTileBytes = kTile * kTile * 8;
+    if (smt) {
+        static bool attr = false;
+        if (!attr) {
+            cudaFuncSetAttribute(step_small_kernel<1, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            cudaFuncSetAttribute(step_small_kernel<3, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            attr = true;
+        }
+        if (P.C == 1)
+            step_small_kernel<1, true><<<P.B, 64, kTileBytes, st>>>(P, actions, bs, es, dabs, dab_count, status, gauss_tab, canvas, dither, obs, perm);
+        else
+            step_small_kernel<3, true><<<P.B, 64, kTileBytes, st>>>(P, actions, bs, es, dabs, dab_count, status, gauss_tab, canvas, dither, obs, perm);
+    } else if (P.C == 1) {
+        step_small_kernel<1, false><<<P.B, 64, 0, st>>>(P, actions, bs, es, dabs, dab_count, status, gauss_tab, canvas, dither, obs, perm);
+    } else {
+        step_small_kernel<3, false><<<P.B, 64, 0, st>>>(P, actions, bs, es, dabs, dab_count, status, gauss_tab, canvas, dither, obs, perm);
+    }
     return cudaGetLastError();
 }
 cudaError_t launch_debug_dabs(const EnvParams &P, const float *dabs, const int32_t *dab_count,

@@ -168,7 +168,7 @@ def test_graph_captured_learner_step_matches_eager_steps(native):
 
     def make(graphs):
         args = make_args("simple_mnist", L=32, C=1, T=3, conditional=True,
-                         extra=["--cuda_graphs", str(graphs), "--policy_act_native", str(native), "--policy_lr", "1e-3"])
+                         extra=["--cuda_graphs", str(graphs), "--policy_act_native", str(native), "--policy_lr", "1e-4"])
         env = sp.create_env(args, num_envs=8)
         torch.manual_seed(0)
         return agent_mod.Agent(args, env)
@@ -184,10 +184,12 @@ def test_graph_captured_learner_step_matches_eager_steps(native):
     for i, ro in enumerate(rollouts):
         m_g = a_graph.train_policy({k: v.clone() for k, v in ro.items()})
         m_e = a_eager.train_policy({k: v.clone() for k, v in ro.items()})
-        # cuDNN may pick other algorithms under capture and Adam turns last-bit gradient differences of near-zero
-        # gradients into lr-sized steps, so the two trajectories agree closely, not bitwise
+        # cuDNN may pick other algorithms under capture (and its backward kernels use atomics), and Adam turns last-bit
+        # differences of near-zero gradients into lr-sized steps, so the two trajectories agree closely, not bitwise;
+        # the step size is kept small enough (1e-4; 1e-3 let the two runs drift apart by the fifth step on some boxes)
+        # that this noise is not amplified by the loss surface
         assert torch.allclose(m_g["model/total_loss"], m_e["model/total_loss"], rtol=5e-3), i
-        assert torch.allclose(m_g["model/grad_global_norm"], m_e["model/grad_global_norm"], rtol=1e-1), i
+        assert torch.allclose(m_g["model/grad_global_norm"], m_e["model/grad_global_norm"], rtol=2e-1), i
     assert a_graph._tp_graph is not None and not a_graph._tp_failed           # steps 3-5 were graph replays
     assert a_graph.policy_opt.t == a_eager.policy_opt.t == 5
     moved = sum(float((p.detach() - s0).pow(2).sum()) for p, s0 in zip(a_graph.policy.parameters(), start)) ** 0.5
