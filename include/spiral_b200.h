@@ -123,7 +123,8 @@ int spiral_env_reset(SpiralEnv *env, uint16_t *canvas_dev, float *brush_state_de
  * rng_table_len (result then invalid).
  * Batches of at most two waves of CTAs (2 x 148 SMs x 8 = 2368 canvases; SPIRAL_FUSED_STEP_MAX overrides, 0 = never)
  * run as ONE kernel in which a second warp composites a canvas's dabs while its brush chain is still producing them;
- * larger batches run spiral_env_expand then spiral_env_composite.  Results are bit-identical either way. */
+ * larger batches run spiral_env_expand then spiral_env_composite.  Results are bit-identical either way.
+ * (SPIRAL_FUSED_SMEM=0: the fused kernel blends in place instead of keeping the tile in shared memory.) */
 int spiral_env_step(SpiralEnv *env, const int32_t *actions_dev, uint16_t *canvas_dev,
                     float *brush_state_dev, double *env_state_dev, float *dab_scratch_dev,
                     int32_t *dab_count_dev, float *obs_dev, int32_t *status_dev, void *stream);
