@@ -38,8 +38,8 @@ sys.path.insert(0, ROOT)
 
 # BASELINE.json configs[3] gives the shape (64x64 RGB, L=64, T=20, colour head); configs[4] ("rendering+reward
 # throughput sweep: 4096-65536 canvases x 20 strokes at 1/2/4/8 GPUs") gives the batch the throughput metric is
-# quoted on.  Default: 16384 canvases per GPU (weak scaling); the 1024-canvas point of configs[3] is reported in
-# the same JSON line under "rgb64_b1024".
+# quoted on.  Default: 65536 canvases per GPU (weak scaling); the 16384-canvas sweep point and the 1024-canvas point of
+# configs[3] are reported in the same JSON line under "rgb64_b16384" / "rgb64_b1024".
 WORKLOAD = dict(workload="rgb64-sweep (configs[3] shape at configs[4]'s largest single-GPU batch)", env="color_mnist",
                 color_channel=3, location_size=64, episode_length=20, canvases_per_gpu=65536, disc_dim=64)
 # DRAM bytes per canvas-step of composite_kernel from the ncu --set full capture in profiles/ (B=16384:

@@ -60,10 +60,10 @@ constexpr int kRowThreads = 128;
 #endif
 constexpr int kGradUnroll = A2C_UNROLL;
 // e^x for x <= 0 via ex2.approx: relative error ~1e-6 at |x| = 20, far inside the 2e-5 the parity tests hold.
-// Three sweeps through L1 with this exponential reach 85 % (B = 16384) / 70 % (B = 65536) of the measured HBM
-// peak; holding the row in registers (80 registers, 24 warps per SM) and a persistent bulk-async (cp.async.bulk +
-// mbarrier) double-buffered variant were both slower on B200 (25 and 44 ms vs 19 ms at B = 65536): the kernel
-// is bounded by instruction issue as much as by bandwidth, and occupancy wins.
+// Three sweeps (the re-reads come from L1 / L2) with this exponential reach 96 % (B = 16384) / 88 % (B = 65536) of the
+// measured HBM peak after the instruction-budget rewrite described at a2c_row_kernel; holding the row in registers
+// (80 registers, 24 warps per SM) and a persistent bulk-async (cp.async.bulk + mbarrier) double-buffered variant were
+// both slower on B200 (25 and 44 ms vs 19 ms at B = 65536 at the time): occupancy wins.
 __device__ __forceinline__ float fast_exp(float x)
 {
     float y;
