@@ -47,6 +47,46 @@ def test_a2c_loss_and_grads_match_oracle(sizes, B, T):
     assert _rel(res.dvf.cpu().numpy(), want["dvf"]) < 2e-5
 
 
+def test_a2c_full_size_properties():
+    """BASELINE sweep size (16,384 canvases x 20 steps, rgb64 heads: too big for the float64 oracle in seconds) through
+    the size-independent properties of agent.py:179-190: d total / d logits sums to zero over every row of every head,
+    a constant added to a row of logits changes nothing, and a slice of rows agrees with the oracle."""
+    sp = _sp()
+    from oracle import a2c_oracle as ao
+    from importlib import import_module
+    rl = import_module(sp.__name__ + ".rl_utils")
+    B, T, sizes = 16384, 20, [4096, 4096, 8, 2, 2, 2]
+    g = torch.Generator(device="cuda")
+    g.manual_seed(5)
+    logits = [torch.randn((B, T, n), generator=g, device="cuda") * 2 for n in sizes]
+    acts = torch.stack([torch.randint(0, n, (B, T), generator=g, device="cuda") for n in sizes], -1).to(torch.int32)
+    rewards = torch.zeros((B, T), device="cuda")
+    rewards[:, -1] = torch.rand((B,), generator=g, device="cuda")
+    values = torch.randn((B, T), generator=g, device="cuda")
+    vf = torch.randn((B, T), generator=g, device="cuda")
+    res = rl.a2c_loss(logits, acts, rewards, values, vf, 0.99, 1.0, 0.01)
+    scale = float(res.adv.abs().max()) + 1.0
+    for d in res.dlogits:
+        assert float(d.sum(-1).abs().max()) < 1e-4 * scale
+    scal = res.scalars.cpu().numpy().astype(np.float64)
+    dl = [d[:64].clone() for d in res.dlogits]
+    shift = torch.randn((B, T, 1), generator=g, device="cuda") * 5
+    res2 = rl.a2c_loss([l + shift for l in logits], acts, rewards, values, vf, 0.99, 1.0, 0.01)
+    scal2 = res2.scalars.cpu().numpy().astype(np.float64)
+    assert np.allclose(scal, scal2, rtol=2e-5)
+    for a, b in zip(dl, res2.dlogits):
+        assert float((a - b[:64]).abs().max()) < 2e-5 * scale
+    # oracle on the first 4 canvases: gradients of a row depend on that row only
+    n = 4
+    want_r, want_adv = ao.multiple_process_rollout(rewards[:n].cpu().numpy().astype(np.float64),
+                                                    values[:n].cpu().numpy().astype(np.float64), 0.99, 1.0)
+    assert _rel(res.adv[:n].cpu().numpy(), want_adv) < 2e-5
+    want = ao.a2c_loss([l[:n].cpu().numpy() for l in logits], acts[:n].cpu().numpy(), want_adv.astype(np.float32),
+                       want_r.astype(np.float32), vf[:n].cpu().numpy(), 0.01)
+    for k in range(len(sizes)):
+        assert _rel(res.dlogits[k][:n].cpu().numpy(), want["dlogits"][k]) < 2e-5
+
+
 def test_a2c_autograd_wrapper_backpropagates():
     sp = _sp()
     from importlib import import_module

@@ -38,6 +38,26 @@ def test_loss_identity_value_term_once_per_head():
     assert np.isclose(out["entropy"], B * T * np.log(8))
 
 
+def test_loss_gradient_rows_sum_to_zero_and_logit_shift_invariance():
+    """Size-independent properties of agent.py:179-190 (they hold for any batch, so they are the checks that scale):
+    softmax terms do not see a constant added to a row of logits, and d total / d logits sums to zero over every row:
+    adv (sum p - 1) + coeff sum p (logp + entropy) = 0."""
+    rng = np.random.RandomState(4)
+    B, T, sizes = 3, 4, [2, 8, 33, 1024]
+    logits = [rng.randn(B, T, n) * 3 for n in sizes]
+    acts = np.stack([rng.randint(n, size=(B, T)) for n in sizes], -1)
+    adv, r, vf = rng.randn(B, T), rng.randn(B, T), rng.randn(B, T)
+    out = ao.a2c_loss(logits, acts, adv, r, vf, 0.01)
+    for g in out["dlogits"]:
+        assert np.abs(np.asarray(g).sum(-1)).max() < 1e-12
+    shifted = [l + rng.randn(B, T, 1) * 10 for l in logits]
+    out2 = ao.a2c_loss(shifted, acts, adv, r, vf, 0.01)
+    for k in ("pi_loss", "vf_loss", "entropy", "total"):
+        assert np.isclose(out[k], out2[k], rtol=1e-12, atol=1e-10), k
+    for g, g2 in zip(out["dlogits"], out2["dlogits"]):
+        assert np.allclose(g, g2, rtol=0, atol=1e-12)
+
+
 def test_disc_shape_chain_and_same_padding():
     w = do.init_weights(1, disc_dim=8)
     assert [w["conv%d/kernel" % l].shape[-1] for l in range(6)] == [8, 16, 32, 64, 128, 256]
