@@ -1,7 +1,13 @@
 """``ReplayBuffer`` -- the reference's replay.py:8-37 as a device-resident uint8 ring of final
 canvases feeding the discriminator's "fake" batch.  Same semantics: pushes truncate
-float -> uint8, a full buffer shifts left by the batch size, sampling is uniform over the filled
-part."""
+float -> uint8; a push that does not fit shifts the buffer left by the batch size and writes the batch
+at the end WITHOUT moving ``idx`` (replay.py:24-27), so sampling stays uniform over ``[0, idx)`` --
+rows at or above ``idx`` are sampled only once later pushes have shifted them down (a quirk of the
+reference when the push size does not divide the buffer size; kept, not fixed).  Deviations: ``sample``
+raises on an empty buffer instead of spinning (replay.py:33-34 waits for the actor threads) and draws
+``n`` rows (the reference draws ``disc_batch_size`` whatever ``n`` is; every caller passes that value);
+a push larger than the buffer keeps its last ``buffer_size`` rows (the reference would fail to
+broadcast).  tests/test_cpu_host.py replays random push sequences against a literal numpy restatement."""
 import torch
 
 
@@ -23,7 +29,6 @@ class ReplayBuffer(object):
         if self.idx + n > self.buffer_size:
             self.data[:-n] = self.data[n:].clone()
             self.data[-n:] = batches
-            self.idx = self.buffer_size
         else:
             self.data[self.idx:self.idx + n] = batches
             self.idx += n

@@ -257,3 +257,39 @@ def test_params_json_roundtrip(tmp_path):
     changed = ck.load_args(b, str(tmp_path))
     assert b.env == "simple_mnist" and b.episode_length == 7 and b.disc_dim == 8
     assert "episode_length" in changed and "load_path" not in changed
+
+
+def test_replay_buffer_follows_the_reference_push_semantics():
+    """replay.py:8-37 restated literally in numpy (uint8 ring, `idx` only moves while a push fits) against the
+    device-resident ReplayBuffer on random push sequences: same contents, same `idx`, float -> uint8 truncation."""
+    import types
+    from importlib import import_module
+
+    import spiral_b200 as sp
+    rb = import_module(sp.__name__ + ".replay")
+    args = types.SimpleNamespace(buffer_batch_num=5, disc_batch_size=4, seed=3)
+    shape = [3, 2, 1]
+    buf = rb.ReplayBuffer(args, shape, device="cpu")
+    size = args.buffer_batch_num * args.disc_batch_size
+    data = np.zeros([size] + shape, np.uint8)
+    idx = 0
+    rng = np.random.RandomState(0)
+    for step in range(40):
+        n = int(rng.randint(1, 9))
+        batch = rng.uniform(0, 255.99, size=[n] + shape).astype(np.float32)
+        if idx + n > size:                       # replay.py:24-27
+            data[:-n] = data[n:]
+            data[-n:] = batch
+        else:                                    # replay.py:28-30
+            data[idx:idx + n] = batch
+            idx += n
+        buf.push(torch.from_numpy(batch))
+        assert buf.idx == idx, step
+        assert (buf.data.numpy() == data).all(), step
+    out = buf.sample(64)
+    assert out.dtype == torch.float32 and out.shape == (64, 3, 2, 1)
+    filled = {tuple(r.ravel()) for r in data[:idx].astype(np.float32)}
+    assert all(tuple(r.ravel()) in filled for r in out.numpy())          # uniform over [0, idx) only
+    empty = rb.ReplayBuffer(args, shape, device="cpu")
+    with pytest.raises(RuntimeError):
+        empty.sample(4)
