@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define SPIRAL_ABI_VERSION 2
+#define SPIRAL_ABI_VERSION 3
 
 #define SPIRAL_OK 0
 #define SPIRAL_EINVAL (-1)      /* bad argument / unsupported configuration */
@@ -104,7 +104,18 @@ typedef struct {
     double entry_pressure0;                       /* np.min(self.pressures), mnist.py:82 */
     SpiralBrush brush;
     uint16_t dither_table[SPIRAL_TILE * SPIRAL_TILE];
+    /* Arithmetic of the brush state machine (libmypaint's expf/logf/hypotf calls and the dab loop around them):
+     *   SPIRAL_MATH_DET  (1)  double-precision, correctly rounded replacements: canvases bit-identical to the CPU
+     *                         oracle's "det" mode, which agrees with glibc on >= 99 % of canvases
+     *   SPIRAL_MATH_FAST (2)  binary32 polynomials and a division-light dab loop (~4x shorter serial chain):
+     *                         bit-identical to the oracle's "fast" mode; against the libm-faithful mode every canvas
+     *                         stays within mean |err| <= 1e-3, and ~80 % (T = 20) within max |err| <= 1/255 -- the
+     *                         rest differ in the random jitter of single dabs (profiles/r2_raster_tolerance.json) */
+    int32_t math_mode;
 } SpiralEnvCfg;
+
+#define SPIRAL_MATH_DET 1
+#define SPIRAL_MATH_FAST 2
 
 typedef struct SpiralEnv SpiralEnv;
 
@@ -153,6 +164,13 @@ int spiral_l2_reward(const float *obs_dev, const float *target_dev, float *rewar
 /* deterministic math used by the expansion kernel (tests compare with the oracle's copy) */
 int spiral_debug_detmath(const double *x_dev, double *exp_out_dev, double *log_out_dev, int32_t n,
                          void *stream);
+/* the binary32 functions of SPIRAL_MATH_FAST (csrc/fastmath.cuh): exp(x), exp(-x), log(x) (0 where x <= 0) and
+ * hypot(x, x_rev) with x_rev[i] = x[n-1-i]; tests compare the bits with the oracle's copy */
+/* the dab loop's branch-free division (csrc/fastmath.cuh div_exact) against the IEEE division over n_pairs pseudo-random
+ * operand pairs; *mismatches_dev (u64, zeroed by the caller) receives the number of pairs whose quotients differ */
+int spiral_debug_divcheck(uint64_t seed, int64_t n_pairs, uint64_t *mismatches_dev, void *stream);
+int spiral_debug_fastmath(const float *x_dev, float *exp_out_dev, float *expneg_out_dev, float *log_out_dev,
+                          float *hypot_out_dev, int32_t n, void *stream);
 
 /* ------------------------------------------------------------------ */
 /* A2C loss (K3)                                                        */

@@ -28,6 +28,12 @@
  * Math modes:  PO_MATH_LIBM = glibc expf/exp/log/hypotf exactly where the C
  * sources call them (upstream-faithful); PO_MATH_DET = det_math.h replacements
  * (bit-reproducible on the GPU).  Everything else is identical.
+ * PO_MATH_FAST = the rasteriser's binary32 arithmetic mode: fast_math.h's
+ * polynomial expf/logf/hypotf AND a restructured dab loop (stroke_to_fast below:
+ * every operation in binary32, the loop's divisions hoisted or replaced by
+ * exp(-x)); it is NOT a restatement of libmypaint's arithmetic but of the CUDA
+ * kernel's, bit for bit, and tests/ measures its distance from the libm mode
+ * (north-star tolerance: max abs <= 1/255 per channel, mean <= 1e-3).
  *
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
  * --impl reference legs may load this library.
@@ -39,6 +45,7 @@
 #include <string.h>
 
 #include "det_math.h"
+#include "fast_math.h"
 #include "paint_oracle.h"
 
 /* ------------------------------------------------------------------ */
@@ -46,18 +53,22 @@
 /* ------------------------------------------------------------------ */
 static inline float m_expf(int mode, float x)
 {
+    if (mode == PO_MATH_FAST) return fast_expf(x);
     return mode == PO_MATH_DET ? (float)det_exp((double)x) : expf(x);
 }
 static inline double m_exp(int mode, double x)
 {
+    if (mode == PO_MATH_FAST) return (double)fast_expf((float)x);
     return mode == PO_MATH_DET ? det_exp(x) : exp(x);
 }
 static inline double m_log(int mode, double x)
 {
+    if (mode == PO_MATH_FAST) return (double)fast_logf((float)x);
     return mode == PO_MATH_DET ? det_log(x) : log(x);
 }
 static inline float m_hypotf(int mode, float a, float b)
 {
+    if (mode == PO_MATH_FAST) return fast_hypotf(a, b);
     return mode == PO_MATH_DET ? det_hypotf(a, b) : hypotf(a, b);
 }
 
@@ -545,6 +556,7 @@ struct POBrush {
     float speed_mapping_q[2];
     int reset_requested;
     long n_events;
+    float inv_actual_radius;      /* PO_MATH_FAST: exp(-radius_logarithmic), kept beside states[ST_ACTUAL_RADIUS] */
 };
 
 static const char *const setting_names[PO_SETTING_COUNT] = {
@@ -976,6 +988,175 @@ static float count_dabs_to(POBrush *self, float x, float y, float pressure, floa
     return res1 + res2 + res3;
 }
 
+/* ------------------------------------------------------------------ */
+/* PO_MATH_FAST: the CUDA kernel's binary32 dab loop (csrc/raster.cu expand_one_fast), restated.
+ * Same state machine as update_states_and_setting_values / count_dabs_to / the loop of
+ * mypaint_brush_stroke_to above; every operation is binary32 and the algebra is rearranged so that the
+ * serial chain per dab is short.  Differences from libmypaint's arithmetic (all at rounding level):
+ *   - dtime_left is a float; X += frac * (x - X) is one fmaf; the event's last update lands exactly on the
+ *     target (X = x instead of X += x - X)
+ *   - a stroke_to event moves linearly in time, so its normalised speed is a constant of the event:
+ *     norm_speed = dist0 * (1 / (dtime * base_radius)) with dist0 the distance measured when the event
+ *     starts (libmypaint re-derives it per dab as hypot(step_dx, step_dy) / step_dtime / base_radius, where
+ *     step_d{x,y} = frac * (x - X), step_dtime = frac * dtime_left and frac cancels); the remaining
+ *     distance follows dist *= 1 - frac instead of a hypot per dab
+ *   - dist / ACTUAL_RADIUS multiplies by exp(-radius_logarithmic)
+ *   - exp_decay(T, t) = fast_expf(t * (-1 / T));  speed inputs = fmaf(fast_logf(gamma + s), m, q)
+ *   - a mapping segment is evaluated as fmaf(slope, x, intercept), slope = (y1 - y0) / (x1 - x0),
+ *     intercept = y0 - slope * x0 (libmypaint: (y1 (x - x0) + y0 (x1 - x)) / (x1 - x0))
+ *   - dabs_todo = fmaf(dist, fmaf(1/AR, dabs_per_actual_radius, dabs_per_basic_radius / base_radius),
+ *                      dtime_left * dabs_per_second)
+ * Inputs no supported mapping reads (stroke, direction, tilt, custom) and the states behind them are
+ * not evolved; the RANDOM input is still drawn on every call (it moves the RNG stream).
+ * ------------------------------------------------------------------ */
+static float exp_decay_fast(float T_const, float t)
+{
+    if (T_const < 0.001f) return 0.0f;
+    return fast_expf(t * (-1.0f / T_const));
+}
+
+static float clamp_radius_f(float r)
+{
+    if (r < 0.2f) r = 0.2f;
+    if (r > 1000.0f) r = 1000.0f;
+    return r;
+}
+
+static float mapping_calculate_fast(const Mapping *self, const float *data)
+{
+    float result = self->base_value;
+    if (self->inputs_used == 0) return result;
+    for (int j = 0; j < PO_INPUT_COUNT; j++) {
+        const ControlPoints *p = &self->points[j];
+        if (p->n) {
+            const float x = data[j];
+            float x0 = p->xvalues[0], y0 = p->yvalues[0];
+            float x1 = p->xvalues[1], y1 = p->yvalues[1];
+            for (int i = 2; i < p->n && x > x1; i++) {
+                x0 = x1; y0 = y1;
+                x1 = p->xvalues[i]; y1 = p->yvalues[i];
+            }
+            float slope = 0.0f, icpt = y0;
+            if (!(x0 == x1 || y0 == y1)) {
+                slope = (y1 - y0) / (x1 - x0);
+                icpt = y0 - slope * x0;
+            }
+            result += fmaf(slope, x, icpt);
+        }
+    }
+    return result;
+}
+
+/* count_dabs_to with the distance handed in (measured at the start of the event, then dist *= 1 - frac) */
+static float count_dabs_fast(POBrush *self, float br_raw, float dist, float dtl)
+{
+    if (self->inv_actual_radius == 0.0f) {                      /* ACTUAL_RADIUS == 0: first event after the reset */
+        self->states[ST_ACTUAL_RADIUS] = clamp_radius_f(br_raw);
+        self->inv_actual_radius = 1.0f / self->states[ST_ACTUAL_RADIUS];
+    }
+    const float br_c = clamp_radius_f(br_raw);
+    if (self->states[ST_ACTUAL_ELLIPTICAL_DAB_RATIO] > 1.0f) unsupported("elliptical dabs");
+    const float k = fmaf(self->inv_actual_radius, self->settings_value[S_DABS_PER_ACTUAL_RADIUS],
+                         self->settings_value[S_DABS_PER_BASIC_RADIUS] / br_c);
+    return fmaf(dist, k, dtl * self->settings_value[S_DABS_PER_SECOND]);
+}
+
+/* update_states_and_setting_values after the position update; norm_speed and step_dtime (> 0) from the caller */
+static void update_states_fast(POBrush *self, float norm_speed, float step_dtime)
+{
+    float inputs[PO_INPUT_COUNT];
+    if (self->states[ST_PRESSURE] <= 0.0f) self->states[ST_PRESSURE] = 0.0f;
+    for (int i = 0; i < PO_INPUT_COUNT; i++) inputs[i] = 0.0f;
+    inputs[I_PRESSURE] = self->states[ST_PRESSURE];                /* pressure_gain_log must be 0 */
+    inputs[I_SPEED1] = fmaf(fast_logf(self->speed_mapping_gamma[0] + self->states[ST_NORM_SPEED1_SLOW]),
+                            self->speed_mapping_m[0], self->speed_mapping_q[0]);
+    inputs[I_SPEED2] = fmaf(fast_logf(self->speed_mapping_gamma[1] + self->states[ST_NORM_SPEED2_SLOW]),
+                            self->speed_mapping_m[1], self->speed_mapping_q[1]);
+    inputs[I_RANDOM] = (float)rng_next(&self->rng);
+    for (int i = 0; i < PO_SETTING_COUNT; i++) {
+        for (int j = I_STROKE; j < PO_INPUT_COUNT; j++)
+            if (self->settings[i].points[j].n) unsupported("mapping on stroke/direction/tilt/custom input (fast mode)");
+        self->settings_value[i] = mapping_calculate_fast(&self->settings[i], inputs);
+    }
+    if (base_value(self, S_PRESSURE_GAIN_LOG) != 0.0f) unsupported("pressure_gain_log (fast mode)");
+    if (self->settings_value[S_SLOW_TRACKING_PER_DAB] != 0.0f) unsupported("slow_tracking_per_dab (fast mode)");
+    self->states[ST_ACTUAL_X] = self->states[ST_X];                /* slow_tracking_per_dab == 0: fac = 1 */
+    self->states[ST_ACTUAL_Y] = self->states[ST_Y];
+    {
+        float fac = 1.0f - exp_decay_fast(self->settings_value[S_SPEED1_SLOWNESS], step_dtime);
+        self->states[ST_NORM_SPEED1_SLOW] += (norm_speed - self->states[ST_NORM_SPEED1_SLOW]) * fac;
+        fac = 1.0f - exp_decay_fast(self->settings_value[S_SPEED2_SLOWNESS], step_dtime);
+        self->states[ST_NORM_SPEED2_SLOW] += (norm_speed - self->states[ST_NORM_SPEED2_SLOW]) * fac;
+    }
+    {
+        float inv;
+        float ar = fast_exp_pm(self->settings_value[S_RADIUS_LOGARITHMIC], &inv);
+        if (ar < 0.2f) { ar = 0.2f; inv = 5.0f; }
+        if (ar > 1000.0f) { ar = 1000.0f; inv = 0.001f; }
+        self->states[ST_ACTUAL_RADIUS] = ar;
+        self->inv_actual_radius = inv;
+    }
+    self->states[ST_ACTUAL_ELLIPTICAL_DAB_RATIO] = self->settings_value[S_ELLIPTICAL_DAB_RATIO];
+    self->states[ST_ACTUAL_ELLIPTICAL_DAB_ANGLE] = self->settings_value[S_ELLIPTICAL_DAB_ANGLE];
+}
+
+/* the body of mypaint_brush_stroke_to after its prologue (pressure clamp, dtime, the split recursion) */
+static int stroke_to_fast(POBrush *self, POSurface *surface, float x, float y, float pressure, double dtime)
+{
+    const float br_raw = fast_expf(base_value(self, S_RADIUS_LOGARITHMIC));
+    if (base_value(self, S_TRACKING_NOISE)) unsupported("tracking_noise (fast mode)");
+    {
+        const float fac = 1.0f - exp_decay_fast(base_value(self, S_SLOW_TRACKING), (float)(100.0 * dtime));
+        x = self->states[ST_X] + (x - self->states[ST_X]) * fac;
+        y = self->states[ST_Y] + (y - self->states[ST_Y]) * fac;
+    }
+    float dabs_moved = self->states[ST_PARTIAL_DABS];
+    if (dtime > 5 || self->reset_requested) {
+        self->reset_requested = 0;
+        for (int i = 0; i < ST_COUNT; i++) self->states[i] = 0;
+        self->inv_actual_radius = 0.0f;
+        self->states[ST_X] = x;
+        self->states[ST_Y] = y;
+        self->states[ST_PRESSURE] = pressure;
+        self->states[ST_ACTUAL_X] = self->states[ST_X];
+        self->states[ST_ACTUAL_Y] = self->states[ST_Y];
+        self->states[ST_STROKE] = 1.0;
+        return 1;
+    }
+    float dtl = (float)dtime;
+    float dist = fast_hypotf(x - self->states[ST_X], y - self->states[ST_Y]);
+    const float norm_speed = dist * (1.0f / (dtl * br_raw));       /* constant over the event */
+    const float inv001 = 1.0f / (0.001f * br_raw);
+    float dabs_todo = count_dabs_fast(self, br_raw, dist, dtl);
+    while (dabs_moved + dabs_todo >= 1.0f) {
+        float step_ddab = 1.0f;
+        if (dabs_moved > 0.0f) {
+            step_ddab = 1.0f - dabs_moved;
+            dabs_moved = 0.0f;
+        }
+        const float frac = step_ddab / dabs_todo;
+        const float step_dtime = frac * dtl;
+        /* the position update keeps libmypaint's own operations (multiply, then add): the dab count is discontinuous
+         * in the position, so every rounding it shares with the reference keeps the two trajectories on the same dabs */
+        self->states[ST_X] += frac * (x - self->states[ST_X]);
+        self->states[ST_Y] += frac * (y - self->states[ST_Y]);
+        self->states[ST_PRESSURE] += frac * (pressure - self->states[ST_PRESSURE]);
+        if (step_dtime > 0.0f) update_states_fast(self, norm_speed, step_dtime);
+        else update_states_fast(self, frac * dist * inv001, 0.001f);       /* step_dtime clamped to 0.001 */
+        prepare_and_draw_dab(self, surface);
+        dtl -= step_dtime;
+        dist = fast_hypotf(x - self->states[ST_X], y - self->states[ST_Y]);
+        dabs_todo = count_dabs_fast(self, br_raw, dist, dtl);
+    }
+    self->states[ST_X] += x - self->states[ST_X];
+    self->states[ST_Y] += y - self->states[ST_Y];
+    self->states[ST_PRESSURE] += pressure - self->states[ST_PRESSURE];
+    if (dtl > 0.0f) update_states_fast(self, norm_speed, dtl);
+    else update_states_fast(self, dist * inv001, 0.001f);
+    self->states[ST_PARTIAL_DABS] = dabs_moved + dabs_todo;
+    return 0;
+}
+
 int po_brush_stroke_to(POBrush *self, POSurface *surface, float x, float y, float pressure,
                        float xtilt, float ytilt, double dtime)
 {
@@ -995,6 +1176,7 @@ int po_brush_stroke_to(POBrush *self, POSurface *surface, float x, float y, floa
         po_brush_stroke_to(self, surface, x, y, 0.0, 0.0, 0.0, dtime - 0.0001);
         dtime = 0.0001;
     }
+    if (mode == PO_MATH_FAST) return stroke_to_fast(self, surface, x, y, pressure, dtime);
 
     {
         if (base_value(self, S_TRACKING_NOISE)) {
@@ -1366,3 +1548,8 @@ void po_env_run_episode(POEnv *e, const int32_t *actions, int T, int K, const ui
 double po_det_exp(double x) { return det_exp(x); }
 double po_det_log(double x) { return det_log(x); }
 float po_det_hypotf(float a, float b) { return det_hypotf(a, b); }
+float po_fast_expf(float x) { return fast_expf(x); }
+float po_fast_exp_neg(float x) { float n; fast_exp_pm(x, &n); return n; }
+float po_fast_logf(float x) { return fast_logf(x); }
+float po_fast_hypotf(float a, float b) { return fast_hypotf(a, b); }
+float po_brush_get_inv_radius(const POBrush *b) { return b->inv_actual_radius; }

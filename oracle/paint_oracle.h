@@ -13,6 +13,7 @@ extern "C" {
 
 #define PO_MATH_LIBM 0
 #define PO_MATH_DET 1
+#define PO_MATH_FAST 2   /* the CUDA kernel's binary32 mode (fast_math.h + stroke_to_fast) */
 
 #define PO_SETTING_COUNT 45
 #define PO_INPUT_COUNT 9
@@ -117,6 +118,11 @@ void po_env_run_episode(POEnv *e, const int32_t *actions, int T, int K, const ui
 double po_det_exp(double x);
 double po_det_log(double x);
 float po_det_hypotf(float a, float b);
+float po_fast_expf(float x);
+float po_fast_exp_neg(float x);
+float po_fast_logf(float x);
+float po_fast_hypotf(float a, float b);
+float po_brush_get_inv_radius(const POBrush *b);
 
 #ifdef __cplusplus
 }

@@ -27,6 +27,7 @@ _LIB_PATH = os.path.join(_HERE, "libpaint_oracle.so")
 
 PO_MATH_LIBM = 0
 PO_MATH_DET = 1
+PO_MATH_FAST = 2      # the CUDA kernel's binary32 mode (oracle/fast_math.h + stroke_to_fast)
 PO_SETTING_COUNT = 45
 PO_INPUT_COUNT = 9
 PO_MAX_POINTS = 8
@@ -146,6 +147,13 @@ def lib():
     L.po_det_log.argtypes = [C.c_double]
     L.po_det_hypotf.restype = C.c_float
     L.po_det_hypotf.argtypes = [C.c_float, C.c_float]
+    for fn in ("po_fast_expf", "po_fast_exp_neg", "po_fast_logf"):
+        getattr(L, fn).restype = C.c_float
+        getattr(L, fn).argtypes = [C.c_float]
+    L.po_fast_hypotf.restype = C.c_float
+    L.po_fast_hypotf.argtypes = [C.c_float, C.c_float]
+    L.po_brush_get_inv_radius.restype = C.c_float
+    L.po_brush_get_inv_radius.argtypes = [vp]
     _lib = L
     return L
 

@@ -15,7 +15,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.environ.get("SPIRAL_B200_LIB") or os.path.join(CSRC, "libspiral_b200.so")   # override: tuning builds
 
-ABI_VERSION = 2
+ABI_VERSION = 3
+MATH_DET, MATH_FAST = 1, 2       # SpiralEnvCfg.math_mode
 MAX_POINTS, MAX_TABLE, MAX_L, TILE = 4, 8, 64, 64
 BRUSH_STATE_FLOATS, ENV_STATE_DOUBLES, DAB_FLOATS = 16, 16, 8
 DYN_NAMES = ["opaque", "opaque_multiply", "radius_logarithmic", "hardness", "radius_by_random",
@@ -57,7 +58,8 @@ class SpiralEnvCfg(C.Structure):
                 ("head", C.c_double), ("tail", C.c_double),
                 ("entry_pressure0", C.c_double),
                 ("brush", SpiralBrush),
-                ("dither_table", C.c_uint16 * (TILE * TILE))]
+                ("dither_table", C.c_uint16 * (TILE * TILE)),
+                ("math_mode", C.c_int32)]
 
 
 class SpiralDiscCfg(C.Structure):
@@ -86,6 +88,8 @@ SYMBOLS = {
     "spiral_env_debug_dabs": (C.c_int, [_vp] * 6),
     "spiral_l2_reward": (C.c_int, [_vp, _vp, _vp, C.c_int32, C.c_int32, _vp]),
     "spiral_debug_detmath": (C.c_int, [_vp, _vp, _vp, C.c_int32, _vp]),
+    "spiral_debug_divcheck": (C.c_int, [C.c_uint64, C.c_int64, _vp, _vp]),
+    "spiral_debug_fastmath": (C.c_int, [_vp, _vp, _vp, _vp, _vp, C.c_int32, _vp]),
     "spiral_a2c_loss": (C.c_int, [C.POINTER(_vp), C.POINTER(C.c_int32), C.c_int32, _vp, _vp, _vp, _vp,
                                   C.c_int32, C.c_int32, C.c_double, C.c_double, C.c_float,
                                   _vp, _vp, _vp, C.POINTER(_vp), _vp, _vp, _vp]),

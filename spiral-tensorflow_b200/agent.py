@@ -49,6 +49,19 @@ class Agent(object):
         self.rng = torch.Generator(device=self.device)
         self.rng.manual_seed(int(args.seed))
         self.world = dist_utils.dist.get_world_size() if dist_utils.dist.is_initialized() else 1
+        # env_runner (rl_utils.py:186-187) fetches policy.get_initial_features ONCE, before its `while True`: an actor's
+        # LSTM state carries over from the last step of one episode into the first step of the next.  [B, 2, lstm] = (c, h),
+        # read at the top of every rollout and written back at its end (inside the captured graph, so replays chain).
+        c0, h0 = self.policy.get_initial_features(env.num_envs)
+        self._lstm_state = torch.stack([c0, h0], 1).contiguous()
+        # K4's call counter lives on the device from the start (graph-capturable; a checkpoint restores it in place)
+        if self.device.type == "cuda":
+            self.policy._sample_counter_dev = torch.full((1,), int(getattr(self.policy, "_sample_offset", 0)),
+                                                         dtype=torch.int64, device=self.device)
+        # trajectory store: observations are integers 0..255 when color_channel == 3 (read-back of the uint8 image), so
+        # `states` is kept as uint8 (4x smaller: 252 MB instead of 1.03 GB at 1,024 canvases x 21 frames, lossless); gray
+        # observations are BT.601 dot products (non-integers) and stay float32 as in the reference's queue (agent.py:42-47)
+        self.state_dtype = torch.uint8 if (int(getattr(env, "channels", 1)) == 3 and getattr(args, "traj_uint8", True)) else torch.float32
         self._graph, self._graph_failed, self._g_out, self._g_target, self._g_z = None, False, {}, None, None
         self._tp_graph, self._tp_failed, self._tp_calls, self._tp_in, self._tp_out = None, False, 0, None, None
         self._tg_graph, self._tg_failed, self._tg_calls, self._tg_in, self._tg_out = None, False, 0, None, None
@@ -88,46 +101,28 @@ class Agent(object):
         self._g_target = env.get_random_target(num=B).clone() if env.conditional else None
         self._g_z = None if env.conditional else torch.zeros((B, env.z_dim), device=self.device)
         if getattr(pi, "_sample_counter_dev", None) is None:
-            pi._sample_counter_dev = torch.zeros((1,), dtype=torch.int64, device=self.device)
+            pi._sample_counter_dev = torch.full((1,), int(getattr(pi, "_sample_offset", 0)), dtype=torch.int64, device=self.device)
         self._g_init_action = torch.as_tensor(env.initial_action, device=self.device).to(torch.int32).expand(B, -1).contiguous()
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
+        saved = (self._lstm_state.clone(), pi._sample_counter_dev.clone())
         with torch.cuda.stream(side):                      # warm-up: lazy initialisation (function attributes, cuBLAS) outside capture
             self._rollout_body(self._g_target, self._g_z)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
+        self._lstm_state.copy_(saved[0])                   # the warm-up episode is not part of the actor's history
+        pi._sample_counter_dev.copy_(saved[1])
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
             self._g_out = self._rollout_body(self._g_target, self._g_z)
         self._graph = g
 
     def _rollout_body(self, target, z_in):
-        env, pi, T, B = self.env, self.policy, self.env.episode_length, self.env.num_envs
-        state, condition, z = env.reset(target=target, z=z_in)
-        c, h = pi.get_initial_features(B)
-        features0 = torch.stack([c, h], 1)
+        env, pi = self.env, self.policy
         last_action = self._g_init_action if getattr(self, "_g_init_action", None) is not None \
             else torch.as_tensor(env.initial_action, device=self.device)
-        states = torch.empty((B, T + 1) + tuple(state.shape[1:]), device=self.device)
-        actions = torch.empty((B, T, len(env.acs)), dtype=torch.int32, device=self.device)
-        rewards = torch.zeros((B, T), device=self.device)
-        values = torch.zeros((B, T, 1), device=self.device)
-        for t in range(T):
-            states[:, t] = state
-            action, value, c, h = (self.actor or pi).act(state, last_action, c, h, condition, z, self.rng)
-            state, reward, terminal, _ = env.step(action)
-            actions[:, t] = action
-            rewards[:, t] = reward
-            values[:, t, 0] = value
-            last_action = action
-        states[:, T] = state
-        out = dict(states=states, actions=actions, rewards=rewards, values=values,
-                   features=features0.unsqueeze(1).expand(B, T, 2, pi.lstm_size))
-        if condition is not None:
-            out["conditions"] = condition.unsqueeze(1).expand((B, T) + tuple(condition.shape[1:]))
-        else:
-            out["z"] = z.unsqueeze(1).expand(B, T, z.shape[-1])
-        return out
+        return rl_utils.batched_env_runner(env, (self.actor or pi).act, self._lstm_state, last_action, pi.lstm_size,
+                                           state_dtype=self.state_dtype, target=target, z=z_in, generator=self.rng)
 
     def _finish_rollout(self, out, clone=False):
         if clone:                                         # the graph's static buffers are overwritten by the next replay
@@ -147,8 +142,9 @@ class Agent(object):
             with torch.no_grad():
                 self.disc.sync_weights()
                 rollout["rewards"][:, -1] = self.disc.predict(rollout["states"][:, -1])       # agent.py:336-338
-        use_graph = (getattr(self.args, "cuda_graphs", True) and self.device.type == "cuda" and not self._tp_failed
-                     and self.world == 1)                # several ranks: eager (the all-reduce stays outside any capture)
+        # several ranks: the NCCL all-reduce is captured into the graph with the rest of the step (every rank replays the
+        # same sequence of collectives)
+        use_graph = getattr(self.args, "cuda_graphs", True) and self.device.type == "cuda" and not self._tp_failed
         if not use_graph:
             return self._train_policy_body(rollout)
         self._tp_calls += 1
@@ -187,7 +183,10 @@ class Agent(object):
         acts = rollout["actions"]
         samples = {name: acts[:, :, i] for i, name in enumerate(pi.acs)}                      # teacher forcing, agent.py:357-365
         feats = rollout["features"][:, 0]
-        logits, _, vf, _ = pi(rollout["states"], acts.float(), (feats[:, 0], feats[:, 1]),
+        states = rollout["states"]
+        if states.dtype != torch.float32:                 # uint8 trajectory store (color_channel 3): exact integers
+            states = states[:, :pi.episode_length].float()
+        logits, _, vf, _ = pi(states, acts.float(), (feats[:, 0], feats[:, 1]),
                               rollout.get("conditions"), rollout.get("z"), samples)
         loss = rl_utils.a2c_loss_autograd([logits[n].contiguous() for n in pi.acs], acts, rollout["rewards"],
                                           rollout["values"][:, :, 0], vf, 0.99, 1.0, args.entropy_coeff)
@@ -212,8 +211,7 @@ class Agent(object):
         fake = self.replay.sample(n)
         real = self.env.get_random_target(n) if reals is None else reals
         alpha = torch.rand((n, 1), generator=self.rng, device=self.device)
-        use_graph = (getattr(args, "cuda_graphs", True) and self.device.type == "cuda" and not self._tg_failed
-                     and self.world == 1)
+        use_graph = getattr(args, "cuda_graphs", True) and self.device.type == "cuda" and not self._tg_failed
         if not use_graph:
             return self._train_gan_body(fake, real, alpha)
         self._tg_calls += 1

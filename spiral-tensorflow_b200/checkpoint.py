@@ -74,6 +74,16 @@ def save_checkpoint(agent, load_path, step):
         state["optim/disc"] = _optim_state(agent.disc_opt)
     ctr = getattr(agent.policy, "_sample_counter_dev", None)
     state["sample_counter"] = int(ctr.item()) if ctr is not None else int(getattr(agent.policy, "_sample_offset", 0))
+    # the random streams and the data a resumed run would otherwise re-draw from their seeds: env (targets, z),
+    # agent (WGAN-GP interpolation), replay (sampling) generators, the replay ring and the actors' carried LSTM state
+    state["rng/env"] = agent.env._rng.get_state().cpu() if hasattr(agent.env, "_rng") else None
+    state["rng/agent"] = agent.rng.get_state().cpu()
+    if agent.gan:
+        state["rng/replay"] = agent.replay.rng.get_state().cpu()
+        state["replay/data"] = agent.replay.data.detach().cpu()
+        state["replay/idx"] = int(agent.replay.idx)
+    if getattr(agent, "_lstm_state", None) is not None:
+        state["actor/lstm_state"] = agent._lstm_state.detach().cpu()
     path = os.path.join(load_path, "model.ckpt-%d.pt" % int(step))
     tmp = path + ".tmp"
     torch.save(state, tmp)
@@ -108,6 +118,21 @@ def load_checkpoint(agent, path_or_dir):
     ctr = getattr(agent.policy, "_sample_counter_dev", None)
     if ctr is not None:
         ctr.fill_(int(state.get("sample_counter", 0)))
-    else:
-        agent.policy._sample_offset = int(state.get("sample_counter", 0))
+    agent.policy._sample_offset = int(state.get("sample_counter", 0))    # read when the device counter is created later
+    if state.get("rng/env") is not None and hasattr(agent.env, "_rng"):
+        agent.env._rng.set_state(state["rng/env"])
+    if state.get("rng/agent") is not None:
+        agent.rng.set_state(state["rng/agent"])
+    if agent.gan and state.get("rng/replay") is not None:
+        agent.replay.rng.set_state(state["rng/replay"])
+        if tuple(state["replay/data"].shape) == tuple(agent.replay.data.shape):
+            agent.replay.data.copy_(state["replay/data"])
+            agent.replay.idx = int(state["replay/idx"])
+    if state.get("actor/lstm_state") is not None and getattr(agent, "_lstm_state", None) is not None \
+            and tuple(state["actor/lstm_state"].shape) == tuple(agent._lstm_state.shape):
+        agent._lstm_state.copy_(state["actor/lstm_state"])
+    # the acting path holds its own packed (bf16) copy of the policy's convolution kernels, refreshed only after a
+    # learner step: re-pack it, or the first rollout after a resume acts with the random-init network
+    if getattr(agent, "actor", None) is not None:
+        agent.actor.sync()
     return int(state["step"])

@@ -69,6 +69,13 @@ def build_parser():
     parser.add_argument('--num_envs', type=int, default=64)
     parser.add_argument('--max_dabs', type=int, default=2560)
     parser.add_argument('--dither', type=str2bool, default=True)
+    # arithmetic of the brush state machine (include/spiral_b200.h SpiralEnvCfg.math_mode): 'det' = double-precision,
+    # correctly rounded exp / log / hypot (canvases bit-identical to the oracle's det mode, which matches glibc on >= 99 %
+    # of canvases); 'fast' = binary32 polynomials and a division-light dab loop (bit-identical to the oracle's fast mode;
+    # against libm: mean |err| <= 1e-3 on every canvas, single-dab jitter differences on ~20 % of 20-step canvases)
+    # trajectory store: RGB observations are integers 0..255, kept as uint8 (lossless, 4x smaller); False = float32
+    parser.add_argument('--traj_uint8', type=str2bool, default=True)
+    parser.add_argument('--raster_math', type=str, default='det', choices=['det', 'fast'])
     parser.add_argument('--disc_precision', type=str, default='bf16x3', choices=['fp32', 'bf16x3', 'bf16'])
     # arithmetic of the WGAN-GP step's convolutions and their gradients (K2b); 'auto' = bf16x6 (24 operand bits,
     # fp32-exact products on the tensor cores) when the reward forward runs on tensor cores, else fp32

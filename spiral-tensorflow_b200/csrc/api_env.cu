@@ -15,6 +15,7 @@
 #include "../../include/spiral_b200.h"
 #include "common.h"
 #include "detmath.cuh"
+#include "fastmath.cuh"
 #include "raster.cuh"
 
 namespace spiral {
@@ -23,15 +24,17 @@ cudaError_t launch_expand(const EnvParams &P, const int32_t *actions, float *bs,
                           int32_t *dab_count, int32_t *status, const float *gauss_tab, int32_t *plan_scratch,
                           cudaStream_t st);
 cudaError_t launch_composite(const EnvParams &P, uint16_t *canvas, const float *dabs, const int32_t *dab_count,
-                             const uint16_t *dither, float *obs, int32_t *work_counter, cudaStream_t st);
+                             const uint16_t *dither, float *obs, const float *gauss_tab, int32_t *work_counter, cudaStream_t st);
 bool fused_step_applies(const EnvParams &P);
 cudaError_t launch_step_small(const EnvParams &P, const int32_t *actions, float *bs, double *es, float *dabs,
                               int32_t *dab_count, int32_t *status, const float *gauss_tab, uint16_t *canvas,
                               const uint16_t *dither, float *obs, int32_t *plan_scratch, cudaStream_t st);
-cudaError_t launch_debug_dabs(const EnvParams &P, const float *dabs, const int32_t *dab_count, float *out,
-                              int32_t *out_count, cudaStream_t st);
+cudaError_t launch_debug_dabs(const EnvParams &P, const float *dabs, const int32_t *dab_count, const float *gauss_tab,
+                              float *out, int32_t *out_count, cudaStream_t st);
 cudaError_t launch_l2_reward(const float *obs, const float *target, float *reward, int batch, int n, cudaStream_t st);
 cudaError_t launch_detmath(const double *x, double *e, double *l, int n, cudaStream_t st);
+cudaError_t launch_fastmath(const float *x, float *e, float *en, float *l, float *h, int n, cudaStream_t st);
+cudaError_t launch_divcheck(unsigned long long seed, long long n, unsigned long long *mismatches, cudaStream_t st);
 }  // namespace spiral
 
 using namespace spiral;
@@ -175,6 +178,8 @@ extern "C" int spiral_env_create(const SpiralEnvCfg *cfg, SpiralEnv **out)
     if ((cfg->idx_color >= 0 || cfg->colorize) && cfg->n_colors < 1)
         return spiral_set_error(SPIRAL_EINVAL, "colour action / colorize needs a palette");
     if (cfg->max_dabs < 32) return spiral_set_error(SPIRAL_EINVAL, "max_dabs must be >= 32");
+    if (cfg->math_mode != SPIRAL_MATH_DET && cfg->math_mode != SPIRAL_MATH_FAST)
+        return spiral_set_error(SPIRAL_EINVAL, "math_mode must be SPIRAL_MATH_DET (1) or SPIRAL_MATH_FAST (2), got %d", cfg->math_mode);
     if (cfg->rng_table_len < 4096 || cfg->rng_table_len > (1 << 26))
         return spiral_set_error(SPIRAL_EINVAL, "rng_table_len must be in 4096..2^26 (got %d)", cfg->rng_table_len);
     {
@@ -238,6 +243,14 @@ extern "C" int spiral_env_create(const SpiralEnvCfg *cfg, SpiralEnv **out)
             for (int k = 0; k + 1 < m.n[j]; k++) {
                 const float den = m.x[j][k + 1] - m.x[j][k];
                 if (is_pow2f(den)) m.inv[j][k] = 1.0f / den;
+                // FAST mode: fmaf(slope, x, icpt) (oracle: mapping_calculate_fast)
+                const float x0 = m.x[j][k], y0 = m.y[j][k], x1 = m.x[j][k + 1], y1 = m.y[j][k + 1];
+                m.slope[j][k] = 0.0f;
+                m.icpt[j][k] = y0;
+                if (!(x0 == x1 || y0 == y1)) {
+                    m.slope[j][k] = (y1 - y0) / (x1 - x0);
+                    m.icpt[j][k] = y0 - m.slope[j][k] * x0;
+                }
             }
         }
     }
@@ -253,13 +266,28 @@ extern "C" int spiral_env_create(const SpiralEnvCfg *cfg, SpiralEnv **out)
             }
         P.dry_structure = ok ? 1 : 0;
     }
+    // arithmetic mode: the per-brush constants below are evaluated with the same functions the kernels (and the oracle's
+    // settings_base_values_have_changed / exp_decay in that mode) use
+    P.math_mode = cfg->math_mode;
+    const bool fast = cfg->math_mode == SPIRAL_MATH_FAST;
+    auto m_expf = [fast](float x) { return fast ? fastmath::fast_expf(x) : detmath::det_expf(x); };
     // base radius per size-table entry: set_base_value('radius_logarithmic', size) takes a float
-    for (int i = 0; i < 8; i++) {
-        P.base_rlog[i] = (float)cfg->sizes[i];
-        P.base_radius[i] = detmath::det_expf(P.base_rlog[i]);
-    }
+    for (int i = 0; i < 8; i++) P.base_rlog[i] = (float)cfg->sizes[i];
     P.base_rlog[8] = br.dyn[SPIRAL_DYN_RADIUS_LOGARITHMIC].base;
-    P.base_radius[8] = detmath::det_expf(P.base_rlog[8]);
+    for (int i = 0; i < 9; i++) {
+        P.base_radius[i] = m_expf(P.base_rlog[i]);
+        // FAST mode tables (oracle: stroke_to_fast / count_dabs_fast / update_states_fast evaluate these expressions in place)
+        const float r = P.base_radius[i];
+        const float rc = r < 0.2f ? 0.2f : (r > 1000.0f ? 1000.0f : r);
+        P.f_inv_norm01[i] = 1.0f / ((float)0.1 * r);
+        P.f_inv_norm1[i] = 1.0f / (1.0f * r);
+        P.f_inv_norm001[i] = 1.0f / (0.001f * r);
+        P.f_k_basic[i] = br.dabs_per_basic_radius / rc;
+    }
+    for (int i = 0; i < 2; i++) {
+        const float T = br.dyn[i == 0 ? SPIRAL_DYN_SPEED1_SLOWNESS : SPIRAL_DYN_SPEED2_SLOWNESS].base;
+        P.f_neg_inv_slow[i] = T < 0.001f ? 0.0f : -1.0f / T;
+    }
 
     P.slow_tracking = br.slow_tracking;
     // stroke_to: fac = 1.0 - exp_decay(slow_tracking, 100.0*dtime) for the two event durations
@@ -268,6 +296,11 @@ extern "C" int spiral_env_create(const SpiralEnvCfg *cfg, SpiralEnv **out)
         for (int i = 0; i < 2; i++) {
             const float t = (float)(100.0 * dts[i]);
             float ed = 0.0f;
+            if (fast) {
+                if (!(br.slow_tracking < 0.001f)) ed = fastmath::fast_expf(t * (-1.0f / br.slow_tracking));
+                P.track_fac[i] = 1.0f - ed;
+                continue;
+            }
             if (!((double)br.slow_tracking <= 0.001)) ed = (float)detmath::det_exp((double)(-t / br.slow_tracking));
             P.track_fac[i] = (float)(1.0 - (double)ed);
         }
@@ -275,9 +308,9 @@ extern "C" int spiral_env_create(const SpiralEnvCfg *cfg, SpiralEnv **out)
     // settings_base_values_have_changed: speed input mapping  y = log(gamma + x) * m + q
     const float gam[2] = {br.speed1_gamma, br.speed2_gamma};
     for (int i = 0; i < 2; i++) {
-        float gamma = detmath::det_expf(gam[i]);
+        float gamma = m_expf(gam[i]);
         const float fix1_x = 45.0f, fix1_y = 0.5f, fix2_x = 45.0f, fix2_dy = 0.015f;
-        const float c1 = (float)detmath::det_log((double)(fix1_x + gamma));
+        const float c1 = fast ? fastmath::fast_logf(fix1_x + gamma) : (float)detmath::det_log((double)(fix1_x + gamma));
         const float m = fix2_dy * (fix2_x + gamma);
         const float q = fix1_y - m * c1;
         P.sp_gamma[i] = gamma; P.sp_m[i] = m; P.sp_q[i] = q;
@@ -302,6 +335,32 @@ extern "C" int spiral_env_create(const SpiralEnvCfg *cfg, SpiralEnv **out)
         bool mapped = false;
         for (int j = 0; j < SPIRAL_IN_COUNT; j++) mapped |= rb.n[j] != 0;
         P.cull_factor = mapped ? 1e30f : (float)(::exp(3.4642 * (double)mx) * 1.001);
+    }
+    // The chain culls on the un-jittered position (raw_dab_may_paint): the margin adds the largest position jitter,
+    // 2 sqrt(3) |offset_by_random| base_radius, and the anti-aliasing fringe.  Bounds exist when those settings read the
+    // pressure input only (0 <= pressure <= 1 here: the env's pressures are <= 0.8) through mappings that end at x >= 1.
+    {
+        auto bound = [&](int sidx, bool &ok) {
+            const SpiralMapping &mp = br.dyn[sidx];
+            float mxv = fabsf(mp.base);
+            for (int j = 0; j < SPIRAL_IN_COUNT; j++) {
+                if (!mp.n[j]) continue;
+                if (j != SPIRAL_IN_PRESSURE || mp.x[j][mp.n[j] - 1] < 1.0f || mp.x[j][0] > 0.0f) { ok = false; continue; }
+                float my = 0.0f;
+                for (int k = 0; k < mp.n[j]; k++) my = fmaxf(my, fabsf(mp.y[j][k]));
+                mxv += my;
+            }
+            return mxv;
+        };
+        bool ok = true;
+        const float obr_max = bound(SPIRAL_DYN_OFFSET_BY_RANDOM, ok);
+        const float aa_max = bound(SPIRAL_DYN_ANTI_ALIASING, ok);
+        for (int i = 0; i < 9; i++)
+            P.cull_pad[i] = ok ? 3.4642f * obr_max * P.base_radius[i] * 1.001f + 0.5f * aa_max + 3.0f : 1e30f;
+        // dabs of zero pressure are blank when opaque_multiply is exactly 0 + y(pressure) with y(0) == 0 (dry_brush.myb)
+        const SpiralMapping &om = br.dyn[SPIRAL_DYN_OPAQUE_MULTIPLY];
+        P.zero_pressure_blank = (P.dry_structure && om.base == 0.0f && om.x[SPIRAL_IN_PRESSURE][0] == 0.0f &&
+                                 om.y[SPIRAL_IN_PRESSURE][0] == 0.0f) ? 1 : 0;
     }
     rng_seed_block(1000, P.rng_seed_block);
 
@@ -362,7 +421,7 @@ extern "C" int spiral_env_composite(SpiralEnv *env, uint16_t *canvas, const floa
                                     float *obs, void *stream)
 {
     REQUIRE(env); REQUIRE(canvas); REQUIRE(dabs); REQUIRE(dab_count); REQUIRE(obs);
-    const cudaError_t e = launch_composite(env->P, canvas, dabs, dab_count, env->d_dither, obs, env->d_plan, (cudaStream_t)stream);
+    const cudaError_t e = launch_composite(env->P, canvas, dabs, dab_count, env->d_dither, obs, env->d_gauss, env->d_plan, (cudaStream_t)stream);
     return e == cudaSuccess ? SPIRAL_OK : spiral_cuda_error(e, "spiral_env_composite");
 }
 
@@ -385,7 +444,7 @@ extern "C" int spiral_env_debug_dabs(SpiralEnv *env, const float *dabs, const in
                                      int32_t *out_count, void *stream)
 {
     REQUIRE(env); REQUIRE(dabs); REQUIRE(dab_count); REQUIRE(out); REQUIRE(out_count);
-    const cudaError_t e = launch_debug_dabs(env->P, dabs, dab_count, out, out_count, (cudaStream_t)stream);
+    const cudaError_t e = launch_debug_dabs(env->P, dabs, dab_count, env->d_gauss, out, out_count, (cudaStream_t)stream);
     return e == cudaSuccess ? SPIRAL_OK : spiral_cuda_error(e, "spiral_env_debug_dabs");
 }
 
@@ -396,6 +455,22 @@ extern "C" int spiral_l2_reward(const float *obs, const float *target, float *re
     if (batch <= 0 || n <= 0 || (n & 3)) return spiral_set_error(SPIRAL_EINVAL, "spiral_l2_reward: n must be a positive multiple of 4");
     const cudaError_t e = launch_l2_reward(obs, target, reward, batch, n, (cudaStream_t)stream);
     return e == cudaSuccess ? SPIRAL_OK : spiral_cuda_error(e, "spiral_l2_reward");
+}
+
+extern "C" int spiral_debug_fastmath(const float *x, float *e_out, float *en_out, float *l_out, float *h_out, int32_t n,
+                                     void *stream)
+{
+    REQUIRE(x); REQUIRE(e_out); REQUIRE(en_out); REQUIRE(l_out); REQUIRE(h_out);
+    const cudaError_t e = launch_fastmath(x, e_out, en_out, l_out, h_out, n, (cudaStream_t)stream);
+    return e == cudaSuccess ? SPIRAL_OK : spiral_cuda_error(e, "spiral_debug_fastmath");
+}
+
+extern "C" int spiral_debug_divcheck(uint64_t seed, int64_t n_pairs, uint64_t *mismatches_dev, void *stream)
+{
+    REQUIRE(mismatches_dev);
+    if (n_pairs <= 0) return spiral_set_error(SPIRAL_EINVAL, "spiral_debug_divcheck: n_pairs must be > 0");
+    const cudaError_t e = launch_divcheck(seed, n_pairs, (unsigned long long *)mismatches_dev, (cudaStream_t)stream);
+    return e == cudaSuccess ? SPIRAL_OK : spiral_cuda_error(e, "spiral_debug_divcheck");
 }
 
 extern "C" int spiral_debug_detmath(const double *x, double *e_out, double *l_out, int32_t n, void *stream)

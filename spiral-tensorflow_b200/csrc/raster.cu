@@ -22,6 +22,7 @@
 #include <stdlib.h>
 
 #include "detmath.cuh"
+#include "fastmath.cuh"
 #include "raster.cuh"
 
 namespace spiral {
@@ -80,11 +81,81 @@ __device__ __forceinline__ float map_seg(const MapDev &m, int j, float x)
     return (inv != 0.0f) ? num * inv : num / (x1 - x0);
 }
 
+// FAST arithmetic mode: a segment is fmaf(slope, x, intercept) with slope = (y1 - y0) / (x1 - x0) and intercept =
+// y0 - slope * x0 tabulated at create time (oracle: mapping_calculate_fast evaluates the same expressions in place)
+__device__ __forceinline__ float map_eval_fast(const MapDev &m, bool mapped, const float (&in)[kIn], float base)
+{
+    float result = base;
+    if (!mapped) return result;
+#pragma unroll
+    for (int j = 0; j < kIn; j++) {
+        const int n = m.n[j];
+        if (n) {
+            const float x = in[j];
+            int seg = 0;
+            for (int i = 2; i < n && x > m.x[j][i - 1]; i++) seg = i - 1;
+            result += fmaf(m.slope[j][seg], x, m.icpt[j][seg]);
+        }
+    }
+    return result;
+}
+__device__ __forceinline__ float map_seg_fast(const MapDev &m, int j, float x) { return fmaf(m.slope[j][0], x, m.icpt[j][0]); }
+
+template <bool FASTM>
+__device__ __forceinline__ float map_any(const MapDev &m, bool mapped, const float (&in)[kIn], float base)
+{
+    return FASTM ? map_eval_fast(m, mapped, in, base) : map_eval(m, mapped, in, base);
+}
+template <bool FASTM>
+__device__ __forceinline__ float seg_any(const MapDev &m, int j, float x)
+{
+    return FASTM ? map_seg_fast(m, j, x) : map_seg(m, j, x);
+}
+
+// The settings a dab needs beyond its position and radius_logarithmic (prepare_and_draw_dab): evaluated from the brush
+// inputs of the dab's update_states call -- by the compositing side (finalize_raw), lane-parallel, not by the serial chain.
+struct DabSettings { float opaque, opaque_mul, hard, rbr, obr, aa; };
+template <bool FASTM>
+__device__ __forceinline__ DabSettings dab_settings(const EnvParams &P, const float (&in)[kIn])
+{
+    DabSettings v;
+    if (P.dry_structure) {
+        v.opaque = P.dyn[0].base + seg_any<FASTM>(P.dyn[0], 0, in[0]);
+        v.opaque_mul = P.dyn[1].base + seg_any<FASTM>(P.dyn[1], 0, in[0]);
+        v.hard = P.dyn[3].base;
+        v.rbr = P.dyn[4].base;
+        v.obr = P.dyn[5].base + seg_any<FASTM>(P.dyn[5], 0, in[0]);
+        v.aa = P.dyn[8].base;
+    } else {
+        const int mm = P.mapped_mask;
+        v.opaque = map_any<FASTM>(P.dyn[0], mm & 1, in, P.dyn[0].base);
+        v.opaque_mul = map_any<FASTM>(P.dyn[1], mm & 2, in, P.dyn[1].base);
+        v.hard = map_any<FASTM>(P.dyn[3], mm & 8, in, P.dyn[3].base);
+        v.rbr = map_any<FASTM>(P.dyn[4], mm & 16, in, P.dyn[4].base);
+        v.obr = map_any<FASTM>(P.dyn[5], mm & 32, in, P.dyn[5].base);
+        v.aa = map_any<FASTM>(P.dyn[8], mm & 256, in, P.dyn[8].base);
+    }
+    return v;
+}
+// the two settings the chain itself needs (they decide how many random numbers a dab consumes)
+template <bool FASTM>
+__device__ __forceinline__ void jitter_settings(const EnvParams &P, const float (&in)[kIn], float &obr, float &rbr)
+{
+    if (P.dry_structure) {
+        rbr = P.dyn[4].base;
+        obr = P.dyn[5].base + seg_any<FASTM>(P.dyn[5], 0, in[0]);
+    } else {
+        const int mm = P.mapped_mask;
+        rbr = map_any<FASTM>(P.dyn[4], mm & 16, in, P.dyn[4].base);
+        obr = map_any<FASTM>(P.dyn[5], mm & 32, in, P.dyn[5].base);
+    }
+}
+
 // exp_decay (mypaint-brush.c): returns float
 __device__ __forceinline__ float exp_decay(float T_const, float t)
 {
     if (T_const < 0.001f) return 0.0f;      // (double)T <= 0.001  <=>  T < 0.001f  ((float)0.001 > 0.001)
-    return (float)det_exp((double)(-t / T_const));
+    return (float)det_exp((double)fastmath::div_exact(-t, T_const));
 }
 __device__ __forceinline__ float one_minus_decay(float T_const, float t)
 {
@@ -104,14 +175,16 @@ __device__ __forceinline__ float one_minus_decay(float T_const, float t)
 struct Brush {
     float X, Y, P, partial, AR, AX, AY, s1, s2;
     int flags;
-    // settings_value[] of the last update_states call
-    float v_opaque, v_opaque_mul, v_rlog, v_hard, v_rbr, v_obr, v_aa;
+    float v_rlog;      // settings_value[radius_logarithmic] of the last update_states call
+    float in[kIn];     // brush inputs of the last update_states call (pressure, speed1, speed2)
 };
 
 constexpr int kExpandThreads = 32;
 #ifndef EXPAND_MIN_BLOCKS
 #define EXPAND_MIN_BLOCKS 16
 #endif
+
+using fastmath::div_exact;   // == IEEE `/` for the operands of the dab loop, branch-free (fastmath.cuh)
 
 __device__ __forceinline__ float clamp_radius(float r)
 {
@@ -132,14 +205,15 @@ __device__ __forceinline__ float count_dabs_to(const EnvParams &P, Brush &S, flo
     const float yy = y - S.Y;
     const float dist = det_hypotf(xx, yy);
     const bool init = (S.flags & 2) != 0;
-    const float res1 = dist / S.AR * (init ? P.dabs_actual : 0.0f);
-    const float res2 = dist / base_radius * (init ? P.dabs_basic : 0.0f);
+    const float res1 = div_exact(dist, S.AR) * (init ? P.dabs_actual : 0.0f);
+    const float res2 = div_exact(dist, base_radius) * (init ? P.dabs_basic : 0.0f);
     const float res3 = dt * (init ? P.dabs_second : 0.0f);
     return res1 + res2 + res3;
 }
 
 // mypaint-brush.c update_states_and_setting_values, live state only (the stroke / direction /
-// custom / norm_d{x,y}_slow states feed inputs no supported mapping reads).
+// custom / norm_d{x,y}_slow states feed inputs no supported mapping reads).  Of the settings only
+// radius_logarithmic is evaluated here: the others are needed per dab, not by the chain (dab_settings).
 __device__ __forceinline__ void update_states(const EnvParams &P, Brush &S, float base_radius,
                                               float rlog_base, float step_dx, float step_dy,
                                               float step_dpressure, float step_dtime)
@@ -152,37 +226,18 @@ __device__ __forceinline__ void update_states(const EnvParams &P, Brush &S, floa
     S.P += step_dpressure;
     if (S.P <= 0.0f) S.P = 0.0f;
 
-    float in[kIn];
-    in[0] = S.P * 1.0f;   // * expf(pressure_gain_log = 0)
-    in[1] = 0.0f;
-    in[2] = 0.0f;
+    S.in[0] = S.P * 1.0f;   // * expf(pressure_gain_log = 0)
+    S.in[1] = 0.0f;
+    S.in[2] = 0.0f;
     if (P.uses_speed1)
-        in[1] = (float)(det_log((double)(P.sp_gamma[0] + S.s1)) * (double)P.sp_m[0] + (double)P.sp_q[0]);
+        S.in[1] = (float)(det_log((double)(P.sp_gamma[0] + S.s1)) * (double)P.sp_m[0] + (double)P.sp_q[0]);
     if (P.uses_speed2)
-        in[2] = (float)(det_log((double)(P.sp_gamma[1] + S.s2)) * (double)P.sp_m[1] + (double)P.sp_q[1]);
+        S.in[2] = (float)(det_log((double)(P.sp_gamma[1] + S.s2)) * (double)P.sp_m[1] + (double)P.sp_q[1]);
 
     const int mm = P.mapped_mask;
-    if (P.dry_structure) {
-        // the default brush's mapping structure (assets/brushes/dry_brush.myb): opaque, opaque_multiply
-        // and offset_by_random read pressure, radius_logarithmic reads speed2, each through one
-        // 2-point segment; everything else is constant.  Straight-line code, constants hoisted.
-        S.v_opaque = P.dyn[0].base + map_seg(P.dyn[0], 0, in[0]);
-        S.v_opaque_mul = P.dyn[1].base + map_seg(P.dyn[1], 0, in[0]);
-        S.v_rlog = rlog_base + map_seg(P.dyn[2], 2, in[2]);
-        S.v_hard = P.dyn[3].base;
-        S.v_rbr = P.dyn[4].base;
-        S.v_obr = P.dyn[5].base + map_seg(P.dyn[5], 0, in[0]);
-        S.v_aa = P.dyn[8].base;
-    } else {
-        S.v_opaque = map_eval(P.dyn[0], mm & 1, in, P.dyn[0].base);
-        S.v_opaque_mul = map_eval(P.dyn[1], mm & 2, in, P.dyn[1].base);
-        // the size action rewrites the base value of radius_logarithmic every step (mnist.py:134-135)
-        S.v_rlog = map_eval(P.dyn[2], mm & 4, in, rlog_base);
-        S.v_hard = map_eval(P.dyn[3], mm & 8, in, P.dyn[3].base);
-        S.v_rbr = map_eval(P.dyn[4], mm & 16, in, P.dyn[4].base);
-        S.v_obr = map_eval(P.dyn[5], mm & 32, in, P.dyn[5].base);
-        S.v_aa = map_eval(P.dyn[8], mm & 256, in, P.dyn[8].base);
-    }
+    // the size action rewrites the base value of radius_logarithmic every step (mnist.py:134-135)
+    if (P.dry_structure) S.v_rlog = rlog_base + map_seg(P.dyn[2], 2, S.in[2]);
+    else S.v_rlog = map_eval(P.dyn[2], mm & 4, S.in, rlog_base);
 
     // slow_tracking_per_dab == 0  =>  fac = 1.0 - 0.0
     {
@@ -191,22 +246,37 @@ __device__ __forceinline__ void update_states(const EnvParams &P, Brush &S, floa
         S.AY += (S.Y - S.AY) * fac;
     }
     if (P.uses_speed1 | P.uses_speed2) {
-        const float norm_dx = step_dx / step_dtime / base_radius;
-        const float norm_dy = step_dy / step_dtime / base_radius;
+        const float norm_dx = div_exact(div_exact(step_dx, step_dtime), base_radius);
+        const float norm_dy = div_exact(div_exact(step_dy, step_dtime), base_radius);
         const float norm_speed = det_hypotf(norm_dx, norm_dy);
         if (P.uses_speed1) {
-            const float v_s1slow = map_eval(P.dyn[6], mm & 64, in, P.dyn[6].base);
+            const float v_s1slow = map_eval(P.dyn[6], mm & 64, S.in, P.dyn[6].base);
             const float fac = one_minus_decay(v_s1slow, step_dtime);
             S.s1 += (norm_speed - S.s1) * fac;
         }
         if (P.uses_speed2) {
-            const float v_s2slow = map_eval(P.dyn[7], mm & 128, in, P.dyn[7].base);
+            const float v_s2slow = map_eval(P.dyn[7], mm & 128, S.in, P.dyn[7].base);
             const float fac = one_minus_decay(v_s2slow, step_dtime);
             S.s2 += (norm_speed - S.s2) * fac;
         }
     }
     S.AR = clamp_radius(det_expf(S.v_rlog));
     S.flags |= 2;
+}
+
+// A dab as the chain hands it to the compositing side: the raw state of its update_states call.
+//   r0 = (ACTUAL_X, ACTUAL_Y, pressure input, settings_value[radius_logarithmic])
+//   r1 = (ACTUAL_RADIUS, RNG cursor at the start of the call [int bits], speed1 input, speed2 input)
+// finalize_raw turns it into the dab libmypaint would draw (opacity and jitter settings, the three gaussians of the
+// stream window, radius jitter, anti-aliasing): ~60 instructions that nothing in the chain depends on, so they run
+// lane-parallel over 32 dabs there instead of serially here.  Dropped here (conservatively): dabs that cannot
+// touch tile (0,0) whatever their jitter, and -- when the brush maps zero pressure to zero opacity -- dabs of
+// pressure-free moves (jump steps).
+__device__ __forceinline__ bool raw_dab_may_paint(const EnvParams &P, float ax, float ay, float ar, float in0, float pad)
+{
+    if (P.zero_pressure_blank && in0 == 0.0f) return false;
+    const float R = fmaf(ar, P.cull_factor, pad);
+    return ax + R >= 0.0f && ax - R < 64.0f && ay + R >= 0.0f && ay - R < 64.0f;
 }
 
 struct StepSetup {
@@ -219,6 +289,9 @@ struct StepSetup {
     int head_range, tail_range;
     int n_events;
     bool curved;
+    // env state at the start of the step and the decoded tables
+    double s_x, s_y, pressure;
+    int size_idx, color_idx;
 };
 
 __device__ __forceinline__ void curve_point(const StepSetup &st, int i, double &px, double &py)
@@ -232,49 +305,24 @@ __device__ __forceinline__ void curve_point(const StepSetup &st, int i, double &
     py = y3 + y5 * ratio;
 }
 
-// One canvas's env step of the brush state machine (the body of expand_kernel).  STREAM: the fused small-batch step
-// (step_small_kernel) runs this in one thread while a second warp of the CTA composites the dabs as they appear;
-// prog = {dabs published, done, colour index, started} in shared memory.
-constexpr int kPublishEvery = 8;        // STREAM: dabs between two publications of the count (power of two)
-template <bool STREAM>
-__device__ __forceinline__ void expand_one(const EnvParams &P, const int b, const int32_t *__restrict__ actions,
-                                           float *__restrict__ brush_state, double *__restrict__ env_state,
-                                           float *__restrict__ dabs, int32_t *__restrict__ dab_count,
-                                           int32_t *__restrict__ status, const float *__restrict__ gauss_tab,
-                                           volatile int *prog)
+// action decode (mnist.py:107-135), pre-positioning event and stroke geometry (mnist.py:137-160, 173-190)
+__device__ __forceinline__ void decode_step(const EnvParams &P, const int32_t *__restrict__ ac,
+                                            const double *__restrict__ es, const int step, StepSetup &st)
 {
-    float *bs = brush_state + (size_t)b * kBrushFloats;
-    double *es = env_state + (size_t)b * kEnvDoubles;
-    Brush S;
-    S.X = bs[BS_X]; S.Y = bs[BS_Y]; S.P = bs[BS_PRESSURE]; S.partial = bs[BS_PARTIAL_DABS];
-    S.AR = bs[BS_ACTUAL_RADIUS]; S.AX = bs[BS_ACTUAL_X]; S.AY = bs[BS_ACTUAL_Y];
-    S.s1 = bs[BS_SPEED1_SLOW]; S.s2 = bs[BS_SPEED2_SLOW];
-    S.flags = __float_as_int(bs[BS_FLAGS]);
-    const int step = __float_as_int(bs[BS_STEP]);
-    int cursor = __float_as_int(bs[BS_RNG_POS]);
-    const int cursor_max = P.rng_table_len - 16;
-    S.v_opaque = S.v_opaque_mul = S.v_rlog = S.v_hard = S.v_rbr = S.v_obr = S.v_aa = 0.0f;
-
-    // ---- action decode (mnist.py:107-135) ----
-    const int32_t *ac = actions + (size_t)b * P.K;
-    StepSetup st;
     const int L = P.L;
     st.x = P.lin[0]; st.y = P.lin[0]; st.c_x = P.lin[0]; st.c_y = P.lin[0];
     double pressure = P.default_pressure;
     st.jump = 0;
-    int size_idx = 8;
-    int color_idx = 0;
+    st.size_idx = 8;
+    st.color_idx = 0;
     if (P.idx_end >= 0) { const int a = ac[P.idx_end]; st.x = P.lin[a % L]; st.y = P.lin[a / L]; }
     if (P.idx_control >= 0) { const int a = ac[P.idx_control]; st.c_x = P.lin[a % L]; st.c_y = P.lin[a / L]; }
     if (P.idx_pressure >= 0) pressure = P.pressures[ac[P.idx_pressure]];
-    if (P.idx_size >= 0) size_idx = ac[P.idx_size];
+    if (P.idx_size >= 0) st.size_idx = ac[P.idx_size];
     if (P.idx_jump >= 0) st.jump = ac[P.idx_jump];
-    if (P.idx_color >= 0) color_idx = ac[P.idx_color];
-    else if (P.colorize) color_idx = step % P.n_colors;
-    const float base_radius = P.base_radius[size_idx];     // expf(base radius_logarithmic), unclamped
-    const float rlog_base = P.base_rlog[size_idx];         // base value of radius_logarithmic this step
+    if (P.idx_color >= 0) st.color_idx = ac[P.idx_color];
+    else if (P.colorize) st.color_idx = step % P.n_colors;
 
-    // ---- pre-positioning event and stroke geometry (mnist.py:137-160) ----
     const bool have_start = es[ES_HAVE_START] != 0.0;
     double s_x = es[ES_SX], s_y = es[ES_SY];
     const double entry_pressure = es[ES_ENTRY_PRESSURE];
@@ -282,7 +330,7 @@ __device__ __forceinline__ void expand_one(const EnvParams &P, const int b, cons
     else if (P.idx_jump >= 0 && st.jump) pressure = 0;
     st.curved = !(P.idx_control < 0 || pressure == 0);
     st.sx = s_x; st.sy = s_y;
-    double cur_pressure_var = pressure;     // the `pressure` variable inside curve()
+    st.s_x = s_x; st.s_y = s_y; st.pressure = pressure;
     if (st.curved) {
         // _line_settings (mnist.py:270-278)
         double p1 = entry_pressure;
@@ -319,6 +367,67 @@ __device__ __forceinline__ void expand_one(const EnvParams &P, const int b, cons
     } else {
         st.n_events = 2;
     }
+}
+
+// stroke_to event `ev` of the step as the env hands it to the brush (mnist.py:137-160, 191-214): position and
+// pressure in double (Python floats), duration.  cur_pressure_var tracks curve()'s `pressure` variable.
+__device__ __forceinline__ void event_raw(const StepSetup &st, const int ev, double &px, double &py, double &pp,
+                                          double &edt, double &cur_pressure_var)
+{
+    if (ev == 0) {
+        px = st.s_x; py = st.s_y; pp = st.pressure; edt = 0.1;
+    } else if (!st.curved) {
+        px = st.x; py = st.y; pp = st.pressure; edt = 1.0;
+    } else if (ev == 1) {
+        px = st.bx; py = st.by; pp = st.entry_p; edt = 0.1;
+    } else {
+        const int i = ev - 1;
+        curve_point(st, i, px, py);
+        if (i < st.head_range) {
+            cur_pressure_var = fabs((double)i / st.head * st.prange1 + st.entry_p);
+            pp = cur_pressure_var;
+        } else if (i < st.tail_range) {
+            pp = st.midpoint_p;
+        } else {
+            cur_pressure_var = fabs(((double)i - st.tail) / st.tail_length * st.prange2 + st.midpoint_p);
+            pp = cur_pressure_var;
+        }
+        edt = 0.1;
+    }
+}
+
+// One canvas's env step of the brush state machine (the body of expand_kernel).  STREAM: the fused small-batch step
+// (step_small_kernel) runs this in one thread while a second warp of the CTA composites the dabs as they appear;
+// prog = {dabs published, done, colour index, started} in shared memory.
+constexpr int kPublishEvery = 8;        // STREAM: dabs between two publications of the count (power of two)
+template <bool STREAM>
+__device__ __forceinline__ void expand_one(const EnvParams &P, const int b, const int32_t *__restrict__ actions,
+                                           float *__restrict__ brush_state, double *__restrict__ env_state,
+                                           float *__restrict__ dabs, int32_t *__restrict__ dab_count,
+                                           int32_t *__restrict__ status, const float *__restrict__ gauss_tab,
+                                           volatile int *prog)
+{
+    float *bs = brush_state + (size_t)b * kBrushFloats;
+    double *es = env_state + (size_t)b * kEnvDoubles;
+    Brush S;
+    S.X = bs[BS_X]; S.Y = bs[BS_Y]; S.P = bs[BS_PRESSURE]; S.partial = bs[BS_PARTIAL_DABS];
+    S.AR = bs[BS_ACTUAL_RADIUS]; S.AX = bs[BS_ACTUAL_X]; S.AY = bs[BS_ACTUAL_Y];
+    S.s1 = bs[BS_SPEED1_SLOW]; S.s2 = bs[BS_SPEED2_SLOW];
+    S.flags = __float_as_int(bs[BS_FLAGS]);
+    const int step = __float_as_int(bs[BS_STEP]);
+    int cursor = __float_as_int(bs[BS_RNG_POS]);
+    const int cursor_max = P.rng_table_len - 16;
+    S.v_rlog = 0.0f;
+    S.in[0] = S.in[1] = S.in[2] = 0.0f;
+
+    StepSetup st;
+    decode_step(P, actions + (size_t)b * P.K, es, step, st);
+    const double pressure = st.pressure;
+    const int color_idx = st.color_idx | (st.size_idx << 8);  // what the compositing side needs to know about the step
+    const float base_radius = P.base_radius[st.size_idx];     // expf(base radius_logarithmic), unclamped
+    const float rlog_base = P.base_rlog[st.size_idx];         // base value of radius_logarithmic this step
+    const float cull_pad = P.cull_pad[st.size_idx];
+    double cur_pressure_var = pressure;     // the `pressure` variable inside curve()
 
     if (STREAM) {                                        // the consumer needs the colour before the first dab
         prog[2] = color_idx;
@@ -347,26 +456,7 @@ __device__ __forceinline__ void expand_one(const EnvParams &P, const int b, cons
                 split = 0;
             } else {
                 double px, py, pp;
-                if (ev == 0) {
-                    px = s_x; py = s_y; pp = pressure; edt = 0.1;
-                } else if (!st.curved) {
-                    px = st.x; py = st.y; pp = pressure; edt = 1.0;
-                } else if (ev == 1) {
-                    px = st.bx; py = st.by; pp = st.entry_p; edt = 0.1;
-                } else {
-                    const int i = ev - 1;
-                    curve_point(st, i, px, py);
-                    if (i < st.head_range) {
-                        cur_pressure_var = fabs((double)i / st.head * st.prange1 + st.entry_p);
-                        pp = cur_pressure_var;
-                    } else if (i < st.tail_range) {
-                        pp = st.midpoint_p;
-                    } else {
-                        cur_pressure_var = fabs(((double)i - st.tail) / st.tail_length * st.prange2 + st.midpoint_p);
-                        pp = cur_pressure_var;
-                    }
-                    edt = 0.1;
-                }
+                event_raw(st, ev, px, py, pp, edt, cur_pressure_var);
                 ex = (float)px; ey = (float)py; ep = (float)pp;
                 if (ep <= 0.0f) ep = 0.0f;
                 if (edt > 0.100 && ep != 0.0f && S.P == 0.0f) split = 1;
@@ -399,21 +489,18 @@ __device__ __forceinline__ void expand_one(const EnvParams &P, const int b, cons
 
     // ---- one update_states_and_setting_values per iteration (dab, or end of event) ----
     while (live) {
-        // gaussians this iteration may need (independent of the state chain: issue the loads early)
-        const int c0 = min(cursor, cursor_max);
-        const float g1 = __ldg(gauss_tab + c0 + 1), g5 = __ldg(gauss_tab + c0 + 5), g9 = __ldg(gauss_tab + c0 + 9);
-
+        const int c0 = cursor;
         const bool is_dab = (dabs_moved + dabs_todo >= 1.0f);
         float step_dx, step_dy, step_dp, step_dtime;
         if (is_dab) {
             float step_ddab;
             if (dabs_moved > 0.0f) {
-                step_ddab = (float)(1.0 - (double)dabs_moved);
+                step_ddab = 1.0f - dabs_moved;           // == (float)(1.0 - (double)dabs_moved): one correctly rounded subtraction
                 dabs_moved = 0.0f;
             } else {
                 step_ddab = 1.0f;
             }
-            const float frac = step_ddab / dabs_todo;
+            const float frac = div_exact(step_ddab, dabs_todo);
             step_dx = frac * (tx - S.X);
             step_dy = frac * (ty - S.Y);
             step_dp = frac * (tp - S.P);
@@ -429,46 +516,26 @@ __device__ __forceinline__ void expand_one(const EnvParams &P, const int b, cons
         cursor += 1;                     // inputs[RANDOM] = rng_double_next(): consumed on every call
 
         if (is_dab) {
-            // prepare_and_draw_dab, state-machine half (RNG draws, position jitter)
-            float opq = S.v_opaque;
-            if (opq < 0.0f) opq = 0.0f;
-            opq = opq * S.v_opaque_mul;
-            opq = opq > 1.0f ? 1.0f : (opq < 0.0f ? 0.0f : opq);
-            float x = S.AX, y = S.AY;
-            float gr = g1;
-            if (S.v_obr != 0.0f) {
-                float amp = S.v_obr;
-                if (amp < 0.0f) amp = 0.0f;
-                x += g1 * amp * base_radius;
-                y += g5 * amp * base_radius;
-                cursor += 8;
-                gr = g9;
-            }
-            float rl = S.v_rlog;
-            const bool has_rand = S.v_rbr != 0.0f;
-            if (has_rand) {
-                rl += gr * S.v_rbr;
-                cursor += 4;
-            }
-            if (opq != 0.0f) {
-                // conservative cull against tile (0,0); composite_kernel does the exact test
-                const float R = S.AR * P.cull_factor + 0.5f * fabsf(S.v_aa) + 3.0f;
-                if (x + R >= 0.0f && x - R < 64.0f && y + R >= 0.0f && y - R < 64.0f) {
-                    if (n_dabs < P.max_dabs) {
-                        float4 *d = reinterpret_cast<float4 *>(my_dabs + (size_t)n_dabs * kDabFloats);
-                        d[0] = make_float4(x, y, rl, S.AR);
-                        d[1] = make_float4(opq, S.v_hard, S.v_aa, has_rand ? 1.0f : 0.0f);
-                        n_dabs++;
-                        if (STREAM && (n_dabs & (kPublishEvery - 1)) == 0) {
-                            // publish to the compositing warp of this CTA -- every 8th dab only: the fence waits for the
-                            // dab stores above, ~150 cycles on a chain of ~1,000 per iteration, and the consumer works
-                            // in rounds of 32 anyway
-                            __threadfence_block();
-                            prog[0] = n_dabs;
-                        }
-                    } else {
-                        err |= 1;
+            // prepare_and_draw_dab: the chain only keeps count of the random numbers the dab draws; the dab itself is
+            // handed over raw (finalize_raw)
+            float v_obr, v_rbr;
+            jitter_settings<false>(P, S.in, v_obr, v_rbr);
+            if (v_obr != 0.0f) cursor += 8;
+            if (v_rbr != 0.0f) cursor += 4;
+            if (raw_dab_may_paint(P, S.AX, S.AY, S.AR, S.in[0], cull_pad)) {
+                if (n_dabs < P.max_dabs) {
+                    float4 *d = reinterpret_cast<float4 *>(my_dabs + (size_t)n_dabs * kDabFloats);
+                    d[0] = make_float4(S.AX, S.AY, S.in[0], S.v_rlog);
+                    d[1] = make_float4(S.AR, __int_as_float(c0), S.in[1], S.in[2]);
+                    n_dabs++;
+                    if (STREAM && (n_dabs & (kPublishEvery - 1)) == 0) {
+                        // publish to the compositing warp of this CTA -- every 8th dab only: the fence waits for the
+                        // dab stores above, and the consumer works in rounds of 32 anyway
+                        __threadfence_block();
+                        prog[0] = n_dabs;
                     }
+                } else {
+                    err |= 1;
                 }
             }
             dtime_left -= (double)step_dtime;
@@ -503,6 +570,251 @@ __device__ __forceinline__ void expand_one(const EnvParams &P, const int b, cons
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// K1a, FAST arithmetic mode (kMathFast).  The same state machine with a shorter serial chain; bit-identical to
+// oracle/paint_oracle.c's stroke_to_fast (PO_MATH_FAST), whose header lists the differences from libmypaint's
+// arithmetic (all at rounding level):
+//   * every operation is binary32 (dtime_left too); exp / log / hypot are fastmath.cuh's polynomials
+//   * a stroke_to event moves linearly in time, so its normalised speed is a constant of the event,
+//     dist0 / (dtime * base_radius), taken once when the event starts instead of per dab from
+//     hypot(step_dx, step_dy) / step_dtime / base_radius (where the dab's fraction cancels)
+//   * dist / ACTUAL_RADIUS multiplies by exp(-radius_logarithmic), which shares its range reduction with ACTUAL_RADIUS
+//   * exp_decay(T, t) = exp(t * (-1 / T)) with -1 / T hoisted when the slowness setting has no mapping
+//   * mapping segments are fmaf(slope, x, intercept)
+// The position update keeps libmypaint's own operations: the dab count is discontinuous in the position, and every
+// rounding shared with the reference keeps the two trajectories on the same dabs (tools/raster_tolerance.py).
+// ------------------------------------------------------------------------------------------
+struct BrushF {
+    float X, Y, P, partial, AR, iAR, s1, s2;
+    int flags;
+    float v_rlog;
+    float in[kIn];
+};
+
+__device__ __forceinline__ float exp_decay_fast(float T_const, float t)
+{
+    if (T_const < 0.001f) return 0.0f;
+    return fastmath::fast_expf(t * div_exact(-1.0f, T_const));
+}
+
+template <bool STREAM>
+__device__ __forceinline__ void expand_one_fast(const EnvParams &P, const int b, const int32_t *__restrict__ actions,
+                                                float *__restrict__ brush_state, double *__restrict__ env_state,
+                                                float *__restrict__ dabs, int32_t *__restrict__ dab_count,
+                                                int32_t *__restrict__ status, const float *__restrict__ gauss_tab,
+                                                volatile int *prog)
+{
+    using fastmath::fast_exp_pm;
+    using fastmath::fast_hypotf;
+    using fastmath::fast_logf;
+    float *bs = brush_state + (size_t)b * kBrushFloats;
+    double *es = env_state + (size_t)b * kEnvDoubles;
+    BrushF S;
+    S.X = bs[BS_X]; S.Y = bs[BS_Y]; S.P = bs[BS_PRESSURE]; S.partial = bs[BS_PARTIAL_DABS];
+    S.AR = bs[BS_ACTUAL_RADIUS]; S.iAR = bs[BS_INV_RADIUS];
+    S.s1 = bs[BS_SPEED1_SLOW]; S.s2 = bs[BS_SPEED2_SLOW];
+    S.flags = __float_as_int(bs[BS_FLAGS]);
+    const int step = __float_as_int(bs[BS_STEP]);
+    int cursor = __float_as_int(bs[BS_RNG_POS]);
+    const int cursor_max = P.rng_table_len - 16;
+    S.v_rlog = 0.0f;
+    S.in[0] = S.in[1] = S.in[2] = 0.0f;
+
+    StepSetup st;
+    decode_step(P, actions + (size_t)b * P.K, es, step, st);
+    const double pressure = st.pressure;
+    const int color_idx = st.color_idx | (st.size_idx << 8);
+    const float br_raw = P.base_radius[st.size_idx];          // fast_expf(base radius_logarithmic), unclamped
+    const float br_c = clamp_radius(br_raw);
+    const float rlog_base = P.base_rlog[st.size_idx];
+    const float inv01 = P.f_inv_norm01[st.size_idx], inv1 = P.f_inv_norm1[st.size_idx];
+    const float inv001 = P.f_inv_norm001[st.size_idx], k_basic = P.f_k_basic[st.size_idx];
+    const float cull_pad = P.cull_pad[st.size_idx];
+    double cur_pressure_var = pressure;
+
+    if (STREAM) {
+        prog[2] = color_idx;
+        __threadfence_block();
+        prog[3] = 1;
+    }
+    float *my_dabs = dabs + (size_t)b * P.max_dabs * kDabFloats;
+    int n_dabs = 0;
+    int err = 0;
+
+    int ev = 0;
+    int split = 0;
+    float ex = 0, ey = 0, ep = 0;
+    double edt = 0;
+    float tx = 0, ty = 0, tp = 0;
+    float dtl = 0;                    // dtime_left
+    float dist = 0;                   // distance to the event's target (count_dabs_to)
+    float ev_speed = 0;               // the event's normalised speed
+    float dabs_moved = 0, dabs_todo = 0;
+
+    // count_dabs_to (dist measured by the caller)
+    auto count_dabs = [&]() {
+        if (S.iAR == 0.0f) { S.AR = br_c; S.iAR = div_exact(1.0f, br_c); }     // ACTUAL_RADIUS == 0: first event after the reset
+        const bool init = (S.flags & 2) != 0;
+        const float k = init ? fmaf(S.iAR, P.dabs_actual, k_basic) : 0.0f;
+        dabs_todo = fmaf(dist, k, dtl * (init ? P.dabs_second : 0.0f));
+    };
+    auto begin_event = [&]() -> bool {
+        for (;;) {
+            if (ev >= st.n_events) return false;
+            if (split == 2) {
+                edt = 0.0001;
+                split = 0;
+            } else {
+                double px, py, pp;
+                event_raw(st, ev, px, py, pp, edt, cur_pressure_var);
+                ex = (float)px; ey = (float)py; ep = (float)pp;
+                if (ep <= 0.0f) ep = 0.0f;
+                if (edt > 0.100 && ep != 0.0f && S.P == 0.0f) split = 1;
+            }
+            float evp = ep;
+            double dt = edt;
+            if (split == 1) { evp = 0.0f; dt = edt - 0.0001; }
+            float fac, inv_dtl;
+            dtl = (float)dt;
+            if (dt == 0.1) { fac = P.track_fac[0]; inv_dtl = inv01; }
+            else if (dt == 1.0) { fac = P.track_fac[1]; inv_dtl = inv1; }
+            else { fac = 1.0f - exp_decay_fast(P.slow_tracking, (float)(100.0 * dt)); inv_dtl = div_exact(1.0f, dtl * br_raw); }
+            tx = S.X + (ex - S.X) * fac;
+            ty = S.Y + (ey - S.Y) * fac;
+            tp = evp;
+            dabs_moved = S.partial;
+            if (!(S.flags & 1)) {
+                dist = fast_hypotf(tx - S.X, ty - S.Y);
+                ev_speed = dist * inv_dtl;
+                count_dabs();
+                return true;
+            }
+            S.flags &= ~1;
+            S.X = tx; S.Y = ty; S.P = tp;
+            S.partial = 0; S.AR = 0; S.iAR = 0; S.s1 = 0; S.s2 = 0;
+            if (split == 1) split = 2; else ev++;
+        }
+    };
+
+    bool live = begin_event();
+
+    const int mm = P.mapped_mask;
+    while (live) {
+        const int c0 = cursor;
+        const bool is_dab = (dabs_moved + dabs_todo >= 1.0f);
+        float step_dx, step_dy, step_dp, step_dtime, corner_speed;
+        if (is_dab) {
+            float step_ddab = 1.0f;
+            if (dabs_moved > 0.0f) {
+                step_ddab = 1.0f - dabs_moved;
+                dabs_moved = 0.0f;
+            }
+            const float frac = div_exact(step_ddab, dabs_todo);
+            step_dx = frac * (tx - S.X);
+            step_dy = frac * (ty - S.Y);
+            step_dp = frac * (tp - S.P);
+            step_dtime = frac * dtl;
+            corner_speed = frac * dist * inv001;
+        } else {
+            step_dx = tx - S.X;
+            step_dy = ty - S.Y;
+            step_dp = tp - S.P;
+            step_dtime = dtl;
+            corner_speed = dist * inv001;
+        }
+        float norm_speed = ev_speed, t_eff = step_dtime;
+        if (!(step_dtime > 0.0f)) {                          // step_dtime clamped to 0.001
+            norm_speed = corner_speed;
+            t_eff = 0.001f;
+        }
+
+        // ---- update_states_and_setting_values ----
+        S.X += step_dx;
+        S.Y += step_dy;
+        S.P += step_dp;
+        if (S.P <= 0.0f) S.P = 0.0f;
+        S.in[0] = S.P;
+        S.in[1] = 0.0f;
+        S.in[2] = 0.0f;
+        if (P.uses_speed1) S.in[1] = fmaf(fast_logf(P.sp_gamma[0] + S.s1), P.sp_m[0], P.sp_q[0]);
+        if (P.uses_speed2) S.in[2] = fmaf(fast_logf(P.sp_gamma[1] + S.s2), P.sp_m[1], P.sp_q[1]);
+        if (P.dry_structure) S.v_rlog = rlog_base + map_seg_fast(P.dyn[2], 2, S.in[2]);
+        else S.v_rlog = map_eval_fast(P.dyn[2], mm & 4, S.in, rlog_base);
+        if (P.uses_speed1) {
+            float decay;
+            if (mm & 64) decay = exp_decay_fast(map_eval_fast(P.dyn[6], true, S.in, P.dyn[6].base), t_eff);
+            else decay = P.dyn[6].base < 0.001f ? 0.0f : fastmath::fast_expf(t_eff * P.f_neg_inv_slow[0]);
+            S.s1 += (norm_speed - S.s1) * (1.0f - decay);
+        }
+        if (P.uses_speed2) {
+            float decay;
+            if (mm & 128) decay = exp_decay_fast(map_eval_fast(P.dyn[7], true, S.in, P.dyn[7].base), t_eff);
+            else decay = P.dyn[7].base < 0.001f ? 0.0f : fastmath::fast_expf(t_eff * P.f_neg_inv_slow[1]);
+            S.s2 += (norm_speed - S.s2) * (1.0f - decay);
+        }
+        {
+            float inv;
+            float ar = fast_exp_pm(S.v_rlog, &inv);
+            if (ar < 0.2f) { ar = 0.2f; inv = 5.0f; }
+            if (ar > 1000.0f) { ar = 1000.0f; inv = 0.001f; }
+            S.AR = ar;
+            S.iAR = inv;
+        }
+        S.flags |= 2;
+        cursor += 1;
+
+        if (is_dab) {
+            float v_obr, v_rbr;
+            jitter_settings<true>(P, S.in, v_obr, v_rbr);
+            if (v_obr != 0.0f) cursor += 8;
+            if (v_rbr != 0.0f) cursor += 4;
+            if (raw_dab_may_paint(P, S.X, S.Y, S.AR, S.in[0], cull_pad)) {
+                if (n_dabs < P.max_dabs) {
+                    float4 *d = reinterpret_cast<float4 *>(my_dabs + (size_t)n_dabs * kDabFloats);
+                    d[0] = make_float4(S.X, S.Y, S.in[0], S.v_rlog);             // ACTUAL_X/Y == X/Y (slow_tracking_per_dab 0)
+                    d[1] = make_float4(S.AR, __int_as_float(c0), S.in[1], S.in[2]);
+                    n_dabs++;
+                    if (STREAM && (n_dabs & (kPublishEvery - 1)) == 0) {
+                        __threadfence_block();
+                        prog[0] = n_dabs;
+                    }
+                } else {
+                    err |= 1;
+                }
+            }
+            dtl -= step_dtime;
+            dist = fast_hypotf(tx - S.X, ty - S.Y);
+            count_dabs();
+        } else {
+            S.partial = dabs_moved + dabs_todo;
+            if (split == 1) split = 2; else ev++;
+            live = begin_event();
+        }
+    }
+    if (cursor > cursor_max) err |= 2;
+
+    bs[BS_X] = S.X; bs[BS_Y] = S.Y; bs[BS_PRESSURE] = S.P; bs[BS_PARTIAL_DABS] = S.partial;
+    bs[BS_ACTUAL_RADIUS] = S.AR; bs[BS_INV_RADIUS] = S.iAR; bs[BS_ACTUAL_X] = S.X; bs[BS_ACTUAL_Y] = S.Y;
+    bs[BS_SPEED1_SLOW] = S.s1; bs[BS_SPEED2_SLOW] = S.s2;
+    bs[BS_FLAGS] = __int_as_float(S.flags);
+    bs[BS_STEP] = __int_as_float(step + 1);
+    bs[BS_RNG_POS] = __int_as_float(cursor);
+    es[ES_SX] = st.x;
+    es[ES_SY] = st.y;
+    es[ES_ENTRY_PRESSURE] = st.curved ? cur_pressure_var : pressure;
+    es[ES_HAVE_START] = 1.0;
+    dab_count[2 * b] = n_dabs;
+    dab_count[2 * b + 1] = color_idx;
+    if (err) atomicOr(status, err);
+    if (STREAM) {
+        __threadfence_block();
+        prog[0] = n_dabs;
+        __threadfence_block();
+        prog[1] = 1;
+    }
+}
+
+template <int MATH>
 __global__ void __launch_bounds__(kExpandThreads, EXPAND_MIN_BLOCKS)
 expand_kernel(const __grid_constant__ EnvParams P, const int32_t *__restrict__ actions,
               float *__restrict__ brush_state, double *__restrict__ env_state,
@@ -529,7 +841,10 @@ expand_kernel(const __grid_constant__ EnvParams P, const int32_t *__restrict__ a
     // chains of similar length instead of idling behind the longest one
     const int b = perm ? perm[slot] : slot;
 
-    expand_one<false>(P, b, actions, brush_state, env_state, dabs, dab_count, status, gauss_tab, nullptr);
+    if (MATH == kMathFast)
+        expand_one_fast<false>(P, b, actions, brush_state, env_state, dabs, dab_count, status, gauss_tab, nullptr);
+    else
+        expand_one<false>(P, b, actions, brush_state, env_state, dabs, dab_count, status, gauss_tab, nullptr);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -638,14 +953,14 @@ struct FinalDab {
 };
 
 // prepare_and_draw_dab's second half + draw_dab_internal + render_dab_mask's per-dab constants
-__device__ __forceinline__ FinalDab finalize_dab(const float4 a, const float4 b)
+__device__ __forceinline__ FinalDab finalize_dab(const float4 a, const float4 b, const bool fast_math)
 {
     FinalDab f;
     float x = a.x, y = a.y;
     float radius = a.w;          // ACTUAL_RADIUS
     float opq = b.x;
     if (b.w != 0.0f) {
-        radius = clamp_radius(det_expf(a.z));
+        radius = clamp_radius(fast_math ? fastmath::fast_expf(a.z) : det_expf(a.z));
         float ac = a.w / radius;
         ac = ac * ac;
         if (ac <= 1.0f) opq *= ac;
@@ -688,6 +1003,36 @@ __device__ __forceinline__ FinalDab finalize_dab(const float4 a, const float4 b)
     ras *= ras / 1.0f;
     f.r_aa_start = ras;
     return f;
+}
+
+// prepare_and_draw_dab from the chain's raw record (see raw_dab_may_paint): the dab's settings from the brush inputs of its
+// update_states call, opacity, the position jitter and the radius jitter from the window of the gaussian stream the
+// dab owns (cursor + 1, + 5, + 9), then finalize_dab.  size_idx: the step's size action (base radius of the jitter).
+template <bool FASTM>
+__device__ __forceinline__ FinalDab finalize_raw(const EnvParams &P, const float4 r0, const float4 r1, const int size_idx,
+                                                 const float *__restrict__ gauss_tab)
+{
+    const float in[kIn] = {r0.z, r1.z, r1.w};
+    const DabSettings v = dab_settings<FASTM>(P, in);
+    float opq = v.opaque;
+    if (opq < 0.0f) opq = 0.0f;
+    opq = opq * v.opaque_mul;
+    opq = opq > 1.0f ? 1.0f : (opq < 0.0f ? 0.0f : opq);
+    float x = r0.x, y = r0.y;
+    const int c0 = min(__float_as_int(r1.y), P.rng_table_len - 16);
+    const float base_radius = P.base_radius[size_idx];
+    int g = c0 + 1;
+    if (v.obr != 0.0f) {
+        float amp = v.obr;
+        if (amp < 0.0f) amp = 0.0f;
+        x += __ldg(gauss_tab + c0 + 1) * amp * base_radius;
+        y += __ldg(gauss_tab + c0 + 5) * amp * base_radius;
+        g = c0 + 9;
+    }
+    float rl = r0.w;
+    const bool has_rand = v.rbr != 0.0f;
+    if (has_rand) rl += __ldg(gauss_tab + g) * v.rbr;
+    return finalize_dab(make_float4(x, y, rl, r1.x), make_float4(opq, v.hard, v.aa, has_rand ? 1.0f : 0.0f), FASTM);
 }
 
 // mypaint-tiled-surface.c calculate_rr_antialiased / calculate_rr with aspect_ratio == 1
@@ -861,6 +1206,7 @@ template <int C, bool SMT, bool STREAM>
 __device__ __forceinline__ void composite_one(const EnvParams &P, const int b, uint16_t *__restrict__ canvas,
                                               const float *__restrict__ dabs, const int32_t *__restrict__ dab_count,
                                               const uint16_t *__restrict__ dither, float *__restrict__ obs,
+                                              const float *__restrict__ gauss_tab,
                                               SharedDab *sd, uint16_t *sp, uint16_t *so, int *soff, uint2 *stile,
                                               const int lane, volatile int *prog)
 {
@@ -875,6 +1221,8 @@ __device__ __forceinline__ void composite_one(const EnvParams &P, const int b, u
         color_idx = dab_count[2 * b + 1];
     }
     bool done = !STREAM;
+    const int size_idx = color_idx >> 8;             // packed by the chain: colour | size action << 8
+    color_idx &= 0xff;
     const uint32_t col_r = P.colors[color_idx][0], col_g = P.colors[color_idx][1],
                    col_b = P.colors[color_idx][2];
     uint2 *gtile = reinterpret_cast<uint2 *>(canvas + (size_t)b * kTile * kTile * 4);   // RGBA u16x4 per pixel
@@ -912,6 +1260,7 @@ __device__ __forceinline__ void composite_one(const EnvParams &P, const int b, u
     };
 
     const float cs_rad_area_1 = P.cs * P.rad_area_1;
+    const bool fast_math = P.math_mode == kMathFast;
     int base = 0;
     for (;;) {
         if (STREAM && !done && n_dabs - base < 32) {
@@ -937,9 +1286,12 @@ __device__ __forceinline__ void composite_one(const EnvParams &P, const int b, u
         f.opacity = 0; f.x0 = 1; f.x1 = 0; f.y0 = 1; f.y1 = 0;
         f.x = f.y = f.radius = f.hardness = f.one_over_r2 = f.r_aa_start = 0;
         f.seg1_slope = f.seg2_offset = f.seg2_slope = 0;
-        if (mine < n_dabs)
-            f = STREAM ? finalize_dab(__ldcg(dl + 2 * mine), __ldcg(dl + 2 * mine + 1))     // written by this CTA's producer
-                       : finalize_dab(__ldg(dl + 2 * mine), __ldg(dl + 2 * mine + 1));
+        if (mine < n_dabs) {
+            // STREAM: the records were written by this CTA's producer (L2-coherent loads)
+            const float4 r0 = STREAM ? __ldcg(dl + 2 * mine) : __ldg(dl + 2 * mine);
+            const float4 r1 = STREAM ? __ldcg(dl + 2 * mine + 1) : __ldg(dl + 2 * mine + 1);
+            f = fast_math ? finalize_raw<true>(P, r0, r1, size_idx, gauss_tab) : finalize_raw<false>(P, r0, r1, size_idx, gauss_tab);
+        }
         const bool hit = f.opacity != 0;             // 0 also when the dab misses tile (0,0)
         const float rlim = f.radius * 1.001f + 0.01f;
         const float rlim2 = rlim * rlim;
@@ -1116,7 +1468,8 @@ template <int C, bool SMT>
 __global__ void __launch_bounds__(32 * kCompWarps, SMT ? 3 : kCompResident / kCompWarps)
 composite_kernel(const __grid_constant__ EnvParams P, uint16_t *__restrict__ canvas,
                  const float *__restrict__ dabs, const int32_t *__restrict__ dab_count,
-                 const uint16_t *__restrict__ dither, float *__restrict__ obs, int32_t *__restrict__ work_counter)
+                 const uint16_t *__restrict__ dither, float *__restrict__ obs, const float *__restrict__ gauss_tab,
+                 int32_t *__restrict__ work_counter)
 {
     extern __shared__ __align__(16) uint8_t s_tiles[];   // SMT: [kCompWarps][64*64] RGBA u16x4
     __shared__ SharedDab s_dab[kCompWarps][32];
@@ -1132,7 +1485,7 @@ composite_kernel(const __grid_constant__ EnvParams P, uint16_t *__restrict__ can
     if (lane == 0) b = atomicAdd(work_counter, 1);
     b = __shfl_sync(0xffffffffu, b, 0);
     if (b >= P.B) return;
-    composite_one<C, SMT, false>(P, b, canvas, dabs, dab_count, dither, obs, s_dab[warp], s_pair[warp], s_opa[warp], s_off[warp],
+    composite_one<C, SMT, false>(P, b, canvas, dabs, dab_count, dither, obs, gauss_tab, s_dab[warp], s_pair[warp], s_opa[warp], s_off[warp],
                                  SMT ? reinterpret_cast<uint2 *>(s_tiles) + warp * (kTile * kTile) : nullptr, lane, nullptr);
     __syncwarp();
     }   // next canvas
@@ -1148,7 +1501,7 @@ composite_kernel(const __grid_constant__ EnvParams P, uint16_t *__restrict__ can
 // SMT: the canvas's tile lives in shared memory for the step (32 KB, 5 CTAs per SM), as in composite_kernel<C, true>: alone
 // on its canvas the compositing warp is bound by the latency of the ordered blend's load -> blend -> store chain, which is
 // several times shorter from shared memory than through L1/L2, so it keeps up with the chain on the densest canvases.
-template <int C, bool SMT>
+template <int C, bool SMT, int MATH>
 __global__ void __launch_bounds__(64, SMT ? 5 : 8)
 step_small_kernel(const __grid_constant__ EnvParams P, const int32_t *__restrict__ actions,
                   float *__restrict__ brush_state, double *__restrict__ env_state, float *__restrict__ dabs,
@@ -1168,9 +1521,12 @@ step_small_kernel(const __grid_constant__ EnvParams P, const int32_t *__restrict
     if (threadIdx.x < 4) s_prog[threadIdx.x] = 0;
     __syncthreads();
     if (threadIdx.x == 0) {
-        expand_one<true>(P, b, actions, brush_state, env_state, dabs, dab_count, status, gauss_tab, s_prog);
+        if (MATH == kMathFast)
+            expand_one_fast<true>(P, b, actions, brush_state, env_state, dabs, dab_count, status, gauss_tab, s_prog);
+        else
+            expand_one<true>(P, b, actions, brush_state, env_state, dabs, dab_count, status, gauss_tab, s_prog);
     } else if (threadIdx.x >= 32) {
-        composite_one<C, SMT, true>(P, b, canvas, dabs, dab_count, dither, obs, s_dab, s_pair, s_opa, s_off,
+        composite_one<C, SMT, true>(P, b, canvas, dabs, dab_count, dither, obs, gauss_tab, s_dab, s_pair, s_opa, s_off,
                                     SMT ? reinterpret_cast<uint2 *>(s_fused_tile) : nullptr, threadIdx.x & 31, s_prog);
     }
 }
@@ -1202,8 +1558,8 @@ __global__ void reset_kernel(const __grid_constant__ EnvParams P, uint16_t *__re
 }
 
 __global__ void debug_dabs_kernel(const __grid_constant__ EnvParams P, const float *__restrict__ dabs,
-                                  const int32_t *__restrict__ dab_count, float *__restrict__ out,
-                                  int32_t *__restrict__ out_count)
+                                  const int32_t *__restrict__ dab_count, const float *__restrict__ gauss_tab,
+                                  float *__restrict__ out, int32_t *__restrict__ out_count)
 {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= P.B) return;
@@ -1212,7 +1568,9 @@ __global__ void debug_dabs_kernel(const __grid_constant__ EnvParams P, const flo
     const int n = dab_count[2 * b];
     int m = 0;
     for (int i = 0; i < n; i++) {
-        const FinalDab f = finalize_dab(dl[2 * i], dl[2 * i + 1]);
+        const int size_idx = dab_count[2 * b + 1] >> 8;
+        const FinalDab f = P.math_mode == kMathFast ? finalize_raw<true>(P, dl[2 * i], dl[2 * i + 1], size_idx, gauss_tab)
+                                                    : finalize_raw<false>(P, dl[2 * i], dl[2 * i + 1], size_idx, gauss_tab);
         if (f.opacity == 0) continue;
         o[m * 5 + 0] = f.x; o[m * 5 + 1] = f.y; o[m * 5 + 2] = f.radius; o[m * 5 + 3] = f.hardness;
         o[m * 5 + 4] = (float)f.opacity;
@@ -1256,6 +1614,37 @@ __global__ void detmath_kernel(const double *__restrict__ x, double *__restrict_
     l[i] = x[i] > 0 ? det_log(x[i]) : 0.0;
 }
 
+__global__ void fastmath_kernel(const float *__restrict__ x, float *__restrict__ e, float *__restrict__ en,
+                                float *__restrict__ l, float *__restrict__ h, int n)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float neg;
+    e[i] = fastmath::fast_exp_pm(x[i], &neg);
+    en[i] = neg;
+    l[i] = x[i] > 0 ? fastmath::fast_logf(x[i]) : 0.0f;
+    h[i] = fastmath::fast_hypotf(x[i], x[n - 1 - i]);
+}
+
+// div_exact (fastmath.cuh) against the IEEE division over pseudo-random operand pairs: magnitudes 2^-24 .. 2^24 with random
+// mantissas and signs (everything the dab loop divides lies well inside).  mismatches: pairs whose bits differ.
+__global__ void divcheck_kernel(unsigned long long seed, long long n, unsigned long long *__restrict__ mismatches)
+{
+    unsigned long long bad = 0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        unsigned long long z = seed + (unsigned long long)i * 0x9E3779B97F4A7C15ULL;      // splitmix64
+        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+        z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+        z ^= z >> 31;
+        const unsigned lo = (unsigned)z, hi = (unsigned)(z >> 32);
+        const unsigned ea = 127u - 24u + (lo >> 23) % 49u, eb = 127u - 24u + (hi >> 23) % 49u;
+        const float a = __uint_as_float((lo & 0x807fffffu) | (ea << 23));
+        const float b = __uint_as_float((hi & 0x807fffffu) | (eb << 23));
+        if (__float_as_uint(fastmath::div_exact(a, b)) != __float_as_uint(__fdiv_rn(a, b))) bad++;
+    }
+    if (bad) atomicAdd(mismatches, bad);
+}
+
 // ------------------------------------------------------------------------------------------
 // host launchers (called from api.cu)
 // ------------------------------------------------------------------------------------------
@@ -1294,11 +1683,14 @@ cudaError_t launch_expand(const EnvParams &P, const int32_t *actions, float *bs,
         if (n_solo > 256) n_solo = 256;
     }
     const int blocks = n_solo + (P.B - n_solo + lanes - 1) / lanes;
-    expand_kernel<<<blocks, kExpandThreads, 0, st>>>(P, actions, bs, es, dabs, dab_count, status, gauss_tab, lanes, perm, n_solo);
+    if (P.math_mode == kMathFast)
+        expand_kernel<kMathFast><<<blocks, kExpandThreads, 0, st>>>(P, actions, bs, es, dabs, dab_count, status, gauss_tab, lanes, perm, n_solo);
+    else
+        expand_kernel<kMathDet><<<blocks, kExpandThreads, 0, st>>>(P, actions, bs, es, dabs, dab_count, status, gauss_tab, lanes, perm, n_solo);
     return cudaGetLastError();
 }
 cudaError_t launch_composite(const EnvParams &P, uint16_t *canvas, const float *dabs,
-                             const int32_t *dab_count, const uint16_t *dither, float *obs,
+                             const int32_t *dab_count, const uint16_t *dither, float *obs, const float *gauss_tab,
                              int32_t *work_counter, cudaStream_t st)
 {
     cudaMemsetAsync(work_counter, 0, sizeof(int32_t), st);
@@ -1318,17 +1710,17 @@ cudaError_t launch_composite(const EnvParams &P, uint16_t *canvas, const float *
         int blocks = (P.B + kCompWarps - 1) / kCompWarps;
         if (blocks > 148 * 3) blocks = 148 * 3;
         if (P.C == 1)
-            composite_kernel<1, true><<<blocks, 32 * kCompWarps, kSmtBytes, st>>>(P, canvas, dabs, dab_count, dither, obs, work_counter);
+            composite_kernel<1, true><<<blocks, 32 * kCompWarps, kSmtBytes, st>>>(P, canvas, dabs, dab_count, dither, obs, gauss_tab, work_counter);
         else
-            composite_kernel<3, true><<<blocks, 32 * kCompWarps, kSmtBytes, st>>>(P, canvas, dabs, dab_count, dither, obs, work_counter);
+            composite_kernel<3, true><<<blocks, 32 * kCompWarps, kSmtBytes, st>>>(P, canvas, dabs, dab_count, dither, obs, gauss_tab, work_counter);
         return cudaGetLastError();
     }
     int blocks = (P.B + kCompWarps - 1) / kCompWarps;
     if (blocks > 148 * kCompResident / kCompWarps) blocks = 148 * kCompResident / kCompWarps;   // one resident warp per slot
     if (P.C == 1)
-        composite_kernel<1, false><<<blocks, 32 * kCompWarps, 0, st>>>(P, canvas, dabs, dab_count, dither, obs, work_counter);
+        composite_kernel<1, false><<<blocks, 32 * kCompWarps, 0, st>>>(P, canvas, dabs, dab_count, dither, obs, gauss_tab, work_counter);
     else
-        composite_kernel<3, false><<<blocks, 32 * kCompWarps, 0, st>>>(P, canvas, dabs, dab_count, dither, obs, work_counter);
+        composite_kernel<3, false><<<blocks, 32 * kCompWarps, 0, st>>>(P, canvas, dabs, dab_count, dither, obs, gauss_tab, work_counter);
     return cudaGetLastError();
 }
 // fused small-batch step (SPIRAL_FUSED_STEP_MAX: largest batch that uses it; 0 = never)
@@ -1360,28 +1752,32 @@ cudaError_t launch_step_small(const EnvParams &P, const int32_t *actions, float 
         perm = pm;
     }
     constexpr int kTileBytes = kTile * kTile * 8;
+#define SPIRAL_STEP_SMALL(C_, SMT_, M_, SMEM_) \
+    step_small_kernel<C_, SMT_, M_><<<P.B, 64, SMEM_, st>>>(P, actions, bs, es, dabs, dab_count, status, gauss_tab, canvas, dither, obs, perm)
+    const bool fast = P.math_mode == kMathFast;
     if (smt) {
         static bool attr = false;
         if (!attr) {
-            cudaFuncSetAttribute(step_small_kernel<1, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-            cudaFuncSetAttribute(step_small_kernel<3, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            cudaFuncSetAttribute(step_small_kernel<1, true, kMathDet>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            cudaFuncSetAttribute(step_small_kernel<3, true, kMathDet>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            cudaFuncSetAttribute(step_small_kernel<1, true, kMathFast>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            cudaFuncSetAttribute(step_small_kernel<3, true, kMathFast>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
             attr = true;
         }
-        if (P.C == 1)
-            step_small_kernel<1, true><<<P.B, 64, kTileBytes, st>>>(P, actions, bs, es, dabs, dab_count, status, gauss_tab, canvas, dither, obs, perm);
-        else
-            step_small_kernel<3, true><<<P.B, 64, kTileBytes, st>>>(P, actions, bs, es, dabs, dab_count, status, gauss_tab, canvas, dither, obs, perm);
+        if (P.C == 1) { if (fast) SPIRAL_STEP_SMALL(1, true, kMathFast, kTileBytes); else SPIRAL_STEP_SMALL(1, true, kMathDet, kTileBytes); }
+        else { if (fast) SPIRAL_STEP_SMALL(3, true, kMathFast, kTileBytes); else SPIRAL_STEP_SMALL(3, true, kMathDet, kTileBytes); }
     } else if (P.C == 1) {
-        step_small_kernel<1, false><<<P.B, 64, 0, st>>>(P, actions, bs, es, dabs, dab_count, status, gauss_tab, canvas, dither, obs, perm);
+        if (fast) SPIRAL_STEP_SMALL(1, false, kMathFast, 0); else SPIRAL_STEP_SMALL(1, false, kMathDet, 0);
     } else {
-        step_small_kernel<3, false><<<P.B, 64, 0, st>>>(P, actions, bs, es, dabs, dab_count, status, gauss_tab, canvas, dither, obs, perm);
+        if (fast) SPIRAL_STEP_SMALL(3, false, kMathFast, 0); else SPIRAL_STEP_SMALL(3, false, kMathDet, 0);
     }
+#undef SPIRAL_STEP_SMALL
     return cudaGetLastError();
 }
-cudaError_t launch_debug_dabs(const EnvParams &P, const float *dabs, const int32_t *dab_count,
+cudaError_t launch_debug_dabs(const EnvParams &P, const float *dabs, const int32_t *dab_count, const float *gauss_tab,
                               float *out, int32_t *out_count, cudaStream_t st)
 {
-    debug_dabs_kernel<<<(P.B + 63) / 64, 64, 0, st>>>(P, dabs, dab_count, out, out_count);
+    debug_dabs_kernel<<<(P.B + 63) / 64, 64, 0, st>>>(P, dabs, dab_count, gauss_tab, out, out_count);
     return cudaGetLastError();
 }
 cudaError_t launch_l2_reward(const float *obs, const float *target, float *reward, int batch, int n,
@@ -1393,6 +1789,17 @@ cudaError_t launch_l2_reward(const float *obs, const float *target, float *rewar
 cudaError_t launch_detmath(const double *x, double *e, double *l, int n, cudaStream_t st)
 {
     detmath_kernel<<<(n + 255) / 256, 256, 0, st>>>(x, e, l, n);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_divcheck(unsigned long long seed, long long n, unsigned long long *mismatches, cudaStream_t st)
+{
+    divcheck_kernel<<<148 * 8, 256, 0, st>>>(seed, n, mismatches);
+    return cudaGetLastError();
+}
+cudaError_t launch_fastmath(const float *x, float *e, float *en, float *l, float *h, int n, cudaStream_t st)
+{
+    fastmath_kernel<<<(n + 255) / 256, 256, 0, st>>>(x, e, en, l, h, n);
     return cudaGetLastError();
 }
 

@@ -16,6 +16,7 @@ enum {
     BS_FLAGS,      // int bits: 1 = reset_requested, 2 = settings_value[] initialised
     BS_STEP,       // int: env._step
     BS_RNG_POS,    // int: rng-double stream position (values consumed since the Brush was created)
+    BS_INV_RADIUS, // FAST arithmetic mode: exp(-radius_logarithmic), kept beside BS_ACTUAL_RADIUS
 };
 // env_state double[B,16]
 enum {
@@ -27,6 +28,10 @@ enum {
 // pending dab record float[8]
 enum { DAB_X = 0, DAB_Y, DAB_RLOG, DAB_ACTUAL_RADIUS, DAB_OPAQUE, DAB_HARDNESS, DAB_AA, DAB_HAS_RAND };
 
+// arithmetic of the brush state machine (SpiralEnvCfg.math_mode)
+constexpr int kMathDet = 1;    // detmath.cuh: double-precision exp / log / hypot, bit-exact vs the oracle's PO_MATH_DET
+constexpr int kMathFast = 2;   // fastmath.cuh + restructured binary32 dab loop, bit-exact vs the oracle's PO_MATH_FAST
+
 constexpr int kDyn = 9;
 constexpr int kIn = 3;
 constexpr int kPts = 4;
@@ -37,6 +42,8 @@ struct MapDev {
     float x[kIn][kPts];
     float y[kIn][kPts];
     float inv[kIn][kPts];   // 1/(x[i+1]-x[i]) when that is a power of two (division == multiplication), else 0
+    float slope[kIn][kPts]; // FAST arithmetic mode: segment i is fmaf(slope[i], x, icpt[i])
+    float icpt[kIn][kPts];
 };
 
 struct EnvParams {
@@ -66,6 +73,16 @@ struct EnvParams {
     int fast_spans;              // round upright dabs (ratio 1, sn == 1, |cs| ~ 0): composite may list candidate pixels
     float cull_factor;           // upper bound of radius / ACTUAL_RADIUS (radius_by_random)
     double rng_seed_block[10];   // first output block of rng_double after set_seed(1000)
+    // ---- FAST arithmetic mode (kMathFast) ----
+    int math_mode;               // kMathDet | kMathFast
+    float f_inv_norm01[9];       // 1 / ((float)0.1 * base_radius[i]): events of 0.1 s
+    float f_inv_norm1[9];        // 1 / (1.0f * base_radius[i]): the straight stroke's 1 s event
+    float f_inv_norm001[9];      // 1 / (0.001f * base_radius[i]): step_dtime clamped
+    float f_k_basic[9];          // dabs_per_basic_radius / clamp(base_radius[i])
+    float f_neg_inv_slow[2];     // -1 / speed{1,2}_slowness when that setting has no mapping (else 0)
+    // ---- raw dab hand-off (raw_dab_may_paint) ----
+    float cull_pad[9];           // per size entry: largest position jitter + anti-aliasing fringe + 3 px
+    int zero_pressure_blank;     // 1: a dab of zero pressure has zero opacity (opaque_multiply = 0 + y(pressure), y(0) = 0)
 };
 
 }  // namespace spiral

@@ -13,7 +13,8 @@ Differences from the reference that are part of the contract:
     (all canvases share the episode length, mnist.py:234); ``reward`` is f32[B]
   * the returned ``state`` tensor is the env's observation buffer (overwritten by the next
     step) -- copy it if you keep it (rl_utils does)
-  * targets are synthetic (BASELINE configs; no dataset download): see ``make_synthetic_targets``
+  * targets are synthetic (BASELINE configs; no dataset download): digit-shaped 28x28 -> 64x64 for gray canvases,
+    CelebA-shaped smooth colour fields for RGB ones, seed 7 (``make_synthetic_targets``)
   * EXTENSIONS beyond the reference, flagged in SURVEY.md: ``color_channel=3`` returns
     ``image[..., :3]`` instead of failing; a ``color`` action head; ``location_size=64``
 """
@@ -26,7 +27,7 @@ import torch
 
 from .. import _native as N
 from .. import brush as brushlib
-from . import utils
+from . import targets, utils
 from .base import Environment
 
 
@@ -91,6 +92,12 @@ class MNIST(Environment):
         else:
             self.brushinfo = brushlib.BrushInfo()
         self.max_dabs = int(max_dabs or getattr(args, "max_dabs", 2560))
+        # arithmetic mode of the brush state machine ('det' | 'fast'; SPIRAL_RASTER_MATH overrides the flag: profiling)
+        import os
+        self.raster_math = os.environ.get("SPIRAL_RASTER_MATH") or getattr(args, "raster_math", "det")
+        if self.raster_math not in ("det", "fast"):
+            raise ValueError("raster_math must be 'det' or 'fast', got %r" % (self.raster_math,))
+        self.math_mode = N.MATH_FAST if self.raster_math == "fast" else N.MATH_DET
 
         self._lib = N.lib()
         self._handle = C.c_void_p()
@@ -152,6 +159,7 @@ class MNIST(Environment):
         cfg.brush = self.brushinfo.compile()
         table = brushlib.dither_table()
         C.memmove(cfg.dither_table, table.ctypes.data, table.nbytes)
+        cfg.math_mode = self.math_mode
         return cfg
 
     def __del__(self):
@@ -257,11 +265,13 @@ class MNIST(Environment):
             out = out.squeeze(0)
         return out
 
-    def make_synthetic_targets(self, count=2048, strokes=4, seed=7):
-        """Synthetic stand-in for ``prepare_mnist`` (mnist.py:280-317; no dataset access here):
-        ``count`` stroke drawings rendered with this very renderer -- dark strokes on white,
-        uint8 [count,64,64,C]."""
-        spec_args = self.args
+    def make_synthetic_targets(self, count=2048, seed=7):
+        """Synthetic stand-in for ``prepare_mnist`` (mnist.py:280-317): see ``envs/targets.py``."""
+        return targets.synthetic_targets(self.channels, count=count, seed=seed, size=N.TILE).to(self.device)
+
+    def make_stroke_targets(self, count=2048, strokes=4, seed=7):
+        """Alternative targets that are reachable by construction: ``count`` stroke drawings rendered with this very
+        renderer -- dark strokes on white, uint8 [count,64,64,C]."""
         B = self.num_envs
         g = np.random.RandomState(seed)
         out = []
@@ -279,7 +289,6 @@ class MNIST(Environment):
             done += B
         self.canvas.copy_(saved[0]); self.brush_state.copy_(saved[1]); self.env_state.copy_(saved[2])
         self.obs.copy_(saved[3]); self._step = saved[4]
-        del spec_args
         return torch.cat(out, 0)[:count]
 
     def get_action_desc(self, ac):

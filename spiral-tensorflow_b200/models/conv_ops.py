@@ -20,6 +20,13 @@ from .. import _native as N
 _WS = {}
 
 
+def bn_name(l):
+    """TensorFlow's automatic name of the unnamed tl.batch_normalization after conv<l> (discriminator.py:76-79; layer 0
+    has none): the first one in the scope is 'batch_normalization', then 'batch_normalization_1', ..."""
+    return "batch_normalization" if l == 1 else "batch_normalization_%d" % (l - 1)
+
+
+
 def _workspace(dev, nbytes):
     key = (dev.index, torch.cuda.current_stream(dev).cuda_stream)
     ws = _WS.get(key)
@@ -136,8 +143,8 @@ def disc_forward_native(params, x, layer_num, batch_norm, normalize=True, precis
         if l > 0 and batch_norm:
             mean = x.mean(dim=(0, 1, 2), keepdim=True)
             var = ((x - mean) ** 2).mean(dim=(0, 1, 2), keepdim=True)
-            x = (x - mean) * torch.rsqrt(var + 1e-3) * params["batch_normalization_%d/gamma" % l] \
-                + params["batch_normalization_%d/beta" % l]
+            x = (x - mean) * torch.rsqrt(var + 1e-3) * params[bn_name(l) + "/gamma"] \
+                + params[bn_name(l) + "/beta"]
         x = torch.where(x > 0, x, 0.2 * x)
     logits = (x.flatten(1) @ params["dense/kernel"] + params["dense/bias"]).reshape(-1)
     return torch.sigmoid(logits), logits

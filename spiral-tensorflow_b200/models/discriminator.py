@@ -78,8 +78,8 @@ class Discriminator(object):
             p["conv%d/kernel" % l] = (torch.randn((5, 5, cin, cout), generator=g) * std)
             p["conv%d/bias" % l] = torch.zeros((cout,))
             if l > 0 and self.batch_norm:
-                p["batch_normalization_%d/gamma" % l] = torch.ones((cout,))
-                p["batch_normalization_%d/beta" % l] = torch.zeros((cout,))
+                p[conv_ops.bn_name(l) + "/gamma"] = torch.ones((cout,))
+                p[conv_ops.bn_name(l) + "/beta"] = torch.zeros((cout,))
             cin = cout
         p["dense/kernel"] = torch.randn((cin, 1), generator=g) * math.sqrt(2.0 / (cin + 1))
         p["dense/bias"] = torch.zeros((1,))
@@ -88,7 +88,10 @@ class Discriminator(object):
     def load_numpy(self, weights):
         """weights: dict in the oracle's naming (conv%d/kernel, bn%d/gamma, dense/kernel ...)."""
         for k, v in weights.items():
-            name = k.replace("bn", "batch_normalization_") if k.startswith("bn") else k
+            name = k
+            if k.startswith("bn"):                    # oracle naming bn<l>/gamma -> TF's automatic layer names
+                l, leaf = k[2:].split("/")
+                name = conv_ops.bn_name(int(l)) + "/" + leaf
             self.params[name].copy_(torch.as_tensor(np.asarray(v)).to(self.params[name]))
         self.sync_weights()
 
@@ -99,8 +102,8 @@ class Discriminator(object):
             w.conv_w[l] = self.params["conv%d/kernel" % l].data_ptr()
             w.conv_b[l] = self.params["conv%d/bias" % l].data_ptr()
             if l > 0 and self.batch_norm:
-                w.bn_gamma[l] = self.params["batch_normalization_%d/gamma" % l].data_ptr()
-                w.bn_beta[l] = self.params["batch_normalization_%d/beta" % l].data_ptr()
+                w.bn_gamma[l] = self.params[conv_ops.bn_name(l) + "/gamma"].data_ptr()
+                w.bn_beta[l] = self.params[conv_ops.bn_name(l) + "/beta"].data_ptr()
         w.dense_w = self.params["dense/kernel"].data_ptr()
         w.dense_b = self.params["dense/bias"].data_ptr()
         N.check(self._lib.spiral_disc_load_weights(self._handle, C.byref(w), N.ptr(self.workspace), N.stream_ptr()),

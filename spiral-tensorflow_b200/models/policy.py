@@ -152,18 +152,33 @@ class Policy(nn.Module):
         for idx, name in enumerate(self.acs):
             size = self.action_sizes[name]
             if len(size) == 1:
-                head = nn.Linear(self.lstm_size, size[0])
-                with torch.no_grad():                                  # normalized_columns_initializer(0.01)
-                    w = torch.randn_like(head.weight)
-                    head.weight.copy_(w * 0.01 / w.pow(2).sum(1, keepdim=True).sqrt())
-                    head.bias.zero_()
-                self.heads[name] = head
+                self.heads[name] = nn.Linear(self.lstm_size, size[0])
             else:
                 self.heads[name] = _LocationHead(self.lstm_size, size[0], n_res)
             if idx < len(self.acs) - 1:
                 self.sample_mlp[name] = _MLP(1, 16)
                 self.concat_z_fc[name] = nn.Linear(self.lstm_size + 16, self.lstm_size)
         self.value = nn.Linear(self.lstm_size, 1)
+        self.reset_parameters_tf()
+
+    @torch.no_grad()
+    def reset_parameters_tf(self):
+        """The reference's initial weights: tf.layers.dense / conv2d / conv2d_transpose and BasicLSTMCell create their
+        kernels with the variable scope's default initializer, glorot_uniform (limit sqrt(6 / (fan_in + fan_out)) with
+        TF's fan convention: receptive field x channels), and their biases with zeros; only the scalar action heads use
+        normalized_columns_initializer(0.01) (policy.py:231-236, 370-375: a normal draw rescaled so that every output
+        unit's weight vector has norm 0.01).  PyTorch's defaults (kaiming-uniform(a=sqrt 5) kernels, uniform biases) give
+        other initial logits and value scales."""
+        for m in self.modules():
+            if isinstance(m, (nn.Linear, nn.Conv2d, nn.ConvTranspose2d)):
+                nn.init.xavier_uniform_(m.weight)           # same fan_in + fan_out as TF for all three kernel layouts
+                if m.bias is not None:
+                    m.bias.zero_()
+        for name in self.acs:
+            head = self.heads[name]
+            if isinstance(head, nn.Linear):
+                w = torch.randn_like(head.weight)           # TF kernel [in, out], normalised over axis 0 = per output unit
+                head.weight.copy_(w * 0.01 / w.pow(2).sum(1, keepdim=True).sqrt())
 
     # ------------------------------------------------------------------
     def get_initial_features(self, batch_size, flat=False, device=None):

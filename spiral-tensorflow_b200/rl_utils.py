@@ -16,6 +16,19 @@ from . import _native as N
 
 Batch = namedtuple("Batch", ["si", "a", "adv", "r", "features", "c", "z"])
 
+_SCRATCH = {}
+
+
+def _scratch(name, shape, dtype, device, zero=False):
+    """Per-(name, shape, device) scratch tensor, allocated once: nothing is allocated on the step path (DESIGN.md 3);
+    the kernels overwrite it on every call."""
+    key = (name, tuple(shape), dtype, str(device))
+    t = _SCRATCH.get(key)
+    if t is None:
+        t = (torch.zeros if zero else torch.empty)(shape, dtype=dtype, device=device)
+        _SCRATCH[key] = t
+    return t
+
 
 def discount(x, gamma):
     """Reverse discounted cumulative sum along axis 1 (reference rl_utils.py:18-20), numpy."""
@@ -25,6 +38,49 @@ def discount(x, gamma):
     for t in range(x.shape[1] - 1, -1, -1):
         acc = x[:, t] + gamma * acc
         out[:, t] = acc
+    return out
+
+
+@torch.no_grad()
+def batched_env_runner(env, act, lstm_state, initial_action, lstm_size, state_dtype=torch.float32,
+                       target=None, z=None, generator=None):
+    """One pass of the body of ``env_runner``'s ``while True`` (reference rl_utils.py:190-238) for B envs at once.
+
+    ``act(state, last_action, c, h, condition, z, generator) -> (action [B,K], value [B], c, h)`` is ``policy.act``.
+    ``lstm_state`` [B, 2, lstm] = (c, h) is the actors' ``last_features``: the reference fetches
+    ``policy.get_initial_features`` once, BEFORE the loop (:186-187), so the state at the end of an episode is the state
+    the next episode starts from -- it is read here and written back in place.  ``PartialRollout.add`` (:205-206) stores
+    the features the step started from, so ``features[:, t]`` is the state BEFORE step t (the learner feeds
+    ``features[:, 0]``, :42); ``states`` gets the final state appended (:232).  The reference resets the env after the
+    episode (:222); here the episode starts with the reset, which is the same sequence one call later."""
+    T, B = env.episode_length, env.num_envs
+    state, condition, z = env.reset(target=target, z=z)
+    dev = state.device
+    c, h = lstm_state[:, 0], lstm_state[:, 1]
+    last_action = initial_action
+    states = torch.empty((B, T + 1) + tuple(state.shape[1:]), dtype=state_dtype, device=dev)
+    actions = torch.empty((B, T, len(env.acs)), dtype=torch.int32, device=dev)
+    rewards = torch.zeros((B, T), device=dev)
+    values = torch.zeros((B, T, 1), device=dev)
+    features = torch.empty((B, T, 2, lstm_size), device=dev)
+    for t in range(T):
+        states[:, t] = state
+        features[:, t, 0] = c
+        features[:, t, 1] = h
+        action, value, c, h = act(state, last_action, c, h, condition, z, generator)
+        state, reward, terminal, _ = env.step(action)
+        actions[:, t] = action
+        rewards[:, t] = reward
+        values[:, t, 0] = value
+        last_action = action
+    states[:, T] = state
+    lstm_state[:, 0] = c
+    lstm_state[:, 1] = h
+    out = dict(states=states, actions=actions, rewards=rewards, values=values, features=features)
+    if condition is not None:
+        out["conditions"] = condition.unsqueeze(1).expand((B, T) + tuple(condition.shape[1:]))
+    else:
+        out["z"] = z.unsqueeze(1).expand(B, T, z.shape[-1])
     return out
 
 
@@ -64,7 +120,7 @@ def a2c_loss(logits, actions, rewards, values, vf, gamma=0.99, lambda_=1.0, entr
         res.dlogits = [torch.empty_like(l) for l in logits] if want_grads else None
         res.dvf = torch.empty((B, T), dtype=torch.float32, device=dev) if want_grads else None
         res.pi_loss = res.vf_loss = res.entropy = res.total = None
-    partial = torch.empty((B * T * 4 + 2048,), dtype=torch.float32, device=dev)
+    partial = _scratch("a2c_partial", (B * T * 4 + 2048,), torch.float32, dev)
     lp = (C.c_void_p * K)(*[l.data_ptr() for l in logits])
     sizes = (C.c_int32 * K)(*[int(l.shape[2]) for l in logits])
     dp = (C.c_void_p * K)(*[d.data_ptr() for d in res.dlogits]) if want_grads else None
@@ -108,13 +164,13 @@ def multiple_process_rollout(rollout, gamma, lambda_=1.0):
     values = rollout['values'][:, :, 0].to(torch.float32).contiguous()
     B, T = rewards.shape
     dev = rewards.device
-    adv = torch.empty((B, T), dtype=torch.float32, device=dev)
+    adv = torch.empty((B, T), dtype=torch.float32, device=dev)       # returned to the caller: the only allocations here
     ret = torch.empty((B, T), dtype=torch.float32, device=dev)
     # reuse the fused entry point with a dummy 1-logit head to get (adv, r) only
-    dummy = torch.zeros((B, T, 1), dtype=torch.float32, device=dev)
-    acts = torch.zeros((B, T, 1), dtype=torch.int32, device=dev)
-    scal = torch.empty((4,), dtype=torch.float32, device=dev)
-    partial = torch.empty((B * T * 4 + 2048,), dtype=torch.float32, device=dev)
+    dummy = _scratch("mpr_dummy", (B, T, 1), torch.float32, dev, zero=True)
+    acts = _scratch("mpr_acts", (B, T, 1), torch.int32, dev, zero=True)
+    scal = _scratch("mpr_scal", (4,), torch.float32, dev)
+    partial = _scratch("a2c_partial", (B * T * 4 + 2048,), torch.float32, dev)
     lp = (C.c_void_p * 1)(dummy.data_ptr())
     sizes = (C.c_int32 * 1)(1)
     N.check(lib.spiral_a2c_loss(lp, sizes, 1, N.ptr(acts), N.ptr(rewards), N.ptr(values), N.ptr(values), B, T,

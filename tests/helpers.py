@@ -9,10 +9,11 @@ ENV_OF = {"simple_mnist": ["jump", "control", "end"],
           "color_mnist": ["control", "end", "color", "jump", "pressure", "size"]}
 
 
-def make_args(env="simple_mnist", L=32, C=1, T=5, conditional=False, jump=True, curve=True, extra=()):
+def make_args(env="simple_mnist", L=32, C=1, T=5, conditional=False, jump=True, curve=True, extra=(), math="det"):
     import spiral_b200 as sp
     argv = ["--env", env, "--location_size", str(L), "--color_channel", str(C), "--episode_length", str(T),
-            "--loss", "l2" if conditional else "gan", "--jump", str(jump), "--curve", str(curve)] + list(extra)
+            "--loss", "l2" if conditional else "gan", "--jump", str(jump), "--curve", str(curve),
+            "--raster_math", math] + list(extra)
     return sp.get_args(argv)
 
 
@@ -24,8 +25,11 @@ def random_actions(env, B, T, seed=0, jump_prob=None):
     return a
 
 
-def oracle_for(env, B, math_mode=1):
+def oracle_for(env, B, math_mode=None):
+    """The CPU oracle in the arithmetic mode the env's kernels reproduce bit for bit (det -> PO_MATH_DET, fast -> PO_MATH_FAST)."""
     from oracle import paint_oracle as po
+    if math_mode is None:
+        math_mode = po.PO_MATH_FAST if getattr(env, "raster_math", "det") == "fast" else po.PO_MATH_DET
     spec = po.EnvSpec(action_names=list(env.acs), location_size=env.location_size,
                       n_color=len(env.colors), colorize=env.colorize, math_mode=math_mode)
     return po.OracleBatchEnv(spec, B, channels=env.channels)

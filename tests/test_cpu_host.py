@@ -293,3 +293,111 @@ def test_replay_buffer_follows_the_reference_push_semantics():
     empty = rb.ReplayBuffer(args, shape, device="cpu")
     with pytest.raises(RuntimeError):
         empty.sample(4)
+
+
+def test_batched_env_runner_follows_the_reference_env_runner():
+    """rl_utils.batched_env_runner against a literal restatement of the reference's env_runner / PartialRollout
+    (rl_utils.py:60-95, 185-238) run once per env: the LSTM features are fetched once before the loop and carried over
+    from episode to episode, ``features[t]`` is the state BEFORE step t, ``states`` has the final state appended,
+    ``last_action`` restarts from ``env.initial_action`` every episode."""
+    rl = _mod("rl_utils")
+    B, T, K, H = 3, 4, 2, 5
+
+    class OneEnv(object):                       # a deterministic stand-in for envs/mnist.py: one canvas
+        def __init__(self, b):
+            self.b, self.t, self.ep = b, 0, 0
+            self.episode_length, self.acs = T, ["a", "b"]
+            self.initial_action = [-1] * K
+
+        def reset(self):
+            self.t = 0
+            self.ep += 1
+            self.obs = np.full((2, 2, 1), 10.0 * self.ep + self.b, np.float32)
+            return self.obs, None, np.full((3,), 0.1 * self.ep + self.b, np.float32)
+
+        def step(self, action):
+            self.t += 1
+            self.obs = self.obs + float(sum(action)) + 1.0
+            return self.obs, 0.25 * self.t + self.b, self.t == T, {}
+
+    def act_one(state, last_action, c, h, condition, z):      # policy.act: any deterministic function of its inputs
+        s = float(np.mean(state)) + float(np.sum(last_action)) + float(np.sum(z))
+        action = [int(abs(s) + float(np.sum(c))) % 3, int(abs(s) + float(np.sum(h))) % 5]
+        return action, 0.5 * s + float(np.sum(h)), c * 0.5 + s * 1e-3, h * 0.25 + np.tanh(c + s * 1e-3)
+
+    def reference_env_runner(env, episodes):                  # rl_utils.py:185-238, literally
+        out = []
+        last_state, condition, z = env.reset()
+        last_features = (np.zeros(H, np.float32), np.zeros(H, np.float32))      # policy.get_initial_features
+        for _ in range(episodes):
+            ro = dict(states=[], actions=[], rewards=[], values=[], features=[], z=[])
+            last_action = env.initial_action
+            for _ in range(T):
+                c, h = last_features
+                action, value_, nc, nh = act_one(last_state, last_action, c, h, condition, z)
+                state, reward, terminal, info = env.step(action)
+                ro["states"] += [last_state]; ro["actions"] += [action]; ro["rewards"] += [reward]
+                ro["values"] += [value_]; ro["features"] += [last_features]; ro["z"] += [z]
+                last_state, last_action, last_features = state, action, (nc, nh)
+            last_state, condition, z = env.reset()
+            ro["states"] += [state]
+            out.append(ro)
+        return out
+
+    want = [reference_env_runner(OneEnv(b), 3) for b in range(B)]
+
+    class BatchEnv(object):                     # the same envs behind the batched API
+        def __init__(self):
+            self.envs = [OneEnv(b) for b in range(B)]
+            self.episode_length, self.num_envs, self.acs = T, B, ["a", "b"]
+
+        def reset(self, target=None, z=None):
+            r = [e.reset() for e in self.envs]
+            return torch.tensor(np.stack([x[0] for x in r])), None, torch.tensor(np.stack([x[2] for x in r]))
+
+        def step(self, action):
+            r = [e.step([int(v) for v in action[b]]) for b, e in enumerate(self.envs)]
+            return torch.tensor(np.stack([x[0] for x in r])), torch.tensor([x[1] for x in r]), r[0][2], {}
+
+    def act_batch(state, last_action, c, h, condition, z, generator):
+        r = [act_one(state[b].numpy(), [int(v) for v in last_action[b]], c[b].numpy(), h[b].numpy(), None, z[b].numpy())
+             for b in range(B)]
+        return (torch.tensor([x[0] for x in r], dtype=torch.int32), torch.tensor([x[1] for x in r]),
+                torch.tensor(np.stack([x[2] for x in r])), torch.tensor(np.stack([x[3] for x in r])))
+
+    env = BatchEnv()
+    lstm_state = torch.zeros((B, 2, H))
+    init = torch.full((B, K), -1, dtype=torch.int32)
+    for ep in range(3):
+        got = rl.batched_env_runner(env, act_batch, lstm_state, init, H)
+        for b in range(B):
+            w = want[b][ep]
+            assert np.allclose(got["states"][b].numpy(), np.stack(w["states"]))
+            assert (got["actions"][b].numpy() == np.array(w["actions"])).all()
+            assert np.allclose(got["rewards"][b].numpy(), w["rewards"]) and np.allclose(got["values"][b, :, 0].numpy(), w["values"])
+            assert np.allclose(got["features"][b, :, 0].numpy(), np.stack([f[0] for f in w["features"]]), atol=1e-6)
+            assert np.allclose(got["features"][b, :, 1].numpy(), np.stack([f[1] for f in w["features"]]), atol=1e-6)
+            assert np.allclose(got["z"][b].numpy(), np.stack(w["z"]))
+        if ep > 0:
+            assert float(got["features"][:, 0].abs().max()) > 0      # the carried-over state, not zeros
+
+
+def test_synthetic_targets_have_the_named_shapes():
+    """SURVEY 8d / BASELINE configs: digit-shaped 28x28 -> 64x64 targets for gray canvases (dark strokes on white, like
+    255 - resized MNIST, mnist.py:303-317), CelebA-shaped smooth colour fields for RGB ones; uint8, seed 7, deterministic."""
+    tg = _mod("envs.targets")
+    d = tg.synthetic_targets(1, count=64, seed=7)
+    assert d.shape == (64, 64, 64, 1) and d.dtype == torch.uint8
+    assert torch.equal(d, tg.synthetic_targets(1, count=64, seed=7))
+    assert not torch.equal(d, tg.synthetic_targets(1, count=64, seed=8))
+    f = d.float()
+    assert float((f > 250).float().mean()) > 0.5 and float(f.min()) < 30       # white paper, dark pen
+    ink = (f < 128).float().mean((1, 2, 3))
+    assert float(ink.min()) > 0.005 and float(ink.max()) < 0.35                # every image has a stroke, none is a blob
+    c = tg.synthetic_targets(3, count=32, seed=7)
+    assert c.shape == (32, 64, 64, 3) and c.dtype == torch.uint8
+    cf = c.float()
+    assert float(cf.min()) == 0.0 and float(cf.max()) >= 254.0
+    # smooth: neighbouring pixels differ by a few grey levels, channels are correlated but not identical
+    assert float((cf[:, 1:] - cf[:, :-1]).abs().mean()) < 8.0
+    assert float((cf[..., 0] - cf[..., 1]).abs().mean()) > 1.0

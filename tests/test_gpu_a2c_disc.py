@@ -164,3 +164,55 @@ def test_discriminator_forward_matches_oracle(C, dd, bn, B, prec):
             rt = 5e-2 if prec == "bf16" else 1e-3
             assert np.allclose(got[l, 0, :n], m.numpy(), rtol=rt, atol=rt * 0.1), l
             assert np.allclose(got[l, 1, :n], v.numpy(), rtol=rt, atol=rt * 0.01), l
+
+
+def _canvas_like(B, C, seed):
+    g = torch.Generator(device="cuda")
+    g.manual_seed(seed)
+    imgs = torch.full((B, 64, 64, C), 255.0, device="cuda")
+    ys = torch.randint(0, 56, (B, 6), generator=g, device="cuda")
+    xs = torch.randint(0, 56, (B, 6), generator=g, device="cuda")
+    vals = torch.randint(0, 255, (B, 6, C), generator=g, device="cuda").float()
+    yy = torch.arange(64, device="cuda")[None, :, None]
+    xx = torch.arange(64, device="cuda")[None, None, :]
+    for k in range(6):
+        m = ((yy >= ys[:, k, None, None]) & (yy < ys[:, k, None, None] + 8) &
+             (xx >= xs[:, k, None, None]) & (xx < xs[:, k, None, None] + 8))
+        imgs = torch.where(m[..., None], vals[:, k, None, None, :], imgs)
+    return imgs.contiguous()
+
+
+def test_discriminator_large_batch_tensor_core_path_vs_fp32_and_oracle():
+    """The reward forward at a batch the bench scores in one call (4,096 images, rgb64 shape, disc_dim 64): the
+    tcgen05 bf16x3 path -- persistent CTAs walking hundreds of tiles, position-pure tiles on the small maps, the pair
+    schedule -- against (a) the fp32 SIMT kernels on the same batch with training-mode batch norm (statistics over all
+    4,096 images), and (b) the float64 oracle on a 512-image batch with batch norm off (per-image, so a slice is exact)."""
+    sp = _sp()
+    from oracle import disc_oracle as do
+    from importlib import import_module
+    models = import_module(sp.__name__ + ".models")
+    B, C, dd = 4096, 3, 64
+    imgs = _canvas_like(B, C, seed=9)
+    w = do.init_weights(C, disc_dim=dd, batch_norm=True, seed=5)
+    out = {}
+    for prec in ("fp32", "bf16x3"):
+        args = sp.get_args(["--color_channel", str(C), "--disc_dim", str(dd), "--disc_batch_norm", "True", "--disc_precision", prec])
+        D = models.Discriminator(args, None, [64, 64, C], norm_fn=lambda x: x, scope_name="global", max_batch=B)
+        D.load_numpy(w)
+        p, l = D.forward(imgs)
+        out[prec] = (p.cpu().numpy().copy(), l.cpu().numpy().copy(), D.bn_stats.cpu().numpy().copy())
+        del D
+    scale = max(1.0, np.abs(out["fp32"][1]).max())
+    assert np.abs(out["bf16x3"][1] - out["fp32"][1]).max() <= 1e-4 * scale
+    assert np.abs(out["bf16x3"][0] - out["fp32"][0]).max() <= 1e-4
+    assert np.allclose(out["bf16x3"][2], out["fp32"][2], rtol=1e-3, atol=1e-4)
+    # (b) batch norm off: every image is scored on its own, so 512 images against the float64 oracle
+    n = 512
+    w0 = do.init_weights(C, disc_dim=dd, batch_norm=False, seed=6)
+    args = sp.get_args(["--color_channel", str(C), "--disc_dim", str(dd), "--disc_batch_norm", "False", "--disc_precision", "bf16x3"])
+    D = models.Discriminator(args, None, [64, 64, C], norm_fn=lambda x: x, scope_name="global", max_batch=n)
+    D.load_numpy(w0)
+    p, l = D.forward(imgs[:n])
+    want_p, want_l = do.predict(imgs[:n].cpu().numpy(), w0, batch_norm=False, dtype=torch.float64)
+    assert np.abs(l.cpu().numpy() - want_l).max() <= 1e-4 * max(1.0, np.abs(want_l).max())
+    assert np.abs(p.cpu().numpy() - want_p).max() <= 1e-4

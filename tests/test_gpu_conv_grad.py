@@ -121,7 +121,7 @@ def test_wgan_gp_step_matches_oracle(C, dd, bn, B, prec, cond):
     for k in ("d_loss", "critic_loss", "gradient_penalty", "g_loss"):
         assert abs(float(out[k]) - want[k]) <= 1e-4 * max(1.0, abs(want[k])), (k, float(out[k]), want[k])
     for k, gref in want["grads"].items():
-        name = k.replace("bn", "batch_normalization_") if k.startswith("bn") else k
+        name = (("batch_normalization" if k[2] == "1" else "batch_normalization_%d" % (int(k[2]) - 1)) + k[3:]) if k.startswith("bn") else k
         got = D.params[name].grad.cpu().numpy()
         if np.abs(gref).max() < 1e-9:        # a conv bias in front of a batch norm: exactly zero gradient
             assert np.abs(got).max() < 1e-5, k

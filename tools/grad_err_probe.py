@@ -30,7 +30,7 @@ for prec in ("fp32", "bf16x6", "bf16x3", "bf16"):
     out["d_loss"].backward()
     print(prec, "d_loss %.6f (want %.6f) gp %.6f (want %.6f)" % (float(out["d_loss"]), want["d_loss"], float(out["gradient_penalty"]), want["gradient_penalty"]))
     for k, g in want["grads"].items():
-        name = k.replace("bn", "batch_normalization_") if k.startswith("bn") else k
+        name = (("batch_normalization" if k[2] == "1" else "batch_normalization_%d" % (int(k[2]) - 1)) + k[3:]) if k.startswith("bn") else k
         got = D.params[name].grad.cpu().numpy().astype(np.float64)
         if np.abs(g).max() < 1e-9:
             continue

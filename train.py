@@ -40,11 +40,20 @@ def main(argv=None):
     torch.cuda.set_device(local)
     torch.manual_seed(0)                                     # identical initial weights on every rank
     args = sp.get_args(argv)
+    if args.env == "simple":
+        raise SystemExit("train.py drives the batched GPU loop; --env simple is the reference's CPU / PIL debug env "
+                         "(BASELINE configs[0]) and has no device path -- step it directly (spiral_b200.create_env)")
+    load_path = str(getattr(args, "load_path", "") or "")
+    if load_path and os.path.isdir(load_path) and os.path.exists(os.path.join(load_path, ck.PARAM_FNAME)) \
+            and ck.latest_checkpoint(load_path):
+        changed = ck.load_args(args, load_path)              # utils/train.py:97-120: a resumed run keeps the saved flags
+        if changed and rank == 0:
+            print(json.dumps({"resumed_flags": {k: list(map(str, v)) for k, v in changed.items()}}), flush=True)
     args.seed = int(args.seed) + rank                        # main.py:21: seed + task index for the actors
     _, count = du.shard(opts["--num_envs"], rank, world)
     env = sp.create_env(args, num_envs=count, device=torch.device("cuda", local))
     agent = agent_mod.Agent(args, env)
-    load_path = str(getattr(args, "load_path", "") or os.path.join("logs", "%s_%s" % (args.env, time.strftime("%Y-%m-%d_%H-%M-%S"))))
+    load_path = load_path or os.path.join("logs", "%s_%s" % (args.env, time.strftime("%Y-%m-%d_%H-%M-%S")))
     step = 0
     if os.path.isdir(load_path) and ck.latest_checkpoint(load_path):
         step = ck.load_checkpoint(agent, load_path)          # every rank restores the same file
@@ -56,7 +65,12 @@ def main(argv=None):
         m = agent.train_policy(ro)
         if agent.gan:
             m.update(agent.train_gan())
-        if rank == 0 and ((it + 1) % max(1, int(args.policy_log_step)) == 0 or it + 1 == opts["--max_iters"]):
+        log_now = (it + 1) % max(1, int(args.policy_log_step)) == 0 or it + 1 == opts["--max_iters"]
+        if log_now:
+            # every rank: a pending-dab overflow or an RNG-table overrun truncates strokes silently on the device; the
+            # flag is read here (a synchronising read, at the logging cadence) and raises
+            env.check_status()
+        if rank == 0 and log_now:
             line = {k: (float(v) if torch.is_tensor(v) else v) for k, v in m.items()}
             line.update(iter=it + 1, env_steps=(it + 1 - step) * opts["--num_envs"] * env.episode_length,
                         seconds=round(time.time() - t0, 2))
