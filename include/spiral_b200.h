@@ -238,6 +238,17 @@ int spiral_disc_load_weights(SpiralDisc *d, const SpiralDiscWeights *w, void *wo
 int spiral_disc_forward(SpiralDisc *d, const float *x_dev, int32_t batch, float *logits_dev,
                         float *probs_dev, float *bn_stats_dev, void *workspace_dev, void *stream);
 
+/* The same forward in stages, for GLOBAL-BATCH batch norm over ranks: models/discriminator.py:76-79 normalises with the
+ * statistics of the batch it is fed, so a batch sharded over GPUs scores like the gathered batch when every layer's
+ * per-channel (sum x, sum x^2) is summed over the ranks before it is used.  Call stage = 0, 1, ..., 5 in order on the same
+ * workspace: stage s >= 1 first finishes layer s's batch norm from sums_dev (f64 [Cout_s][2], as left by stage s-1 and
+ * all-reduced by the caller -- NCCL sum) with global_count = the summed number of elements per channel (sum over ranks of
+ * batch * (32 >> s)^2), then runs layer s+1 and leaves ITS sums in sums_dev; stage 0 runs layers 0 and 1; stage 5
+ * finishes layer 5 and writes logits / probs.  One rank without all-reduce == spiral_disc_forward, bit for bit. */
+int spiral_disc_forward_staged(SpiralDisc *d, const float *x_dev, int32_t batch, int32_t stage, double global_count,
+                               double *sums_dev, float *logits_dev, float *probs_dev, float *bn_stats_dev,
+                               void *workspace_dev, void *stream);
+
 /* ------------------------------------------------------------------ */
 /* Convolution layer and its gradients (K2b)                            */
 /* replaces: what tf.gradients(d_loss) executes for                     */

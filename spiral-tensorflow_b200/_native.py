@@ -98,6 +98,7 @@ SYMBOLS = {
     "spiral_disc_workspace_bytes": (C.c_int64, [_vp, C.c_int32]),
     "spiral_disc_load_weights": (C.c_int, [_vp, C.POINTER(SpiralDiscWeights), _vp, _vp]),
     "spiral_disc_forward": (C.c_int, [_vp, _vp, C.c_int32, _vp, _vp, _vp, _vp, _vp]),
+    "spiral_disc_forward_staged": (C.c_int, [_vp, _vp, C.c_int32, C.c_int32, C.c_double, _vp, _vp, _vp, _vp, _vp, _vp]),
     "spiral_categorical_sample": (C.c_int, [_vp, C.c_int32, C.c_int32, C.c_uint64, C.c_uint64, _vp, _vp, _vp]),
     "spiral_debug_philox": (C.c_int, [C.POINTER(C.c_uint32), _vp, _vp]),
     "spiral_grad_global_norm": (C.c_int, [C.POINTER(_vp), C.POINTER(C.c_int64), C.c_int32, _vp, _vp, _vp]),

@@ -6,7 +6,7 @@ one process per GPU owns B canvases; a step of the loop is
 
     rollout()        rl_utils.py:185-238   policy.act -> env.step, T times, everything on the GPU
     train_policy()   agent.py:333-403      GAN reward (K2) -> fused A2C loss (K3) -> backward through
-                                           the PyTorch policy -> all-reduce -> clip 40 -> Adam
+                                           the PyTorch policy -> all-reduce (overlapped, GradReducer) -> clip 40 -> Adam
     train_gan()      agent.py:409-437      WGAN-GP step on (replay fakes, real targets)
 
 The three kernel families of the north-star path are native, including the discriminator's
@@ -61,10 +61,31 @@ class Agent(object):
         # trajectory store: observations are integers 0..255 when color_channel == 3 (read-back of the uint8 image), so
         # `states` is kept as uint8 (4x smaller: 252 MB instead of 1.03 GB at 1,024 canvases x 21 frames, lossless); gray
         # observations are BT.601 dot products (non-integers) and stay float32 as in the reference's queue (agent.py:42-47)
+        # several ranks: gradients accumulate into one flat buffer per network and are all-reduced bucket by bucket from
+        # backward hooks, overlapping the rest of the backward (distributed.GradReducer); SPIRAL_GRAD_REDUCER=1 uses the
+        # same path on one rank (tests)
+        import os
+        use_red = self.device.type == "cuda" and (self.world > 1 or os.environ.get("SPIRAL_GRAD_REDUCER") == "1")
+        self._pol_red = dist_utils.GradReducer(self.policy.parameters(), world=self.world) if use_red else None
+        self._disc_red = dist_utils.GradReducer(list(self.disc.params.values()), world=self.world) if (use_red and self.gan) else None
+        self._global_bn = dist_utils.allreduce_bn_sums_ if (self.world > 1 and getattr(args, "disc_global_bn", False)) else None
         self.state_dtype = torch.uint8 if (int(getattr(env, "channels", 1)) == 3 and getattr(args, "traj_uint8", True)) else torch.float32
         self._graph, self._graph_failed, self._g_out, self._g_target, self._g_z = None, False, {}, None, None
         self._tp_graph, self._tp_failed, self._tp_calls, self._tp_in, self._tp_out = None, False, 0, None, None
         self._tg_graph, self._tg_failed, self._tg_calls, self._tg_in, self._tg_out = None, False, 0, None, None
+
+    def close(self):
+        """Drop the captured CUDA graphs.  With several ranks the learner graphs hold NCCL collectives: they must be gone
+        (and the device idle) before ``torch.distributed.destroy_process_group()``, which otherwise waits forever for the
+        communicator the graphs still reference."""
+        if self.device.type == "cuda":
+            torch.cuda.synchronize()
+        self._graph = self._tp_graph = self._tg_graph = None
+        self._g_out, self._tp_out, self._tg_out = {}, None, None
+        import gc
+        gc.collect()
+        if self.device.type == "cuda":
+            torch.cuda.synchronize()
 
     # ------------------------------------------------------------------
     @torch.no_grad()
@@ -141,7 +162,7 @@ class Agent(object):
         if self.gan:
             with torch.no_grad():
                 self.disc.sync_weights()
-                rollout["rewards"][:, -1] = self.disc.predict(rollout["states"][:, -1])       # agent.py:336-338
+                rollout["rewards"][:, -1] = self.disc.predict(rollout["states"][:, -1], global_bn=self._global_bn)   # agent.py:336-338
         # several ranks: the NCCL all-reduce is captured into the graph with the rest of the step (every rank replays the
         # same sequence of collectives)
         use_graph = getattr(self.args, "cuda_graphs", True) and self.device.type == "cuda" and not self._tp_failed
@@ -160,7 +181,8 @@ class Agent(object):
         if self._tp_graph is None:
             try:
                 self._tp_in = {k: rollout[k].clone() for k in keys}
-                self.policy_opt.zero_grad(set_to_none=True)
+                if self._pol_red is None:
+                    self.policy_opt.zero_grad(set_to_none=True)
                 torch.cuda.synchronize()
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g):
@@ -190,10 +212,13 @@ class Agent(object):
                               rollout.get("conditions"), rollout.get("z"), samples)
         loss = rl_utils.a2c_loss_autograd([logits[n].contiguous() for n in pi.acs], acts, rollout["rewards"],
                                           rollout["values"][:, :, 0], vf, 0.99, 1.0, args.entropy_coeff)
-        self.policy_opt.zero_grad(set_to_none=True)
-        loss.backward()
-        grads = [p.grad for p in pi.parameters() if p.grad is not None]
-        dist_utils.allreduce_grads_(grads, self.world, average=False)                         # sum; 1/world is folded into K5
+        if self._pol_red is not None:
+            self._pol_red.zero()                          # gradients accumulate into the flat buffer ...
+            loss.backward()                               # ... whose buckets are all-reduced from backward hooks as they fill
+            self._pol_red.wait()                          # sum over ranks; 1/world is folded into K5
+        else:
+            self.policy_opt.zero_grad(set_to_none=True)
+            loss.backward()
         gnorm = self.policy_opt.step(clip_norm=float(args.grad_clip), grad_scale=1.0 / self.world, advance=advance)   # agent.py:231-239
         if self.actor is not None:
             self.actor.sync()                             # actors pull the new weights (trainer.py:117 policy_sync)
@@ -225,7 +250,8 @@ class Agent(object):
         if self._tg_graph is None:
             try:
                 self._tg_in = [t.to(self.device, torch.float32).clone() for t in (fake, real, alpha)]
-                self.disc_opt.zero_grad(set_to_none=True)
+                if self._disc_red is None:
+                    self.disc_opt.zero_grad(set_to_none=True)
                 torch.cuda.synchronize()
                 g = torch.cuda.CUDAGraph()
                 with torch.cuda.graph(g):
@@ -248,9 +274,13 @@ class Agent(object):
         p = D.params
         out = D.wgan_gp_loss(fake, real, alpha)          # convolutions + every gradient on K2b
         d_loss, critic, gp, fake_logits_mean = out["d_loss"], out["critic_loss"], out["gradient_penalty"], -out["g_loss"]
-        self.disc_opt.zero_grad(set_to_none=True)
-        d_loss.backward()
-        dist_utils.allreduce_grads_([q.grad for q in p.values() if q.grad is not None], self.world, average=False)
+        if self._disc_red is not None:
+            self._disc_red.zero()
+            d_loss.backward()
+            self._disc_red.wait()
+        else:
+            self.disc_opt.zero_grad(set_to_none=True)
+            d_loss.backward()
         self.disc_opt.step(grad_scale=1.0 / self.world, advance=advance)                      # discriminator.py:124-126
         D.sync_weights()
         return {"gan/critic_loss": critic.detach(), "gan/disc_loss": d_loss.detach(), "gan/penalty": gp.detach(),

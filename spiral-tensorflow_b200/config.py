@@ -75,6 +75,10 @@ def build_parser():
     # against libm: mean |err| <= 1e-3 on every canvas, single-dab jitter differences on ~20 % of 20-step canvases)
     # trajectory store: RGB observations are integers 0..255, kept as uint8 (lossless, 4x smaller); False = float32
     parser.add_argument('--traj_uint8', type=str2bool, default=True)
+    # several ranks: score the GAN reward with batch-norm statistics of the GLOBAL batch (per-layer all-reduce of the
+    # channel sums, spiral_disc_forward_staged) instead of each rank's shard (the reference normalises with whatever
+    # batch the learner dequeued, discriminator.py:76-79)
+    parser.add_argument('--disc_global_bn', type=str2bool, default=False)
     parser.add_argument('--raster_math', type=str, default='det', choices=['det', 'fast'])
     parser.add_argument('--disc_precision', type=str, default='bf16x3', choices=['fp32', 'bf16x3', 'bf16'])
     # arithmetic of the WGAN-GP step's convolutions and their gradients (K2b); 'auto' = bf16x6 (24 operand bits,

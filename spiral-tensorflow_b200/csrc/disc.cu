@@ -252,7 +252,7 @@ __global__ void __launch_bounds__(256)
 bn_finalize_kernel(const double *__restrict__ sliced, int Cout, double count,
                    const float *__restrict__ gamma, const float *__restrict__ beta,
                    float eps, float *__restrict__ scale, float *__restrict__ shift,
-                   float *__restrict__ stats, int stats_stride)
+                   float *__restrict__ stats, int stats_stride, double *__restrict__ sums_out)
 {
     __shared__ double s_s[8][32], s_q[8][32];
     const int cl = threadIdx.x & 31, g = threadIdx.x >> 5;
@@ -269,6 +269,31 @@ bn_finalize_kernel(const double *__restrict__ sliced, int Cout, double count,
     __syncthreads();
     if (g != 0 || c >= Cout) return;
     for (int k = 1; k < 8; k++) { s += s_s[k][cl]; q += s_q[k][cl]; }
+    if (sums_out) {          // staged forward: hand (sum x, sum x^2) to the caller (all-reduce across ranks), no affine yet
+        sums_out[2 * c] = s;
+        sums_out[2 * c + 1] = q;
+        return;
+    }
+    const double mean = s / count;
+    double var = q / count - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const float inv = (float)(1.0 / sqrt(var + (double)eps));
+    const float sc = gamma[c] * inv;
+    scale[c] = sc;
+    shift[c] = beta[c] - (float)mean * sc;
+    if (stats) { stats[c] = (float)mean; stats[stats_stride + c] = (float)var; }
+}
+
+// the second half of bn_finalize_kernel from per-channel sums [Cout][2] (the rank's own, or all-reduced over ranks with
+// `count` the global element count): same expressions, so one rank staged == one rank unstaged, bit for bit
+__global__ void __launch_bounds__(128)
+bn_affine_kernel(const double *__restrict__ sums, int Cout, double count, const float *__restrict__ gamma,
+                 const float *__restrict__ beta, float eps, float *__restrict__ scale, float *__restrict__ shift,
+                 float *__restrict__ stats, int stats_stride)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= Cout) return;
+    const double s = sums[2 * c], q = sums[2 * c + 1];
     const double mean = s / count;
     double var = q / count - mean * mean;
     if (var < 0.0) var = 0.0;
@@ -291,7 +316,21 @@ void launch_bn_finalize(float *part, int n_part, int Cout, double count, const f
     double *sliced = reinterpret_cast<double *>(reinterpret_cast<char *>(part) + disc_align((size_t)n_part * Cout * 2 * sizeof(float)));
     dim3 g1((Cout + 31) / 32, kBnSlices);
     bn_reduce_kernel<<<g1, 256, 0, st>>>(part, n_part, Cout, sliced);
-    bn_finalize_kernel<<<(Cout + 31) / 32, 256, 0, st>>>(sliced, Cout, count, gamma, beta, eps, scale, shift, stats, stats_stride);
+    bn_finalize_kernel<<<(Cout + 31) / 32, 256, 0, st>>>(sliced, Cout, count, gamma, beta, eps, scale, shift, stats, stats_stride, nullptr);
+}
+
+void launch_bn_sums(float *part, int n_part, int Cout, double *sums, cudaStream_t st)
+{
+    double *sliced = reinterpret_cast<double *>(reinterpret_cast<char *>(part) + disc_align((size_t)n_part * Cout * 2 * sizeof(float)));
+    dim3 g1((Cout + 31) / 32, kBnSlices);
+    bn_reduce_kernel<<<g1, 256, 0, st>>>(part, n_part, Cout, sliced);
+    bn_finalize_kernel<<<(Cout + 31) / 32, 256, 0, st>>>(sliced, Cout, 1.0, nullptr, nullptr, 0.0f, nullptr, nullptr, nullptr, 0, sums);
+}
+
+void launch_bn_affine(const double *sums, int Cout, double count, const float *gamma, const float *beta, float eps,
+                      float *scale, float *shift, float *stats, int stats_stride, cudaStream_t st)
+{
+    bn_affine_kernel<<<(Cout + 127) / 128, 128, 0, st>>>(sums, Cout, count, gamma, beta, eps, scale, shift, stats, stats_stride);
 }
 
 __global__ void fill_affine_kernel(float *scale, float *shift, int n, float sc, float sh)
@@ -371,13 +410,21 @@ int disc_conv0(SpiralDisc *d, const float *x, int batch, float *out, void *out_h
 }
 
 int disc_forward_simt(SpiralDisc *d, const float *x, int batch, float *logits, float *probs,
-                      float *bn_stats, char *ws, cudaStream_t st)
+                      float *bn_stats, char *ws, cudaStream_t st, int stage, double count, double *sums)
 {
     DiscPlan pl;
     disc_plan(d, batch, &pl);
     const SpiralDiscWeights &W = d->w;
     const int maxC = d->cfg.disc_dim << (d->n_layers - 1);
-    for (int l = 0; l < d->n_layers; l++) {
+    // staged (global-batch batch norm, spiral_disc_forward_staged): stage s finishes layer s's batch norm from `sums`
+    // (s >= 1), runs layer s + 1 (stage 0: layers 0 and 1) and leaves that layer's per-channel sums in `sums`
+    const int l_first = stage <= 0 ? 0 : stage + 1;                                   // stage n-1: no layer left (empty range)
+    const int l_last = stage < 0 ? d->n_layers - 1 : (stage + 1 < d->n_layers ? stage + 1 : d->n_layers - 1);
+    if (stage >= 1)
+        launch_bn_affine(sums, pl.Cout[stage], count, (const float *)W.bn_gamma[stage], (const float *)W.bn_beta[stage], 1e-3f,
+                         (float *)(ws + pl.scale_off[stage]), (float *)(ws + pl.shift_off[stage]),
+                         bn_stats ? bn_stats + (size_t)stage * 2 * maxC : nullptr, maxC, st);
+    for (int l = l_first; l <= l_last; l++) {
         const int H = pl.H[l], Cin = pl.Cin[l], Cout = pl.Cout[l], Ho = H / 2;
         float *out = (float *)(ws + pl.act_off[l]);
         float *scale = (float *)(ws + pl.scale_off[l]);
@@ -395,7 +442,9 @@ int disc_forward_simt(SpiralDisc *d, const float *x, int batch, float *logits, f
             conv_simt_kernel<<<grid, 256, 0, st>>>(in, isc, ish, (const float *)W.conv_w[l], (const float *)W.conv_b[l],
                                                    out, bn ? part : nullptr, batch, H, Cin, Cout);
         }
-        if (bn) {
+        if (bn && stage >= 0) {
+            launch_bn_sums(part, pl.mtiles[l], Cout, sums, st);          // the caller all-reduces, the next stage finishes
+        } else if (bn) {
             launch_bn_finalize(part, pl.mtiles[l], Cout, (double)batch * Ho * Ho, (const float *)W.bn_gamma[l],
                                (const float *)W.bn_beta[l], 1e-3f, scale, shift,
                                bn_stats ? bn_stats + (size_t)l * 2 * maxC : nullptr, maxC, st);
@@ -404,10 +453,11 @@ int disc_forward_simt(SpiralDisc *d, const float *x, int batch, float *logits, f
         }
     }
     const int last = d->n_layers - 1;
-    dense_sigmoid_kernel<<<(batch * 32 + 127) / 128, 128, 0, st>>>(
-        (const float *)(ws + pl.act_off[last]), (const float *)(ws + pl.scale_off[last]),
-        (const float *)(ws + pl.shift_off[last]), (const float *)W.dense_w, (const float *)W.dense_b, logits, probs,
-        batch, pl.Cout[last]);
+    if (stage < 0 || stage == last)
+        dense_sigmoid_kernel<<<(batch * 32 + 127) / 128, 128, 0, st>>>(
+            (const float *)(ws + pl.act_off[last]), (const float *)(ws + pl.scale_off[last]),
+            (const float *)(ws + pl.shift_off[last]), (const float *)W.dense_w, (const float *)W.dense_b, logits, probs,
+            batch, pl.Cout[last]);
     const cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? SPIRAL_OK : spiral_cuda_error(e, "spiral_disc_forward(fp32)");
 }
@@ -479,6 +529,21 @@ extern "C" int spiral_disc_forward(SpiralDisc *d, const float *x, int32_t batch,
     if (!d->have_weights) return spiral_set_error(SPIRAL_EINVAL, "spiral_disc_forward: call spiral_disc_load_weights first");
     if (batch < 1 || batch > d->cfg.max_batch) return spiral_set_error(SPIRAL_EINVAL, "batch %d outside 1..max_batch=%d", batch, d->cfg.max_batch);
     if (d->cfg.precision == 0)
-        return disc_forward_simt(d, x, batch, logits, probs, bn_stats, (char *)workspace, (cudaStream_t)stream);
-    return disc_tc_forward(d, x, batch, logits, probs, bn_stats, (char *)workspace, (cudaStream_t)stream);
+        return disc_forward_simt(d, x, batch, logits, probs, bn_stats, (char *)workspace, (cudaStream_t)stream, -1, 0.0, nullptr);
+    return disc_tc_forward(d, x, batch, logits, probs, bn_stats, (char *)workspace, (cudaStream_t)stream, -1, 0.0, nullptr);
+}
+
+extern "C" int spiral_disc_forward_staged(SpiralDisc *d, const float *x, int32_t batch, int32_t stage, double global_count,
+                                          double *sums, float *logits, float *probs, float *bn_stats, void *workspace,
+                                          void *stream)
+{
+    SPIRAL_REQUIRE(d); SPIRAL_REQUIRE(x); SPIRAL_REQUIRE(logits); SPIRAL_REQUIRE(workspace); SPIRAL_REQUIRE(sums);
+    if (!d->have_weights) return spiral_set_error(SPIRAL_EINVAL, "spiral_disc_forward_staged: call spiral_disc_load_weights first");
+    if (!d->cfg.batch_norm) return spiral_set_error(SPIRAL_EINVAL, "spiral_disc_forward_staged needs batch_norm (nothing to reduce without it)");
+    if (batch < 1 || batch > d->cfg.max_batch) return spiral_set_error(SPIRAL_EINVAL, "batch %d outside 1..max_batch=%d", batch, d->cfg.max_batch);
+    if (stage < 0 || stage >= d->n_layers) return spiral_set_error(SPIRAL_EINVAL, "stage %d outside 0..%d", stage, d->n_layers - 1);
+    if (stage >= 1 && !(global_count > 0.0)) return spiral_set_error(SPIRAL_EINVAL, "global_count must be > 0");
+    if (d->cfg.precision == 0)
+        return disc_forward_simt(d, x, batch, logits, probs, bn_stats, (char *)workspace, (cudaStream_t)stream, stage, global_count, sums);
+    return disc_tc_forward(d, x, batch, logits, probs, bn_stats, (char *)workspace, (cudaStream_t)stream, stage, global_count, sums);
 }

@@ -32,6 +32,10 @@ void disc_plan(const SpiralDisc *d, int batch, DiscPlan *pl);
 size_t bn_partial_bytes(int n_part, int Cout);
 void launch_bn_finalize(float *part, int n_part, int Cout, double count, const float *gamma, const float *beta, float eps,
                         float *scale, float *shift, float *stats, int stats_stride, cudaStream_t st);
+// staged forward (global-batch batch norm): per-channel (sum x, sum x^2) out, affine from (possibly all-reduced) sums in
+void launch_bn_sums(float *part, int n_part, int Cout, double *sums, cudaStream_t st);
+void launch_bn_affine(const double *sums, int Cout, double count, const float *gamma, const float *beta, float eps,
+                      float *scale, float *shift, float *stats, int stats_stride, cudaStream_t st);
 __global__ void fill_affine_kernel(float *scale, float *shift, int n, float sc, float sh);
 __global__ void dense_sigmoid_kernel(const float *in, const float *in_scale, const float *in_shift, const float *w,
                                      const float *bias, float *logits, float *probs, int B, int C);
@@ -50,6 +54,6 @@ int disc_tc_init(SpiralDisc *d);
 size_t disc_tc_workspace_bytes(const SpiralDisc *d, int batch);
 int disc_tc_pack_weights(SpiralDisc *d, char *ws, cudaStream_t st);
 int disc_tc_forward(SpiralDisc *d, const float *x, int batch, float *logits, float *probs, float *bn_stats,
-                    char *ws, cudaStream_t st);
+                    char *ws, cudaStream_t st, int stage, double count, double *sums);
 
 }  // namespace spiral

@@ -563,7 +563,7 @@ static int encode_w_map(const DiscTc *t, CUtensorMap *map, void *ptr, int K, int
 }
 
 int disc_tc_forward(SpiralDisc *d, const float *x, int batch, float *logits, float *probs, float *bn_stats,
-                    char *ws, cudaStream_t st)
+                    char *ws, cudaStream_t st, int stage, double count, double *sums)
 {
     const DiscTc *t = (const DiscTc *)d->tc;
     DiscPlan pl;
@@ -580,11 +580,21 @@ int disc_tc_forward(SpiralDisc *d, const float *x, int batch, float *logits, flo
     // layer 0 (K = 25 * C, C in {1,3,6}): mma.sync implicit GEMM gathered from a shared-memory input tile
     // (disc_conv0_mma.cu; direct fp32 convolution when disc_dim != 64); the epilogue applies the leaky-ReLU
     // (no BN at layer 0) and writes the bf16 hi/lo pair layer 1 reads
-    int rc = conv0_mma_supported(d)
-                 ? conv0_mma_forward(d, x, batch, tc + o.w0_hi, tc + o.w0_lo, tc + o.act_hi[1], tc + o.act_lo[1], x3, st)
-                 : disc_conv0(d, x, batch, nullptr, tc + o.act_hi[1], tc + o.act_lo[1], st);
-    if (rc != SPIRAL_OK) return rc;
-    for (int l = 1; l < d->n_layers; l++) {
+    // staged (global-batch batch norm, spiral_disc_forward_staged): stage s finishes layer s's batch norm from `sums`
+    // (s >= 1), runs layer s + 1 (stage 0: layers 0 and 1) and leaves that layer's per-channel sums in `sums`
+    const int l_first = stage <= 0 ? 1 : stage + 1;
+    const int l_last = stage < 0 ? d->n_layers - 1 : (stage + 1 < d->n_layers ? stage + 1 : d->n_layers - 1);
+    if (stage >= 1)
+        launch_bn_affine(sums, pl.Cout[stage], count, (const float *)W.bn_gamma[stage], (const float *)W.bn_beta[stage], 1e-3f,
+                         (float *)(ws + pl.scale_off[stage]), (float *)(ws + pl.shift_off[stage]),
+                         bn_stats ? bn_stats + (size_t)stage * 2 * maxC : nullptr, maxC, st);
+    if (stage <= 0) {
+        int rc = conv0_mma_supported(d)
+                     ? conv0_mma_forward(d, x, batch, tc + o.w0_hi, tc + o.w0_lo, tc + o.act_hi[1], tc + o.act_lo[1], x3, st)
+                     : disc_conv0(d, x, batch, nullptr, tc + o.act_hi[1], tc + o.act_lo[1], st);
+        if (rc != SPIRAL_OK) return rc;
+    }
+    for (int l = l_first; l <= l_last; l++) {
         const int H = pl.H[l], Cin = pl.Cin[l], Cout = pl.Cout[l], Ho = H / 2;
         // producer's BN + leaky-ReLU, then hi/lo split of this layer's input
         const size_t n4 = tc_layer_act_elems(pl, l, batch) / 4;
@@ -614,7 +624,9 @@ int disc_tc_forward(SpiralDisc *d, const float *x, int batch, float *logits, flo
         conv_tc_launch(grid, st, ma_hi, ma_lo, mw_hi, mw_lo, p, (const float *)W.conv_b[l], (float *)(ws + pl.act_off[l]),
                        bn ? part : nullptr);
         float *scale = (float *)(ws + pl.scale_off[l]), *shift = (float *)(ws + pl.shift_off[l]);
-        if (bn) {
+        if (bn && stage >= 0) {
+            launch_bn_sums(part, mtiles, Cout, sums, st);                // the caller all-reduces, the next stage finishes
+        } else if (bn) {
             launch_bn_finalize(part, mtiles, Cout, (double)batch * Ho * Ho, (const float *)W.bn_gamma[l],
                                (const float *)W.bn_beta[l], 1e-3f, scale, shift,
                                bn_stats ? bn_stats + (size_t)l * 2 * maxC : nullptr, maxC, st);
@@ -623,9 +635,10 @@ int disc_tc_forward(SpiralDisc *d, const float *x, int batch, float *logits, flo
         }
     }
     const int last = d->n_layers - 1;
-    dense_sigmoid_kernel<<<(batch * 32 + 127) / 128, 128, 0, st>>>(
-        (const float *)(ws + pl.act_off[last]), (const float *)(ws + pl.scale_off[last]), (const float *)(ws + pl.shift_off[last]),
-        (const float *)W.dense_w, (const float *)W.dense_b, logits, probs, batch, pl.Cout[last]);
+    if (stage < 0 || stage == last)
+        dense_sigmoid_kernel<<<(batch * 32 + 127) / 128, 128, 0, st>>>(
+            (const float *)(ws + pl.act_off[last]), (const float *)(ws + pl.scale_off[last]), (const float *)(ws + pl.shift_off[last]),
+            (const float *)W.dense_w, (const float *)W.dense_b, logits, probs, batch, pl.Cout[last]);
     const cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? SPIRAL_OK : spiral_cuda_error(e, "spiral_disc_forward(tensor cores)");
 }

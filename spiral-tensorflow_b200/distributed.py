@@ -76,6 +76,104 @@ def allreduce_grads_(tensors, world=None, average=True, bucket_bytes=64 << 20):
     return tensors
 
 
+class GradReducer(object):
+    """Gradient exchange overlapped with the backward pass, into a buffer the optimiser reads in place.
+
+    All parameters' gradients live in ONE persistent flat buffer (``p.grad`` are views of it, laid out in reverse
+    parameter order -- the order in which backward produces them), cut into buckets of ``bucket_bytes``.  A
+    post-accumulate-grad hook counts a bucket's parameters down and, when the last one is in, launches that bucket's
+    all-reduce (sum) asynchronously on the process group's stream -- NCCL over NVLink/NVSwitch runs under the rest of the
+    backward instead of after a ``torch.cat`` -> reduce -> copy-back pass (``allreduce_grads_``).  ``wait()`` joins the
+    outstanding collectives (and reduces buckets whose parameters received no gradient); K5 (``FusedTFAdam``) then reads
+    the reduced gradients where they are, with the explicit 1/world in its ``grad_scale``.  The hooks issue the same
+    sequence of collectives on every rank and every step, so the step can be captured into a CUDA graph."""
+
+    def __init__(self, params, world=None, bucket_bytes=64 << 20):
+        self.params = [p for p in params]
+        self.world = (dist.get_world_size() if dist.is_initialized() else 1) if world is None else int(world)
+        dev, dt = self.params[0].device, self.params[0].dtype
+        total = sum(p.numel() for p in self.params)
+        self.flat = torch.zeros((total,), dtype=dt, device=dev)
+        self.buckets = []                                  # [start, end) element ranges of the flat buffer
+        self._bucket_of = {}
+        off, b_start, b_elems = 0, 0, 0
+        per_bucket = max(1, int(bucket_bytes) // self.flat.element_size())
+        self._members = [[]]
+        for i in reversed(range(len(self.params))):
+            p = self.params[i]
+            n = p.numel()
+            if b_elems and b_elems + n > per_bucket:
+                self.buckets.append((b_start, off))
+                self._members.append([])
+                b_start, b_elems = off, 0
+            p.grad = self.flat[off:off + n].view_as(p)
+            self._bucket_of[i] = len(self._members) - 1
+            self._members[-1].append(i)
+            off += n
+            b_elems += n
+        self.buckets.append((b_start, off))
+        self._pending = [len(m) for m in self._members]
+        self._fired = [False] * len(self.buckets)
+        self._work = []
+        self._hooks = [p.register_post_accumulate_grad_hook(self._make_hook(i)) for i, p in enumerate(self.params)]
+
+    def _make_hook(self, i):
+        def hook(param):
+            if param.grad is None or param.grad.data_ptr() != self.flat.data_ptr() + self._offset_bytes(i):
+                # something replaced the view (zero_grad(set_to_none=True)): copy into the flat buffer and re-attach
+                g = param.grad
+                param.grad = self._view(i)
+                if g is not None:
+                    param.grad.copy_(g)
+            b = self._bucket_of[i]
+            self._pending[b] -= 1
+            if self._pending[b] == 0:
+                self._fire(b)
+        return hook
+
+    def _view(self, i):
+        off = self._offset_bytes(i) // self.flat.element_size()
+        return self.flat[off:off + self.params[i].numel()].view_as(self.params[i])
+
+    def _offset_bytes(self, i):
+        if not hasattr(self, "_offs"):
+            self._offs, off = {}, 0
+            for j in reversed(range(len(self.params))):
+                self._offs[j] = off * self.flat.element_size()
+                off += self.params[j].numel()
+        return self._offs[i]
+
+    def _fire(self, b):
+        if self._fired[b]:
+            return
+        self._fired[b] = True
+        if self.world > 1:
+            s, e = self.buckets[b]
+            self._work.append(dist.all_reduce(self.flat[s:e], op=dist.ReduceOp.SUM, async_op=True))
+
+    def zero(self):
+        """Start of a step: clear the flat buffer (gradients accumulate into it) and re-arm the buckets."""
+        self.flat.zero_()
+        for i, p in enumerate(self.params):
+            if p.grad is None:
+                p.grad = self._view(i)
+        self._pending = [len(m) for m in self._members]
+        self._fired = [False] * len(self.buckets)
+        self._work = []
+
+    def wait(self):
+        """After backward: reduce the buckets that never filled (parameters without a gradient this step), then make the
+        current stream wait for every collective."""
+        for b in range(len(self.buckets)):
+            self._fire(b)
+        for w in self._work:
+            w.wait()
+        self._work = []
+
+    def collective_bytes(self):
+        return self.flat.numel() * self.flat.element_size()
+
+
 def clip_by_global_norm_(tensors, clip_norm):
     """tf.clip_by_global_norm (agent.py:231): g *= clip / max(||g||, clip).  Returns the norm."""
     if not tensors:
@@ -85,6 +183,14 @@ def clip_by_global_norm_(tensors, clip_norm):
     for t in tensors:
         t.mul_(scale)
     return norm
+
+
+def allreduce_bn_sums_(sums, count):
+    """The ``global_bn`` hook of ``Discriminator.forward``: sum a layer's per-channel (sum x, sum x^2) [C,2] float64 and the
+    element count [1] float64 over the ranks, in place (NCCL on GPUs, gloo in the CPU tests)."""
+    if dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(sums, op=dist.ReduceOp.SUM)
+        dist.all_reduce(count, op=dist.ReduceOp.SUM)
 
 
 def allreduce_bn_stats_(sum_and_sumsq, count, world=None):

@@ -118,8 +118,14 @@ class Discriminator(object):
             pass
 
     # ------------------------------------------------------------------
-    def forward(self, images, logits_out=None, probs_out=None):
-        """images f32[N,S,S,C] (0..255 when norm_fn is set) -> (probs[N], logits[N])."""
+    def forward(self, images, logits_out=None, probs_out=None, global_bn=None):
+        """images f32[N,S,S,C] (0..255 when norm_fn is set) -> (probs[N], logits[N]).
+
+        ``global_bn``: score with GLOBAL-batch batch-norm statistics when the batch is sharded over ranks (the reference
+        normalises with the statistics of whatever batch it is fed, discriminator.py:76-79, so a sharded batch equals the
+        gathered one only if every layer's per-channel sums are all-reduced): the forward runs in stages
+        (``spiral_disc_forward_staged``) and ``global_bn(sums_f64 [C,2], count_f64 [1])`` is called between them to reduce
+        both tensors in place over the ranks (``distributed.allreduce_bn_sums_``).  None / one rank: one call."""
         x = images
         if self.conditional:
             x = torch.cat([x, x], -1)                 # real <- concat[real, real] (reference :36-38)
@@ -130,14 +136,31 @@ class Discriminator(object):
                                                               self.in_channels // (2 if self.conditional else 1)))
         logits = logits_out if logits_out is not None else torch.empty((n,), dtype=torch.float32, device=self.device)
         probs = probs_out if probs_out is not None else torch.empty((n,), dtype=torch.float32, device=self.device)
+        if global_bn is not None and self.batch_norm:
+            if getattr(self, "_bn_sums", None) is None:
+                self._bn_sums = torch.zeros((self.disc_dim * 2 ** (self.layer_num - 1), 2), dtype=torch.float64, device=self.device)
+                self._bn_count = torch.zeros((1,), dtype=torch.float64, device=self.device)
+            count = 0.0
+            for stage in range(self.layer_num):
+                N.check(self._lib.spiral_disc_forward_staged(self._handle, N.ptr(x), n, stage, C.c_double(count),
+                                                             N.ptr(self._bn_sums), N.ptr(logits), N.ptr(probs),
+                                                             N.ptr(self.bn_stats), N.ptr(self.workspace), N.stream_ptr()),
+                        "spiral_disc_forward_staged")
+                if stage + 1 < self.layer_num:
+                    ho = self.image_shape[0] >> (stage + 2)                 # output side of layer stage + 1
+                    cout = self.disc_dim * 2 ** (stage + 1)
+                    self._bn_count.fill_(float(n * ho * ho))
+                    global_bn(self._bn_sums[:cout], self._bn_count)
+                    count = float(self._bn_count.item())
+            return probs, logits
         N.check(self._lib.spiral_disc_forward(self._handle, N.ptr(x), n, N.ptr(logits), N.ptr(probs),
                                               N.ptr(self.bn_stats), N.ptr(self.workspace), N.stream_ptr()),
                 "spiral_disc_forward")
         return probs, logits
 
-    def predict(self, images):
+    def predict(self, images, global_bn=None):
         """reference :157-163."""
-        return self.forward(images)[0]
+        return self.forward(images, global_bn=global_bn)[0]
 
     # ------------------------------------------------------------------
     def logits_fn(self, x_normed):

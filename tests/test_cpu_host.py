@@ -187,6 +187,35 @@ mine = full[start:start + count]
 ss = torch.stack([mine.sum(0), (mine ** 2).sum(0)])
 mean, var, n = dm.allreduce_bn_stats_(ss, mine.shape[0])
 assert n == 10 and torch.allclose(mean, full.mean(0)) and torch.allclose(var, full.var(0, unbiased=False))
+# GradReducer: per-bucket all-reduce launched from backward hooks into a persistent flat buffer == the plain sum
+torch.manual_seed(0)
+net = torch.nn.Sequential(torch.nn.Linear(4, 8), torch.nn.Tanh(), torch.nn.Linear(8, 8), torch.nn.Tanh(), torch.nn.Linear(8, 1))
+ref = [torch.zeros_like(p) for p in net.parameters()]
+red = dm.GradReducer(net.parameters(), bucket_bytes=128)          # several buckets
+assert len(red.buckets) > 2 and red.collective_bytes() == 4 * sum(p.numel() for p in net.parameters())
+for step in range(3):
+    xs = [torch.randn(5, 4, generator=torch.Generator().manual_seed(10 * step + r)) for r in range(world)]
+    want = [torch.zeros_like(p) for p in net.parameters()]
+    for xr in xs:                                                  # what every rank's backward contributes
+        for w_, g in zip(want, torch.autograd.grad(net(xr).pow(2).sum(), list(net.parameters()))):
+            w_ += g
+    red.zero()
+    net(xs[rank]).pow(2).sum().backward()
+    red.wait()
+    for p, w_ in zip(net.parameters(), want):
+        assert p.grad.data_ptr() >= red.flat.data_ptr() and torch.allclose(p.grad, w_, rtol=1e-5, atol=1e-6), step
+# a parameter that takes no part in the loss: its bucket is still reduced (zeros), nothing hangs
+extra = torch.nn.Parameter(torch.ones(3))
+red2 = dm.GradReducer(list(net.parameters()) + [extra], bucket_bytes=64)
+red2.zero()
+net(xs[rank]).sum().backward()
+red2.wait()
+assert float(extra.grad.abs().max()) == 0.0
+# the global_bn hook of Discriminator.forward
+sums = torch.full((4, 2), float(rank + 1), dtype=torch.float64)
+cnt = torch.tensor([10.0 * (rank + 1)], dtype=torch.float64)
+dm.allreduce_bn_sums_(sums, cnt)
+assert float(sums[0, 0]) == 3.0 and float(cnt) == 30.0
 dist.destroy_process_group()
 print("rank", rank, "ok")
 '''

@@ -216,3 +216,59 @@ def test_discriminator_large_batch_tensor_core_path_vs_fp32_and_oracle():
     want_p, want_l = do.predict(imgs[:n].cpu().numpy(), w0, batch_norm=False, dtype=torch.float64)
     assert np.abs(l.cpu().numpy() - want_l).max() <= 1e-4 * max(1.0, np.abs(want_l).max())
     assert np.abs(p.cpu().numpy() - want_p).max() <= 1e-4
+
+
+@pytest.mark.parametrize("prec,dd", [("fp32", 16), ("bf16x3", 64)])
+def test_staged_forward_with_summed_statistics_equals_the_gathered_batch(prec, dd):
+    """Global-batch batch norm over ranks (spiral_disc_forward_staged): two "ranks" on one GPU each score half of a batch
+    in stages; between stages their per-channel (sum x, sum x^2) and element counts are added -- what the NCCL all-reduce
+    of distributed.allreduce_bn_sums_ does -- and both must reproduce the scores of the whole batch in one call
+    (discriminator.py:76-79: the statistics are those of the batch that is fed).  One rank alone, staged, is bit-identical
+    to the unstaged call."""
+    sp = _sp()
+    import ctypes as C
+    from oracle import disc_oracle as do
+    from importlib import import_module
+    models = import_module(sp.__name__ + ".models")
+    N = sp._native
+    lib = N.lib()
+    B, Cc = 256, 3
+    args = sp.get_args(["--color_channel", str(Cc), "--disc_dim", str(dd), "--disc_batch_norm", "True", "--disc_precision", prec])
+    w = do.init_weights(Cc, disc_dim=dd, batch_norm=True, seed=8)
+    imgs = _canvas_like(B, Cc, seed=4)
+    imgs[B // 2:] *= 0.5                                       # the two halves have different statistics
+
+    def make(n):
+        D = models.Discriminator(args, None, [64, 64, Cc], norm_fn=lambda x: x, scope_name="global", max_batch=n)
+        D.load_numpy(w)
+        return D
+
+    whole = make(B)
+    want_p, want_l = [t.clone() for t in whole.forward(imgs)]
+    # one rank, staged, no reduction: same bits
+    got_p, got_l = whole.forward(imgs, global_bn=lambda sums, count: None)
+    assert torch.equal(got_l, want_l) and torch.equal(got_p, want_p)
+    # two ranks in lockstep
+    ranks = [make(B // 2), make(B // 2)]
+    xs = [imgs[:B // 2].contiguous(), imgs[B // 2:].contiguous()]
+    outs = [(torch.empty(B // 2, device="cuda"), torch.empty(B // 2, device="cuda")) for _ in ranks]
+    sums = [torch.zeros((dd * 32, 2), dtype=torch.float64, device="cuda") for _ in ranks]
+    count = 0.0
+    for stage in range(6):
+        for D, x, (lg, pr), sm in zip(ranks, xs, outs, sums):
+            N.check(lib.spiral_disc_forward_staged(D._handle, N.ptr(x), B // 2, stage, C.c_double(count), N.ptr(sm),
+                                                   N.ptr(lg), N.ptr(pr), N.ptr(D.bn_stats), N.ptr(D.workspace), N.stream_ptr()))
+        if stage < 5:
+            total = sums[0] + sums[1]                          # the all-reduce
+            for sm in sums:
+                sm.copy_(total)
+            ho = 64 >> (stage + 2)
+            count = float(2 * (B // 2) * ho * ho)
+    got_l = torch.cat([outs[0][0], outs[1][0]])
+    got_p = torch.cat([outs[0][1], outs[1][1]])
+    scale = max(1.0, float(want_l.abs().max()))
+    assert float((got_l - want_l).abs().max()) <= 2e-5 * scale
+    assert float((got_p - want_p).abs().max()) <= 2e-5
+    # per-shard statistics, by contrast, give other scores (that is what the flag is for)
+    own = torch.cat([ranks[0].forward(xs[0])[1], ranks[1].forward(xs[1])[1]])
+    assert float((own - want_l).abs().max()) > 1e-3 * scale

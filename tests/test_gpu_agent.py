@@ -149,6 +149,8 @@ def test_checkpoint_resume_restores_weights_and_optimizer(tmp_path):
     assert ck.latest_checkpoint(str(tmp_path)) == path
     want_p = [p.detach().clone() for p in ag.policy.parameters()]
     want_d = {k: v.detach().clone() for k, v in ag.disc.params.items()}
+    snap = dict(replay=ag.replay.data.clone(), idx=ag.replay.idx, lstm=ag._lstm_state.clone(),
+                ctr=int(ag.policy._sample_counter_dev.item()), rng=ag.rng.get_state().clone(), env_rng=ag.env._rng.get_state().clone())
     x = ag.rollout()["states"][:, -1]
     want_reward = ag.disc.predict(x).clone()
     ag2 = agent_mod.Agent(args, sp.create_env(args, num_envs=8))
@@ -157,18 +159,40 @@ def test_checkpoint_resume_restores_weights_and_optimizer(tmp_path):
     assert all(torch.equal(want_d[k], ag2.disc.params[k]) for k in want_d)
     assert ag2.policy_opt.t == ag.policy_opt.t and torch.equal(ag2.disc_opt.m[0], ag.disc_opt.m[0])
     assert torch.equal(ag2.disc.predict(x), want_reward)              # the packed kernel weights were refreshed
+    # the acting path's packed (bf16) copies of the policy's convolution kernels were re-packed from the restored weights:
+    # the first rollout after a resume must act with the saved network, not the fresh random one
+    assert ag.actor is not None and ag2.actor is not None
+    ob = x.float()
+    last = torch.zeros((8, 3), dtype=torch.int32, device="cuda")
+    c = torch.randn((8, args.lstm_size), device="cuda")
+    h = torch.randn((8, args.lstm_size), device="cuda")
+    z = torch.rand((8, args.z_dim), device="cuda") - 0.5
+    e1, e2 = ag.actor.encode(ob, last, None, z), ag2.actor.encode(ob, last, None, z)
+    assert torch.equal(e1, e2)
+    fresh = agent_mod.Agent(args, sp.create_env(args, num_envs=8))
+    assert not torch.equal(e1, fresh.actor.encode(ob, last, None, z))
+    # the random streams, the replay ring and the actors' carried LSTM state continue where the saved run stopped
+    assert torch.equal(ag2.replay.data, snap["replay"]) and ag2.replay.idx == snap["idx"]
+    assert torch.equal(ag2._lstm_state, snap["lstm"]) and float(snap["lstm"].abs().max()) > 0
+    assert int(ag2.policy._sample_counter_dev.item()) == snap["ctr"] > 0
+    assert torch.equal(ag2.rng.get_state(), snap["rng"]) and torch.equal(ag2.env._rng.get_state(), snap["env_rng"])
 
 
 @pytest.mark.parametrize("native", [False, True])
-def test_graph_captured_learner_step_matches_eager_steps(native):
+def test_graph_captured_learner_step_matches_eager_steps(native, monkeypatch):
     """The CUDA graph of train_policy (captured at the third call) must update the policy exactly like eager steps:
     two agents with identical weights are fed the same rollouts for five learner steps; the graph reads each step's
     bias-corrected Adam step size from device memory (FusedTFAdam.advance)."""
     sp, agent_mod, _ = _mods()
+    # deterministic cuDNN algorithms and strict fp32 in both agents: what is left between the two runs is the order of
+    # floating-point sums inside the kernels, not a different choice of algorithm under capture
+    monkeypatch.setattr(torch.backends.cudnn, "deterministic", True)
+    monkeypatch.setattr(torch.backends.cudnn, "benchmark", False)
 
     def make(graphs):
         args = make_args("simple_mnist", L=32, C=1, T=3, conditional=True,
-                         extra=["--cuda_graphs", str(graphs), "--policy_act_native", str(native), "--policy_lr", "1e-4"])
+                         extra=["--cuda_graphs", str(graphs), "--policy_act_native", str(native), "--policy_lr", "1e-4",
+                                "--policy_tf32", "False"])
         env = sp.create_env(args, num_envs=8)
         torch.manual_seed(0)
         return agent_mod.Agent(args, env)
@@ -189,7 +213,7 @@ def test_graph_captured_learner_step_matches_eager_steps(native):
         # the step size is kept small enough (1e-4; 1e-3 let the two runs drift apart by the fifth step on some boxes)
         # that this noise is not amplified by the loss surface
         assert torch.allclose(m_g["model/total_loss"], m_e["model/total_loss"], rtol=5e-3), i
-        assert torch.allclose(m_g["model/grad_global_norm"], m_e["model/grad_global_norm"], rtol=2e-1), i
+        assert torch.allclose(m_g["model/grad_global_norm"], m_e["model/grad_global_norm"], rtol=5e-2), i
     assert a_graph._tp_graph is not None and not a_graph._tp_failed           # steps 3-5 were graph replays
     assert a_graph.policy_opt.t == a_eager.policy_opt.t == 5
     moved = sum(float((p.detach() - s0).pow(2).sum()) for p, s0 in zip(a_graph.policy.parameters(), start)) ** 0.5
@@ -230,4 +254,147 @@ def test_graph_captured_discriminator_step_matches_eager_steps():
     moved = sum(float((v.detach() - start[k]).pow(2).sum()) for k, v in a_graph.disc.params.items()) ** 0.5
     apart = sum(float((v.detach() - a_eager.disc.params[k].detach()).pow(2).sum())
                 for k, v in a_graph.disc.params.items()) ** 0.5
+    assert moved > 0 and apart < 0.05 * moved, (moved, apart)
+
+
+@pytest.mark.parametrize("graphs", [False, True])
+def test_actor_lstm_state_carries_over_and_features_are_per_step(graphs):
+    """rl_utils.py:185-238: an actor fetches the initial LSTM features once, before its loop, so episode n+1 starts from
+    the state episode n ended in; PartialRollout stores the features each step STARTED from.  Checked on the rollout
+    (eager and CUDA-graph replay): features[:, 0] of the second episode is the final state of the first, and stepping the
+    LSTM by hand from features[:, t] with the recorded frames and actions gives features[:, t + 1]."""
+    sp, agent_mod, _ = _mods()
+    args = make_args("simple_mnist", L=32, C=1, T=3, extra=["--cuda_graphs", str(graphs), "--policy_act_native", "False",
+                                                             "--policy_tf32", "False", "--disc_dim", "8", "--disc_precision", "fp32"])
+    env = sp.create_env(args, num_envs=6)
+    ag = agent_mod.Agent(args, env)
+    ro1 = ag.rollout()
+    end1 = ag._lstm_state.clone()
+    ro2 = ag.rollout()
+    assert float(ro1["features"][:, 0].abs().max()) == 0.0                 # get_initial_features: zeros, once
+    assert torch.equal(ro2["features"][:, 0], end1)                        # carried over, never reset
+    assert float(end1.abs().max()) > 0
+    pi = ag.policy
+    init = torch.as_tensor(env.initial_action, device="cuda").float()
+    for ro in (ro1, ro2):
+        T = ro["actions"].shape[1]
+        for t in range(T):
+            last = init if t == 0 else ro["actions"][:, t - 1].float()
+            enc = pi.encode(ro["states"][:, t:t + 1].float(), last.unsqueeze(1), None, ro["z"][:, t:t + 1])
+            _, (c, h) = pi.lstm(enc[:, 0], (ro["features"][:, t, 0], ro["features"][:, t, 1]))
+            want = ro["features"][:, t + 1] if t + 1 < T else (end1 if ro is ro1 else ag._lstm_state)
+            assert torch.allclose(c, want[:, 0], atol=1e-5) and torch.allclose(h, want[:, 1], atol=1e-5), t
+
+
+def test_rgb_trajectory_states_are_uint8_and_lossless():
+    """color_channel 3 observations are the read-back uint8 image: the rollout keeps `states` as uint8 (4x smaller) and the
+    env reproduces exactly those frames from the recorded actions; the learner step consumes them."""
+    sp, agent_mod, _ = _mods()
+    args = make_args("color_mnist", L=64, C=3, T=3, extra=["--disc_dim", "8", "--disc_precision", "fp32", "--disc_batch_size", "4"])
+    env = sp.create_env(args, num_envs=4)
+    ag = agent_mod.Agent(args, env)
+    ro = ag.rollout()
+    assert ro["states"].dtype == torch.uint8 and ro["states"].shape == (4, 4, 64, 64, 3)
+    env.reset()
+    for t in range(3):
+        assert torch.equal(env.state, ro["states"][:, t].float())
+        env.step(ro["actions"][:, t])
+    assert torch.equal(env.state, ro["states"][:, 3].float())
+    m = ag.train_policy(ro)
+    assert torch.isfinite(m["model/total_loss"])
+    gray = agent_mod.Agent(make_args("simple_mnist", L=32, C=1, T=2, conditional=True), sp.create_env(make_args("simple_mnist", L=32, C=1, T=2, conditional=True), num_envs=2))
+    assert gray.rollout()["states"].dtype == torch.float32                # BT.601 gray values are not integers
+
+
+def test_replay_buffer_on_the_device_follows_the_reference():
+    """replay.py:8-37 restated in numpy against the device-resident ring on the GPU (pushes of uint8-truncated float
+    canvases, the shift-left overflow rule, sampling from [0, idx))."""
+    import types
+    sp, _, _ = _mods()
+    from importlib import import_module
+    rb = import_module(sp.__name__ + ".replay")
+    args = types.SimpleNamespace(buffer_batch_num=6, disc_batch_size=8, seed=5)
+    shape = [64, 64, 3]
+    buf = rb.ReplayBuffer(args, shape, device="cuda")
+    size = 48
+    data = np.zeros([size] + shape, np.uint8)
+    idx = 0
+    rng = np.random.RandomState(1)
+    for step in range(25):
+        n = int(rng.randint(1, 20))
+        batch = rng.uniform(0, 255.99, size=[n] + shape).astype(np.float32)
+        if idx + n > size:
+            data[:-n] = data[n:]
+            data[-n:] = batch
+        else:
+            data[idx:idx + n] = batch
+            idx += n
+        buf.push(torch.from_numpy(batch).cuda())
+        assert buf.idx == idx and (buf.data.cpu().numpy() == data).all(), step
+    out = buf.sample(8).cpu().numpy()
+    rows = {r.tobytes() for r in data[:idx].astype(np.float32)}
+    assert out.shape == (8, 64, 64, 3) and all(r.tobytes() in rows for r in out)
+
+
+def test_discriminator_variables_carry_tensorflow_names():
+    """tl.batch_normalization is unnamed in the reference (discriminator.py:76-79): TensorFlow names the first one in the
+    scope 'batch_normalization', then 'batch_normalization_1', ...; conv<l>/{kernel,bias}, dense/{kernel,bias}."""
+    sp, _, _ = _mods()
+    from importlib import import_module
+    models = import_module(sp.__name__ + ".models")
+    args = sp.get_args(["--color_channel", "3", "--disc_dim", "8", "--disc_precision", "fp32"])
+    D = models.Discriminator(args, None, [64, 64, 3], norm_fn=lambda x: x, max_batch=4)
+    names = set(D.params)
+    want = {"conv%d/%s" % (l, k) for l in range(6) for k in ("kernel", "bias")} | {"dense/kernel", "dense/bias"}
+    want |= {"batch_normalization/gamma", "batch_normalization/beta"}
+    want |= {"batch_normalization_%d/%s" % (i, k) for i in range(1, 5) for k in ("gamma", "beta")}
+    assert names == want
+
+
+def test_grad_reducer_path_matches_the_plain_path_on_one_rank(monkeypatch):
+    """distributed.GradReducer (flat gradient buffer, per-bucket all-reduce from backward hooks) is what several ranks use;
+    on one rank (SPIRAL_GRAD_REDUCER=1) it must update the networks like the plain path, eagerly and under the CUDA graph."""
+    sp, agent_mod, _ = _mods()
+
+    def make(reducer):
+        if reducer:
+            monkeypatch.setenv("SPIRAL_GRAD_REDUCER", "1")
+        else:
+            monkeypatch.delenv("SPIRAL_GRAD_REDUCER", raising=False)
+        args = make_args("simple_mnist", L=32, C=1, T=3, extra=["--cuda_graphs", "True", "--policy_act_native", "False",
+                                                                 "--disc_dim", "8", "--disc_batch_size", "8", "--disc_precision", "fp32",
+                                                                 "--policy_lr", "1e-4"])
+        env = sp.create_env(args, num_envs=8)
+        torch.manual_seed(0)
+        return agent_mod.Agent(args, env)
+
+    a_red, a_plain = make(True), make(False)
+    assert a_red._pol_red is not None and a_red._disc_red is not None and a_plain._pol_red is None
+    a_plain.policy.load_state_dict(a_red.policy.state_dict())
+    for k, v in a_red.disc.params.items():
+        a_plain.disc.params[k].data.copy_(v.data)
+    a_plain.disc.sync_weights()
+    start = [p.detach().clone() for p in a_red.policy.parameters()]
+    g = torch.Generator(device="cuda")
+    g.manual_seed(3)
+    for i in range(5):
+        ro = a_plain.rollout()
+        ro["rewards"][:, -1] = torch.linspace(0, 1, 8, device="cuda")
+        a_red.replay.push(ro["states"][:, -1])
+        m1 = a_red.train_policy({k: v.clone() for k, v in ro.items()})
+        m2 = a_plain.train_policy({k: v.clone() for k, v in ro.items()})
+        assert torch.allclose(m1["model/grad_global_norm"], m2["model/grad_global_norm"], rtol=2e-1), i
+        fake = torch.rand((8, 64, 64, 1), generator=g, device="cuda") * 255
+        real = torch.rand((8, 64, 64, 1), generator=g, device="cuda") * 255
+        for ag in (a_red, a_plain):
+            ag.replay.sample = lambda n, f=fake: f
+            ag.rng.manual_seed(100 + i)
+        d1, d2 = a_red.train_gan(real), a_plain.train_gan(real)
+        assert torch.allclose(d1["gan/disc_loss"], d2["gan/disc_loss"], rtol=2e-2, atol=1e-3), i
+    assert a_red._tp_graph is not None and a_red._tg_graph is not None          # captured with the hooks in place
+    for p in a_red.policy.parameters():                                          # gradients still live in the flat buffer
+        assert a_red._pol_red.flat.data_ptr() <= p.grad.data_ptr() < a_red._pol_red.flat.data_ptr() + a_red._pol_red.collective_bytes()
+    moved = sum(float((p.detach() - s0).pow(2).sum()) for p, s0 in zip(a_red.policy.parameters(), start)) ** 0.5
+    apart = sum(float((p.detach() - q.detach()).pow(2).sum())
+                for p, q in zip(a_red.policy.parameters(), a_plain.policy.parameters())) ** 0.5
     assert moved > 0 and apart < 0.05 * moved, (moved, apart)

@@ -77,7 +77,9 @@ def main(argv=None):
             print(json.dumps(line), flush=True)
         if rank == 0 and ((it + 1) % opts["--save_iters"] == 0 or it + 1 == opts["--max_iters"]):
             ck.save_checkpoint(agent, load_path, it + 1)
+    agent.close()                                            # captured graphs hold NCCL collectives: drop them before the group
     if world > 1:
+        torch.distributed.barrier()
         torch.distributed.destroy_process_group()
     return load_path
 
