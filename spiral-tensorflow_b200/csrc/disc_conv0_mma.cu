@@ -30,7 +30,7 @@ constexpr int kC0Cout = 64;
 // weights).  The 5*CIN inputs of one kernel row are CONSECUTIVE elements of the staged NHWC input row, so an MMA
 // A-fragment pair (k', k'+1) is one aligned 32-bit shared-memory load at a compile-time offset -- no k -> offset
 // table, no 16-bit loads, no packing -- and the pad entries read finite neighbours that meet zero weights.
-__host__ __device__ constexpr int c0_seg(int cin) { return cin == 1 ? 8 : (cin == 3 ? 16 : 32); }
+__host__ __device__ constexpr int c0_seg(int cin) { return cin == 1 ? 8 : (cin <= 3 ? 16 : 32); }   // >= 5 * cin
 __host__ __device__ constexpr int c0_kpad(int cin) { return (5 * c0_seg(cin) + 15) / 16 * 16; }
 __host__ __device__ constexpr int c0_kstride(int cin) { return c0_kpad(cin) + 8; }   // bf16 per row; conflict-free, 16-byte rows
 __host__ __device__ constexpr int c0_rowstride(int cin) { return (kC0Iw * cin + 1) & ~1; }   // staged input row, even
@@ -258,7 +258,7 @@ size_t conv0_mma_pack_bytes(int Cin) { return (size_t)kC0Cout * c0_kstride(Cin) 
 bool conv0_mma_supported(const SpiralDisc *d)
 {
     const int Cin = d->cfg.in_channels, Ho = d->cfg.screen_size / 2;
-    return d->cfg.disc_dim == kC0Cout && (Cin == 1 || Cin == 3 || Cin == 6) && (Ho % kC0Tw) == 0 && (Ho % kC0Th) == 0;
+    return d->cfg.disc_dim == kC0Cout && (Cin == 1 || Cin == 2 || Cin == 3 || Cin == 6) && (Ho % kC0Tw) == 0 && (Ho % kC0Th) == 0;
 }
 
 void conv0_mma_pack(const SpiralDisc *d, void *w_hi, void *w_lo, cudaStream_t st)
@@ -295,10 +295,11 @@ int conv0_mma_forward(const SpiralDisc *d, const float *x, int batch, const void
 {
     switch (d->cfg.in_channels) {
     case 1: return conv0_launch<1>(d, x, batch, w_hi, w_lo, out_hi, out_lo, x3, st);
+    case 2: return conv0_launch<2>(d, x, batch, w_hi, w_lo, out_hi, out_lo, x3, st);      // conditional D on gray canvases
     case 3: return conv0_launch<3>(d, x, batch, w_hi, w_lo, out_hi, out_lo, x3, st);
     case 6: return conv0_launch<6>(d, x, batch, w_hi, w_lo, out_hi, out_lo, x3, st);
     }
-    return spiral_set_error(SPIRAL_EUNSUPPORTED, "conv0_mma: in_channels must be 1, 3 or 6");
+    return spiral_set_error(SPIRAL_EUNSUPPORTED, "conv0_mma: in_channels must be 1, 2, 3 or 6");
 }
 
 }  // namespace spiral

@@ -94,7 +94,7 @@ class MNIST(Environment):
         self.max_dabs = int(max_dabs or getattr(args, "max_dabs", 2560))
         # arithmetic mode of the brush state machine ('det' | 'fast'; SPIRAL_RASTER_MATH overrides the flag: profiling)
         import os
-        self.raster_math = os.environ.get("SPIRAL_RASTER_MATH") or getattr(args, "raster_math", "det")
+        self.raster_math = os.environ.get("SPIRAL_RASTER_MATH") or getattr(args, "raster_math", "fast")
         if self.raster_math not in ("det", "fast"):
             raise ValueError("raster_math must be 'det' or 'fast', got %r" % (self.raster_math,))
         self.math_mode = N.MATH_FAST if self.raster_math == "fast" else N.MATH_DET

@@ -123,14 +123,16 @@ def test_a2c_autograd_wrapper_backpropagates():
                                             # whole tiles of 128 images: position-pure tiles on the 2x2 .. 8x8 maps
                                             (3, 64, True, 128, "bf16x3"), (1, 64, True, 256, "bf16x3"),
                                             # 6 input channels: the conditional discriminator's concat[fake, real]
-                                            (6, 64, True, 8, "bf16x3")])
+                                            (6, 64, True, 8, "bf16x3"),
+                                            # 2 input channels: the conditional discriminator on gray canvases (mnist-cond)
+                                            (2, 64, True, 8, "bf16x3"), (2, 64, True, 8, "fp32")])
 def test_discriminator_forward_matches_oracle(C, dd, bn, B, prec):
     sp = _sp()
     from oracle import disc_oracle as do
     from importlib import import_module
     models = import_module(sp.__name__ + ".models")
-    cond = C == 6                                   # conditional D: 3-channel images, fed as concat[x, x] (reference :36-38)
-    Cnet, C = C, (3 if cond else C)
+    cond = C in (2, 6)                              # conditional D: 1- / 3-channel images, fed as concat[x, x] (reference :36-38)
+    Cnet, C = C, ({2: 1, 6: 3}[C] if cond else C)
     args = sp.get_args(["--color_channel", str(C), "--disc_dim", str(dd), "--disc_batch_norm", str(bn),
                         "--disc_precision", prec])
     args.conditional = cond                         # config.py:83-101 forces False with --loss gan; the D graph itself supports it

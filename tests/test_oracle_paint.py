@@ -283,3 +283,24 @@ def test_dab_statistics_are_plausible():
     travel = lin[28] - lin[2]
     assert 5.0 < len(d) / travel < 8.5
     assert 1.2 < d["radius"].mean() < 2.4 and (d["hardness"] == np.float32(0.2)).all()
+
+
+def test_oracle_reproduces_the_committed_render_fixtures():
+    """tests/golden/*.npz (render fixtures, det and fast arithmetic modes) are oracle outputs committed so that a change
+    of the oracle -- or of the fast mode's shared arithmetic contract (oracle/fast_math.h <-> csrc/fastmath.cuh) --
+    cannot go unnoticed: the oracle of today must still produce them bit for bit."""
+    import glob
+    import os
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    paths = sorted(p for p in glob.glob(os.path.join(here, "*.npz")) if not os.path.basename(p).startswith("nets_"))
+    assert len(paths) >= 6
+    for path in paths:
+        g = np.load(path)
+        math = str(g["math"]) if "math" in g.files else "det"
+        acs = [str(a) for a in g["acs"]]
+        spec = po.EnvSpec(action_names=acs, location_size=int(g["L"]), n_color=8,
+                          math_mode=po.PO_MATH_FAST if math == "fast" else po.PO_MATH_DET)
+        env = po.OracleBatchEnv(spec, g["actions"].shape[0], channels=int(g["C"]))
+        canv, obs = env.run_episodes(g["actions"], want_obs=True)
+        assert (canv == g["canvas"]).all(), path
+        assert (obs[:, -1].astype(np.float32) == g["obs_final"]).all(), path
