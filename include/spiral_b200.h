@@ -346,6 +346,41 @@ int spiral_phead_last(const void *u_bf16_dev, const void *w_up_packed_dev, const
                       const void *w_out_packed_dev, const float *bias_out_dev, float *logits_dev, int32_t B, int32_t Hh,
                       void *stream);
 
+/* ------------------------------------------------------------------ */
+/* Policy convolutions for the learner (forward, input gradient, weight */
+/* gradient), fp32 parity on bf16 tensor cores (bf16x3)                 */
+/* replaces: what tf.gradients(loss) executes through the conv layers   */
+/*           of models/policy.py:94-114 (trunk), :242-295 (location     */
+/*           heads) when agent.py:161-239 evaluates the A2C loss        */
+/* ------------------------------------------------------------------ */
+/* Operand precision: n_planes = 2 ("bf16x3": operands split into two bf16 planes, three MMAs per k-step, 16 operand bits)
+ * or 3 ("bf16x6": three planes, six MMAs, 24 bits = fp32-exact operands -- the default of the learner, whose trunk is
+ * ~20 convolutions deep).
+ * spiral_lconv_pack: an fp32 kernel -> n_planes contiguous bf16 planes [rows_pad][KS], rows_pad = rows rounded up to 8,
+ * K = n_taps * Ck, KS = (K rounded up to 16) + 8:
+ *   packed[row][tap * Ck + c] = w[row * s_row + c * s_c + tap_ky[tap] * s_ky + tap_kx[tap] * s_kx]
+ * (strides in elements).  The strides and the tap table select the forward kernel of a convolution, its adjoint (input
+ * gradient: flipped taps, rows <-> channels) or one parity class of a stride-2 transposed convolution.
+ * spiral_lconv_packed_elems = rows_pad * KS (elements of ONE plane). */
+int64_t spiral_lconv_packed_elems(int32_t Cin, int32_t Cout, int32_t n_taps);
+int spiral_lconv_pack(const float *w_dev, void *packed_planes_dev, int32_t n_planes, int32_t rows, int32_t Ck, int32_t n_taps,
+                      int64_t s_row, int64_t s_c, int64_t s_ky, int64_t s_kx, const int32_t *tap_ky, const int32_t *tap_kx,
+                      void *stream);
+/* out[b, oy*o_sy + o_oy, ox*o_sx + o_ox, co] = bias[co] + sum_{ky,kx,c} x[b, oy*stride - pad_t + ky, ox*stride - pad_l + kx, c]
+ *                                                                        * packed[co][(ky*KW + kx)*Cin + c]
+ * for oy < Hout, ox < Wout (positions outside [oH, oW] are skipped, input positions outside the map read 0).  x f32
+ * [B,Hin,Win,Cin] NHWC, out f32 [B,oH,oW,Cout]; Cin in {1,2,3,6,16,32}, Cout <= 32; bias may be NULL. */
+int spiral_lconv_forward(const float *x_dev, const void *w_planes_dev, int32_t n_planes, const float *bias_dev, float *out_dev,
+                         int32_t B, int32_t Hin, int32_t Win, int32_t Cin, int32_t Hout, int32_t Wout, int32_t Cout,
+                         int32_t KH, int32_t KW, int32_t stride, int32_t pad_t, int32_t pad_l, int32_t oH, int32_t oW,
+                         int32_t o_sy, int32_t o_sx, int32_t o_oy, int32_t o_ox, void *stream);
+/* dw[(ky*KW + kx)*Cin + c][co] = sum_{b,oy,ox} x[b, oy*stride - pad_t + ky, ox*stride - pad_l + kx, c] * dy[b, oy, ox, co];
+ * dy f32 [B,Hout,Wout,Cout], dw f32 [KH*KW*Cin, Cout]; workspace: spiral_lconv_wgrad_workspace_floats() floats. */
+int64_t spiral_lconv_wgrad_workspace_floats(int32_t Cin, int32_t Cout, int32_t n_taps);
+int spiral_lconv_wgrad(const float *x_dev, const float *dy_dev, float *dw_dev, float *workspace_dev, int32_t n_planes, int32_t B,
+                       int32_t Hin, int32_t Win, int32_t Cin, int32_t Hout, int32_t Wout, int32_t Cout, int32_t KH, int32_t KW,
+                       int32_t stride, int32_t pad_t, int32_t pad_l, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -109,6 +109,12 @@ SYMBOLS = {
     "spiral_pconv_forward": (C.c_int, [_vp] * 6 + [C.c_int32] * 20 + [_vp]),
     "spiral_pres_stack": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int32, C.c_int32, C.c_int32, _vp]),
     "spiral_phead_last": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, C.c_int32, C.c_int32, _vp]),
+    "spiral_lconv_packed_elems": (C.c_int64, [C.c_int32] * 3),
+    "spiral_lconv_pack": (C.c_int, [_vp, _vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_int64, C.c_int64, C.c_int64,
+                                    C.POINTER(C.c_int32), C.POINTER(C.c_int32), _vp]),
+    "spiral_lconv_forward": (C.c_int, [_vp, _vp, C.c_int32, _vp, _vp] + [C.c_int32] * 18 + [_vp]),
+    "spiral_lconv_wgrad_workspace_floats": (C.c_int64, [C.c_int32] * 3),
+    "spiral_lconv_wgrad": (C.c_int, [_vp] * 4 + [C.c_int32] * 13 + [_vp]),
     "spiral_conv_workspace_bytes": (C.c_int64, [C.c_int32] * 5),
     "spiral_conv_forward": (C.c_int, [_vp, _vp, _vp] + [C.c_int32] * 5 + [_vp, _vp]),
     "spiral_conv_dgrad": (C.c_int, [_vp, _vp, _vp] + [C.c_int32] * 5 + [_vp, _vp]),

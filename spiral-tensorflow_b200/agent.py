@@ -35,6 +35,11 @@ class Agent(object):
         torch.backends.cudnn.allow_tf32 = tf32            # policy trunk only: K1-K5 do not go through cuDNN / cuBLAS
         torch.backends.cuda.matmul.allow_tf32 = tf32
         self.policy = Policy(args, env, "global", env.observation_shape, env.action_sizes).to(self.device)
+        # learner: the trunk's and the location heads' convolutions, forward and backward, on libspiral_b200.so (bf16x3)
+        self.policy.learn_native = bool(getattr(args, "policy_learn_native", True)) and self.device.type == "cuda"
+        if self.policy.learn_native:
+            from .models import policy_learn
+            policy_learn.PLANES = 2 if getattr(args, "policy_learn_precision", "bf16x6") == "bf16x3" else 3
         self.policy_opt = FusedTFAdam(self.policy.parameters(), args.policy_lr)
         # acting path: the trunk's convolutions on libspiral_b200.so (bf16 tensor cores); the learner keeps the fp32 module
         self.actor = NativeActor(self.policy) if (getattr(args, "policy_act_native", True) and self.device.type == "cuda") else None

@@ -88,6 +88,13 @@ def build_parser():
     parser.add_argument('--policy_tf32', type=str2bool, default=True)
     # acting path (policy.act in the rollout): trunk convolutions through libspiral_b200.so in bf16 (the learner stays fp32)
     parser.add_argument('--policy_act_native', type=str2bool, default=True)
+    # learner path (policy forward / backward over the [B*T] frames): convolutions and their gradients through
+    # libspiral_b200.so (csrc/policy_learn.cu, bf16x3: fp32 parity); False = the PyTorch module's cuDNN convolutions
+    parser.add_argument('--policy_learn_native', type=str2bool, default=True)
+    # operand split of those kernels: 'bf16x6' = three bf16 planes / six products, fp32-exact operands (logits and gradients
+    # as close to float64 as PyTorch's strict-fp32 path); 'bf16x3' = two planes / three products, 16 operand bits (~2x
+    # faster, per-layer error ~1e-5: 64x finer than TF32)
+    parser.add_argument('--policy_learn_precision', type=str, default='bf16x6', choices=['bf16x6', 'bf16x3'])
     # capture the T-step rollout (policy.act + env.step) into one CUDA graph and replay it
     parser.add_argument('--cuda_graphs', type=str2bool, default=True)
     parser.add_argument('--disc_grad_precision', type=str, default='auto',

@@ -20,7 +20,7 @@ compile() { # src extra-flags...
 compile raster.cu --fmad=false ${RASTER_DEFS:-} ${PTXAS_V:+-Xptxas -v}
 compile api_env.cu --fmad=false
 compile a2c.cu ${A2C_DEFS:-} ${PTXAS_V:+-Xptxas -v}
-for f in sample.cu optim.cu policy_conv.cu disc.cu disc_tc.cu disc_conv0_mma.cu conv_ops.cu conv_tc.cu; do [ -f $f ] && compile $f ${PTXAS_V:+-Xptxas -v}; done
+for f in sample.cu optim.cu policy_conv.cu policy_learn.cu disc.cu disc_tc.cu disc_conv0_mma.cu conv_ops.cu conv_tc.cu; do [ -f $f ] && compile $f ${PTXAS_V:+-Xptxas -v}; done
 for p in "${pids[@]:-}"; do [ -n "$p" ] && wait $p; done
 OBJS=$(ls build/*.o)
 OUT=${SPIRAL_LIB_NAME:-libspiral_b200.so}

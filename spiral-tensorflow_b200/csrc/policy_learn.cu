@@ -1,0 +1,706 @@
+// policy_learn.cu -- the policy network's convolutions for the LEARNER (forward, input gradient, weight gradient), fp32
+// parity on bf16 tensor cores.
+//
+// Replaces what tf.gradients runs through the trunk and the location heads of models/policy.py when the learner
+// evaluates the A2C loss over [B*T] frames (agent.py:161-239): conv 5x5 'same' (policy.py:94-99), three conv 4x4 /
+// stride 2 'valid' (:103-109), the res-blocks' conv 3x3 'same' (:349-362), conv2d_transpose 4x4 / stride 2 'same'
+// (:242-247, :275-281) and the final conv 3x3 -> 1 channel (:290-295).  All of them are <= 32-channel convolutions on
+// <= 64x64 maps: K = taps * Cin <= 512, N = Cout <= 32 -- too narrow for a TMA / tcgen05 pipeline (a 128-wide N tile
+// would be 3/4 padding), so they are mma.sync.m16n8k16 implicit GEMMs like the acting path's (policy_conv.cu), with the
+// learner's two extra requirements:
+//
+//   * fp32 parity: activations and kernels are fp32 tensors; operands are split x = hi + lo into two bf16 planes while
+//     they are staged in shared memory and every k-step issues three MMAs (hi*hi + hi*lo + lo*hi): 16 operand bits, fp32
+//     accumulation -- the same split the discriminator's reward forward uses (disc_tc.cu)
+//   * gradients: the input gradient of every one of these layers is again one of these convolutions with a re-indexed
+//     kernel (flipped taps for stride 1; the four parity classes of a transposed convolution for stride 2; a strided
+//     convolution for the transposed ones), so `lconv_kernel` + `lpack_kernel` (a strided gather of the kernel into the
+//     [Cout][taps * Cin] layout the MMA reads) cover forward AND dgrad; `lwgrad_kernel` is the one new contraction:
+//     dW[tap, ci][co] = sum over frames and output pixels of x[pixel * stride + tap - pad][ci] * dy[pixel][co], an implicit
+//     GEMM whose reduction runs over pixels, accumulated in registers by persistent CTAs and reduced over CTAs in a fixed
+//     order (deterministic, no atomics).
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/spiral_b200.h"
+#include "common.h"
+
+namespace spiral {
+
+constexpr int kLcTw = 16, kLcTh = 8;             // output tile: 8 warps x 16 pixels
+constexpr int kLcMaxTaps = 25;
+
+struct LConvParams {
+    int B, Hin, Win, Hout, Wout;                 // input map and the grid of outputs this launch computes, per frame
+    int Cout, CoutPad;                           // CoutPad: multiple of 8, <= 32
+    int KH, KW, stride, pad_t, pad_l;
+    int K, KP, KS;                               // K = KH*KW*Cin; KP = K rounded up to 16; KS = KP + 8 (row stride, bf16)
+    int IH, IW;                                  // staged input tile
+    int tiles_x, tiles_y;
+    int oH, oW, o_sy, o_sx, o_oy, o_ox;          // output pixel (oy, ox) -> (oy*o_sy + o_oy, ox*o_sx + o_ox) of an [oH, oW] map
+};
+
+__device__ __forceinline__ void lc_mma(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2])
+{
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
+// v = p[0] + p[1] (+ p[2]) + O(2^-8NPL |v|): NPL bf16 planes of 8 bits each (16 bits: "bf16x3", the three products
+// p0*q0 + p0*q1 + p1*q0; 24 bits: "bf16x6", fp32-exact operands, six products)
+template <int NPL>
+__device__ __forceinline__ void lc_split(float v, uint16_t (&pl)[NPL])
+{
+#pragma unroll
+    for (int i = 0; i < NPL; i++) {
+        const __nv_bfloat16 h = __float2bfloat16_rn(v);
+        pl[i] = __bfloat16_as_ushort(h);
+        v -= __bfloat162float(h);
+    }
+}
+
+// The tensor core adds every MMA into its fp32 accumulator with truncation, so the error of an accumulator grows with the
+// number of MMAs chained into it.  Two accumulators per tile: `hi` takes only the dominant p0*q0 product of each k-step
+// (K/16 MMAs), `lo` every cross product (2^-8 .. 2^-16 of the result: their truncation is invisible); the epilogue adds the
+// two in registers with round-to-nearest.
+template <int NPL>
+__device__ __forceinline__ void lc_mma_planes(float (&hi)[4], float (&lo)[4], const uint32_t (&a)[NPL][4], const uint32_t (&b)[NPL][2])
+{
+    if (NPL == 3) {
+        lc_mma(lo, a[2], b[0]);
+        lc_mma(lo, a[0], b[2]);
+        lc_mma(lo, a[1], b[1]);
+    }
+    lc_mma(lo, a[1], b[0]);
+    lc_mma(lo, a[0], b[1]);
+    lc_mma(hi, a[0], b[0]);
+}
+
+// ------------------------------------------------------------------------------------------
+// kernel packing: packed_{hi,lo}[row][tap * Ck + c] = w[row * s_row + c * s_c + ky(tap) * s_ky + kx(tap) * s_kx]
+// (zero for row >= rows and for the k padding).  With the strides and the tap table chosen by the caller this is the
+// forward kernel of a convolution, its flipped / transposed adjoint, or one parity class of a transposed convolution.
+// ------------------------------------------------------------------------------------------
+struct LPackParams {
+    int rows, rows_pad, Ck, n_taps, K, KS;
+    long long s_row, s_c, s_ky, s_kx;
+    int tap_ky[kLcMaxTaps], tap_kx[kLcMaxTaps];
+};
+
+template <int NPL>
+__global__ void __launch_bounds__(256)
+lpack_kernel(const __grid_constant__ LPackParams p, const float *__restrict__ w, uint16_t *__restrict__ planes)
+{
+    const int n = p.rows_pad * p.KS;                                          // elements per plane; planes are contiguous
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const int row = i / p.KS, k = i - row * p.KS;
+        float v = 0.0f;
+        if (row < p.rows && k < p.K) {
+            const int tap = k / p.Ck, c = k - tap * p.Ck;
+            v = w[row * p.s_row + c * p.s_c + p.tap_ky[tap] * p.s_ky + p.tap_kx[tap] * p.s_kx];
+        }
+        uint16_t pl[NPL];
+        lc_split<NPL>(v, pl);
+#pragma unroll
+        for (int q = 0; q < NPL; q++) planes[(size_t)q * n + i] = pl[q];
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// forward / dgrad: out[frame, scatter(oy, ox), co] = bias[co] + sum_k x[frame, oy*stride - pad + ky, ox*stride - pad + kx, c] * W[co][k]
+// ------------------------------------------------------------------------------------------
+// stage an fp32 NHWC input tile (zero outside the map) as NPL bf16 planes s_i[q][IH][IW][CIN]
+template <int CIN, int NPL>
+__device__ __forceinline__ void lc_stage_input(const LConvParams &p, const float *__restrict__ xi, int iy0, int ix0,
+                                               uint16_t *s_i, int n_in8, int tid)
+{
+    if (CIN % 4 == 0) {
+        constexpr int V = CIN / 4 > 0 ? CIN / 4 : 1;                           // float4 per pixel
+        constexpr int U = 4;                                                   // loads in flight per thread: the staging is
+        const int n_vec = p.IH * p.IW * V;                                     // latency-bound (8 warps per SM), not bandwidth-bound
+        for (int i0 = tid; i0 < n_vec; i0 += 256 * U) {
+            float4 val[U];
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                const int i = i0 + u * 256;
+                val[u] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                if (i < n_vec) {
+                    const int pix = i / V, v = i - pix * V;
+                    const int ly = pix / p.IW, lx = pix - ly * p.IW;
+                    const int iy = iy0 + ly, ix = ix0 + lx;
+                    if (iy >= 0 && iy < p.Hin && ix >= 0 && ix < p.Win)
+                        val[u] = __ldg(reinterpret_cast<const float4 *>(xi + ((size_t)iy * p.Win + ix) * CIN) + v);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                const int i = i0 + u * 256;
+                if (i < n_vec) {
+                    uint16_t a[NPL], b[NPL], c[NPL], d[NPL];
+                    lc_split<NPL>(val[u].x, a); lc_split<NPL>(val[u].y, b); lc_split<NPL>(val[u].z, c); lc_split<NPL>(val[u].w, d);
+#pragma unroll
+                    for (int q = 0; q < NPL; q++)
+                        *reinterpret_cast<uint2 *>(s_i + (size_t)q * n_in8 + (size_t)i * 4) =
+                            make_uint2(a[q] | ((uint32_t)b[q] << 16), c[q] | ((uint32_t)d[q] << 16));
+                }
+            }
+        }
+    } else {
+        const int n_in = p.IH * p.IW * CIN;
+        constexpr int U = 8;
+        for (int i0 = tid; i0 < n_in; i0 += 256 * U) {
+            float val[U];
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                const int i = i0 + u * 256;
+                val[u] = 0.0f;
+                if (i < n_in) {
+                    const int pix = i / CIN, c = i - pix * CIN;
+                    const int ly = pix / p.IW, lx = pix - ly * p.IW;
+                    const int iy = iy0 + ly, ix = ix0 + lx;
+                    if (iy >= 0 && iy < p.Hin && ix >= 0 && ix < p.Win) val[u] = __ldg(xi + ((size_t)iy * p.Win + ix) * CIN + c);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                const int i = i0 + u * 256;
+                if (i < n_in) {
+                    uint16_t pl[NPL];
+                    lc_split<NPL>(val[u], pl);
+#pragma unroll
+                    for (int q = 0; q < NPL; q++) s_i[(size_t)q * n_in8 + i] = pl[q];
+                }
+            }
+        }
+    }
+}
+
+__device__ __forceinline__ void lc_koff_table(const LConvParams &p, int cin, int *s_koff, int tid)
+{
+    for (int k = tid; k < p.KP; k += 256) {
+        int off = 0;
+        if (k < p.K) {
+            const int tap = k / cin, c = k - tap * cin;
+            const int ky = tap / p.KW, kx = tap - ky * p.KW;
+            off = (ky * p.IW + kx) * cin + c;
+        }
+        s_koff[k] = off;
+    }
+}
+
+template <int CIN, int NPL>
+__global__ void __launch_bounds__(256)
+lconv_kernel(const __grid_constant__ LConvParams p, const float *__restrict__ x, const uint16_t *__restrict__ w_planes,
+             const float *__restrict__ bias, float *__restrict__ out)
+{
+    extern __shared__ __align__(16) uint8_t sm_raw[];
+    const int n_w = p.CoutPad * p.KS;                                          // multiple of 8 (KS is)
+    const int n_in8 = (p.IH * p.IW * CIN + 7) & ~7;
+    uint16_t *s_w = reinterpret_cast<uint16_t *>(sm_raw);                     // [NPL][CoutPad][KS]
+    uint16_t *s_i = s_w + NPL * n_w;                                           // [NPL][IH][IW][CIN]
+    int *s_koff = reinterpret_cast<int *>(s_i + NPL * n_in8);                  // [KP]
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tiles = p.tiles_x * p.tiles_y;
+    const int img = blockIdx.x / tiles;
+    const int trem = blockIdx.x % tiles;
+    const int oy0 = (trem / p.tiles_x) * kLcTh, ox0 = (trem % p.tiles_x) * kLcTw;
+
+    {
+        const uint4 *gw = reinterpret_cast<const uint4 *>(w_planes);
+        uint4 *sw = reinterpret_cast<uint4 *>(s_w);
+        for (int i = tid; i < NPL * n_w / 8; i += 256) sw[i] = __ldg(gw + i);
+        lc_koff_table(p, CIN, s_koff, tid);
+        lc_stage_input<CIN, NPL>(p, x + (size_t)img * p.Hin * p.Win * CIN, oy0 * p.stride - p.pad_t, ox0 * p.stride - p.pad_l,
+                                 s_i, n_in8, tid);
+    }
+    __syncthreads();
+
+    // warp = output row `warp` of the tile, 16 pixels x CoutPad channels
+    const int g = lane >> 2, t = lane & 3;
+    const int base0 = ((warp * p.stride) * p.IW + g * p.stride) * CIN;         // pixel g
+    const int base1 = base0 + 8 * p.stride * CIN;                               // pixel g + 8
+    const int NT = p.CoutPad >> 3;
+    float acc[4][4], acl[4][4];
+#pragma unroll
+    for (int nt = 0; nt < 4; nt++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) { acc[nt][j] = 0.0f; acl[nt][j] = 0.0f; }
+
+#pragma unroll 1
+    for (int ks = 0; ks < p.KP / 16; ks++) {
+        const int k0 = ks * 16 + 2 * t;
+        uint32_t a[NPL][4];
+        if (CIN % 2 == 0) {
+            // k0 is even and CIN is even: k0 and k0+1 are adjacent channels of one tap -> one 32-bit load
+            const int o0 = s_koff[k0], o8 = s_koff[k0 + 8];
+#pragma unroll
+            for (int q = 0; q < NPL; q++) {
+                const uint16_t *si = s_i + (size_t)q * n_in8;
+                a[q][0] = *reinterpret_cast<const uint32_t *>(si + base0 + o0);
+                a[q][1] = *reinterpret_cast<const uint32_t *>(si + base1 + o0);
+                a[q][2] = *reinterpret_cast<const uint32_t *>(si + base0 + o8);
+                a[q][3] = *reinterpret_cast<const uint32_t *>(si + base1 + o8);
+            }
+        } else {
+            const int o0 = s_koff[k0], o1 = s_koff[k0 + 1], o8 = s_koff[k0 + 8], o9 = s_koff[k0 + 9];
+#pragma unroll
+            for (int q = 0; q < NPL; q++) {
+                const uint16_t *si = s_i + (size_t)q * n_in8;
+                a[q][0] = (uint32_t)si[base0 + o0] | ((uint32_t)si[base0 + o1] << 16);
+                a[q][1] = (uint32_t)si[base1 + o0] | ((uint32_t)si[base1 + o1] << 16);
+                a[q][2] = (uint32_t)si[base0 + o8] | ((uint32_t)si[base0 + o9] << 16);
+                a[q][3] = (uint32_t)si[base1 + o8] | ((uint32_t)si[base1 + o9] << 16);
+            }
+        }
+        // k padding: the packed kernel is zero there and the gathered activations are finite values of the tile
+#pragma unroll
+        for (int nt = 0; nt < 4; nt++) {
+            if (nt < NT) {
+                const int wrow = (nt * 8 + g) * p.KS + k0;
+                uint32_t b[NPL][2];
+#pragma unroll
+                for (int q = 0; q < NPL; q++) {
+                    b[q][0] = *reinterpret_cast<const uint32_t *>(s_w + (size_t)q * n_w + wrow);
+                    b[q][1] = *reinterpret_cast<const uint32_t *>(s_w + (size_t)q * n_w + wrow + 8);
+                }
+                lc_mma_planes<NPL>(acc[nt], acl[nt], a, b);
+            }
+        }
+    }
+#pragma unroll
+    for (int nt = 0; nt < 4; nt++)
+#pragma unroll
+        for (int j = 0; j < 4; j++) acc[nt][j] += acl[nt][j];
+
+    const int oy = oy0 + warp;
+    if (oy >= p.Hout) return;
+    const int py = oy * p.o_sy + p.o_oy;
+    if (py < 0 || py >= p.oH) return;
+    const size_t frame_out = (size_t)img * p.oH * p.oW;
+#pragma unroll
+    for (int half = 0; half < 2; half++) {
+        const int ox = ox0 + g + 8 * half;
+        if (ox >= p.Wout) continue;
+        const int px = ox * p.o_sx + p.o_ox;
+        if (px < 0 || px >= p.oW) continue;
+        const size_t pix = frame_out + (size_t)py * p.oW + px;
+#pragma unroll
+        for (int nt = 0; nt < 4; nt++) {
+            if (nt >= NT) continue;
+            const int ch = nt * 8 + 2 * t;
+            float v0 = acc[nt][2 * half], v1 = acc[nt][2 * half + 1];
+            if (bias) {
+                if (ch < p.Cout) v0 += __ldg(bias + ch);
+                if (ch + 1 < p.Cout) v1 += __ldg(bias + ch + 1);
+            }
+            if ((p.Cout & 1) == 0 && ch + 1 < p.Cout) {
+                *reinterpret_cast<float2 *>(out + pix * p.Cout + ch) = make_float2(v0, v1);
+            } else {
+                if (ch < p.Cout) out[pix * p.Cout + ch] = v0;
+                if (ch + 1 < p.Cout) out[pix * p.Cout + ch + 1] = v1;
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// wgrad: dW[k = tap * CIN + c][co] = sum_{frame, oy, ox} x[frame, oy*stride - pad + ky, ox*stride - pad + kx, c] * dy[frame, oy, ox, co]
+// Persistent CTAs walk (frame, 8x16 tile of output pixels) work items; per item the input tile and the dy tile are
+// staged as bf16 planes, dy TRANSPOSED ([co][pixel]) so that B fragments are 32-bit loads; warp w owns the m-tiles
+// (16 rows of k) w, w + 8, ... and keeps their accumulators in registers across all items; partial[cta][k][co] at the end.
+// ------------------------------------------------------------------------------------------
+constexpr int kLwMaxMt = 4;                      // m-tiles per warp: K <= 8 * 4 * 16 = 512
+constexpr int kLwPix = kLcTw * kLcTh;            // 128 reduction elements per item
+constexpr int kLwPS = kLwPix + 8;                // row stride of the transposed dy tile
+
+template <int CIN, int NPL>
+__global__ void __launch_bounds__(256, 1)
+lwgrad_kernel(const __grid_constant__ LConvParams p, const float *__restrict__ x, const float *__restrict__ dy,
+              float *__restrict__ partial, int n_items)
+{
+    extern __shared__ __align__(16) uint8_t sm_raw[];
+    const int n_in8 = (p.IH * p.IW * CIN + 7) & ~7;
+    const int n_d = p.CoutPad * kLwPS;
+    uint16_t *s_i = reinterpret_cast<uint16_t *>(sm_raw);                     // [NPL][IH][IW][CIN]
+    uint16_t *s_d = s_i + NPL * n_in8;                                         // [NPL][CoutPad][kLwPS]
+    int *s_koff = reinterpret_cast<int *>(s_d + NPL * n_d);                    // [KP]
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, t = lane & 3;
+    const int NT = p.CoutPad >> 3;
+    const int n_mt = p.KP / 16;
+    const int tiles = p.tiles_x * p.tiles_y;
+
+    lc_koff_table(p, CIN, s_koff, tid);
+
+    // `hi` (dominant products) is flushed into the fp32 sum `tot` after every work item, so that an accumulator never chains
+    // more than 8 MMAs; `lo` (cross products) runs through all items
+    float acc[kLwMaxMt][4][4], acl[kLwMaxMt][4][4], tot[kLwMaxMt][4][4];
+#pragma unroll
+    for (int m = 0; m < kLwMaxMt; m++)
+#pragma unroll
+        for (int nt = 0; nt < 4; nt++)
+#pragma unroll
+            for (int j = 0; j < 4; j++) { acc[m][nt][j] = 0.0f; acl[m][nt][j] = 0.0f; tot[m][nt][j] = 0.0f; }
+
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int img = item / tiles, trem = item - img * tiles;
+        const int oy0 = (trem / p.tiles_x) * kLcTh, ox0 = (trem % p.tiles_x) * kLcTw;
+        __syncthreads();                                                       // the previous item's MMAs are done with the tiles
+        lc_stage_input<CIN, NPL>(p, x + (size_t)img * p.Hin * p.Win * CIN, oy0 * p.stride - p.pad_t, ox0 * p.stride - p.pad_l,
+                                 s_i, n_in8, tid);
+        {
+            // dy tile, transposed: s_d[q][co][pixel]; pixels outside the output map are zero
+            const float *di = dy + (size_t)img * p.Hout * p.Wout * p.Cout;
+            constexpr int U = 4;
+            const int n_dy = kLwPix * p.CoutPad;
+            for (int i0 = tid; i0 < n_dy; i0 += 256 * U) {
+                float val[U];
+#pragma unroll
+                for (int u = 0; u < U; u++) {
+                    const int i = i0 + u * 256;
+                    const int pix = i / p.CoutPad, co = i - pix * p.CoutPad;
+                    const int oy = oy0 + pix / kLcTw, ox = ox0 + pix % kLcTw;
+                    val[u] = 0.0f;
+                    if (i < n_dy && co < p.Cout && oy < p.Hout && ox < p.Wout) val[u] = __ldg(di + ((size_t)oy * p.Wout + ox) * p.Cout + co);
+                }
+#pragma unroll
+                for (int u = 0; u < U; u++) {
+                    const int i = i0 + u * 256;
+                    if (i < n_dy) {
+                        const int pix = i / p.CoutPad, co = i - pix * p.CoutPad;
+                        uint16_t pl[NPL];
+                        lc_split<NPL>(val[u], pl);
+#pragma unroll
+                        for (int q = 0; q < NPL; q++) s_d[(size_t)q * n_d + co * kLwPS + pix] = pl[q];
+                    }
+                }
+            }
+        }
+        __syncthreads();
+
+#pragma unroll 1
+        for (int ks = 0; ks < kLcTh; ks++) {                                   // 16 pixels per k-step: tile row ks
+            // B fragments (dy^T): b[0] = {B[2t][n], B[2t+1][n]}, b[1] = {B[2t+8][n], B[2t+9][n]}, n = nt*8 + g
+            uint32_t b[4][NPL][2];
+#pragma unroll
+            for (int nt = 0; nt < 4; nt++) {
+                if (nt < NT) {
+                    const int o = (nt * 8 + g) * kLwPS + ks * kLcTw + 2 * t;
+#pragma unroll
+                    for (int q = 0; q < NPL; q++) {
+                        b[nt][q][0] = *reinterpret_cast<const uint32_t *>(s_d + (size_t)q * n_d + o);
+                        b[nt][q][1] = *reinterpret_cast<const uint32_t *>(s_d + (size_t)q * n_d + o + 8);
+                    }
+                }
+            }
+            const int pb = ((ks * p.stride) * p.IW) * CIN;                     // tile row ks
+            const int c0 = pb + (2 * t) * p.stride * CIN, c1 = c0 + p.stride * CIN;        // pixels 2t, 2t+1
+            const int c8 = c0 + 8 * p.stride * CIN, c9 = c8 + p.stride * CIN;              // pixels 2t+8, 2t+9
+#pragma unroll
+            for (int m = 0; m < kLwMaxMt; m++) {
+                const int mt = warp + 8 * m;
+                if (mt < n_mt) {
+                    const int r0 = s_koff[mt * 16 + g], r1 = s_koff[mt * 16 + g + 8];
+                    uint32_t a[NPL][4];
+#pragma unroll
+                    for (int q = 0; q < NPL; q++) {
+                        const uint16_t *si = s_i + (size_t)q * n_in8;
+                        a[q][0] = (uint32_t)si[r0 + c0] | ((uint32_t)si[r0 + c1] << 16);
+                        a[q][1] = (uint32_t)si[r1 + c0] | ((uint32_t)si[r1 + c1] << 16);
+                        a[q][2] = (uint32_t)si[r0 + c8] | ((uint32_t)si[r0 + c9] << 16);
+                        a[q][3] = (uint32_t)si[r1 + c8] | ((uint32_t)si[r1 + c9] << 16);
+                    }
+#pragma unroll
+                    for (int nt = 0; nt < 4; nt++) {
+                        if (nt < NT) lc_mma_planes<NPL>(acc[m][nt], acl[m][nt], a, b[nt]);
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int m = 0; m < kLwMaxMt; m++)
+#pragma unroll
+            for (int nt = 0; nt < 4; nt++)
+#pragma unroll
+                for (int j = 0; j < 4; j++) { tot[m][nt][j] += acc[m][nt][j]; acc[m][nt][j] = 0.0f; }
+    }
+#pragma unroll
+    for (int m = 0; m < kLwMaxMt; m++)
+#pragma unroll
+        for (int nt = 0; nt < 4; nt++)
+#pragma unroll
+            for (int j = 0; j < 4; j++) acc[m][nt][j] = tot[m][nt][j] + acl[m][nt][j];
+
+    // partial[cta][k][co]: accumulator fragment (rows g, g+8; columns 2t, 2t+1 of n-tile nt)
+    float *mine = partial + (size_t)blockIdx.x * p.KP * p.CoutPad;
+#pragma unroll
+    for (int m = 0; m < kLwMaxMt; m++) {
+        const int mt = warp + 8 * m;
+        if (mt >= n_mt) continue;
+#pragma unroll
+        for (int nt = 0; nt < 4; nt++) {
+            if (nt >= NT) continue;
+            const int col = nt * 8 + 2 * t;
+            *reinterpret_cast<float2 *>(mine + (size_t)(mt * 16 + g) * p.CoutPad + col) = make_float2(acc[m][nt][0], acc[m][nt][1]);
+            *reinterpret_cast<float2 *>(mine + (size_t)(mt * 16 + g + 8) * p.CoutPad + col) = make_float2(acc[m][nt][2], acc[m][nt][3]);
+        }
+    }
+}
+
+// Cout == 1 (the location heads' final 3x3 -> 1 convolution): dW[tap][c] = sum_pixels x[pixel + tap][c] * dy[pixel] is a
+// correlation with a scalar map -- on the MMA path 7 of 8 output columns would be padding.  Plain fp32 FMAs instead: the
+// input tile is staged as fp32, thread (pixel row r = tid / 32, channel c = tid % 32) runs over the 16 pixels of its row
+// and the taps, accumulates in registers across all work items; rows are combined through shared memory at the end.
+// Same partial[cta][k][CoutPad = 8] layout as lwgrad_kernel, so the same reduction follows.
+template <int CIN>
+__global__ void __launch_bounds__(256)
+lwgrad1_kernel(const __grid_constant__ LConvParams p, const float *__restrict__ x, const float *__restrict__ dy,
+               float *__restrict__ partial, int n_items)
+{
+    extern __shared__ __align__(16) uint8_t sm_raw[];
+    float *s_x = reinterpret_cast<float *>(sm_raw);                            // [IH][IW][CIN]
+    float *s_dy = s_x + p.IH * p.IW * CIN;                                     // [128]
+    __shared__ int s_toff[kLcMaxTaps];                                         // tap -> offset in the staged tile
+    const int tid = threadIdx.x;
+    if (tid < kLcMaxTaps) s_toff[tid] = tid < p.KH * p.KW ? ((tid / p.KW) * p.IW + tid % p.KW) * CIN : 0;
+    const int c = tid % CIN, r = tid / CIN;                                    // rows handled: r, r + 256 / CIN, ...
+    constexpr int RSTEP = 256 / CIN;
+    const int tiles = p.tiles_x * p.tiles_y;
+    const int taps = p.KH * p.KW;
+    float acc[kLcMaxTaps];
+#pragma unroll
+    for (int i = 0; i < kLcMaxTaps; i++) acc[i] = 0.0f;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int img = item / tiles, trem = item - img * tiles;
+        const int oy0 = (trem / p.tiles_x) * kLcTh, ox0 = (trem % p.tiles_x) * kLcTw;
+        __syncthreads();
+        const float *xi = x + (size_t)img * p.Hin * p.Win * CIN;
+        const int iy0 = oy0 * p.stride - p.pad_t, ix0 = ox0 * p.stride - p.pad_l;
+        {
+            // float4 loads, 4 in flight per thread (the staging is latency-bound)
+            constexpr int V = CIN / 4, U = 4;
+            const int n_vec = p.IH * p.IW * V;
+            for (int i0 = tid; i0 < n_vec; i0 += 256 * U) {
+                float4 val[U];
+#pragma unroll
+                for (int u = 0; u < U; u++) {
+                    const int i = i0 + u * 256;
+                    val[u] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                    if (i < n_vec) {
+                        const int pix = i / V, v = i - pix * V;
+                        const int ly = pix / p.IW, lx = pix - ly * p.IW;
+                        const int iy = iy0 + ly, ix = ix0 + lx;
+                        if (iy >= 0 && iy < p.Hin && ix >= 0 && ix < p.Win)
+                            val[u] = __ldg(reinterpret_cast<const float4 *>(xi + ((size_t)iy * p.Win + ix) * CIN) + v);
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < U; u++) {
+                    const int i = i0 + u * 256;
+                    if (i < n_vec) reinterpret_cast<float4 *>(s_x)[i] = val[u];
+                }
+            }
+        }
+        if (tid < kLcTw * kLcTh) {
+            const int oy = oy0 + tid / kLcTw, ox = ox0 + tid % kLcTw;
+            s_dy[tid] = (oy < p.Hout && ox < p.Wout) ? __ldg(dy + ((size_t)img * p.Hout + oy) * p.Wout + ox) : 0.0f;
+        }
+        __syncthreads();
+        for (int row = r; row < kLcTh; row += RSTEP) {
+#pragma unroll 4
+            for (int col = 0; col < kLcTw; col++) {
+                const float d = s_dy[row * kLcTw + col];
+                const float *xp = s_x + ((row * p.stride) * p.IW + col * p.stride) * CIN + c;
+#pragma unroll
+                for (int tp = 0; tp < kLcMaxTaps; tp++)
+                    if (tp < taps) acc[tp] = fmaf(xp[s_toff[tp]], d, acc[tp]);
+            }
+        }
+    }
+    // combine the row groups: s_red[g][tap][c]
+    __syncthreads();
+    float *s_red = reinterpret_cast<float *>(sm_raw);
+    for (int tp = 0; tp < taps; tp++) s_red[(r * taps + tp) * CIN + c] = acc[tp];
+    __syncthreads();
+    float *mine = partial + (size_t)blockIdx.x * p.KP * p.CoutPad;
+    for (int k = tid; k < p.KP; k += 256) {
+        float sum = 0.0f;
+        if (k < p.K) {
+            const int tp = k / CIN, cc = k - tp * CIN;
+            for (int g = 0; g < RSTEP && g < kLcTh; g++) sum += s_red[(g * taps + tp) * CIN + cc];
+        }
+        for (int j = 0; j < p.CoutPad; j++) mine[(size_t)k * p.CoutPad + j] = j == 0 ? sum : 0.0f;
+    }
+}
+
+// dw[k][co] (k < K, co < Cout) = sum over CTAs, fixed order
+__global__ void __launch_bounds__(256)
+lwgrad_reduce_kernel(const float *__restrict__ partial, float *__restrict__ dw, int n_cta, int K, int KP, int Cout, int CoutPad)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= K * Cout) return;
+    const int k = i / Cout, co = i - k * Cout;
+    float s = 0.0f;
+    for (int c = 0; c < n_cta; c++) s += partial[((size_t)c * KP + k) * CoutPad + co];
+    dw[i] = s;
+}
+
+static void lc_fill(LConvParams &p, int B, int Hin, int Win, int Cin, int Hout, int Wout, int Cout, int KH, int KW, int stride,
+                    int pad_t, int pad_l, int oH, int oW, int o_sy, int o_sx, int o_oy, int o_ox)
+{
+    p.B = B; p.Hin = Hin; p.Win = Win; p.Hout = Hout; p.Wout = Wout;
+    p.Cout = Cout; p.CoutPad = (Cout + 7) & ~7;
+    p.KH = KH; p.KW = KW; p.stride = stride; p.pad_t = pad_t; p.pad_l = pad_l;
+    p.K = KH * KW * Cin; p.KP = (p.K + 15) & ~15; p.KS = p.KP + 8;
+    p.IH = (kLcTh - 1) * stride + KH; p.IW = (kLcTw - 1) * stride + KW;
+    p.tiles_x = (Wout + kLcTw - 1) / kLcTw; p.tiles_y = (Hout + kLcTh - 1) / kLcTh;
+    p.oH = oH; p.oW = oW; p.o_sy = o_sy; p.o_sx = o_sx; p.o_oy = o_oy; p.o_ox = o_ox;
+}
+
+constexpr size_t kLcSmemMax = 227 * 1024;        // per-CTA shared memory on sm_100
+
+}  // namespace spiral
+
+using namespace spiral;
+
+static bool lc_cin_ok(int Cin) { return Cin == 1 || Cin == 2 || Cin == 3 || Cin == 6 || Cin == 16 || Cin == 32; }
+
+// elements of ONE plane of a packed kernel
+extern "C" int64_t spiral_lconv_packed_elems(int32_t Cin, int32_t Cout, int32_t n_taps)
+{
+    const int K = n_taps * Cin, KP = (K + 15) & ~15, KS = KP + 8, CoutPad = (Cout + 7) & ~7;
+    return (int64_t)CoutPad * KS;
+}
+
+extern "C" int spiral_lconv_pack(const float *w, void *packed_planes, int32_t n_planes, int32_t rows, int32_t Ck, int32_t n_taps,
+                                 int64_t s_row, int64_t s_c, int64_t s_ky, int64_t s_kx, const int32_t *tap_ky,
+                                 const int32_t *tap_kx, void *stream)
+{
+    SPIRAL_REQUIRE(w); SPIRAL_REQUIRE(packed_planes); SPIRAL_REQUIRE(tap_ky); SPIRAL_REQUIRE(tap_kx);
+    if (rows < 1 || rows > 32 || !lc_cin_ok(Ck) || n_taps < 1 || n_taps > kLcMaxTaps || (n_planes != 2 && n_planes != 3))
+        return spiral_set_error(SPIRAL_EINVAL, "lconv_pack: unsupported shape rows=%d Ck=%d taps=%d planes=%d", rows, Ck, n_taps, n_planes);
+    LPackParams p;
+    p.rows = rows; p.rows_pad = (rows + 7) & ~7; p.Ck = Ck; p.n_taps = n_taps;
+    p.K = n_taps * Ck; p.KS = ((p.K + 15) & ~15) + 8;
+    p.s_row = s_row; p.s_c = s_c; p.s_ky = s_ky; p.s_kx = s_kx;
+    for (int i = 0; i < kLcMaxTaps; i++) { p.tap_ky[i] = i < n_taps ? tap_ky[i] : 0; p.tap_kx[i] = i < n_taps ? tap_kx[i] : 0; }
+    const int n = p.rows_pad * p.KS;
+    if (n_planes == 2) lpack_kernel<2><<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(p, w, (uint16_t *)packed_planes);
+    else lpack_kernel<3><<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(p, w, (uint16_t *)packed_planes);
+    const cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? SPIRAL_OK : spiral_cuda_error(e, "spiral_lconv_pack");
+}
+
+template <int CIN, int NPL>
+static int lconv_launch(const LConvParams &p, const float *x, const void *w, const float *bias, float *out, int grid, size_t smem,
+                        cudaStream_t st)
+{
+    static bool attr = false;
+    if (!attr) {
+        const cudaError_t e = cudaFuncSetAttribute(lconv_kernel<CIN, NPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLcSmemMax);
+        if (e != cudaSuccess) return spiral_cuda_error(e, "cudaFuncSetAttribute(lconv_kernel)");
+        attr = true;
+    }
+    lconv_kernel<CIN, NPL><<<grid, 256, smem, st>>>(p, x, (const uint16_t *)w, bias, out);
+    return SPIRAL_OK;
+}
+
+template <int CIN, int NPL>
+static int lwgrad_launch(const LConvParams &p, const float *x, const float *dy, float *ws, int n_items, int grid, size_t smem,
+                         cudaStream_t st)
+{
+    static bool attr = false;
+    if (!attr) {
+        const cudaError_t e = cudaFuncSetAttribute(lwgrad_kernel<CIN, NPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLcSmemMax);
+        if (e != cudaSuccess) return spiral_cuda_error(e, "cudaFuncSetAttribute(lwgrad_kernel)");
+        attr = true;
+    }
+    lwgrad_kernel<CIN, NPL><<<grid, 256, smem, st>>>(p, x, dy, ws, n_items);
+    return SPIRAL_OK;
+}
+
+#define LC_DISPATCH(FN, ...)                                                                                          \
+    do {                                                                                                              \
+        int rc_;                                                                                                      \
+        if (n_planes == 2) {                                                                                          \
+            switch (Cin) {                                                                                            \
+            case 1: rc_ = FN<1, 2>(__VA_ARGS__); break;                                                               \
+            case 2: rc_ = FN<2, 2>(__VA_ARGS__); break;                                                               \
+            case 3: rc_ = FN<3, 2>(__VA_ARGS__); break;                                                               \
+            case 6: rc_ = FN<6, 2>(__VA_ARGS__); break;                                                               \
+            case 16: rc_ = FN<16, 2>(__VA_ARGS__); break;                                                             \
+            default: rc_ = FN<32, 2>(__VA_ARGS__); break;                                                             \
+            }                                                                                                         \
+        } else {                                                                                                      \
+            switch (Cin) {                                                                                            \
+            case 1: rc_ = FN<1, 3>(__VA_ARGS__); break;                                                               \
+            case 2: rc_ = FN<2, 3>(__VA_ARGS__); break;                                                               \
+            case 3: rc_ = FN<3, 3>(__VA_ARGS__); break;                                                               \
+            case 6: rc_ = FN<6, 3>(__VA_ARGS__); break;                                                               \
+            case 16: rc_ = FN<16, 3>(__VA_ARGS__); break;                                                             \
+            default: rc_ = FN<32, 3>(__VA_ARGS__); break;                                                             \
+            }                                                                                                         \
+        }                                                                                                             \
+        if (rc_ != SPIRAL_OK) return rc_;                                                                             \
+    } while (0)
+
+extern "C" int spiral_lconv_forward(const float *x, const void *w_planes, int32_t n_planes, const float *bias, float *out,
+                                    int32_t B, int32_t Hin, int32_t Win, int32_t Cin, int32_t Hout, int32_t Wout, int32_t Cout,
+                                    int32_t KH, int32_t KW, int32_t stride, int32_t pad_t, int32_t pad_l, int32_t oH,
+                                    int32_t oW, int32_t o_sy, int32_t o_sx, int32_t o_oy, int32_t o_ox, void *stream)
+{
+    SPIRAL_REQUIRE(x); SPIRAL_REQUIRE(w_planes); SPIRAL_REQUIRE(out);
+    if (B <= 0 || Cout <= 0 || Cout > 32 || !lc_cin_ok(Cin) || KH * KW > kLcMaxTaps || (n_planes != 2 && n_planes != 3))
+        return spiral_set_error(SPIRAL_EINVAL, "lconv: unsupported shape Cin=%d Cout=%d taps=%d planes=%d", Cin, Cout, KH * KW, n_planes);
+    LConvParams p;
+    lc_fill(p, B, Hin, Win, Cin, Hout, Wout, Cout, KH, KW, stride, pad_t, pad_l, oH, oW, o_sy, o_sx, o_oy, o_ox);
+    const size_t n_w = (size_t)p.CoutPad * p.KS, n_in8 = ((size_t)p.IH * p.IW * Cin + 7) & ~(size_t)7;
+    const size_t smem = (size_t)n_planes * (n_w + n_in8) * 2 + (size_t)p.KP * 4;
+    if (smem > kLcSmemMax) return spiral_set_error(SPIRAL_EUNSUPPORTED, "lconv: tile does not fit shared memory (%zu bytes)", smem);
+    const int grid = B * p.tiles_x * p.tiles_y;
+    cudaStream_t st = (cudaStream_t)stream;
+    LC_DISPATCH(lconv_launch, p, x, w_planes, bias, out, grid, smem, st);
+    const cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? SPIRAL_OK : spiral_cuda_error(e, "spiral_lconv_forward");
+}
+
+extern "C" int64_t spiral_lconv_wgrad_workspace_floats(int32_t Cin, int32_t Cout, int32_t n_taps)
+{
+    const int K = n_taps * Cin, KP = (K + 15) & ~15, CoutPad = (Cout + 7) & ~7;
+    return (int64_t)(148 * 2) * KP * CoutPad;
+}
+
+extern "C" int spiral_lconv_wgrad(const float *x, const float *dy, float *dw, float *workspace, int32_t n_planes, int32_t B,
+                                  int32_t Hin, int32_t Win, int32_t Cin, int32_t Hout, int32_t Wout, int32_t Cout, int32_t KH,
+                                  int32_t KW, int32_t stride, int32_t pad_t, int32_t pad_l, void *stream)
+{
+    SPIRAL_REQUIRE(x); SPIRAL_REQUIRE(dy); SPIRAL_REQUIRE(dw); SPIRAL_REQUIRE(workspace);
+    if (B <= 0 || Cout <= 0 || Cout > 32 || !lc_cin_ok(Cin) || KH * KW > kLcMaxTaps || KH * KW * Cin > 8 * kLwMaxMt * 16 ||
+        (n_planes != 2 && n_planes != 3))
+        return spiral_set_error(SPIRAL_EINVAL, "lconv_wgrad: unsupported shape Cin=%d Cout=%d taps=%d planes=%d", Cin, Cout, KH * KW, n_planes);
+    LConvParams p;
+    lc_fill(p, B, Hin, Win, Cin, Hout, Wout, Cout, KH, KW, stride, pad_t, pad_l, Hout, Wout, 1, 1, 0, 0);
+    const size_t n_in8 = ((size_t)p.IH * p.IW * Cin + 7) & ~(size_t)7;
+    const size_t smem = (size_t)n_planes * (n_in8 + (size_t)p.CoutPad * kLwPS) * 2 + (size_t)p.KP * 4;
+    if (smem > kLcSmemMax) return spiral_set_error(SPIRAL_EUNSUPPORTED, "lconv_wgrad: tile does not fit shared memory (%zu bytes)", smem);
+    const int n_items = B * p.tiles_x * p.tiles_y;
+    const int grid = n_items < 148 * 2 ? n_items : 148 * 2;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (Cout == 1 && Cin == 32) {
+        // scalar output map: fp32 SIMT correlation (lwgrad1_kernel)
+        const size_t smem1 = ((size_t)p.IH * p.IW * Cin + kLcTw * kLcTh) * sizeof(float);
+        const size_t red = (size_t)(256 / Cin) * KH * KW * Cin * sizeof(float);
+        lwgrad1_kernel<32><<<grid, 256, smem1 > red ? smem1 : red, st>>>(p, x, dy, workspace, n_items);
+    } else {
+        LC_DISPATCH(lwgrad_launch, p, x, dy, workspace, n_items, grid, smem, st);
+    }
+    const int n = p.K * Cout;
+    lwgrad_reduce_kernel<<<(n + 255) / 256, 256, 0, st>>>(workspace, dw, grid, p.K, p.KP, Cout, p.CoutPad);
+    const cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? SPIRAL_OK : spiral_cuda_error(e, "spiral_lconv_wgrad");
+}

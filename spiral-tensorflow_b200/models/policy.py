@@ -187,7 +187,16 @@ class Policy(nn.Module):
         c = torch.zeros((batch_size, self.lstm_size), device=dev)
         return [c, torch.zeros_like(c)]
 
+    def _native(self, x):
+        """Learner path (gradients enabled, CUDA): the convolutions and their gradients on libspiral_b200.so
+        (models/policy_learn.py).  ``act`` runs under no_grad and keeps the plain module (the actors have their own
+        kernels, models/policy_native.py)."""
+        return bool(getattr(self, "learn_native", False)) and x.is_cuda and torch.is_grad_enabled()
+
     def encode(self, x, ac, c=None, z=None):
+        if self._native(x):
+            from . import policy_learn
+            return policy_learn.encode(self, x, ac, c, z)
         B, T = x.shape[:2]
         if self.conditional:
             x = torch.cat([x, c], -1)
@@ -213,7 +222,11 @@ class Policy(nn.Module):
         logits, out_samples = {}, {}
         for idx, name in enumerate(self.acs):
             z_flat = z.reshape(B * T, self.lstm_size)
-            logit = self.heads[name](z_flat)
+            if isinstance(self.heads[name], _LocationHead) and self._native(z_flat):
+                from . import policy_learn
+                logit = policy_learn.location_head(self.heads[name], z_flat)
+            else:
+                logit = self.heads[name](z_flat)
             logits[name] = logit.view(B, T, -1)
             if samples is not None and name in samples:
                 s = samples[name].reshape(B * T).long()

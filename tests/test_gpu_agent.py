@@ -280,8 +280,9 @@ def test_actor_lstm_state_carries_over_and_features_are_per_step(graphs):
         T = ro["actions"].shape[1]
         for t in range(T):
             last = init if t == 0 else ro["actions"][:, t - 1].float()
-            enc = pi.encode(ro["states"][:, t:t + 1].float(), last.unsqueeze(1), None, ro["z"][:, t:t + 1])
-            _, (c, h) = pi.lstm(enc[:, 0], (ro["features"][:, t, 0], ro["features"][:, t, 1]))
+            with torch.no_grad():                          # the acting path (policy.act runs under no_grad)
+                enc = pi.encode(ro["states"][:, t:t + 1].float(), last.unsqueeze(1), None, ro["z"][:, t:t + 1])
+                _, (c, h) = pi.lstm(enc[:, 0], (ro["features"][:, t, 0], ro["features"][:, t, 1]))
             want = ro["features"][:, t + 1] if t + 1 < T else (end1 if ro is ro1 else ag._lstm_state)
             assert torch.allclose(c, want[:, 0], atol=1e-5) and torch.allclose(h, want[:, 1], atol=1e-5), t
 

@@ -127,3 +127,143 @@ def test_agent_rollout_with_native_actor_sees_weight_updates():
         assert torch.equal(env.state, ro2["states"][:, t])
         env.step(ro2["actions"][:, t])
     assert torch.equal(env.state, ro2["states"][:, 3])
+
+
+def _learner_case(envname, L, C, T, conditional, B):
+    import spiral_b200 as sp
+    from importlib import import_module
+    from helpers import make_args
+    pol = import_module(sp.__name__ + ".models.policy")
+    args = make_args(envname, L=L, C=C, T=T, conditional=conditional, extra=["--policy_tf32", "False"])
+    env = sp.create_env(args, num_envs=B)
+    torch.manual_seed(3)
+    pi = pol.Policy(args, env).cuda()
+    g = torch.Generator(device="cuda")
+    g.manual_seed(5)
+    K = len(pi.acs)
+    x = torch.randint(0, 256, (B, T + 1, 64, 64, C), generator=g, device="cuda").float()
+    ac = torch.stack([torch.randint(0, env.head_sizes[i], (B, T), generator=g, device="cuda") for i in range(K)], -1)
+    cond = torch.randint(0, 256, (B, T, 64, 64, C), generator=g, device="cuda").float() if conditional else None
+    z = None if conditional else torch.rand((B, T, args.z_dim), generator=g, device="cuda") - 0.5
+    st = [torch.randn((B, args.lstm_size), generator=g, device="cuda") * 0.1 for _ in range(2)]
+    samples = {n: ac[:, :, i] for i, n in enumerate(pi.acs)}
+    return pi, (x, ac.float(), st, cond, z, samples), g
+
+
+@pytest.fixture
+def strict_fp32():
+    """TF32 off for the PyTorch reference path of a test, restored afterwards (other tests keep the process defaults)."""
+    saved = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+    torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = saved
+
+
+def _run_learner(pi, inp, native, dtype=torch.float32):
+    x, ac, st, cond, z, samples = inp
+    f = lambda t_: None if t_ is None else t_.to(dtype)
+    pi.learn_native = native
+    pi.zero_grad(set_to_none=True)
+    logits, _, vf, _ = pi(f(x), f(ac), (f(st[0]), f(st[1])), f(cond), f(z), samples)
+    gg = torch.Generator(device="cuda")
+    gg.manual_seed(11)
+    loss = (vf * torch.randn(vf.shape, generator=gg, device="cuda").to(dtype)).sum()
+    for n in pi.acs:
+        loss = loss + (logits[n] * torch.randn(logits[n].shape, generator=gg, device="cuda").to(dtype)).sum()
+    loss.backward()
+    return ({n: logits[n].detach().double() for n in pi.acs}, vf.detach().double(),
+            {k: p.grad.detach().double() for k, p in pi.named_parameters() if p.grad is not None})
+
+
+def _rel(a, b):
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+CASES = [("simple_mnist", 32, 1, 2, False, 3), ("color_mnist", 64, 3, 2, False, 2), ("simple_mnist", 32, 1, 2, True, 2)]
+
+
+def _check_learner(envname, L, C, T, conditional, B):
+    import copy
+    pi, inp, _ = _learner_case(envname, L, C, T, conditional, B)
+    ref = _run_learner(copy.deepcopy(pi).double(), inp, False, torch.float64)       # the module in float64: ground truth
+    t32 = _run_learner(pi, inp, False)                                              # PyTorch fp32 (cuDNN / cuBLAS, TF32 off)
+    got = _run_learner(pi, inp, True)                                               # csrc/policy_learn.cu
+    assert set(got[2]) == set(ref[2]) and len(ref[2]) > 60
+    for n in pi.acs:
+        assert _rel(got[0][n], ref[0][n]) < 1e-4, n
+        assert _rel(got[0][n], t32[0][n]) < 1e-4, n
+    assert _rel(got[1], ref[1]) < 1e-4 and _rel(got[1], t32[1]) < 1e-4
+    # every gradient tensor agrees with the float64 truth -- or, where fp32 rounding puts a ReLU pre-activation on the other
+    # side of zero than float64 does (then PyTorch's fp32 path deviates from float64 by the same amount), with the fp32 module
+    worst = max((min(_rel(got[2][k], ref[2][k]), _rel(got[2][k], t32[2][k])), k) for k in ref[2])
+    w64 = max((_rel(got[2][k], ref[2][k]), k) for k in ref[2])
+    w32 = max((_rel(t32[2][k], ref[2][k]), k) for k in ref[2])
+    print("worst parameter-gradient error vs float64: native %.2e (%s), PyTorch fp32 %.2e (%s)" % (w64 + w32))
+    assert worst[0] < 1e-4, worst
+    assert w64[0] < 4 * max(w32[0], 1e-5)                # as good as the fp32 module itself, give or take
+
+
+@pytest.mark.parametrize("envname,L,C,T,conditional,B", CASES)
+def test_learner_forward_and_gradients_match_the_module(envname, L, C, T, conditional, B, strict_fp32):
+    """Policy(learn_native=True): every convolution of the trunk and the location heads, and its input and weight
+    gradients, on csrc/policy_learn.cu (bf16x6, two accumulators) against the same module evaluated in float64: logits of
+    every head, the value and EVERY parameter gradient of a loss that touches all heads within 1e-4 (relative to the
+    largest entry of each tensor) -- and within a small factor of what PyTorch's own fp32 path (cuDNN / cuBLAS, TF32 off)
+    achieves against float64; logits and value also within 1e-4 of that fp32 path directly.  (The network is full of ReLU
+    kinks: a pre-activation within rounding of zero passes the gradient in float64 and blocks it in fp32, or the reverse,
+    which moves a whole gradient tensor by percents -- for PyTorch's fp32 path exactly as for this one; such a tensor must
+    then agree with the fp32 module instead.)"""
+    _check_learner(envname, L, C, T, conditional, B)
+
+
+def test_learner_gradients_on_a_smooth_network(monkeypatch, strict_fp32):
+    """The same comparison with the ReLUs replaced by softplus (no kinks for rounding to flip): every forward, input-
+    gradient and weight-gradient kernel in its place in the graph."""
+    monkeypatch.setattr(torch.nn.functional, "relu", lambda x, inplace=False: torch.nn.functional.softplus(x))
+    _check_learner("color_mnist", 64, 3, 2, False, 2)
+
+
+def test_learner_convolution_primitives_match_torch(strict_fp32):
+    """Each geometry on its own (forward, dgrad, wgrad): 5x5 'same' on 1/3/6 channels, 4x4 / stride 2 'valid' on odd and even
+    maps, 3x3 'same', 3x3 -> 1 channel, transposed 4x4 / stride 2 with 16 and 32 input channels; ragged tile edges."""
+    import spiral_b200 as sp
+    from importlib import import_module
+    pl = import_module(sp.__name__ + ".models.policy_learn")
+    g = torch.Generator(device="cuda")
+    g.manual_seed(0)
+
+    def check(kind, cin, cout, k, stride, pad, H, W, B=3):
+        if kind == "conv":
+            mod = torch.nn.Conv2d(cin, cout, k, stride=stride, padding=pad).cuda()
+        else:
+            mod = torch.nn.ConvTranspose2d(cin, cout, 4, stride=2, padding=1).cuda()
+        x = torch.randn((B, H, W, cin), generator=g, device="cuda")
+        outs = []
+        for native in (False, True):
+            xx = x.clone().requires_grad_(True)
+            mod.zero_grad(set_to_none=True)
+            if native:
+                y = pl.conv2d(xx, mod, stride=stride, pad=pad) if kind == "conv" else pl.conv_transpose2d(xx, mod)
+            else:
+                y = mod(xx.permute(0, 3, 1, 2)).permute(0, 2, 3, 1)
+            gy = torch.randn(y.shape, generator=torch.Generator(device="cuda").manual_seed(1), device="cuda")
+            (y * gy).sum().backward()
+            outs.append((y.detach(), xx.grad.clone(), mod.weight.grad.clone(), mod.bias.grad.clone()))
+        for a, b, name in zip(outs[1], outs[0], ("y", "dx", "dw", "db")):
+            assert a.shape == b.shape, (kind, name)
+            err = float((a - b).abs().max() / b.abs().max())
+            assert err < 5e-5, (kind, cin, cout, k, stride, H, W, name, err)
+
+    for cin in (1, 3, 6):
+        check("conv", cin, 32, 5, 1, 2, 64, 64, B=2)
+    check("conv", 32, 32, 4, 2, 0, 64, 64, B=2)
+    check("conv", 32, 32, 4, 2, 0, 31, 31)
+    check("conv", 32, 32, 4, 2, 0, 14, 14)
+    check("conv", 32, 32, 3, 1, 1, 6, 6, B=5)
+    check("conv", 32, 32, 3, 1, 1, 8, 8)
+    check("conv", 32, 1, 3, 1, 1, 32, 32)
+    check("conv", 32, 1, 3, 1, 1, 64, 64, B=2)
+    check("convT", 16, 32, 4, 2, 1, 4, 4)
+    check("convT", 32, 32, 4, 2, 1, 8, 8)
+    check("convT", 32, 32, 4, 2, 1, 32, 32, B=2)
