@@ -424,7 +424,7 @@ def run_ours(args):
             sampler.start()
         # batches of at most two waves take spiral_env_step's fused kernel (include/spiral_b200.h): `value` is then timed
         # through spiral_env_step itself and the expand / composite split comes from a separate, untimed recorded pass
-        fused = B <= int(os.environ.get("SPIRAL_FUSED_STEP_MAX", 148 * 8 * 2))
+        fused = B <= int(os.environ.get("SPIRAL_FUSED_STEP_MAX", 148 * 8 * (5 if math == "fast" else 2)))
         ms = timed(resident=True, record=(not fused) and record_kernels)
         if fused or not record_kernels:
             for _ in range(max(2, args.steps // 2)):
@@ -676,6 +676,39 @@ def run_ours(args):
         return dict(canvases=n, ms=times, env_steps_per_s=n * 20 / (total * 1e-3),
                     note="full loop incl. the PyTorch policy (not the headline metric)")
 
+    def learner_paths(n=128):
+        """Agent.train_policy (policy forward over [n*20] frames, fused A2C loss, backward, clip + Adam; CUDA-graph replay) for
+        the convolution paths of the learner: the library's kernels (default, bf16x6 = fp32 parity; bf16x3), PyTorch / cuDNN in
+        strict fp32 (the parity-equivalent library path) and in TF32 (10-bit operands, what round 1 ran)."""
+        agent_mod = import_module(sp.__name__ + ".agent")
+        W = WORKLOADS["rgb64"]
+        modes = {"native_bf16x6": ["--policy_learn_native", "True", "--policy_tf32", "False"],
+                 "native_bf16x3": ["--policy_learn_native", "True", "--policy_tf32", "False", "--policy_learn_precision", "bf16x3"],
+                 "cudnn_fp32": ["--policy_learn_native", "False", "--policy_tf32", "False"],
+                 "cudnn_tf32": ["--policy_learn_native", "False", "--policy_tf32", "True"]}
+        res = {}
+        for name, extra in modes.items():
+            a = sp.get_args(["--env", W["env"], "--location_size", str(W["location_size"]), "--color_channel",
+                             str(W["color_channel"]), "--episode_length", "20", "--loss", "l2", "--raster_math", args.raster_math] + extra)
+            env = sp.create_env(a, num_envs=n, device=dev)
+            ag = agent_mod.Agent(a, env)
+            ro = ag.rollout()
+            ts = []
+            for i in range(7):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                ag.train_policy({k: v.clone() for k, v in ro.items()})
+                e1.record()
+                torch.cuda.synchronize()
+                ts.append(e0.elapsed_time(e1))
+            res[name] = dict(train_policy_ms=float(np.mean(ts[3:])))
+            ag.close()
+            del ag, env
+            torch.cuda.empty_cache()
+        res["note"] = ("%d canvases x 20 steps = %d frames per learner step; native = csrc/policy_learn.cu (mma.sync implicit GEMMs, forward + "
+                       "dgrad + wgrad; gradients within 3e-5 of float64 like cuDNN fp32); TF32 is ~1e-3" % (n, n * 20))
+        return res
+
     # ---- headline ----
     if args.scaling == "strong":
         args.canvases_total = args.canvases
@@ -727,6 +760,7 @@ def run_ours(args):
             out[cfg]["config"] = sec["config"]
         out["disc_train"] = disc_train_step(C)
         out["agent_loop"] = agent_loop()
+        out["learner_paths"] = learner_paths()
     if world == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline(args, acs_list, head_list, C, L, T, args.W["disc_dim"], args.W["conditional"])
     _emit(json.dumps(out))

@@ -132,7 +132,7 @@ int spiral_env_reset(SpiralEnv *env, uint16_t *canvas_dev, float *brush_state_de
  * dab_count i32[B,2] are scratch owned by the caller (contents undefined between calls).
  * status_dev i32[1] is OR-ed with 1 if any canvas overflowed max_dabs and with 2 if a canvas ran past
  * rng_table_len (result then invalid).
- * Batches of at most two waves of CTAs (2 x 148 SMs x 8 = 2368 canvases; SPIRAL_FUSED_STEP_MAX overrides, 0 = never)
+ * Small batches (det arithmetic: at most 2 x 148 SMs x 8 = 2368 canvases; fast: 5920; SPIRAL_FUSED_STEP_MAX overrides, 0 = never)
  * run as ONE kernel in which a second warp composites a canvas's dabs while its brush chain is still producing them;
  * larger batches run spiral_env_expand then spiral_env_composite.  Results are bit-identical either way.
  * (SPIRAL_FUSED_SMEM=0: the fused kernel blends in place instead of keeping the tile in shared memory.) */

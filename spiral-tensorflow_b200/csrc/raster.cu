@@ -1728,7 +1728,9 @@ constexpr int kFusedWave = 148 * 8;        // CTAs of step_small_kernel resident
 constexpr int kFusedWaveSmt = 148 * 5;     // with the 32 KB tile in shared memory (37.5 KB per CTA)
 bool fused_step_applies(const EnvParams &P)
 {
-    int mx = FUSED_STEP_MAX_DEFAULT;
+    // measured (B200, tools/fused_step_probe.py): the fused kernel wins up to ~3k canvases with the det chain and up to ~6k
+    // with the fast one (22.1 vs 30.0 ms per 20-step episode at 4,096; 41.9 vs 34.2 at 8,192)
+    int mx = P.math_mode == kMathFast ? 148 * 8 * 5 : FUSED_STEP_MAX_DEFAULT;
     if (const char *e = getenv("SPIRAL_FUSED_STEP_MAX")) mx = atoi(e);
     return P.B <= mx;
 }
