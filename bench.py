@@ -674,7 +674,11 @@ def run_ours(args):
                 times["train_gan"] += e2.elapsed_time(e3) / iters
         total = sum(times.values())
         return dict(canvases=n, ms=times, env_steps_per_s=n * 20 / (total * 1e-3),
-                    note="full loop incl. the PyTorch policy (not the headline metric)")
+                    acting_precision="bf16 (--policy_act_native True: the actors' convolutions on bf16 tensor cores, logits within 3e-2 "
+                                     "of the fp32 module -- narrower than the reference's fp32 actors; it only perturbs the behaviour "
+                                     "policy's samples, the learner's logits / loss are fp32-parity)",
+                    learner_precision="bf16x6 (--policy_learn_native True: fp32-exact operands, gradients within 3e-5 of float64)",
+                    note="full loop incl. the policy (not the headline metric)")
 
     def learner_paths(n=128):
         """Agent.train_policy (policy forward over [n*20] frames, fused A2C loss, backward, clip + Adam; CUDA-graph replay) for

@@ -166,6 +166,10 @@ int spiral_debug_detmath(const double *x_dev, double *exp_out_dev, double *log_o
                          void *stream);
 /* the binary32 functions of SPIRAL_MATH_FAST (csrc/fastmath.cuh): exp(x), exp(-x), log(x) (0 where x <= 0) and
  * hypot(x, x_rev) with x_rev[i] = x[n-1-i]; tests compare the bits with the oracle's copy */
+/* Index checks of the checked build (libspiral_b200_checked.so, -DSPIRAL_BOUNDS_CHECK: every data-dependent shared-memory,
+ * tile, list and table index of the rasteriser and of the learner's convolution kernels is tested against its bound):
+ * number of violations counted on the device since the library was loaded; -1 in the product build (no checks compiled in). */
+int64_t spiral_debug_bounds_violations(void);
 /* the dab loop's branch-free division (csrc/fastmath.cuh div_exact) against the IEEE division over n_pairs pseudo-random
  * operand pairs; *mismatches_dev (u64, zeroed by the caller) receives the number of pairs whose quotients differ */
 int spiral_debug_divcheck(uint64_t seed, int64_t n_pairs, uint64_t *mismatches_dev, void *stream);

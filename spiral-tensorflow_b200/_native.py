@@ -88,6 +88,7 @@ SYMBOLS = {
     "spiral_env_debug_dabs": (C.c_int, [_vp] * 6),
     "spiral_l2_reward": (C.c_int, [_vp, _vp, _vp, C.c_int32, C.c_int32, _vp]),
     "spiral_debug_detmath": (C.c_int, [_vp, _vp, _vp, C.c_int32, _vp]),
+    "spiral_debug_bounds_violations": (C.c_int64, []),
     "spiral_debug_divcheck": (C.c_int, [C.c_uint64, C.c_int64, _vp, _vp]),
     "spiral_debug_fastmath": (C.c_int, [_vp, _vp, _vp, _vp, _vp, C.c_int32, _vp]),
     "spiral_a2c_loss": (C.c_int, [C.POINTER(_vp), C.POINTER(C.c_int32), C.c_int32, _vp, _vp, _vp, _vp,

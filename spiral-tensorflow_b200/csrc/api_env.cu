@@ -35,6 +35,8 @@ cudaError_t launch_l2_reward(const float *obs, const float *target, float *rewar
 cudaError_t launch_detmath(const double *x, double *e, double *l, int n, cudaStream_t st);
 cudaError_t launch_fastmath(const float *x, float *e, float *en, float *l, float *h, int n, cudaStream_t st);
 cudaError_t launch_divcheck(unsigned long long seed, long long n, unsigned long long *mismatches, cudaStream_t st);
+long long bounds_violations_raster();
+long long bounds_violations_learn();
 }  // namespace spiral
 
 using namespace spiral;
@@ -463,6 +465,13 @@ extern "C" int spiral_debug_fastmath(const float *x, float *e_out, float *en_out
     REQUIRE(x); REQUIRE(e_out); REQUIRE(en_out); REQUIRE(l_out); REQUIRE(h_out);
     const cudaError_t e = launch_fastmath(x, e_out, en_out, l_out, h_out, n, (cudaStream_t)stream);
     return e == cudaSuccess ? SPIRAL_OK : spiral_cuda_error(e, "spiral_debug_fastmath");
+}
+
+extern "C" int64_t spiral_debug_bounds_violations(void)
+{
+    const long long a = bounds_violations_raster(), b = bounds_violations_learn();
+    if (a < 0 || b < 0) return a < b ? a : b;      // -1: not a checked build
+    return (int64_t)(a + b);
 }
 
 extern "C" int spiral_debug_divcheck(uint64_t seed, int64_t n_pairs, uint64_t *mismatches_dev, void *stream)

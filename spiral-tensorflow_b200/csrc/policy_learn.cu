@@ -237,6 +237,7 @@ lconv_kernel(const __grid_constant__ LConvParams p, const float *__restrict__ x,
         if (CIN % 2 == 0) {
             // k0 is even and CIN is even: k0 and k0+1 are adjacent channels of one tap -> one 32-bit load
             const int o0 = s_koff[k0], o8 = s_koff[k0 + 8];
+            SP_CHECK(k0 + 9 < p.KP + 8 && base1 + o8 + 1 < n_in8 && base0 + o0 >= 0);
 #pragma unroll
             for (int q = 0; q < NPL; q++) {
                 const uint16_t *si = s_i + (size_t)q * n_in8;
@@ -247,6 +248,7 @@ lconv_kernel(const __grid_constant__ LConvParams p, const float *__restrict__ x,
             }
         } else {
             const int o0 = s_koff[k0], o1 = s_koff[k0 + 1], o8 = s_koff[k0 + 8], o9 = s_koff[k0 + 9];
+            SP_CHECK(k0 + 9 < p.KP && base1 + o9 < n_in8 && base1 + o1 < n_in8 && base0 + o0 >= 0);
 #pragma unroll
             for (int q = 0; q < NPL; q++) {
                 const uint16_t *si = s_i + (size_t)q * n_in8;
@@ -288,6 +290,7 @@ lconv_kernel(const __grid_constant__ LConvParams p, const float *__restrict__ x,
         const int px = ox * p.o_sx + p.o_ox;
         if (px < 0 || px >= p.oW) continue;
         const size_t pix = frame_out + (size_t)py * p.oW + px;
+        SP_CHECK(img >= 0 && img < p.B && pix < (size_t)p.B * p.oH * p.oW);
 #pragma unroll
         for (int nt = 0; nt < 4; nt++) {
             if (nt >= NT) continue;
@@ -406,6 +409,7 @@ lwgrad_kernel(const __grid_constant__ LConvParams p, const float *__restrict__ x
                 const int mt = warp + 8 * m;
                 if (mt < n_mt) {
                     const int r0 = s_koff[mt * 16 + g], r1 = s_koff[mt * 16 + g + 8];
+                    SP_CHECK(mt * 16 + g + 8 < p.KP && r0 + c0 >= 0 && r1 + c9 < n_in8 && r0 + c9 < n_in8);
                     uint32_t a[NPL][4];
 #pragma unroll
                     for (int q = 0; q < NPL; q++) {
@@ -563,6 +567,15 @@ static void lc_fill(LConvParams &p, int B, int Hin, int Win, int Cin, int Hout, 
 }
 
 constexpr size_t kLcSmemMax = 227 * 1024;        // per-CTA shared memory on sm_100
+
+long long bounds_violations_learn()
+{
+#ifdef SPIRAL_BOUNDS_CHECK
+    return spiral_tu_bounds_violations();
+#else
+    return -1;
+#endif
+}
 
 }  // namespace spiral
 

@@ -21,6 +21,7 @@
 #include <stdint.h>
 #include <stdlib.h>
 
+#include "common.h"
 #include "detmath.cuh"
 #include "fastmath.cuh"
 #include "raster.cuh"
@@ -524,6 +525,7 @@ __device__ __forceinline__ void expand_one(const EnvParams &P, const int b, cons
             if (v_rbr != 0.0f) cursor += 4;
             if (raw_dab_may_paint(P, S.AX, S.AY, S.AR, S.in[0], cull_pad)) {
                 if (n_dabs < P.max_dabs) {
+                    SP_CHECK(n_dabs >= 0 && n_dabs < P.max_dabs && b >= 0 && b < P.B);
                     float4 *d = reinterpret_cast<float4 *>(my_dabs + (size_t)n_dabs * kDabFloats);
                     d[0] = make_float4(S.AX, S.AY, S.in[0], S.v_rlog);
                     d[1] = make_float4(S.AR, __int_as_float(c0), S.in[1], S.in[2]);
@@ -770,6 +772,7 @@ __device__ __forceinline__ void expand_one_fast(const EnvParams &P, const int b,
             if (v_rbr != 0.0f) cursor += 4;
             if (raw_dab_may_paint(P, S.X, S.Y, S.AR, S.in[0], cull_pad)) {
                 if (n_dabs < P.max_dabs) {
+                    SP_CHECK(n_dabs >= 0 && n_dabs < P.max_dabs && b >= 0 && b < P.B);
                     float4 *d = reinterpret_cast<float4 *>(my_dabs + (size_t)n_dabs * kDabFloats);
                     d[0] = make_float4(S.X, S.Y, S.in[0], S.v_rlog);             // ACTUAL_X/Y == X/Y (slow_tracking_per_dab 0)
                     d[1] = make_float4(S.AR, __int_as_float(c0), S.in[1], S.in[2]);
@@ -906,6 +909,7 @@ plan_kernel(const __grid_constant__ EnvParams P, const int32_t *__restrict__ act
         key = key > kPlanBuckets - 1 ? kPlanBuckets - 1 : key;
         key = kPlanBuckets - 1 - key;                      // longest chains first
         key_out[b] = (uint8_t)key;
+        SP_CHECK(key >= 0 && key < kPlanBuckets);
         atomicAdd(&s_hist[key], 1);
     }
     __syncthreads();
@@ -938,6 +942,7 @@ scatter_kernel(int B, const uint8_t *__restrict__ key, int32_t *__restrict__ his
     if (b < B) {
         const int k = key[b];
         const int pos = s_start[k] + atomicAdd(&hist[kPlanBuckets + k], 1);
+        SP_CHECK(pos >= 0 && pos < B && k >= 0 && k < kPlanBuckets);
         perm[pos] = b;
     }
 }
@@ -1020,6 +1025,7 @@ __device__ __forceinline__ FinalDab finalize_raw(const EnvParams &P, const float
     opq = opq > 1.0f ? 1.0f : (opq < 0.0f ? 0.0f : opq);
     float x = r0.x, y = r0.y;
     const int c0 = min(__float_as_int(r1.y), P.rng_table_len - 16);
+    SP_CHECK(size_idx >= 0 && size_idx < 9 && c0 >= 0 && c0 + 12 < P.rng_table_len);
     const float base_radius = P.base_radius[size_idx];
     int g = c0 + 1;
     if (v.obr != 0.0f) {
@@ -1249,6 +1255,7 @@ __device__ __forceinline__ void composite_one(const EnvParams &P, const int b, u
     };
     // draw_dab_pixels_BlendMode_Normal for one pixel
     auto blend = [&](int idx, uint32_t opa_a) {
+        SP_CHECK(idx >= 0 && idx < kTile * kTile && opa_a <= (1u << 15));
         const uint2 px = tile[idx];
         const uint32_t opa_b = (1u << 15) - opa_a;
         uint32_t r = px.x & 0xffffu, g = px.x >> 16, bl = px.y & 0xffffu, al = px.y >> 16;
@@ -1288,6 +1295,7 @@ __device__ __forceinline__ void composite_one(const EnvParams &P, const int b, u
         f.seg1_slope = f.seg2_offset = f.seg2_slope = 0;
         if (mine < n_dabs) {
             // STREAM: the records were written by this CTA's producer (L2-coherent loads)
+            SP_CHECK(mine >= 0 && mine < P.max_dabs);
             const float4 r0 = STREAM ? __ldcg(dl + 2 * mine) : __ldg(dl + 2 * mine);
             const float4 r1 = STREAM ? __ldcg(dl + 2 * mine + 1) : __ldg(dl + 2 * mine + 1);
             f = fast_math ? finalize_raw<true>(P, r0, r1, size_idx, gauss_tab) : finalize_raw<false>(P, r0, r1, size_idx, gauss_tab);
@@ -1372,14 +1380,19 @@ __device__ __forceinline__ void composite_one(const EnvParams &P, const int b, u
                 const float h = span_sqrt(h2);
                 const int xa = max(f.x0, (int)floorf(f.x - h - 1.0f));
                 const int xb = min(f.x1, (int)floorf(f.x + h));
-                for (int xp = xa; xp <= xb; xp++) sp[n++] = (uint16_t)((lane << 8) | ((yp - f.y0) << 4) | (xp - f.x0));
+                for (int xp = xa; xp <= xb; xp++) {
+                    SP_CHECK(n >= 0 && n < kDense && yp - f.y0 >= 0 && yp - f.y0 < 16 && xp - f.x0 >= 0 && xp - f.x0 < 16);
+                    sp[n++] = (uint16_t)((lane << 8) | ((yp - f.y0) << 4) | (xp - f.x0));
+                }
             }
         }
         __syncwarp();
 
         // ---- phase 1: coverage and opacity of every (dab, pixel) pair, densely packed ----
         for (int k = lane; k < total; k += 32) {
+            SP_CHECK(k >= 0 && k < kDense && total <= kDense);
             const uint32_t e = sp[k];
+            SP_CHECK((e >> 8) < 32u);
             const SharedDab &cur = sd[e >> 8];
             const uint32_t box = cur.box;
             const int xp = (int)(box & 0xff) + (int)(e & 15), yp = (int)((box >> 8) & 0xff) + (int)((e >> 4) & 15);
@@ -1398,6 +1411,7 @@ __device__ __forceinline__ void composite_one(const EnvParams &P, const int b, u
         // ---- phase 2: ordered blend ----
         for (int j = 0; j < m; j++) {
             const int o0 = soff[j], o1 = soff[j + 1];
+            SP_CHECK(o0 >= 0 && o0 <= o1 && o1 <= kDense && o1 - o0 <= kListCap);
             if (o0 == o1) continue;
             // a dab on this path has at most kListCap = 64 candidate pixels: two passes, no loop
             int k = o0 + lane;
@@ -1424,6 +1438,7 @@ __device__ __forceinline__ void composite_one(const EnvParams &P, const int b, u
         ymax = max(ymax, __shfl_xor_sync(0xffffffffu, ymax, off));
     }
     if (ymax < ymin) return;
+    SP_CHECK(ymin >= 0 && ymax < kTile && b >= 0 && b < P.B);
     const uint4 *src = reinterpret_cast<const uint4 *>(tile);        // uint4 = 2 RGBA pixels
     float *ob = obs + (size_t)b * kTile * kTile * C;
 #pragma unroll 4
@@ -1794,6 +1809,14 @@ cudaError_t launch_detmath(const double *x, double *e, double *l, int n, cudaStr
     return cudaGetLastError();
 }
 
+long long bounds_violations_raster()
+{
+#ifdef SPIRAL_BOUNDS_CHECK
+    return spiral_tu_bounds_violations();
+#else
+    return -1;                                     // not a checked build
+#endif
+}
 cudaError_t launch_divcheck(unsigned long long seed, long long n, unsigned long long *mismatches, cudaStream_t st)
 {
     divcheck_kernel<<<148 * 8, 256, 0, st>>>(seed, n, mismatches);
