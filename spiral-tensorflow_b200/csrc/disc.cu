@@ -383,6 +383,8 @@ void disc_plan(const SpiralDisc *d, int batch, DiscPlan *pl)
         pl->part_off[l] = off; off += bn_partial_bytes(mtiles, Cout);
         pl->scale_off[l] = off; off += disc_align((size_t)Cout * sizeof(float));
         pl->shift_off[l] = off; off += disc_align((size_t)Cout * sizeof(float));
+        pl->pack_off[l] = off;
+        if (l > 0 && lconv_disc_layer_supported(Cin, Cout)) off += disc_align(lconv_disc_pack_bytes(Cin, Cout));
         H = Ho; Cin = Cout;
     }
     pl->simt_bytes = off;
@@ -431,6 +433,7 @@ int disc_forward_simt(SpiralDisc *d, const float *x, int batch, float *logits, f
         float *shift = (float *)(ws + pl.shift_off[l]);
         float *part = (float *)(ws + pl.part_off[l]);
         const bool bn = l > 0 && d->cfg.batch_norm;
+        int n_part = pl.mtiles[l];                   // rows of the batch-norm partials this layer's kernel writes
         if (l == 0) {
             const int rc = disc_conv0(d, x, batch, out, nullptr, nullptr, st);
             if (rc != SPIRAL_OK) return rc;
@@ -438,14 +441,21 @@ int disc_forward_simt(SpiralDisc *d, const float *x, int batch, float *logits, f
             const float *in = (const float *)(ws + pl.act_off[l - 1]);
             const float *isc = (const float *)(ws + pl.scale_off[l - 1]);
             const float *ish = (const float *)(ws + pl.shift_off[l - 1]);
-            dim3 grid(pl.mtiles[l], (Cout + 63) / 64);
-            conv_simt_kernel<<<grid, 256, 0, st>>>(in, isc, ish, (const float *)W.conv_w[l], (const float *)W.conv_b[l],
-                                                   out, bn ? part : nullptr, batch, H, Cin, Cout);
+            if (lconv_disc_layer_supported(Cin, Cout)) {
+                // narrow layer (disc_dim 8 / 16): the mma.sync implicit GEMM of policy_learn.cu, bf16x6
+                const int rc = lconv_disc_layer(in, isc, ish, (const float *)W.conv_w[l], (const float *)W.conv_b[l], out,
+                                                bn ? part : nullptr, ws + pl.pack_off[l], batch, H, Cin, Cout, &n_part, st);
+                if (rc != SPIRAL_OK) return rc;
+            } else {
+                dim3 grid(pl.mtiles[l], (Cout + 63) / 64);
+                conv_simt_kernel<<<grid, 256, 0, st>>>(in, isc, ish, (const float *)W.conv_w[l], (const float *)W.conv_b[l],
+                                                       out, bn ? part : nullptr, batch, H, Cin, Cout);
+            }
         }
         if (bn && stage >= 0) {
-            launch_bn_sums(part, pl.mtiles[l], Cout, sums, st);          // the caller all-reduces, the next stage finishes
+            launch_bn_sums(part, n_part, Cout, sums, st);                // the caller all-reduces, the next stage finishes
         } else if (bn) {
-            launch_bn_finalize(part, pl.mtiles[l], Cout, (double)batch * Ho * Ho, (const float *)W.bn_gamma[l],
+            launch_bn_finalize(part, n_part, Cout, (double)batch * Ho * Ho, (const float *)W.bn_gamma[l],
                                (const float *)W.bn_beta[l], 1e-3f, scale, shift,
                                bn_stats ? bn_stats + (size_t)l * 2 * maxC : nullptr, maxC, st);
         } else {

@@ -22,6 +22,7 @@ struct DiscPlan {
     int mtiles[SPIRAL_DISC_MAX_LAYERS];
     size_t act_off[SPIRAL_DISC_MAX_LAYERS], part_off[SPIRAL_DISC_MAX_LAYERS];
     size_t scale_off[SPIRAL_DISC_MAX_LAYERS], shift_off[SPIRAL_DISC_MAX_LAYERS];
+    size_t pack_off[SPIRAL_DISC_MAX_LAYERS];      // packed kernel planes of the narrow layers (lconv_disc_layer)
     size_t simt_bytes;
 };
 
@@ -41,6 +42,13 @@ __global__ void dense_sigmoid_kernel(const float *in, const float *in_scale, con
                                      const float *bias, float *logits, float *probs, int B, int C);
 
 int disc_conv0(SpiralDisc *d, const float *x, int batch, float *out, void *out_hi, void *out_lo, cudaStream_t st);
+
+// narrow layers (disc_dim 8 / 16) on the mma.sync implicit GEMM of policy_learn.cu
+bool lconv_disc_layer_supported(int Cin, int Cout);
+size_t lconv_disc_pack_bytes(int Cin, int Cout);
+int lconv_disc_layer(const float *in, const float *in_scale, const float *in_shift, const float *w_hwio, const float *bias,
+                     float *out, float *bn_partial, void *pack_scratch, int B, int H, int Cin, int Cout, int *n_part,
+                     cudaStream_t st);
 
 // layer 0 on tensor cores (disc_conv0_mma.cu)
 size_t conv0_mma_pack_bytes(int Cin);

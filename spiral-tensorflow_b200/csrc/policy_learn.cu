@@ -113,9 +113,12 @@ lpack_kernel(const __grid_constant__ LPackParams p, const float *__restrict__ w,
 // forward / dgrad: out[frame, scatter(oy, ox), co] = bias[co] + sum_k x[frame, oy*stride - pad + ky, ox*stride - pad + kx, c] * W[co][k]
 // ------------------------------------------------------------------------------------------
 // stage an fp32 NHWC input tile (zero outside the map) as NPL bf16 planes s_i[q][IH][IW][CIN]
+// in_scale / in_shift (optional, per input channel): v <- leaky_relu(v * scale + shift, 0.2) on load -- the batch norm and
+// activation of the PRODUCER layer, as the discriminator's kernels apply them (disc.cu); padding stays zero
 template <int CIN, int NPL>
 __device__ __forceinline__ void lc_stage_input(const LConvParams &p, const float *__restrict__ xi, int iy0, int ix0,
-                                               uint16_t *s_i, int n_in8, int tid)
+                                               uint16_t *s_i, int n_in8, int tid, const float *__restrict__ in_scale = nullptr,
+                                               const float *__restrict__ in_shift = nullptr)
 {
     if (CIN % 4 == 0) {
         constexpr int V = CIN / 4 > 0 ? CIN / 4 : 1;                           // float4 per pixel
@@ -131,8 +134,17 @@ __device__ __forceinline__ void lc_stage_input(const LConvParams &p, const float
                     const int pix = i / V, v = i - pix * V;
                     const int ly = pix / p.IW, lx = pix - ly * p.IW;
                     const int iy = iy0 + ly, ix = ix0 + lx;
-                    if (iy >= 0 && iy < p.Hin && ix >= 0 && ix < p.Win)
+                    if (iy >= 0 && iy < p.Hin && ix >= 0 && ix < p.Win) {
                         val[u] = __ldg(reinterpret_cast<const float4 *>(xi + ((size_t)iy * p.Win + ix) * CIN) + v);
+                        if (in_scale) {
+                            const float4 sc = __ldg(reinterpret_cast<const float4 *>(in_scale) + v);
+                            const float4 sh = __ldg(reinterpret_cast<const float4 *>(in_shift) + v);
+                            float4 &q = val[u];
+                            q.x = fmaf(q.x, sc.x, sh.x); q.y = fmaf(q.y, sc.y, sh.y); q.z = fmaf(q.z, sc.z, sh.z); q.w = fmaf(q.w, sc.w, sh.w);
+                            q.x = q.x > 0.f ? q.x : 0.2f * q.x; q.y = q.y > 0.f ? q.y : 0.2f * q.y;
+                            q.z = q.z > 0.f ? q.z : 0.2f * q.z; q.w = q.w > 0.f ? q.w : 0.2f * q.w;
+                        }
+                    }
                 }
             }
 #pragma unroll
@@ -194,9 +206,11 @@ __device__ __forceinline__ void lc_koff_table(const LConvParams &p, int cin, int
 template <int CIN, int NPL>
 __global__ void __launch_bounds__(256)
 lconv_kernel(const __grid_constant__ LConvParams p, const float *__restrict__ x, const uint16_t *__restrict__ w_planes,
-             const float *__restrict__ bias, float *__restrict__ out)
+             const float *__restrict__ bias, float *__restrict__ out, const float *__restrict__ in_scale,
+             const float *__restrict__ in_shift, float *__restrict__ bn_partial)
 {
     extern __shared__ __align__(16) uint8_t sm_raw[];
+    __shared__ float s_bn[8][32][2];                                           // per warp, per channel: (sum, sum of squares)
     const int n_w = p.CoutPad * p.KS;                                          // multiple of 8 (KS is)
     const int n_in8 = (p.IH * p.IW * CIN + 7) & ~7;
     uint16_t *s_w = reinterpret_cast<uint16_t *>(sm_raw);                     // [NPL][CoutPad][KS]
@@ -215,7 +229,7 @@ lconv_kernel(const __grid_constant__ LConvParams p, const float *__restrict__ x,
         for (int i = tid; i < NPL * n_w / 8; i += 256) sw[i] = __ldg(gw + i);
         lc_koff_table(p, CIN, s_koff, tid);
         lc_stage_input<CIN, NPL>(p, x + (size_t)img * p.Hin * p.Win * CIN, oy0 * p.stride - p.pad_t, ox0 * p.stride - p.pad_l,
-                                 s_i, n_in8, tid);
+                                 s_i, n_in8, tid, in_scale, in_shift);
     }
     __syncthreads();
 
@@ -279,16 +293,17 @@ lconv_kernel(const __grid_constant__ LConvParams p, const float *__restrict__ x,
         for (int j = 0; j < 4; j++) acc[nt][j] += acl[nt][j];
 
     const int oy = oy0 + warp;
-    if (oy >= p.Hout) return;
     const int py = oy * p.o_sy + p.o_oy;
-    if (py < 0 || py >= p.oH) return;
+    const bool row_ok = oy < p.Hout && py >= 0 && py < p.oH;
     const size_t frame_out = (size_t)img * p.oH * p.oW;
+    float bs[4][2], bq[4][2];                                                  // batch-norm partials of this thread's channels
+#pragma unroll
+    for (int nt = 0; nt < 4; nt++) { bs[nt][0] = bs[nt][1] = bq[nt][0] = bq[nt][1] = 0.0f; }
 #pragma unroll
     for (int half = 0; half < 2; half++) {
         const int ox = ox0 + g + 8 * half;
-        if (ox >= p.Wout) continue;
         const int px = ox * p.o_sx + p.o_ox;
-        if (px < 0 || px >= p.oW) continue;
+        if (!row_ok || ox >= p.Wout || px < 0 || px >= p.oW) continue;
         const size_t pix = frame_out + (size_t)py * p.oW + px;
         SP_CHECK(img >= 0 && img < p.B && pix < (size_t)p.B * p.oH * p.oW);
 #pragma unroll
@@ -300,12 +315,41 @@ lconv_kernel(const __grid_constant__ LConvParams p, const float *__restrict__ x,
                 if (ch < p.Cout) v0 += __ldg(bias + ch);
                 if (ch + 1 < p.Cout) v1 += __ldg(bias + ch + 1);
             }
+            bs[nt][0] += v0; bq[nt][0] += v0 * v0;
+            bs[nt][1] += v1; bq[nt][1] += v1 * v1;
             if ((p.Cout & 1) == 0 && ch + 1 < p.Cout) {
                 *reinterpret_cast<float2 *>(out + pix * p.Cout + ch) = make_float2(v0, v1);
             } else {
                 if (ch < p.Cout) out[pix * p.Cout + ch] = v0;
                 if (ch + 1 < p.Cout) out[pix * p.Cout + ch + 1] = v1;
             }
+        }
+    }
+    if (bn_partial) {
+        // per-CTA per-channel (sum, sum of squares) of the raw outputs for this layer's batch norm (fixed order: lanes of a
+        // warp by shuffles, warps through shared memory), written as partial[cta][Cout][2] like conv_simt_kernel does
+#pragma unroll
+        for (int nt = 0; nt < 4; nt++)
+#pragma unroll
+            for (int e = 0; e < 2; e++) {
+#pragma unroll
+                for (int off = 4; off < 32; off <<= 1) {
+                    bs[nt][e] += __shfl_xor_sync(0xffffffffu, bs[nt][e], off);
+                    bq[nt][e] += __shfl_xor_sync(0xffffffffu, bq[nt][e], off);
+                }
+                if (g == 0 && nt < NT) {
+                    s_bn[warp][nt * 8 + 2 * t + e][0] = bs[nt][e];
+                    s_bn[warp][nt * 8 + 2 * t + e][1] = bq[nt][e];
+                }
+            }
+        __syncthreads();
+        if (tid < p.Cout) {
+            float sum = 0.0f, sq = 0.0f;
+#pragma unroll
+            for (int w = 0; w < 8; w++) { sum += s_bn[w][tid][0]; sq += s_bn[w][tid][1]; }
+            float *dst = bn_partial + ((size_t)blockIdx.x * p.Cout + tid) * 2;
+            dst[0] = sum;
+            dst[1] = sq;
         }
     }
 }
@@ -581,7 +625,7 @@ long long bounds_violations_learn()
 
 using namespace spiral;
 
-static bool lc_cin_ok(int Cin) { return Cin == 1 || Cin == 2 || Cin == 3 || Cin == 6 || Cin == 16 || Cin == 32; }
+static bool lc_cin_ok(int Cin) { return Cin == 1 || Cin == 2 || Cin == 3 || Cin == 6 || Cin == 8 || Cin == 16 || Cin == 32; }
 
 // elements of ONE plane of a packed kernel
 extern "C" int64_t spiral_lconv_packed_elems(int32_t Cin, int32_t Cout, int32_t n_taps)
@@ -611,15 +655,16 @@ extern "C" int spiral_lconv_pack(const float *w, void *packed_planes, int32_t n_
 
 template <int CIN, int NPL>
 static int lconv_launch(const LConvParams &p, const float *x, const void *w, const float *bias, float *out, int grid, size_t smem,
-                        cudaStream_t st)
+                        cudaStream_t st, const float *in_scale = nullptr, const float *in_shift = nullptr, float *bn_partial = nullptr)
 {
     static bool attr = false;
     if (!attr) {
-        const cudaError_t e = cudaFuncSetAttribute(lconv_kernel<CIN, NPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLcSmemMax);
+        // the kernel also has 2 KB of static shared memory (batch-norm partials)
+        const cudaError_t e = cudaFuncSetAttribute(lconv_kernel<CIN, NPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kLcSmemMax - 2048));
         if (e != cudaSuccess) return spiral_cuda_error(e, "cudaFuncSetAttribute(lconv_kernel)");
         attr = true;
     }
-    lconv_kernel<CIN, NPL><<<grid, 256, smem, st>>>(p, x, (const uint16_t *)w, bias, out);
+    lconv_kernel<CIN, NPL><<<grid, 256, smem, st>>>(p, x, (const uint16_t *)w, bias, out, in_scale, in_shift, bn_partial);
     return SPIRAL_OK;
 }
 
@@ -646,6 +691,7 @@ static int lwgrad_launch(const LConvParams &p, const float *x, const float *dy, 
             case 2: rc_ = FN<2, 2>(__VA_ARGS__); break;                                                               \
             case 3: rc_ = FN<3, 2>(__VA_ARGS__); break;                                                               \
             case 6: rc_ = FN<6, 2>(__VA_ARGS__); break;                                                               \
+            case 8: rc_ = FN<8, 2>(__VA_ARGS__); break;                                                               \
             case 16: rc_ = FN<16, 2>(__VA_ARGS__); break;                                                             \
             default: rc_ = FN<32, 2>(__VA_ARGS__); break;                                                             \
             }                                                                                                         \
@@ -655,6 +701,7 @@ static int lwgrad_launch(const LConvParams &p, const float *x, const float *dy, 
             case 2: rc_ = FN<2, 3>(__VA_ARGS__); break;                                                               \
             case 3: rc_ = FN<3, 3>(__VA_ARGS__); break;                                                               \
             case 6: rc_ = FN<6, 3>(__VA_ARGS__); break;                                                               \
+            case 8: rc_ = FN<8, 3>(__VA_ARGS__); break;                                                               \
             case 16: rc_ = FN<16, 3>(__VA_ARGS__); break;                                                             \
             default: rc_ = FN<32, 3>(__VA_ARGS__); break;                                                             \
             }                                                                                                         \
@@ -674,13 +721,47 @@ extern "C" int spiral_lconv_forward(const float *x, const void *w_planes, int32_
     lc_fill(p, B, Hin, Win, Cin, Hout, Wout, Cout, KH, KW, stride, pad_t, pad_l, oH, oW, o_sy, o_sx, o_oy, o_ox);
     const size_t n_w = (size_t)p.CoutPad * p.KS, n_in8 = ((size_t)p.IH * p.IW * Cin + 7) & ~(size_t)7;
     const size_t smem = (size_t)n_planes * (n_w + n_in8) * 2 + (size_t)p.KP * 4;
-    if (smem > kLcSmemMax) return spiral_set_error(SPIRAL_EUNSUPPORTED, "lconv: tile does not fit shared memory (%zu bytes)", smem);
+    if (smem > kLcSmemMax - 2048) return spiral_set_error(SPIRAL_EUNSUPPORTED, "lconv: tile does not fit shared memory (%zu bytes)", smem);
     const int grid = B * p.tiles_x * p.tiles_y;
     cudaStream_t st = (cudaStream_t)stream;
     LC_DISPATCH(lconv_launch, p, x, w_planes, bias, out, grid, smem, st);
     const cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? SPIRAL_OK : spiral_cuda_error(e, "spiral_lconv_forward");
 }
+
+// A narrow layer of the discriminator (disc_dim 8 / 16: Cin <= 16, Cout <= 32; 5x5 / stride 2 / 'SAME' = pad 1 before, 2 after)
+// on this kernel instead of the fp32 SIMT tile (64 x 64 outputs per CTA: at Cout = 16, Cin = 8 seven eighths of its FMAs are
+// padding): kernel HWIO fp32 -> three bf16 planes (bf16x6, fp32-exact operands), the producer's BN + leaky-ReLU applied while
+// the input tile is staged, + bias, raw fp32 output, per-CTA batch-norm partials.  Returns the number of partial rows.
+namespace spiral {
+bool lconv_disc_layer_supported(int Cin, int Cout) { return (Cin == 8 || Cin == 16) && Cout <= 32 && Cout % 2 == 0; }
+size_t lconv_disc_pack_bytes(int Cin, int Cout)
+{
+    return (size_t)3 * spiral_lconv_packed_elems(Cin, Cout, 25) * sizeof(uint16_t);
+}
+int lconv_disc_layer(const float *in, const float *in_scale, const float *in_shift, const float *w_hwio, const float *bias,
+                     float *out, float *bn_partial, void *pack_scratch, int B, int H, int Cin, int Cout, int *n_part,
+                     cudaStream_t st)
+{
+    int tk[25], tx[25];
+    for (int i = 0; i < 25; i++) { tk[i] = i / 5; tx[i] = i % 5; }
+    int rc = spiral_lconv_pack(w_hwio, pack_scratch, 3, Cout, Cin, 25, 1, Cout, (int64_t)5 * Cin * Cout, (int64_t)Cin * Cout, tk, tx, st);
+    if (rc != SPIRAL_OK) return rc;
+    const int Ho = H / 2;
+    LConvParams p;
+    lc_fill(p, B, H, H, Cin, Ho, Ho, Cout, 5, 5, 2, 1, 1, Ho, Ho, 1, 1, 0, 0);
+    const size_t n_w = (size_t)p.CoutPad * p.KS, n_in8 = ((size_t)p.IH * p.IW * Cin + 7) & ~(size_t)7;
+    const size_t smem = (size_t)3 * (n_w + n_in8) * 2 + (size_t)p.KP * 4;
+    if (smem > kLcSmemMax - 4096) return spiral_set_error(SPIRAL_EUNSUPPORTED, "lconv_disc_layer: tile does not fit shared memory");
+    const int grid = B * p.tiles_x * p.tiles_y;
+    *n_part = grid;
+    if (Cin == 8) rc = lconv_launch<8, 3>(p, in, pack_scratch, bias, out, grid, smem, st, in_scale, in_shift, bn_partial);
+    else rc = lconv_launch<16, 3>(p, in, pack_scratch, bias, out, grid, smem, st, in_scale, in_shift, bn_partial);
+    if (rc != SPIRAL_OK) return rc;
+    const cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? SPIRAL_OK : spiral_cuda_error(e, "lconv_disc_layer");
+}
+}  // namespace spiral
 
 extern "C" int64_t spiral_lconv_wgrad_workspace_floats(int32_t Cin, int32_t Cout, int32_t n_taps)
 {
