@@ -39,7 +39,7 @@ class Agent(object):
         self.policy.learn_native = bool(getattr(args, "policy_learn_native", True)) and self.device.type == "cuda"
         if self.policy.learn_native:
             from .models import policy_learn
-            policy_learn.PLANES = 2 if getattr(args, "policy_learn_precision", "bf16x6") == "bf16x3" else 3
+            policy_learn.PLANES = policy_learn.FORMATS[getattr(args, "policy_learn_precision", "f16x3")]
         self.policy_opt = FusedTFAdam(self.policy.parameters(), args.policy_lr)
         # acting path: the trunk's convolutions on libspiral_b200.so (bf16 tensor cores); the learner keeps the fp32 module
         self.actor = NativeActor(self.policy) if (getattr(args, "policy_act_native", True) and self.device.type == "cuda") else None

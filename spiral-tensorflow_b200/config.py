@@ -94,7 +94,7 @@ def build_parser():
     # operand split of those kernels: 'bf16x6' = three bf16 planes / six products, fp32-exact operands (logits and gradients
     # as close to float64 as PyTorch's strict-fp32 path); 'bf16x3' = two planes / three products, 16 operand bits (~2x
     # faster, per-layer error ~1e-5: 64x finer than TF32)
-    parser.add_argument('--policy_learn_precision', type=str, default='bf16x6', choices=['bf16x6', 'bf16x3'])
+    parser.add_argument('--policy_learn_precision', type=str, default='f16x3', choices=['f16x3', 'bf16x6', 'bf16x3'])
     # capture the T-step rollout (policy.act + env.step) into one CUDA graph and replay it
     parser.add_argument('--cuda_graphs', type=str2bool, default=True)
     parser.add_argument('--disc_grad_precision', type=str, default='auto',

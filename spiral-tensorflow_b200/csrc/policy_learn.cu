@@ -20,6 +20,7 @@
 //     GEMM whose reduction runs over pixels, accumulated in registers by persistent CTAs and reduced over CTAs in a fixed
 //     order (deterministic, no atomics).
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -39,6 +40,10 @@ struct LConvParams {
     int IH, IW;                                  // staged input tile
     int tiles_x, tiles_y;
     int oH, oW, o_sy, o_sx, o_oy, o_ox;          // output pixel (oy, ox) -> (oy*o_sy + o_oy, ox*o_sx + o_ox) of an [oH, oW] map
+    // v2 kernels (lconv2_kernel / lwgrad2_kernel): a CTA covers fr frames x th rows x tw columns of outputs
+    int tw, th, fr, mt_rows;                     // tw = 16 or 8; mt_rows = 16 / tw rows per 16-pixel m-tile; th a power of two
+    int th_log;
+    int n_in;                                    // halfwords per plane of the staged input tile (multiple of 64)
 };
 
 __device__ __forceinline__ void lc_mma(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2])
@@ -47,6 +52,72 @@ __device__ __forceinline__ void lc_mma(float (&d)[4], const uint32_t (&a)[4], co
         "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
         : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
         : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
+__device__ __forceinline__ void lc_mma_h(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2])
+{
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
+__device__ __forceinline__ uint32_t lc_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void lc_ldsm4(uint32_t (&r)[4], uint32_t addr)
+{
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+
+__device__ __forceinline__ void lc_ldsm4t(uint32_t (&r)[4], uint32_t addr)
+{
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+
+__device__ __forceinline__ void lc_cp_async16(uint32_t dst, const void *src)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+
+__device__ __forceinline__ void lc_cp_async_wait()
+{
+    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
+
+// The third operand format, "f16x3": v = h + l * 2^-11 with h = fp16(v) and l = fp16((v - h) * 2^11) -- 22 operand bits in TWO
+// planes and three products (h*h into `hi`; h*l + l*h into `lo`, which the epilogue scales by 2^-11; the dropped l*l term is
+// 2^-22 of the result).  The scaling keeps the residual plane in fp16's normal range whenever h is: |v| >= 6.1e-5 carries 22
+// bits, smaller values an absolute error <= 3e-11; |v| is clamped to fp16's 65504 (activations, kernels and gradients of the
+// policy network are orders of magnitude inside that).  Half the MMAs and two thirds of the shared memory of bf16x6 at
+// the same parity (tests/test_gpu_policy_native.py compares both with float64).
+constexpr float kF16LoScale = 2048.0f, kF16LoInv = 1.0f / 2048.0f;
+
+__device__ __forceinline__ uint32_t lc_h2_bits(__half2 h) { return *reinterpret_cast<uint32_t *>(&h); }
+__device__ __forceinline__ uint32_t lc_b2_bits(__nv_bfloat162 h) { return *reinterpret_cast<uint32_t *>(&h); }
+
+// two values -> NPL packed pairs (low half = v0)
+template <int NPL, bool F16>
+__device__ __forceinline__ void lc_split_pair(float v0, float v1, uint32_t (&pl)[NPL])
+{
+    if (F16) {
+        v0 = fminf(fmaxf(v0, -65504.0f), 65504.0f);
+        v1 = fminf(fmaxf(v1, -65504.0f), 65504.0f);
+        const __half2 h = __floats2half2_rn(v0, v1);
+        const float2 f = __half22float2(h);
+        pl[0] = lc_h2_bits(h);
+        pl[1] = lc_h2_bits(__floats2half2_rn((v0 - f.x) * kF16LoScale, (v1 - f.y) * kF16LoScale));
+    } else {
+#pragma unroll
+        for (int q = 0; q < NPL; q++) {
+            const __nv_bfloat162 h = __floats2bfloat162_rn(v0, v1);
+            const float2 f = __bfloat1622float2(h);
+            pl[q] = lc_b2_bits(h);
+            v0 -= f.x;
+            v1 -= f.y;
+        }
+    }
 }
 
 // v = p[0] + p[1] (+ p[2]) + O(2^-8NPL |v|): NPL bf16 planes of 8 bits each (16 bits: "bf16x3", the three products
@@ -79,6 +150,18 @@ __device__ __forceinline__ void lc_mma_planes(float (&hi)[4], float (&lo)[4], co
     lc_mma(hi, a[0], b[0]);
 }
 
+template <int NPL, bool F16>
+__device__ __forceinline__ void lc_mma_planes2(float (&hi)[4], float (&lo)[4], const uint32_t (&a)[NPL][4], const uint32_t (&b)[NPL][2])
+{
+    if (F16) {
+        lc_mma_h(lo, a[1], b[0]);
+        lc_mma_h(lo, a[0], b[1]);
+        lc_mma_h(hi, a[0], b[0]);
+    } else {
+        lc_mma_planes<NPL>(hi, lo, a, b);
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // kernel packing: packed_{hi,lo}[row][tap * Ck + c] = w[row * s_row + c * s_c + ky(tap) * s_ky + kx(tap) * s_kx]
 // (zero for row >= rows and for the k padding).  With the strides and the tap table chosen by the caller this is the
@@ -90,7 +173,7 @@ struct LPackParams {
     int tap_ky[kLcMaxTaps], tap_kx[kLcMaxTaps];
 };
 
-template <int NPL>
+template <int NPL, bool F16 = false>
 __global__ void __launch_bounds__(256)
 lpack_kernel(const __grid_constant__ LPackParams p, const float *__restrict__ w, uint16_t *__restrict__ planes)
 {
@@ -102,10 +185,17 @@ lpack_kernel(const __grid_constant__ LPackParams p, const float *__restrict__ w,
             const int tap = k / p.Ck, c = k - tap * p.Ck;
             v = w[row * p.s_row + c * p.s_c + p.tap_ky[tap] * p.s_ky + p.tap_kx[tap] * p.s_kx];
         }
-        uint16_t pl[NPL];
-        lc_split<NPL>(v, pl);
+        if (F16) {
+            uint32_t pp[NPL];
+            lc_split_pair<NPL, F16>(v, 0.0f, pp);
 #pragma unroll
-        for (int q = 0; q < NPL; q++) planes[(size_t)q * n + i] = pl[q];
+            for (int q = 0; q < NPL; q++) planes[(size_t)q * n + i] = (uint16_t)(pp[q] & 0xffffu);
+        } else {
+            uint16_t pl[NPL];
+            lc_split<NPL>(v, pl);
+#pragma unroll
+            for (int q = 0; q < NPL; q++) planes[(size_t)q * n + i] = pl[q];
+        }
     }
 }
 
@@ -598,6 +688,338 @@ lwgrad_reduce_kernel(const float *__restrict__ partial, float *__restrict__ dw, 
     dw[i] = s;
 }
 
+
+// ==========================================================================================
+// v2 kernels (Cin a multiple of 8): the learner's hot shapes.
+//
+// What the first kernels above paid for (ncu / per-call timings, tools/learner_probe.py): 8-way bank conflicts on the A
+// fragments (a pixel's 32 channels are 64 B, so the 8 pixels of a fragment column start in the same banks), scalar 32-bit /
+// 16-bit fragment loads, the 100 KB kernel re-read per 128 output pixels, and half-empty 8 x 16 tiles on the 8 x 8 / 6 x 6
+// maps of the res-blocks.  Here:
+//   * the staged tile is [pixel][channel] with the 16-byte chunks of every 128-byte line XOR-swizzled by the line index, so
+//     the eight rows of an ldmatrix land in eight different bank groups for stride 1 and stride 2; fragments come from
+//     ldmatrix.x4 (forward) / ldmatrix.x4.trans (wgrad: the reduction runs over pixels, the transposed load IS the
+//     pixel-major -> channel-major transpose the first kernel did with 16-bit loads)
+//   * a CTA covers 256 outputs (two m-tiles per warp, B fragments used twice) as fr frames x th rows x tw columns with
+//     tw = 8 for maps up to 8 wide (four 8 x 8 frames per CTA instead of half of one 8 x 16 tile)
+//   * the kernel planes arrive by cp.async while the input tile is converted
+//   * operand format f16x3 (above) next to bf16x3 / bf16x6
+// ==========================================================================================
+__device__ __forceinline__ int lc_swz(int L) { return (L & ~7) | ((L ^ (L >> 3)) & 7); }
+
+// stage the box [fr frames][RH rows][RW columns][C channels] of an NHWC fp32 tensor [., H, W, C] starting at (y0, x0) of frame 0
+// of `src` (zero outside the map and for frames >= frames_left) as NPL swizzled planes of n_plane halfwords
+template <int C, int NPL, bool F16>
+__device__ __forceinline__ void lc2_stage(const float *__restrict__ src, size_t frame_elems, int frames_left, int H, int W,
+                                          int RH, int RW, int y0, int x0, int fr, uint16_t *s, int n_plane, int warp, int lane)
+{
+    constexpr int V = C / 4;                                                   // float4 per pixel
+    constexpr int U = 8;                                                       // loads in flight per thread
+    const int rows = fr * RH, rowlen = RW * V;
+    for (int gr = warp; gr < rows; gr += 8) {
+        const int f = gr / RH, ly = gr - f * RH;
+        const int iy = y0 + ly;
+        const bool row_ok = f < frames_left && iy >= 0 && iy < H;
+        // only dereferenced for pixels inside the map
+        const float4 *rowp = reinterpret_cast<const float4 *>(src + (ptrdiff_t)f * (ptrdiff_t)frame_elems +
+                                                              ((ptrdiff_t)iy * W + x0) * C);
+        const int e_row = gr * RW * C;
+        for (int i0 = lane; i0 < rowlen; i0 += 32 * U) {
+            float4 val[U];
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                const int i = i0 + 32 * u;
+                val[u] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                if (i < rowlen && row_ok) {
+                    const int ix = x0 + i / V;
+                    if (ix >= 0 && ix < W) val[u] = __ldg(rowp + i);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                const int i = i0 + 32 * u;
+                if (i < rowlen) {
+                    const int e = e_row + i * 4;                               // element index in the unswizzled tile
+                    const int L = e >> 3;
+                    uint32_t p0[NPL], p1[NPL];
+                    lc_split_pair<NPL, F16>(val[u].x, val[u].y, p0);
+                    lc_split_pair<NPL, F16>(val[u].z, val[u].w, p1);
+                    SP_CHECK(lc_swz(L) * 8 + 8 <= n_plane);
+                    uint16_t *dst = s + lc_swz(L) * 8 + (e & 4);
+#pragma unroll
+                    for (int q = 0; q < NPL; q++) *reinterpret_cast<uint2 *>(dst + (size_t)q * n_plane) = make_uint2(p0[q], p1[q]);
+                }
+            }
+        }
+    }
+}
+
+// chunk q (8 consecutive k) of the packed reduction index -> chunk offset in the staged tile
+template <int CIN>
+__device__ __forceinline__ void lc2_qoff_table(const LConvParams &p, int *s_qoff, int tid)
+{
+    constexpr int CH = CIN / 8;
+    for (int q = tid; q < p.KP / 8; q += 256) {
+        int off = 0;
+        if (q * 8 < p.K) {
+            const int tap = q / CH, c8 = q - tap * CH;
+            const int ky = tap / p.KW, kx = tap - ky * p.KW;
+            off = (ky * p.IW + kx) * CH + c8;
+        }
+        s_qoff[q] = off;
+    }
+}
+
+template <int CIN, int NPL, bool F16, int MT>
+__global__ void __launch_bounds__(256, (NPL == 2) ? 2 : 1)
+lconv2_kernel(const __grid_constant__ LConvParams p, const float *__restrict__ x, const uint16_t *__restrict__ w_planes,
+              const float *__restrict__ bias, float *__restrict__ out)
+{
+    extern __shared__ __align__(16) uint8_t sm_raw[];
+    constexpr int CH = CIN / 8;
+    const int n_w = p.CoutPad * p.KS;
+    uint16_t *s_i = reinterpret_cast<uint16_t *>(sm_raw);                     // [NPL][n_in], swizzled
+    uint16_t *s_w = s_i + (size_t)NPL * p.n_in;                                // [NPL][CoutPad][KS]
+    int *s_qoff = reinterpret_cast<int *>(s_w + (size_t)NPL * n_w);            // [KP / 8]
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tiles = p.tiles_x * p.tiles_y;
+    const int fg = blockIdx.x / tiles, trem = blockIdx.x - fg * tiles;
+    const int oy0 = (trem / p.tiles_x) * p.th, ox0 = (trem % p.tiles_x) * p.tw;
+    const int img0 = fg * p.fr;
+    {
+        const uint32_t sw = lc_smem_u32(s_w);
+        const int n16 = NPL * n_w / 8;
+        const uint4 *gw = reinterpret_cast<const uint4 *>(w_planes);
+        for (int i = tid; i < n16; i += 256) lc_cp_async16(sw + (uint32_t)i * 16u, gw + i);
+    }
+    lc2_qoff_table<CIN>(p, s_qoff, tid);
+    lc2_stage<CIN, NPL, F16>(x + (size_t)img0 * p.Hin * p.Win * CIN, (size_t)p.Hin * p.Win * CIN, p.B - img0, p.Hin, p.Win, p.IH,
+                             p.IW, oy0 * p.stride - p.pad_t, ox0 * p.stride - p.pad_l, p.fr, s_i, p.n_in, warp, lane);
+    lc_cp_async_wait();
+    __syncthreads();
+
+    // ldmatrix roles of this lane: matrix j = lane / 8, row r = lane % 8
+    const int j = lane >> 3, r = lane & 7;
+    const int rows_w = MT * p.mt_rows;                                          // output rows of this warp
+    int pixA[MT];
+#pragma unroll
+    for (int mt = 0; mt < MT; mt++) {
+        const int i_m = r + ((j & 1) << 3);                                     // A: matrices 1, 3 are pixels 8..15 of the m-tile
+        const int rowg = warp * rows_w + mt * p.mt_rows + (p.tw == 8 ? (i_m >> 3) : 0);
+        const int col = p.tw == 8 ? (i_m & 7) : i_m;
+        const int f = rowg >> p.th_log, ry = rowg & (p.th - 1);
+        pixA[mt] = ((f * p.IH + ry * p.stride) * p.IW + col * p.stride) * CH;
+    }
+    const int qsel = j >> 1;                                                    // A: matrices 2, 3 are the k-step's second chunk
+    int wrow[2];
+#pragma unroll
+    for (int ntp = 0; ntp < 2; ntp++) {                                         // B: matrices 0, 1 = n-tile 2 ntp (k chunks 0, 1), 2, 3 = n-tile 2 ntp + 1
+        int n = ntp * 16 + ((j >> 1) << 3) + r;
+        n = n < p.CoutPad ? n : p.CoutPad - 1;
+        wrow[ntp] = n * p.KS + ((j & 1) << 3);
+    }
+    const uint32_t si_base = lc_smem_u32(s_i), sw_base = lc_smem_u32(s_w);
+    const uint32_t in_plane = (uint32_t)p.n_in * 2u, w_plane = (uint32_t)n_w * 2u;
+    const int NT = p.CoutPad >> 3;
+
+    float acc[MT][4][4], acl[MT][4][4];
+#pragma unroll
+    for (int mt = 0; mt < MT; mt++)
+#pragma unroll
+        for (int nt = 0; nt < 4; nt++)
+#pragma unroll
+            for (int e = 0; e < 4; e++) { acc[mt][nt][e] = 0.0f; acl[mt][nt][e] = 0.0f; }
+
+#pragma unroll 1
+    for (int ks = 0; ks < p.KP / 16; ks++) {
+        const int qo = s_qoff[2 * ks + qsel];
+        uint32_t a[MT][NPL][4];
+#pragma unroll
+        for (int mt = 0; mt < MT; mt++) {
+            const int L = pixA[mt] + qo;
+            SP_CHECK(L >= 0 && lc_swz(L) * 8 + 8 <= p.n_in);
+            const uint32_t ad = si_base + ((uint32_t)lc_swz(L) << 4);
+#pragma unroll
+            for (int q = 0; q < NPL; q++) lc_ldsm4(a[mt][q], ad + (uint32_t)q * in_plane);
+        }
+        uint32_t b[4][NPL][2];
+#pragma unroll
+        for (int ntp = 0; ntp < 2; ntp++) {
+            if (ntp * 2 < NT) {
+                const uint32_t ad = sw_base + ((uint32_t)(wrow[ntp] + ks * 16) << 1);
+#pragma unroll
+                for (int q = 0; q < NPL; q++) {
+                    uint32_t t4[4];
+                    lc_ldsm4(t4, ad + (uint32_t)q * w_plane);
+                    b[2 * ntp][q][0] = t4[0]; b[2 * ntp][q][1] = t4[1];
+                    b[2 * ntp + 1][q][0] = t4[2]; b[2 * ntp + 1][q][1] = t4[3];
+                }
+            }
+        }
+#pragma unroll
+        for (int mt = 0; mt < MT; mt++)
+#pragma unroll
+            for (int nt = 0; nt < 4; nt++)
+                if (nt < NT) lc_mma_planes2<NPL, F16>(acc[mt][nt], acl[mt][nt], a[mt], b[nt]);
+    }
+
+    const int g = lane >> 2, t = lane & 3;
+    const float lo_scale = F16 ? kF16LoInv : 1.0f;
+#pragma unroll
+    for (int mt = 0; mt < MT; mt++) {
+#pragma unroll
+        for (int half = 0; half < 2; half++) {
+            const int i_m = g + 8 * half;
+            const int rowg = warp * rows_w + mt * p.mt_rows + (p.tw == 8 ? (i_m >> 3) : 0);
+            const int col = p.tw == 8 ? (i_m & 7) : i_m;
+            const int f = rowg >> p.th_log, ry = rowg & (p.th - 1);
+            const int img = img0 + f, oy = oy0 + ry, ox = ox0 + col;
+            const int py = oy * p.o_sy + p.o_oy, px = ox * p.o_sx + p.o_ox;
+            if (img >= p.B || oy >= p.Hout || ox >= p.Wout || py < 0 || py >= p.oH || px < 0 || px >= p.oW) continue;
+            const size_t pix = ((size_t)img * p.oH + py) * p.oW + px;
+#pragma unroll
+            for (int nt = 0; nt < 4; nt++) {
+                if (nt >= NT) continue;
+                const int ch = nt * 8 + 2 * t;
+                float v0 = fmaf(acl[mt][nt][2 * half], lo_scale, acc[mt][nt][2 * half]);
+                float v1 = fmaf(acl[mt][nt][2 * half + 1], lo_scale, acc[mt][nt][2 * half + 1]);
+                if (bias) {
+                    if (ch < p.Cout) v0 += __ldg(bias + ch);
+                    if (ch + 1 < p.Cout) v1 += __ldg(bias + ch + 1);
+                }
+                if ((p.Cout & 1) == 0 && ch + 1 < p.Cout) {
+                    *reinterpret_cast<float2 *>(out + pix * p.Cout + ch) = make_float2(v0, v1);
+                } else {
+                    if (ch < p.Cout) out[pix * p.Cout + ch] = v0;
+                    if (ch + 1 < p.Cout) out[pix * p.Cout + ch + 1] = v1;
+                }
+            }
+        }
+    }
+}
+
+// wgrad v2: an item is 128 output pixels (8 k-steps of one 16-pixel group each: a row of a 16-wide tile, or two rows of an
+// 8-wide one) of fr frames; x tile and dy tile are staged by the same routine ([pixel][channel], swizzled) and both
+// fragments are transposed ldmatrix loads.  Accumulators, flush and partial layout as lwgrad_kernel.
+template <int CIN, int NPL, bool F16>
+__global__ void __launch_bounds__(256, 1)
+lwgrad2_kernel(const __grid_constant__ LConvParams p, const float *__restrict__ x, const float *__restrict__ dy,
+               float *__restrict__ partial, int n_items)
+{
+    extern __shared__ __align__(16) uint8_t sm_raw[];
+    constexpr int CH = CIN / 8;
+    const int CC = p.CoutPad, CCH = CC >> 3;                                    // dy channels (8, 16 or 32) and chunks per pixel
+    const int n_d = kLwPix * CC;                                                // multiple of 64
+    uint16_t *s_i = reinterpret_cast<uint16_t *>(sm_raw);                     // [NPL][n_in]
+    uint16_t *s_d = s_i + (size_t)NPL * p.n_in;                                // [NPL][128][CC]
+    int *s_qoff = reinterpret_cast<int *>(s_d + (size_t)NPL * n_d);            // [KP / 8]
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int j = lane >> 3, r = lane & 7;
+    const int NT = CC >> 3;
+    const int n_mt = p.KP / 16;
+    const int tiles = p.tiles_x * p.tiles_y;
+    lc2_qoff_table<CIN>(p, s_qoff, tid);
+
+    float acc[kLwMaxMt][4][4], acl[kLwMaxMt][4][4], tot[kLwMaxMt][4][4];
+#pragma unroll
+    for (int m = 0; m < kLwMaxMt; m++)
+#pragma unroll
+        for (int nt = 0; nt < 4; nt++)
+#pragma unroll
+            for (int e = 0; e < 4; e++) { acc[m][nt][e] = 0.0f; acl[m][nt][e] = 0.0f; tot[m][nt][e] = 0.0f; }
+
+    // A (transposed load): matrix j = (chunk j & 1 of the m-tile, pixels 8 (j >> 1) .. + 7 of the k-step)
+    const int i_a = r + ((j >> 1) << 3);
+    // B (transposed load): matrix j = (pixels 8 (j & 1) .. + 7, n-tile 2 ntp + (j >> 1))
+    const int i_b = r + ((j & 1) << 3);
+    const uint32_t si_base = lc_smem_u32(s_i), sd_base = lc_smem_u32(s_d);
+    const uint32_t in_plane = (uint32_t)p.n_in * 2u, d_plane = (uint32_t)n_d * 2u;
+
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int fg = item / tiles, trem = item - fg * tiles;
+        const int oy0 = (trem / p.tiles_x) * p.th, ox0 = (trem % p.tiles_x) * p.tw;
+        const int img0 = fg * p.fr;
+        __syncthreads();                                                       // the previous item's MMAs are done with the tiles
+        lc2_stage<CIN, NPL, F16>(x + (size_t)img0 * p.Hin * p.Win * CIN, (size_t)p.Hin * p.Win * CIN, p.B - img0, p.Hin, p.Win,
+                                 p.IH, p.IW, oy0 * p.stride - p.pad_t, ox0 * p.stride - p.pad_l, p.fr, s_i, p.n_in, warp, lane);
+        {
+            const float *dsrc = dy + (size_t)img0 * p.Hout * p.Wout * CC;
+            const size_t fe = (size_t)p.Hout * p.Wout * CC;
+            if (CC == 32) lc2_stage<32, NPL, F16>(dsrc, fe, p.B - img0, p.Hout, p.Wout, p.th, p.tw, oy0, ox0, p.fr, s_d, n_d, warp, lane);
+            else if (CC == 16) lc2_stage<16, NPL, F16>(dsrc, fe, p.B - img0, p.Hout, p.Wout, p.th, p.tw, oy0, ox0, p.fr, s_d, n_d, warp, lane);
+            else lc2_stage<8, NPL, F16>(dsrc, fe, p.B - img0, p.Hout, p.Wout, p.th, p.tw, oy0, ox0, p.fr, s_d, n_d, warp, lane);
+        }
+        __syncthreads();
+
+#pragma unroll 1
+        for (int ks = 0; ks < 8; ks++) {
+            uint32_t b[4][NPL][2];
+#pragma unroll
+            for (int ntp = 0; ntp < 2; ntp++) {
+                if (ntp * 2 < NT) {
+                    int chunk = ntp * 2 + (j >> 1);
+                    chunk = chunk < CCH ? chunk : CCH - 1;
+                    const int L = (ks * 16 + i_b) * CCH + chunk;
+                    const uint32_t ad = sd_base + ((uint32_t)lc_swz(L) << 4);
+#pragma unroll
+                    for (int q = 0; q < NPL; q++) {
+                        uint32_t t4[4];
+                        lc_ldsm4t(t4, ad + (uint32_t)q * d_plane);
+                        b[2 * ntp][q][0] = t4[0]; b[2 * ntp][q][1] = t4[1];
+                        b[2 * ntp + 1][q][0] = t4[2]; b[2 * ntp + 1][q][1] = t4[3];
+                    }
+                }
+            }
+            // staged pixel of this lane's row of the A matrices
+            const int rowg = ks * p.mt_rows + (p.tw == 8 ? (i_a >> 3) : 0);
+            const int col = p.tw == 8 ? (i_a & 7) : i_a;
+            const int f = rowg >> p.th_log, ry = rowg & (p.th - 1);
+            const int pix = ((f * p.IH + ry * p.stride) * p.IW + col * p.stride) * CH;
+#pragma unroll
+            for (int m = 0; m < kLwMaxMt; m++) {
+                const int mt = warp + 8 * m;
+                if (mt < n_mt) {
+                    const int L = pix + s_qoff[2 * mt + (j & 1)];
+                    SP_CHECK(L >= 0 && lc_swz(L) * 8 + 8 <= p.n_in);
+                    const uint32_t ad = si_base + ((uint32_t)lc_swz(L) << 4);
+                    uint32_t a[NPL][4];
+#pragma unroll
+                    for (int q = 0; q < NPL; q++) lc_ldsm4t(a[q], ad + (uint32_t)q * in_plane);
+#pragma unroll
+                    for (int nt = 0; nt < 4; nt++)
+                        if (nt < NT) lc_mma_planes2<NPL, F16>(acc[m][nt], acl[m][nt], a, b[nt]);
+                }
+            }
+        }
+#pragma unroll
+        for (int m = 0; m < kLwMaxMt; m++)
+#pragma unroll
+            for (int nt = 0; nt < 4; nt++)
+#pragma unroll
+                for (int e = 0; e < 4; e++) { tot[m][nt][e] += acc[m][nt][e]; acc[m][nt][e] = 0.0f; }
+    }
+    const float lo_scale = F16 ? kF16LoInv : 1.0f;
+    const int g = lane >> 2, t = lane & 3;
+    float *mine = partial + (size_t)blockIdx.x * p.KP * p.CoutPad;
+#pragma unroll
+    for (int m = 0; m < kLwMaxMt; m++) {
+        const int mt = warp + 8 * m;
+        if (mt >= n_mt) continue;
+#pragma unroll
+        for (int nt = 0; nt < 4; nt++) {
+            if (nt >= NT) continue;
+            const int col = nt * 8 + 2 * t;
+            float v[4];
+#pragma unroll
+            for (int e = 0; e < 4; e++) v[e] = fmaf(acl[m][nt][e], lo_scale, tot[m][nt][e]);
+            *reinterpret_cast<float2 *>(mine + (size_t)(mt * 16 + g) * p.CoutPad + col) = make_float2(v[0], v[1]);
+            *reinterpret_cast<float2 *>(mine + (size_t)(mt * 16 + g + 8) * p.CoutPad + col) = make_float2(v[2], v[3]);
+        }
+    }
+}
+
 static void lc_fill(LConvParams &p, int B, int Hin, int Win, int Cin, int Hout, int Wout, int Cout, int KH, int KW, int stride,
                     int pad_t, int pad_l, int oH, int oW, int o_sy, int o_sx, int o_oy, int o_ox)
 {
@@ -608,6 +1030,24 @@ static void lc_fill(LConvParams &p, int B, int Hin, int Win, int Cin, int Hout, 
     p.IH = (kLcTh - 1) * stride + KH; p.IW = (kLcTw - 1) * stride + KW;
     p.tiles_x = (Wout + kLcTw - 1) / kLcTw; p.tiles_y = (Hout + kLcTh - 1) / kLcTh;
     p.oH = oH; p.oW = oW; p.o_sy = o_sy; p.o_sx = o_sx; p.o_oy = o_oy; p.o_ox = o_ox;
+    p.tw = kLcTw; p.th = kLcTh; p.fr = 1; p.mt_rows = 1; p.th_log = 3; p.n_in = 0;
+}
+
+// tile of the v2 kernels: `rows` = output rows a CTA covers over all its frames (8 warps x m-tiles per warp x mt_rows)
+static void lc2_tile(LConvParams &p, int Cin, int m_tiles_per_warp)
+{
+    p.tw = p.Wout <= 8 ? 8 : 16;
+    p.mt_rows = 16 / p.tw;
+    const int rows_w = m_tiles_per_warp * p.mt_rows, rows = 8 * rows_w;
+    int th = rows_w;
+    while (th < p.Hout && th < rows) th *= 2;
+    p.th = th;
+    p.th_log = 0;
+    while ((1 << p.th_log) < th) p.th_log++;
+    p.fr = rows / th;
+    p.IH = (p.th - 1) * p.stride + p.KH; p.IW = (p.tw - 1) * p.stride + p.KW;
+    p.tiles_x = (p.Wout + p.tw - 1) / p.tw; p.tiles_y = (p.Hout + p.th - 1) / p.th;
+    p.n_in = (p.fr * p.IH * p.IW * Cin + 63) & ~63;
 }
 
 constexpr size_t kLcSmemMax = 227 * 1024;        // per-CTA shared memory on sm_100
@@ -626,6 +1066,9 @@ long long bounds_violations_learn()
 using namespace spiral;
 
 static bool lc_cin_ok(int Cin) { return Cin == 1 || Cin == 2 || Cin == 3 || Cin == 6 || Cin == 8 || Cin == 16 || Cin == 32; }
+// operand formats (the `n_planes` argument of the C ABI): 2 = bf16x3, 3 = bf16x6, 4 = f16x3 (two fp16 planes)
+static bool lc_prec_ok(int code) { return code == 2 || code == 3 || code == 4; }
+static int lc_prec_planes(int code) { return code == 3 ? 3 : 2; }
 
 // elements of ONE plane of a packed kernel
 extern "C" int64_t spiral_lconv_packed_elems(int32_t Cin, int32_t Cout, int32_t n_taps)
@@ -639,7 +1082,7 @@ extern "C" int spiral_lconv_pack(const float *w, void *packed_planes, int32_t n_
                                  const int32_t *tap_kx, void *stream)
 {
     SPIRAL_REQUIRE(w); SPIRAL_REQUIRE(packed_planes); SPIRAL_REQUIRE(tap_ky); SPIRAL_REQUIRE(tap_kx);
-    if (rows < 1 || rows > 32 || !lc_cin_ok(Ck) || n_taps < 1 || n_taps > kLcMaxTaps || (n_planes != 2 && n_planes != 3))
+    if (rows < 1 || rows > 32 || !lc_cin_ok(Ck) || n_taps < 1 || n_taps > kLcMaxTaps || !lc_prec_ok(n_planes))
         return spiral_set_error(SPIRAL_EINVAL, "lconv_pack: unsupported shape rows=%d Ck=%d taps=%d planes=%d", rows, Ck, n_taps, n_planes);
     LPackParams p;
     p.rows = rows; p.rows_pad = (rows + 7) & ~7; p.Ck = Ck; p.n_taps = n_taps;
@@ -648,6 +1091,7 @@ extern "C" int spiral_lconv_pack(const float *w, void *packed_planes, int32_t n_
     for (int i = 0; i < kLcMaxTaps; i++) { p.tap_ky[i] = i < n_taps ? tap_ky[i] : 0; p.tap_kx[i] = i < n_taps ? tap_kx[i] : 0; }
     const int n = p.rows_pad * p.KS;
     if (n_planes == 2) lpack_kernel<2><<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(p, w, (uint16_t *)packed_planes);
+    else if (n_planes == 4) lpack_kernel<2, true><<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(p, w, (uint16_t *)packed_planes);
     else lpack_kernel<3><<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(p, w, (uint16_t *)packed_planes);
     const cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? SPIRAL_OK : spiral_cuda_error(e, "spiral_lconv_pack");
@@ -682,6 +1126,56 @@ static int lwgrad_launch(const LConvParams &p, const float *x, const float *dy, 
     return SPIRAL_OK;
 }
 
+template <int CIN, int NPL, bool F16, int MT>
+static int lconv2_launch(const LConvParams &p, const float *x, const void *w, const float *bias, float *out, int grid, size_t smem,
+                         cudaStream_t st)
+{
+    static bool attr = false;
+    if (!attr) {
+        const cudaError_t e = cudaFuncSetAttribute(lconv2_kernel<CIN, NPL, F16, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLcSmemMax);
+        if (e != cudaSuccess) return spiral_cuda_error(e, "cudaFuncSetAttribute(lconv2_kernel)");
+        attr = true;
+    }
+    lconv2_kernel<CIN, NPL, F16, MT><<<grid, 256, smem, st>>>(p, x, (const uint16_t *)w, bias, out);
+    return SPIRAL_OK;
+}
+
+template <int CIN, int NPL, bool F16>
+static int lwgrad2_launch(const LConvParams &p, const float *x, const float *dy, float *ws, int n_items, int grid, size_t smem,
+                          cudaStream_t st)
+{
+    static bool attr = false;
+    if (!attr) {
+        const cudaError_t e = cudaFuncSetAttribute(lwgrad2_kernel<CIN, NPL, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLcSmemMax);
+        if (e != cudaSuccess) return spiral_cuda_error(e, "cudaFuncSetAttribute(lwgrad2_kernel)");
+        attr = true;
+    }
+    lwgrad2_kernel<CIN, NPL, F16><<<grid, 256, smem, st>>>(p, x, dy, ws, n_items);
+    return SPIRAL_OK;
+}
+
+// v2 dispatch over (Cin in {8, 16, 32}) x (operand format); FN<CIN, NPL, F16, ...>
+#define LC2_DISPATCH(FN, MTARG, ...)                                                                                  \
+    do {                                                                                                              \
+        int rc_;                                                                                                      \
+        if (n_planes == 4) {                                                                                          \
+            if (Cin == 8) rc_ = FN<8, 2, true MTARG>(__VA_ARGS__);                                                    \
+            else if (Cin == 16) rc_ = FN<16, 2, true MTARG>(__VA_ARGS__);                                             \
+            else rc_ = FN<32, 2, true MTARG>(__VA_ARGS__);                                                            \
+        } else if (n_planes == 2) {                                                                                   \
+            if (Cin == 8) rc_ = FN<8, 2, false MTARG>(__VA_ARGS__);                                                   \
+            else if (Cin == 16) rc_ = FN<16, 2, false MTARG>(__VA_ARGS__);                                            \
+            else rc_ = FN<32, 2, false MTARG>(__VA_ARGS__);                                                           \
+        } else {                                                                                                      \
+            if (Cin == 8) rc_ = FN<8, 3, false MTARG>(__VA_ARGS__);                                                   \
+            else if (Cin == 16) rc_ = FN<16, 3, false MTARG>(__VA_ARGS__);                                            \
+            else rc_ = FN<32, 3, false MTARG>(__VA_ARGS__);                                                           \
+        }                                                                                                             \
+        if (rc_ != SPIRAL_OK) return rc_;                                                                             \
+    } while (0)
+#define LC2_COMMA_1 , 1
+#define LC2_COMMA_2 , 2
+
 #define LC_DISPATCH(FN, ...)                                                                                          \
     do {                                                                                                              \
         int rc_;                                                                                                      \
@@ -715,15 +1209,34 @@ extern "C" int spiral_lconv_forward(const float *x, const void *w_planes, int32_
                                     int32_t oW, int32_t o_sy, int32_t o_sx, int32_t o_oy, int32_t o_ox, void *stream)
 {
     SPIRAL_REQUIRE(x); SPIRAL_REQUIRE(w_planes); SPIRAL_REQUIRE(out);
-    if (B <= 0 || Cout <= 0 || Cout > 32 || !lc_cin_ok(Cin) || KH * KW > kLcMaxTaps || (n_planes != 2 && n_planes != 3))
+    if (B <= 0 || Cout <= 0 || Cout > 32 || !lc_cin_ok(Cin) || KH * KW > kLcMaxTaps || !lc_prec_ok(n_planes))
         return spiral_set_error(SPIRAL_EINVAL, "lconv: unsupported shape Cin=%d Cout=%d taps=%d planes=%d", Cin, Cout, KH * KW, n_planes);
     LConvParams p;
     lc_fill(p, B, Hin, Win, Cin, Hout, Wout, Cout, KH, KW, stride, pad_t, pad_l, oH, oW, o_sy, o_sx, o_oy, o_ox);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (Cin % 8 == 0) {
+        const int npl = lc_prec_planes(n_planes);
+        const size_t n_w2 = (size_t)p.CoutPad * p.KS;
+        for (int mt = 2; mt >= 1; mt--) {
+            lc2_tile(p, Cin, mt);
+            const size_t smem2 = (size_t)npl * ((size_t)p.n_in + n_w2) * 2 + (size_t)(p.KP / 8) * 4;
+            if (smem2 > kLcSmemMax) {
+                if (mt == 1) return spiral_set_error(SPIRAL_EUNSUPPORTED, "lconv: tile does not fit shared memory (%zu bytes)", smem2);
+                continue;
+            }
+            const int grid2 = ((B + p.fr - 1) / p.fr) * p.tiles_x * p.tiles_y;
+            if (mt == 2) LC2_DISPATCH(lconv2_launch, LC2_COMMA_2, p, x, w_planes, bias, out, grid2, smem2, st);
+            else LC2_DISPATCH(lconv2_launch, LC2_COMMA_1, p, x, w_planes, bias, out, grid2, smem2, st);
+            break;
+        }
+        const cudaError_t e2 = cudaGetLastError();
+        return e2 == cudaSuccess ? SPIRAL_OK : spiral_cuda_error(e2, "spiral_lconv_forward");
+    }
+    if (n_planes == 4) return spiral_set_error(SPIRAL_EUNSUPPORTED, "lconv: the f16x3 format needs Cin %% 8 == 0 (Cin=%d)", Cin);
     const size_t n_w = (size_t)p.CoutPad * p.KS, n_in8 = ((size_t)p.IH * p.IW * Cin + 7) & ~(size_t)7;
     const size_t smem = (size_t)n_planes * (n_w + n_in8) * 2 + (size_t)p.KP * 4;
     if (smem > kLcSmemMax - 2048) return spiral_set_error(SPIRAL_EUNSUPPORTED, "lconv: tile does not fit shared memory (%zu bytes)", smem);
     const int grid = B * p.tiles_x * p.tiles_y;
-    cudaStream_t st = (cudaStream_t)stream;
     LC_DISPATCH(lconv_launch, p, x, w_planes, bias, out, grid, smem, st);
     const cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? SPIRAL_OK : spiral_cuda_error(e, "spiral_lconv_forward");
@@ -775,16 +1288,31 @@ extern "C" int spiral_lconv_wgrad(const float *x, const float *dy, float *dw, fl
 {
     SPIRAL_REQUIRE(x); SPIRAL_REQUIRE(dy); SPIRAL_REQUIRE(dw); SPIRAL_REQUIRE(workspace);
     if (B <= 0 || Cout <= 0 || Cout > 32 || !lc_cin_ok(Cin) || KH * KW > kLcMaxTaps || KH * KW * Cin > 8 * kLwMaxMt * 16 ||
-        (n_planes != 2 && n_planes != 3))
+        !lc_prec_ok(n_planes))
         return spiral_set_error(SPIRAL_EINVAL, "lconv_wgrad: unsupported shape Cin=%d Cout=%d taps=%d planes=%d", Cin, Cout, KH * KW, n_planes);
     LConvParams p;
     lc_fill(p, B, Hin, Win, Cin, Hout, Wout, Cout, KH, KW, stride, pad_t, pad_l, Hout, Wout, 1, 1, 0, 0);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (Cin % 8 == 0 && (Cout == 8 || Cout == 16 || Cout == 32)) {
+        const int npl = lc_prec_planes(n_planes);
+        lc2_tile(p, Cin, 1);
+        const size_t smem2 = (size_t)npl * ((size_t)p.n_in + (size_t)kLwPix * p.CoutPad) * 2 + (size_t)(p.KP / 8) * 4;
+        if (smem2 > kLcSmemMax) return spiral_set_error(SPIRAL_EUNSUPPORTED, "lconv_wgrad: tile does not fit shared memory (%zu bytes)", smem2);
+        const int n_items2 = ((B + p.fr - 1) / p.fr) * p.tiles_x * p.tiles_y;
+        const int grid2 = n_items2 < 148 ? n_items2 : 148;
+        LC2_DISPATCH(lwgrad2_launch, , p, x, dy, workspace, n_items2, grid2, smem2, st);
+        const int n2 = p.K * Cout;
+        lwgrad_reduce_kernel<<<(n2 + 255) / 256, 256, 0, st>>>(workspace, dw, grid2, p.K, p.KP, Cout, p.CoutPad);
+        const cudaError_t e2 = cudaGetLastError();
+        return e2 == cudaSuccess ? SPIRAL_OK : spiral_cuda_error(e2, "spiral_lconv_wgrad");
+    }
+    // shapes outside the v2 kernels: f16x3 -> bf16x6 (LC_DISPATCH takes every format but bf16x3 as three planes)
+    const int n_planes_old = n_planes == 2 ? 2 : 3;
     const size_t n_in8 = ((size_t)p.IH * p.IW * Cin + 7) & ~(size_t)7;
-    const size_t smem = (size_t)n_planes * (n_in8 + (size_t)p.CoutPad * kLwPS) * 2 + (size_t)p.KP * 4;
+    const size_t smem = (size_t)n_planes_old * (n_in8 + (size_t)p.CoutPad * kLwPS) * 2 + (size_t)p.KP * 4;
     if (smem > kLcSmemMax) return spiral_set_error(SPIRAL_EUNSUPPORTED, "lconv_wgrad: tile does not fit shared memory (%zu bytes)", smem);
     const int n_items = B * p.tiles_x * p.tiles_y;
     const int grid = n_items < 148 * 2 ? n_items : 148 * 2;
-    cudaStream_t st = (cudaStream_t)stream;
     if (Cout == 1 && Cin == 32) {
         // scalar output map: fp32 SIMT correlation (lwgrad1_kernel)
         const size_t smem1 = ((size_t)p.IH * p.IW * Cin + kLcTw * kLcTh) * sizeof(float);

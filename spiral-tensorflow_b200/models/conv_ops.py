@@ -131,20 +131,29 @@ def conv5x5s2(x, w, precision=1):
     return _Conv.apply(x, w, int(precision))
 
 
-def disc_forward_native(params, x, layer_num, batch_norm, normalize=True, precision=1):
+def disc_forward_native(params, x, layer_num, batch_norm, normalize=True, precision=1, groups=1):
     """Differentiable D(x) (models/discriminator.py:51-95) whose convolutions and all their
     gradients run on libspiral_b200.so.  x f32[N,S,S,C] NHWC (0..255 when ``normalize``).
     TF semantics: SAME padding 1/2, BN epsilon 1e-3 with the biased batch variance (training mode),
-    leaky-ReLU 0.2.  Returns (probs[N], logits[N])."""
+    leaky-ReLU 0.2.  Returns (probs[N], logits[N]).
+
+    ``groups`` > 1: x holds that many equal batches back to back, each normalised with ITS OWN batch statistics, i.e.
+    the result of ``groups`` separate calls of the shared-weight network (what build_optim does with real, fake and the
+    interpolates, :99-117) from one launch per layer instead of one per call."""
     if normalize:
         x = (x - 127.5) / 127.5
+    G = int(groups)
+    if x.shape[0] % G:
+        raise ValueError("batch %d does not split into %d groups" % (x.shape[0], G))
     for l in range(layer_num):
         x = conv5x5s2(x, params["conv%d/kernel" % l], precision) + params["conv%d/bias" % l]
         if l > 0 and batch_norm:
-            mean = x.mean(dim=(0, 1, 2), keepdim=True)
-            var = ((x - mean) ** 2).mean(dim=(0, 1, 2), keepdim=True)
-            x = (x - mean) * torch.rsqrt(var + 1e-3) * params[bn_name(l) + "/gamma"] \
-                + params[bn_name(l) + "/beta"]
+            shp = x.shape
+            xg = x.view(G, shp[0] // G, shp[1], shp[2], shp[3])
+            mean = xg.mean(dim=(1, 2, 3), keepdim=True)
+            xc = xg - mean
+            var = (xc * xc).mean(dim=(1, 2, 3), keepdim=True)
+            x = (xc * torch.rsqrt(var + 1e-3)).view(shp) * params[bn_name(l) + "/gamma"] + params[bn_name(l) + "/beta"]
         x = torch.where(x > 0, x, 0.2 * x)
     logits = (x.flatten(1) @ params["dense/kernel"] + params["dense/bias"]).reshape(-1)
     return torch.sigmoid(logits), logits

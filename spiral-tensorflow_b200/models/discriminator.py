@@ -9,6 +9,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 
 import numpy as np
 import torch
@@ -39,6 +40,8 @@ class Discriminator(object):
         self.precision = PRECISIONS[getattr(args, "disc_precision", "fp32")]
         gp = getattr(args, "disc_grad_precision", "auto")
         self.grad_precision = (3 if self.precision != 0 else 0) if gp == "auto" else PRECISIONS[gp]
+        # WGAN-GP step: real / fake / interpolates as one grouped pass (wgan_gp_loss); 0 = three separate passes
+        self.fused_passes = os.environ.get("SPIRAL_DISC_FUSED_PASSES", "1") != "0"
 
         self.params = self._init_params(seed)
         self.var_list = list(self.params.values())
@@ -163,11 +166,11 @@ class Discriminator(object):
         return self.forward(images, global_bn=global_bn)[0]
 
     # ------------------------------------------------------------------
-    def logits_fn(self, x_normed):
+    def logits_fn(self, x_normed, groups=1):
         """Differentiable D on already-normalised NHWC input; convolutions and all their gradients
-        run on libspiral_b200.so (models/conv_ops.py)."""
+        run on libspiral_b200.so (models/conv_ops.py).  ``groups``: see conv_ops.disc_forward_native."""
         return conv_ops.disc_forward_native(self.params, x_normed, self.layer_num, self.batch_norm,
-                                            normalize=False, precision=self.grad_precision)
+                                            normalize=False, precision=self.grad_precision, groups=groups)
 
     def wgan_gp_loss(self, fake, real, alpha, wgan_lambda=None):
         """reference :97-122 (build_optim): critic + lambda * gradient penalty, the penalty on the
@@ -182,12 +185,21 @@ class Discriminator(object):
         if self.conditional:                       # reference :36-38
             f = torch.cat([f, r], -1)
             r = torch.cat([r, r], -1)
-        _, real_logits = self.logits_fn(r)
-        _, fake_logits = self.logits_fn(f)
+        inter = (r.flatten(1) + alpha * (f.flatten(1) - r.flatten(1))).detach().requires_grad_(True)
+        if self.fused_passes:
+            # the three shared-weight passes as ONE pass over [real; fake; interpolates], each third with its own batch
+            # statistics: a third of the launches.  The penalty's gradient is taken w.r.t. the interpolates only; the
+            # first two thirds of every dgrad operand are exact zeros (no statistic crosses a group), so the value is
+            # that of the separate passes.
+            n = r.shape[0]
+            probs, logits = self.logits_fn(torch.cat([r, f, inter.view_as(f)], 0), groups=3)
+            real_logits, fake_logits, probs = logits[:n], logits[n:2 * n], probs[2 * n:]
+        else:
+            _, real_logits = self.logits_fn(r)
+            _, fake_logits = self.logits_fn(f)
+            probs, _ = self.logits_fn(inter.view_as(f))
         g_loss = -fake_logits.mean()
         critic = fake_logits.mean() - real_logits.mean()
-        inter = (r.flatten(1) + alpha * (f.flatten(1) - r.flatten(1))).detach().requires_grad_(True)
-        probs, _ = self.logits_fn(inter.view_as(f))
         grads = torch.autograd.grad(probs.sum(), inter, create_graph=True)[0]
         slopes = torch.sqrt(1e-8 + (grads ** 2).sum(1))
         gp = ((slopes - 1.0) ** 2).mean()

@@ -27,7 +27,15 @@ import torch.nn.functional as F
 from .. import _native as N
 
 _WS = {}
-PLANES = 3          # operand planes: 3 = bf16x6 (24 operand bits, fp32-exact operands; the default), 2 = bf16x3 (16 bits)
+# operand format of the kernels (the C ABI's `n_planes`): 4 = f16x3 (two fp16 planes, 22 operand bits, three products; the
+# default), 3 = bf16x6 (three bf16 planes, 24 bits, six products), 2 = bf16x3 (16 bits)
+PLANES = 4
+FORMATS = {"f16x3": 4, "bf16x6": 3, "bf16x3": 2}
+
+
+def _fmt(cin):
+    """f16x3 exists for channel counts that are multiples of 8 (the v2 kernels); other shapes take bf16x6."""
+    return 3 if (PLANES == 4 and cin % 8) else PLANES
 
 
 def _workspace(dev, n):
@@ -41,10 +49,11 @@ def _workspace(dev, n):
 def _pack(w, rows, ck, taps, s_row, s_c, s_ky, s_kx):
     """-> PLANES contiguous bf16 planes [round8(rows)][KS] (as int16) for spiral_lconv_forward."""
     n = int(N.lib().spiral_lconv_packed_elems(ck, rows, len(taps)))
-    planes = torch.empty((PLANES * n,), dtype=torch.int16, device=w.device)
+    fmt = _fmt(ck)
+    planes = torch.empty(((3 if fmt == 3 else 2) * n,), dtype=torch.int16, device=w.device)
     ky = (C.c_int32 * len(taps))(*[t[0] for t in taps])
     kx = (C.c_int32 * len(taps))(*[t[1] for t in taps])
-    N.check(N.lib().spiral_lconv_pack(N.ptr(w), N.ptr(planes), PLANES, rows, ck, len(taps), s_row, s_c, s_ky, s_kx, ky, kx,
+    N.check(N.lib().spiral_lconv_pack(N.ptr(w), N.ptr(planes), fmt, rows, ck, len(taps), s_row, s_c, s_ky, s_kx, ky, kx,
                                       N.stream_ptr()), "spiral_lconv_pack")
     return planes
 
@@ -52,7 +61,7 @@ def _pack(w, rows, ck, taps, s_row, s_c, s_ky, s_kx):
 def _launch(x, packed, bias, out, cin, cout, hout, wout, kh, kw, stride, pad_t, pad_l, scatter=(1, 1, 0, 0)):
     B, hin, win, _ = x.shape
     oh, ow = out.shape[1], out.shape[2]
-    N.check(N.lib().spiral_lconv_forward(N.ptr(x), N.ptr(packed), PLANES, N.ptr(bias), N.ptr(out), B, hin, win,
+    N.check(N.lib().spiral_lconv_forward(N.ptr(x), N.ptr(packed), _fmt(cin), N.ptr(bias), N.ptr(out), B, hin, win,
                                          cin, hout, wout, cout, kh, kw, stride, pad_t, pad_l, oh, ow, scatter[0], scatter[1],
                                          scatter[2], scatter[3], N.stream_ptr()), "spiral_lconv_forward")
     return out

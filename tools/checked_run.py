@@ -49,7 +49,7 @@ for math in ("det", "fast"):
 pl = import_module(sp.__name__ + ".models.policy_learn")
 g = torch.Generator(device="cuda")
 g.manual_seed(0)
-for planes in (3, 2):
+for planes in (4, 3, 2):
     pl.PLANES = planes
     for kind, cin, cout, k, stride, pad, H in (("conv", 3, 32, 5, 1, 2, 64), ("conv", 1, 32, 5, 1, 2, 64), ("conv", 32, 32, 4, 2, 0, 64),
                                                ("conv", 32, 32, 4, 2, 0, 31), ("conv", 32, 32, 3, 1, 1, 6), ("conv", 32, 1, 3, 1, 1, 64),
