@@ -15,7 +15,7 @@
 //   * gradients: the input gradient of every one of these layers is again one of these convolutions with a re-indexed
 //     kernel (flipped taps for stride 1; the four parity classes of a transposed convolution for stride 2; a strided
 //     convolution for the transposed ones), so `lconv_kernel` + `lpack_kernel` (a strided gather of the kernel into the
-//     [Cout][taps * Cin] layout the MMA reads) cover forward AND dgrad; `lwgrad_kernel` is the one new contraction:
+//     [Cout][taps * Cin] layout the MMA reads) cover forward AND dgrad; `lwgrad2_kernel` is the one new contraction:
 //     dW[tap, ci][co] = sum over frames and output pixels of x[pixel * stride + tap - pad][ci] * dy[pixel][co], an implicit
 //     GEMM whose reduction runs over pixels, accumulated in registers by persistent CTAs and reduced over CTAs in a fixed
 //     order (deterministic, no atomics).
@@ -168,7 +168,8 @@ __device__ __forceinline__ void lc_mma_planes2(float (&hi)[4], float (&lo)[4], c
 // forward kernel of a convolution, its flipped / transposed adjoint, or one parity class of a transposed convolution.
 // ------------------------------------------------------------------------------------------
 struct LPackParams {
-    int rows, rows_pad, Ck, n_taps, K, KS;
+    int rows, rows_pad, Ck, n_taps, K, KS;       // Ck: channels per tap of the packed layout
+    int Ck_src;                                  // channels of the kernel tensor (< Ck: the rest of each tap is zero)
     long long s_row, s_c, s_ky, s_kx;
     int tap_ky[kLcMaxTaps], tap_kx[kLcMaxTaps];
 };
@@ -183,7 +184,7 @@ lpack_kernel(const __grid_constant__ LPackParams p, const float *__restrict__ w,
         float v = 0.0f;
         if (row < p.rows && k < p.K) {
             const int tap = k / p.Ck, c = k - tap * p.Ck;
-            v = w[row * p.s_row + c * p.s_c + p.tap_ky[tap] * p.s_ky + p.tap_kx[tap] * p.s_kx];
+            if (c < p.Ck_src) v = w[row * p.s_row + c * p.s_c + p.tap_ky[tap] * p.s_ky + p.tap_kx[tap] * p.s_kx];
         }
         if (F16) {
             uint32_t pp[NPL];
@@ -446,245 +447,25 @@ lconv_kernel(const __grid_constant__ LConvParams p, const float *__restrict__ x,
 
 // ------------------------------------------------------------------------------------------
 // wgrad: dW[k = tap * CIN + c][co] = sum_{frame, oy, ox} x[frame, oy*stride - pad + ky, ox*stride - pad + kx, c] * dy[frame, oy, ox, co]
-// Persistent CTAs walk (frame, 8x16 tile of output pixels) work items; per item the input tile and the dy tile are
-// staged as bf16 planes, dy TRANSPOSED ([co][pixel]) so that B fragments are 32-bit loads; warp w owns the m-tiles
-// (16 rows of k) w, w + 8, ... and keeps their accumulators in registers across all items; partial[cta][k][co] at the end.
+// (lwgrad2_kernel below).  Persistent CTAs walk work items of 128 output pixels; warp w owns the m-tiles (16 rows of k)
+// w, w + 8, ... and keeps their accumulators in registers across all items; partial[cta][k][co] at the end, reduced over
+// CTAs in a fixed order.
 // ------------------------------------------------------------------------------------------
 constexpr int kLwMaxMt = 4;                      // m-tiles per warp: K <= 8 * 4 * 16 = 512
 constexpr int kLwPix = kLcTw * kLcTh;            // 128 reduction elements per item
-constexpr int kLwPS = kLwPix + 8;                // row stride of the transposed dy tile
-
-template <int CIN, int NPL>
-__global__ void __launch_bounds__(256, 1)
-lwgrad_kernel(const __grid_constant__ LConvParams p, const float *__restrict__ x, const float *__restrict__ dy,
-              float *__restrict__ partial, int n_items)
-{
-    extern __shared__ __align__(16) uint8_t sm_raw[];
-    const int n_in8 = (p.IH * p.IW * CIN + 7) & ~7;
-    const int n_d = p.CoutPad * kLwPS;
-    uint16_t *s_i = reinterpret_cast<uint16_t *>(sm_raw);                     // [NPL][IH][IW][CIN]
-    uint16_t *s_d = s_i + NPL * n_in8;                                         // [NPL][CoutPad][kLwPS]
-    int *s_koff = reinterpret_cast<int *>(s_d + NPL * n_d);                    // [KP]
-
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int g = lane >> 2, t = lane & 3;
-    const int NT = p.CoutPad >> 3;
-    const int n_mt = p.KP / 16;
-    const int tiles = p.tiles_x * p.tiles_y;
-
-    lc_koff_table(p, CIN, s_koff, tid);
-
-    // `hi` (dominant products) is flushed into the fp32 sum `tot` after every work item, so that an accumulator never chains
-    // more than 8 MMAs; `lo` (cross products) runs through all items
-    float acc[kLwMaxMt][4][4], acl[kLwMaxMt][4][4], tot[kLwMaxMt][4][4];
-#pragma unroll
-    for (int m = 0; m < kLwMaxMt; m++)
-#pragma unroll
-        for (int nt = 0; nt < 4; nt++)
-#pragma unroll
-            for (int j = 0; j < 4; j++) { acc[m][nt][j] = 0.0f; acl[m][nt][j] = 0.0f; tot[m][nt][j] = 0.0f; }
-
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-        const int img = item / tiles, trem = item - img * tiles;
-        const int oy0 = (trem / p.tiles_x) * kLcTh, ox0 = (trem % p.tiles_x) * kLcTw;
-        __syncthreads();                                                       // the previous item's MMAs are done with the tiles
-        lc_stage_input<CIN, NPL>(p, x + (size_t)img * p.Hin * p.Win * CIN, oy0 * p.stride - p.pad_t, ox0 * p.stride - p.pad_l,
-                                 s_i, n_in8, tid);
-        {
-            // dy tile, transposed: s_d[q][co][pixel]; pixels outside the output map are zero
-            const float *di = dy + (size_t)img * p.Hout * p.Wout * p.Cout;
-            constexpr int U = 4;
-            const int n_dy = kLwPix * p.CoutPad;
-            for (int i0 = tid; i0 < n_dy; i0 += 256 * U) {
-                float val[U];
-#pragma unroll
-                for (int u = 0; u < U; u++) {
-                    const int i = i0 + u * 256;
-                    const int pix = i / p.CoutPad, co = i - pix * p.CoutPad;
-                    const int oy = oy0 + pix / kLcTw, ox = ox0 + pix % kLcTw;
-                    val[u] = 0.0f;
-                    if (i < n_dy && co < p.Cout && oy < p.Hout && ox < p.Wout) val[u] = __ldg(di + ((size_t)oy * p.Wout + ox) * p.Cout + co);
-                }
-#pragma unroll
-                for (int u = 0; u < U; u++) {
-                    const int i = i0 + u * 256;
-                    if (i < n_dy) {
-                        const int pix = i / p.CoutPad, co = i - pix * p.CoutPad;
-                        uint16_t pl[NPL];
-                        lc_split<NPL>(val[u], pl);
-#pragma unroll
-                        for (int q = 0; q < NPL; q++) s_d[(size_t)q * n_d + co * kLwPS + pix] = pl[q];
-                    }
-                }
-            }
-        }
-        __syncthreads();
-
-#pragma unroll 1
-        for (int ks = 0; ks < kLcTh; ks++) {                                   // 16 pixels per k-step: tile row ks
-            // B fragments (dy^T): b[0] = {B[2t][n], B[2t+1][n]}, b[1] = {B[2t+8][n], B[2t+9][n]}, n = nt*8 + g
-            uint32_t b[4][NPL][2];
-#pragma unroll
-            for (int nt = 0; nt < 4; nt++) {
-                if (nt < NT) {
-                    const int o = (nt * 8 + g) * kLwPS + ks * kLcTw + 2 * t;
-#pragma unroll
-                    for (int q = 0; q < NPL; q++) {
-                        b[nt][q][0] = *reinterpret_cast<const uint32_t *>(s_d + (size_t)q * n_d + o);
-                        b[nt][q][1] = *reinterpret_cast<const uint32_t *>(s_d + (size_t)q * n_d + o + 8);
-                    }
-                }
-            }
-            const int pb = ((ks * p.stride) * p.IW) * CIN;                     // tile row ks
-            const int c0 = pb + (2 * t) * p.stride * CIN, c1 = c0 + p.stride * CIN;        // pixels 2t, 2t+1
-            const int c8 = c0 + 8 * p.stride * CIN, c9 = c8 + p.stride * CIN;              // pixels 2t+8, 2t+9
-#pragma unroll
-            for (int m = 0; m < kLwMaxMt; m++) {
-                const int mt = warp + 8 * m;
-                if (mt < n_mt) {
-                    const int r0 = s_koff[mt * 16 + g], r1 = s_koff[mt * 16 + g + 8];
-                    SP_CHECK(mt * 16 + g + 8 < p.KP && r0 + c0 >= 0 && r1 + c9 < n_in8 && r0 + c9 < n_in8);
-                    uint32_t a[NPL][4];
-#pragma unroll
-                    for (int q = 0; q < NPL; q++) {
-                        const uint16_t *si = s_i + (size_t)q * n_in8;
-                        a[q][0] = (uint32_t)si[r0 + c0] | ((uint32_t)si[r0 + c1] << 16);
-                        a[q][1] = (uint32_t)si[r1 + c0] | ((uint32_t)si[r1 + c1] << 16);
-                        a[q][2] = (uint32_t)si[r0 + c8] | ((uint32_t)si[r0 + c9] << 16);
-                        a[q][3] = (uint32_t)si[r1 + c8] | ((uint32_t)si[r1 + c9] << 16);
-                    }
-#pragma unroll
-                    for (int nt = 0; nt < 4; nt++) {
-                        if (nt < NT) lc_mma_planes<NPL>(acc[m][nt], acl[m][nt], a, b[nt]);
-                    }
-                }
-            }
-        }
-#pragma unroll
-        for (int m = 0; m < kLwMaxMt; m++)
-#pragma unroll
-            for (int nt = 0; nt < 4; nt++)
-#pragma unroll
-                for (int j = 0; j < 4; j++) { tot[m][nt][j] += acc[m][nt][j]; acc[m][nt][j] = 0.0f; }
-    }
-#pragma unroll
-    for (int m = 0; m < kLwMaxMt; m++)
-#pragma unroll
-        for (int nt = 0; nt < 4; nt++)
-#pragma unroll
-            for (int j = 0; j < 4; j++) acc[m][nt][j] = tot[m][nt][j] + acl[m][nt][j];
-
-    // partial[cta][k][co]: accumulator fragment (rows g, g+8; columns 2t, 2t+1 of n-tile nt)
-    float *mine = partial + (size_t)blockIdx.x * p.KP * p.CoutPad;
-#pragma unroll
-    for (int m = 0; m < kLwMaxMt; m++) {
-        const int mt = warp + 8 * m;
-        if (mt >= n_mt) continue;
-#pragma unroll
-        for (int nt = 0; nt < 4; nt++) {
-            if (nt >= NT) continue;
-            const int col = nt * 8 + 2 * t;
-            *reinterpret_cast<float2 *>(mine + (size_t)(mt * 16 + g) * p.CoutPad + col) = make_float2(acc[m][nt][0], acc[m][nt][1]);
-            *reinterpret_cast<float2 *>(mine + (size_t)(mt * 16 + g + 8) * p.CoutPad + col) = make_float2(acc[m][nt][2], acc[m][nt][3]);
-        }
-    }
-}
-
-// Cout == 1 (the location heads' final 3x3 -> 1 convolution): dW[tap][c] = sum_pixels x[pixel + tap][c] * dy[pixel] is a
-// correlation with a scalar map -- on the MMA path 7 of 8 output columns would be padding.  Plain fp32 FMAs instead: the
-// input tile is staged as fp32, thread (pixel row r = tid / 32, channel c = tid % 32) runs over the 16 pixels of its row
-// and the taps, accumulates in registers across all work items; rows are combined through shared memory at the end.
-// Same partial[cta][k][CoutPad = 8] layout as lwgrad_kernel, so the same reduction follows.
-template <int CIN>
-__global__ void __launch_bounds__(256)
-lwgrad1_kernel(const __grid_constant__ LConvParams p, const float *__restrict__ x, const float *__restrict__ dy,
-               float *__restrict__ partial, int n_items)
-{
-    extern __shared__ __align__(16) uint8_t sm_raw[];
-    float *s_x = reinterpret_cast<float *>(sm_raw);                            // [IH][IW][CIN]
-    float *s_dy = s_x + p.IH * p.IW * CIN;                                     // [128]
-    __shared__ int s_toff[kLcMaxTaps];                                         // tap -> offset in the staged tile
-    const int tid = threadIdx.x;
-    if (tid < kLcMaxTaps) s_toff[tid] = tid < p.KH * p.KW ? ((tid / p.KW) * p.IW + tid % p.KW) * CIN : 0;
-    const int c = tid % CIN, r = tid / CIN;                                    // rows handled: r, r + 256 / CIN, ...
-    constexpr int RSTEP = 256 / CIN;
-    const int tiles = p.tiles_x * p.tiles_y;
-    const int taps = p.KH * p.KW;
-    float acc[kLcMaxTaps];
-#pragma unroll
-    for (int i = 0; i < kLcMaxTaps; i++) acc[i] = 0.0f;
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-        const int img = item / tiles, trem = item - img * tiles;
-        const int oy0 = (trem / p.tiles_x) * kLcTh, ox0 = (trem % p.tiles_x) * kLcTw;
-        __syncthreads();
-        const float *xi = x + (size_t)img * p.Hin * p.Win * CIN;
-        const int iy0 = oy0 * p.stride - p.pad_t, ix0 = ox0 * p.stride - p.pad_l;
-        {
-            // float4 loads, 4 in flight per thread (the staging is latency-bound)
-            constexpr int V = CIN / 4, U = 4;
-            const int n_vec = p.IH * p.IW * V;
-            for (int i0 = tid; i0 < n_vec; i0 += 256 * U) {
-                float4 val[U];
-#pragma unroll
-                for (int u = 0; u < U; u++) {
-                    const int i = i0 + u * 256;
-                    val[u] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-                    if (i < n_vec) {
-                        const int pix = i / V, v = i - pix * V;
-                        const int ly = pix / p.IW, lx = pix - ly * p.IW;
-                        const int iy = iy0 + ly, ix = ix0 + lx;
-                        if (iy >= 0 && iy < p.Hin && ix >= 0 && ix < p.Win)
-                            val[u] = __ldg(reinterpret_cast<const float4 *>(xi + ((size_t)iy * p.Win + ix) * CIN) + v);
-                    }
-                }
-#pragma unroll
-                for (int u = 0; u < U; u++) {
-                    const int i = i0 + u * 256;
-                    if (i < n_vec) reinterpret_cast<float4 *>(s_x)[i] = val[u];
-                }
-            }
-        }
-        if (tid < kLcTw * kLcTh) {
-            const int oy = oy0 + tid / kLcTw, ox = ox0 + tid % kLcTw;
-            s_dy[tid] = (oy < p.Hout && ox < p.Wout) ? __ldg(dy + ((size_t)img * p.Hout + oy) * p.Wout + ox) : 0.0f;
-        }
-        __syncthreads();
-        for (int row = r; row < kLcTh; row += RSTEP) {
-#pragma unroll 4
-            for (int col = 0; col < kLcTw; col++) {
-                const float d = s_dy[row * kLcTw + col];
-                const float *xp = s_x + ((row * p.stride) * p.IW + col * p.stride) * CIN + c;
-#pragma unroll
-                for (int tp = 0; tp < kLcMaxTaps; tp++)
-                    if (tp < taps) acc[tp] = fmaf(xp[s_toff[tp]], d, acc[tp]);
-            }
-        }
-    }
-    // combine the row groups: s_red[g][tap][c]
-    __syncthreads();
-    float *s_red = reinterpret_cast<float *>(sm_raw);
-    for (int tp = 0; tp < taps; tp++) s_red[(r * taps + tp) * CIN + c] = acc[tp];
-    __syncthreads();
-    float *mine = partial + (size_t)blockIdx.x * p.KP * p.CoutPad;
-    for (int k = tid; k < p.KP; k += 256) {
-        float sum = 0.0f;
-        if (k < p.K) {
-            const int tp = k / CIN, cc = k - tp * CIN;
-            for (int g = 0; g < RSTEP && g < kLcTh; g++) sum += s_red[(g * taps + tp) * CIN + cc];
-        }
-        for (int j = 0; j < p.CoutPad; j++) mine[(size_t)k * p.CoutPad + j] = j == 0 ? sum : 0.0f;
-    }
-}
 
 // dw[k][co] (k < K, co < Cout) = sum over CTAs, fixed order
+// (cin < cin_pad: the partials' k index is tap * cin_pad + c, dw's is tap * cin + c)
 __global__ void __launch_bounds__(256)
-lwgrad_reduce_kernel(const float *__restrict__ partial, float *__restrict__ dw, int n_cta, int K, int KP, int Cout, int CoutPad)
+lwgrad_reduce_kernel(const float *__restrict__ partial, float *__restrict__ dw, int n_cta, int K, int KP, int Cout, int CoutPad,
+                     int cin = 1, int cin_pad = 1)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= K * Cout) return;
     const int k = i / Cout, co = i - k * Cout;
+    const int kp = (k / cin) * cin_pad + k % cin;
     float s = 0.0f;
-    for (int c = 0; c < n_cta; c++) s += partial[((size_t)c * KP + k) * CoutPad + co];
+    for (int c = 0; c < n_cta; c++) s += partial[((size_t)c * KP + kp) * CoutPad + co];
     dw[i] = s;
 }
 
@@ -707,47 +488,87 @@ lwgrad_reduce_kernel(const float *__restrict__ partial, float *__restrict__ dw, 
 // ==========================================================================================
 __device__ __forceinline__ int lc_swz(int L) { return (L & ~7) | ((L ^ (L >> 3)) & 7); }
 
-// stage the box [fr frames][RH rows][RW columns][C channels] of an NHWC fp32 tensor [., H, W, C] starting at (y0, x0) of frame 0
-// of `src` (zero outside the map and for frames >= frames_left) as NPL swizzled planes of n_plane halfwords
-template <int C, int NPL, bool F16>
+// stage the box [fr frames][RH rows][RW columns] of an NHWC fp32 tensor [., H, W, CSRC] starting at (y0, x0) of frame 0 of
+// `src` (zero outside the map and for frames >= frames_left) as NPL swizzled planes [pixel][C] of n_plane halfwords.
+// CSRC == C: float4 loads.  CSRC < C = 8 (1, 2, 3 or 6 image / scalar-map channels): the pixel's channels are padded with
+// zeros to one 16-byte chunk, so these layers run on the same kernels (the padded k rows meet zero kernel columns).
+template <int CSRC, int C, int NPL, bool F16>
 __device__ __forceinline__ void lc2_stage(const float *__restrict__ src, size_t frame_elems, int frames_left, int H, int W,
                                           int RH, int RW, int y0, int x0, int fr, uint16_t *s, int n_plane, int warp, int lane)
 {
-    constexpr int V = C / 4;                                                   // float4 per pixel
-    constexpr int U = 8;                                                       // loads in flight per thread
-    const int rows = fr * RH, rowlen = RW * V;
-    for (int gr = warp; gr < rows; gr += 8) {
-        const int f = gr / RH, ly = gr - f * RH;
-        const int iy = y0 + ly;
-        const bool row_ok = f < frames_left && iy >= 0 && iy < H;
-        // only dereferenced for pixels inside the map
-        const float4 *rowp = reinterpret_cast<const float4 *>(src + (ptrdiff_t)f * (ptrdiff_t)frame_elems +
-                                                              ((ptrdiff_t)iy * W + x0) * C);
-        const int e_row = gr * RW * C;
-        for (int i0 = lane; i0 < rowlen; i0 += 32 * U) {
-            float4 val[U];
+    static_assert(CSRC == C || C == 8, "channel padding goes to one chunk");
+    const int rows = fr * RH;
+    if (CSRC == C) {
+        constexpr int V = C / 4;                                               // float4 per pixel
+        constexpr int U = 8;                                                   // loads in flight per thread
+        const int rowlen = RW * V;
+        for (int gr = warp; gr < rows; gr += 8) {
+            const int f = gr / RH, ly = gr - f * RH;
+            const int iy = y0 + ly;
+            const bool row_ok = f < frames_left && iy >= 0 && iy < H;
+            // only dereferenced for pixels inside the map
+            const float4 *rowp = reinterpret_cast<const float4 *>(src + (ptrdiff_t)f * (ptrdiff_t)frame_elems +
+                                                                  ((ptrdiff_t)iy * W + x0) * C);
+            const int e_row = gr * RW * C;
+            for (int i0 = lane; i0 < rowlen; i0 += 32 * U) {
+                float4 val[U];
 #pragma unroll
-            for (int u = 0; u < U; u++) {
-                const int i = i0 + 32 * u;
-                val[u] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-                if (i < rowlen && row_ok) {
-                    const int ix = x0 + i / V;
-                    if (ix >= 0 && ix < W) val[u] = __ldg(rowp + i);
+                for (int u = 0; u < U; u++) {
+                    const int i = i0 + 32 * u;
+                    val[u] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                    if (i < rowlen && row_ok) {
+                        const int ix = x0 + i / V;
+                        if (ix >= 0 && ix < W) val[u] = __ldg(rowp + i);
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < U; u++) {
+                    const int i = i0 + 32 * u;
+                    if (i < rowlen) {
+                        const int e = e_row + i * 4;                           // element index in the unswizzled tile
+                        const int L = e >> 3;
+                        uint32_t p0[NPL], p1[NPL];
+                        lc_split_pair<NPL, F16>(val[u].x, val[u].y, p0);
+                        lc_split_pair<NPL, F16>(val[u].z, val[u].w, p1);
+                        SP_CHECK(lc_swz(L) * 8 + 8 <= n_plane);
+                        uint16_t *dst = s + lc_swz(L) * 8 + (e & 4);
+#pragma unroll
+                        for (int q = 0; q < NPL; q++) *reinterpret_cast<uint2 *>(dst + (size_t)q * n_plane) = make_uint2(p0[q], p1[q]);
+                    }
                 }
             }
+        }
+    } else {
+        constexpr int U = 4;                                                   // pixels in flight per lane
+        for (int gr = warp; gr < rows; gr += 8) {
+            const int f = gr / RH, ly = gr - f * RH;
+            const int iy = y0 + ly;
+            const bool row_ok = f < frames_left && iy >= 0 && iy < H;
+            const float *rowp = src + (ptrdiff_t)f * (ptrdiff_t)frame_elems + ((ptrdiff_t)iy * W + x0) * CSRC;
+            for (int i0 = lane; i0 < RW; i0 += 32 * U) {
+                float val[U][8];
 #pragma unroll
-            for (int u = 0; u < U; u++) {
-                const int i = i0 + 32 * u;
-                if (i < rowlen) {
-                    const int e = e_row + i * 4;                               // element index in the unswizzled tile
-                    const int L = e >> 3;
-                    uint32_t p0[NPL], p1[NPL];
-                    lc_split_pair<NPL, F16>(val[u].x, val[u].y, p0);
-                    lc_split_pair<NPL, F16>(val[u].z, val[u].w, p1);
-                    SP_CHECK(lc_swz(L) * 8 + 8 <= n_plane);
-                    uint16_t *dst = s + lc_swz(L) * 8 + (e & 4);
+                for (int u = 0; u < U; u++) {
+                    const int i = i0 + 32 * u;
+                    const int ix = x0 + i;
+                    const bool ok = i < RW && row_ok && ix >= 0 && ix < W;
 #pragma unroll
-                    for (int q = 0; q < NPL; q++) *reinterpret_cast<uint2 *>(dst + (size_t)q * n_plane) = make_uint2(p0[q], p1[q]);
+                    for (int c = 0; c < 8; c++) val[u][c] = (c < CSRC && ok) ? __ldg(rowp + i * CSRC + c) : 0.0f;
+                }
+#pragma unroll
+                for (int u = 0; u < U; u++) {
+                    const int i = i0 + 32 * u;
+                    if (i < RW) {
+                        const int L = gr * RW + i;                             // one chunk per pixel
+                        uint32_t pp[4][NPL];
+#pragma unroll
+                        for (int h = 0; h < 4; h++) lc_split_pair<NPL, F16>(val[u][2 * h], val[u][2 * h + 1], pp[h]);
+                        SP_CHECK(lc_swz(L) * 8 + 8 <= n_plane);
+                        uint16_t *dst = s + lc_swz(L) * 8;
+#pragma unroll
+                        for (int q = 0; q < NPL; q++)
+                            *reinterpret_cast<uint4 *>(dst + (size_t)q * n_plane) = make_uint4(pp[0][q], pp[1][q], pp[2][q], pp[3][q]);
+                    }
                 }
             }
         }
@@ -770,12 +591,13 @@ __device__ __forceinline__ void lc2_qoff_table(const LConvParams &p, int *s_qoff
     }
 }
 
-template <int CIN, int NPL, bool F16, int MT>
+template <int CSRC, int NPL, bool F16, int MT>
 __global__ void __launch_bounds__(256, (NPL == 2) ? 2 : 1)
 lconv2_kernel(const __grid_constant__ LConvParams p, const float *__restrict__ x, const uint16_t *__restrict__ w_planes,
               const float *__restrict__ bias, float *__restrict__ out)
 {
     extern __shared__ __align__(16) uint8_t sm_raw[];
+    constexpr int CIN = CSRC < 8 ? 8 : CSRC;                                    // channels of the staged tile (lc2_stage pads)
     constexpr int CH = CIN / 8;
     const int n_w = p.CoutPad * p.KS;
     uint16_t *s_i = reinterpret_cast<uint16_t *>(sm_raw);                     // [NPL][n_in], swizzled
@@ -794,8 +616,8 @@ lconv2_kernel(const __grid_constant__ LConvParams p, const float *__restrict__ x
         for (int i = tid; i < n16; i += 256) lc_cp_async16(sw + (uint32_t)i * 16u, gw + i);
     }
     lc2_qoff_table<CIN>(p, s_qoff, tid);
-    lc2_stage<CIN, NPL, F16>(x + (size_t)img0 * p.Hin * p.Win * CIN, (size_t)p.Hin * p.Win * CIN, p.B - img0, p.Hin, p.Win, p.IH,
-                             p.IW, oy0 * p.stride - p.pad_t, ox0 * p.stride - p.pad_l, p.fr, s_i, p.n_in, warp, lane);
+    lc2_stage<CSRC, CIN, NPL, F16>(x + (size_t)img0 * p.Hin * p.Win * CSRC, (size_t)p.Hin * p.Win * CSRC, p.B - img0, p.Hin, p.Win,
+                                   p.IH, p.IW, oy0 * p.stride - p.pad_t, ox0 * p.stride - p.pad_l, p.fr, s_i, p.n_in, warp, lane);
     lc_cp_async_wait();
     __syncthreads();
 
@@ -901,15 +723,17 @@ lconv2_kernel(const __grid_constant__ LConvParams p, const float *__restrict__ x
 
 // wgrad v2: an item is 128 output pixels (8 k-steps of one 16-pixel group each: a row of a 16-wide tile, or two rows of an
 // 8-wide one) of fr frames; x tile and dy tile are staged by the same routine ([pixel][channel], swizzled) and both
-// fragments are transposed ldmatrix loads.  Accumulators, flush and partial layout as lwgrad_kernel.
-template <int CIN, int NPL, bool F16>
+// fragments are transposed ldmatrix loads.  `hi` (dominant products) is flushed into the fp32 sum `tot` after every item, so
+// that an accumulator never chains more than 8 MMAs; `lo` (cross products) runs through all items.
+template <int CSRC, int NPL, bool F16>
 __global__ void __launch_bounds__(256, 1)
 lwgrad2_kernel(const __grid_constant__ LConvParams p, const float *__restrict__ x, const float *__restrict__ dy,
                float *__restrict__ partial, int n_items)
 {
     extern __shared__ __align__(16) uint8_t sm_raw[];
+    constexpr int CIN = CSRC < 8 ? 8 : CSRC;
     constexpr int CH = CIN / 8;
-    const int CC = p.CoutPad, CCH = CC >> 3;                                    // dy channels (8, 16 or 32) and chunks per pixel
+    const int CC = p.CoutPad, CCH = CC >> 3;                                    // staged dy channels (8, 16 or 32) and chunks per pixel
     const int n_d = kLwPix * CC;                                                // multiple of 64
     uint16_t *s_i = reinterpret_cast<uint16_t *>(sm_raw);                     // [NPL][n_in]
     uint16_t *s_d = s_i + (size_t)NPL * p.n_in;                                // [NPL][128][CC]
@@ -942,14 +766,15 @@ lwgrad2_kernel(const __grid_constant__ LConvParams p, const float *__restrict__ 
         const int oy0 = (trem / p.tiles_x) * p.th, ox0 = (trem % p.tiles_x) * p.tw;
         const int img0 = fg * p.fr;
         __syncthreads();                                                       // the previous item's MMAs are done with the tiles
-        lc2_stage<CIN, NPL, F16>(x + (size_t)img0 * p.Hin * p.Win * CIN, (size_t)p.Hin * p.Win * CIN, p.B - img0, p.Hin, p.Win,
-                                 p.IH, p.IW, oy0 * p.stride - p.pad_t, ox0 * p.stride - p.pad_l, p.fr, s_i, p.n_in, warp, lane);
+        lc2_stage<CSRC, CIN, NPL, F16>(x + (size_t)img0 * p.Hin * p.Win * CSRC, (size_t)p.Hin * p.Win * CSRC, p.B - img0, p.Hin,
+                                       p.Win, p.IH, p.IW, oy0 * p.stride - p.pad_t, ox0 * p.stride - p.pad_l, p.fr, s_i, p.n_in, warp, lane);
         {
-            const float *dsrc = dy + (size_t)img0 * p.Hout * p.Wout * CC;
-            const size_t fe = (size_t)p.Hout * p.Wout * CC;
-            if (CC == 32) lc2_stage<32, NPL, F16>(dsrc, fe, p.B - img0, p.Hout, p.Wout, p.th, p.tw, oy0, ox0, p.fr, s_d, n_d, warp, lane);
-            else if (CC == 16) lc2_stage<16, NPL, F16>(dsrc, fe, p.B - img0, p.Hout, p.Wout, p.th, p.tw, oy0, ox0, p.fr, s_d, n_d, warp, lane);
-            else lc2_stage<8, NPL, F16>(dsrc, fe, p.B - img0, p.Hout, p.Wout, p.th, p.tw, oy0, ox0, p.fr, s_d, n_d, warp, lane);
+            const float *dsrc = dy + (size_t)img0 * p.Hout * p.Wout * p.Cout;
+            const size_t fe = (size_t)p.Hout * p.Wout * p.Cout;
+            if (p.Cout == 32) lc2_stage<32, 32, NPL, F16>(dsrc, fe, p.B - img0, p.Hout, p.Wout, p.th, p.tw, oy0, ox0, p.fr, s_d, n_d, warp, lane);
+            else if (p.Cout == 16) lc2_stage<16, 16, NPL, F16>(dsrc, fe, p.B - img0, p.Hout, p.Wout, p.th, p.tw, oy0, ox0, p.fr, s_d, n_d, warp, lane);
+            else if (p.Cout == 8) lc2_stage<8, 8, NPL, F16>(dsrc, fe, p.B - img0, p.Hout, p.Wout, p.th, p.tw, oy0, ox0, p.fr, s_d, n_d, warp, lane);
+            else lc2_stage<1, 8, NPL, F16>(dsrc, fe, p.B - img0, p.Hout, p.Wout, p.th, p.tw, oy0, ox0, p.fr, s_d, n_d, warp, lane);   // scalar map
         }
         __syncthreads();
 
@@ -1020,6 +845,89 @@ lwgrad2_kernel(const __grid_constant__ LConvParams p, const float *__restrict__ 
     }
 }
 
+
+// wgrad of a convolution to ONE output channel (the location heads' final 3x3 -> 1, policy.py:290-295), stride 1, 32 input
+// channels: dW[tap][c] = sum_q x[q][c] * dy[q + pad - tap] is a correlation of each input channel with a scalar map -- 288
+// outputs from a 1.3 GB read, memory-bound, and on the MMA path 7 of 8 columns would be padding.  Plain fp32 FMAs (exact
+// products): a warp walks input rows, lane = channel, one coalesced 128-byte load per pixel; the KH x KW window of dy values
+// that pixel meets slides along the row in registers (KH uniform loads per pixel).  Fixed row -> warp assignment and a
+// fixed-order reduction: deterministic.
+template <int KH, int KW>
+__global__ void __launch_bounds__(256)
+lwgrad_scalar_kernel(const float *__restrict__ x, const float *__restrict__ dy, float *__restrict__ partial, int B, int Hin, int Win,
+                     int Hout, int Wout, int pad_t, int pad_l)
+{
+    __shared__ float s_red[8][KH * KW][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int gw = blockIdx.x * 8 + warp, nw = gridDim.x * 8;
+    float acc[KH * KW];
+#pragma unroll
+    for (int i = 0; i < KH * KW; i++) acc[i] = 0.0f;
+    const int rows = B * Hin;
+    for (int rw = gw; rw < rows; rw += nw) {
+        const int img = rw / Hin, iy = rw - img * Hin;
+        const float *xr = x + (size_t)rw * Win * 32 + lane;
+        const float *dr[KH];
+        bool ok[KH];
+#pragma unroll
+        for (int ky = 0; ky < KH; ky++) {
+            const int oy = iy + pad_t - ky;
+            ok[ky] = oy >= 0 && oy < Hout;
+            dr[ky] = dy + ((size_t)img * Hout + (ok[ky] ? oy : 0)) * Wout;
+        }
+        float w[KH][KW];                                                       // w[ky][kx] = dy[oy(ky)][ix + pad_l - kx]
+#pragma unroll
+        for (int ky = 0; ky < KH; ky++)
+#pragma unroll
+            for (int kx = 0; kx < KW; kx++) {
+                const int o = pad_l - kx - 1;                                  // the window of ix = -1
+                w[ky][kx] = (ok[ky] && o >= 0 && o < Wout) ? __ldg(dr[ky] + o) : 0.0f;
+            }
+        constexpr int U = 8;
+        for (int ix0 = 0; ix0 < Win; ix0 += U) {
+            float xv[U], dn[U][KH];
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                const int ix = ix0 + u;
+                xv[u] = ix < Win ? __ldg(xr + (size_t)ix * 32) : 0.0f;
+                const int o = ix + pad_l;
+#pragma unroll
+                for (int ky = 0; ky < KH; ky++) dn[u][ky] = (ok[ky] && o < Wout) ? __ldg(dr[ky] + o) : 0.0f;
+            }
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+#pragma unroll
+                for (int ky = 0; ky < KH; ky++) {
+#pragma unroll
+                    for (int kx = KW - 1; kx > 0; kx--) w[ky][kx] = w[ky][kx - 1];
+                    w[ky][0] = dn[u][ky];
+#pragma unroll
+                    for (int kx = 0; kx < KW; kx++) acc[ky * KW + kx] = fmaf(xv[u], w[ky][kx], acc[ky * KW + kx]);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < KH * KW; i++) s_red[warp][i][lane] = acc[i];
+    __syncthreads();
+    for (int k = threadIdx.x; k < KH * KW * 32; k += 256) {
+        float sum = 0.0f;
+#pragma unroll
+        for (int wv = 0; wv < 8; wv++) sum += s_red[wv][k >> 5][k & 31];
+        partial[(size_t)blockIdx.x * (KH * KW * 32) + k] = sum;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+lwgrad_scalar_reduce_kernel(const float *__restrict__ partial, float *__restrict__ dw, int n_cta, int K)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= K) return;
+    float s = 0.0f;
+    for (int c = 0; c < n_cta; c++) s += partial[(size_t)c * K + k];
+    dw[k] = s;
+}
+
 static void lc_fill(LConvParams &p, int B, int Hin, int Win, int Cin, int Hout, int Wout, int Cout, int KH, int KW, int stride,
                     int pad_t, int pad_l, int oH, int oW, int o_sy, int o_sx, int o_oy, int o_ox)
 {
@@ -1066,6 +974,7 @@ long long bounds_violations_learn()
 using namespace spiral;
 
 static bool lc_cin_ok(int Cin) { return Cin == 1 || Cin == 2 || Cin == 3 || Cin == 6 || Cin == 8 || Cin == 16 || Cin == 32; }
+static int lc_cin_pad(int Cin) { return Cin < 8 ? 8 : Cin; }                  // channels per tap of the staged tile / packed kernel
 // operand formats (the `n_planes` argument of the C ABI): 2 = bf16x3, 3 = bf16x6, 4 = f16x3 (two fp16 planes)
 static bool lc_prec_ok(int code) { return code == 2 || code == 3 || code == 4; }
 static int lc_prec_planes(int code) { return code == 3 ? 3 : 2; }
@@ -1073,7 +982,7 @@ static int lc_prec_planes(int code) { return code == 3 ? 3 : 2; }
 // elements of ONE plane of a packed kernel
 extern "C" int64_t spiral_lconv_packed_elems(int32_t Cin, int32_t Cout, int32_t n_taps)
 {
-    const int K = n_taps * Cin, KP = (K + 15) & ~15, KS = KP + 8, CoutPad = (Cout + 7) & ~7;
+    const int K = n_taps * lc_cin_pad(Cin), KP = (K + 15) & ~15, KS = KP + 8, CoutPad = (Cout + 7) & ~7;
     return (int64_t)CoutPad * KS;
 }
 
@@ -1085,8 +994,8 @@ extern "C" int spiral_lconv_pack(const float *w, void *packed_planes, int32_t n_
     if (rows < 1 || rows > 32 || !lc_cin_ok(Ck) || n_taps < 1 || n_taps > kLcMaxTaps || !lc_prec_ok(n_planes))
         return spiral_set_error(SPIRAL_EINVAL, "lconv_pack: unsupported shape rows=%d Ck=%d taps=%d planes=%d", rows, Ck, n_taps, n_planes);
     LPackParams p;
-    p.rows = rows; p.rows_pad = (rows + 7) & ~7; p.Ck = Ck; p.n_taps = n_taps;
-    p.K = n_taps * Ck; p.KS = ((p.K + 15) & ~15) + 8;
+    p.rows = rows; p.rows_pad = (rows + 7) & ~7; p.Ck = lc_cin_pad(Ck); p.Ck_src = Ck; p.n_taps = n_taps;
+    p.K = n_taps * p.Ck; p.KS = ((p.K + 15) & ~15) + 8;
     p.s_row = s_row; p.s_c = s_c; p.s_ky = s_ky; p.s_kx = s_kx;
     for (int i = 0; i < kLcMaxTaps; i++) { p.tap_ky[i] = i < n_taps ? tap_ky[i] : 0; p.tap_kx[i] = i < n_taps ? tap_kx[i] : 0; }
     const int n = p.rows_pad * p.KS;
@@ -1097,6 +1006,7 @@ extern "C" int spiral_lconv_pack(const float *w, void *packed_planes, int32_t n_
     return e == cudaSuccess ? SPIRAL_OK : spiral_cuda_error(e, "spiral_lconv_pack");
 }
 
+// the first-generation kernel: the discriminator's narrow layers (batch norm + leaky-ReLU on load, batch-norm partials)
 template <int CIN, int NPL>
 static int lconv_launch(const LConvParams &p, const float *x, const void *w, const float *bias, float *out, int grid, size_t smem,
                         cudaStream_t st, const float *in_scale = nullptr, const float *in_shift = nullptr, float *bn_partial = nullptr)
@@ -1112,93 +1022,56 @@ static int lconv_launch(const LConvParams &p, const float *x, const void *w, con
     return SPIRAL_OK;
 }
 
-template <int CIN, int NPL>
-static int lwgrad_launch(const LConvParams &p, const float *x, const float *dy, float *ws, int n_items, int grid, size_t smem,
-                         cudaStream_t st)
-{
-    static bool attr = false;
-    if (!attr) {
-        const cudaError_t e = cudaFuncSetAttribute(lwgrad_kernel<CIN, NPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLcSmemMax);
-        if (e != cudaSuccess) return spiral_cuda_error(e, "cudaFuncSetAttribute(lwgrad_kernel)");
-        attr = true;
-    }
-    lwgrad_kernel<CIN, NPL><<<grid, 256, smem, st>>>(p, x, dy, ws, n_items);
-    return SPIRAL_OK;
-}
-
-template <int CIN, int NPL, bool F16, int MT>
+template <int CSRC, int NPL, bool F16, int MT>
 static int lconv2_launch(const LConvParams &p, const float *x, const void *w, const float *bias, float *out, int grid, size_t smem,
                          cudaStream_t st)
 {
     static bool attr = false;
     if (!attr) {
-        const cudaError_t e = cudaFuncSetAttribute(lconv2_kernel<CIN, NPL, F16, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLcSmemMax);
+        const cudaError_t e = cudaFuncSetAttribute(lconv2_kernel<CSRC, NPL, F16, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLcSmemMax);
         if (e != cudaSuccess) return spiral_cuda_error(e, "cudaFuncSetAttribute(lconv2_kernel)");
         attr = true;
     }
-    lconv2_kernel<CIN, NPL, F16, MT><<<grid, 256, smem, st>>>(p, x, (const uint16_t *)w, bias, out);
+    lconv2_kernel<CSRC, NPL, F16, MT><<<grid, 256, smem, st>>>(p, x, (const uint16_t *)w, bias, out);
     return SPIRAL_OK;
 }
 
-template <int CIN, int NPL, bool F16>
+template <int CSRC, int NPL, bool F16>
 static int lwgrad2_launch(const LConvParams &p, const float *x, const float *dy, float *ws, int n_items, int grid, size_t smem,
                           cudaStream_t st)
 {
     static bool attr = false;
     if (!attr) {
-        const cudaError_t e = cudaFuncSetAttribute(lwgrad2_kernel<CIN, NPL, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLcSmemMax);
+        const cudaError_t e = cudaFuncSetAttribute(lwgrad2_kernel<CSRC, NPL, F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kLcSmemMax);
         if (e != cudaSuccess) return spiral_cuda_error(e, "cudaFuncSetAttribute(lwgrad2_kernel)");
         attr = true;
     }
-    lwgrad2_kernel<CIN, NPL, F16><<<grid, 256, smem, st>>>(p, x, dy, ws, n_items);
+    lwgrad2_kernel<CSRC, NPL, F16><<<grid, 256, smem, st>>>(p, x, dy, ws, n_items);
     return SPIRAL_OK;
 }
 
-// v2 dispatch over (Cin in {8, 16, 32}) x (operand format); FN<CIN, NPL, F16, ...>
-#define LC2_DISPATCH(FN, MTARG, ...)                                                                                  \
-    do {                                                                                                              \
-        int rc_;                                                                                                      \
-        if (n_planes == 4) {                                                                                          \
-            if (Cin == 8) rc_ = FN<8, 2, true MTARG>(__VA_ARGS__);                                                    \
-            else if (Cin == 16) rc_ = FN<16, 2, true MTARG>(__VA_ARGS__);                                             \
-            else rc_ = FN<32, 2, true MTARG>(__VA_ARGS__);                                                            \
-        } else if (n_planes == 2) {                                                                                   \
-            if (Cin == 8) rc_ = FN<8, 2, false MTARG>(__VA_ARGS__);                                                   \
-            else if (Cin == 16) rc_ = FN<16, 2, false MTARG>(__VA_ARGS__);                                            \
-            else rc_ = FN<32, 2, false MTARG>(__VA_ARGS__);                                                           \
-        } else {                                                                                                      \
-            if (Cin == 8) rc_ = FN<8, 3, false MTARG>(__VA_ARGS__);                                                   \
-            else if (Cin == 16) rc_ = FN<16, 3, false MTARG>(__VA_ARGS__);                                            \
-            else rc_ = FN<32, 3, false MTARG>(__VA_ARGS__);                                                           \
-        }                                                                                                             \
-        if (rc_ != SPIRAL_OK) return rc_;                                                                             \
-    } while (0)
-#define LC2_COMMA_1 , 1
-#define LC2_COMMA_2 , 2
+template <int CSRC, int NPL, bool F16>
+static int lconv2_launch_mt(int mt, const LConvParams &p, const float *x, const void *w, const float *bias, float *out, int grid,
+                            size_t smem, cudaStream_t st)
+{
+    return mt == 2 ? lconv2_launch<CSRC, NPL, F16, 2>(p, x, w, bias, out, grid, smem, st)
+                   : lconv2_launch<CSRC, NPL, F16, 1>(p, x, w, bias, out, grid, smem, st);
+}
 
-#define LC_DISPATCH(FN, ...)                                                                                          \
+// dispatch over the tensor's channel count x the operand format; FN<CSRC, NPL, F16>
+#define LC2_FORMAT(FN, CS, ...)                                                                                       \
+    (n_planes == 4 ? FN<CS, 2, true>(__VA_ARGS__) : n_planes == 2 ? FN<CS, 2, false>(__VA_ARGS__) : FN<CS, 3, false>(__VA_ARGS__))
+#define LC2_DISPATCH(FN, ...)                                                                                         \
     do {                                                                                                              \
         int rc_;                                                                                                      \
-        if (n_planes == 2) {                                                                                          \
-            switch (Cin) {                                                                                            \
-            case 1: rc_ = FN<1, 2>(__VA_ARGS__); break;                                                               \
-            case 2: rc_ = FN<2, 2>(__VA_ARGS__); break;                                                               \
-            case 3: rc_ = FN<3, 2>(__VA_ARGS__); break;                                                               \
-            case 6: rc_ = FN<6, 2>(__VA_ARGS__); break;                                                               \
-            case 8: rc_ = FN<8, 2>(__VA_ARGS__); break;                                                               \
-            case 16: rc_ = FN<16, 2>(__VA_ARGS__); break;                                                             \
-            default: rc_ = FN<32, 2>(__VA_ARGS__); break;                                                             \
-            }                                                                                                         \
-        } else {                                                                                                      \
-            switch (Cin) {                                                                                            \
-            case 1: rc_ = FN<1, 3>(__VA_ARGS__); break;                                                               \
-            case 2: rc_ = FN<2, 3>(__VA_ARGS__); break;                                                               \
-            case 3: rc_ = FN<3, 3>(__VA_ARGS__); break;                                                               \
-            case 6: rc_ = FN<6, 3>(__VA_ARGS__); break;                                                               \
-            case 8: rc_ = FN<8, 3>(__VA_ARGS__); break;                                                               \
-            case 16: rc_ = FN<16, 3>(__VA_ARGS__); break;                                                             \
-            default: rc_ = FN<32, 3>(__VA_ARGS__); break;                                                             \
-            }                                                                                                         \
+        switch (Cin) {                                                                                                \
+        case 1: rc_ = LC2_FORMAT(FN, 1, __VA_ARGS__); break;                                                          \
+        case 2: rc_ = LC2_FORMAT(FN, 2, __VA_ARGS__); break;                                                          \
+        case 3: rc_ = LC2_FORMAT(FN, 3, __VA_ARGS__); break;                                                          \
+        case 6: rc_ = LC2_FORMAT(FN, 6, __VA_ARGS__); break;                                                          \
+        case 8: rc_ = LC2_FORMAT(FN, 8, __VA_ARGS__); break;                                                          \
+        case 16: rc_ = LC2_FORMAT(FN, 16, __VA_ARGS__); break;                                                        \
+        default: rc_ = LC2_FORMAT(FN, 32, __VA_ARGS__); break;                                                        \
         }                                                                                                             \
         if (rc_ != SPIRAL_OK) return rc_;                                                                             \
     } while (0)
@@ -1211,41 +1084,31 @@ extern "C" int spiral_lconv_forward(const float *x, const void *w_planes, int32_
     SPIRAL_REQUIRE(x); SPIRAL_REQUIRE(w_planes); SPIRAL_REQUIRE(out);
     if (B <= 0 || Cout <= 0 || Cout > 32 || !lc_cin_ok(Cin) || KH * KW > kLcMaxTaps || !lc_prec_ok(n_planes))
         return spiral_set_error(SPIRAL_EINVAL, "lconv: unsupported shape Cin=%d Cout=%d taps=%d planes=%d", Cin, Cout, KH * KW, n_planes);
+    const int CinP = lc_cin_pad(Cin);
     LConvParams p;
-    lc_fill(p, B, Hin, Win, Cin, Hout, Wout, Cout, KH, KW, stride, pad_t, pad_l, oH, oW, o_sy, o_sx, o_oy, o_ox);
+    lc_fill(p, B, Hin, Win, CinP, Hout, Wout, Cout, KH, KW, stride, pad_t, pad_l, oH, oW, o_sy, o_sx, o_oy, o_ox);
     cudaStream_t st = (cudaStream_t)stream;
-    if (Cin % 8 == 0) {
-        const int npl = lc_prec_planes(n_planes);
-        const size_t n_w2 = (size_t)p.CoutPad * p.KS;
-        for (int mt = 2; mt >= 1; mt--) {
-            lc2_tile(p, Cin, mt);
-            const size_t smem2 = (size_t)npl * ((size_t)p.n_in + n_w2) * 2 + (size_t)(p.KP / 8) * 4;
-            if (smem2 > kLcSmemMax) {
-                if (mt == 1) return spiral_set_error(SPIRAL_EUNSUPPORTED, "lconv: tile does not fit shared memory (%zu bytes)", smem2);
-                continue;
-            }
-            const int grid2 = ((B + p.fr - 1) / p.fr) * p.tiles_x * p.tiles_y;
-            if (mt == 2) LC2_DISPATCH(lconv2_launch, LC2_COMMA_2, p, x, w_planes, bias, out, grid2, smem2, st);
-            else LC2_DISPATCH(lconv2_launch, LC2_COMMA_1, p, x, w_planes, bias, out, grid2, smem2, st);
-            break;
+    const int npl = lc_prec_planes(n_planes);
+    const size_t n_w = (size_t)p.CoutPad * p.KS;
+    for (int mt = 2; mt >= 1; mt--) {
+        lc2_tile(p, CinP, mt);
+        const size_t smem = (size_t)npl * ((size_t)p.n_in + n_w) * 2 + (size_t)(p.KP / 8) * 4;
+        if (smem > kLcSmemMax) {
+            if (mt == 1) return spiral_set_error(SPIRAL_EUNSUPPORTED, "lconv: tile does not fit shared memory (%zu bytes)", smem);
+            continue;
         }
-        const cudaError_t e2 = cudaGetLastError();
-        return e2 == cudaSuccess ? SPIRAL_OK : spiral_cuda_error(e2, "spiral_lconv_forward");
+        const int grid = ((B + p.fr - 1) / p.fr) * p.tiles_x * p.tiles_y;
+        LC2_DISPATCH(lconv2_launch_mt, mt, p, x, w_planes, bias, out, grid, smem, st);
+        break;
     }
-    if (n_planes == 4) return spiral_set_error(SPIRAL_EUNSUPPORTED, "lconv: the f16x3 format needs Cin %% 8 == 0 (Cin=%d)", Cin);
-    const size_t n_w = (size_t)p.CoutPad * p.KS, n_in8 = ((size_t)p.IH * p.IW * Cin + 7) & ~(size_t)7;
-    const size_t smem = (size_t)n_planes * (n_w + n_in8) * 2 + (size_t)p.KP * 4;
-    if (smem > kLcSmemMax - 2048) return spiral_set_error(SPIRAL_EUNSUPPORTED, "lconv: tile does not fit shared memory (%zu bytes)", smem);
-    const int grid = B * p.tiles_x * p.tiles_y;
-    LC_DISPATCH(lconv_launch, p, x, w_planes, bias, out, grid, smem, st);
     const cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? SPIRAL_OK : spiral_cuda_error(e, "spiral_lconv_forward");
 }
 
 // A narrow layer of the discriminator (disc_dim 8 / 16: Cin <= 16, Cout <= 32; 5x5 / stride 2 / 'SAME' = pad 1 before, 2 after)
-// on this kernel instead of the fp32 SIMT tile (64 x 64 outputs per CTA: at Cout = 16, Cin = 8 seven eighths of its FMAs are
-// padding): kernel HWIO fp32 -> three bf16 planes (bf16x6, fp32-exact operands), the producer's BN + leaky-ReLU applied while
-// the input tile is staged, + bias, raw fp32 output, per-CTA batch-norm partials.  Returns the number of partial rows.
+// on the first-generation kernel instead of the fp32 SIMT tile (64 x 64 outputs per CTA: at Cout = 16, Cin = 8 seven eighths of
+// its FMAs are padding): kernel HWIO fp32 -> three bf16 planes (bf16x6, fp32-exact operands), the producer's BN + leaky-ReLU
+// applied while the input tile is staged, + bias, raw fp32 output, per-CTA batch-norm partials.  Returns the number of partial rows.
 namespace spiral {
 bool lconv_disc_layer_supported(int Cin, int Cout) { return (Cin == 8 || Cin == 16) && Cout <= 32 && Cout % 2 == 0; }
 size_t lconv_disc_pack_bytes(int Cin, int Cout)
@@ -1278,8 +1141,9 @@ int lconv_disc_layer(const float *in, const float *in_scale, const float *in_shi
 
 extern "C" int64_t spiral_lconv_wgrad_workspace_floats(int32_t Cin, int32_t Cout, int32_t n_taps)
 {
-    const int K = n_taps * Cin, KP = (K + 15) & ~15, CoutPad = (Cout + 7) & ~7;
-    return (int64_t)(148 * 2) * KP * CoutPad;
+    const int K = n_taps * lc_cin_pad(Cin), KP = (K + 15) & ~15, CoutPad = (Cout + 7) & ~7;
+    const int64_t mma = (int64_t)148 * KP * CoutPad, scalar = (int64_t)148 * 4 * K;
+    return mma > scalar ? mma : scalar;
 }
 
 extern "C" int spiral_lconv_wgrad(const float *x, const float *dy, float *dw, float *workspace, int32_t n_planes, int32_t B,
@@ -1287,42 +1151,31 @@ extern "C" int spiral_lconv_wgrad(const float *x, const float *dy, float *dw, fl
                                   int32_t KW, int32_t stride, int32_t pad_t, int32_t pad_l, void *stream)
 {
     SPIRAL_REQUIRE(x); SPIRAL_REQUIRE(dy); SPIRAL_REQUIRE(dw); SPIRAL_REQUIRE(workspace);
-    if (B <= 0 || Cout <= 0 || Cout > 32 || !lc_cin_ok(Cin) || KH * KW > kLcMaxTaps || KH * KW * Cin > 8 * kLwMaxMt * 16 ||
-        !lc_prec_ok(n_planes))
+    const int CinP = lc_cin_pad(Cin);
+    if (B <= 0 || !(Cout == 1 || Cout == 8 || Cout == 16 || Cout == 32) || !lc_cin_ok(Cin) || KH * KW > kLcMaxTaps ||
+        KH * KW * CinP > 8 * kLwMaxMt * 16 || !lc_prec_ok(n_planes))
         return spiral_set_error(SPIRAL_EINVAL, "lconv_wgrad: unsupported shape Cin=%d Cout=%d taps=%d planes=%d", Cin, Cout, KH * KW, n_planes);
     LConvParams p;
-    lc_fill(p, B, Hin, Win, Cin, Hout, Wout, Cout, KH, KW, stride, pad_t, pad_l, Hout, Wout, 1, 1, 0, 0);
+    lc_fill(p, B, Hin, Win, CinP, Hout, Wout, Cout, KH, KW, stride, pad_t, pad_l, Hout, Wout, 1, 1, 0, 0);
     cudaStream_t st = (cudaStream_t)stream;
-    if (Cin % 8 == 0 && (Cout == 8 || Cout == 16 || Cout == 32)) {
-        const int npl = lc_prec_planes(n_planes);
-        lc2_tile(p, Cin, 1);
-        const size_t smem2 = (size_t)npl * ((size_t)p.n_in + (size_t)kLwPix * p.CoutPad) * 2 + (size_t)(p.KP / 8) * 4;
-        if (smem2 > kLcSmemMax) return spiral_set_error(SPIRAL_EUNSUPPORTED, "lconv_wgrad: tile does not fit shared memory (%zu bytes)", smem2);
-        const int n_items2 = ((B + p.fr - 1) / p.fr) * p.tiles_x * p.tiles_y;
-        const int grid2 = n_items2 < 148 ? n_items2 : 148;
-        LC2_DISPATCH(lwgrad2_launch, , p, x, dy, workspace, n_items2, grid2, smem2, st);
-        const int n2 = p.K * Cout;
-        lwgrad_reduce_kernel<<<(n2 + 255) / 256, 256, 0, st>>>(workspace, dw, grid2, p.K, p.KP, Cout, p.CoutPad);
-        const cudaError_t e2 = cudaGetLastError();
-        return e2 == cudaSuccess ? SPIRAL_OK : spiral_cuda_error(e2, "spiral_lconv_wgrad");
+    if (Cout == 1 && Cin == 32 && KH == 3 && KW == 3 && stride == 1) {
+        // scalar output map: fp32 correlation (lwgrad_scalar_kernel); partial[cta][288] fits the workspace of the MMA path
+        const int rows = B * Hin;
+        const int grid = rows < 148 * 4 * 8 ? (rows + 7) / 8 : 148 * 4;
+        lwgrad_scalar_kernel<3, 3><<<grid, 256, 0, st>>>(x, dy, workspace, B, Hin, Win, Hout, Wout, pad_t, pad_l);
+        lwgrad_scalar_reduce_kernel<<<(288 + 255) / 256, 256, 0, st>>>(workspace, dw, grid, 288);
+        const cudaError_t e1 = cudaGetLastError();
+        return e1 == cudaSuccess ? SPIRAL_OK : spiral_cuda_error(e1, "spiral_lconv_wgrad");
     }
-    // shapes outside the v2 kernels: f16x3 -> bf16x6 (LC_DISPATCH takes every format but bf16x3 as three planes)
-    const int n_planes_old = n_planes == 2 ? 2 : 3;
-    const size_t n_in8 = ((size_t)p.IH * p.IW * Cin + 7) & ~(size_t)7;
-    const size_t smem = (size_t)n_planes_old * (n_in8 + (size_t)p.CoutPad * kLwPS) * 2 + (size_t)p.KP * 4;
+    const int npl = lc_prec_planes(n_planes);
+    lc2_tile(p, CinP, 1);
+    const size_t smem = (size_t)npl * ((size_t)p.n_in + (size_t)kLwPix * p.CoutPad) * 2 + (size_t)(p.KP / 8) * 4;
     if (smem > kLcSmemMax) return spiral_set_error(SPIRAL_EUNSUPPORTED, "lconv_wgrad: tile does not fit shared memory (%zu bytes)", smem);
-    const int n_items = B * p.tiles_x * p.tiles_y;
-    const int grid = n_items < 148 * 2 ? n_items : 148 * 2;
-    if (Cout == 1 && Cin == 32) {
-        // scalar output map: fp32 SIMT correlation (lwgrad1_kernel)
-        const size_t smem1 = ((size_t)p.IH * p.IW * Cin + kLcTw * kLcTh) * sizeof(float);
-        const size_t red = (size_t)(256 / Cin) * KH * KW * Cin * sizeof(float);
-        lwgrad1_kernel<32><<<grid, 256, smem1 > red ? smem1 : red, st>>>(p, x, dy, workspace, n_items);
-    } else {
-        LC_DISPATCH(lwgrad_launch, p, x, dy, workspace, n_items, grid, smem, st);
-    }
-    const int n = p.K * Cout;
-    lwgrad_reduce_kernel<<<(n + 255) / 256, 256, 0, st>>>(workspace, dw, grid, p.K, p.KP, Cout, p.CoutPad);
+    const int n_items = ((B + p.fr - 1) / p.fr) * p.tiles_x * p.tiles_y;
+    const int grid = n_items < 148 ? n_items : 148;
+    LC2_DISPATCH(lwgrad2_launch, p, x, dy, workspace, n_items, grid, smem, st);
+    const int n = KH * KW * Cin * Cout;
+    lwgrad_reduce_kernel<<<(n + 255) / 256, 256, 0, st>>>(workspace, dw, grid, KH * KW * Cin, p.KP, Cout, p.CoutPad, Cin, CinP);
     const cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? SPIRAL_OK : spiral_cuda_error(e, "spiral_lconv_wgrad");
 }

@@ -34,8 +34,7 @@ FORMATS = {"f16x3": 4, "bf16x6": 3, "bf16x3": 2}
 
 
 def _fmt(cin):
-    """f16x3 exists for channel counts that are multiples of 8 (the v2 kernels); other shapes take bf16x6."""
-    return 3 if (PLANES == 4 and cin % 8) else PLANES
+    return PLANES
 
 
 def _workspace(dev, n):

@@ -183,54 +183,97 @@ def _rel(a, b):
 CASES = [("simple_mnist", 32, 1, 2, False, 3), ("color_mnist", 64, 3, 2, False, 2), ("simple_mnist", 32, 1, 2, True, 2)]
 
 
-def _check_learner(envname, L, C, T, conditional, B, seeds=(5, 6, 7)):
-    """Logits, value and every parameter gradient against the module in float64.  A ReLU pre-activation within rounding of
-    zero passes the gradient in one arithmetic and blocks it in another -- one such unit moves whole gradient tensors by
-    percents, for PyTorch's own fp32 path exactly as for the kernels, and which unit it hits depends on the last bit.  The
-    forward bars hold for every input; the gradient bars must hold on at least one of a few seeded inputs (a wrong kernel
-    fails all of them; test_learner_gradients_on_a_smooth_network has no kinks and no such escape)."""
+class _PinnedRelu:
+    """F.relu with the activation pattern of a recorded run.  A ReLU pre-activation within rounding of zero passes the
+    gradient in one arithmetic and blocks it in another; one such unit moves whole gradient tensors by 1e-3 .. 5e-2 -- for
+    PyTorch's own fp32 path against float64 exactly as for the kernels -- and on 64 x 64 maps (a million units) about one
+    unit per run sits that close.  Recording the masks in the float64 run and replaying them in the fp32 runs evaluates the
+    same linear branch of the network everywhere, so what is compared is arithmetic.  (The forward value changes by the
+    pre-activation of the flipped unit, ~1e-7.)  The module's 4-D tensors are NCHW, the kernels' NHWC."""
+
+    def __init__(self):
+        self.masks, self.i, self.record, self.nhwc = [], 0, True, False
+
+    def replay(self, nhwc):
+        self.i, self.record, self.nhwc = 0, False, nhwc
+
+    def __call__(self, x, inplace=False):
+        if self.record:
+            m = x > 0
+            self.masks.append(m)
+        else:
+            m = self.masks[self.i]
+            self.i += 1
+            if m.dim() == 4 and self.nhwc:
+                m = m.permute(0, 2, 3, 1)
+            assert m.shape == x.shape, (self.i, tuple(m.shape), tuple(x.shape))
+        return x * m.to(x.dtype)
+
+
+def _check_learner(monkeypatch, envname, L, C, T, conditional, B, smooth=False):
     import copy
-    failures = []
-    for seed in seeds:
-        pi, inp, _ = _learner_case(envname, L, C, T, conditional, B, seed)
-        ref = _run_learner(copy.deepcopy(pi).double(), inp, False, torch.float64)       # the module in float64: ground truth
-        t32 = _run_learner(pi, inp, False)                                              # PyTorch fp32 (cuDNN / cuBLAS, TF32 off)
-        got = _run_learner(pi, inp, True)                                               # csrc/policy_learn.cu
-        assert set(got[2]) == set(ref[2]) and len(ref[2]) > 60
-        for n in pi.acs:
-            assert _rel(got[0][n], ref[0][n]) < 1e-4, n
-            assert _rel(got[0][n], t32[0][n]) < 1e-4, n
-        assert _rel(got[1], ref[1]) < 1e-4 and _rel(got[1], t32[1]) < 1e-4
-        # every gradient tensor agrees with the float64 truth -- or, where fp32 rounding puts a ReLU pre-activation on the
-        # other side of zero than float64 does (PyTorch's fp32 path then deviates by the same amount), with the fp32 module
-        worst = max((min(_rel(got[2][k], ref[2][k]), _rel(got[2][k], t32[2][k])), k) for k in ref[2])
-        w64 = max((_rel(got[2][k], ref[2][k]), k) for k in ref[2])
-        w32 = max((_rel(t32[2][k], ref[2][k]), k) for k in ref[2])
-        print("seed %d: worst parameter-gradient error vs float64: native %.2e (%s), PyTorch fp32 %.2e (%s)" % ((seed,) + w64 + w32))
-        if worst[0] < 1e-4 and w64[0] < 4 * max(w32[0], 1e-5):      # as good as the fp32 module itself, give or take
-            return
-        failures.append((seed, worst, w64, w32))
-    raise AssertionError("gradients off on every seed: %r" % (failures,))
+    pi, inp, _ = _learner_case(envname, L, C, T, conditional, B)
+    if smooth:
+        # ReLUs replaced by softplus: no kinks, nothing pinned
+        monkeypatch.setattr(torch.nn.functional, "relu", lambda x, inplace=False: torch.nn.functional.softplus(x))
+    # forward: logits and value of the plain network (no pinning: the forward has no kink problem)
+    with torch.no_grad():
+        f64 = _forward_only(copy.deepcopy(pi).double(), inp, False, torch.float64)
+        f32 = _forward_only(pi, inp, False)
+        fnat = _forward_only(pi, inp, True)
+    for n in pi.acs:
+        assert _rel(fnat[0][n], f64[0][n]) < 1e-4 and _rel(fnat[0][n], f32[0][n]) < 1e-4, n
+    assert _rel(fnat[1], f64[1]) < 1e-4 and _rel(fnat[1], f32[1]) < 1e-4
+    # gradients, with the activation pattern pinned to the float64 run's
+    pinned = _PinnedRelu()
+    if not smooth:
+        monkeypatch.setattr(torch.nn.functional, "relu", pinned)
+    ref = _run_learner(copy.deepcopy(pi).double(), inp, False, torch.float64)       # the module in float64: ground truth
+    n_relu = len(pinned.masks)
+    pinned.replay(nhwc=False)
+    t32 = _run_learner(pi, inp, False)                                              # PyTorch fp32 (cuDNN / cuBLAS, TF32 off)
+    assert pinned.i == n_relu
+    pinned.replay(nhwc=True)
+    got = _run_learner(pi, inp, True)                                               # csrc/policy_learn.cu
+    assert pinned.i == n_relu and (smooth or n_relu > 40)
+    assert set(got[2]) == set(ref[2]) and len(ref[2]) > 60
+    for n in pi.acs:
+        assert _rel(got[0][n], ref[0][n]) < 1e-4, n
+    w64 = max((_rel(got[2][k], ref[2][k]), k) for k in ref[2])
+    w32 = max((_rel(t32[2][k], ref[2][k]), k) for k in ref[2])
+    print("worst parameter-gradient error vs float64: native %.2e (%s), PyTorch fp32 %.2e (%s)" % (w64 + w32))
+    # EVERY gradient tensor within 1e-4 of float64 -- or, for the few small ill-conditioned ones (the action encoder's
+    # first layers, at the far end of the backward pass) where PyTorch's fp32 path itself is at 0.5e-4 .. 1e-4, within 3x of
+    # what that path achieves on the same tensor; and never past 3e-4
+    for k in ref[2]:
+        e64, e32 = _rel(got[2][k], ref[2][k]), _rel(t32[2][k], ref[2][k])
+        assert e64 < max(1e-4, min(3 * e32, 3e-4)), (k, e64, e32)
+    assert w64[0] < 4 * max(w32[0], 1e-5)                     # and as good as the fp32 module itself, give or take
+
+
+def _forward_only(pi, inp, native, dtype=torch.float32):
+    x, ac, st, cond, z, samples = inp
+    f = lambda t_: None if t_ is None else t_.to(dtype)
+    pi.learn_native = native
+    logits, _, vf, _ = pi(f(x), f(ac), (f(st[0]), f(st[1])), f(cond), f(z), samples)
+    return {n: logits[n].double() for n in pi.acs}, vf.double()
 
 
 @pytest.mark.parametrize("envname,L,C,T,conditional,B", CASES)
-def test_learner_forward_and_gradients_match_the_module(envname, L, C, T, conditional, B, strict_fp32):
+def test_learner_forward_and_gradients_match_the_module(monkeypatch, envname, L, C, T, conditional, B, strict_fp32):
     """Policy(learn_native=True): every convolution of the trunk and the location heads, and its input and weight
-    gradients, on csrc/policy_learn.cu (bf16x6, two accumulators) against the same module evaluated in float64: logits of
-    every head, the value and EVERY parameter gradient of a loss that touches all heads within 1e-4 (relative to the
-    largest entry of each tensor) -- and within a small factor of what PyTorch's own fp32 path (cuDNN / cuBLAS, TF32 off)
-    achieves against float64; logits and value also within 1e-4 of that fp32 path directly.  (The network is full of ReLU
-    kinks: a pre-activation within rounding of zero passes the gradient in float64 and blocks it in fp32, or the reverse,
-    which moves a whole gradient tensor by percents -- for PyTorch's fp32 path exactly as for this one; such a tensor must
-    then agree with the fp32 module instead.)"""
-    _check_learner(envname, L, C, T, conditional, B)
+    gradients, on csrc/policy_learn.cu (default operand format f16x3) against the same module evaluated in float64:
+    logits of every head and the value within 1e-4 of float64 AND of PyTorch's fp32 path (cuDNN / cuBLAS, TF32 off); EVERY
+    parameter gradient of a loss that touches all heads within 1e-4 (relative to the largest entry of each tensor) of
+    float64 with the ReLU activation pattern pinned to the float64 run's (_PinnedRelu says why), and within a small factor
+    of what PyTorch's fp32 path achieves under the same pinning."""
+    _check_learner(monkeypatch, envname, L, C, T, conditional, B)
 
 
 def test_learner_gradients_on_a_smooth_network(monkeypatch, strict_fp32):
     """The same comparison with the ReLUs replaced by softplus (no kinks for rounding to flip): every forward, input-
     gradient and weight-gradient kernel in its place in the graph."""
-    monkeypatch.setattr(torch.nn.functional, "relu", lambda x, inplace=False: torch.nn.functional.softplus(x))
-    _check_learner("color_mnist", 64, 3, 2, False, 2)
+    _check_learner(monkeypatch, "color_mnist", 64, 3, 2, False, 2, smooth=True)
 
 
 def test_learner_convolution_primitives_match_torch(strict_fp32):
@@ -262,13 +305,11 @@ def test_learner_convolution_primitives_match_torch(strict_fp32):
         for a, b, name in zip(outs[1], outs[0], ("y", "dx", "dw", "db")):
             assert a.shape == b.shape, (kind, name)
             err = float((a - b).abs().max() / b.abs().max())
-            assert err < 5e-5, (kind, cin, cout, k, stride, H, W, name, err)
+            assert err < (5e-5 if pl.PLANES != 2 else 2e-4), (kind, cin, cout, k, stride, H, W, name, err)
 
-    for cin in (1, 3, 6):
-        check("conv", cin, 32, 5, 1, 2, 64, 64, B=2)
     saved = pl.PLANES
     try:
-        for fmt in ("f16x3", "bf16x6"):                       # the v2 kernels (channel counts that are multiples of 8) in both formats
+        for fmt in ("f16x3", "bf16x6", "bf16x3"):
             pl.PLANES = pl.FORMATS[fmt]
             _v2_shapes(check)
     finally:
@@ -276,6 +317,9 @@ def test_learner_convolution_primitives_match_torch(strict_fp32):
 
 
 def _v2_shapes(check):
+    for cin in (1, 2, 3, 6):                                  # image channels: padded to one 8-channel chunk while staged
+        check("conv", cin, 32, 5, 1, 2, 64, 64, B=2)
+    check("conv", 1, 32, 3, 1, 1, 33, 20, B=3)
     check("conv", 32, 32, 4, 2, 0, 64, 64, B=2)
     check("conv", 32, 32, 4, 2, 0, 31, 31)
     check("conv", 32, 32, 4, 2, 0, 14, 14)
