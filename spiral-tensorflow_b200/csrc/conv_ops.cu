@@ -271,6 +271,7 @@ extern "C" int64_t spiral_conv_workspace_bytes(int32_t B, int32_t H, int32_t Cin
     if (precision != 0) {
         const size_t t = conv_tc_workspace_bytes(B, H, Cin, Cout);
         if (t > n) n = t;
+        if (lwgrad2_image_layer_supported(Cin, Cout) && lwgrad2_image_layer_workspace_bytes() > n) n = lwgrad2_image_layer_workspace_bytes();
     }
     return (int64_t)n;
 }
@@ -317,7 +318,11 @@ extern "C" int spiral_conv_wgrad(const float *x, const float *dy, float *dw, int
     int rc = check_shape(B, H, Cin, Cout, precision);
     if (rc != SPIRAL_OK) return rc;
     cudaStream_t st = (cudaStream_t)stream;
-    if (precision != 0 && conv_tc_supported(2, B, H, Cin, Cout)) {
+    if (precision != 0 && lwgrad2_image_layer_supported(Cin, Cout)) {
+        // the image layer: policy_learn.cu's mma.sync wgrad over 32-channel slices of dy (bf16x6 unless the caller asked for less)
+        rc = lwgrad2_image_layer(x, dy, dw, (float *)ws, precision_planes(precision) == 3 ? 3 : 2, B, H, Cin, Cout, st);
+        if (rc != SPIRAL_OK) return rc;
+    } else if (precision != 0 && conv_tc_supported(2, B, H, Cin, Cout)) {
         rc = conv_tc_wgrad(x, dy, dw, B, H, Cin, Cout, precision_planes(precision), (char *)ws, st);
         if (rc != SPIRAL_OK) return rc;
     } else {

@@ -16,4 +16,10 @@ int conv_tc_dgrad(const float *dy, const float *w, float *dx, int B, int H, int 
 int conv_tc_wgrad(const float *x, const float *dy, float *dw, int B, int H, int Cin, int Cout, int ns, char *ws,
                   cudaStream_t st);
 
+// policy_learn.cu: kernel gradient of the image layer (Cin 1 / 2 / 3 / 6) on the mma.sync wgrad kernel; n_planes 2 = bf16x3, 3 = bf16x6
+bool lwgrad2_image_layer_supported(int Cin, int Cout);
+size_t lwgrad2_image_layer_workspace_bytes();
+int lwgrad2_image_layer(const float *x, const float *dy, float *dw, float *workspace, int n_planes, int B, int H, int Cin, int Cout,
+                        cudaStream_t st);
+
 }  // namespace spiral

@@ -51,6 +51,7 @@ constexpr int kThreadsG = 192;
 constexpr uint32_t kATile = kM * kK * 2;                         // 16 KB
 
 constexpr int kMaxSplit = 3;
+constexpr int kMaxTapSlices = 5;   // taps_tc_kernel: CTAs sharing one tile's taps at small batch
 // The tensor core adds each MMA into the fp32 TMEM accumulator with truncation, so the accumulation error grows
 // with the number of MMAs chained into one accumulator (measured: bf16x6 through ONE accumulator is less accurate
 // than bf16x3).  Four accumulators per tile: the dominant p0*p0 products alternate between 0 and 1 (halving their
@@ -195,6 +196,8 @@ struct TapsParams {
     int bw, bh, bb;           // A box: pixels, rows, images (bw*bh*bb == 128) on the Ho = H/2 grid
     int M;                    // B * Ho * Ho tile rows (per parity class for dgrad)
     int ns;
+    int n_slices;             // the tile's taps are split over n_slices CTAs (gridDim.z = classes * n_slices), each writing its
+    size_t slice_stride;      // own fp32 copy of the output, slice_stride floats apart (reduced afterwards in a fixed order)
 };
 
 template <int BN>
@@ -205,8 +208,11 @@ taps_tc_kernel(const __grid_constant__ MapSet maps, const __grid_constant__ Taps
     const Pipe pp = pipe_setup<BN>(smem_raw, p.ns);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m_tile = blockIdx.x, n_tile = blockIdx.y;
-    const int py = blockIdx.z >> 1, px = blockIdx.z & 1;       // dgrad parity class (0 for forward)
+    const int n_classes = p.mode == 0 ? 1 : 4;
+    const int cls = blockIdx.z % n_classes, slice = blockIdx.z / n_classes;
+    const int py = cls >> 1, px = cls & 1;                      // dgrad parity class (0 for forward)
     const int Ho = p.H / 2;
+    out += (size_t)slice * p.slice_stride;
     const int m0 = m_tile * kM;
     const int img0 = m0 / (Ho * Ho);
     const int r0 = (m0 % (Ho * Ho)) / Ho;                       // first tile row on the Ho grid
@@ -233,14 +239,18 @@ taps_tc_kernel(const __grid_constant__ MapSet maps, const __grid_constant__ Taps
     }
     const int kdim = p.mode == 0 ? p.Cin : p.Cout;              // channels reduced per tap
     const int chunks = kdim / kK;
-    const int n_iter = n_taps * chunks;
+    // this CTA's share of the taps (deep layers at small batch have a handful of tiles: without the split 16 - 32 CTAs stream
+    // the whole 25 * Cin reduction while the other SMs idle)
+    const int per = (n_taps + p.n_slices - 1) / p.n_slices;
+    const int t_begin = min(n_taps, slice * per), t_end = min(n_taps, t_begin + per);
+    const int n_iter = (t_end - t_begin) * chunks;
 
     if (warp == 0) {
         if (lane == 0) {
             tma_prefetch_desc(&maps.a[0]);
             tma_prefetch_desc(&maps.w[0]);
             int it = 0;
-            for (int t = 0; t < n_taps; t++) {
+            for (int t = t_begin; t < t_end; t++) {
                 const int ky = taps[t] / 5, kx = taps[t] % 5;
                 int cx, cy;
                 if (p.mode == 0) { cx = kx - 1; cy = 2 * r0 + ky - 1; }
@@ -511,8 +521,8 @@ size_t conv_tc_workspace_bytes(int B, int H, int Cin, int Cout)
     const size_t Ppad = (size_t)padded_pixels(B, H);
     const size_t nx = (size_t)B * H * H * Cin, ny = (size_t)B * (H / 2) * (H / 2) * Cout, nw = (size_t)25 * Cin * Cout;
     // forward: x planes + packed w planes;  dgrad: dy planes + w planes
-    const size_t fwd = al(ns * nx * 2) + al(ns * nw * 2);
-    const size_t dg = al(ns * ny * 2) + al(ns * nw * 2);
+    const size_t fwd = al(ns * nx * 2) + al(ns * nw * 2) + al((size_t)kMaxTapSlices * ny * 4);
+    const size_t dg = al(ns * ny * 2) + al(ns * nw * 2) + al((size_t)kMaxTapSlices * nx * 4);
     // wgrad: x^T per tap planes, dy^T planes, slice partials
     const int BN = (Cout % 128) == 0 ? 128 : 64;
     int list[25], nv;
@@ -550,9 +560,17 @@ static void launch_split(const float *x, void *dst, size_t n, int ns, cudaStream
 }
 
 // mode 0 forward / mode 1 dgrad through taps_tc_kernel; act = the activation-side operand planes
+static int taps_slices(int mode, long long ctas)
+{
+    if (ctas >= 74) return 1;
+    int s = (int)((148 + ctas - 1) / ctas);
+    const int cap = mode == 0 ? kMaxTapSlices : 3;             // a dgrad parity class has 4 .. 9 taps
+    return s > cap ? cap : s;
+}
+
 template <int BN>
 static int taps_launch(int mode, char *act, size_t act_plane, char *wp, size_t w_plane, float *out, int B, int H, int Cin,
-                       int Cout, int ns, cudaStream_t st)
+                       int Cout, int ns, cudaStream_t st, float *part)
 {
     static uint32_t attr = 0;
     int rc = set_smem(taps_tc_kernel<BN>, Cfg<BN>::smem_bytes(ns), &attr);
@@ -596,8 +614,14 @@ static int taps_launch(int mode, char *act, size_t act_plane, char *wp, size_t w
     for (int q = ns; q < kMaxSplit; q++) { maps.a[q] = maps.a[0]; maps.w[q] = maps.w[0]; }
     if (er) return spiral_set_error(SPIRAL_ECUDA, "cuTensorMapEncodeTiled failed (mode %d, CUresult %d)", mode, er);
     const int ncols = mode == 0 ? Cout : Cin;
-    dim3 grid((p.M + kM - 1) / kM, (ncols + BN - 1) / BN, mode == 0 ? 1 : 4);
-    taps_tc_kernel<BN><<<grid, kThreadsG, Cfg<BN>::smem_bytes(ns), st>>>(maps, p, out);
+    const int n_classes = mode == 0 ? 1 : 4;
+    dim3 grid((p.M + kM - 1) / kM, (ncols + BN - 1) / BN, n_classes);
+    const size_t n_out = mode == 0 ? (size_t)p.M * Cout : (size_t)B * H * H * Cin;
+    p.n_slices = taps_slices(mode, (long long)grid.x * grid.y * grid.z);
+    p.slice_stride = p.n_slices > 1 ? n_out : 0;
+    grid.z = n_classes * p.n_slices;
+    taps_tc_kernel<BN><<<grid, kThreadsG, Cfg<BN>::smem_bytes(ns), st>>>(maps, p, p.n_slices > 1 ? part : out);
+    if (p.n_slices > 1) reduce_slices_kernel<<<148 * 2, 256, 0, st>>>(part, out, n_out, p.n_slices);
     return SPIRAL_OK;
 }
 
@@ -613,7 +637,8 @@ int conv_tc_forward(const float *x, const float *w, float *y, int B, int H, int 
         return conv_tc_layer(xp, xp + nx * 2, wp, wp + nw * 2, y, B, H, Cin, Cout, ns == 2 ? 1 : 0, st);
     }
     pack_kmajor_kernel<<<148 * 4, 256, 0, st>>>(w, (__nv_bfloat16 *)wp, Cin, Cout, nw, ns);
-    return taps_launch<128>(0, xp, nx * 2, wp, nw * 2, y, B, H, Cin, Cout, ns, st);
+    float *part = reinterpret_cast<float *>(wp + al((size_t)kMaxSplit * nw * 2));
+    return taps_launch<128>(0, xp, nx * 2, wp, nw * 2, y, B, H, Cin, Cout, ns, st, part);
 }
 
 int conv_tc_dgrad(const float *dy, const float *w, float *dx, int B, int H, int Cin, int Cout, int ns, char *ws,
@@ -623,8 +648,9 @@ int conv_tc_dgrad(const float *dy, const float *w, float *dx, int B, int H, int 
     char *dyp = ws, *wp = ws + al((size_t)kMaxSplit * ny * 2);
     launch_split(dy, dyp, ny, ns, st);
     launch_split(w, wp, nw, ns, st);                       // HWIO: [tap][ci][co] is already K-major per tap
-    if (Cin >= 128) return taps_launch<128>(1, dyp, ny * 2, wp, nw * 2, dx, B, H, Cin, Cout, ns, st);
-    return taps_launch<64>(1, dyp, ny * 2, wp, nw * 2, dx, B, H, Cin, Cout, ns, st);
+    float *part = reinterpret_cast<float *>(wp + al((size_t)kMaxSplit * nw * 2));
+    if (Cin >= 128) return taps_launch<128>(1, dyp, ny * 2, wp, nw * 2, dx, B, H, Cin, Cout, ns, st, part);
+    return taps_launch<64>(1, dyp, ny * 2, wp, nw * 2, dx, B, H, Cin, Cout, ns, st, part);
 }
 
 template <int BN>

@@ -44,6 +44,7 @@ struct LConvParams {
     int tw, th, fr, mt_rows;                     // tw = 16 or 8; mt_rows = 16 / tw rows per 16-pixel m-tile; th a power of two
     int th_log;
     int n_in;                                    // halfwords per plane of the staged input tile (multiple of 64)
+    int dy_pitch, dy_c0;                         // wgrad: dy is [.., dy_pitch] channels per pixel, this launch takes [dy_c0, dy_c0 + Cout)
 };
 
 __device__ __forceinline__ void lc_mma(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2])
@@ -458,7 +459,7 @@ constexpr int kLwPix = kLcTw * kLcTh;            // 128 reduction elements per i
 // (cin < cin_pad: the partials' k index is tap * cin_pad + c, dw's is tap * cin + c)
 __global__ void __launch_bounds__(256)
 lwgrad_reduce_kernel(const float *__restrict__ partial, float *__restrict__ dw, int n_cta, int K, int KP, int Cout, int CoutPad,
-                     int cin = 1, int cin_pad = 1)
+                     int cin = 1, int cin_pad = 1, int ld = 0, int co0 = 0)    // dw[k][ld] columns [co0, co0 + Cout); ld 0: Cout
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= K * Cout) return;
@@ -466,7 +467,7 @@ lwgrad_reduce_kernel(const float *__restrict__ partial, float *__restrict__ dw, 
     const int kp = (k / cin) * cin_pad + k % cin;
     float s = 0.0f;
     for (int c = 0; c < n_cta; c++) s += partial[((size_t)c * KP + kp) * CoutPad + co];
-    dw[i] = s;
+    dw[(size_t)k * (ld ? ld : Cout) + co0 + co] = s;
 }
 
 
@@ -494,7 +495,8 @@ __device__ __forceinline__ int lc_swz(int L) { return (L & ~7) | ((L ^ (L >> 3))
 // zeros to one 16-byte chunk, so these layers run on the same kernels (the padded k rows meet zero kernel columns).
 template <int CSRC, int C, int NPL, bool F16>
 __device__ __forceinline__ void lc2_stage(const float *__restrict__ src, size_t frame_elems, int frames_left, int H, int W,
-                                          int RH, int RW, int y0, int x0, int fr, uint16_t *s, int n_plane, int warp, int lane)
+                                          int RH, int RW, int y0, int x0, int fr, uint16_t *s, int n_plane, int warp, int lane,
+                                          int pitch = CSRC)                    // floats per pixel of the source (>= CSRC: a channel slice)
 {
     static_assert(CSRC == C || C == 8, "channel padding goes to one chunk");
     const int rows = fr * RH;
@@ -507,8 +509,7 @@ __device__ __forceinline__ void lc2_stage(const float *__restrict__ src, size_t 
             const int iy = y0 + ly;
             const bool row_ok = f < frames_left && iy >= 0 && iy < H;
             // only dereferenced for pixels inside the map
-            const float4 *rowp = reinterpret_cast<const float4 *>(src + (ptrdiff_t)f * (ptrdiff_t)frame_elems +
-                                                                  ((ptrdiff_t)iy * W + x0) * C);
+            const float *rowp = src + (ptrdiff_t)f * (ptrdiff_t)frame_elems + ((ptrdiff_t)iy * W + x0) * pitch;
             const int e_row = gr * RW * C;
             for (int i0 = lane; i0 < rowlen; i0 += 32 * U) {
                 float4 val[U];
@@ -517,8 +518,9 @@ __device__ __forceinline__ void lc2_stage(const float *__restrict__ src, size_t 
                     const int i = i0 + 32 * u;
                     val[u] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
                     if (i < rowlen && row_ok) {
-                        const int ix = x0 + i / V;
-                        if (ix >= 0 && ix < W) val[u] = __ldg(rowp + i);
+                        const int lx = i / V;
+                        const int ix = x0 + lx;
+                        if (ix >= 0 && ix < W) val[u] = __ldg(reinterpret_cast<const float4 *>(rowp + (ptrdiff_t)lx * pitch) + (i - lx * V));
                     }
                 }
 #pragma unroll
@@ -544,7 +546,7 @@ __device__ __forceinline__ void lc2_stage(const float *__restrict__ src, size_t 
             const int f = gr / RH, ly = gr - f * RH;
             const int iy = y0 + ly;
             const bool row_ok = f < frames_left && iy >= 0 && iy < H;
-            const float *rowp = src + (ptrdiff_t)f * (ptrdiff_t)frame_elems + ((ptrdiff_t)iy * W + x0) * CSRC;
+            const float *rowp = src + (ptrdiff_t)f * (ptrdiff_t)frame_elems + ((ptrdiff_t)iy * W + x0) * pitch;
             for (int i0 = lane; i0 < RW; i0 += 32 * U) {
                 float val[U][8];
 #pragma unroll
@@ -553,7 +555,7 @@ __device__ __forceinline__ void lc2_stage(const float *__restrict__ src, size_t 
                     const int ix = x0 + i;
                     const bool ok = i < RW && row_ok && ix >= 0 && ix < W;
 #pragma unroll
-                    for (int c = 0; c < 8; c++) val[u][c] = (c < CSRC && ok) ? __ldg(rowp + i * CSRC + c) : 0.0f;
+                    for (int c = 0; c < 8; c++) val[u][c] = (c < CSRC && ok) ? __ldg(rowp + i * pitch + c) : 0.0f;
                 }
 #pragma unroll
                 for (int u = 0; u < U; u++) {
@@ -769,12 +771,13 @@ lwgrad2_kernel(const __grid_constant__ LConvParams p, const float *__restrict__ 
         lc2_stage<CSRC, CIN, NPL, F16>(x + (size_t)img0 * p.Hin * p.Win * CSRC, (size_t)p.Hin * p.Win * CSRC, p.B - img0, p.Hin,
                                        p.Win, p.IH, p.IW, oy0 * p.stride - p.pad_t, ox0 * p.stride - p.pad_l, p.fr, s_i, p.n_in, warp, lane);
         {
-            const float *dsrc = dy + (size_t)img0 * p.Hout * p.Wout * p.Cout;
-            const size_t fe = (size_t)p.Hout * p.Wout * p.Cout;
-            if (p.Cout == 32) lc2_stage<32, 32, NPL, F16>(dsrc, fe, p.B - img0, p.Hout, p.Wout, p.th, p.tw, oy0, ox0, p.fr, s_d, n_d, warp, lane);
-            else if (p.Cout == 16) lc2_stage<16, 16, NPL, F16>(dsrc, fe, p.B - img0, p.Hout, p.Wout, p.th, p.tw, oy0, ox0, p.fr, s_d, n_d, warp, lane);
-            else if (p.Cout == 8) lc2_stage<8, 8, NPL, F16>(dsrc, fe, p.B - img0, p.Hout, p.Wout, p.th, p.tw, oy0, ox0, p.fr, s_d, n_d, warp, lane);
-            else lc2_stage<1, 8, NPL, F16>(dsrc, fe, p.B - img0, p.Hout, p.Wout, p.th, p.tw, oy0, ox0, p.fr, s_d, n_d, warp, lane);   // scalar map
+            const float *dsrc = dy + (size_t)img0 * p.Hout * p.Wout * p.dy_pitch + p.dy_c0;
+            const size_t fe = (size_t)p.Hout * p.Wout * p.dy_pitch;
+            const int rem = p.B - img0, pt = p.dy_pitch;
+            if (p.Cout == 32) lc2_stage<32, 32, NPL, F16>(dsrc, fe, rem, p.Hout, p.Wout, p.th, p.tw, oy0, ox0, p.fr, s_d, n_d, warp, lane, pt);
+            else if (p.Cout == 16) lc2_stage<16, 16, NPL, F16>(dsrc, fe, rem, p.Hout, p.Wout, p.th, p.tw, oy0, ox0, p.fr, s_d, n_d, warp, lane, pt);
+            else if (p.Cout == 8) lc2_stage<8, 8, NPL, F16>(dsrc, fe, rem, p.Hout, p.Wout, p.th, p.tw, oy0, ox0, p.fr, s_d, n_d, warp, lane, pt);
+            else lc2_stage<1, 8, NPL, F16>(dsrc, fe, rem, p.Hout, p.Wout, p.th, p.tw, oy0, ox0, p.fr, s_d, n_d, warp, lane, pt);   // scalar map
         }
         __syncthreads();
 
@@ -939,6 +942,7 @@ static void lc_fill(LConvParams &p, int B, int Hin, int Win, int Cin, int Hout, 
     p.tiles_x = (Wout + kLcTw - 1) / kLcTw; p.tiles_y = (Hout + kLcTh - 1) / kLcTh;
     p.oH = oH; p.oW = oW; p.o_sy = o_sy; p.o_sx = o_sx; p.o_oy = o_oy; p.o_ox = o_ox;
     p.tw = kLcTw; p.th = kLcTh; p.fr = 1; p.mt_rows = 1; p.th_log = 3; p.n_in = 0;
+    p.dy_pitch = Cout; p.dy_c0 = 0;
 }
 
 // tile of the v2 kernels: `rows` = output rows a CTA covers over all its frames (8 warps x m-tiles per warp x mt_rows)
@@ -1136,6 +1140,36 @@ int lconv_disc_layer(const float *in, const float *in_scale, const float *in_shi
     if (rc != SPIRAL_OK) return rc;
     const cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? SPIRAL_OK : spiral_cuda_error(e, "lconv_disc_layer");
+}
+}  // namespace spiral
+
+// Kernel gradient of the discriminator's IMAGE layer (5x5 / stride 2 / 'SAME' on 1, 2, 3 or 6 channels -> Cout a multiple of
+// 32): on the tcgen05 wgrad GEMM (conv_tc.cu) M = Cin pads 3 rows to 128 and the 25-fold im2col^T of the 64 x 64 input costs
+// as much as the GEMM; here it is lwgrad2_kernel over 32-channel slices of dy (the padded input chunk is 8 channels wide).
+// dw HWIO [5][5][Cin][Cout].
+namespace spiral {
+bool lwgrad2_image_layer_supported(int Cin, int Cout) { return (Cin == 1 || Cin == 2 || Cin == 3 || Cin == 6) && Cout % 32 == 0; }
+size_t lwgrad2_image_layer_workspace_bytes() { return (size_t)148 * 208 * 32 * sizeof(float); }
+int lwgrad2_image_layer(const float *x, const float *dy, float *dw, float *workspace, int n_planes, int B, int H, int Cin, int Cout,
+                        cudaStream_t st)
+{
+    const int Ho = H / 2, CinP = 8;
+    for (int c0 = 0; c0 < Cout; c0 += 32) {
+        LConvParams p;
+        lc_fill(p, B, H, H, CinP, Ho, Ho, 32, 5, 5, 2, 1, 1, Ho, Ho, 1, 1, 0, 0);
+        p.dy_pitch = Cout; p.dy_c0 = c0;
+        lc2_tile(p, CinP, 1);
+        const int npl = lc_prec_planes(n_planes);
+        const size_t smem = (size_t)npl * ((size_t)p.n_in + (size_t)kLwPix * p.CoutPad) * 2 + (size_t)(p.KP / 8) * 4;
+        if (smem > kLcSmemMax) return spiral_set_error(SPIRAL_EUNSUPPORTED, "lwgrad2_image_layer: tile does not fit shared memory");
+        const int n_items = ((B + p.fr - 1) / p.fr) * p.tiles_x * p.tiles_y;
+        const int grid = n_items < 148 ? n_items : 148;
+        LC2_DISPATCH(lwgrad2_launch, p, x, dy, workspace, n_items, grid, smem, st);
+        const int n = 25 * Cin * 32;
+        lwgrad_reduce_kernel<<<(n + 255) / 256, 256, 0, st>>>(workspace, dw, grid, 25 * Cin, p.KP, 32, p.CoutPad, Cin, CinP, Cout, c0);
+    }
+    const cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? SPIRAL_OK : spiral_cuda_error(e, "lwgrad2_image_layer");
 }
 }  // namespace spiral
 
