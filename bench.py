@@ -629,18 +629,49 @@ def run_ours(args):
             out = D.wgan_gp_loss(fake, real, alpha, 20.0)
             out["d_loss"].backward()
             return out
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        # (1) as Agent.train_gan runs it: one CUDA graph replay per step (captured before any eager step touches the
+        # parameters: autograd pins a leaf's gradient accumulation to the stream it first ran on)
+        graph_ms = None
+        try:
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(2):
+                    step()
+            torch.cuda.current_stream().wait_stream(side)
+            for q in D.params.values():
+                q.grad = None
+            g_ = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g_):
+                o = D.wgan_gp_loss(fake, real, alpha, 20.0)
+                o["d_loss"].backward()
+            g_.replay()
+            torch.cuda.synchronize()
+            s.record()
+            for _ in range(iters):
+                g_.replay()
+            e.record()
+            torch.cuda.synchronize()
+            graph_ms = s.elapsed_time(e) / iters
+            del g_
+        except Exception as ex:                              # noqa: BLE001 -- report, the eager number still stands
+            graph_ms = "capture failed: %s" % (str(ex).splitlines()[0],)
+        # (2) eager (one launch per kernel from Python)
         for _ in range(2):
             step()
         torch.cuda.synchronize()
-        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s.record()
         for _ in range(iters):
             out = step()
         e.record()
         torch.cuda.synchronize()
-        return dict(ms_per_step=s.elapsed_time(e) / iters, batch=n, precision="bf16x3 forward / bf16x6 gradients",
-                    d_loss=float(out["d_loss"]), note="WGAN-GP step incl. double backward; conv fwd/dgrad/wgrad on K2b kernels, "
-                                                      "BN/leaky-ReLU/dense glue in PyTorch")
+        return dict(ms_per_step=graph_ms if isinstance(graph_ms, float) else s.elapsed_time(e) / iters,
+                    ms_per_step_graph=graph_ms, ms_per_step_eager=s.elapsed_time(e) / iters, batch=n,
+                    precision="bf16x3 forward / bf16x6 gradients", d_loss=float(out["d_loss"].detach()),
+                    note="WGAN-GP step incl. double backward; conv fwd/dgrad/wgrad on K2b kernels (each kernel's operand planes "
+                         "split once per step), BN/leaky-ReLU/dense glue in PyTorch; ms_per_step = the CUDA-graph replay "
+                         "Agent.train_gan uses")
 
     def agent_loop(n=128, iters=3):
         """The whole synchronous loop at a small batch, for context: policy.act (PyTorch module + K4 sampling)

@@ -277,6 +277,19 @@ int spiral_conv_dgrad(const float *dy_dev, const float *w_dev, float *dx_dev, in
 int spiral_conv_wgrad(const float *x_dev, const float *dy_dev, float *dw_dev, int32_t B, int32_t H,
                       int32_t Cin, int32_t Cout, int32_t precision, void *workspace_dev, void *stream);
 
+/* The same kernel serves several calls of one optimiser step (build_optim evaluates the shared-weight discriminator on real,
+ * fake and the interpolates, models/discriminator.py:99-117, and tf.gradients walks each pass): spiral_conv_pack splits it into
+ * the tensor-core operand planes ONCE (op 0: for the forward, op 1: for the input gradient), the *_packed calls take the planes.
+ * spiral_conv_packed_bytes: size of the planes, 0 when this shape / precision runs on a path without packed kernels (then
+ * use the plain entry points), -1 on a bad shape. */
+int64_t spiral_conv_packed_bytes(int32_t op, int32_t B, int32_t H, int32_t Cin, int32_t Cout, int32_t precision);
+int spiral_conv_pack(const float *w_dev, void *packed_dev, int32_t op, int32_t B, int32_t H, int32_t Cin, int32_t Cout,
+                     int32_t precision, void *stream);
+int spiral_conv_forward_packed(const float *x_dev, const void *packed_dev, float *y_dev, int32_t B, int32_t H, int32_t Cin,
+                               int32_t Cout, int32_t precision, void *workspace_dev, void *stream);
+int spiral_conv_dgrad_packed(const float *dy_dev, const void *packed_dev, float *dx_dev, int32_t B, int32_t H, int32_t Cin,
+                             int32_t Cout, int32_t precision, void *workspace_dev, void *stream);
+
 /* ------------------------------------------------------------------ */
 /* Categorical sampling for the action heads (K4)                       */
 /* replaces: models/policy.py:364-368 categorical_sample                */

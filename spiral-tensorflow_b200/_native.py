@@ -120,6 +120,10 @@ SYMBOLS = {
     "spiral_conv_forward": (C.c_int, [_vp, _vp, _vp] + [C.c_int32] * 5 + [_vp, _vp]),
     "spiral_conv_dgrad": (C.c_int, [_vp, _vp, _vp] + [C.c_int32] * 5 + [_vp, _vp]),
     "spiral_conv_wgrad": (C.c_int, [_vp, _vp, _vp] + [C.c_int32] * 5 + [_vp, _vp]),
+    "spiral_conv_packed_bytes": (C.c_int64, [C.c_int32] * 6),
+    "spiral_conv_pack": (C.c_int, [_vp, _vp] + [C.c_int32] * 6 + [_vp]),
+    "spiral_conv_forward_packed": (C.c_int, [_vp, _vp, _vp] + [C.c_int32] * 5 + [_vp, _vp]),
+    "spiral_conv_dgrad_packed": (C.c_int, [_vp, _vp, _vp] + [C.c_int32] * 5 + [_vp, _vp]),
 }
 
 _lib = None

@@ -276,6 +276,49 @@ extern "C" int64_t spiral_conv_workspace_bytes(int32_t B, int32_t H, int32_t Cin
     return (int64_t)n;
 }
 
+extern "C" int64_t spiral_conv_packed_bytes(int32_t op, int32_t B, int32_t H, int32_t Cin, int32_t Cout, int32_t precision)
+{
+    if (check_shape(B, H, Cin, Cout, precision) != SPIRAL_OK || (op != 0 && op != 1)) return -1;
+    return (precision != 0 && conv_tc_supported(op, B, H, Cin, Cout)) ? (int64_t)conv_tc_packed_bytes(Cin, Cout) : 0;
+}
+
+extern "C" int spiral_conv_pack(const float *w, void *packed, int32_t op, int32_t B, int32_t H, int32_t Cin, int32_t Cout,
+                                int32_t precision, void *stream)
+{
+    SPIRAL_REQUIRE(w); SPIRAL_REQUIRE(packed);
+    if (spiral_conv_packed_bytes(op, B, H, Cin, Cout, precision) <= 0)
+        return spiral_set_error(SPIRAL_EINVAL, "conv_pack: this shape / precision has no packed kernel (op %d Cin=%d Cout=%d precision %d)", op, Cin, Cout, precision);
+    conv_tc_pack(w, (char *)packed, op, Cin, Cout, precision_planes(precision), (cudaStream_t)stream);
+    const cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? SPIRAL_OK : spiral_cuda_error(e, "spiral_conv_pack");
+}
+
+extern "C" int spiral_conv_forward_packed(const float *x, const void *packed, float *y, int32_t B, int32_t H, int32_t Cin,
+                                          int32_t Cout, int32_t precision, void *ws, void *stream)
+{
+    SPIRAL_REQUIRE(x); SPIRAL_REQUIRE(packed); SPIRAL_REQUIRE(y); SPIRAL_REQUIRE(ws);
+    if (spiral_conv_packed_bytes(0, B, H, Cin, Cout, precision) <= 0)
+        return spiral_set_error(SPIRAL_EINVAL, "conv_forward_packed: this shape / precision has no packed kernel");
+    const int rc = conv_tc_forward(x, nullptr, y, B, H, Cin, Cout, precision_planes(precision), (char *)ws, (cudaStream_t)stream,
+                                   (const char *)packed);
+    if (rc != SPIRAL_OK) return rc;
+    const cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? SPIRAL_OK : spiral_cuda_error(e, "spiral_conv_forward_packed");
+}
+
+extern "C" int spiral_conv_dgrad_packed(const float *dy, const void *packed, float *dx, int32_t B, int32_t H, int32_t Cin,
+                                        int32_t Cout, int32_t precision, void *ws, void *stream)
+{
+    SPIRAL_REQUIRE(dy); SPIRAL_REQUIRE(packed); SPIRAL_REQUIRE(dx); SPIRAL_REQUIRE(ws);
+    if (spiral_conv_packed_bytes(1, B, H, Cin, Cout, precision) <= 0)
+        return spiral_set_error(SPIRAL_EINVAL, "conv_dgrad_packed: this shape / precision has no packed kernel");
+    const int rc = conv_tc_dgrad(dy, nullptr, dx, B, H, Cin, Cout, precision_planes(precision), (char *)ws, (cudaStream_t)stream,
+                                 (const char *)packed);
+    if (rc != SPIRAL_OK) return rc;
+    const cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? SPIRAL_OK : spiral_cuda_error(e, "spiral_conv_dgrad_packed");
+}
+
 extern "C" int spiral_conv_forward(const float *x, const float *w, float *y, int32_t B, int32_t H, int32_t Cin,
                                    int32_t Cout, int32_t precision, void *ws, void *stream)
 {

@@ -9,10 +9,13 @@ namespace spiral {
 // op: 0 forward, 1 dgrad, 2 wgrad
 bool conv_tc_supported(int op, int B, int H, int Cin, int Cout);
 size_t conv_tc_workspace_bytes(int B, int H, int Cin, int Cout);
+// packed: the kernel's operand planes from conv_tc_pack (nullptr: split `w` into the workspace)
+size_t conv_tc_packed_bytes(int Cin, int Cout);
+void conv_tc_pack(const float *w, char *packed, int op, int Cin, int Cout, int ns, cudaStream_t st);
 int conv_tc_forward(const float *x, const float *w, float *y, int B, int H, int Cin, int Cout, int ns, char *ws,
-                    cudaStream_t st);
+                    cudaStream_t st, const char *packed = nullptr);
 int conv_tc_dgrad(const float *dy, const float *w, float *dx, int B, int H, int Cin, int Cout, int ns, char *ws,
-                  cudaStream_t st);
+                  cudaStream_t st, const char *packed = nullptr);
 int conv_tc_wgrad(const float *x, const float *dy, float *dw, int B, int H, int Cin, int Cout, int ns, char *ws,
                   cudaStream_t st);
 

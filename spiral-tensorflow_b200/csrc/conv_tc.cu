@@ -625,30 +625,43 @@ static int taps_launch(int mode, char *act, size_t act_plane, char *wp, size_t w
     return SPIRAL_OK;
 }
 
+// The operand planes of a kernel, for the forward (op 0: K-major [Cout][25 * Cin]) or the input gradient (op 1: HWIO as it is --
+// [tap][ci][co] is K-major per tap).  The three shared-weight passes of a WGAN-GP step (and the convolutions of its double
+// backward) read the same kernels: spiral_conv_pack + the *_packed entry points split each kernel once per step instead of
+// once per call.
+size_t conv_tc_packed_bytes(int Cin, int Cout) { return al((size_t)kMaxSplit * 25 * Cin * Cout * 2); }
+
+void conv_tc_pack(const float *w, char *wp, int op, int Cin, int Cout, int ns, cudaStream_t st)
+{
+    const size_t nw = (size_t)25 * Cin * Cout;
+    if (op == 1) launch_split(w, wp, nw, ns, st);
+    else if (ns <= 2) conv_tc_pack_weights(w, wp, wp + nw * 2, Cin, Cout, st);      // the reward path's layout (disc_tc.cu): planes 0/1 = hi/lo
+    else pack_kmajor_kernel<<<148 * 4, 256, 0, st>>>(w, (__nv_bfloat16 *)wp, Cin, Cout, nw, ns);
+}
+
+// workspace: [activation planes][kernel planes (unused when `packed` is given)][tap-slice partials]
 int conv_tc_forward(const float *x, const float *w, float *y, int B, int H, int Cin, int Cout, int ns, char *ws,
-                    cudaStream_t st)
+                    cudaStream_t st, const char *packed)
 {
     const size_t nx = (size_t)B * H * H * Cin, nw = (size_t)25 * Cin * Cout;
     char *xp = ws, *wp = ws + al((size_t)kMaxSplit * nx * 2);
-    launch_split(x, xp, nx, ns, st);
-    if (ns <= 2) {
-        // the reward path's persistent kernel (disc_tc.cu): planes 0/1 = hi/lo
-        conv_tc_pack_weights(w, wp, wp + nw * 2, Cin, Cout, st);
-        return conv_tc_layer(xp, xp + nx * 2, wp, wp + nw * 2, y, B, H, Cin, Cout, ns == 2 ? 1 : 0, st);
-    }
-    pack_kmajor_kernel<<<148 * 4, 256, 0, st>>>(w, (__nv_bfloat16 *)wp, Cin, Cout, nw, ns);
     float *part = reinterpret_cast<float *>(wp + al((size_t)kMaxSplit * nw * 2));
+    launch_split(x, xp, nx, ns, st);
+    if (packed) wp = const_cast<char *>(packed);
+    else conv_tc_pack(w, wp, 0, Cin, Cout, ns, st);
+    if (ns <= 2) return conv_tc_layer(xp, xp + nx * 2, wp, wp + nw * 2, y, B, H, Cin, Cout, ns == 2 ? 1 : 0, st);
     return taps_launch<128>(0, xp, nx * 2, wp, nw * 2, y, B, H, Cin, Cout, ns, st, part);
 }
 
 int conv_tc_dgrad(const float *dy, const float *w, float *dx, int B, int H, int Cin, int Cout, int ns, char *ws,
-                  cudaStream_t st)
+                  cudaStream_t st, const char *packed)
 {
     const size_t ny = (size_t)B * (H / 2) * (H / 2) * Cout, nw = (size_t)25 * Cin * Cout;
     char *dyp = ws, *wp = ws + al((size_t)kMaxSplit * ny * 2);
-    launch_split(dy, dyp, ny, ns, st);
-    launch_split(w, wp, nw, ns, st);                       // HWIO: [tap][ci][co] is already K-major per tap
     float *part = reinterpret_cast<float *>(wp + al((size_t)kMaxSplit * nw * 2));
+    launch_split(dy, dyp, ny, ns, st);
+    if (packed) wp = const_cast<char *>(packed);
+    else conv_tc_pack(w, wp, 1, Cin, Cout, ns, st);
     if (Cin >= 128) return taps_launch<128>(1, dyp, ny * 2, wp, nw * 2, dx, B, H, Cin, Cout, ns, st, part);
     return taps_launch<64>(1, dyp, ny * 2, wp, nw * 2, dx, B, H, Cin, Cout, ns, st, part);
 }

@@ -53,21 +53,64 @@ def _call(fn_name, a, b, out, B, H, Cin, Cout, precision):
     return out
 
 
-def conv_forward(x, w, precision=1):
+class PackScope:
+    """Operand planes of the kernels used while ONE loss is evaluated and differentiated (Discriminator.wgan_gp_loss opens a
+    scope per call): the three shared-weight passes and the convolutions of the penalty's double backward read the same
+    kernels, so each is split into tensor-core planes once per scope (spiral_conv_pack) instead of once per convolution.
+    Keyed by the kernel's storage; the weights must not change while a scope is in use (they do not: the optimiser runs
+    after backward).  Scopes are not reused across steps -- under a CUDA graph the pack kernels are part of the graph."""
+
+    def __init__(self):
+        self.planes = {}
+
+    def get(self, w, op, B, H, Cin, Cout, precision):
+        key = (w.data_ptr(), op, Cin, Cout, precision)
+        hit = self.planes.get(key)
+        if hit is not None:
+            return hit[0]
+        lib = N.lib()
+        nbytes = int(lib.spiral_conv_packed_bytes(op, B, H, Cin, Cout, precision))
+        if nbytes <= 0:
+            self.planes[key] = (None, w)
+            return None
+        buf = torch.empty((nbytes,), dtype=torch.uint8, device=w.device)
+        N.check(lib.spiral_conv_pack(N.ptr(w), N.ptr(buf), op, B, H, Cin, Cout, precision, N.stream_ptr()), "spiral_conv_pack")
+        self.planes[key] = (buf, w)                          # holds w: its storage cannot be recycled under the key
+        return buf
+
+
+def _call_packed(fn_name, a, packed, out, B, H, Cin, Cout, precision):
+    lib = N.lib()
+    nbytes = lib.spiral_conv_workspace_bytes(B, H, Cin, Cout, precision)
+    if nbytes < 0:
+        N.check(-1, "spiral_conv_workspace_bytes")
+    ws = _workspace(a.device, nbytes)
+    N.check(getattr(lib, fn_name)(N.ptr(a), N.ptr(packed), N.ptr(out), B, H, Cin, Cout, precision, N.ptr(ws), N.stream_ptr()),
+            fn_name)
+    return out
+
+
+def conv_forward(x, w, precision=1, scope=None):
     """y[B,H/2,H/2,Cout] = conv(x[B,H,H,Cin], w[5,5,Cin,Cout]); no autograd."""
     x, w = _check(x, "x"), _check(w, "w")
     B, H, _, Cin = x.shape
     Cout = w.shape[3]
     y = torch.empty((B, H // 2, H // 2, Cout), dtype=torch.float32, device=x.device)
+    packed = scope.get(w, 0, B, H, Cin, Cout, precision) if scope is not None else None
+    if packed is not None:
+        return _call_packed("spiral_conv_forward_packed", x, packed, y, B, H, Cin, Cout, precision)
     return _call("spiral_conv_forward", x, w, y, B, H, Cin, Cout, precision)
 
 
-def conv_dgrad(dy, w, precision=1):
+def conv_dgrad(dy, w, precision=1, scope=None):
     """dx[B,H,H,Cin] for dy[B,H/2,H/2,Cout]; no autograd."""
     dy, w = _check(dy, "dy"), _check(w, "w")
     B, Ho, _, Cout = dy.shape
     Cin = w.shape[2]
     dx = torch.empty((B, 2 * Ho, 2 * Ho, Cin), dtype=torch.float32, device=dy.device)
+    packed = scope.get(w, 1, B, 2 * Ho, Cin, Cout, precision) if scope is not None else None
+    if packed is not None:
+        return _call_packed("spiral_conv_dgrad_packed", dy, packed, dx, B, 2 * Ho, Cin, Cout, precision)
     return _call("spiral_conv_dgrad", dy, w, dx, B, 2 * Ho, Cin, Cout, precision)
 
 
@@ -80,58 +123,60 @@ def conv_wgrad(x, dy, precision=1):
     return _call("spiral_conv_wgrad", x, dy, dw, B, H, Cin, Cout, precision)
 
 
+# `scope` (a PackScope or None) rides along as a non-tensor argument; only convolutions whose kernel operand is a network
+# PARAMETER use it (the kernel-shaped tensors of the double backward, ggw, are different every time)
 class _Conv(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, w, precision):
+    def forward(ctx, x, w, precision, scope):
         ctx.save_for_backward(x, w)
-        ctx.precision = precision
-        return conv_forward(x, w, precision)
+        ctx.precision, ctx.scope = precision, scope
+        return conv_forward(x, w, precision, scope)
 
     @staticmethod
     def backward(ctx, gy):
         x, w = ctx.saved_tensors
-        gx = _Dgrad.apply(gy, w, ctx.precision) if ctx.needs_input_grad[0] else None
-        gw = _Wgrad.apply(x, gy, ctx.precision) if ctx.needs_input_grad[1] else None
-        return gx, gw, None
+        gx = _Dgrad.apply(gy, w, ctx.precision, ctx.scope) if ctx.needs_input_grad[0] else None
+        gw = _Wgrad.apply(x, gy, ctx.precision, ctx.scope) if ctx.needs_input_grad[1] else None
+        return gx, gw, None, None
 
 
 class _Dgrad(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, gy, w, precision):
+    def forward(ctx, gy, w, precision, scope):
         ctx.save_for_backward(gy, w)
-        ctx.precision = precision
-        return conv_dgrad(gy, w, precision)
+        ctx.precision, ctx.scope = precision, scope
+        return conv_dgrad(gy, w, precision, scope)
 
     @staticmethod
     def backward(ctx, ggx):
         gy, w = ctx.saved_tensors
-        g_gy = _Conv.apply(ggx, w, ctx.precision) if ctx.needs_input_grad[0] else None
-        g_w = _Wgrad.apply(ggx, gy, ctx.precision) if ctx.needs_input_grad[1] else None
-        return g_gy, g_w, None
+        g_gy = _Conv.apply(ggx, w, ctx.precision, ctx.scope) if ctx.needs_input_grad[0] else None
+        g_w = _Wgrad.apply(ggx, gy, ctx.precision, ctx.scope) if ctx.needs_input_grad[1] else None
+        return g_gy, g_w, None, None
 
 
 class _Wgrad(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, gy, precision):
+    def forward(ctx, x, gy, precision, scope):
         ctx.save_for_backward(x, gy)
-        ctx.precision = precision
+        ctx.precision, ctx.scope = precision, scope
         return conv_wgrad(x, gy, precision)
 
     @staticmethod
     def backward(ctx, ggw):
         x, gy = ctx.saved_tensors
-        g_x = _Dgrad.apply(gy, ggw, ctx.precision) if ctx.needs_input_grad[0] else None
-        g_gy = _Conv.apply(x, ggw, ctx.precision) if ctx.needs_input_grad[1] else None
-        return g_x, g_gy, None
+        g_x = _Dgrad.apply(gy, ggw, ctx.precision, None) if ctx.needs_input_grad[0] else None
+        g_gy = _Conv.apply(x, ggw, ctx.precision, None) if ctx.needs_input_grad[1] else None
+        return g_x, g_gy, None, None
 
 
-def conv5x5s2(x, w, precision=1):
+def conv5x5s2(x, w, precision=1, scope=None):
     """Differentiable (to any order) tf.layers.conv2d(x, Cout, 5, strides=2, padding='same',
     use_bias=False) on NHWC ``x`` with HWIO ``w``."""
-    return _Conv.apply(x, w, int(precision))
+    return _Conv.apply(x, w, int(precision), scope)
 
 
-def disc_forward_native(params, x, layer_num, batch_norm, normalize=True, precision=1, groups=1):
+def disc_forward_native(params, x, layer_num, batch_norm, normalize=True, precision=1, groups=1, scope=None):
     """Differentiable D(x) (models/discriminator.py:51-95) whose convolutions and all their
     gradients run on libspiral_b200.so.  x f32[N,S,S,C] NHWC (0..255 when ``normalize``).
     TF semantics: SAME padding 1/2, BN epsilon 1e-3 with the biased batch variance (training mode),
@@ -146,7 +191,7 @@ def disc_forward_native(params, x, layer_num, batch_norm, normalize=True, precis
     if x.shape[0] % G:
         raise ValueError("batch %d does not split into %d groups" % (x.shape[0], G))
     for l in range(layer_num):
-        x = conv5x5s2(x, params["conv%d/kernel" % l], precision) + params["conv%d/bias" % l]
+        x = conv5x5s2(x, params["conv%d/kernel" % l], precision, scope) + params["conv%d/bias" % l]
         if l > 0 and batch_norm:
             shp = x.shape
             xg = x.view(G, shp[0] // G, shp[1], shp[2], shp[3])

@@ -168,11 +168,11 @@ class Discriminator(object):
         return self.forward(images, global_bn=global_bn)[0]
 
     # ------------------------------------------------------------------
-    def logits_fn(self, x_normed, groups=1):
+    def logits_fn(self, x_normed, groups=1, scope=None):
         """Differentiable D on already-normalised NHWC input; convolutions and all their gradients
-        run on libspiral_b200.so (models/conv_ops.py).  ``groups``: see conv_ops.disc_forward_native."""
+        run on libspiral_b200.so (models/conv_ops.py).  ``groups``, ``scope``: see conv_ops.disc_forward_native / PackScope."""
         return conv_ops.disc_forward_native(self.params, x_normed, self.layer_num, self.batch_norm,
-                                            normalize=False, precision=self.grad_precision, groups=groups)
+                                            normalize=False, precision=self.grad_precision, groups=groups, scope=scope)
 
     def wgan_gp_loss(self, fake, real, alpha, wgan_lambda=None):
         """reference :97-122 (build_optim): critic + lambda * gradient penalty, the penalty on the
@@ -188,18 +188,19 @@ class Discriminator(object):
             f = torch.cat([f, r], -1)
             r = torch.cat([r, r], -1)
         inter = (r.flatten(1) + alpha * (f.flatten(1) - r.flatten(1))).detach().requires_grad_(True)
+        scope = conv_ops.PackScope()               # each kernel's tensor-core planes once for the three passes and their gradients
         if self.fused_passes:
             # the three shared-weight passes as ONE pass over [real; fake; interpolates], each third with its own batch
             # statistics: a third of the launches.  The penalty's gradient is taken w.r.t. the interpolates only; the
             # first two thirds of every dgrad operand are exact zeros (no statistic crosses a group), so the value is
             # that of the separate passes.
             n = r.shape[0]
-            probs, logits = self.logits_fn(torch.cat([r, f, inter.view_as(f)], 0), groups=3)
+            probs, logits = self.logits_fn(torch.cat([r, f, inter.view_as(f)], 0), groups=3, scope=scope)
             real_logits, fake_logits, probs = logits[:n], logits[n:2 * n], probs[2 * n:]
         else:
-            _, real_logits = self.logits_fn(r)
-            _, fake_logits = self.logits_fn(f)
-            probs, _ = self.logits_fn(inter.view_as(f))
+            _, real_logits = self.logits_fn(r, scope=scope)
+            _, fake_logits = self.logits_fn(f, scope=scope)
+            probs, _ = self.logits_fn(inter.view_as(f), scope=scope)
         g_loss = -fake_logits.mean()
         critic = fake_logits.mean() - real_logits.mean()
         grads = torch.autograd.grad(probs.sum(), inter, create_graph=True)[0]

@@ -26,11 +26,33 @@ def step():
     out = D.wgan_gp_loss(fake, real, alpha, 20.0)
     out["d_loss"].backward()
     return out
-step(); torch.cuda.synchronize()
-t0 = time.perf_counter()
 s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-s.record()
-for _ in range(iters):
+if os.environ.get("DSTEP_GRAPH", "1") != "only":
+  step(); torch.cuda.synchronize()
+  t0 = time.perf_counter()
+  s.record()
+  for _ in range(iters):
     out = step()
-e.record(); torch.cuda.synchronize()
-print("ok d_loss %.5f  %.2f ms/step (events)  %.2f ms/step (wall)" % (float(out["d_loss"].detach()), s.elapsed_time(e) / iters, (time.perf_counter() - t0) * 1e3 / iters))
+  e.record(); torch.cuda.synchronize()
+  print("ok d_loss %.5f  %.2f ms/step (events)  %.2f ms/step (wall)" % (float(out["d_loss"].detach()), s.elapsed_time(e) / iters, (time.perf_counter() - t0) * 1e3 / iters))
+if os.environ.get("DSTEP_GRAPH", "1") != "0":
+    # the same step as a CUDA graph replay (how Agent.train_gan runs it): no launch gaps
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(2):
+            o = D.wgan_gp_loss(fake, real, alpha, 20.0)
+            o["d_loss"].backward()
+    torch.cuda.current_stream().wait_stream(side)
+    for q in D.params.values():
+        q.grad = None                                         # the gradients live in the graph's pool (as in Agent.train_gan)
+    g_ = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g_):
+        o = D.wgan_gp_loss(fake, real, alpha, 20.0)
+        o["d_loss"].backward()
+    g_.replay(); torch.cuda.synchronize()
+    s.record()
+    for _ in range(iters):
+        g_.replay()
+    e.record(); torch.cuda.synchronize()
+    print("graph replay: d_loss %.5f  %.2f ms/step" % (float(o["d_loss"].detach()), s.elapsed_time(e) / iters))
