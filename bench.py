@@ -708,16 +708,17 @@ def run_ours(args):
                     acting_precision="bf16 (--policy_act_native True: the actors' convolutions on bf16 tensor cores, logits within 3e-2 "
                                      "of the fp32 module -- narrower than the reference's fp32 actors; it only perturbs the behaviour "
                                      "policy's samples, the learner's logits / loss are fp32-parity)",
-                    learner_precision="bf16x6 (--policy_learn_native True: fp32-exact operands, gradients within 3e-5 of float64)",
+                    learner_precision="f16x3 (--policy_learn_native True: 22 operand bits in two fp16 planes, gradients as close to float64 as PyTorch strict fp32)",
                     note="full loop incl. the policy (not the headline metric)")
 
     def learner_paths(n=128):
         """Agent.train_policy (policy forward over [n*20] frames, fused A2C loss, backward, clip + Adam; CUDA-graph replay) for
-        the convolution paths of the learner: the library's kernels (default, bf16x6 = fp32 parity; bf16x3), PyTorch / cuDNN in
+        the convolution paths of the learner: the library's kernels (f16x3: the default, fp32 parity; bf16x6: fp32 parity; bf16x3: 16 operand bits), PyTorch / cuDNN in
         strict fp32 (the parity-equivalent library path) and in TF32 (10-bit operands, what round 1 ran)."""
         agent_mod = import_module(sp.__name__ + ".agent")
         W = WORKLOADS["rgb64"]
-        modes = {"native_bf16x6": ["--policy_learn_native", "True", "--policy_tf32", "False"],
+        modes = {"native_f16x3": ["--policy_learn_native", "True", "--policy_tf32", "False", "--policy_learn_precision", "f16x3"],
+                 "native_bf16x6": ["--policy_learn_native", "True", "--policy_tf32", "False", "--policy_learn_precision", "bf16x6"],
                  "native_bf16x3": ["--policy_learn_native", "True", "--policy_tf32", "False", "--policy_learn_precision", "bf16x3"],
                  "cudnn_fp32": ["--policy_learn_native", "False", "--policy_tf32", "False"],
                  "cudnn_tf32": ["--policy_learn_native", "False", "--policy_tf32", "True"]}
@@ -741,7 +742,8 @@ def run_ours(args):
             del ag, env
             torch.cuda.empty_cache()
         res["note"] = ("%d canvases x 20 steps = %d frames per learner step; native = csrc/policy_learn.cu (mma.sync implicit GEMMs, forward + "
-                       "dgrad + wgrad; gradients within 3e-5 of float64 like cuDNN fp32); TF32 is ~1e-3" % (n, n * 20))
+                       "dgrad + wgrad; f16x3 = 22 operand bits in two fp16 planes, three products: gradients as close to float64 as cuDNN "
+                       "strict fp32, tests/test_gpu_policy_native.py); TF32 is ~1e-3" % (n, n * 20))
         return res
 
     # ---- headline ----

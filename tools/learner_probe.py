@@ -18,6 +18,7 @@ from importlib import import_module  # noqa: E402
 
 agent_mod = import_module(sp.__name__ + ".agent")
 MODES = {"native": ["--policy_learn_native", "True", "--policy_tf32", "False"],
+         "native_x6": ["--policy_learn_native", "True", "--policy_tf32", "False", "--policy_learn_precision", "bf16x6"],
          "native_x3": ["--policy_learn_native", "True", "--policy_tf32", "False", "--policy_learn_precision", "bf16x3"],
          "fp32": ["--policy_learn_native", "False", "--policy_tf32", "False"],
          "tf32": ["--policy_learn_native", "False", "--policy_tf32", "True"]}
@@ -29,14 +30,14 @@ for mode in (sys.argv[1:] or ["native", "native_x3", "fp32", "tf32"]):
     ag = agent_mod.Agent(a, env)
     ro = ag.rollout()
     times = []
-    for i in range(8):
+    for i in range(int(os.environ.get("PROBE_ITERS", "8"))):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         m = ag.train_policy({k: v.clone() for k, v in ro.items()})
         e1.record()
         torch.cuda.synchronize()
         times.append(e0.elapsed_time(e1))
-    print("%-7s train_policy %.1f ms (graph replay; first eager step %.1f ms), loss %.4f" % (mode, sum(times[4:]) / 4, times[0], float(m["model/total_loss"])),
+    print("%-7s train_policy %.1f ms (graph replay; first eager step %.1f ms), loss %.4f" % (mode, sum(times[-4:]) / len(times[-4:]), times[0], float(m["model/total_loss"])),
           flush=True)
     ag.close()
     del ag, env
