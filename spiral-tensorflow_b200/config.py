@@ -72,14 +72,15 @@ def build_parser():
     # arithmetic of the brush state machine (include/spiral_b200.h SpiralEnvCfg.math_mode): 'det' = double-precision,
     # correctly rounded exp / log / hypot (canvases bit-identical to the oracle's det mode, which matches glibc on >= 99 %
     # of canvases); 'fast' = binary32 polynomials and a division-light dab loop (bit-identical to the oracle's fast mode;
-    # against libm: mean |err| <= 1e-3 on every canvas, single-dab jitter differences on ~20 % of 20-step canvases)
+    # against libm: mean |err| <= 1e-3 on every canvas, single-dab jitter differences on ~20 % of 20-step canvases; the
+    # default, DESIGN.md section 2 says why)
+    parser.add_argument('--raster_math', type=str, default='fast', choices=['det', 'fast'])
     # trajectory store: RGB observations are integers 0..255, kept as uint8 (lossless, 4x smaller); False = float32
     parser.add_argument('--traj_uint8', type=str2bool, default=True)
     # several ranks: score the GAN reward with batch-norm statistics of the GLOBAL batch (per-layer all-reduce of the
     # channel sums, spiral_disc_forward_staged) instead of each rank's shard (the reference normalises with whatever
     # batch the learner dequeued, discriminator.py:76-79)
     parser.add_argument('--disc_global_bn', type=str2bool, default=False)
-    parser.add_argument('--raster_math', type=str, default='det', choices=['det', 'fast'])
     parser.add_argument('--disc_precision', type=str, default='bf16x3', choices=['fp32', 'bf16x3', 'bf16'])
     # arithmetic of the WGAN-GP step's convolutions and their gradients (K2b); 'auto' = bf16x6 (24 operand bits,
     # fp32-exact products on the tensor cores) when the reward forward runs on tensor cores, else fp32
