@@ -349,6 +349,13 @@ int spiral_pconv_forward(const void *x_bf16_dev, const void *w_packed_bf16_dev, 
                          int32_t KH, int32_t KW, int32_t stride, int32_t pad_t, int32_t pad_l, int32_t relu,
                          int32_t oH, int32_t oW, int32_t o_sy, int32_t o_sx, int32_t o_oy, int32_t o_ox,
                          int32_t out_f32, void *stream);
+/* Packs a convolution kernel for spiral_pconv_forward: one bf16 plane [round8(rows)][round16(n_taps * Ck) + 8] with
+ * packed[row][tap * Ck + c] = w[row * s_row + c * s_c + tap_ky[tap] * s_ky + tap_kx[tap] * s_kx] (element strides of the fp32
+ * tensor: any layout / view / subset of taps, e.g. one parity class of a transposed convolution); permute_rows (rows == 32):
+ * row nt*8 + j holds channel (j>>1)*8 + nt*2 + (j&1), the order spiral_pconv_forward expects for 32 output channels. */
+int spiral_pconv_pack(const float *w_dev, void *packed_bf16_dev, int32_t rows, int32_t Ck, int32_t n_taps, int64_t s_row,
+                      int64_t s_c, int64_t s_ky, int64_t s_kx, const int32_t *tap_ky, const int32_t *tap_kx,
+                      int32_t permute_rows, void *stream);
 
 /* Fused res-block stack (policy.py:111-114, :255-258, :349-362): n_convs / 2 blocks of [conv3x3 -> ReLU -> conv3x3, + x]
  * on bf16 NHWC [B,S,S,32] maps with S = 6 or 8; w_packed = n_convs kernels packed as for spiral_pconv_forward

@@ -108,6 +108,8 @@ SYMBOLS = {
     "spiral_adam_step_lr_dev": (C.c_int, [C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(C.c_int64),
                                           C.c_int32, _vp, C.c_float, C.c_float, C.c_float, C.c_float, _vp, C.c_float, _vp]),
     "spiral_pconv_forward": (C.c_int, [_vp] * 6 + [C.c_int32] * 20 + [_vp]),
+    "spiral_pconv_pack": (C.c_int, [_vp, _vp, C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_int64, C.c_int64, C.c_int64, _vp, _vp,
+                                    C.c_int32, _vp]),
     "spiral_pres_stack": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int32, C.c_int32, C.c_int32, _vp]),
     "spiral_phead_last": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, C.c_int32, C.c_int32, _vp]),
     "spiral_lconv_packed_elems": (C.c_int64, [C.c_int32] * 3),

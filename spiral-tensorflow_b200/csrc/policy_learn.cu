@@ -171,6 +171,8 @@ __device__ __forceinline__ void lc_mma_planes2(float (&hi)[4], float (&lo)[4], c
 struct LPackParams {
     int rows, rows_pad, Ck, n_taps, K, KS;       // Ck: channels per tap of the packed layout
     int Ck_src;                                  // channels of the kernel tensor (< Ck: the rest of each tap is zero)
+    int perm;                                    // acting path (pconv_kernel with 32 output channels): row nt*8 + j holds
+                                                 // channel (j>>1)*8 + nt*2 + (j&1), so a thread's accumulators are 8 adjacent channels
     long long s_row, s_c, s_ky, s_kx;
     int tap_ky[kLcMaxTaps], tap_kx[kLcMaxTaps];
 };
@@ -181,7 +183,8 @@ lpack_kernel(const __grid_constant__ LPackParams p, const float *__restrict__ w,
 {
     const int n = p.rows_pad * p.KS;                                          // elements per plane; planes are contiguous
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const int row = i / p.KS, k = i - row * p.KS;
+        const int prow = i / p.KS, k = i - prow * p.KS;
+        const int row = p.perm ? (((prow & 7) >> 1) * 8 + (prow >> 3) * 2 + (prow & 1)) : prow;
         float v = 0.0f;
         if (row < p.rows && k < p.K) {
             const int tap = k / p.Ck, c = k - tap * p.Ck;
@@ -998,7 +1001,7 @@ extern "C" int spiral_lconv_pack(const float *w, void *packed_planes, int32_t n_
     if (rows < 1 || rows > 32 || !lc_cin_ok(Ck) || n_taps < 1 || n_taps > kLcMaxTaps || !lc_prec_ok(n_planes))
         return spiral_set_error(SPIRAL_EINVAL, "lconv_pack: unsupported shape rows=%d Ck=%d taps=%d planes=%d", rows, Ck, n_taps, n_planes);
     LPackParams p;
-    p.rows = rows; p.rows_pad = (rows + 7) & ~7; p.Ck = lc_cin_pad(Ck); p.Ck_src = Ck; p.n_taps = n_taps;
+    p.rows = rows; p.rows_pad = (rows + 7) & ~7; p.Ck = lc_cin_pad(Ck); p.Ck_src = Ck; p.n_taps = n_taps; p.perm = 0;
     p.K = n_taps * p.Ck; p.KS = ((p.K + 15) & ~15) + 8;
     p.s_row = s_row; p.s_c = s_c; p.s_ky = s_ky; p.s_kx = s_kx;
     for (int i = 0; i < kLcMaxTaps; i++) { p.tap_ky[i] = i < n_taps ? tap_ky[i] : 0; p.tap_kx[i] = i < n_taps ? tap_kx[i] : 0; }
@@ -1008,6 +1011,27 @@ extern "C" int spiral_lconv_pack(const float *w, void *packed_planes, int32_t n_
     else lpack_kernel<3><<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(p, w, (uint16_t *)packed_planes);
     const cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? SPIRAL_OK : spiral_cuda_error(e, "spiral_lconv_pack");
+}
+
+// The ACTING path's kernels (policy_conv.cu: one bf16 plane [round8(rows)][round16(taps * Ck) + 8], channels NOT padded,
+// rows channel-permuted when there are 32 of them) from the same strided gather -- one launch per layer when the actors pull
+// new weights (NativeActor.sync inside the learner step's CUDA graph) instead of a dozen indexing kernels.
+extern "C" int spiral_pconv_pack(const float *w, void *packed_bf16, int32_t rows, int32_t Ck, int32_t n_taps, int64_t s_row,
+                                 int64_t s_c, int64_t s_ky, int64_t s_kx, const int32_t *tap_ky, const int32_t *tap_kx,
+                                 int32_t permute_rows, void *stream)
+{
+    SPIRAL_REQUIRE(w); SPIRAL_REQUIRE(packed_bf16); SPIRAL_REQUIRE(tap_ky); SPIRAL_REQUIRE(tap_kx);
+    if (rows < 1 || rows > 32 || Ck < 1 || Ck > 32 || n_taps < 1 || n_taps > kLcMaxTaps || (permute_rows && rows != 32))
+        return spiral_set_error(SPIRAL_EINVAL, "pconv_pack: unsupported shape rows=%d Ck=%d taps=%d", rows, Ck, n_taps);
+    LPackParams p;
+    p.rows = rows; p.rows_pad = (rows + 7) & ~7; p.Ck = Ck; p.Ck_src = Ck; p.n_taps = n_taps; p.perm = permute_rows ? 1 : 0;
+    p.K = n_taps * Ck; p.KS = ((p.K + 15) & ~15) + 8;
+    p.s_row = s_row; p.s_c = s_c; p.s_ky = s_ky; p.s_kx = s_kx;
+    for (int i = 0; i < kLcMaxTaps; i++) { p.tap_ky[i] = i < n_taps ? tap_ky[i] : 0; p.tap_kx[i] = i < n_taps ? tap_kx[i] : 0; }
+    const int n = p.rows_pad * p.KS;
+    lpack_kernel<1><<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(p, w, (uint16_t *)packed_bf16);
+    const cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? SPIRAL_OK : spiral_cuda_error(e, "spiral_pconv_pack");
 }
 
 // the first-generation kernel: the discriminator's narrow layers (batch norm + leaky-ReLU on load, batch-norm partials)

@@ -13,6 +13,8 @@ module to ~1e-2, which only perturbs the actors' behaviour policy.
 """
 from __future__ import annotations
 
+import ctypes as C
+
 import torch
 import torch.nn.functional as F
 
@@ -20,42 +22,40 @@ from .. import _native as N
 from .policy import categorical_sample
 
 
-def _pack(w_khkwcico, permute):
-    """[KH,KW,Cin,Cout] fp32 -> bf16 [round8(Cout)][KP + 8], k = (ky*KW + kx)*Cin + c, zero padded."""
-    KH, KW, Cin, Cout = w_khkwcico.shape
-    K = KH * KW * Cin
-    KP = (K + 15) // 16 * 16
-    KS = KP + 8
-    cp = (Cout + 7) // 8 * 8
-    m = w_khkwcico.reshape(K, Cout).t().contiguous()                 # [Cout][K]
-    out = torch.zeros((cp, KS), dtype=torch.float32, device=m.device)
-    if permute:                                                      # row nt*8 + j holds channel (j>>1)*8 + nt*2 + (j&1)
-        rows = torch.arange(cp, device=m.device)
-        nt, j = rows // 8, rows % 8
-        ch = (j // 2) * 8 + nt * 2 + (j % 2)
-        out[:, :K] = m[ch]
-    else:
-        out[:Cout, :K] = m
-    return out.to(torch.bfloat16).contiguous()
-
-
 class _Conv(object):
-    """One launch of spiral_pconv_forward; weights packed from a torch Conv2d."""
+    """One launch of spiral_pconv_forward; the kernel packed by spiral_pconv_pack from a torch Conv2d weight (or any
+    [Cout, Cin, KH, KW]-indexed VIEW of one: the packer takes element strides and a tap list, so a transposed convolution's
+    parity class is the permuted view of its weight plus its four taps -- no copies, one launch per layer)."""
 
-    def __init__(self, weight_oihw, bias, stride, pad, relu, scatter=None):
-        w = weight_oihw.detach().permute(2, 3, 1, 0).contiguous().float()          # [KH,KW,Cin,Cout]
-        self.KH, self.KW, self.Cin, self.Cout = w.shape
+    def __init__(self, weight_oihw, bias, stride, pad, relu, scatter=None, taps=None):
+        self.Cout, self.Cin = int(weight_oihw.shape[0]), int(weight_oihw.shape[1])
+        if taps is None:
+            self.KH, self.KW = int(weight_oihw.shape[2]), int(weight_oihw.shape[3])
+            taps = [(ky, kx) for ky in range(self.KH) for kx in range(self.KW)]
+        else:
+            self.KH = self.KW = 2                                                    # a 2x2 parity class of a 4x4 kernel
+            assert len(taps) == 4
+        self._tap_ky = (C.c_int32 * len(taps))(*[t[0] for t in taps])
+        self._tap_kx = (C.c_int32 * len(taps))(*[t[1] for t in taps])
+        self._n_taps = len(taps)
         self.stride, self.pad_t, self.pad_l, self.relu = stride, pad[0], pad[1], int(relu)
-        self.wpk = _pack(w, self.Cout == 32)
-        self.bias = torch.zeros(((self.Cout + 7) // 8 * 8,), dtype=torch.float32, device=w.device)
-        self.bias[:self.Cout] = bias.detach().float()
+        K = self._n_taps * self.Cin
+        cp = (self.Cout + 7) // 8 * 8
+        dev = weight_oihw.device
+        self.wpk = torch.empty((cp, (K + 15) // 16 * 16 + 8), dtype=torch.bfloat16, device=dev)
+        self.bias = torch.zeros((cp,), dtype=torch.float32, device=dev)
         self.scatter = scatter                                                       # (sy, sx, oy, ox) for transposed-conv classes
+        self.repack(weight_oihw, bias)
 
     def repack(self, weight_oihw, bias):
         """Refresh the packed kernel IN PLACE (a captured CUDA graph keeps pointing at these buffers)."""
-        w = weight_oihw.detach().permute(2, 3, 1, 0).contiguous().float()
-        self.wpk.copy_(_pack(w, self.Cout == 32))
-        self.bias[:self.Cout].copy_(bias.detach().float())
+        w = weight_oihw.detach()
+        if w.dtype != torch.float32:
+            w = w.float()
+        st = w.stride()
+        N.check(N.lib().spiral_pconv_pack(N.ptr(w), N.ptr(self.wpk), self.Cout, self.Cin, self._n_taps, st[0], st[1], st[2], st[3],
+                                          self._tap_ky, self._tap_kx, int(self.Cout == 32), N.stream_ptr()), "spiral_pconv_pack")
+        self.bias[:self.Cout].copy_(bias.detach())
 
     def out_hw(self, Hin, Win, same):
         if same:
@@ -79,29 +79,20 @@ class _Deconv(object):
     x[a + (py + 1 - kk) / 2] * w[kk] (same along x)."""
 
     def __init__(self, weight_iohw, bias, relu):
-        w = weight_iohw.detach().float()                                             # [Cin, Cout, 4, 4]
         self.classes = []
+        w = weight_iohw.detach().permute(1, 0, 2, 3)                                 # [Cout, Cin, 4, 4] view
         for py in (0, 1):
             for px in (0, 1):
                 kys = (3, 1) if py == 0 else (2, 0)          # tap row 0, 1 of the 2x2 window (input rows a-1,a / a,a+1)
                 kxs = (3, 1) if px == 0 else (2, 0)
-                sub = w[:, :, kys, :][:, :, :, kxs]                                   # [Cin, Cout, 2, 2]
-                conv = _Conv(sub.permute(1, 0, 2, 3), bias, 1, (1 if py == 0 else 0, 1 if px == 0 else 0), relu,
-                             scatter=(2, 2, py, px))
+                conv = _Conv(w, bias, 1, (1 if py == 0 else 0, 1 if px == 0 else 0), relu, scatter=(2, 2, py, px),
+                             taps=[(ky, kx) for ky in kys for kx in kxs])
                 self.classes.append(conv)
 
     def repack(self, weight_iohw, bias):
-        w = weight_iohw.detach().float()
-        i = 0
-        for py in (0, 1):
-            for px in (0, 1):
-                kys = (3, 1) if py == 0 else (2, 0)
-                kxs = (3, 1) if px == 0 else (2, 0)
-                # slices, not index lists: an index list is a host tensor copied to the device on every call, which a
-                # CUDA-graph capture of the learner step (Agent.train_policy) cannot record
-                sub = torch.stack([torch.stack([w[:, :, ky, kx] for kx in kxs], -1) for ky in kys], -2)   # [Cin, Cout, 2, 2]
-                self.classes[i].repack(sub.permute(1, 0, 2, 3), bias)
-                i += 1
+        w = weight_iohw.detach().permute(1, 0, 2, 3)
+        for conv in self.classes:
+            conv.repack(w, bias)
 
     def __call__(self, x, out):
         B, Hin, Win, _ = x.shape
