@@ -392,12 +392,14 @@ int spiral_lconv_pack(const float *w_dev, void *packed_planes_dev, int32_t n_pla
                       void *stream);
 /* out[b, oy*o_sy + o_oy, ox*o_sx + o_ox, co] = bias[co] + sum_{ky,kx,c} x[b, oy*stride - pad_t + ky, ox*stride - pad_l + kx, c]
  *                                                                        * packed[co][(ky*KW + kx)*Cin + c]
- * for oy < Hout, ox < Wout (positions outside [oH, oW] are skipped, input positions outside the map read 0).  x f32
- * [B,Hin,Win,Cin] NHWC, out f32 [B,oH,oW,Cout]; Cin in {1,2,3,6,16,32}, Cout <= 32; bias may be NULL. */
+ * for oy < Hout, ox < Wout (positions outside [oH, oW] are skipped, input positions outside the map read 0), then max(., 0)
+ * when relu != 0.  x f32 [B,Hin,Wi,Cin] NHWC, out f32 [B,oH,oW,Cout]; Cin in {1,2,3,6,8,16,32} (counts below 8 are padded to 8
+ * inside), Cout <= 32; bias may be NULL.  n_planes selects the operand format: 4 = f16x3 (two fp16 planes, three
+ * products), 3 = bf16x6, 2 = bf16x3; w_planes must come from spiral_lconv_pack with the same value. */
 int spiral_lconv_forward(const float *x_dev, const void *w_planes_dev, int32_t n_planes, const float *bias_dev, float *out_dev,
                          int32_t B, int32_t Hin, int32_t Win, int32_t Cin, int32_t Hout, int32_t Wout, int32_t Cout,
                          int32_t KH, int32_t KW, int32_t stride, int32_t pad_t, int32_t pad_l, int32_t oH, int32_t oW,
-                         int32_t o_sy, int32_t o_sx, int32_t o_oy, int32_t o_ox, void *stream);
+                         int32_t o_sy, int32_t o_sx, int32_t o_oy, int32_t o_ox, int32_t relu, void *stream);
 /* dw[(ky*KW + kx)*Cin + c][co] = sum_{b,oy,ox} x[b, oy*stride - pad_t + ky, ox*stride - pad_l + kx, c] * dy[b, oy, ox, co];
  * dy f32 [B,Hout,Wout,Cout], dw f32 [KH*KW*Cin, Cout]; workspace: spiral_lconv_wgrad_workspace_floats() floats. */
 int64_t spiral_lconv_wgrad_workspace_floats(int32_t Cin, int32_t Cout, int32_t n_taps);

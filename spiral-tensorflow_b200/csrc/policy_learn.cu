@@ -44,6 +44,7 @@ struct LConvParams {
     int tw, th, fr, mt_rows;                     // tw = 16 or 8; mt_rows = 16 / tw rows per 16-pixel m-tile; th a power of two
     int th_log;
     int n_in;                                    // halfwords per plane of the staged input tile (multiple of 64)
+    int relu;                                    // forward epilogue: max(v, 0) after the bias (tf.nn.relu of the layer's activation)
     int dy_pitch, dy_c0;                         // wgrad: dy is [.., dy_pitch] channels per pixel, this launch takes [dy_c0, dy_c0 + Cout)
 };
 
@@ -460,17 +461,23 @@ constexpr int kLwPix = kLcTw * kLcTh;            // 128 reduction elements per i
 
 // dw[k][co] (k < K, co < Cout) = sum over CTAs, fixed order
 // (cin < cin_pad: the partials' k index is tap * cin_pad + c, dw's is tap * cin + c)
+// Eight lanes per output: lane j adds the CTAs j, j + 8, ... in order, the eight sums are combined as a fixed tree.
 __global__ void __launch_bounds__(256)
 lwgrad_reduce_kernel(const float *__restrict__ partial, float *__restrict__ dw, int n_cta, int K, int KP, int Cout, int CoutPad,
                      int cin = 1, int cin_pad = 1, int ld = 0, int co0 = 0)    // dw[k][ld] columns [co0, co0 + Cout); ld 0: Cout
 {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= K * Cout) return;
-    const int k = i / Cout, co = i - k * Cout;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = t >> 3, j = t & 7;
+    const bool ok = i < K * Cout;                                             // whole groups of 8 lanes agree
+    const int k = ok ? i / Cout : 0, co = ok ? i - k * Cout : 0;
     const int kp = (k / cin) * cin_pad + k % cin;
     float s = 0.0f;
-    for (int c = 0; c < n_cta; c++) s += partial[((size_t)c * KP + kp) * CoutPad + co];
-    dw[(size_t)k * (ld ? ld : Cout) + co0 + co] = s;
+    if (ok)
+        for (int c = j; c < n_cta; c += 8) s += partial[((size_t)c * KP + kp) * CoutPad + co];
+    s += __shfl_xor_sync(0xffffffffu, s, 1);
+    s += __shfl_xor_sync(0xffffffffu, s, 2);
+    s += __shfl_xor_sync(0xffffffffu, s, 4);
+    if (ok && j == 0) dw[(size_t)k * (ld ? ld : Cout) + co0 + co] = s;
 }
 
 
@@ -715,6 +722,7 @@ lconv2_kernel(const __grid_constant__ LConvParams p, const float *__restrict__ x
                     if (ch < p.Cout) v0 += __ldg(bias + ch);
                     if (ch + 1 < p.Cout) v1 += __ldg(bias + ch + 1);
                 }
+                if (p.relu) { v0 = fmaxf(v0, 0.0f); v1 = fmaxf(v1, 0.0f); }
                 if ((p.Cout & 1) == 0 && ch + 1 < p.Cout) {
                     *reinterpret_cast<float2 *>(out + pix * p.Cout + ch) = make_float2(v0, v1);
                 } else {
@@ -945,7 +953,7 @@ static void lc_fill(LConvParams &p, int B, int Hin, int Win, int Cin, int Hout, 
     p.tiles_x = (Wout + kLcTw - 1) / kLcTw; p.tiles_y = (Hout + kLcTh - 1) / kLcTh;
     p.oH = oH; p.oW = oW; p.o_sy = o_sy; p.o_sx = o_sx; p.o_oy = o_oy; p.o_ox = o_ox;
     p.tw = kLcTw; p.th = kLcTh; p.fr = 1; p.mt_rows = 1; p.th_log = 3; p.n_in = 0;
-    p.dy_pitch = Cout; p.dy_c0 = 0;
+    p.dy_pitch = Cout; p.dy_c0 = 0; p.relu = 0;
 }
 
 // tile of the v2 kernels: `rows` = output rows a CTA covers over all its frames (8 warps x m-tiles per warp x mt_rows)
@@ -1107,7 +1115,7 @@ static int lconv2_launch_mt(int mt, const LConvParams &p, const float *x, const 
 extern "C" int spiral_lconv_forward(const float *x, const void *w_planes, int32_t n_planes, const float *bias, float *out,
                                     int32_t B, int32_t Hin, int32_t Win, int32_t Cin, int32_t Hout, int32_t Wout, int32_t Cout,
                                     int32_t KH, int32_t KW, int32_t stride, int32_t pad_t, int32_t pad_l, int32_t oH,
-                                    int32_t oW, int32_t o_sy, int32_t o_sx, int32_t o_oy, int32_t o_ox, void *stream)
+                                    int32_t oW, int32_t o_sy, int32_t o_sx, int32_t o_oy, int32_t o_ox, int32_t relu, void *stream)
 {
     SPIRAL_REQUIRE(x); SPIRAL_REQUIRE(w_planes); SPIRAL_REQUIRE(out);
     if (B <= 0 || Cout <= 0 || Cout > 32 || !lc_cin_ok(Cin) || KH * KW > kLcMaxTaps || !lc_prec_ok(n_planes))
@@ -1115,6 +1123,7 @@ extern "C" int spiral_lconv_forward(const float *x, const void *w_planes, int32_
     const int CinP = lc_cin_pad(Cin);
     LConvParams p;
     lc_fill(p, B, Hin, Win, CinP, Hout, Wout, Cout, KH, KW, stride, pad_t, pad_l, oH, oW, o_sy, o_sx, o_oy, o_ox);
+    p.relu = relu ? 1 : 0;
     cudaStream_t st = (cudaStream_t)stream;
     const int npl = lc_prec_planes(n_planes);
     const size_t n_w = (size_t)p.CoutPad * p.KS;
@@ -1190,7 +1199,7 @@ int lwgrad2_image_layer(const float *x, const float *dy, float *dw, float *works
         const int grid = n_items < 148 ? n_items : 148;
         LC2_DISPATCH(lwgrad2_launch, p, x, dy, workspace, n_items, grid, smem, st);
         const int n = 25 * Cin * 32;
-        lwgrad_reduce_kernel<<<(n + 255) / 256, 256, 0, st>>>(workspace, dw, grid, 25 * Cin, p.KP, 32, p.CoutPad, Cin, CinP, Cout, c0);
+        lwgrad_reduce_kernel<<<(n * 8 + 255) / 256, 256, 0, st>>>(workspace, dw, grid, 25 * Cin, p.KP, 32, p.CoutPad, Cin, CinP, Cout, c0);
     }
     const cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? SPIRAL_OK : spiral_cuda_error(e, "lwgrad2_image_layer");
@@ -1233,7 +1242,7 @@ extern "C" int spiral_lconv_wgrad(const float *x, const float *dy, float *dw, fl
     const int grid = n_items < 148 ? n_items : 148;
     LC2_DISPATCH(lwgrad2_launch, p, x, dy, workspace, n_items, grid, smem, st);
     const int n = KH * KW * Cin * Cout;
-    lwgrad_reduce_kernel<<<(n + 255) / 256, 256, 0, st>>>(workspace, dw, grid, KH * KW * Cin, p.KP, Cout, p.CoutPad, Cin, CinP);
+    lwgrad_reduce_kernel<<<(n * 8 + 255) / 256, 256, 0, st>>>(workspace, dw, grid, KH * KW * Cin, p.KP, Cout, p.CoutPad, Cin, CinP);
     const cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? SPIRAL_OK : spiral_cuda_error(e, "spiral_lconv_wgrad");
 }

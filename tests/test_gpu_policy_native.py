@@ -224,7 +224,11 @@ def _check_learner(monkeypatch, envname, L, C, T, conditional, B, smooth=False):
     for n in pi.acs:
         assert _rel(fnat[0][n], f64[0][n]) < 1e-4 and _rel(fnat[0][n], f32[0][n]) < 1e-4, n
     assert _rel(fnat[1], f64[1]) < 1e-4 and _rel(fnat[1], f32[1]) < 1e-4
-    # gradients, with the activation pattern pinned to the float64 run's
+    # gradients, with the activation pattern pinned to the float64 run's (the kernels' fused ReLU epilogue is switched off so
+    # that every ReLU goes through F.relu; test_learner_fused_relu_is_bit_identical ties the fused path to this one)
+    import spiral_b200 as sp
+    from importlib import import_module
+    monkeypatch.setattr(import_module(sp.__name__ + ".models.policy_learn"), "FUSE_RELU", False)
     pinned = _PinnedRelu()
     if not smooth:
         monkeypatch.setattr(torch.nn.functional, "relu", pinned)
@@ -274,6 +278,25 @@ def test_learner_gradients_on_a_smooth_network(monkeypatch, strict_fp32):
     """The same comparison with the ReLUs replaced by softplus (no kinks for rounding to flip): every forward, input-
     gradient and weight-gradient kernel in its place in the graph."""
     _check_learner(monkeypatch, "color_mnist", 64, 3, 2, False, 2, smooth=True)
+
+
+def test_learner_fused_relu_is_bit_identical(monkeypatch, strict_fp32):
+    """ReLU in the convolution's epilogue + its mask from the saved output (policy_learn.FUSE_RELU, the default) against
+    F.relu around the same kernels: logits, value and every parameter gradient bit for bit."""
+    import spiral_b200 as sp
+    from importlib import import_module
+    pl = import_module(sp.__name__ + ".models.policy_learn")
+    pi, inp, _ = _learner_case("color_mnist", 64, 3, 2, False, 2)
+    monkeypatch.setattr(pl, "FUSE_RELU", True)
+    fused = _run_learner(pi, inp, True)
+    monkeypatch.setattr(pl, "FUSE_RELU", False)
+    plain = _run_learner(pi, inp, True)
+    for n in pi.acs:
+        assert torch.equal(fused[0][n], plain[0][n]), n
+    assert torch.equal(fused[1], plain[1])
+    assert set(fused[2]) == set(plain[2])
+    for k in plain[2]:
+        assert torch.equal(fused[2][k], plain[2][k]), k
 
 
 def test_learner_convolution_primitives_match_torch(strict_fp32):
