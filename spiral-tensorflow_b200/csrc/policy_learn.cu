@@ -497,6 +497,9 @@ lwgrad_reduce_kernel(const float *__restrict__ partial, float *__restrict__ dw, 
 //   * the kernel planes arrive by cp.async while the input tile is converted
 //   * operand format f16x3 (above) next to bf16x3 / bf16x6
 // ==========================================================================================
+#ifndef LC2_STAGE_U
+#define LC2_STAGE_U 8
+#endif
 __device__ __forceinline__ int lc_swz(int L) { return (L & ~7) | ((L ^ (L >> 3)) & 7); }
 
 // stage the box [fr frames][RH rows][RW columns] of an NHWC fp32 tensor [., H, W, CSRC] starting at (y0, x0) of frame 0 of
@@ -512,7 +515,7 @@ __device__ __forceinline__ void lc2_stage(const float *__restrict__ src, size_t 
     const int rows = fr * RH;
     if (CSRC == C) {
         constexpr int V = C / 4;                                               // float4 per pixel
-        constexpr int U = 8;                                                   // loads in flight per thread
+        constexpr int U = LC2_STAGE_U;                                         // loads in flight per thread
         const int rowlen = RW * V;
         for (int gr = warp; gr < rows; gr += 8) {
             const int f = gr / RH, ly = gr - f * RH;
