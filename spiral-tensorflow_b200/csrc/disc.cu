@@ -384,7 +384,7 @@ void disc_plan(const SpiralDisc *d, int batch, DiscPlan *pl)
         pl->scale_off[l] = off; off += disc_align((size_t)Cout * sizeof(float));
         pl->shift_off[l] = off; off += disc_align((size_t)Cout * sizeof(float));
         pl->pack_off[l] = off;
-        if (l > 0 && lconv_disc_layer_supported(Cin, Cout)) off += disc_align(lconv_disc_pack_bytes(Cin, Cout));
+        if (lconv_disc_layer_supported(Cin, Cout)) off += disc_align(lconv_disc_pack_bytes(Cin, Cout));
         H = Ho; Cin = Cout;
     }
     pl->simt_bytes = off;
@@ -434,7 +434,14 @@ int disc_forward_simt(SpiralDisc *d, const float *x, int batch, float *logits, f
         float *part = (float *)(ws + pl.part_off[l]);
         const bool bn = l > 0 && d->cfg.batch_norm;
         int n_part = pl.mtiles[l];                   // rows of the batch-norm partials this layer's kernel writes
-        if (l == 0) {
+        if (l == 0 && lconv_disc_layer_supported(Cin, Cout)) {
+            // image layer: normalisation (x - 127.5) / 127.5 applied while the tile is staged ('SAME' pads the normalised image)
+            const bool nz = d->cfg.normalize != 0;
+            const int rc = lconv_disc_layer(x, nz ? 2 : 0, nullptr, nullptr, 1.0f / 127.5f, -1.0f, (const float *)W.conv_w[0],
+                                            (const float *)W.conv_b[0], out, nullptr, ws + pl.pack_off[0], batch, H, Cin, Cout,
+                                            &n_part, st);
+            if (rc != SPIRAL_OK) return rc;
+        } else if (l == 0) {
             const int rc = disc_conv0(d, x, batch, out, nullptr, nullptr, st);
             if (rc != SPIRAL_OK) return rc;
         } else {
@@ -442,9 +449,9 @@ int disc_forward_simt(SpiralDisc *d, const float *x, int batch, float *logits, f
             const float *isc = (const float *)(ws + pl.scale_off[l - 1]);
             const float *ish = (const float *)(ws + pl.shift_off[l - 1]);
             if (lconv_disc_layer_supported(Cin, Cout)) {
-                // narrow layer (disc_dim 8 / 16): the mma.sync implicit GEMM of policy_learn.cu, bf16x6
-                const int rc = lconv_disc_layer(in, isc, ish, (const float *)W.conv_w[l], (const float *)W.conv_b[l], out,
-                                                bn ? part : nullptr, ws + pl.pack_off[l], batch, H, Cin, Cout, &n_part, st);
+                // narrow layer (Cin <= 32, Cout <= 128): the mma.sync implicit GEMM of policy_learn.cu (lconv2_kernel, f16x3)
+                const int rc = lconv_disc_layer(in, 1, isc, ish, 0.0f, 0.0f, (const float *)W.conv_w[l], (const float *)W.conv_b[l],
+                                                out, bn ? part : nullptr, ws + pl.pack_off[l], batch, H, Cin, Cout, &n_part, st);
                 if (rc != SPIRAL_OK) return rc;
             } else {
                 dim3 grid(pl.mtiles[l], (Cout + 63) / 64);

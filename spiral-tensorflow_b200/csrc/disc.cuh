@@ -46,9 +46,9 @@ int disc_conv0(SpiralDisc *d, const float *x, int batch, float *out, void *out_h
 // narrow layers (disc_dim 8 / 16) on the mma.sync implicit GEMM of policy_learn.cu
 bool lconv_disc_layer_supported(int Cin, int Cout);
 size_t lconv_disc_pack_bytes(int Cin, int Cout);
-int lconv_disc_layer(const float *in, const float *in_scale, const float *in_shift, const float *w_hwio, const float *bias,
-                     float *out, float *bn_partial, void *pack_scratch, int B, int H, int Cin, int Cout, int *n_part,
-                     cudaStream_t st);
+int lconv_disc_layer(const float *in, int in_mode, const float *in_scale, const float *in_shift, float in_a, float in_b,
+                     const float *w_hwio, const float *bias, float *out, float *bn_partial, void *pack_scratch, int B, int H,
+                     int Cin, int Cout, int *n_part, cudaStream_t st);
 
 // layer 0 on tensor cores (disc_conv0_mma.cu)
 size_t conv0_mma_pack_bytes(int Cin);

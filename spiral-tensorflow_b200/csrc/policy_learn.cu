@@ -23,6 +23,7 @@
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <string.h>
 
 #include "../../include/spiral_b200.h"
 #include "common.h"
@@ -44,8 +45,23 @@ struct LConvParams {
     int tw, th, fr, mt_rows;                     // tw = 16 or 8; mt_rows = 16 / tw rows per 16-pixel m-tile; th a power of two
     int th_log;
     int n_in;                                    // halfwords per plane of the staged input tile (multiple of 64)
+    uint32_t mIH, mIW, mTH, mTW;                 // lc_magic of IH, IW (input tile) and th, tw (wgrad's dy tile)
     int relu;                                    // forward epilogue: max(v, 0) after the bias (tf.nn.relu of the layer's activation)
     int dy_pitch, dy_c0;                         // wgrad: dy is [.., dy_pitch] channels per pixel, this launch takes [dy_c0, dy_c0 + Cout)
+};
+
+// What the discriminator's narrow layers need on top of a plain convolution (lconv2_kernel<..., XF = true>): the producer
+// layer's batch norm + leaky-ReLU applied to the input while it is staged (in_mode 1: v <- lrelu(v * scale[c] + shift[c],
+// 0.2), disc.cu's convention: a layer stores its RAW output and the consumer normalises), or the image normalisation of layer
+// 0 (in_mode 2: v <- v * in_a + in_b); padding stays zero in the transformed space, as 'SAME' padding pads the activation.
+// Output columns [out_c0, out_c0 + Cout) of an [.., out_ld]-channel map, and per-CTA batch-norm partials
+// bn_partial[cta][bn_ld][2] = (sum, sum of squares) of this launch's raw outputs per channel.
+struct LConvExtra {
+    const float *in_scale, *in_shift;
+    float in_a, in_b;
+    int in_mode;
+    float *bn_partial;
+    int out_ld, out_c0, bn_ld;
 };
 
 __device__ __forceinline__ void lc_mma(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2])
@@ -206,251 +222,6 @@ lpack_kernel(const __grid_constant__ LPackParams p, const float *__restrict__ w,
 }
 
 // ------------------------------------------------------------------------------------------
-// forward / dgrad: out[frame, scatter(oy, ox), co] = bias[co] + sum_k x[frame, oy*stride - pad + ky, ox*stride - pad + kx, c] * W[co][k]
-// ------------------------------------------------------------------------------------------
-// stage an fp32 NHWC input tile (zero outside the map) as NPL bf16 planes s_i[q][IH][IW][CIN]
-// in_scale / in_shift (optional, per input channel): v <- leaky_relu(v * scale + shift, 0.2) on load -- the batch norm and
-// activation of the PRODUCER layer, as the discriminator's kernels apply them (disc.cu); padding stays zero
-template <int CIN, int NPL>
-__device__ __forceinline__ void lc_stage_input(const LConvParams &p, const float *__restrict__ xi, int iy0, int ix0,
-                                               uint16_t *s_i, int n_in8, int tid, const float *__restrict__ in_scale = nullptr,
-                                               const float *__restrict__ in_shift = nullptr)
-{
-    if (CIN % 4 == 0) {
-        constexpr int V = CIN / 4 > 0 ? CIN / 4 : 1;                           // float4 per pixel
-        constexpr int U = 4;                                                   // loads in flight per thread: the staging is
-        const int n_vec = p.IH * p.IW * V;                                     // latency-bound (8 warps per SM), not bandwidth-bound
-        for (int i0 = tid; i0 < n_vec; i0 += 256 * U) {
-            float4 val[U];
-#pragma unroll
-            for (int u = 0; u < U; u++) {
-                const int i = i0 + u * 256;
-                val[u] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-                if (i < n_vec) {
-                    const int pix = i / V, v = i - pix * V;
-                    const int ly = pix / p.IW, lx = pix - ly * p.IW;
-                    const int iy = iy0 + ly, ix = ix0 + lx;
-                    if (iy >= 0 && iy < p.Hin && ix >= 0 && ix < p.Win) {
-                        val[u] = __ldg(reinterpret_cast<const float4 *>(xi + ((size_t)iy * p.Win + ix) * CIN) + v);
-                        if (in_scale) {
-                            const float4 sc = __ldg(reinterpret_cast<const float4 *>(in_scale) + v);
-                            const float4 sh = __ldg(reinterpret_cast<const float4 *>(in_shift) + v);
-                            float4 &q = val[u];
-                            q.x = fmaf(q.x, sc.x, sh.x); q.y = fmaf(q.y, sc.y, sh.y); q.z = fmaf(q.z, sc.z, sh.z); q.w = fmaf(q.w, sc.w, sh.w);
-                            q.x = q.x > 0.f ? q.x : 0.2f * q.x; q.y = q.y > 0.f ? q.y : 0.2f * q.y;
-                            q.z = q.z > 0.f ? q.z : 0.2f * q.z; q.w = q.w > 0.f ? q.w : 0.2f * q.w;
-                        }
-                    }
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < U; u++) {
-                const int i = i0 + u * 256;
-                if (i < n_vec) {
-                    uint16_t a[NPL], b[NPL], c[NPL], d[NPL];
-                    lc_split<NPL>(val[u].x, a); lc_split<NPL>(val[u].y, b); lc_split<NPL>(val[u].z, c); lc_split<NPL>(val[u].w, d);
-#pragma unroll
-                    for (int q = 0; q < NPL; q++)
-                        *reinterpret_cast<uint2 *>(s_i + (size_t)q * n_in8 + (size_t)i * 4) =
-                            make_uint2(a[q] | ((uint32_t)b[q] << 16), c[q] | ((uint32_t)d[q] << 16));
-                }
-            }
-        }
-    } else {
-        const int n_in = p.IH * p.IW * CIN;
-        constexpr int U = 8;
-        for (int i0 = tid; i0 < n_in; i0 += 256 * U) {
-            float val[U];
-#pragma unroll
-            for (int u = 0; u < U; u++) {
-                const int i = i0 + u * 256;
-                val[u] = 0.0f;
-                if (i < n_in) {
-                    const int pix = i / CIN, c = i - pix * CIN;
-                    const int ly = pix / p.IW, lx = pix - ly * p.IW;
-                    const int iy = iy0 + ly, ix = ix0 + lx;
-                    if (iy >= 0 && iy < p.Hin && ix >= 0 && ix < p.Win) val[u] = __ldg(xi + ((size_t)iy * p.Win + ix) * CIN + c);
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < U; u++) {
-                const int i = i0 + u * 256;
-                if (i < n_in) {
-                    uint16_t pl[NPL];
-                    lc_split<NPL>(val[u], pl);
-#pragma unroll
-                    for (int q = 0; q < NPL; q++) s_i[(size_t)q * n_in8 + i] = pl[q];
-                }
-            }
-        }
-    }
-}
-
-__device__ __forceinline__ void lc_koff_table(const LConvParams &p, int cin, int *s_koff, int tid)
-{
-    for (int k = tid; k < p.KP; k += 256) {
-        int off = 0;
-        if (k < p.K) {
-            const int tap = k / cin, c = k - tap * cin;
-            const int ky = tap / p.KW, kx = tap - ky * p.KW;
-            off = (ky * p.IW + kx) * cin + c;
-        }
-        s_koff[k] = off;
-    }
-}
-
-template <int CIN, int NPL>
-__global__ void __launch_bounds__(256)
-lconv_kernel(const __grid_constant__ LConvParams p, const float *__restrict__ x, const uint16_t *__restrict__ w_planes,
-             const float *__restrict__ bias, float *__restrict__ out, const float *__restrict__ in_scale,
-             const float *__restrict__ in_shift, float *__restrict__ bn_partial)
-{
-    extern __shared__ __align__(16) uint8_t sm_raw[];
-    __shared__ float s_bn[8][32][2];                                           // per warp, per channel: (sum, sum of squares)
-    const int n_w = p.CoutPad * p.KS;                                          // multiple of 8 (KS is)
-    const int n_in8 = (p.IH * p.IW * CIN + 7) & ~7;
-    uint16_t *s_w = reinterpret_cast<uint16_t *>(sm_raw);                     // [NPL][CoutPad][KS]
-    uint16_t *s_i = s_w + NPL * n_w;                                           // [NPL][IH][IW][CIN]
-    int *s_koff = reinterpret_cast<int *>(s_i + NPL * n_in8);                  // [KP]
-
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int tiles = p.tiles_x * p.tiles_y;
-    const int img = blockIdx.x / tiles;
-    const int trem = blockIdx.x % tiles;
-    const int oy0 = (trem / p.tiles_x) * kLcTh, ox0 = (trem % p.tiles_x) * kLcTw;
-
-    {
-        const uint4 *gw = reinterpret_cast<const uint4 *>(w_planes);
-        uint4 *sw = reinterpret_cast<uint4 *>(s_w);
-        for (int i = tid; i < NPL * n_w / 8; i += 256) sw[i] = __ldg(gw + i);
-        lc_koff_table(p, CIN, s_koff, tid);
-        lc_stage_input<CIN, NPL>(p, x + (size_t)img * p.Hin * p.Win * CIN, oy0 * p.stride - p.pad_t, ox0 * p.stride - p.pad_l,
-                                 s_i, n_in8, tid, in_scale, in_shift);
-    }
-    __syncthreads();
-
-    // warp = output row `warp` of the tile, 16 pixels x CoutPad channels
-    const int g = lane >> 2, t = lane & 3;
-    const int base0 = ((warp * p.stride) * p.IW + g * p.stride) * CIN;         // pixel g
-    const int base1 = base0 + 8 * p.stride * CIN;                               // pixel g + 8
-    const int NT = p.CoutPad >> 3;
-    float acc[4][4], acl[4][4];
-#pragma unroll
-    for (int nt = 0; nt < 4; nt++)
-#pragma unroll
-        for (int j = 0; j < 4; j++) { acc[nt][j] = 0.0f; acl[nt][j] = 0.0f; }
-
-#pragma unroll 1
-    for (int ks = 0; ks < p.KP / 16; ks++) {
-        const int k0 = ks * 16 + 2 * t;
-        uint32_t a[NPL][4];
-        if (CIN % 2 == 0) {
-            // k0 is even and CIN is even: k0 and k0+1 are adjacent channels of one tap -> one 32-bit load
-            const int o0 = s_koff[k0], o8 = s_koff[k0 + 8];
-            SP_CHECK(k0 + 9 < p.KP + 8 && base1 + o8 + 1 < n_in8 && base0 + o0 >= 0);
-#pragma unroll
-            for (int q = 0; q < NPL; q++) {
-                const uint16_t *si = s_i + (size_t)q * n_in8;
-                a[q][0] = *reinterpret_cast<const uint32_t *>(si + base0 + o0);
-                a[q][1] = *reinterpret_cast<const uint32_t *>(si + base1 + o0);
-                a[q][2] = *reinterpret_cast<const uint32_t *>(si + base0 + o8);
-                a[q][3] = *reinterpret_cast<const uint32_t *>(si + base1 + o8);
-            }
-        } else {
-            const int o0 = s_koff[k0], o1 = s_koff[k0 + 1], o8 = s_koff[k0 + 8], o9 = s_koff[k0 + 9];
-            SP_CHECK(k0 + 9 < p.KP && base1 + o9 < n_in8 && base1 + o1 < n_in8 && base0 + o0 >= 0);
-#pragma unroll
-            for (int q = 0; q < NPL; q++) {
-                const uint16_t *si = s_i + (size_t)q * n_in8;
-                a[q][0] = (uint32_t)si[base0 + o0] | ((uint32_t)si[base0 + o1] << 16);
-                a[q][1] = (uint32_t)si[base1 + o0] | ((uint32_t)si[base1 + o1] << 16);
-                a[q][2] = (uint32_t)si[base0 + o8] | ((uint32_t)si[base0 + o9] << 16);
-                a[q][3] = (uint32_t)si[base1 + o8] | ((uint32_t)si[base1 + o9] << 16);
-            }
-        }
-        // k padding: the packed kernel is zero there and the gathered activations are finite values of the tile
-#pragma unroll
-        for (int nt = 0; nt < 4; nt++) {
-            if (nt < NT) {
-                const int wrow = (nt * 8 + g) * p.KS + k0;
-                uint32_t b[NPL][2];
-#pragma unroll
-                for (int q = 0; q < NPL; q++) {
-                    b[q][0] = *reinterpret_cast<const uint32_t *>(s_w + (size_t)q * n_w + wrow);
-                    b[q][1] = *reinterpret_cast<const uint32_t *>(s_w + (size_t)q * n_w + wrow + 8);
-                }
-                lc_mma_planes<NPL>(acc[nt], acl[nt], a, b);
-            }
-        }
-    }
-#pragma unroll
-    for (int nt = 0; nt < 4; nt++)
-#pragma unroll
-        for (int j = 0; j < 4; j++) acc[nt][j] += acl[nt][j];
-
-    const int oy = oy0 + warp;
-    const int py = oy * p.o_sy + p.o_oy;
-    const bool row_ok = oy < p.Hout && py >= 0 && py < p.oH;
-    const size_t frame_out = (size_t)img * p.oH * p.oW;
-    float bs[4][2], bq[4][2];                                                  // batch-norm partials of this thread's channels
-#pragma unroll
-    for (int nt = 0; nt < 4; nt++) { bs[nt][0] = bs[nt][1] = bq[nt][0] = bq[nt][1] = 0.0f; }
-#pragma unroll
-    for (int half = 0; half < 2; half++) {
-        const int ox = ox0 + g + 8 * half;
-        const int px = ox * p.o_sx + p.o_ox;
-        if (!row_ok || ox >= p.Wout || px < 0 || px >= p.oW) continue;
-        const size_t pix = frame_out + (size_t)py * p.oW + px;
-        SP_CHECK(img >= 0 && img < p.B && pix < (size_t)p.B * p.oH * p.oW);
-#pragma unroll
-        for (int nt = 0; nt < 4; nt++) {
-            if (nt >= NT) continue;
-            const int ch = nt * 8 + 2 * t;
-            float v0 = acc[nt][2 * half], v1 = acc[nt][2 * half + 1];
-            if (bias) {
-                if (ch < p.Cout) v0 += __ldg(bias + ch);
-                if (ch + 1 < p.Cout) v1 += __ldg(bias + ch + 1);
-            }
-            bs[nt][0] += v0; bq[nt][0] += v0 * v0;
-            bs[nt][1] += v1; bq[nt][1] += v1 * v1;
-            if ((p.Cout & 1) == 0 && ch + 1 < p.Cout) {
-                *reinterpret_cast<float2 *>(out + pix * p.Cout + ch) = make_float2(v0, v1);
-            } else {
-                if (ch < p.Cout) out[pix * p.Cout + ch] = v0;
-                if (ch + 1 < p.Cout) out[pix * p.Cout + ch + 1] = v1;
-            }
-        }
-    }
-    if (bn_partial) {
-        // per-CTA per-channel (sum, sum of squares) of the raw outputs for this layer's batch norm (fixed order: lanes of a
-        // warp by shuffles, warps through shared memory), written as partial[cta][Cout][2] like conv_simt_kernel does
-#pragma unroll
-        for (int nt = 0; nt < 4; nt++)
-#pragma unroll
-            for (int e = 0; e < 2; e++) {
-#pragma unroll
-                for (int off = 4; off < 32; off <<= 1) {
-                    bs[nt][e] += __shfl_xor_sync(0xffffffffu, bs[nt][e], off);
-                    bq[nt][e] += __shfl_xor_sync(0xffffffffu, bq[nt][e], off);
-                }
-                if (g == 0 && nt < NT) {
-                    s_bn[warp][nt * 8 + 2 * t + e][0] = bs[nt][e];
-                    s_bn[warp][nt * 8 + 2 * t + e][1] = bq[nt][e];
-                }
-            }
-        __syncthreads();
-        if (tid < p.Cout) {
-            float sum = 0.0f, sq = 0.0f;
-#pragma unroll
-            for (int w = 0; w < 8; w++) { sum += s_bn[w][tid][0]; sq += s_bn[w][tid][1]; }
-            float *dst = bn_partial + ((size_t)blockIdx.x * p.Cout + tid) * 2;
-            dst[0] = sum;
-            dst[1] = sq;
-        }
-    }
-}
-
-// ------------------------------------------------------------------------------------------
 // wgrad: dW[k = tap * CIN + c][co] = sum_{frame, oy, ox} x[frame, oy*stride - pad + ky, ox*stride - pad + kx, c] * dy[frame, oy, ox, co]
 // (lwgrad2_kernel below).  Persistent CTAs walk work items of 128 output pixels; warp w owns the m-tiles (16 rows of k)
 // w, w + 8, ... and keeps their accumulators in registers across all items; partial[cta][k][co] at the end, reduced over
@@ -502,88 +273,114 @@ lwgrad_reduce_kernel(const float *__restrict__ partial, float *__restrict__ dw, 
 #endif
 __device__ __forceinline__ int lc_swz(int L) { return (L & ~7) | ((L ^ (L >> 3)) & 7); }
 
+// n / d for n < 2^16 with the host-computed magic m = ceil(2^32 / d) (d >= 2): exact, two instructions
+__device__ __forceinline__ int lc_fastdiv(int n, uint32_t m) { return (int)__umulhi((uint32_t)n, m); }
+static uint32_t lc_magic(int d) { return (uint32_t)((0x100000000ull + (uint64_t)d - 1) / (uint64_t)d); }
+
 // stage the box [fr frames][RH rows][RW columns] of an NHWC fp32 tensor [., H, W, CSRC] starting at (y0, x0) of frame 0 of
 // `src` (zero outside the map and for frames >= frames_left) as NPL swizzled planes [pixel][C] of n_plane halfwords.
 // CSRC == C: float4 loads.  CSRC < C = 8 (1, 2, 3 or 6 image / scalar-map channels): the pixel's channels are padded with
 // zeros to one 16-byte chunk, so these layers run on the same kernels (the padded k rows meet zero kernel columns).
-template <int CSRC, int C, int NPL, bool F16>
+// The box is walked as ONE flat list by all 256 threads, up to eight loads in flight per thread: a tile is a few thousand
+// float4, and staging it is latency-bound -- row-per-warp loops serialised three to nine round trips where this takes one
+// to five.  (mRW, mRH: lc_magic of RW, RH; the box has < 2^16 pixels.)
+template <int CSRC, int C, int NPL, bool F16, bool XF = false>
 __device__ __forceinline__ void lc2_stage(const float *__restrict__ src, size_t frame_elems, int frames_left, int H, int W,
-                                          int RH, int RW, int y0, int x0, int fr, uint16_t *s, int n_plane, int warp, int lane,
-                                          int pitch = CSRC)                    // floats per pixel of the source (>= CSRC: a channel slice)
+                                          int RH, int RW, uint32_t mRH, uint32_t mRW, int y0, int x0, int fr, uint16_t *s,
+                                          int n_plane, int tid,
+                                          int pitch = CSRC,                    // floats per pixel of the source (>= CSRC: a channel slice)
+                                          const LConvExtra *ex = nullptr)      // XF: input transform (LConvExtra)
 {
     static_assert(CSRC == C || C == 8, "channel padding goes to one chunk");
-    const int rows = fr * RH;
+    const int npix = fr * RH * RW;
     if (CSRC == C) {
         constexpr int V = C / 4;                                               // float4 per pixel
         constexpr int U = LC2_STAGE_U;                                         // loads in flight per thread
-        const int rowlen = RW * V;
-        for (int gr = warp; gr < rows; gr += 8) {
-            const int f = gr / RH, ly = gr - f * RH;
-            const int iy = y0 + ly;
-            const bool row_ok = f < frames_left && iy >= 0 && iy < H;
-            // only dereferenced for pixels inside the map
-            const float *rowp = src + (ptrdiff_t)f * (ptrdiff_t)frame_elems + ((ptrdiff_t)iy * W + x0) * pitch;
-            const int e_row = gr * RW * C;
-            for (int i0 = lane; i0 < rowlen; i0 += 32 * U) {
-                float4 val[U];
+        const int n_vec = npix * V;
+        for (int i0 = tid; i0 < n_vec; i0 += 256 * U) {
+            float4 val[U];
 #pragma unroll
-                for (int u = 0; u < U; u++) {
-                    const int i = i0 + 32 * u;
-                    val[u] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-                    if (i < rowlen && row_ok) {
-                        const int lx = i / V;
-                        const int ix = x0 + lx;
-                        if (ix >= 0 && ix < W) val[u] = __ldg(reinterpret_cast<const float4 *>(rowp + (ptrdiff_t)lx * pitch) + (i - lx * V));
+            for (int u = 0; u < U; u++) {
+                const int i = i0 + 256 * u;
+                val[u] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                if (i < n_vec) {
+                    const int pixel = i / V, iv = i - pixel * V;
+                    const int grow = lc_fastdiv(pixel, mRW), lx = pixel - grow * RW;
+                    const int f = lc_fastdiv(grow, mRH), ly = grow - f * RH;
+                    const int iy = y0 + ly, ix = x0 + lx;
+                    if (f < frames_left && iy >= 0 && iy < H && ix >= 0 && ix < W) {
+                        val[u] = __ldg(reinterpret_cast<const float4 *>(src + (ptrdiff_t)f * (ptrdiff_t)frame_elems +
+                                                                        ((ptrdiff_t)iy * W + ix) * pitch) + iv);
+                        if (XF) {
+                            float4 &q = val[u];
+                            if (ex->in_mode == 1) {
+                                const float4 sc = __ldg(reinterpret_cast<const float4 *>(ex->in_scale) + iv);
+                                const float4 sh = __ldg(reinterpret_cast<const float4 *>(ex->in_shift) + iv);
+                                q.x = fmaf(q.x, sc.x, sh.x); q.y = fmaf(q.y, sc.y, sh.y); q.z = fmaf(q.z, sc.z, sh.z); q.w = fmaf(q.w, sc.w, sh.w);
+                                q.x = q.x > 0.f ? q.x : 0.2f * q.x; q.y = q.y > 0.f ? q.y : 0.2f * q.y;
+                                q.z = q.z > 0.f ? q.z : 0.2f * q.z; q.w = q.w > 0.f ? q.w : 0.2f * q.w;
+                            } else if (ex->in_mode == 2) {
+                                q.x = fmaf(q.x, ex->in_a, ex->in_b); q.y = fmaf(q.y, ex->in_a, ex->in_b);
+                                q.z = fmaf(q.z, ex->in_a, ex->in_b); q.w = fmaf(q.w, ex->in_a, ex->in_b);
+                            }
+                        }
                     }
                 }
+            }
 #pragma unroll
-                for (int u = 0; u < U; u++) {
-                    const int i = i0 + 32 * u;
-                    if (i < rowlen) {
-                        const int e = e_row + i * 4;                           // element index in the unswizzled tile
-                        const int L = e >> 3;
-                        uint32_t p0[NPL], p1[NPL];
-                        lc_split_pair<NPL, F16>(val[u].x, val[u].y, p0);
-                        lc_split_pair<NPL, F16>(val[u].z, val[u].w, p1);
-                        SP_CHECK(lc_swz(L) * 8 + 8 <= n_plane);
-                        uint16_t *dst = s + lc_swz(L) * 8 + (e & 4);
+            for (int u = 0; u < U; u++) {
+                const int i = i0 + 256 * u;
+                if (i < n_vec) {
+                    const int e = i * 4;                                       // element index in the unswizzled tile
+                    const int L = e >> 3;
+                    uint32_t p0[NPL], p1[NPL];
+                    lc_split_pair<NPL, F16>(val[u].x, val[u].y, p0);
+                    lc_split_pair<NPL, F16>(val[u].z, val[u].w, p1);
+                    SP_CHECK(lc_swz(L) * 8 + 8 <= n_plane);
+                    uint16_t *dst = s + lc_swz(L) * 8 + (e & 4);
 #pragma unroll
-                        for (int q = 0; q < NPL; q++) *reinterpret_cast<uint2 *>(dst + (size_t)q * n_plane) = make_uint2(p0[q], p1[q]);
-                    }
+                    for (int q = 0; q < NPL; q++) *reinterpret_cast<uint2 *>(dst + (size_t)q * n_plane) = make_uint2(p0[q], p1[q]);
                 }
             }
         }
     } else {
-        constexpr int U = 4;                                                   // pixels in flight per lane
-        for (int gr = warp; gr < rows; gr += 8) {
-            const int f = gr / RH, ly = gr - f * RH;
-            const int iy = y0 + ly;
-            const bool row_ok = f < frames_left && iy >= 0 && iy < H;
-            const float *rowp = src + (ptrdiff_t)f * (ptrdiff_t)frame_elems + ((ptrdiff_t)iy * W + x0) * pitch;
-            for (int i0 = lane; i0 < RW; i0 += 32 * U) {
-                float val[U][8];
+        constexpr int U = 4;                                                   // pixels in flight per thread
+        for (int i0 = tid; i0 < npix; i0 += 256 * U) {
+            float val[U][8];
 #pragma unroll
-                for (int u = 0; u < U; u++) {
-                    const int i = i0 + 32 * u;
-                    const int ix = x0 + i;
-                    const bool ok = i < RW && row_ok && ix >= 0 && ix < W;
+            for (int u = 0; u < U; u++) {
+                const int i = i0 + 256 * u;
+                const int grow = lc_fastdiv(i, mRW), lx = i - grow * RW;
+                const int f = lc_fastdiv(grow, mRH), ly = grow - f * RH;
+                const int iy = y0 + ly, ix = x0 + lx;
+                const bool ok = i < npix && f < frames_left && iy >= 0 && iy < H && ix >= 0 && ix < W;
+                const float *pp = src + (ptrdiff_t)f * (ptrdiff_t)frame_elems + ((ptrdiff_t)iy * W + ix) * pitch;
 #pragma unroll
-                    for (int c = 0; c < 8; c++) val[u][c] = (c < CSRC && ok) ? __ldg(rowp + i * pitch + c) : 0.0f;
-                }
-#pragma unroll
-                for (int u = 0; u < U; u++) {
-                    const int i = i0 + 32 * u;
-                    if (i < RW) {
-                        const int L = gr * RW + i;                             // one chunk per pixel
-                        uint32_t pp[4][NPL];
-#pragma unroll
-                        for (int h = 0; h < 4; h++) lc_split_pair<NPL, F16>(val[u][2 * h], val[u][2 * h + 1], pp[h]);
-                        SP_CHECK(lc_swz(L) * 8 + 8 <= n_plane);
-                        uint16_t *dst = s + lc_swz(L) * 8;
-#pragma unroll
-                        for (int q = 0; q < NPL; q++)
-                            *reinterpret_cast<uint4 *>(dst + (size_t)q * n_plane) = make_uint4(pp[0][q], pp[1][q], pp[2][q], pp[3][q]);
+                for (int c = 0; c < 8; c++) {
+                    float v = (c < CSRC && ok) ? __ldg(pp + c) : 0.0f;
+                    if (XF && c < CSRC && ok) {
+                        if (ex->in_mode == 1) {
+                            v = fmaf(v, __ldg(ex->in_scale + c), __ldg(ex->in_shift + c));
+                            v = v > 0.f ? v : 0.2f * v;
+                        } else if (ex->in_mode == 2) {
+                            v = fmaf(v, ex->in_a, ex->in_b);
+                        }
                     }
+                    val[u][c] = v;
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                const int i = i0 + 256 * u;
+                if (i < npix) {
+                    uint32_t pp[4][NPL];                                       // one chunk per pixel
+#pragma unroll
+                    for (int h = 0; h < 4; h++) lc_split_pair<NPL, F16>(val[u][2 * h], val[u][2 * h + 1], pp[h]);
+                    SP_CHECK(lc_swz(i) * 8 + 8 <= n_plane);
+                    uint16_t *dst = s + lc_swz(i) * 8;
+#pragma unroll
+                    for (int q = 0; q < NPL; q++)
+                        *reinterpret_cast<uint4 *>(dst + (size_t)q * n_plane) = make_uint4(pp[0][q], pp[1][q], pp[2][q], pp[3][q]);
                 }
             }
         }
@@ -606,10 +403,10 @@ __device__ __forceinline__ void lc2_qoff_table(const LConvParams &p, int *s_qoff
     }
 }
 
-template <int CSRC, int NPL, bool F16, int MT>
+template <int CSRC, int NPL, bool F16, int MT, bool XF = false>
 __global__ void __launch_bounds__(256, (NPL == 2) ? 2 : 1)
 lconv2_kernel(const __grid_constant__ LConvParams p, const float *__restrict__ x, const uint16_t *__restrict__ w_planes,
-              const float *__restrict__ bias, float *__restrict__ out)
+              const float *__restrict__ bias, float *__restrict__ out, const __grid_constant__ LConvExtra ex)
 {
     extern __shared__ __align__(16) uint8_t sm_raw[];
     constexpr int CIN = CSRC < 8 ? 8 : CSRC;                                    // channels of the staged tile (lc2_stage pads)
@@ -631,8 +428,9 @@ lconv2_kernel(const __grid_constant__ LConvParams p, const float *__restrict__ x
         for (int i = tid; i < n16; i += 256) lc_cp_async16(sw + (uint32_t)i * 16u, gw + i);
     }
     lc2_qoff_table<CIN>(p, s_qoff, tid);
-    lc2_stage<CSRC, CIN, NPL, F16>(x + (size_t)img0 * p.Hin * p.Win * CSRC, (size_t)p.Hin * p.Win * CSRC, p.B - img0, p.Hin, p.Win,
-                                   p.IH, p.IW, oy0 * p.stride - p.pad_t, ox0 * p.stride - p.pad_l, p.fr, s_i, p.n_in, warp, lane);
+    lc2_stage<CSRC, CIN, NPL, F16, XF>(x + (size_t)img0 * p.Hin * p.Win * CSRC, (size_t)p.Hin * p.Win * CSRC, p.B - img0, p.Hin,
+                                       p.Win, p.IH, p.IW, p.mIH, p.mIW, oy0 * p.stride - p.pad_t, ox0 * p.stride - p.pad_l, p.fr, s_i,
+                                       p.n_in, tid, CSRC, &ex);
     lc_cp_async_wait();
     __syncthreads();
 
@@ -703,6 +501,10 @@ lconv2_kernel(const __grid_constant__ LConvParams p, const float *__restrict__ x
 
     const int g = lane >> 2, t = lane & 3;
     const float lo_scale = F16 ? kF16LoInv : 1.0f;
+    const int out_ld = XF ? ex.out_ld : p.Cout, out_c0 = XF ? ex.out_c0 : 0;
+    float bs[4][2], bq[4][2];                                                  // XF: batch-norm partials of this thread's channels
+#pragma unroll
+    for (int nt = 0; nt < 4; nt++) { bs[nt][0] = bs[nt][1] = bq[nt][0] = bq[nt][1] = 0.0f; }
 #pragma unroll
     for (int mt = 0; mt < MT; mt++) {
 #pragma unroll
@@ -726,12 +528,46 @@ lconv2_kernel(const __grid_constant__ LConvParams p, const float *__restrict__ x
                     if (ch + 1 < p.Cout) v1 += __ldg(bias + ch + 1);
                 }
                 if (p.relu) { v0 = fmaxf(v0, 0.0f); v1 = fmaxf(v1, 0.0f); }
-                if ((p.Cout & 1) == 0 && ch + 1 < p.Cout) {
-                    *reinterpret_cast<float2 *>(out + pix * p.Cout + ch) = make_float2(v0, v1);
-                } else {
-                    if (ch < p.Cout) out[pix * p.Cout + ch] = v0;
-                    if (ch + 1 < p.Cout) out[pix * p.Cout + ch + 1] = v1;
+                if (XF) {
+                    bs[nt][0] += v0; bq[nt][0] += v0 * v0;
+                    bs[nt][1] += v1; bq[nt][1] += v1 * v1;
                 }
+                float *o = out + pix * out_ld + out_c0 + ch;
+                if ((p.Cout & 1) == 0 && ch + 1 < p.Cout && ((out_ld | out_c0) & 1) == 0) {
+                    *reinterpret_cast<float2 *>(o) = make_float2(v0, v1);
+                } else {
+                    if (ch < p.Cout) o[0] = v0;
+                    if (ch + 1 < p.Cout) o[1] = v1;
+                }
+            }
+        }
+    }
+    if constexpr (XF) {
+        if (ex.bn_partial) {
+            // per-CTA per-channel (sum, sum of squares) in a fixed order: lanes of a warp by shuffles, warps through shared memory
+            __shared__ float s_bn[8][32][2];
+#pragma unroll
+            for (int nt = 0; nt < 4; nt++)
+#pragma unroll
+                for (int e = 0; e < 2; e++) {
+#pragma unroll
+                    for (int off = 4; off < 32; off <<= 1) {
+                        bs[nt][e] += __shfl_xor_sync(0xffffffffu, bs[nt][e], off);
+                        bq[nt][e] += __shfl_xor_sync(0xffffffffu, bq[nt][e], off);
+                    }
+                    if (g == 0 && nt < NT) {
+                        s_bn[warp][nt * 8 + 2 * t + e][0] = bs[nt][e];
+                        s_bn[warp][nt * 8 + 2 * t + e][1] = bq[nt][e];
+                    }
+                }
+            __syncthreads();
+            if (tid < p.Cout) {
+                float sum = 0.0f, sq = 0.0f;
+#pragma unroll
+                for (int w = 0; w < 8; w++) { sum += s_bn[w][tid][0]; sq += s_bn[w][tid][1]; }
+                float *dst = ex.bn_partial + ((size_t)blockIdx.x * ex.bn_ld + ex.out_c0 + tid) * 2;
+                dst[0] = sum;
+                dst[1] = sq;
             }
         }
     }
@@ -783,15 +619,16 @@ lwgrad2_kernel(const __grid_constant__ LConvParams p, const float *__restrict__ 
         const int img0 = fg * p.fr;
         __syncthreads();                                                       // the previous item's MMAs are done with the tiles
         lc2_stage<CSRC, CIN, NPL, F16>(x + (size_t)img0 * p.Hin * p.Win * CSRC, (size_t)p.Hin * p.Win * CSRC, p.B - img0, p.Hin,
-                                       p.Win, p.IH, p.IW, oy0 * p.stride - p.pad_t, ox0 * p.stride - p.pad_l, p.fr, s_i, p.n_in, warp, lane);
+                                       p.Win, p.IH, p.IW, p.mIH, p.mIW, oy0 * p.stride - p.pad_t, ox0 * p.stride - p.pad_l, p.fr, s_i,
+                                       p.n_in, tid);
         {
             const float *dsrc = dy + (size_t)img0 * p.Hout * p.Wout * p.dy_pitch + p.dy_c0;
             const size_t fe = (size_t)p.Hout * p.Wout * p.dy_pitch;
             const int rem = p.B - img0, pt = p.dy_pitch;
-            if (p.Cout == 32) lc2_stage<32, 32, NPL, F16>(dsrc, fe, rem, p.Hout, p.Wout, p.th, p.tw, oy0, ox0, p.fr, s_d, n_d, warp, lane, pt);
-            else if (p.Cout == 16) lc2_stage<16, 16, NPL, F16>(dsrc, fe, rem, p.Hout, p.Wout, p.th, p.tw, oy0, ox0, p.fr, s_d, n_d, warp, lane, pt);
-            else if (p.Cout == 8) lc2_stage<8, 8, NPL, F16>(dsrc, fe, rem, p.Hout, p.Wout, p.th, p.tw, oy0, ox0, p.fr, s_d, n_d, warp, lane, pt);
-            else lc2_stage<1, 8, NPL, F16>(dsrc, fe, rem, p.Hout, p.Wout, p.th, p.tw, oy0, ox0, p.fr, s_d, n_d, warp, lane, pt);   // scalar map
+            if (p.Cout == 32) lc2_stage<32, 32, NPL, F16>(dsrc, fe, rem, p.Hout, p.Wout, p.th, p.tw, p.mTH, p.mTW, oy0, ox0, p.fr, s_d, n_d, tid, pt);
+            else if (p.Cout == 16) lc2_stage<16, 16, NPL, F16>(dsrc, fe, rem, p.Hout, p.Wout, p.th, p.tw, p.mTH, p.mTW, oy0, ox0, p.fr, s_d, n_d, tid, pt);
+            else if (p.Cout == 8) lc2_stage<8, 8, NPL, F16>(dsrc, fe, rem, p.Hout, p.Wout, p.th, p.tw, p.mTH, p.mTW, oy0, ox0, p.fr, s_d, n_d, tid, pt);
+            else lc2_stage<1, 8, NPL, F16>(dsrc, fe, rem, p.Hout, p.Wout, p.th, p.tw, p.mTH, p.mTW, oy0, ox0, p.fr, s_d, n_d, tid, pt);   // scalar map
         }
         __syncthreads();
 
@@ -974,6 +811,7 @@ static void lc2_tile(LConvParams &p, int Cin, int m_tiles_per_warp)
     p.IH = (p.th - 1) * p.stride + p.KH; p.IW = (p.tw - 1) * p.stride + p.KW;
     p.tiles_x = (p.Wout + p.tw - 1) / p.tw; p.tiles_y = (p.Hout + p.th - 1) / p.th;
     p.n_in = (p.fr * p.IH * p.IW * Cin + 63) & ~63;
+    p.mIH = lc_magic(p.IH); p.mIW = lc_magic(p.IW); p.mTH = lc_magic(p.th); p.mTW = lc_magic(p.tw);
 }
 
 constexpr size_t kLcSmemMax = 227 * 1024;        // per-CTA shared memory on sm_100
@@ -1045,22 +883,6 @@ extern "C" int spiral_pconv_pack(const float *w, void *packed_bf16, int32_t rows
     return e == cudaSuccess ? SPIRAL_OK : spiral_cuda_error(e, "spiral_pconv_pack");
 }
 
-// the first-generation kernel: the discriminator's narrow layers (batch norm + leaky-ReLU on load, batch-norm partials)
-template <int CIN, int NPL>
-static int lconv_launch(const LConvParams &p, const float *x, const void *w, const float *bias, float *out, int grid, size_t smem,
-                        cudaStream_t st, const float *in_scale = nullptr, const float *in_shift = nullptr, float *bn_partial = nullptr)
-{
-    static bool attr = false;
-    if (!attr) {
-        // the kernel also has 2 KB of static shared memory (batch-norm partials)
-        const cudaError_t e = cudaFuncSetAttribute(lconv_kernel<CIN, NPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kLcSmemMax - 2048));
-        if (e != cudaSuccess) return spiral_cuda_error(e, "cudaFuncSetAttribute(lconv_kernel)");
-        attr = true;
-    }
-    lconv_kernel<CIN, NPL><<<grid, 256, smem, st>>>(p, x, (const uint16_t *)w, bias, out, in_scale, in_shift, bn_partial);
-    return SPIRAL_OK;
-}
-
 template <int CSRC, int NPL, bool F16, int MT>
 static int lconv2_launch(const LConvParams &p, const float *x, const void *w, const float *bias, float *out, int grid, size_t smem,
                          cudaStream_t st)
@@ -1071,7 +893,26 @@ static int lconv2_launch(const LConvParams &p, const float *x, const void *w, co
         if (e != cudaSuccess) return spiral_cuda_error(e, "cudaFuncSetAttribute(lconv2_kernel)");
         attr = true;
     }
-    lconv2_kernel<CSRC, NPL, F16, MT><<<grid, 256, smem, st>>>(p, x, (const uint16_t *)w, bias, out);
+    LConvExtra none;
+    memset(&none, 0, sizeof(none));
+    lconv2_kernel<CSRC, NPL, F16, MT><<<grid, 256, smem, st>>>(p, x, (const uint16_t *)w, bias, out, none);
+    return SPIRAL_OK;
+}
+
+// the discriminator's variant (input transform, output slice, batch-norm partials), operand format f16x3
+template <int CSRC, int MT>
+static int lconv2x_launch(const LConvParams &p, const float *x, const void *w, const float *bias, float *out, const LConvExtra &ex,
+                          int grid, size_t smem, cudaStream_t st)
+{
+    static bool attr = false;
+    if (!attr) {
+        // 2 KB of static shared memory next to the dynamic tile
+        const cudaError_t e = cudaFuncSetAttribute(lconv2_kernel<CSRC, 2, true, MT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                   (int)(kLcSmemMax - 2048));
+        if (e != cudaSuccess) return spiral_cuda_error(e, "cudaFuncSetAttribute(lconv2_kernel, discriminator variant)");
+        attr = true;
+    }
+    lconv2_kernel<CSRC, 2, true, MT, true><<<grid, 256, smem, st>>>(p, x, (const uint16_t *)w, bias, out, ex);
     return SPIRAL_OK;
 }
 
@@ -1145,35 +986,71 @@ extern "C" int spiral_lconv_forward(const float *x, const void *w_planes, int32_
     return e == cudaSuccess ? SPIRAL_OK : spiral_cuda_error(e, "spiral_lconv_forward");
 }
 
-// A narrow layer of the discriminator (disc_dim 8 / 16: Cin <= 16, Cout <= 32; 5x5 / stride 2 / 'SAME' = pad 1 before, 2 after)
-// on the first-generation kernel instead of the fp32 SIMT tile (64 x 64 outputs per CTA: at Cout = 16, Cin = 8 seven eighths of
-// its FMAs are padding): kernel HWIO fp32 -> three bf16 planes (bf16x6, fp32-exact operands), the producer's BN + leaky-ReLU
-// applied while the input tile is staged, + bias, raw fp32 output, per-CTA batch-norm partials.  Returns the number of partial rows.
+// A narrow layer of the discriminator (disc_dim 8 / 16 / 32; 5x5 / stride 2 / 'SAME' = pad 1 before, 2 after) on
+// lconv2_kernel's discriminator variant instead of the fp32 SIMT tiles (64 x 64 outputs per CTA: at Cout = 16, Cin = 8
+// seven eighths of their FMAs are padding; the image layer's kernel is a 25-term scalar loop): kernel HWIO fp32 -> two fp16
+// planes (f16x3: 22 operand bits), the producer's BN + leaky-ReLU -- or, for layer 0, the image normalisation -- applied
+// while the input tile is staged, + bias, RAW fp32 output, per-CTA batch-norm partials.  Up to 128 output channels as
+// slices of 32.  *n_part = rows of the partials (CTAs of one launch).
 namespace spiral {
-bool lconv_disc_layer_supported(int Cin, int Cout) { return (Cin == 8 || Cin == 16) && Cout <= 32 && Cout % 2 == 0; }
+bool lconv_disc_layer_supported(int Cin, int Cout)
+{
+    return lc_cin_ok(Cin) && Cout % 2 == 0 && (Cout <= 32 || (Cout % 32 == 0 && Cout <= 128));
+}
 size_t lconv_disc_pack_bytes(int Cin, int Cout)
 {
-    return (size_t)3 * spiral_lconv_packed_elems(Cin, Cout, 25) * sizeof(uint16_t);
+    const int slices = (Cout + 31) / 32;
+    return (size_t)slices * 2 * spiral_lconv_packed_elems(Cin, Cout < 32 ? Cout : 32, 25) * sizeof(uint16_t);
 }
-int lconv_disc_layer(const float *in, const float *in_scale, const float *in_shift, const float *w_hwio, const float *bias,
-                     float *out, float *bn_partial, void *pack_scratch, int B, int H, int Cin, int Cout, int *n_part,
-                     cudaStream_t st)
+
+template <int MT>
+static int lconv2x_dispatch(int Cin, const LConvParams &p, const float *x, const void *w, const float *bias, float *out,
+                            const LConvExtra &ex, int grid, size_t smem, cudaStream_t st)
+{
+    switch (Cin) {
+    case 1: return lconv2x_launch<1, MT>(p, x, w, bias, out, ex, grid, smem, st);
+    case 2: return lconv2x_launch<2, MT>(p, x, w, bias, out, ex, grid, smem, st);
+    case 3: return lconv2x_launch<3, MT>(p, x, w, bias, out, ex, grid, smem, st);
+    case 6: return lconv2x_launch<6, MT>(p, x, w, bias, out, ex, grid, smem, st);
+    case 8: return lconv2x_launch<8, MT>(p, x, w, bias, out, ex, grid, smem, st);
+    case 16: return lconv2x_launch<16, MT>(p, x, w, bias, out, ex, grid, smem, st);
+    default: return lconv2x_launch<32, MT>(p, x, w, bias, out, ex, grid, smem, st);
+    }
+}
+
+// in_mode 0: the input as it is; 1: leaky_relu(in * in_scale[c] + in_shift[c]); 2: in * in_a + in_b
+int lconv_disc_layer(const float *in, int in_mode, const float *in_scale, const float *in_shift, float in_a, float in_b,
+                     const float *w_hwio, const float *bias, float *out, float *bn_partial, void *pack_scratch, int B, int H,
+                     int Cin, int Cout, int *n_part, cudaStream_t st)
 {
     int tk[25], tx[25];
     for (int i = 0; i < 25; i++) { tk[i] = i / 5; tx[i] = i % 5; }
-    int rc = spiral_lconv_pack(w_hwio, pack_scratch, 3, Cout, Cin, 25, 1, Cout, (int64_t)5 * Cin * Cout, (int64_t)Cin * Cout, tk, tx, st);
-    if (rc != SPIRAL_OK) return rc;
-    const int Ho = H / 2;
-    LConvParams p;
-    lc_fill(p, B, H, H, Cin, Ho, Ho, Cout, 5, 5, 2, 1, 1, Ho, Ho, 1, 1, 0, 0);
-    const size_t n_w = (size_t)p.CoutPad * p.KS, n_in8 = ((size_t)p.IH * p.IW * Cin + 7) & ~(size_t)7;
-    const size_t smem = (size_t)3 * (n_w + n_in8) * 2 + (size_t)p.KP * 4;
-    if (smem > kLcSmemMax - 4096) return spiral_set_error(SPIRAL_EUNSUPPORTED, "lconv_disc_layer: tile does not fit shared memory");
-    const int grid = B * p.tiles_x * p.tiles_y;
-    *n_part = grid;
-    if (Cin == 8) rc = lconv_launch<8, 3>(p, in, pack_scratch, bias, out, grid, smem, st, in_scale, in_shift, bn_partial);
-    else rc = lconv_launch<16, 3>(p, in, pack_scratch, bias, out, grid, smem, st, in_scale, in_shift, bn_partial);
-    if (rc != SPIRAL_OK) return rc;
+    const int Ho = H / 2, CinP = lc_cin_pad(Cin);
+    for (int c0 = 0; c0 < Cout; c0 += 32) {
+        const int cs = Cout - c0 < 32 ? Cout - c0 : 32;
+        char *planes = (char *)pack_scratch + (size_t)(c0 / 32) * 2 * spiral_lconv_packed_elems(Cin, Cout < 32 ? Cout : 32, 25) * sizeof(uint16_t);
+        int rc = spiral_lconv_pack(w_hwio + c0, planes, 4, cs, Cin, 25, 1, Cout, (int64_t)5 * Cin * Cout, (int64_t)Cin * Cout, tk, tx, st);
+        if (rc != SPIRAL_OK) return rc;
+        LConvParams p;
+        lc_fill(p, B, H, H, CinP, Ho, Ho, cs, 5, 5, 2, 1, 1, Ho, Ho, 1, 1, 0, 0);
+        LConvExtra ex;
+        ex.in_scale = in_scale; ex.in_shift = in_shift; ex.in_a = in_a; ex.in_b = in_b; ex.in_mode = in_mode;
+        ex.bn_partial = bn_partial; ex.out_ld = Cout; ex.out_c0 = c0; ex.bn_ld = Cout;
+        const size_t n_w = (size_t)p.CoutPad * p.KS;
+        bool done = false;
+        for (int mt = 2; mt >= 1 && !done; mt--) {
+            lc2_tile(p, CinP, mt);
+            const size_t smem = (size_t)2 * ((size_t)p.n_in + n_w) * 2 + (size_t)(p.KP / 8) * 4;
+            if (smem > kLcSmemMax - 2048) continue;
+            const int grid = ((B + p.fr - 1) / p.fr) * p.tiles_x * p.tiles_y;
+            *n_part = grid;
+            rc = mt == 2 ? lconv2x_dispatch<2>(Cin, p, in, planes, bias ? bias + c0 : nullptr, out, ex, grid, smem, st)
+                         : lconv2x_dispatch<1>(Cin, p, in, planes, bias ? bias + c0 : nullptr, out, ex, grid, smem, st);
+            if (rc != SPIRAL_OK) return rc;
+            done = true;
+        }
+        if (!done) return spiral_set_error(SPIRAL_EUNSUPPORTED, "lconv_disc_layer: tile does not fit shared memory");
+    }
     const cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? SPIRAL_OK : spiral_cuda_error(e, "lconv_disc_layer");
 }
