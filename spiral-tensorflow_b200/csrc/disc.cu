@@ -13,6 +13,7 @@
 // reference for the tensor-core path) and the kernels shared by both paths (BN finalise,
 // dense + sigmoid).  The tcgen05 implicit-GEMM path lives in disc_tc.cu.
 #include "disc.cuh"
+#include "conv_ops.cuh"
 
 #include <cuda_bf16.h>
 
@@ -364,6 +365,58 @@ __global__ void dense_sigmoid_kernel(const float *__restrict__ in, const float *
 }
 
 // ------------------------------------------------------------------------------------------
+// Wide layers of a NARROW discriminator (disc_dim 8 / 16: its last layers have Cin >= 64, Cout >= 128 on 4x4 .. 1x1 maps): plain
+// GEMM shapes that the fp32 SIMT tile runs at ~33 TFLOP/s.  They take K2b's tcgen05 forward with three bf16 planes (bf16x6:
+// fp32-exact operands, conv_tc.cu) between two small elementwise passes -- the maps are a few hundred MB:
+//   bn_act_kernel        y = leaky_relu(x * scale[c] + shift[c])   (this path's layers store RAW outputs, the consumer normalises)
+//   bias_partial_kernel  out += bias[c]; partial[tile of 64 rows][c] = (sum, sum of squares) for the layer's batch norm
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+bn_act_kernel(const float *__restrict__ x, const float *__restrict__ scale, const float *__restrict__ shift, float *__restrict__ y,
+              size_t n4, int C)
+{
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        const int c = (int)((i * 4) % (size_t)C);
+        float4 v = __ldg(reinterpret_cast<const float4 *>(x) + i);
+        const float4 sc = __ldg(reinterpret_cast<const float4 *>(scale + c)), sh = __ldg(reinterpret_cast<const float4 *>(shift + c));
+        v.x = fmaf(v.x, sc.x, sh.x); v.y = fmaf(v.y, sc.y, sh.y); v.z = fmaf(v.z, sc.z, sh.z); v.w = fmaf(v.w, sc.w, sh.w);
+        v.x = v.x > 0.f ? v.x : 0.2f * v.x; v.y = v.y > 0.f ? v.y : 0.2f * v.y;
+        v.z = v.z > 0.f ? v.z : 0.2f * v.z; v.w = v.w > 0.f ? v.w : 0.2f * v.w;
+        reinterpret_cast<float4 *>(y)[i] = v;
+    }
+}
+
+// grid (tiles of 64 rows, Cout / 64); thread = (row group tid / 64, channel tid % 64): fixed order, deterministic
+__global__ void __launch_bounds__(256)
+bias_partial_kernel(float *__restrict__ out, const float *__restrict__ bias, float *__restrict__ partial, long long rows, int C)
+{
+    __shared__ float s_s[4][64], s_q[4][64];
+    const int c = blockIdx.y * 64 + (threadIdx.x & 63), rg = threadIdx.x >> 6;
+    const long long r0 = (long long)blockIdx.x * 64;
+    const float b = __ldg(bias + c);
+    float sum = 0.0f, sq = 0.0f;
+    for (int j = rg; j < 64; j += 4) {
+        const long long r = r0 + j;
+        if (r < rows) {
+            const float v = out[r * C + c] + b;
+            out[r * C + c] = v;
+            sum += v;
+            sq += v * v;
+        }
+    }
+    s_s[rg][threadIdx.x & 63] = sum;
+    s_q[rg][threadIdx.x & 63] = sq;
+    __syncthreads();
+    if (rg == 0 && partial) {
+        const int k = threadIdx.x;
+        float *dst = partial + ((size_t)blockIdx.x * C + c) * 2;
+        dst[0] = (s_s[0][k] + s_s[1][k]) + (s_s[2][k] + s_s[3][k]);
+        dst[1] = (s_q[0][k] + s_q[1][k]) + (s_q[2][k] + s_q[3][k]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // host object
 // ------------------------------------------------------------------------------------------
 size_t disc_align(size_t v) { return (v + 255) & ~(size_t)255; }
@@ -385,6 +438,9 @@ void disc_plan(const SpiralDisc *d, int batch, DiscPlan *pl)
         pl->shift_off[l] = off; off += disc_align((size_t)Cout * sizeof(float));
         pl->pack_off[l] = off;
         if (lconv_disc_layer_supported(Cin, Cout)) off += disc_align(lconv_disc_pack_bytes(Cin, Cout));
+        pl->tc_off[l] = off;
+        if (d->cfg.disc_dim < 64 && l > 0 && !lconv_disc_layer_supported(Cin, Cout) && conv_tc_supported(0, batch, H, Cin, Cout))
+            off += disc_align((size_t)batch * H * H * Cin * sizeof(float)) + disc_align(conv_tc_workspace_bytes(batch, H, Cin, Cout));
         H = Ho; Cin = Cout;
     }
     pl->simt_bytes = off;
@@ -434,7 +490,10 @@ int disc_forward_simt(SpiralDisc *d, const float *x, int batch, float *logits, f
         float *part = (float *)(ws + pl.part_off[l]);
         const bool bn = l > 0 && d->cfg.batch_norm;
         int n_part = pl.mtiles[l];                   // rows of the batch-norm partials this layer's kernel writes
-        if (l == 0 && lconv_disc_layer_supported(Cin, Cout)) {
+        // (disc_dim 64 with precision 0 stays on the fp32 SIMT kernels throughout: it is the independent reference of the
+        // tensor-core reward path in the tests)
+        const bool narrow = d->cfg.disc_dim < 64;
+        if (l == 0 && narrow && lconv_disc_layer_supported(Cin, Cout)) {
             // image layer: normalisation (x - 127.5) / 127.5 applied while the tile is staged ('SAME' pads the normalised image)
             const bool nz = d->cfg.normalize != 0;
             const int rc = lconv_disc_layer(x, nz ? 2 : 0, nullptr, nullptr, 1.0f / 127.5f, -1.0f, (const float *)W.conv_w[0],
@@ -448,11 +507,23 @@ int disc_forward_simt(SpiralDisc *d, const float *x, int batch, float *logits, f
             const float *in = (const float *)(ws + pl.act_off[l - 1]);
             const float *isc = (const float *)(ws + pl.scale_off[l - 1]);
             const float *ish = (const float *)(ws + pl.shift_off[l - 1]);
-            if (lconv_disc_layer_supported(Cin, Cout)) {
+            if (narrow && lconv_disc_layer_supported(Cin, Cout)) {
                 // narrow layer (Cin <= 32, Cout <= 128): the mma.sync implicit GEMM of policy_learn.cu (lconv2_kernel, f16x3)
                 const int rc = lconv_disc_layer(in, 1, isc, ish, 0.0f, 0.0f, (const float *)W.conv_w[l], (const float *)W.conv_b[l],
                                                 out, bn ? part : nullptr, ws + pl.pack_off[l], batch, H, Cin, Cout, &n_part, st);
                 if (rc != SPIRAL_OK) return rc;
+            } else if (narrow && conv_tc_supported(0, batch, H, Cin, Cout)) {
+                // wide tail of a narrow discriminator: activation pass, tcgen05 forward (bf16x6), bias + batch-norm partials
+                float *act = (float *)(ws + pl.tc_off[l]);
+                char *tcws = ws + pl.tc_off[l] + disc_align((size_t)batch * H * H * Cin * sizeof(float));
+                const size_t n4 = (size_t)batch * H * H * Cin / 4;
+                const size_t want = (n4 + 255) / 256;
+                bn_act_kernel<<<(unsigned)(want < 148 * 8 ? want : 148 * 8), 256, 0, st>>>(in, isc, ish, act, n4, Cin);
+                const int rc = conv_tc_forward(act, (const float *)W.conv_w[l], out, batch, H, Cin, Cout, 3, tcws, st);
+                if (rc != SPIRAL_OK) return rc;
+                dim3 grid(pl.mtiles[l], Cout / 64);
+                bias_partial_kernel<<<grid, 256, 0, st>>>(out, (const float *)W.conv_b[l], bn ? part : nullptr,
+                                                          (long long)batch * Ho * Ho, Cout);
             } else {
                 dim3 grid(pl.mtiles[l], (Cout + 63) / 64);
                 conv_simt_kernel<<<grid, 256, 0, st>>>(in, isc, ish, (const float *)W.conv_w[l], (const float *)W.conv_b[l],

@@ -22,6 +22,7 @@ struct DiscPlan {
     int mtiles[SPIRAL_DISC_MAX_LAYERS];
     size_t act_off[SPIRAL_DISC_MAX_LAYERS], part_off[SPIRAL_DISC_MAX_LAYERS];
     size_t scale_off[SPIRAL_DISC_MAX_LAYERS], shift_off[SPIRAL_DISC_MAX_LAYERS];
+    size_t tc_off[SPIRAL_DISC_MAX_LAYERS];        // wide tail layers of a narrow discriminator on K2b's tcgen05 forward: activated input + its workspace
     size_t pack_off[SPIRAL_DISC_MAX_LAYERS];      // packed kernel planes of the narrow layers (lconv_disc_layer)
     size_t simt_bytes;
 };
