@@ -493,7 +493,10 @@ int disc_forward_simt(SpiralDisc *d, const float *x, int batch, float *logits, f
         // (disc_dim 64 with precision 0 stays on the fp32 SIMT kernels throughout: it is the independent reference of the
         // tensor-core reward path in the tests)
         const bool narrow = d->cfg.disc_dim < 64;
-        if (l == 0 && narrow && lconv_disc_layer_supported(Cin, Cout)) {
+        // measured at 65,536 images (profiles/r2_mnist_uncond_disc_layers.md): the 1 -> 8 image layer is faster on the
+        // scalar kernel (4.9 vs 7.6 ms: 25 FMAs per output against a staging-bound MMA tile that is 7/8 padding); wider
+        // image layers and the 32 -> 64 layer on 4x4 maps (half of an 8-wide tile is padding) likewise stay where they are faster
+        if (l == 0 && narrow && Cin * Cout > 8 && lconv_disc_layer_supported(Cin, Cout)) {
             // image layer: normalisation (x - 127.5) / 127.5 applied while the tile is staged ('SAME' pads the normalised image)
             const bool nz = d->cfg.normalize != 0;
             const int rc = lconv_disc_layer(x, nz ? 2 : 0, nullptr, nullptr, 1.0f / 127.5f, -1.0f, (const float *)W.conv_w[0],
@@ -507,7 +510,7 @@ int disc_forward_simt(SpiralDisc *d, const float *x, int batch, float *logits, f
             const float *in = (const float *)(ws + pl.act_off[l - 1]);
             const float *isc = (const float *)(ws + pl.scale_off[l - 1]);
             const float *ish = (const float *)(ws + pl.shift_off[l - 1]);
-            if (narrow && lconv_disc_layer_supported(Cin, Cout)) {
+            if (narrow && Cout <= 32 && lconv_disc_layer_supported(Cin, Cout)) {
                 // narrow layer (Cin <= 32, Cout <= 128): the mma.sync implicit GEMM of policy_learn.cu (lconv2_kernel, f16x3)
                 const int rc = lconv_disc_layer(in, 1, isc, ish, 0.0f, 0.0f, (const float *)W.conv_w[l], (const float *)W.conv_b[l],
                                                 out, bn ? part : nullptr, ws + pl.pack_off[l], batch, H, Cin, Cout, &n_part, st);
