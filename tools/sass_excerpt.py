@@ -13,7 +13,7 @@ LIB = os.path.join(ROOT, "spiral-tensorflow_b200", "csrc", "libspiral_b200.so")
 PATS = collections.OrderedDict([("UTCHMMA (tcgen05.mma)", r"\bUTC[A-Z]*MMA"), ("UTMALDG (TMA load)", r"\bUTMALDG"),
                                 ("UTMASTG (TMA store)", r"\bUTMASTG"), ("LDTM (tcgen05.ld)", r"\bLDTM"),
                                 ("UTCBAR (tcgen05.commit)", r"\bUTCBAR"), ("HMMA (mma.sync)", r"\bHMMA"),
-                                ("LDGSTS (cp.async)", r"\bLDGSTS"), ("MUFU", r"\bMUFU"), ("DFMA/DMUL/DADD", r"\bD(FMA|MUL|ADD)"),
+                                ("LDGSTS (cp.async)", r"\bLDGSTS"), ("LDSM (ldmatrix)", r"\bLDSM"), ("MUFU", r"\bMUFU"), ("DFMA/DMUL/DADD", r"\bD(FMA|MUL|ADD)"),
                                 ("instructions", r"^\s+/\*[0-9a-f]{4,5}\*/")])
 
 
