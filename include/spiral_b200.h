@@ -313,7 +313,8 @@ int spiral_debug_philox(const uint32_t *ctr_key6_host, uint32_t *out4_dev, void 
 /*           models/discriminator.py:124-126 (Adam, beta1 .5, beta2 .9) */
 /* ------------------------------------------------------------------ */
 /* Pointer tables are HOST arrays of device pointers, sizes in elements.
- * spiral_grad_global_norm: norm_out_dev f32[1] = sqrt(sum of squares of every tensor); scratch_dev f64[32 * n_tensors].
+ * spiral_grad_global_norm: norm_out_dev f32[1] = sqrt(sum of squares of every tensor); scratch_dev f64[32 * pieces] with
+ * pieces = sum over tensors of ceil(size / 2^20) (tensors are processed in pieces of 2^20 elements; = n_tensors when none is larger).
  * spiral_adam_step: g' = g * grad_scale * clip / max(norm * grad_scale, clip)  (skipped when norm_dev is NULL or
  * clip_norm <= 0);  m = b1 m + (1-b1) g';  v = b2 v + (1-b2) g'^2;  p -= lr_t * m / (sqrt(v) + eps), with
  * lr_t = lr * sqrt(1 - b2^t) / (1 - b1^t) computed by the caller (TensorFlow's formulation).  No host sync. */

@@ -21,6 +21,9 @@ namespace spiral {
 
 constexpr int kMaxTensors = 48;
 constexpr int kOptBlocksX = 32;
+// A table entry is a PIECE of at most 2^20 elements of a tensor (32 CTAs each): the discriminator's 279 MB are two big
+// kernels and a handful of small tensors, and with one entry per tensor its update ran on 32 SMs (7.7 ms for a 2 GB sweep).
+constexpr long long kPiece = 1ll << 20;
 
 struct TensorTable {
     float *p[kMaxTensors];
@@ -96,17 +99,32 @@ extern "C" int spiral_grad_global_norm(const float *const *grads, const int64_t 
                                        double *scratch, float *norm_out, void *stream)
 {
     SPIRAL_REQUIRE(grads); SPIRAL_REQUIRE(sizes); SPIRAL_REQUIRE(scratch); SPIRAL_REQUIRE(norm_out);
-    if (n_tensors <= 0 || n_tensors > 4096 / kOptBlocksX * 8)
-        return spiral_set_error(SPIRAL_EINVAL, "grad_global_norm: 1..1024 tensors (scratch holds 32 partials each)");
+    if (n_tensors <= 0 || n_tensors > 1024)
+        return spiral_set_error(SPIRAL_EINVAL, "grad_global_norm: 1..1024 tensors");
     cudaStream_t st = (cudaStream_t)stream;
-    for (int t0 = 0; t0 < n_tensors; t0 += kMaxTensors) {
-        TensorTable T;
-        T.count = n_tensors - t0 < kMaxTensors ? n_tensors - t0 : kMaxTensors;
-        for (int i = 0; i < T.count; i++) { T.g[i] = grads[t0 + i]; T.n[i] = sizes[t0 + i]; T.p[i] = nullptr; T.m[i] = nullptr; T.v[i] = nullptr; }
+    // pieces in tensor order: the partial sums, and so the norm, do not depend on how the launches are grouped
+    long long n_pieces = 0;
+    TensorTable T;
+    T.count = 0;
+    auto flush = [&]() {
+        if (T.count == 0) return;
         dim3 grid(kOptBlocksX, T.count);
-        grad_sumsq_kernel<<<grid, 256, 0, st>>>(T, scratch + (size_t)t0 * kOptBlocksX);
+        grad_sumsq_kernel<<<grid, 256, 0, st>>>(T, scratch + (size_t)(n_pieces - T.count) * kOptBlocksX);
+        T.count = 0;
+    };
+    for (int t = 0; t < n_tensors; t++) {
+        if (sizes[t] < 0) return spiral_set_error(SPIRAL_EINVAL, "grad_global_norm: negative size");
+        for (long long off = 0; off < sizes[t]; off += kPiece) {
+            const int i = T.count++;
+            T.g[i] = grads[t] + off; T.n[i] = sizes[t] - off < kPiece ? sizes[t] - off : kPiece;
+            T.p[i] = nullptr; T.m[i] = nullptr; T.v[i] = nullptr;
+            n_pieces++;
+            if (T.count == kMaxTensors) flush();
+        }
     }
-    norm_final_kernel<<<1, 256, 0, st>>>(scratch, n_tensors * kOptBlocksX, norm_out);
+    flush();
+    if (n_pieces == 0) return spiral_set_error(SPIRAL_EINVAL, "grad_global_norm: every tensor is empty");
+    norm_final_kernel<<<1, 256, 0, st>>>(scratch, (int)(n_pieces * kOptBlocksX), norm_out);
     const cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? SPIRAL_OK : spiral_cuda_error(e, "spiral_grad_global_norm");
 }
@@ -118,15 +136,23 @@ static int adam_step_impl(float *const *params, const float *const *grads, float
     SPIRAL_REQUIRE(params); SPIRAL_REQUIRE(grads); SPIRAL_REQUIRE(m); SPIRAL_REQUIRE(v); SPIRAL_REQUIRE(sizes);
     if (n_tensors <= 0) return spiral_set_error(SPIRAL_EINVAL, "adam_step: no tensors");
     cudaStream_t st = (cudaStream_t)stream;
-    for (int t0 = 0; t0 < n_tensors; t0 += kMaxTensors) {
-        TensorTable T;
-        T.count = n_tensors - t0 < kMaxTensors ? n_tensors - t0 : kMaxTensors;
-        for (int i = 0; i < T.count; i++) {
-            T.p[i] = params[t0 + i]; T.g[i] = grads[t0 + i]; T.m[i] = m[t0 + i]; T.v[i] = v[t0 + i]; T.n[i] = sizes[t0 + i];
-        }
+    TensorTable T;
+    T.count = 0;
+    auto flush = [&]() {
+        if (T.count == 0) return;
         dim3 grid(kOptBlocksX, T.count);
         adam_step_kernel<<<grid, 256, 0, st>>>(T, lr_t, lr_t_dev, beta1, beta2, eps, grad_scale, norm_dev, clip_norm);
+        T.count = 0;
+    };
+    for (int t = 0; t < n_tensors; t++) {
+        for (long long off = 0; off < sizes[t]; off += kPiece) {
+            const int i = T.count++;
+            T.p[i] = params[t] + off; T.g[i] = grads[t] + off; T.m[i] = m[t] + off; T.v[i] = v[t] + off;
+            T.n[i] = sizes[t] - off < kPiece ? sizes[t] - off : kPiece;
+            if (T.count == kMaxTensors) flush();
+        }
     }
+    flush();
     const cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? SPIRAL_OK : spiral_cuda_error(e, "spiral_adam_step");
 }

@@ -27,7 +27,8 @@ class FusedTFAdam(object):
         self.m = [torch.zeros_like(p) for p in self.params]
         self.v = [torch.zeros_like(p) for p in self.params]
         dev = self.params[0].device
-        self._scratch = torch.empty((32 * len(self.params),), dtype=torch.float64, device=dev)
+        pieces = sum(max(1, -(-p.numel() // (1 << 20))) for p in self.params)      # include/spiral_b200.h: 32 partials per 2^20-element piece
+        self._scratch = torch.empty((32 * pieces,), dtype=torch.float64, device=dev)
         self._norm = torch.zeros((1,), dtype=torch.float32, device=dev)
         self._lr_t = torch.zeros((1,), dtype=torch.float32, device=dev)     # this step's lr_t, device-resident (CUDA graphs)
 
