@@ -86,7 +86,8 @@ def test_fused_clip_adam_matches_reference_formulas():
     optim = import_module(sp.__name__ + ".optim")
     du = import_module(sp.__name__ + ".distributed")
     g = torch.Generator(device="cuda").manual_seed(0)
-    shapes = [(5, 5, 3, 64), (64,), (1152, 256), (7,), (300, 33)] * 12          # 60 tensors: more than one launch
+    # 61 tensors: more than one launch; one of 2.5 * 2^20 + 3 elements: three pieces of the 2^20-element table entries
+    shapes = [(5, 5, 3, 64), (64,), (1152, 256), (7,), (300, 33)] * 12 + [(5 * (1 << 19) + 3,)]
     pa = [torch.randn(s, generator=g, device="cuda") for s in shapes]
     pb = [p.clone() for p in pa]
     ref = TFAdam(pb, 1e-3, beta1=0.5, beta2=0.9)
