@@ -45,6 +45,7 @@ struct LConvParams {
     int tw, th, fr, mt_rows;                     // tw = 16 or 8; mt_rows = 16 / tw rows per 16-pixel m-tile; th a power of two
     int th_log;
     int n_in;                                    // halfwords per plane of the staged input tile (multiple of 64)
+    int lw_ks;                                   // wgrad: k-steps (16 output pixels each) per item: 8 or 16
     uint32_t mIH, mIW, mTH, mTW;                 // lc_magic of IH, IW (input tile) and th, tw (wgrad's dy tile)
     int relu;                                    // forward epilogue: max(v, 0) after the bias (tf.nn.relu of the layer's activation)
     int dy_pitch, dy_c0;                         // wgrad: dy is [.., dy_pitch] channels per pixel, this launch takes [dy_c0, dy_c0 + Cout)
@@ -586,7 +587,7 @@ lwgrad2_kernel(const __grid_constant__ LConvParams p, const float *__restrict__ 
     constexpr int CIN = CSRC < 8 ? 8 : CSRC;
     constexpr int CH = CIN / 8;
     const int CC = p.CoutPad, CCH = CC >> 3;                                    // staged dy channels (8, 16 or 32) and chunks per pixel
-    const int n_d = kLwPix * CC;                                                // multiple of 64
+    const int n_d = p.lw_ks * 16 * CC;                                          // multiple of 64
     uint16_t *s_i = reinterpret_cast<uint16_t *>(sm_raw);                     // [NPL][n_in]
     uint16_t *s_d = s_i + (size_t)NPL * p.n_in;                                // [NPL][128][CC]
     int *s_qoff = reinterpret_cast<int *>(s_d + (size_t)NPL * n_d);            // [KP / 8]
@@ -633,7 +634,7 @@ lwgrad2_kernel(const __grid_constant__ LConvParams p, const float *__restrict__ 
         __syncthreads();
 
 #pragma unroll 1
-        for (int ks = 0; ks < 8; ks++) {
+        for (int ks = 0; ks < p.lw_ks; ks++) {
             uint32_t b[4][NPL][2];
 #pragma unroll
             for (int ntp = 0; ntp < 2; ntp++) {
@@ -793,7 +794,7 @@ static void lc_fill(LConvParams &p, int B, int Hin, int Win, int Cin, int Hout, 
     p.tiles_x = (Wout + kLcTw - 1) / kLcTw; p.tiles_y = (Hout + kLcTh - 1) / kLcTh;
     p.oH = oH; p.oW = oW; p.o_sy = o_sy; p.o_sx = o_sx; p.o_oy = o_oy; p.o_ox = o_ox;
     p.tw = kLcTw; p.th = kLcTh; p.fr = 1; p.mt_rows = 1; p.th_log = 3; p.n_in = 0;
-    p.dy_pitch = Cout; p.dy_c0 = 0; p.relu = 0;
+    p.dy_pitch = Cout; p.dy_c0 = 0; p.relu = 0; p.lw_ks = 8;
 }
 
 // tile of the v2 kernels: `rows` = output rows a CTA covers over all its frames (8 warps x m-tiles per warp x mt_rows)
@@ -1072,6 +1073,7 @@ int lwgrad2_image_layer(const float *x, const float *dy, float *dw, float *works
         lc_fill(p, B, H, H, CinP, Ho, Ho, 32, 5, 5, 2, 1, 1, Ho, Ho, 1, 1, 0, 0);
         p.dy_pitch = Cout; p.dy_c0 = c0;
         lc2_tile(p, CinP, 1);
+        p.lw_ks = 8;
         const int npl = lc_prec_planes(n_planes);
         const size_t smem = (size_t)npl * ((size_t)p.n_in + (size_t)kLwPix * p.CoutPad) * 2 + (size_t)(p.KP / 8) * 4;
         if (smem > kLcSmemMax) return spiral_set_error(SPIRAL_EUNSUPPORTED, "lwgrad2_image_layer: tile does not fit shared memory");
@@ -1115,10 +1117,18 @@ extern "C" int spiral_lconv_wgrad(const float *x, const float *dy, float *dw, fl
         return e1 == cudaSuccess ? SPIRAL_OK : spiral_cuda_error(e1, "spiral_lconv_wgrad");
     }
     const int npl = lc_prec_planes(n_planes);
-    lc2_tile(p, CinP, 1);
-    const size_t smem = (size_t)npl * ((size_t)p.n_in + (size_t)kLwPix * p.CoutPad) * 2 + (size_t)(p.KP / 8) * 4;
+    // items of 256 output pixels when there are enough of them to keep 148 persistent CTAs balanced (the per-item cost --
+    // two barriers, one staging round trip -- is what the large maps pay), else of 128
+    size_t smem = 0;
+    int n_items = 0;
+    for (int mtw = 2; mtw >= 1; mtw--) {
+        lc2_tile(p, CinP, mtw);
+        p.lw_ks = 8 * mtw;
+        smem = (size_t)npl * ((size_t)p.n_in + (size_t)p.lw_ks * 16 * p.CoutPad) * 2 + (size_t)(p.KP / 8) * 4;
+        n_items = ((B + p.fr - 1) / p.fr) * p.tiles_x * p.tiles_y;
+        if (mtw == 1 || (smem <= kLcSmemMax && n_items >= 148 * 8)) break;
+    }
     if (smem > kLcSmemMax) return spiral_set_error(SPIRAL_EUNSUPPORTED, "lconv_wgrad: tile does not fit shared memory (%zu bytes)", smem);
-    const int n_items = ((B + p.fr - 1) / p.fr) * p.tiles_x * p.tiles_y;
     const int grid = n_items < 148 ? n_items : 148;
     LC2_DISPATCH(lwgrad2_launch, p, x, dy, workspace, n_items, grid, smem, st);
     const int n = KH * KW * Cin * Cout;
