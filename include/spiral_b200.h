@@ -401,6 +401,15 @@ int spiral_lconv_forward(const float *x_dev, const void *w_planes_dev, int32_t n
                          int32_t B, int32_t Hin, int32_t Win, int32_t Cin, int32_t Hout, int32_t Wout, int32_t Cout,
                          int32_t KH, int32_t KW, int32_t stride, int32_t pad_t, int32_t pad_l, int32_t oH, int32_t oW,
                          int32_t o_sy, int32_t o_sx, int32_t o_oy, int32_t o_ox, int32_t relu, void *stream);
+/* The four parity classes (c = py * 2 + px) of a transposed convolution's forward (tf.layers.conv2d_transpose 4x4 / stride 2,
+ * policy.py:242-247, 275-281) or of a 4x4 / stride-2 convolution's input gradient in ONE launch: 2x2-tap / stride-1
+ * convolutions over the same input with per-class padding (0 or 1), kernel and output phase --
+ *   out[b, 2 oy + py, 2 ox + px, co] = bias[co] + sum x[b, oy - cls_pad_t[c] + ky, ox - cls_pad_l[c] + kx, ci] * packed_c[co][(ky*2 + kx)*Cin + ci]
+ * for oy < Hout, ox < Wout (pixels outside [oH, oW] skipped).  w_planes: the classes' spiral_lconv_pack outputs back to back. */
+int spiral_lconv_forward_classes(const float *x_dev, const void *w_planes_dev, int32_t n_planes, const float *bias_dev,
+                                 float *out_dev, int32_t B, int32_t Hin, int32_t Win, int32_t Cin, int32_t Hout, int32_t Wout,
+                                 int32_t Cout, const int32_t *cls_pad_t, const int32_t *cls_pad_l, int32_t oH, int32_t oW,
+                                 int32_t relu, void *stream);
 /* dw[(ky*KW + kx)*Cin + c][co] = sum_{b,oy,ox} x[b, oy*stride - pad_t + ky, ox*stride - pad_l + kx, c] * dy[b, oy, ox, co];
  * dy f32 [B,Hout,Wout,Cout], dw f32 [KH*KW*Cin, Cout]; workspace: spiral_lconv_wgrad_workspace_floats() floats. */
 int64_t spiral_lconv_wgrad_workspace_floats(int32_t Cin, int32_t Cout, int32_t n_taps);

@@ -116,6 +116,7 @@ SYMBOLS = {
     "spiral_lconv_pack": (C.c_int, [_vp, _vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int64, C.c_int64, C.c_int64, C.c_int64,
                                     C.POINTER(C.c_int32), C.POINTER(C.c_int32), _vp]),
     "spiral_lconv_forward": (C.c_int, [_vp, _vp, C.c_int32, _vp, _vp] + [C.c_int32] * 19 + [_vp]),
+    "spiral_lconv_forward_classes": (C.c_int, [_vp, _vp, C.c_int32, _vp, _vp] + [C.c_int32] * 7 + [_vp, _vp] + [C.c_int32] * 3 + [_vp]),
     "spiral_lconv_wgrad_workspace_floats": (C.c_int64, [C.c_int32] * 3),
     "spiral_lconv_wgrad": (C.c_int, [_vp] * 4 + [C.c_int32] * 13 + [_vp]),
     "spiral_conv_workspace_bytes": (C.c_int64, [C.c_int32] * 5),

@@ -45,6 +45,10 @@ struct LConvParams {
     int tw, th, fr, mt_rows;                     // tw = 16 or 8; mt_rows = 16 / tw rows per 16-pixel m-tile; th a power of two
     int th_log;
     int n_in;                                    // halfwords per plane of the staged input tile (multiple of 64)
+    // forward: n_cls > 1 = the four parity classes of a transposed / stride-2-adjoint convolution from ONE staged tile: class c
+    // reads taps shifted by (cls_dy, cls_dx) inside the tile (staged with the largest padding) and writes output pixel
+    // (oy * o_sy + cls_oy[c], ox * o_sx + cls_ox[c]); its kernel planes follow class c - 1's
+    int n_cls, cls_dy[4], cls_dx[4], cls_oy[4], cls_ox[4];
     int lw_ks;                                   // wgrad: k-steps (16 output pixels each) per item: 8 or 16
     uint32_t mIH, mIW, mTH, mTW;                 // lc_magic of IH, IW (input tile) and th, tw (wgrad's dy tile)
     int relu;                                    // forward epilogue: max(v, 0) after the bias (tf.nn.relu of the layer's activation)
@@ -393,14 +397,16 @@ template <int CIN>
 __device__ __forceinline__ void lc2_qoff_table(const LConvParams &p, int *s_qoff, int tid)
 {
     constexpr int CH = CIN / 8;
-    for (int q = tid; q < p.KP / 8; q += 256) {
+    const int nq = p.KP / 8;
+    for (int i = tid; i < nq * p.n_cls; i += 256) {
+        const int cls = i / nq, q = i - cls * nq;
         int off = 0;
         if (q * 8 < p.K) {
             const int tap = q / CH, c8 = q - tap * CH;
             const int ky = tap / p.KW, kx = tap - ky * p.KW;
-            off = (ky * p.IW + kx) * CH + c8;
+            off = ((ky + p.cls_dy[cls]) * p.IW + kx + p.cls_dx[cls]) * CH + c8;
         }
-        s_qoff[q] = off;
+        s_qoff[i] = off;
     }
 }
 
@@ -415,7 +421,7 @@ lconv2_kernel(const __grid_constant__ LConvParams p, const float *__restrict__ x
     const int n_w = p.CoutPad * p.KS;
     uint16_t *s_i = reinterpret_cast<uint16_t *>(sm_raw);                     // [NPL][n_in], swizzled
     uint16_t *s_w = s_i + (size_t)NPL * p.n_in;                                // [NPL][CoutPad][KS]
-    int *s_qoff = reinterpret_cast<int *>(s_w + (size_t)NPL * n_w);            // [KP / 8]
+    int *s_qoff = reinterpret_cast<int *>(s_w + (size_t)p.n_cls * NPL * n_w);  // [n_cls][KP / 8]
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int tiles = p.tiles_x * p.tiles_y;
@@ -424,7 +430,7 @@ lconv2_kernel(const __grid_constant__ LConvParams p, const float *__restrict__ x
     const int img0 = fg * p.fr;
     {
         const uint32_t sw = lc_smem_u32(s_w);
-        const int n16 = NPL * n_w / 8;
+        const int n16 = p.n_cls * NPL * n_w / 8;
         const uint4 *gw = reinterpret_cast<const uint4 *>(w_planes);
         for (int i = tid; i < n16; i += 256) lc_cp_async16(sw + (uint32_t)i * 16u, gw + i);
     }
@@ -458,7 +464,17 @@ lconv2_kernel(const __grid_constant__ LConvParams p, const float *__restrict__ x
     const uint32_t si_base = lc_smem_u32(s_i), sw_base = lc_smem_u32(s_w);
     const uint32_t in_plane = (uint32_t)p.n_in * 2u, w_plane = (uint32_t)n_w * 2u;
     const int NT = p.CoutPad >> 3;
+    const int g = lane >> 2, t = lane & 3;
+    const float lo_scale = F16 ? kF16LoInv : 1.0f;
+    const int out_ld = XF ? ex.out_ld : p.Cout, out_c0 = XF ? ex.out_c0 : 0;
+    float bs[4][2], bq[4][2];                                                  // XF: batch-norm partials of this thread's channels
+#pragma unroll
+    for (int nt = 0; nt < 4; nt++) { bs[nt][0] = bs[nt][1] = bq[nt][0] = bq[nt][1] = 0.0f; }
 
+#pragma unroll 1
+  for (int cls = 0; cls < p.n_cls; cls++) {
+    const uint32_t sw_cls = sw_base + (uint32_t)cls * NPL * w_plane;
+    const int *qoff_cls = s_qoff + cls * (p.KP / 8);
     float acc[MT][4][4], acl[MT][4][4];
 #pragma unroll
     for (int mt = 0; mt < MT; mt++)
@@ -469,7 +485,7 @@ lconv2_kernel(const __grid_constant__ LConvParams p, const float *__restrict__ x
 
 #pragma unroll 1
     for (int ks = 0; ks < p.KP / 16; ks++) {
-        const int qo = s_qoff[2 * ks + qsel];
+        const int qo = qoff_cls[2 * ks + qsel];
         uint32_t a[MT][NPL][4];
 #pragma unroll
         for (int mt = 0; mt < MT; mt++) {
@@ -483,7 +499,7 @@ lconv2_kernel(const __grid_constant__ LConvParams p, const float *__restrict__ x
 #pragma unroll
         for (int ntp = 0; ntp < 2; ntp++) {
             if (ntp * 2 < NT) {
-                const uint32_t ad = sw_base + ((uint32_t)(wrow[ntp] + ks * 16) << 1);
+                const uint32_t ad = sw_cls + ((uint32_t)(wrow[ntp] + ks * 16) << 1);
 #pragma unroll
                 for (int q = 0; q < NPL; q++) {
                     uint32_t t4[4];
@@ -500,12 +516,6 @@ lconv2_kernel(const __grid_constant__ LConvParams p, const float *__restrict__ x
                 if (nt < NT) lc_mma_planes2<NPL, F16>(acc[mt][nt], acl[mt][nt], a[mt], b[nt]);
     }
 
-    const int g = lane >> 2, t = lane & 3;
-    const float lo_scale = F16 ? kF16LoInv : 1.0f;
-    const int out_ld = XF ? ex.out_ld : p.Cout, out_c0 = XF ? ex.out_c0 : 0;
-    float bs[4][2], bq[4][2];                                                  // XF: batch-norm partials of this thread's channels
-#pragma unroll
-    for (int nt = 0; nt < 4; nt++) { bs[nt][0] = bs[nt][1] = bq[nt][0] = bq[nt][1] = 0.0f; }
 #pragma unroll
     for (int mt = 0; mt < MT; mt++) {
 #pragma unroll
@@ -515,7 +525,7 @@ lconv2_kernel(const __grid_constant__ LConvParams p, const float *__restrict__ x
             const int col = p.tw == 8 ? (i_m & 7) : i_m;
             const int f = rowg >> p.th_log, ry = rowg & (p.th - 1);
             const int img = img0 + f, oy = oy0 + ry, ox = ox0 + col;
-            const int py = oy * p.o_sy + p.o_oy, px = ox * p.o_sx + p.o_ox;
+            const int py = oy * p.o_sy + p.cls_oy[cls], px = ox * p.o_sx + p.cls_ox[cls];
             if (img >= p.B || oy >= p.Hout || ox >= p.Wout || py < 0 || py >= p.oH || px < 0 || px >= p.oW) continue;
             const size_t pix = ((size_t)img * p.oH + py) * p.oW + px;
 #pragma unroll
@@ -543,6 +553,7 @@ lconv2_kernel(const __grid_constant__ LConvParams p, const float *__restrict__ x
             }
         }
     }
+  }   // next class
     if constexpr (XF) {
         if (ex.bn_partial) {
             // per-CTA per-channel (sum, sum of squares) in a fixed order: lanes of a warp by shuffles, warps through shared memory
@@ -795,6 +806,8 @@ static void lc_fill(LConvParams &p, int B, int Hin, int Win, int Cin, int Hout, 
     p.oH = oH; p.oW = oW; p.o_sy = o_sy; p.o_sx = o_sx; p.o_oy = o_oy; p.o_ox = o_ox;
     p.tw = kLcTw; p.th = kLcTh; p.fr = 1; p.mt_rows = 1; p.th_log = 3; p.n_in = 0;
     p.dy_pitch = Cout; p.dy_c0 = 0; p.relu = 0; p.lw_ks = 8;
+    p.n_cls = 1;
+    for (int c = 0; c < 4; c++) { p.cls_dy[c] = 0; p.cls_dx[c] = 0; p.cls_oy[c] = o_oy; p.cls_ox[c] = o_ox; }
 }
 
 // tile of the v2 kernels: `rows` = output rows a CTA covers over all its frames (8 warps x m-tiles per warp x mt_rows)
@@ -809,7 +822,8 @@ static void lc2_tile(LConvParams &p, int Cin, int m_tiles_per_warp)
     p.th_log = 0;
     while ((1 << p.th_log) < th) p.th_log++;
     p.fr = rows / th;
-    p.IH = (p.th - 1) * p.stride + p.KH; p.IW = (p.tw - 1) * p.stride + p.KW;
+    const int ext = p.n_cls > 1 ? 1 : 0;                                      // classes shift their taps by 0 or 1
+    p.IH = (p.th - 1) * p.stride + p.KH + ext; p.IW = (p.tw - 1) * p.stride + p.KW + ext;
     p.tiles_x = (p.Wout + p.tw - 1) / p.tw; p.tiles_y = (p.Hout + p.th - 1) / p.th;
     p.n_in = (p.fr * p.IH * p.IW * Cin + 63) & ~63;
     p.mIH = lc_magic(p.IH); p.mIW = lc_magic(p.IW); p.mTH = lc_magic(p.th); p.mTW = lc_magic(p.tw);
@@ -985,6 +999,49 @@ extern "C" int spiral_lconv_forward(const float *x, const void *w_planes, int32_
     }
     const cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? SPIRAL_OK : spiral_cuda_error(e, "spiral_lconv_forward");
+}
+
+// The four parity classes (c = py * 2 + px) of a transposed convolution's forward, or of a stride-2 convolution's input
+// gradient, in ONE launch: 2x2-tap / stride-1 convolutions over the same input that differ in their padding (0 or 1 per
+// axis), their kernel and the output pixels they own --
+//   out[b, 2 oy + py, 2 ox + px, co] = bias[co] + sum_{ky,kx,ci} x[b, oy - pad_t[c] + ky, ox - pad_l[c] + kx, ci] * packed_c[co][(ky*2 + kx)*Cin + ci]
+// for oy < Hout, ox < Wout (pixels outside [oH, oW] are skipped).  The input tile is staged once (with padding 1) for all
+// four; w_planes holds the classes' packed kernels back to back (spiral_lconv_pack with the class's four taps).
+extern "C" int spiral_lconv_forward_classes(const float *x, const void *w_planes, int32_t n_planes, const float *bias, float *out,
+                                            int32_t B, int32_t Hin, int32_t Win, int32_t Cin, int32_t Hout, int32_t Wout,
+                                            int32_t Cout, const int32_t *cls_pad_t, const int32_t *cls_pad_l, int32_t oH,
+                                            int32_t oW, int32_t relu, void *stream)
+{
+    SPIRAL_REQUIRE(x); SPIRAL_REQUIRE(w_planes); SPIRAL_REQUIRE(out); SPIRAL_REQUIRE(cls_pad_t); SPIRAL_REQUIRE(cls_pad_l);
+    if (B <= 0 || Cout <= 0 || Cout > 32 || !lc_cin_ok(Cin) || !lc_prec_ok(n_planes))
+        return spiral_set_error(SPIRAL_EINVAL, "lconv classes: unsupported shape Cin=%d Cout=%d planes=%d", Cin, Cout, n_planes);
+    for (int c = 0; c < 4; c++)
+        if ((cls_pad_t[c] | cls_pad_l[c]) & ~1) return spiral_set_error(SPIRAL_EINVAL, "lconv classes: paddings must be 0 or 1");
+    const int CinP = lc_cin_pad(Cin);
+    LConvParams p;
+    lc_fill(p, B, Hin, Win, CinP, Hout, Wout, Cout, 2, 2, 1, 1, 1, oH, oW, 2, 2, 0, 0);
+    p.relu = relu ? 1 : 0;
+    p.n_cls = 4;
+    for (int c = 0; c < 4; c++) {
+        p.cls_dy[c] = 1 - cls_pad_t[c]; p.cls_dx[c] = 1 - cls_pad_l[c];
+        p.cls_oy[c] = c >> 1; p.cls_ox[c] = c & 1;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    const int npl = lc_prec_planes(n_planes);
+    const size_t n_w = (size_t)p.CoutPad * p.KS;
+    for (int mt = 2; mt >= 1; mt--) {
+        lc2_tile(p, CinP, mt);
+        const size_t smem = (size_t)npl * ((size_t)p.n_in + 4 * n_w) * 2 + (size_t)4 * (p.KP / 8) * 4;
+        if (smem > kLcSmemMax) {
+            if (mt == 1) return spiral_set_error(SPIRAL_EUNSUPPORTED, "lconv classes: tile does not fit shared memory (%zu bytes)", smem);
+            continue;
+        }
+        const int grid = ((B + p.fr - 1) / p.fr) * p.tiles_x * p.tiles_y;
+        LC2_DISPATCH(lconv2_launch_mt, mt, p, x, w_planes, bias, out, grid, smem, st);
+        break;
+    }
+    const cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? SPIRAL_OK : spiral_cuda_error(e, "spiral_lconv_forward_classes");
 }
 
 // A narrow layer of the discriminator (disc_dim 8 / 16 / 32; 5x5 / stride 2 / 'SAME' = pad 1 before, 2 after) on

@@ -77,6 +77,30 @@ def _wgrad(x, dy, kh, kw, stride, pad_t, pad_l):
     return dw
 
 
+def _pack_classes(w, rows, ck, class_taps, s_row, s_c, s_ky, s_kx):
+    """The four parity classes' kernels, packed back to back for spiral_lconv_forward_classes."""
+    n = int(N.lib().spiral_lconv_packed_elems(ck, rows, 4))
+    fmt = _fmt(ck)
+    per = (3 if fmt == 3 else 2) * n
+    planes = torch.empty((4 * per,), dtype=torch.int16, device=w.device)
+    for c, taps in enumerate(class_taps):
+        ky = (C.c_int32 * 4)(*[t[0] for t in taps])
+        kx = (C.c_int32 * 4)(*[t[1] for t in taps])
+        N.check(N.lib().spiral_lconv_pack(N.ptr(w), N.ptr(planes[c * per:(c + 1) * per]), fmt, rows, ck, 4, s_row, s_c, s_ky, s_kx,
+                                          ky, kx, N.stream_ptr()), "spiral_lconv_pack")
+    return planes
+
+
+def _launch_classes(x, packed, bias, out, cin, cout, hout, wout, pads_t, pads_l, relu=False):
+    B, hin, win, _ = x.shape
+    pt = (C.c_int32 * 4)(*pads_t)
+    pl_ = (C.c_int32 * 4)(*pads_l)
+    N.check(N.lib().spiral_lconv_forward_classes(N.ptr(x), N.ptr(packed), _fmt(cin), N.ptr(bias), N.ptr(out), B, hin, win, cin,
+                                                 hout, wout, cout, pt, pl_, out.shape[1], out.shape[2], int(relu),
+                                                 N.stream_ptr()), "spiral_lconv_forward_classes")
+    return out
+
+
 def _all_taps(kh, kw):
     return [(ky, kx) for ky in range(kh) for kx in range(kw)]
 
@@ -126,11 +150,9 @@ class _Conv2d(torch.autograd.Function):
                     dx[:, 2 * ho + 2:].zero_()
                 if Wd > 2 * wo + 2:
                     dx[:, :, 2 * wo + 2:].zero_()
-                for py in (0, 1):
-                    for px in (0, 1):
-                        taps = [(ky, kx) for ky in (py + 2, py) for kx in (px + 2, px)]
-                        packed = _pack(w, cin, cout, taps, kh * kw, cin * kh * kw, kw, 1)
-                        _launch(dy, packed, None, dx, cout, cin, ho + 1, wo + 1, 2, 2, 1, 1, 1, scatter=(2, 2, py, px))
+                class_taps = [[(ky, kx) for ky in (py + 2, py) for kx in (px + 2, px)] for py in (0, 1) for px in (0, 1)]
+                packed = _pack_classes(w, cin, cout, class_taps, kh * kw, cin * kh * kw, kw, 1)
+                _launch_classes(dy, packed, None, dx, cout, cin, ho + 1, wo + 1, (1, 1, 1, 1), (1, 1, 1, 1))
         if ctx.needs_input_grad[1]:
             g = _wgrad(x, dy, kh, kw, stride, pad, pad)                        # [(ky*kw + kx)*cin + ci][co]
             dw = g.view(kh, kw, cin, cout).permute(3, 2, 0, 1).contiguous()
@@ -152,14 +174,16 @@ class _ConvT2d(torch.autograd.Function):
         assert kh == 4 and kw == 4
         B, H, Wd, _ = x.shape
         out = torch.empty((B, 2 * H, 2 * Wd, cout), dtype=torch.float32, device=x.device)
+        class_taps, pads_t, pads_l = [], [], []
         for py in (0, 1):
             for px in (0, 1):
                 kys = (3, 1) if py == 0 else (2, 0)
                 kxs = (3, 1) if px == 0 else (2, 0)
-                taps = [(ky, kx) for ky in kys for kx in kxs]
-                packed = _pack(w, cout, cin, taps, kh * kw, cout * kh * kw, kw, 1)
-                _launch(x, packed, b, out, cin, cout, H, Wd, 2, 2, 1, 1 if py == 0 else 0, 1 if px == 0 else 0,
-                        scatter=(2, 2, py, px), relu=relu)
+                class_taps.append([(ky, kx) for ky in kys for kx in kxs])
+                pads_t.append(1 if py == 0 else 0)
+                pads_l.append(1 if px == 0 else 0)
+        packed = _pack_classes(w, cout, cin, class_taps, kh * kw, cout * kh * kw, kw, 1)
+        _launch_classes(x, packed, b, out, cin, cout, H, Wd, pads_t, pads_l, relu=relu)
         ctx.save_for_backward(x, w, out if relu else None)
         ctx.has_bias = b is not None
         return out

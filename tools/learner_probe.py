@@ -67,6 +67,9 @@ if os.environ.get("PROBE_BREAKDOWN"):
                        "conv  %2d->%2d %dx%d s%d in %dx%d" % (cin, cout, kh, kw, stride, x.shape[1], x.shape[2]))
     pl._wgrad = timed(pl._wgrad, lambda x, dy, kh, kw, stride, *r: "wgrad %2d->%2d %dx%d s%d in %dx%d" % (x.shape[3], dy.shape[3], kh, kw, stride, x.shape[1], x.shape[2]))
     pl._pack = timed(pl._pack, lambda *r, **k: "pack")
+    pl._pack_classes = timed(pl._pack_classes, lambda *r, **k: "pack (4 classes)")
+    pl._launch_classes = timed(pl._launch_classes, lambda x, packed, bias, out, cin, cout, hout, wout, *r, **k:
+                               "conv  %2d->%2d 4 parity classes of 2x2 taps, in %dx%d" % (cin, cout, x.shape[1], x.shape[2]))
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     ag.train_policy({k: v.clone() for k, v in ro.items()})
